@@ -1,0 +1,101 @@
+"""Host-side mirror of the reference block constructors on top of the C ABI.
+
+Names, argument order and meaning follow the reference's make() functions
+(include/dvbt/<block>.h) so parity tests read like tests of the reference blocks.
+Buffers are numpy arrays (host) or raw device pointers (ints) for the *_dev calls.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import capi
+from .capi import check, lib
+
+__all__ = ["viterbi_decoder", "QPSK", "QAM16", "QAM64", "NH", "C1_2", "C2_3", "C3_4", "C5_6", "C7_8", "T2k", "T8k", "G1_32"]
+
+QPSK, QAM16, QAM64 = 0, 1, 2
+NH = 0
+C1_2, C2_3, C3_4, C5_6, C7_8 = 0, 1, 2, 3, 4
+T2k, T8k = 0, 1
+G1_32 = 0
+
+
+def _addr(x):
+    if isinstance(x, np.ndarray):
+        assert x.flags["C_CONTIGUOUS"]
+        return x.ctypes.data
+    return int(x)
+
+
+class viterbi_decoder:
+    """dvbt.viterbi_decoder(constellation, hierarchy, coderate, bsize, S0, SK)
+    (include/dvbt/viterbi_decoder.h:51-52)."""
+
+    def __init__(self, constellation, hierarchy, coderate, bsize=768, S0=0, SK=-1):
+        self._h = C.c_void_p()
+        p = capi.ViterbiParams(constellation, hierarchy, coderate, bsize, S0, SK)
+        check(lib().dvbt_b200_viterbi_create(C.byref(p), C.byref(self._h)))
+        self.output_multiple = lib().dvbt_b200_viterbi_output_multiple(self._h)
+        self.ntraceback = lib().dvbt_b200_viterbi_ntraceback(self._h)
+        self.m = 2 * (constellation + 1)
+        self.k = [1, 2, 3, 5, 7][coderate]
+        self.n = self.k + 1
+
+    def close(self):
+        if getattr(self, "_h", None):
+            try:
+                lib().dvbt_b200_viterbi_destroy(self._h)
+            except Exception:  # interpreter shutdown
+                pass
+            self._h = None
+
+    __del__ = close
+
+    def set_tuning(self, chunk_bytes=0, warmup_bytes=0, threads_per_block=0):
+        t = capi.ViterbiTuning(chunk_bytes, warmup_bytes, threads_per_block)
+        check(lib().dvbt_b200_viterbi_set_tuning(self._h, C.byref(t)))
+
+    def reset(self):
+        check(lib().dvbt_b200_viterbi_reset(self._h))
+
+    def forecast(self, noutput_items):
+        return lib().dvbt_b200_viterbi_forecast(self._h, noutput_items)
+
+    def general_work(self, noutput_items, inp, tags=()):
+        """One scheduler call on host arrays.  tags: iterable of (offset, key_name, value) relative
+        to inp[0].  Returns (out array of the produced items, consumed, out_tags)."""
+        inp = np.ascontiguousarray(inp, np.uint8)
+        out = np.zeros(max(noutput_items, 1), np.uint8)
+        tin = (capi.Tag * max(1, len(tags)))()
+        for i, (off, key, val) in enumerate(tags):
+            tin[i] = capi.Tag(off, capi.TAG_KEYS[key], val)
+        tout = (capi.Tag * 4)()
+        ntout = C.c_size_t(0)
+        cons, prod = C.c_size_t(0), C.c_size_t(0)
+        check(lib().dvbt_b200_viterbi_work(self._h, inp.ctypes.data, inp.size, out.ctypes.data, noutput_items,
+                                           C.byref(cons), C.byref(prod), tin, len(tags), tout, 4, C.byref(ntout)))
+        otags = [(int(tout[i].offset), capi.TAG_NAMES[tout[i].key], int(tout[i].value)) for i in range(ntout.value)]
+        return out[: prod.value].copy(), int(cons.value), otags
+
+    def decode(self, inp, nstreams=1):
+        """Batch decode of nstreams equal-length streams (rows of inp), each from a reset (host arrays)."""
+        inp = np.ascontiguousarray(inp, np.uint8).reshape(nstreams, -1)
+        n_in = inp.shape[1]
+        nbt = n_in * self.m * self.k // (8 * self.n)
+        out = np.zeros((nstreams, max(nbt - self.ntraceback, 0)), np.uint8)
+        n_out = C.c_size_t(0)
+        check(lib().dvbt_b200_viterbi_decode_host(self._h, inp.ctypes.data, n_in, n_in, nstreams, out.ctypes.data,
+                                                  out.shape[1], C.byref(n_out)))
+        assert n_out.value == out.shape[1]
+        return out
+
+    def decode_dev(self, d_in, in_stride, n_in, nstreams, d_out, out_stride):
+        n_out = C.c_size_t(0)
+        check(lib().dvbt_b200_viterbi_decode_dev(self._h, _addr(d_in), in_stride, n_in, nstreams, _addr(d_out), out_stride,
+                                                 C.byref(n_out)))
+        return int(n_out.value)
+
+    def last_stats(self):
+        a, b, ms = C.c_longlong(0), C.c_longlong(0), C.c_float(0)
+        check(lib().dvbt_b200_viterbi_last_stats(self._h, C.byref(a), C.byref(b), C.byref(ms)))
+        return dict(chunks=int(a.value), repaired=int(b.value), acs_kernel_ms=float(ms.value))

@@ -1,0 +1,66 @@
+"""ctypes declarations for include/dvbt_b200.h."""
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libdvbt_b200.so")
+
+
+class DvbtError(RuntimeError):
+    def __init__(self, code, text):
+        super().__init__("libdvbt_b200: %s (code %d)" % (text, code))
+        self.code = code
+
+
+class Tag(C.Structure):
+    _fields_ = [("offset", C.c_uint64), ("key", C.c_int32), ("value", C.c_int64)]
+
+
+TAG_SYNC_START, TAG_SUPERFRAME_START, TAG_SYMBOL_INDEX = 1, 2, 3
+TAG_NAMES = {1: "sync_start", 2: "superframe_start", 3: "symbol_index"}
+TAG_KEYS = {v: k for k, v in TAG_NAMES.items()}
+
+
+class ViterbiParams(C.Structure):
+    _fields_ = [("constellation", C.c_int), ("hierarchy", C.c_int), ("code_rate", C.c_int),
+                ("bsize", C.c_int), ("S0", C.c_int), ("SK", C.c_int)]
+
+
+class ViterbiTuning(C.Structure):
+    _fields_ = [("chunk_bytes", C.c_int), ("warmup_bytes", C.c_int), ("threads_per_block", C.c_int)]
+
+
+_lib = None
+
+
+def lib():
+    """Loads libdvbt_b200.so; raises if it has not been built (no fallback of any kind)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError("gr_dvbt_b200/libdvbt_b200.so is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                              "(nvcc, sm_100a).  There is no CPU fallback.")
+        L = C.CDLL(LIB_PATH)
+        vp = C.c_void_p
+        L.dvbt_b200_last_error.restype = C.c_char_p
+        L.dvbt_b200_kernel_launches.restype = C.c_ulonglong
+        L.dvbt_b200_set_device.argtypes = [C.c_int]
+        L.dvbt_b200_viterbi_create.argtypes = [C.POINTER(ViterbiParams), C.POINTER(vp)]
+        L.dvbt_b200_viterbi_destroy.argtypes = [vp]
+        L.dvbt_b200_viterbi_set_tuning.argtypes = [vp, C.POINTER(ViterbiTuning)]
+        L.dvbt_b200_viterbi_reset.argtypes = [vp]
+        L.dvbt_b200_viterbi_forecast.argtypes = [vp, C.c_int]
+        L.dvbt_b200_viterbi_output_multiple.argtypes = [vp]
+        L.dvbt_b200_viterbi_ntraceback.argtypes = [vp]
+        L.dvbt_b200_viterbi_work.argtypes = [vp, vp, C.c_size_t, vp, C.c_size_t, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t),
+                                             C.POINTER(Tag), C.c_size_t, C.POINTER(Tag), C.c_size_t, C.POINTER(C.c_size_t)]
+        for name in ("dvbt_b200_viterbi_decode_host", "dvbt_b200_viterbi_decode_dev"):
+            getattr(L, name).argtypes = [vp, vp, C.c_size_t, C.c_size_t, C.c_int, vp, C.c_size_t, C.POINTER(C.c_size_t)]
+        L.dvbt_b200_viterbi_last_stats.argtypes = [vp, C.POINTER(C.c_longlong), C.POINTER(C.c_longlong), C.POINTER(C.c_float)]
+        _lib = L
+    return _lib
+
+
+def check(rc):
+    if rc != 0:
+        raise DvbtError(rc, lib().dvbt_b200_last_error().decode(errors="replace"))

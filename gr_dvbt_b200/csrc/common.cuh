@@ -1,0 +1,56 @@
+// Internal helpers shared by the CUDA translation units of libdvbt_b200.so.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/dvbt_b200.h"
+
+namespace dvbt {
+
+void set_error(const char *fmt, ...);
+void count_launch(unsigned n = 1);
+int ensure_device();  // 0 or a negative DVBT_B200_E* code (sets the error text)
+
+#define DVBT_CUDA_TRY(expr)                                                              \
+  do {                                                                                   \
+    cudaError_t err__ = (expr);                                                          \
+    if (err__ != cudaSuccess) {                                                          \
+      dvbt::set_error("%s failed at %s:%d: %s", #expr, __FILE__, __LINE__,               \
+                      cudaGetErrorString(err__));                                        \
+      return DVBT_B200_ECUDA;                                                            \
+    }                                                                                    \
+  } while (0)
+
+// A growable device (or pinned-host) buffer; never shrinks.
+struct DevBuf {
+  void *p = nullptr;
+  size_t cap = 0;
+  bool host = false;
+  int reserve(size_t bytes) {
+    if (bytes <= cap) return 0;
+    release();
+    size_t want = bytes + bytes / 8 + 256;
+    cudaError_t e = host ? cudaMallocHost(&p, want) : cudaMalloc(&p, want);
+    if (e != cudaSuccess) {
+      p = nullptr;
+      cap = 0;
+      set_error("%s of %zu bytes failed: %s", host ? "cudaMallocHost" : "cudaMalloc", want,
+                cudaGetErrorString(e));
+      return DVBT_B200_ENOMEM;
+    }
+    cap = want;
+    return 0;
+  }
+  void release() {
+    if (p) {
+      if (host) cudaFreeHost(p); else cudaFree(p);
+    }
+    p = nullptr;
+    cap = 0;
+  }
+  template <class T> T *as() const { return (T *)p; }
+};
+
+}  // namespace dvbt

@@ -1,0 +1,128 @@
+/* dvbt_b200.h — C ABI of libdvbt_b200.so, the B200 (sm_100a) receive hot path that sits
+ * behind gr-dvbt's GNU Radio block API.
+ *
+ * Every entry point below replaces one reference interface (cited as file:line relative to
+ * the BogdanDIA/gr-dvbt tree).  The gr::block shims in gr_dvbt_b200/shim/ and any other
+ * host (ctypes, a GR-free harness) call only these functions.  Conventions:
+ *   - plain pointers and sizes, no C++ or torch types; never throws across the ABI;
+ *   - return 0 on success, a negative DVBT_B200_E* code on failure;
+ *     dvbt_b200_last_error() returns a thread-local description of the last failure;
+ *   - "host" buffers are borrowed for the duration of the call (the library stages them
+ *     through pinned memory); "dev" entry points take CUDA device pointers on the current
+ *     device and enqueue on the handle's stream, then synchronise before returning unless
+ *     stated otherwise;
+ *   - a handle is not thread-safe; distinct handles are independent (the reference's
+ *     process-global Viterbi state, viterbi_decoder_impl.cc:49-52, is not reproduced);
+ *   - there is NO CPU fallback: without a CUDA device every create() fails with
+ *     DVBT_B200_ENODEV.
+ */
+#ifndef DVBT_B200_H
+#define DVBT_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DVBT_B200_OK 0
+#define DVBT_B200_EINVAL (-22)  /* bad argument */
+#define DVBT_B200_ENOMEM (-12)  /* host or device allocation failed */
+#define DVBT_B200_ENODEV (-19)  /* no usable CUDA device */
+#define DVBT_B200_ECUDA (-5)    /* a CUDA call or kernel failed */
+#define DVBT_B200_ENOSPC (-28)  /* output capacity too small */
+
+/* enums of include/dvbt/dvbt_config.h:34-76 (values are the TPS codes) */
+enum { DVBT_QPSK = 0, DVBT_QAM16 = 1, DVBT_QAM64 = 2 };
+enum { DVBT_NH = 0, DVBT_ALPHA1 = 1, DVBT_ALPHA2 = 2, DVBT_ALPHA4 = 3 };
+enum { DVBT_C1_2 = 0, DVBT_C2_3 = 1, DVBT_C3_4 = 2, DVBT_C5_6 = 3, DVBT_C7_8 = 4 };
+enum { DVBT_T2K = 0, DVBT_T8K = 1 };
+enum { DVBT_G1_32 = 0, DVBT_G1_16 = 1, DVBT_G1_8 = 2, DVBT_G1_4 = 3 };
+
+/* Stream tags (part of the block ABI).  offset is relative to the first item
+ * of the buffer handed to the call (the shim subtracts nitems_read / adds nitems_written). */
+enum { DVBT_TAG_SYNC_START = 1, DVBT_TAG_SUPERFRAME_START = 2, DVBT_TAG_SYMBOL_INDEX = 3 };
+typedef struct dvbt_b200_tag {
+  uint64_t offset;
+  int32_t key;   /* DVBT_TAG_* */
+  int64_t value; /* pmt::from_long payload */
+} dvbt_b200_tag;
+
+const char *dvbt_b200_last_error(void);
+/* number of CUDA devices visible (0 if none / no driver); selects nothing */
+int dvbt_b200_device_count(void);
+/* bind the calling thread (and handles created afterwards) to a device */
+int dvbt_b200_set_device(int device);
+/* how many kernels of this library have been launched by this process (bench evidence) */
+unsigned long long dvbt_b200_kernel_launches(void);
+
+/* ------------------------------------------------------------------------------------
+ * viterbi_decoder  — replaces gr::dvbt::viterbi_decoder
+ *   make():         include/dvbt/viterbi_decoder.h:51-52
+ *   forecast():     lib/viterbi_decoder_impl.cc:180-189
+ *   general_work(): lib/viterbi_decoder_impl.cc:191-324 (+ lib/d_viterbi.c:461-576,680-735)
+ * Input: one constellation symbol per byte, m hard bits in the low bits, MSB first.
+ * Output: decoded bytes, MSB first; out[i] is information byte i after a reset.
+ * ------------------------------------------------------------------------------------ */
+typedef struct dvbt_b200_viterbi dvbt_b200_viterbi;
+
+typedef struct dvbt_b200_viterbi_params { /* the make() arguments, in order */
+  int constellation; /* DVBT_QPSK / QAM16 / QAM64 */
+  int hierarchy;     /* DVBT_NH (hierarchical modes are parameterised but untested upstream) */
+  int code_rate;     /* DVBT_C1_2 .. DVBT_C7_8 */
+  int bsize;         /* 768 in every shipped flowgraph */
+  int S0, SK;        /* unused by the reference decoder (kept for signature parity) */
+} dvbt_b200_viterbi_params;
+
+/* Tunables of the chunk-parallel decoder (0 = library default).  They change speed only:
+ * every chunk boundary is verified against the sequential decoder state and repaired when
+ * it differs, so the output is bit-identical for any setting. */
+typedef struct dvbt_b200_viterbi_tuning {
+  int chunk_bytes; /* output bytes decoded by one GPU thread */
+  int warmup_bytes; /* byte times of warm-up before a chunk's first output */
+  int threads_per_block;
+} dvbt_b200_viterbi_tuning;
+
+int dvbt_b200_viterbi_create(const dvbt_b200_viterbi_params *p, dvbt_b200_viterbi **out);
+void dvbt_b200_viterbi_destroy(dvbt_b200_viterbi *h);
+int dvbt_b200_viterbi_set_tuning(dvbt_b200_viterbi *h, const dvbt_b200_viterbi_tuning *t);
+/* what a superframe_start tag does (viterbi_decoder_impl.cc:217-221) */
+int dvbt_b200_viterbi_reset(dvbt_b200_viterbi *h);
+/* forecast(): input items needed for noutput_items */
+int dvbt_b200_viterbi_forecast(const dvbt_b200_viterbi *h, int noutput_items);
+/* set_output_multiple() value, bsize*k/8, and ntraceback */
+int dvbt_b200_viterbi_output_multiple(const dvbt_b200_viterbi *h);
+int dvbt_b200_viterbi_ntraceback(const dvbt_b200_viterbi *h);
+
+/* One general_work() call on HOST buffers.  noutput_items must be a multiple of
+ * output_multiple; `in` must hold forecast(noutput_items) items.  Reproduces the tag
+ * behaviour: a superframe_start tag inside the window resets the decoder, and if it is not
+ * at the first item the call consumes up to it and produces nothing; the first producing
+ * call after a reset emits a superframe_start tag (value 1) at output offset 0 and
+ * produces noutput_items - ntraceback.  The decoder state is carried from call to call. */
+int dvbt_b200_viterbi_work(dvbt_b200_viterbi *h, const uint8_t *in, size_t n_in_items,
+                           uint8_t *out, size_t noutput_items, size_t *consumed,
+                           size_t *produced, const dvbt_b200_tag *tags_in, size_t n_tags_in,
+                           dvbt_b200_tag *tags_out, size_t tags_out_capacity, size_t *n_tags_out);
+
+/* Batch entry points: nstreams independent streams, each decoded from a reset.
+ * Stream s reads n_in bytes at in + s*in_stride and writes n_in*k*m/(8n) - ntraceback bytes
+ * at out + s*out_stride (*n_out receives that count).  n_in*m*k must be a multiple of 8n.
+ * _host: pageable or pinned host pointers (copies are inside the call).
+ * _dev:  device pointers; returns after the stream has been synchronised. */
+int dvbt_b200_viterbi_decode_host(dvbt_b200_viterbi *h, const uint8_t *in, size_t in_stride,
+                                  size_t n_in, int nstreams, uint8_t *out, size_t out_stride,
+                                  size_t *n_out);
+int dvbt_b200_viterbi_decode_dev(dvbt_b200_viterbi *h, const uint8_t *d_in, size_t in_stride,
+                                 size_t n_in, int nstreams, uint8_t *d_out, size_t out_stride,
+                                 size_t *n_out);
+/* statistics of the last decode: chunks launched, chunks whose warm-up state differed from
+ * the sequential state and were re-decoded, and device time of the ACS kernel in ms */
+int dvbt_b200_viterbi_last_stats(const dvbt_b200_viterbi *h, long long *chunks,
+                                 long long *repaired, float *acs_kernel_ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DVBT_B200_H */

@@ -1,0 +1,96 @@
+"""TEST INFRASTRUCTURE ONLY — ctypes binding of oracle/libdvbt_oracle.so (oracle/port/*.c)."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+SO = os.path.join(HERE, "libdvbt_oracle.so")
+
+RATE_KN = {0: (1, 2), 1: (2, 3), 2: (3, 4), 3: (5, 6), 4: (7, 8)}
+NTRACEBACK = {0: 5, 1: 9, 2: 10, 3: 15, 4: 24}
+
+_lib = None
+
+
+def build():
+    subprocess.check_call(["make", "-s", "-C", HERE, "port"])
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(SO):
+            build()
+        L = C.CDLL(SO)
+        L.dvbt_oracle_viterbi_create.restype = C.c_void_p
+        L.dvbt_oracle_viterbi_create.argtypes = [C.c_int, C.c_int, C.c_int]
+        L.dvbt_oracle_viterbi_destroy.argtypes = [C.c_void_p]
+        L.dvbt_oracle_viterbi_reset.argtypes = [C.c_void_p]
+        L.dvbt_oracle_viterbi_work.restype = C.c_long
+        L.dvbt_oracle_viterbi_work.argtypes = [C.c_void_p, C.c_void_p, C.c_long, C.c_void_p]
+        L.dvbt_oracle_viterbi_in_bytes_per_block.argtypes = [C.c_void_p]
+        L.dvbt_oracle_viterbi_out_bytes_per_block.argtypes = [C.c_void_p]
+        L.dvbt_oracle_viterbi_ntraceback.argtypes = [C.c_void_p]
+        L.dvbt_oracle_viterbi_metrics.argtypes = [C.c_void_p, C.c_void_p]
+        L.dvbt_oracle_conv_encode.restype = C.c_long
+        L.dvbt_oracle_conv_encode.argtypes = [C.c_void_p, C.c_long, C.c_int, C.c_int, C.c_void_p]
+        _lib = L
+    return _lib
+
+
+class Viterbi:
+    """Restated viterbi_decoder block (one instance = one decoder; no global state)."""
+
+    def __init__(self, m, rate, bsize=768):
+        self.L = lib()
+        self.h = self.L.dvbt_oracle_viterbi_create(m, rate, bsize)
+        if not self.h:
+            raise ValueError("bad viterbi parameters")
+        self.in_per_block = self.L.dvbt_oracle_viterbi_in_bytes_per_block(self.h)
+        self.out_per_block = self.L.dvbt_oracle_viterbi_out_bytes_per_block(self.h)
+        self.ntb = self.L.dvbt_oracle_viterbi_ntraceback(self.h)
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            self.L.dvbt_oracle_viterbi_destroy(self.h)
+            self.h = None
+
+    def reset(self):
+        self.L.dvbt_oracle_viterbi_reset(self.h)
+
+    def work(self, inp, nblocks=None):
+        inp = np.ascontiguousarray(inp, np.uint8).reshape(-1)
+        if nblocks is None:
+            nblocks = len(inp) // self.in_per_block
+        assert nblocks * self.in_per_block <= len(inp)
+        out = np.zeros(nblocks * self.out_per_block, np.uint8)
+        n = self.L.dvbt_oracle_viterbi_work(self.h, inp.ctypes.data, nblocks, out.ctypes.data)
+        return out[: max(n, 0)]
+
+    def metrics(self):
+        m = np.zeros(64, np.uint8)
+        self.L.dvbt_oracle_viterbi_metrics(self.h, m.ctypes.data)
+        return m
+
+
+def conv_encode(data, m, rate):
+    """K=7 encode + puncture + pack m bits per byte (the Viterbi block's input format)."""
+    data = np.ascontiguousarray(data, np.uint8).reshape(-1)
+    k, n = RATE_KN[rate]
+    nbits = len(data) * 8
+    assert nbits % k == 0 and (nbits * n // k) % m == 0
+    out = np.zeros(nbits * n // k // m, np.uint8)
+    r = lib().dvbt_oracle_conv_encode(data.ctypes.data, len(data), m, rate, out.ctypes.data)
+    assert r == len(out), (r, len(out))
+    return out
+
+
+def flip_bits(coded, m, ber, seed):
+    """Hard-decision channel: flip each of the m used bits of every byte with probability ber."""
+    rng = np.random.default_rng(seed)
+    coded = coded.copy()
+    for j in range(m):
+        coded ^= (rng.random(len(coded)) < ber).astype(np.uint8) << j
+    return coded

@@ -1,0 +1,50 @@
+/* TEST INFRASTRUCTURE ONLY — oracle/libdvbt_oracle.so
+ *
+ * Plain-C, single-thread restatement of the gr-dvbt receive hot path
+ * (BogdanDIA/gr-dvbt; every function cites the reference file:line it follows).
+ * It is the checker for the CUDA path: only tests/, __graft_entry__.smoke() and
+ * bench.py's cpu_baseline / --impl reference legs may load it.  The product
+ * (gr_dvbt_b200/) never links or calls it and has no CPU fallback.
+ *
+ * Pinning: the reference ships no golden vectors (all qa_* tests are empty
+ * templates).  Each restatement is pinned against the reference's
+ * own sources compiled verbatim (oracle/_ref, built by oracle/Makefile) in
+ * tests/test_oracle_vs_ref.py, and against fixtures generated from that build and
+ * committed under tests/golden/ (script: tests/golden/make_golden.py).
+ */
+#ifndef DVBT_ORACLE_H
+#define DVBT_ORACLE_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- Viterbi (viterbi_decoder_impl.cc + d_viterbi.c) ------------------------------ */
+typedef struct dvbt_oracle_viterbi dvbt_oracle_viterbi;
+/* m = bits per constellation symbol (2,4,6); rate = 0..4 for 1/2,2/3,3/4,5/6,7/8 */
+dvbt_oracle_viterbi *dvbt_oracle_viterbi_create(int m, int rate, int bsize);
+void dvbt_oracle_viterbi_destroy(dvbt_oracle_viterbi *);
+/* what a superframe_start tag does (viterbi_decoder_impl.cc:217-221) */
+void dvbt_oracle_viterbi_reset(dvbt_oracle_viterbi *);
+/* one general_work() body without the tag search: decodes nblocks blocks of
+ * bsize*n/m input bytes, writes the output bytes and returns how many are valid
+ * (nblocks*bsize*k/8, minus ntraceback on the first call after a reset). */
+long dvbt_oracle_viterbi_work(dvbt_oracle_viterbi *, const uint8_t *in, long nblocks, uint8_t *out);
+int dvbt_oracle_viterbi_in_bytes_per_block(const dvbt_oracle_viterbi *);
+int dvbt_oracle_viterbi_out_bytes_per_block(const dvbt_oracle_viterbi *);
+int dvbt_oracle_viterbi_ntraceback(const dvbt_oracle_viterbi *);
+/* the 64 path metrics as the reference holds them right now (after the last
+ * get_output's min subtraction), for boundary-state tests */
+void dvbt_oracle_viterbi_metrics(const dvbt_oracle_viterbi *, uint8_t metrics[64]);
+/* K=7 encoder + DVB-T puncturing + packing of m bits per byte, MSB first:
+ * d_viterbi.c:106-124 (d_encode) with the puncture order of
+ * viterbi_decoder_impl.cc:61-65.  nbytes*8 must be a multiple of k, and
+ * nbytes*8*n/k a multiple of m.  Returns the number of output bytes. */
+long dvbt_oracle_conv_encode(const uint8_t *data, long nbytes, int m, int rate, uint8_t *out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

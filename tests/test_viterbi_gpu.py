@@ -1,0 +1,135 @@
+"""GPU parity: CUDA viterbi_decoder (through the C ABI) vs the oracle restatement of
+viterbi_decoder_impl.cc / d_viterbi.c.  Bit-exact is the bar (integer path)."""
+import numpy as np
+import pytest
+
+from oracle import port as O
+
+pytestmark = pytest.mark.gpu
+
+CON = {2: 0, 4: 1, 6: 2}
+
+
+def make_case(rate, m, nblocks, ber, seed):
+    k, n = O.RATE_KN[rate]
+    data = np.random.default_rng(seed).integers(0, 256, nblocks * 96 * k, dtype=np.uint8)
+    rx = O.conv_encode(data, m, rate)
+    if ber > 0:
+        rx = O.flip_bits(rx, m, ber, seed + 1)
+    return data, rx
+
+
+@pytest.mark.parametrize("rate", [0, 1, 2, 3, 4])
+@pytest.mark.parametrize("m", [2, 4, 6])
+@pytest.mark.parametrize("ber", [0.0, 0.01])
+def test_batch_matches_oracle(rate, m, ber):
+    import gr_dvbt_b200 as g
+    data, rx = make_case(rate, m, 12, ber, 100 * rate + m)
+    ref = O.Viterbi(m, rate).work(rx)
+    dec = g.viterbi_decoder(CON[m], g.NH, rate)
+    out = dec.decode(rx)[0]
+    assert np.array_equal(out, ref)
+    if ber == 0.0:
+        assert np.array_equal(out, data[: len(out)])
+    # small chunks: many chunk boundaries inside the stream
+    dec.set_tuning(chunk_bytes=64, warmup_bytes=40, threads_per_block=64)
+    out2 = dec.decode(rx)[0]
+    assert np.array_equal(out2, ref)
+    assert dec.last_stats()["chunks"] > 8
+
+
+@pytest.mark.parametrize("rate,m,ber", [(0, 4, 0.04), (4, 6, 0.006), (2, 2, 0.03), (3, 4, 0.01)])
+def test_repair_path_is_exact(rate, m, ber):
+    """warm-up of 1 byte time cannot converge: boundaries mismatch and are repaired sequentially."""
+    import gr_dvbt_b200 as g
+    data, rx = make_case(rate, m, 10, ber, 7)
+    ref = O.Viterbi(m, rate).work(rx)
+    dec = g.viterbi_decoder(CON[m], g.NH, rate)
+    dec.set_tuning(chunk_bytes=96, warmup_bytes=1, threads_per_block=32)
+    out = dec.decode(rx)[0]
+    st = dec.last_stats()
+    assert np.array_equal(out, ref)
+    assert st["repaired"] > 0, st
+
+
+def test_multi_stream_batch():
+    import gr_dvbt_b200 as g
+    rate, m = 4, 6
+    cases = [make_case(rate, m, 4, 0.004 if s % 2 else 0.0, 50 + s) for s in range(37)]
+    rx = np.stack([c[1] for c in cases])
+    dec = g.viterbi_decoder(CON[m], g.NH, rate)
+    out = dec.decode(rx, nstreams=len(cases))
+    for s, (data, r) in enumerate(cases):
+        assert np.array_equal(out[s], O.Viterbi(m, rate).work(r)), s
+
+
+@pytest.mark.parametrize("rate,m", [(0, 4), (4, 6), (2, 2)])
+def test_streaming_general_work_with_tags(rate, m):
+    """general_work() call by call: carried state, superframe_start reset mid-stream, consume-to-tag."""
+    import gr_dvbt_b200 as g
+    k, n = O.RATE_KN[rate]
+    dec = g.viterbi_decoder(CON[m], g.NH, rate)
+    om = dec.output_multiple
+    per_block_in = 768 * n // m
+    _, rx1 = make_case(rate, m, 9, 0.01, 1)
+    _, rx2 = make_case(rate, m, 7, 0.01, 2)
+    junk = np.random.default_rng(3).integers(0, 1 << m, 123, dtype=np.uint8)
+    stream = np.concatenate([rx1, junk, rx2])
+    tag_pos = len(rx1) + len(junk)
+    # oracle: decode rx1 from reset; then the tag resets and rx2 is decoded from reset
+    o = O.Viterbi(m, rate)
+    ref1 = o.work(rx1)
+    o.reset()
+    ref2 = o.work(rx2)
+    got = []
+    otags = []
+    nread = 0
+    produced_total = 0
+    sizes = [1, 3, 2, 5, 1, 4, 2, 6, 3, 2, 1, 1]
+    i = 0
+    while True:
+        nb = sizes[i % len(sizes)]
+        i += 1
+        avail = len(stream) - nread
+        nb = min(nb, avail // per_block_in)
+        if nb < 1:
+            break
+        window = nb * per_block_in
+        tags = [(tag_pos - nread, "superframe_start", 0xAA)] if nread <= tag_pos < nread + window else []
+        out, cons, ot = dec.general_work(nb * om, stream[nread: nread + dec.forecast(nb * om)], tags)
+        for t in ot:
+            otags.append((produced_total + t[0], t[1], t[2]))
+        got.append(out)
+        produced_total += len(out)
+        nread += cons
+        if cons == 0 and len(out) == 0:
+            break
+    got = np.concatenate(got)
+    # what the reference scheduler would have produced: ref1 truncated at the last whole call
+    # before the tag, then ref2
+    n1 = len(got) - len(ref2)
+    assert n1 > 0 and np.array_equal(got[:n1], ref1[:n1])
+    assert np.array_equal(got[n1:], ref2)
+    assert otags[0] == (0, "superframe_start", 1)
+    assert otags[1] == (n1, "superframe_start", 1)
+
+
+def test_large_stream_round_trip_and_chunk_invariance():
+    """Full-size property test (config 5 scale is covered by bench.py): clean channel decodes to
+    the transmitted bytes; two different chunkings give identical bytes on a noisy channel."""
+    import gr_dvbt_b200 as g
+    rate, m = 4, 6
+    k, n = O.RATE_KN[rate]
+    data = np.random.default_rng(11).integers(0, 256, 2000 * 96 * k, dtype=np.uint8)
+    rx = O.conv_encode(data, m, rate)
+    dec = g.viterbi_decoder(CON[m], g.NH, rate)
+    out = dec.decode(rx)[0]
+    assert np.array_equal(out, data[: len(out)])
+    assert dec.last_stats()["repaired"] == 0
+    noisy = O.flip_bits(rx, m, 0.005, 5)
+    a = dec.decode(noisy)[0]
+    dec.set_tuning(chunk_bytes=333, warmup_bytes=64, threads_per_block=96)
+    b = dec.decode(noisy)[0]
+    assert np.array_equal(a, b)
+    ref = O.Viterbi(m, rate).work(noisy[: 40 * 768 * n // m])
+    assert np.array_equal(a[: len(ref)], ref)
