@@ -11,7 +11,7 @@ import numpy as np
 from . import capi
 from .capi import check, lib
 
-__all__ = ["viterbi_decoder", "QPSK", "QAM16", "QAM64", "NH", "C1_2", "C2_3", "C3_4", "C5_6", "C7_8", "T2k", "T8k", "G1_32"]
+__all__ = ["viterbi_decoder", "reed_solomon_dec", "dvbt_demap", "QPSK", "QAM16", "QAM64", "NH", "C1_2", "C2_3", "C3_4", "C5_6", "C7_8", "T2k", "T8k", "G1_32"]
 
 QPSK, QAM16, QAM64 = 0, 1, 2
 NH = 0
@@ -99,3 +99,71 @@ class viterbi_decoder:
         a, b, ms = C.c_longlong(0), C.c_longlong(0), C.c_float(0)
         check(lib().dvbt_b200_viterbi_last_stats(self._h, C.byref(a), C.byref(b), C.byref(ms)))
         return dict(chunks=int(a.value), repaired=int(b.value), acs_kernel_ms=float(ms.value))
+
+
+class _Handle:
+    _destroy = None
+
+    def close(self):
+        if getattr(self, "_h", None):
+            try:
+                getattr(lib(), self._destroy)(self._h)
+            except Exception:  # interpreter shutdown
+                pass
+            self._h = None
+
+    __del__ = close
+
+
+class reed_solomon_dec(_Handle):
+    """dvbt.reed_solomon_dec(p, m, gfpoly, n, k, t, s, blocks) (include/dvbt/reed_solomon_dec.h:49)."""
+    _destroy = "dvbt_b200_rsdec_destroy"
+
+    def __init__(self, p=2, m=8, gfpoly=0x11D, n=255, k=239, t=8, s=51, blocks=8):
+        self._h = C.c_void_p()
+        par = capi.RsdecParams(p, m, gfpoly, n, k, t, s, blocks)
+        check(lib().dvbt_b200_rsdec_create(C.byref(par), C.byref(self._h)))
+        self.blocks = blocks
+
+    def set_compat(self, as_built):
+        check(lib().dvbt_b200_rsdec_set_compat(self._h, int(as_built)))
+
+    def general_work(self, noutput_items, inp):
+        inp = np.ascontiguousarray(inp, np.uint8)
+        out = np.zeros(noutput_items * self.blocks * 188, np.uint8)
+        cons, prod = C.c_size_t(0), C.c_size_t(0)
+        check(lib().dvbt_b200_rsdec_work(self._h, inp.ctypes.data, inp.size // (self.blocks * 204), out.ctypes.data, noutput_items,
+                                         C.byref(cons), C.byref(prod)))
+        return out[: prod.value * self.blocks * 188], int(cons.value)
+
+    def decode_dev(self, d_in, npackets, d_out, d_status=None):
+        check(lib().dvbt_b200_rsdec_decode_dev(self._h, _addr(d_in), npackets, _addr(d_out), _addr(d_status) if d_status is not None else None))
+
+
+class dvbt_demap(_Handle):
+    """dvbt.dvbt_demap(nsize, constellation, hierarchy, transmission, gain) (include/dvbt/dvbt_demap.h:50)."""
+    _destroy = "dvbt_b200_demap_destroy"
+
+    def __init__(self, nsize, constellation, hierarchy, transmission, gain=1.0):
+        self._h = C.c_void_p()
+        par = capi.DemapParams(nsize, constellation, hierarchy, transmission, gain)
+        check(lib().dvbt_b200_demap_create(C.byref(par), C.byref(self._h)))
+        self.nsize = nsize
+
+    def points(self):
+        buf = np.zeros(128, np.float32)
+        n = lib().dvbt_b200_demap_points(self._h, buf.ctypes.data, 64)
+        if n < 0:
+            check(n)
+        return buf[: 2 * n].view(np.complex64).copy()
+
+    def general_work(self, noutput_items, inp):
+        inp = np.ascontiguousarray(inp, np.complex64)
+        out = np.zeros(noutput_items * self.nsize, np.uint8)
+        cons, prod = C.c_size_t(0), C.c_size_t(0)
+        check(lib().dvbt_b200_demap_work(self._h, inp.ctypes.data, inp.size // self.nsize, out.ctypes.data, noutput_items,
+                                         C.byref(cons), C.byref(prod)))
+        return out[: prod.value * self.nsize], int(cons.value)
+
+    def run_dev(self, d_in, ncells, d_out):
+        check(lib().dvbt_b200_demap_run_dev(self._h, _addr(d_in), ncells, _addr(d_out)))

@@ -26,6 +26,14 @@ class ViterbiParams(C.Structure):
                 ("bsize", C.c_int), ("S0", C.c_int), ("SK", C.c_int)]
 
 
+class RsdecParams(C.Structure):
+    _fields_ = [(n, C.c_int) for n in ("p", "m", "gfpoly", "n", "k", "t", "s", "blocks")]
+
+
+class DemapParams(C.Structure):
+    _fields_ = [("nsize", C.c_int), ("constellation", C.c_int), ("hierarchy", C.c_int), ("transmission", C.c_int), ("gain", C.c_float)]
+
+
 class ViterbiTuning(C.Structure):
     _fields_ = [("chunk_bytes", C.c_int), ("warmup_bytes", C.c_int), ("threads_per_block", C.c_int)]
 
@@ -57,6 +65,16 @@ def lib():
         for name in ("dvbt_b200_viterbi_decode_host", "dvbt_b200_viterbi_decode_dev"):
             getattr(L, name).argtypes = [vp, vp, C.c_size_t, C.c_size_t, C.c_int, vp, C.c_size_t, C.POINTER(C.c_size_t)]
         L.dvbt_b200_viterbi_last_stats.argtypes = [vp, C.POINTER(C.c_longlong), C.POINTER(C.c_longlong), C.POINTER(C.c_float)]
+        L.dvbt_b200_rsdec_create.argtypes = [C.POINTER(RsdecParams), C.POINTER(vp)]
+        L.dvbt_b200_rsdec_destroy.argtypes = [vp]
+        L.dvbt_b200_rsdec_set_compat.argtypes = [vp, C.c_int]
+        L.dvbt_b200_rsdec_work.argtypes = [vp, vp, C.c_size_t, vp, C.c_size_t, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]
+        L.dvbt_b200_rsdec_decode_dev.argtypes = [vp, vp, C.c_size_t, vp, vp]
+        L.dvbt_b200_demap_create.argtypes = [C.POINTER(DemapParams), C.POINTER(vp)]
+        L.dvbt_b200_demap_destroy.argtypes = [vp]
+        L.dvbt_b200_demap_points.argtypes = [vp, vp, C.c_int]
+        L.dvbt_b200_demap_work.argtypes = [vp, vp, C.c_size_t, vp, C.c_size_t, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]
+        L.dvbt_b200_demap_run_dev.argtypes = [vp, vp, C.c_size_t, vp]
         _lib = L
     return _lib
 

@@ -1,0 +1,175 @@
+// dvbt_demap — hard-decision constellation demapper.
+//
+// Replaces gr::dvbt::dvbt_demap (lib/dvbt_demap_impl.cc:217-240 general_work,
+// :167-203 find_constellation_value, :117-165 make_constellation_points).  The decision is
+// the reference's: the first index with the strictly smallest squared distance, distances
+// computed as VOLK's generic 32fc_x2_square_dist_32f does (complex subtract, re*re + im*im,
+// every float operation rounded on its own: __fsub_rn/__fmul_rn/__fadd_rn forbid FMA
+// contraction), scanned from index 0 upwards.  One thread per cell; the 4/16/64 points sit in
+// the kernel parameter block (constant bank, read uniformly by the warp).  HBM bound:
+// 8 B in + 1 B out per cell.
+#include "common.cuh"
+
+#include <math.h>
+#include <new>
+
+namespace dvbt {
+
+struct DemapTable {
+  float2 pts[64];
+  int size;
+};
+
+static int gray(int v) { return (v >> 1) ^ v; }
+
+// dvbt_demap_impl.cc:117-165 with the normalisation of dvbt_config.cc:229-249
+int make_demap_table(int constellation, int hierarchy, float gain, DemapTable *t) {
+  if (constellation < DVBT_QPSK || constellation > DVBT_QAM64) return DVBT_B200_EINVAL;
+  int alpha = hierarchy == DVBT_ALPHA2 ? 2 : hierarchy == DVBT_ALPHA4 ? 4 : 1;
+  int m = 2 * (constellation + 1);
+  int size = 1 << m;
+  const int step = 2;
+  float norm;
+  if (m == 2) norm = (float)(1.0 / sqrt(2));
+  else if (m == 4) norm = (float)(alpha == 1 ? 1.0 / sqrt(10) : alpha == 2 ? 1.0 / sqrt(20) : 1.0 / sqrt(52));
+  else norm = (float)(alpha == 1 ? 1.0 / sqrt(42) : alpha == 2 ? 1.0 / sqrt(60) : 1.0 / sqrt(108));
+  float g = gain * norm;
+  int bpa = m / 2, spa = (1 << bpa) / 2 - 1;
+  for (int i = 0; i < size; i++) {
+    int q = (i >> (2 * (bpa - 1))) & 3;
+    int sign0 = (q >> 1) ? -1 : 1, sign1 = (q & 1) ? -1 : 1;
+    int x = (i >> (bpa - 1)) & ((1 << (bpa - 1)) - 1), y = i & ((1 << (bpa - 1)) - 1);
+    int xval = alpha + (spa - x) * step, yval = alpha + (spa - y) * step;
+    int val = (gray(x) << (bpa - 1)) + gray(y);
+    x = 0; y = 0;
+    for (int j = 0; j < bpa - 1; j++) {
+      x += ((val >> (1 + 2 * j)) & 1) << j;
+      y += ((val >> (2 * j)) & 1) << j;
+    }
+    val = (q << (2 * (bpa - 1))) + (x << (bpa - 1)) + y;
+    t->pts[val] = make_float2(g * (float)(sign0 * xval), g * (float)(sign1 * yval));
+  }
+  t->size = size;
+  return 0;
+}
+
+// shared with the fused equalise+demap kernel
+__device__ __forceinline__ uint8_t demap_cell(const DemapTable &t, float2 v) {
+  float dr = __fsub_rn(v.x, t.pts[0].x), di = __fsub_rn(v.y, t.pts[0].y);
+  float min_dist = __fadd_rn(__fmul_rn(dr, dr), __fmul_rn(di, di));
+  int min_index = 0;
+#pragma unroll 8
+  for (int i = 1; i < t.size; i++) {  // i = 0 can never be strictly smaller than itself
+    dr = __fsub_rn(v.x, t.pts[i].x);
+    di = __fsub_rn(v.y, t.pts[i].y);
+    float d = __fadd_rn(__fmul_rn(dr, dr), __fmul_rn(di, di));
+    if (d < min_dist) { min_dist = d; min_index = i; }
+  }
+  return (uint8_t)min_index;
+}
+
+__global__ void __launch_bounds__(256) demap_kernel(const float2 *__restrict__ in, uint8_t *__restrict__ out, long long n,
+                                                    const __grid_constant__ DemapTable t) {
+  long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (i + 3 < n) {
+    const float4 *p = reinterpret_cast<const float4 *>(in + i);
+    float4 a = p[0], b = p[1];
+    uchar4 r;
+    r.x = demap_cell(t, make_float2(a.x, a.y));
+    r.y = demap_cell(t, make_float2(a.z, a.w));
+    r.z = demap_cell(t, make_float2(b.x, b.y));
+    r.w = demap_cell(t, make_float2(b.z, b.w));
+    *reinterpret_cast<uchar4 *>(out + i) = r;
+  } else {
+    for (; i < n; i++) out[i] = demap_cell(t, in[i]);
+  }
+}
+
+int demap_launch(const DemapTable &t, const float2 *d_in, uint8_t *d_out, long long ncells, cudaStream_t st) {
+  if (ncells <= 0) return 0;
+  long long threads = (ncells + 3) / 4;
+  unsigned grid = (unsigned)((threads + 255) / 256);
+  demap_kernel<<<grid, 256, 0, st>>>(d_in, d_out, ncells, t);
+  count_launch();
+  DVBT_CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace dvbt
+
+struct dvbt_b200_demap {
+  dvbt_b200_demap_params par;
+  dvbt::DemapTable table;
+  cudaStream_t stream = nullptr;
+  dvbt::DevBuf d_in, d_out;
+};
+
+extern "C" {
+
+int dvbt_b200_demap_create(const dvbt_b200_demap_params *p, dvbt_b200_demap **out) {
+  if (!p || !out) { dvbt::set_error("demap_create: null argument"); return DVBT_B200_EINVAL; }
+  *out = nullptr;
+  if (p->nsize <= 0) { dvbt::set_error("demap_create: nsize must be positive"); return DVBT_B200_EINVAL; }
+  dvbt::DemapTable t;
+  if (dvbt::make_demap_table(p->constellation, p->hierarchy, p->gain, &t)) {
+    dvbt::set_error("demap_create: bad constellation %d", p->constellation);
+    return DVBT_B200_EINVAL;
+  }
+  int rc = dvbt::ensure_device();
+  if (rc) return rc;
+  dvbt_b200_demap *h = new (std::nothrow) dvbt_b200_demap();
+  if (!h) { dvbt::set_error("demap_create: out of memory"); return DVBT_B200_ENOMEM; }
+  h->par = *p;
+  h->table = t;
+  if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) {
+    dvbt::set_error("demap_create: cannot create stream");
+    delete h;
+    return DVBT_B200_ECUDA;
+  }
+  *out = h;
+  return 0;
+}
+
+void dvbt_b200_demap_destroy(dvbt_b200_demap *h) {
+  if (!h) return;
+  if (h->stream) { cudaStreamSynchronize(h->stream); cudaStreamDestroy(h->stream); }
+  h->d_in.release();
+  h->d_out.release();
+  delete h;
+}
+
+int dvbt_b200_demap_points(const dvbt_b200_demap *h, float *re_im, int capacity_points) {
+  if (!h || !re_im || capacity_points < h->table.size) { dvbt::set_error("demap_points: bad argument"); return DVBT_B200_EINVAL; }
+  for (int i = 0; i < h->table.size; i++) { re_im[2 * i] = h->table.pts[i].x; re_im[2 * i + 1] = h->table.pts[i].y; }
+  return h->table.size;
+}
+
+int dvbt_b200_demap_run_dev(dvbt_b200_demap *h, const void *d_in, size_t ncells, uint8_t *d_out) {
+  if (!h || (ncells && (!d_in || !d_out))) { dvbt::set_error("demap_run_dev: bad argument"); return DVBT_B200_EINVAL; }
+  int rc = dvbt::demap_launch(h->table, (const float2 *)d_in, d_out, (long long)ncells, h->stream);
+  if (rc) return rc;
+  DVBT_CUDA_TRY(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+int dvbt_b200_demap_work(dvbt_b200_demap *h, const void *in, size_t n_in_items, uint8_t *out, size_t noutput_items,
+                         size_t *consumed, size_t *produced) {
+  if (!h || !consumed || !produced) { dvbt::set_error("demap_work: null argument"); return DVBT_B200_EINVAL; }
+  *consumed = *produced = 0;
+  if (n_in_items < noutput_items) { dvbt::set_error("demap_work: %zu input items for %zu output items", n_in_items, noutput_items); return DVBT_B200_EINVAL; }
+  if (noutput_items == 0) return 0;
+  if (!in || !out) { dvbt::set_error("demap_work: null buffer"); return DVBT_B200_EINVAL; }
+  size_t ncells = noutput_items * (size_t)h->par.nsize;
+  int rc;
+  if ((rc = h->d_in.reserve(ncells * 8))) return rc;
+  if ((rc = h->d_out.reserve(ncells))) return rc;
+  DVBT_CUDA_TRY(cudaMemcpyAsync(h->d_in.p, in, ncells * 8, cudaMemcpyHostToDevice, h->stream));
+  rc = dvbt::demap_launch(h->table, h->d_in.as<float2>(), h->d_out.as<uint8_t>(), (long long)ncells, h->stream);
+  if (rc) return rc;
+  DVBT_CUDA_TRY(cudaMemcpyAsync(out, h->d_out.p, ncells, cudaMemcpyDeviceToHost, h->stream));
+  DVBT_CUDA_TRY(cudaStreamSynchronize(h->stream));
+  *consumed = *produced = noutput_items;  // 1:1 (dvbt_demap_impl.cc:211-215, :236-239)
+  return 0;
+}
+
+}  // extern "C"

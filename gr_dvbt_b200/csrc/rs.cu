@@ -1,0 +1,311 @@
+// K5 — RS(204,188) decoder, one warp per transport packet, GF(2^8) poly 0x11d.
+//
+// Replaces gr::dvbt::reed_solomon_dec (lib/reed_solomon_dec_impl.cc:77-116) and
+// reed_solomon::rs_decode (lib/reed_solomon.cc:246-489).  The algebra is the reference's:
+// syndromes S_i = r(a^i), i = 0..15 (:281-288; the 51 zero symbols of the shortened code
+// contribute nothing, so only the 204 received bytes are read), the reference's
+// Berlekamp-Massey iteration (:315-354), Chien search in increasing position order
+// (:376-403), error evaluator and Forney values (:419-486) including the "uncorrectable:
+// leave the packet alone" and "null denominator: keep what was already corrected" exits.
+//
+// Mapping: the 32 lanes split the 204 bytes (7 per lane); each lane accumulates its 16
+// partial syndromes from log/exp tables in shared memory; a butterfly of warp shuffles
+// XOR-reduces them (16 syndromes packed in 4 registers).  Clean packets — the common case —
+// are then copied out by the same warp.  Packets with errors run the locator iteration on
+// lane 0, the Chien search on all lanes (8 positions per lane, ballots keep the order) and
+// Forney on lane 0.
+#include "common.cuh"
+
+#include <new>
+
+namespace {
+
+constexpr int kN = 255, kT = 8, kS = 51, kPktIn = 204, kPktOut = 188;
+
+__constant__ uint8_t c_exp2[512];
+__constant__ uint8_t c_log[256];
+bool g_tables_ready[64] = {false};
+
+struct GfTables {
+  const uint8_t *exp2;  // exp2[i] = a^(i mod 255), 0 <= i < 512
+  const uint8_t *log;   // log[0] = 255
+  __device__ __forceinline__ int mul(int a, int b) const { return (a && b) ? exp2[log[a] + log[b]] : 0; }
+  __device__ __forceinline__ int div(int a, int b) const { return (a && b) ? exp2[255 + log[a] - log[b]] : 0; }
+  // a * alpha^p for any p >= 0 (gf_pow, reed_solomon.cc:136-143)
+  __device__ __forceinline__ int mulpow(int a, int p) const { return a ? exp2[(log[a] + p) % 255] : 0; }
+};
+
+// Berlekamp-Massey exactly as reed_solomon.cc:307-364 (no erasures).  Returns deg(sigma).
+__device__ int rs_locator(const GfTables &gf, const uint8_t *syn, uint8_t *sigma) {
+  uint8_t b[2 * kT + 1], T[2 * kT + 1];
+  for (int i = 0; i <= 2 * kT; i++) { sigma[i] = 0; }
+  sigma[0] = 1;
+  for (int i = 0; i <= 2 * kT; i++) b[i] = sigma[i];
+  int r = 0, el = 0;
+  while (++r <= 2 * kT) {
+    int discr = 0;
+    for (int i = 0; i < r; i++) discr ^= gf.mul(sigma[i], syn[r - i - 1]);
+    if (discr == 0) {
+      for (int i = 2 * kT; i > 0; i--) b[i] = b[i - 1];
+      b[0] = 0;
+    } else {
+      T[0] = sigma[0];
+      for (int i = 0; i < 2 * kT; i++) T[i + 1] = (uint8_t)(sigma[i + 1] ^ gf.mul(discr, b[i]));
+      if (2 * el <= r - 1) {
+        el = r - el;
+        for (int i = 0; i <= 2 * kT; i++) b[i] = (uint8_t)gf.div(sigma[i], discr);
+      } else {
+        for (int i = 2 * kT; i > 0; i--) b[i] = b[i - 1];
+        b[0] = 0;
+      }
+      for (int i = 0; i <= 2 * kT; i++) sigma[i] = T[i];
+    }
+  }
+  int deg = 0;
+  for (int i = 0; i <= 2 * kT; i++)
+    if (sigma[i]) deg = i;
+  return deg;
+}
+
+// Forney, reed_solomon.cc:417-486.  root[]/loc[] hold no_roots == deg_sigma entries.
+// pkt = the 204 received bytes (positions 51..254 of the code word).
+__device__ int rs_forney(const GfTables &gf, const uint8_t *syn, const uint8_t *sigma, int deg_sigma,
+                         const uint8_t *root, const uint8_t *loc, int no_roots, uint8_t *pkt) {
+  uint8_t omega[2 * kT + 1];
+  int deg_omega = 0;
+  for (int i = 0; i < 2 * kT; i++) {
+    int tmp = 0;
+    int j = (deg_sigma < i) ? deg_sigma : i;
+    for (; j >= 0; j--) tmp ^= gf.mul(syn[i - j], sigma[j]);
+    if (tmp) deg_omega = i;
+    omega[i] = (uint8_t)tmp;
+  }
+  for (int j = no_roots - 1; j >= 0; j--) {
+    int rt = root[j];
+    int num1 = 0;
+    for (int i = deg_omega; i >= 0; i--) num1 ^= gf.mulpow(omega[i], i * rt);
+    int num2 = gf.exp2[(kN - rt) % kN];
+    int den = 0;
+    int deg_max = deg_sigma < 2 * kT - 1 ? deg_sigma : 2 * kT - 1;
+    for (int i = 1; i <= deg_max; i += 2)
+      if (sigma[i]) den ^= gf.exp2[(gf.log[sigma[i]] + (i - 1) * rt) % kN];
+    if (den == 0) return -1;  // :470-479, earlier corrections stay
+    int err = gf.div(gf.mul(num1, num2), den);
+    int pos = loc[j];
+    if (pos >= kS) pkt[pos - kS] ^= (uint8_t)err;  // positions < 51 are the discarded zero prefix
+  }
+  return no_roots;
+}
+
+__global__ void __launch_bounds__(256) rs_decode_kernel(const uint8_t *__restrict__ in, uint8_t *__restrict__ out,
+                                                        int *__restrict__ status, long long npackets, int as_built) {
+  __shared__ __align__(16) uint8_t s_exp2[512];
+  __shared__ __align__(16) uint8_t s_log[256];
+  __shared__ __align__(16) uint32_t s_pkt[8][52];
+  __shared__ uint8_t s_work[8][80];  // per warp: syn[16] | sigma[17] | root[17] | loc[17] | deg, status
+  for (int i = threadIdx.x; i < 512; i += blockDim.x) s_exp2[i] = c_exp2[i];
+  for (int i = threadIdx.x; i < 256; i += blockDim.x) s_log[i] = c_log[i];
+  __syncthreads();
+  GfTables gf{s_exp2, s_log};
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  uint8_t *pkt = reinterpret_cast<uint8_t *>(s_pkt[warp]);
+  uint8_t *syn = s_work[warp], *sigma = syn + 16, *root = sigma + 17, *loc = root + 17, *misc = loc + 17;
+  for (long long p = (long long)blockIdx.x * 8 + warp; p < npackets; p += (long long)gridDim.x * 8) {
+    const uint32_t *src = reinterpret_cast<const uint32_t *>(in + p * kPktIn);
+    s_pkt[warp][lane] = src[lane];
+    if (lane + 32 < 51) s_pkt[warp][lane + 32] = src[lane + 32];
+    __syncwarp();
+    // ---- syndromes: byte j carries x^(203-j); lane takes j = lane, lane+32, ...
+    uint32_t S0 = 0, S1 = 0, S2 = 0, S3 = 0;
+#pragma unroll
+    for (int t = 0; t < 7; t++) {
+      int j = lane + 32 * t;
+      if (j < kPktIn) {
+        int v = pkt[j];
+        if (v) {
+          int ex = 203 - j;
+          int e = s_log[v];
+          uint32_t acc[4] = {0, 0, 0, 0};
+#pragma unroll
+          for (int i = 0; i < 16; i++) {
+            acc[i >> 2] |= (uint32_t)s_exp2[e] << (8 * (i & 3));
+            e += ex;
+            if (e >= 255) e -= 255;
+          }
+          S0 ^= acc[0]; S1 ^= acc[1]; S2 ^= acc[2]; S3 ^= acc[3];
+        }
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      S0 ^= __shfl_xor_sync(0xffffffffu, S0, o);
+      S1 ^= __shfl_xor_sync(0xffffffffu, S1, o);
+      S2 ^= __shfl_xor_sync(0xffffffffu, S2, o);
+      S3 ^= __shfl_xor_sync(0xffffffffu, S3, o);
+    }
+    int st = 0;
+    if ((S0 | S1 | S2 | S3) != 0u) {  // warp-uniform
+      if (lane == 0) {
+        uint32_t S[4] = {S0, S1, S2, S3};
+        for (int i = 0; i < 16; i++) syn[i] = (uint8_t)(S[i >> 2] >> (8 * (i & 3)));
+        misc[0] = (uint8_t)rs_locator(gf, syn, sigma);
+      }
+      __syncwarp();
+      int deg = misc[0];
+      // ---- Chien: q(i) = 1 + sum_j sigma[j] a^(j*i), i = 1..255 in increasing order
+      int nroots = 0;
+      for (int t = 0; t < 8; t++) {
+        int i = 32 * t + lane + 1;
+        int q = 1;
+        if (i <= kN) {
+          for (int j = deg; j > 0; j--) q ^= gf.mulpow(sigma[j], j * i);
+        }
+        unsigned hit = __ballot_sync(0xffffffffu, i <= kN && q == 0);
+        if (q == 0 && i <= kN) {
+          int idx = nroots + __popc(hit & ((1u << lane) - 1u));
+          if (idx < 17) { root[idx] = (uint8_t)i; loc[idx] = (uint8_t)(i - 1); }
+        }
+        nroots += __popc(hit);
+      }
+      __syncwarp();
+      if (lane == 0) {
+        if (nroots != deg) {
+          st = -1;  // uncorrectable: data untouched (:405-415)
+        } else {
+          // the reference's out-of-bounds omega[2t] = 0 lands on loc[0] with gcc 13.3
+          if (as_built) loc[0] = 0;
+          st = rs_forney(gf, syn, sigma, deg, root, loc, nroots, pkt);
+        }
+        misc[1] = (uint8_t)(st & 0xff);
+      }
+      __syncwarp();
+      st = (int)(int8_t)misc[1];
+    }
+    uint32_t *dst = reinterpret_cast<uint32_t *>(out + p * kPktOut);
+    dst[lane] = s_pkt[warp][lane];
+    if (lane + 32 < 47) dst[lane + 32] = s_pkt[warp][lane + 32];
+    if (status && lane == 0) status[p] = st;
+    __syncwarp();
+  }
+}
+
+}  // namespace
+
+struct dvbt_b200_rsdec {
+  dvbt_b200_rsdec_params par;
+  int as_built = 0;
+  cudaStream_t stream = nullptr;
+  dvbt::DevBuf d_in, d_out;
+  int sm_count = 148;
+};
+
+namespace dvbt {
+int rs_upload_tables() {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 64 && g_tables_ready[dev]) return 0;
+  uint8_t e2[512], lg[256];
+  int reg = 1;  // reed_solomon.cc:48-89 with p = 2, m = 8, gfpoly = 0x11d
+  lg[0] = 255;
+  for (int i = 0; i < 255; i++) {
+    e2[i] = (uint8_t)reg;
+    lg[reg] = (uint8_t)i;
+    reg <<= 1;
+    if (reg & 0x100) reg ^= 0x11d;
+    reg &= 0xff;
+  }
+  for (int i = 255; i < 512; i++) e2[i] = e2[i - 255];
+  DVBT_CUDA_TRY(cudaMemcpyToSymbol(c_exp2, e2, 512));
+  DVBT_CUDA_TRY(cudaMemcpyToSymbol(c_log, lg, 256));
+  if (dev < 64) g_tables_ready[dev] = true;
+  return 0;
+}
+
+int rs_launch(const uint8_t *d_in, uint8_t *d_out, int *d_status, long long npackets, int as_built, int sm_count,
+              cudaStream_t st) {
+  if (npackets <= 0) return 0;
+  int rc = rs_upload_tables();
+  if (rc) return rc;
+  long long blocks = (npackets + 7) / 8;
+  long long cap = (long long)sm_count * 8;
+  unsigned grid = (unsigned)(blocks < cap ? blocks : cap);
+  rs_decode_kernel<<<grid, 256, 0, st>>>(d_in, d_out, d_status, npackets, as_built);
+  count_launch();
+  DVBT_CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+}  // namespace dvbt
+
+extern "C" {
+
+int dvbt_b200_rsdec_create(const dvbt_b200_rsdec_params *p, dvbt_b200_rsdec **out) {
+  if (!p || !out) { dvbt::set_error("rsdec_create: null argument"); return DVBT_B200_EINVAL; }
+  *out = nullptr;
+  if (p->p != 2 || p->m != 8 || p->gfpoly != 0x11d || p->n != 255 || p->k != 239 || p->t != 8 || p->s != 51 || p->blocks <= 0) {
+    dvbt::set_error("rsdec_create: only the DVB-T outer code is built: (p,m,gfpoly,n,k,t,s) = (2,8,0x11d,255,239,8,51)");
+    return DVBT_B200_EINVAL;
+  }
+  int rc = dvbt::ensure_device();
+  if (rc) return rc;
+  dvbt_b200_rsdec *h = new (std::nothrow) dvbt_b200_rsdec();
+  if (!h) { dvbt::set_error("rsdec_create: out of memory"); return DVBT_B200_ENOMEM; }
+  h->par = *p;
+  if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) {
+    dvbt::set_error("rsdec_create: cannot create stream");
+    delete h;
+    return DVBT_B200_ECUDA;
+  }
+  int dev = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, dev);
+  *out = h;
+  return 0;
+}
+
+void dvbt_b200_rsdec_destroy(dvbt_b200_rsdec *h) {
+  if (!h) return;
+  if (h->stream) { cudaStreamSynchronize(h->stream); cudaStreamDestroy(h->stream); }
+  h->d_in.release();
+  h->d_out.release();
+  delete h;
+}
+
+int dvbt_b200_rsdec_set_compat(dvbt_b200_rsdec *h, int as_built) {
+  if (!h) { dvbt::set_error("rsdec_set_compat: null handle"); return DVBT_B200_EINVAL; }
+  h->as_built = as_built ? 1 : 0;
+  return 0;
+}
+
+int dvbt_b200_rsdec_decode_dev(dvbt_b200_rsdec *h, const uint8_t *d_in, size_t npackets, uint8_t *d_out, int *d_status) {
+  if (!h || (npackets && (!d_in || !d_out))) { dvbt::set_error("rsdec_decode_dev: bad argument"); return DVBT_B200_EINVAL; }
+  int rc = dvbt::rs_launch(d_in, d_out, d_status, (long long)npackets, h->as_built, h->sm_count, h->stream);
+  if (rc) return rc;
+  DVBT_CUDA_TRY(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+int dvbt_b200_rsdec_work(dvbt_b200_rsdec *h, const uint8_t *in, size_t n_in_items, uint8_t *out, size_t noutput_items,
+                         size_t *consumed, size_t *produced) {
+  if (!h || !consumed || !produced) { dvbt::set_error("rsdec_work: null argument"); return DVBT_B200_EINVAL; }
+  *consumed = *produced = 0;
+  if (n_in_items < noutput_items) {  // forecast: 1:1 (reed_solomon_dec_impl.cc:71-75)
+    dvbt::set_error("rsdec_work: %zu input items for %zu output items", n_in_items, noutput_items);
+    return DVBT_B200_EINVAL;
+  }
+  if (noutput_items == 0) return 0;
+  if (!in || !out) { dvbt::set_error("rsdec_work: null buffer"); return DVBT_B200_EINVAL; }
+  size_t npk = noutput_items * (size_t)h->par.blocks;
+  int rc;
+  if ((rc = h->d_in.reserve(npk * kPktIn))) return rc;
+  if ((rc = h->d_out.reserve(npk * kPktOut))) return rc;
+  DVBT_CUDA_TRY(cudaMemcpyAsync(h->d_in.p, in, npk * kPktIn, cudaMemcpyHostToDevice, h->stream));
+  rc = dvbt::rs_launch(h->d_in.as<uint8_t>(), h->d_out.as<uint8_t>(), nullptr, (long long)npk, h->as_built, h->sm_count, h->stream);
+  if (rc) return rc;
+  DVBT_CUDA_TRY(cudaMemcpyAsync(out, h->d_out.p, npk * kPktOut, cudaMemcpyDeviceToHost, h->stream));
+  DVBT_CUDA_TRY(cudaStreamSynchronize(h->stream));
+  *consumed = noutput_items;
+  *produced = noutput_items;
+  return 0;
+}
+
+}  // extern "C"

@@ -122,6 +122,62 @@ int dvbt_b200_viterbi_decode_dev(dvbt_b200_viterbi *h, const uint8_t *d_in, size
 int dvbt_b200_viterbi_last_stats(const dvbt_b200_viterbi *h, long long *chunks,
                                  long long *repaired, float *acs_kernel_ms);
 
+/* ------------------------------------------------------------------------------------
+ * reed_solomon_dec — replaces gr::dvbt::reed_solomon_dec
+ *   make():         include/dvbt/reed_solomon_dec.h:49
+ *   general_work(): lib/reed_solomon_dec_impl.cc:77-116 -> reed_solomon::rs_decode
+ *                   (lib/reed_solomon.cc:246-489)
+ * Items: `blocks` packets of n-s = 204 bytes in, `blocks` packets of k-s = 188 bytes out.
+ * Packets rs_decode reports as uncorrectable pass through unmodified (its return value is
+ * dropped by the block, reed_solomon_dec_impl.cc:100).
+ * ------------------------------------------------------------------------------------ */
+typedef struct dvbt_b200_rsdec dvbt_b200_rsdec;
+typedef struct dvbt_b200_rsdec_params { /* the make() arguments, in order */
+  int p, m, gfpoly, n, k, t, s, blocks; /* 2, 8, 0x11d, 255, 239, 8, 51, 8 in every flowgraph */
+} dvbt_b200_rsdec_params;
+
+int dvbt_b200_rsdec_create(const dvbt_b200_rsdec_params *p, dvbt_b200_rsdec **out);
+void dvbt_b200_rsdec_destroy(dvbt_b200_rsdec *h);
+/* as_built = 0 (default): the decoder the reference source describes (corrects up to t = 8
+ * byte errors).  as_built = 1: reproduce the reference *binary* as gcc 13 builds it, where the
+ * out-of-bounds store at reed_solomon.cc:434 (array declared :255) zeroes loc[0], so the
+ * lowest-position error of every corrupted packet is left uncorrected. */
+int dvbt_b200_rsdec_set_compat(dvbt_b200_rsdec *h, int as_built);
+/* one general_work() call on HOST buffers; forecast is 1:1 */
+int dvbt_b200_rsdec_work(dvbt_b200_rsdec *h, const uint8_t *in, size_t n_in_items, uint8_t *out,
+                         size_t noutput_items, size_t *consumed, size_t *produced);
+/* npackets packets of 204 bytes at d_in -> 188 bytes each at d_out (device pointers);
+ * d_status (nullable, int[npackets]) receives rs_decode's return value per packet:
+ * 0 clean, >0 corrected symbols, -1 uncorrectable */
+int dvbt_b200_rsdec_decode_dev(dvbt_b200_rsdec *h, const uint8_t *d_in, size_t npackets,
+                               uint8_t *d_out, int *d_status);
+
+/* ------------------------------------------------------------------------------------
+ * dvbt_demap — replaces gr::dvbt::dvbt_demap
+ *   make():         include/dvbt/dvbt_demap.h:50
+ *   general_work(): lib/dvbt_demap_impl.cc:217-240 (find_constellation_value :167-203,
+ *                   make_constellation_points :117-165)
+ * Items: nsize gr_complex (float re, im) in, nsize bytes out (constellation index < 2^m).
+ * ------------------------------------------------------------------------------------ */
+typedef struct dvbt_b200_demap dvbt_b200_demap;
+typedef struct dvbt_b200_demap_params { /* the make() arguments, in order */
+  int nsize;         /* cells per item: 1512 (2k) or 6048 (8k) */
+  int constellation; /* DVBT_QPSK / QAM16 / QAM64 */
+  int hierarchy;     /* DVBT_NH, ALPHA1, ALPHA2, ALPHA4 */
+  int transmission;  /* DVBT_T2K / DVBT_T8K (unused by the decision, kept for signature parity) */
+  float gain;
+} dvbt_b200_demap_params;
+
+int dvbt_b200_demap_create(const dvbt_b200_demap_params *p, dvbt_b200_demap **out);
+void dvbt_b200_demap_destroy(dvbt_b200_demap *h);
+/* the constellation table (re, im pairs indexed by output value); returns its size */
+int dvbt_b200_demap_points(const dvbt_b200_demap *h, float *re_im, int capacity_points);
+/* one general_work() call on HOST buffers; forecast is 1:1 */
+int dvbt_b200_demap_work(dvbt_b200_demap *h, const void *in, size_t n_in_items, uint8_t *out,
+                         size_t noutput_items, size_t *consumed, size_t *produced);
+/* ncells complex cells at d_in -> ncells bytes at d_out (device pointers, 16-byte aligned) */
+int dvbt_b200_demap_run_dev(dvbt_b200_demap *h, const void *d_in, size_t ncells, uint8_t *d_out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -36,6 +36,10 @@ def lib():
         L.dvbt_oracle_viterbi_metrics.argtypes = [C.c_void_p, C.c_void_p]
         L.dvbt_oracle_conv_encode.restype = C.c_long
         L.dvbt_oracle_conv_encode.argtypes = [C.c_void_p, C.c_long, C.c_int, C.c_int, C.c_void_p]
+        L.dvbt_oracle_rs_decode.argtypes = [C.c_void_p, C.c_long, C.c_void_p, C.c_int, C.c_void_p]
+        L.dvbt_oracle_rs_encode.argtypes = [C.c_void_p, C.c_long, C.c_void_p]
+        L.dvbt_oracle_constellation.argtypes = [C.c_int, C.c_int, C.c_float, C.c_void_p]
+        L.dvbt_oracle_demap.argtypes = [C.c_void_p, C.c_long, C.c_int, C.c_int, C.c_float, C.c_void_p]
         _lib = L
     return _lib
 
@@ -94,3 +98,34 @@ def flip_bits(coded, m, ber, seed):
     for j in range(m):
         coded ^= (rng.random(len(coded)) < ber).astype(np.uint8) << j
     return coded
+
+
+def rs_encode(packets188):
+    """(npk,188) -> (npk,204) systematic RS(204,188) code words (generator roots a^0..a^15)."""
+    d = np.ascontiguousarray(packets188, np.uint8).reshape(-1, 188)
+    out = np.zeros((d.shape[0], 204), np.uint8)
+    lib().dvbt_oracle_rs_encode(d.ctypes.data, d.shape[0], out.ctypes.data)
+    return out
+
+
+def rs_decode(packets204, as_built=False):
+    """(npk,204) -> ((npk,188), status[npk]) following reed_solomon_dec_impl.cc / reed_solomon.cc."""
+    d = np.ascontiguousarray(packets204, np.uint8).reshape(-1, 204)
+    out = np.zeros((d.shape[0], 188), np.uint8)
+    st = np.zeros(d.shape[0], np.int32)
+    lib().dvbt_oracle_rs_decode(d.ctypes.data, d.shape[0], out.ctypes.data, int(as_built), st.ctypes.data)
+    return out, st
+
+
+def constellation_points(constellation, alpha=1, gain=1.0):
+    pts = np.zeros(128, np.float32)
+    n = lib().dvbt_oracle_constellation(constellation, alpha, gain, pts.ctypes.data)
+    return pts[: 2 * n].view(np.complex64).copy()
+
+
+def demap(cells, constellation, alpha=1, gain=1.0):
+    """complex64 cells -> hard-decision bytes (dvbt_demap_impl.cc:167-203)."""
+    c = np.ascontiguousarray(cells, np.complex64).reshape(-1)
+    out = np.zeros(len(c), np.uint8)
+    lib().dvbt_oracle_demap(c.ctypes.data, len(c), constellation, alpha, gain, out.ctypes.data)
+    return out

@@ -44,6 +44,15 @@ void dvbt_oracle_viterbi_metrics(const dvbt_oracle_viterbi *, uint8_t metrics[64
  * nbytes*8*n/k a multiple of m.  Returns the number of output bytes. */
 long dvbt_oracle_conv_encode(const uint8_t *data, long nbytes, int m, int rate, uint8_t *out);
 
+/* ---- Reed-Solomon (reed_solomon.cc, reed_solomon_dec_impl.cc) ----------------------- */
+/* npackets packets of 204 bytes -> 188 bytes each; as_built: see rs_port.c; status optional */
+void dvbt_oracle_rs_decode(const uint8_t *in, long npackets, uint8_t *out, int as_built, int *status);
+void dvbt_oracle_rs_encode(const uint8_t *in, long npackets, uint8_t *out);
+
+/* ---- dvbt_demap (dvbt_demap_impl.cc) ------------------------------------------------ */
+int dvbt_oracle_constellation(int constellation, int alpha, float gain, float *points);
+void dvbt_oracle_demap(const float *in, long n, int constellation, int alpha, float gain, uint8_t *out);
+
 #ifdef __cplusplus
 }
 #endif
