@@ -11,7 +11,7 @@ import numpy as np
 from . import capi
 from .capi import check, lib
 
-__all__ = ["viterbi_decoder", "reed_solomon_dec", "dvbt_demap", "QPSK", "QAM16", "QAM64", "NH", "C1_2", "C2_3", "C3_4", "C5_6", "C7_8", "T2k", "T8k", "G1_32"]
+__all__ = ["viterbi_decoder", "reed_solomon_dec", "dvbt_demap", "demod_reference_signals", "QPSK", "QAM16", "QAM64", "NH", "C1_2", "C2_3", "C3_4", "C5_6", "C7_8", "T2k", "T8k", "G1_32"]
 
 QPSK, QAM16, QAM64 = 0, 1, 2
 NH = 0
@@ -167,3 +167,34 @@ class dvbt_demap(_Handle):
 
     def run_dev(self, d_in, ncells, d_out):
         check(lib().dvbt_b200_demap_run_dev(self._h, _addr(d_in), ncells, _addr(d_out)))
+
+
+class demod_reference_signals(_Handle):
+    """dvbt.demod_reference_signals(itemsize, ninput, noutput, constellation, hierarchy, code_rate_HP, code_rate_LP,
+    guard_interval, transmission_mode, include_cell_id, cell_id) (include/dvbt/demod_reference_signals.h:50-54)."""
+    _destroy = "dvbt_b200_demod_destroy"
+
+    def __init__(self, itemsize, ninput, noutput, constellation, hierarchy, code_rate_HP, code_rate_LP, guard_interval,
+                 transmission_mode, include_cell_id=0, cell_id=0):
+        self._h = C.c_void_p()
+        par = capi.DemodParams(itemsize, ninput, noutput, constellation, hierarchy, code_rate_HP, code_rate_LP, guard_interval,
+                               transmission_mode, include_cell_id, cell_id)
+        check(lib().dvbt_b200_demod_create(C.byref(par), C.byref(self._h)))
+        self.N, self.P = ninput, noutput
+
+    def general_work(self, inp, out_capacity=None, tags=()):
+        """inp: (nsym, N) complex64.  Returns (cells (nout, P), consumed, out_tags)."""
+        inp = np.ascontiguousarray(inp, np.complex64).reshape(-1, self.N)
+        nsym = inp.shape[0]
+        cap = out_capacity if out_capacity is not None else max(nsym - 1, 1)
+        out = np.zeros((cap, self.P), np.complex64)
+        tin = (capi.Tag * max(1, len(tags)))()
+        for i, (off, key, val) in enumerate(tags):
+            tin[i] = capi.Tag(off, capi.TAG_KEYS[key], val)
+        tout = (capi.Tag * (cap + 4))()
+        ntout = C.c_size_t(0)
+        cons, prod = C.c_size_t(0), C.c_size_t(0)
+        check(lib().dvbt_b200_demod_work(self._h, inp.ctypes.data, nsym, out.ctypes.data, cap, C.byref(cons), C.byref(prod),
+                                         tin, len(tags), tout, cap + 4, C.byref(ntout)))
+        otags = [(int(tout[i].offset), capi.TAG_NAMES[tout[i].key], int(tout[i].value)) for i in range(ntout.value)]
+        return out[: prod.value].copy(), int(cons.value), otags

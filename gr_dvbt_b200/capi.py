@@ -34,6 +34,11 @@ class DemapParams(C.Structure):
     _fields_ = [("nsize", C.c_int), ("constellation", C.c_int), ("hierarchy", C.c_int), ("transmission", C.c_int), ("gain", C.c_float)]
 
 
+class DemodParams(C.Structure):
+    _fields_ = [(n, C.c_int) for n in ("itemsize", "ninput", "noutput", "constellation", "hierarchy", "code_rate_HP", "code_rate_LP",
+                                       "guard_interval", "transmission_mode", "include_cell_id", "cell_id")]
+
+
 class ViterbiTuning(C.Structure):
     _fields_ = [("chunk_bytes", C.c_int), ("warmup_bytes", C.c_int), ("threads_per_block", C.c_int)]
 
@@ -75,6 +80,10 @@ def lib():
         L.dvbt_b200_demap_points.argtypes = [vp, vp, C.c_int]
         L.dvbt_b200_demap_work.argtypes = [vp, vp, C.c_size_t, vp, C.c_size_t, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]
         L.dvbt_b200_demap_run_dev.argtypes = [vp, vp, C.c_size_t, vp]
+        L.dvbt_b200_demod_create.argtypes = [C.POINTER(DemodParams), C.POINTER(vp)]
+        L.dvbt_b200_demod_destroy.argtypes = [vp]
+        L.dvbt_b200_demod_work.argtypes = [vp, vp, C.c_size_t, vp, C.c_size_t, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t),
+                                           C.POINTER(Tag), C.c_size_t, C.POINTER(Tag), C.c_size_t, C.POINTER(C.c_size_t)]
         _lib = L
     return _lib
 

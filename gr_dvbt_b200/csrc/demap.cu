@@ -8,17 +8,12 @@
 // contraction), scanned from index 0 upwards.  One thread per cell; the 4/16/64 points sit in
 // the kernel parameter block (constant bank, read uniformly by the warp).  HBM bound:
 // 8 B in + 1 B out per cell.
-#include "common.cuh"
+#include "demod.cuh"
 
 #include <math.h>
 #include <new>
 
 namespace dvbt {
-
-struct DemapTable {
-  float2 pts[64];
-  int size;
-};
 
 static int gray(int v) { return (v >> 1) ^ v; }
 

@@ -1,0 +1,571 @@
+// K4 — demod_reference_signals on sm_100a: post-FFT frequency correction, scattered-pilot
+// channel estimate, equalisation (+ fused demap), TPS decoding and frame synchronisation.
+//
+// Replaces gr::dvbt::demod_reference_signals (lib/demod_reference_signals_impl.cc:96-150) and
+// pilot_gen::parse_input with its callees (lib/reference_signals_impl.cc:1188-1248):
+//   process_cpilot_data   :714-744   integer CFO in [-8,8) from continual-pilot differences
+//   compute_oneshot_csft  :746-790   fractional CFO from this and the next symbol
+//   frequency_correction  :792-819   one rotor per symbol + bin shift
+//   process_spilot_data   :535-689   scattered-pilot phase (symbol index mod 4), pilot gains,
+//                                    linear interpolation with the reference's constant /11 step
+//   process_tps_data      :918-1032  DBPSK majority vote, 68-bit FIFO, sync word + BCH(67,53)
+//   process_payload_data  :1064-1124 payload carriers x gain
+//
+// The reference is one sequential loop per symbol.  Here every float operation that feeds a
+// decision or an output keeps the reference's operand order and rounding (explicit
+// __f*_rn / __d*_rn, no FMA contraction; complex division as libgcc's __divsc3 does it for
+// float operands: straight formula in double), but the work is split:
+//   demod_stage1_kernel : one warp per symbol  - CFO sums (16 lanes), one-shot sums (2 lanes),
+//                                                rotor, scattered-pilot phase (4 lanes)
+//   demod_equalise_kernel: one block per symbol - pilot gains -> shared memory, interpolation,
+//                                                TPS carriers, payload cells (+ demap)
+//   demod_vote_kernel   : one thread per symbol - TPS majority vote against the previous symbol
+//   demod_scan_kernel   : one thread            - the genuinely sequential part (symbol/frame
+//                                                index, TPS FIFO, BCH, superframe gating)
+// HBM traffic per symbol: 2 x 8N B read (this + next symbol for the one-shot estimate; the
+// second read hits L2) and 8P (cells) + P (demapped) written.
+#include "demod.cuh"
+
+#include <math.h>
+#include <string.h>
+#include <new>
+#include <vector>
+
+namespace dvbt {
+
+// ---------------------------------------------------------------------------------------
+// tables
+// ---------------------------------------------------------------------------------------
+static const short kCpilot2k[45] = {0,   48,  54,  87,  141, 156, 192, 201, 255,  279,  282,  333,  432,  450,  483,
+                                    525, 531, 618, 636, 714, 759, 765, 780, 804,  873,  888,  918,  939,  942,  969,
+                                    984, 1050, 1101, 1107, 1110, 1137, 1140, 1146, 1206, 1269, 1323, 1377, 1491, 1683, 1704};
+static const short kTps2k[17] = {34, 50, 209, 346, 413, 569, 595, 688, 790, 901, 1073, 1219, 1262, 1286, 1469, 1594, 1687};
+
+int ModeTables::init(int tm, int gi) {
+  if (tm != DVBT_T2K && tm != DVBT_T8K) { set_error("mode tables: bad transmission mode %d", tm); return DVBT_B200_EINVAL; }
+  ModeDev &d = dev;
+  d.N = tm == DVBT_T2K ? 2048 : 8192;
+  d.P = tm == DVBT_T2K ? 1512 : 6048;
+  int Kmax = tm == DVBT_T2K ? 1704 : 6816;
+  d.K = Kmax + 1;
+  d.zl = (int)ceil((d.N - d.K) / 2.0);  // dvbt_config.cc:124
+  d.cp = gi == DVBT_G1_16 ? d.N / 16 : gi == DVBT_G1_8 ? d.N / 8 : gi == DVBT_G1_4 ? d.N / 4 : d.N / 32;
+  d.ncp = tm == DVBT_T2K ? 45 : 177;
+  d.ntps = tm == DVBT_T2K ? 17 : 68;
+  // reference_signals_impl.cc:753 — float(cp)/float(N) in float, the rest in double, stored in a float
+  d.carrier_coeff = (float)(1.0 / (2 * M_PI * (1 + float(d.cp) / float(d.N)) * 2));
+  const int K = d.K, P = d.P;
+  // the 8k tables are the 2k tables repeated with +1704*r (reference_signals_impl.cc:77-117)
+  std::vector<short> cpl, tpl;
+  int reps = tm == DVBT_T2K ? 1 : 4;
+  for (int r = 0; r < reps; r++)
+    for (int i = 0; i < 45; i++) {
+      short v = (short)(kCpilot2k[i] + 1704 * r);
+      if (cpl.empty() || cpl.back() != v) cpl.push_back(v);
+    }
+  for (int r = 0; r < reps; r++)
+    for (int i = 0; i < 17; i++) tpl.push_back((short)(kTps2k[i] + 1704 * r));
+  if ((int)cpl.size() != d.ncp || (int)tpl.size() != d.ntps) { set_error("mode tables: pilot table size mismatch"); return DVBT_B200_EINVAL; }
+  // PRBS x^11 + x^2 + 1 (:333-345)
+  std::vector<float> pval(K);
+  {
+    unsigned reg = (1u << 11) - 1;
+    for (int k = 0; k < K; k++) {
+      int w = reg & 1;
+      int nb = ((reg >> 2) ^ reg) & 1;
+      reg = (reg >> 1) | (nb << 10);
+      pval[k] = (float)(4 * 2 * (0.5 - w) / 3);  // :474-479 / :700-705
+    }
+  }
+  std::vector<float> known(d.ncp - 1);
+  for (int i = 0; i < d.ncp - 1; i++) {
+    float dr = pval[cpl[i + 1]] - pval[cpl[i]];
+    known[i] = dr * dr + 0.0f * 0.0f;  // norm() of a real difference (:224-228)
+  }
+  std::vector<unsigned char> kind(4 * K, 0);
+  std::vector<short> prevp(4 * K), nextp(4 * K), payload(4 * P);
+  for (int r = 0; r < 4; r++) {
+    unsigned char *kd = &kind[r * K];
+    for (int k = 3 * r; k < K; k += 12) kd[k] |= 1;
+    for (short c : cpl) kd[c] |= 1;
+    for (short t : tpl) kd[t] |= 2;
+    int last = 0;
+    for (int k = 0; k < K; k++) {
+      if (kd[k] & 1) last = k;
+      prevp[r * K + k] = (short)last;
+    }
+    int nxt = K - 1;
+    for (int k = K - 1; k >= 0; k--) {
+      nextp[r * K + k] = (short)nxt;
+      if (kd[k] & 1) nxt = k;
+    }
+    int n = 0;
+    for (int k = 0; k < K; k++)
+      if (kd[k] == 0) {
+        if (n < P) payload[r * P + n] = (short)k;
+        n++;
+      }
+    if (n != P) { set_error("mode tables: %d payload carriers for scattered phase %d, expected %d", n, r, P); return DVBT_B200_EINVAL; }
+  }
+  // symbol interleaver H(q) (symbol_inner_interleaver_impl.cc:35-96)
+  std::vector<short> H(P), Hinv(P);
+  {
+    const int Nr = tm == DVBT_T2K ? 11 : 13;
+    static const char perm2k[] = {4, 3, 9, 6, 2, 8, 1, 5, 7, 0};
+    static const char perm8k[] = {7, 1, 4, 2, 9, 6, 8, 10, 0, 3, 11, 5};
+    const char *perm = tm == DVBT_T2K ? perm2k : perm8k;
+    int q = 0;
+    unsigned reg = 0;
+    for (int i = 0; i < d.N; i++) {
+      if (i < 2) reg = 0;
+      else if (i == 2) reg = 1;
+      else {
+        unsigned nb = tm == DVBT_T2K ? ((reg ^ (reg >> 3)) & 1u) : ((reg ^ (reg >> 1) ^ (reg >> 4) ^ (reg >> 6)) & 1u);
+        reg = ((reg >> 1) | (nb << (Nr - 2))) & ((1u << Nr) - 1u);
+      }
+      unsigned newreg = 0;
+      for (int k = 0; k < Nr - 1; k++) newreg |= ((reg >> k) & 1u) << perm[k];
+      int h = ((i % 2) << (Nr - 1)) + (int)newreg;
+      if (h < P) {
+        if (q < P) H[q] = (short)h;
+        q++;
+      }
+    }
+    if (q != P) { set_error("mode tables: symbol interleaver produced %d entries", q); return DVBT_B200_EINVAL; }
+    for (int i = 0; i < P; i++) Hinv[H[i]] = (short)i;
+  }
+  // pack into one device blob
+  size_t off = 0;
+  auto place = [&](size_t bytes) { size_t o = off; off += (bytes + 15) & ~(size_t)15; return o; };
+  size_t o_cp = place(cpl.size() * 2), o_tps = place(tpl.size() * 2), o_known = place(known.size() * 4), o_pval = place(pval.size() * 4),
+         o_kind = place(kind.size()), o_prev = place(prevp.size() * 2), o_next = place(nextp.size() * 2), o_pay = place(payload.size() * 2),
+         o_H = place(H.size() * 2), o_Hi = place(Hinv.size() * 2);
+  std::vector<unsigned char> host(off);
+  memcpy(&host[o_cp], cpl.data(), cpl.size() * 2);
+  memcpy(&host[o_tps], tpl.data(), tpl.size() * 2);
+  memcpy(&host[o_known], known.data(), known.size() * 4);
+  memcpy(&host[o_pval], pval.data(), pval.size() * 4);
+  memcpy(&host[o_kind], kind.data(), kind.size());
+  memcpy(&host[o_prev], prevp.data(), prevp.size() * 2);
+  memcpy(&host[o_next], nextp.data(), nextp.size() * 2);
+  memcpy(&host[o_pay], payload.data(), payload.size() * 2);
+  memcpy(&host[o_H], H.data(), H.size() * 2);
+  memcpy(&host[o_Hi], Hinv.data(), Hinv.size() * 2);
+  int rc = blob.reserve(off);
+  if (rc) return rc;
+  DVBT_CUDA_TRY(cudaMemcpy(blob.p, host.data(), off, cudaMemcpyHostToDevice));
+  unsigned char *base = blob.as<unsigned char>();
+  d.cpilot = (const short *)(base + o_cp);
+  d.tps = (const short *)(base + o_tps);
+  d.known = (const float *)(base + o_known);
+  d.pval = (const float *)(base + o_pval);
+  d.kind = base + o_kind;
+  d.prevp = (const short *)(base + o_prev);
+  d.nextp = (const short *)(base + o_next);
+  d.payload = (const short *)(base + o_pay);
+  d.H = (const short *)(base + o_H);
+  d.Hinv = (const short *)(base + o_Hi);
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------
+// exact float helpers (operand order of libstdc++ / libgcc, no contraction)
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ float2 cmul(float2 a, float2 b) {  // (a.x*b.x - a.y*b.y, a.x*b.y + a.y*b.x)
+  return make_float2(__fsub_rn(__fmul_rn(a.x, b.x), __fmul_rn(a.y, b.y)), __fadd_rn(__fmul_rn(a.x, b.y), __fmul_rn(a.y, b.x)));
+}
+__device__ __forceinline__ float2 cmul_conj(float2 a, float2 b) { return cmul(a, make_float2(b.x, -b.y)); }
+__device__ __forceinline__ float cnorm(float2 a) { return __fadd_rn(__fmul_rn(a.x, a.x), __fmul_rn(a.y, a.y)); }
+__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(__fadd_rn(a.x, b.x), __fadd_rn(a.y, b.y)); }
+__device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(__fsub_rn(a.x, b.x), __fsub_rn(a.y, b.y)); }
+// libgcc __divsc3 for float operands (GCC >= 12): the textbook formula evaluated in double
+__device__ __forceinline__ float2 cdiv(float2 n, float2 d) {
+  double a = n.x, b = n.y, c = d.x, e = d.y;
+  double denom = __dadd_rn(__dmul_rn(c, c), __dmul_rn(e, e));
+  double x = __ddiv_rn(__dadd_rn(__dmul_rn(a, c), __dmul_rn(b, e)), denom);
+  double y = __ddiv_rn(__dsub_rn(__dmul_rn(b, c), __dmul_rn(a, e)), denom);
+  return make_float2((float)x, (float)y);
+}
+
+// ---------------------------------------------------------------------------------------
+// stage 1: one warp per symbol
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) demod_stage1_kernel(ModeDev md, const float2 *__restrict__ X, int nparse,
+                                                           int *__restrict__ fo_out, float2 *__restrict__ rot_out,
+                                                           int *__restrict__ mod_out) {
+  int s = (int)((blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5);
+  int lane = threadIdx.x & 31;
+  if (s >= nparse) return;
+  const float2 *x0 = X + (long long)s * md.N;
+  const float2 *x1 = x0 + md.N;
+  // ---- process_cpilot_data (:714-744): lanes 0..15 hold candidate i = zl - 8 + lane
+  float sum = 0.f;
+  if (lane < 16) {
+    int i = md.zl - 8 + lane;
+    float2 prev = x0[i + md.cpilot[0]];
+    for (int j = 0; j < md.ncp - 1; j++) {
+      float2 cur = x0[i + md.cpilot[j + 1]];
+      float phase = cnorm(csub(cur, prev));
+      sum = __fadd_rn(sum, __fmul_rn(md.known[j], phase));
+      prev = cur;
+    }
+  }
+  float best = 0.f;
+  int start = 0;
+  for (int l = 0; l < 16; l++) {  // sequential first-strict-maximum scan
+    float v = __shfl_sync(0xffffffffu, sum, l);
+    if (v > best) { best = v; start = md.zl - 8 + l; }
+  }
+  // all-zero input leaves start = 0 in the reference (offset -zl, out-of-bounds reads there);
+  // a zero offset is used instead
+  int fo = (best > 0.f) ? start - md.zl : 0;
+  // ---- compute_oneshot_csft (:746-790): lane 0 = left half, lane 1 = right half
+  float angle = 0.f;
+  if (lane < 2) {
+    int half = (md.ncp - 1) / 2;
+    int j0 = lane == 0 ? 0 : half + 1, j1 = lane == 0 ? half : md.ncp;
+    float2 acc = make_float2(0.f, 0.f);
+    for (int j = j0; j < j1; j++) {
+      int idx = fo + md.zl + md.cpilot[j];
+      acc = cadd(acc, cmul_conj(x0[idx], x1[idx]));
+    }
+    angle = atan2f(acc.y, acc.x);
+  }
+  float left = __shfl_sync(0xffffffffu, angle, 0), right = __shfl_sync(0xffffffffu, angle, 1);
+  float corr = __fmul_rn(__fadd_rn(right, left), md.carrier_coeff);
+  // ---- frequency_correction (:792-819): one rotor for the whole symbol
+  float correction = __fadd_rn((float)fo, corr);
+  double ang = __ddiv_rn(__dmul_rn(__dmul_rn(-2.0 * M_PI, (double)correction), (double)(md.N + md.cp)), (double)md.N);
+  float sn, cs;
+  sincosf((float)ang, &sn, &cs);
+  float2 rot = make_float2(cs, sn);
+  // ---- process_spilot_data, phase detection (:547-582): lanes 0..3 = candidate phase
+  float ssum = 0.f;
+  if (lane < 4) {
+    float2 c = make_float2(0.f, 0.f);
+    for (int j = 0; j < 10; j++) {
+      int k = 3 * lane + 12 * j;
+      float2 dv = cmul(rot, x0[md.zl + k + fo]);
+      c = cadd(c, cmul_conj(make_float2(md.pval[k], 0.f), dv));
+    }
+    ssum = cnorm(c);
+  }
+  float smax = 0.f;
+  int mod = -1;  // -1: no candidate exceeded 0, the reference keeps the previous value
+  for (int l = 0; l < 4; l++) {
+    float v = __shfl_sync(0xffffffffu, ssum, l);
+    if (v > smax) { smax = v; mod = l; }
+  }
+  if (lane == 0) {
+    fo_out[s] = fo;
+    rot_out[s] = rot;
+    mod_out[s] = mod;
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// stage 2: one block per symbol — gains, interpolation, TPS carriers, payload (+ demap)
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ uint8_t demap_cell_dev(const DemapTable &t, float2 v) {
+  float dr = __fsub_rn(v.x, t.pts[0].x), di = __fsub_rn(v.y, t.pts[0].y);
+  float min_dist = __fadd_rn(__fmul_rn(dr, dr), __fmul_rn(di, di));
+  int min_index = 0;
+#pragma unroll 8
+  for (int i = 1; i < t.size; i++) {
+    dr = __fsub_rn(v.x, t.pts[i].x);
+    di = __fsub_rn(v.y, t.pts[i].y);
+    float d = __fadd_rn(__fmul_rn(dr, dr), __fmul_rn(di, di));
+    if (d < min_dist) { min_dist = d; min_index = i; }
+  }
+  return (uint8_t)min_index;
+}
+
+__global__ void __launch_bounds__(256) demod_equalise_kernel(ModeDev md, const __grid_constant__ DemapTable dt, int do_demap,
+                                                             const float2 *__restrict__ X, const int *__restrict__ fo_in,
+                                                             const float2 *__restrict__ rot_in, const int *__restrict__ mod_in,
+                                                             float2 *__restrict__ tpsval, float2 *__restrict__ Y,
+                                                             uint8_t *__restrict__ dm) {
+  extern __shared__ float2 s_gain[];  // [K]
+  const int s = blockIdx.x;
+  const int fo = fo_in[s];
+  const float2 rot = rot_in[s];
+  int r = mod_in[s];
+  if (r < 0) r = 0;  // degenerate all-zero symbol; the scan resolves the index bookkeeping
+  const float2 *x = X + (long long)s * md.N + md.zl + fo;
+  const unsigned char *kind = md.kind + r * md.K;
+  // pilot gains: gain = tx / rx (:484-489 set_channel_gain)
+  for (int k = threadIdx.x; k < md.K; k += blockDim.x) {
+    if (kind[k] & 1) s_gain[k] = cdiv(make_float2(md.pval[k], 0.f), cmul(rot, x[k]));
+  }
+  __syncthreads();
+  // linear interpolation with the reference's fixed /11 slope (:617-642)
+  const short *prevp = md.prevp + r * md.K, *nextp = md.nextp + r * md.K;
+  for (int k = threadIdx.x; k < md.K; k += blockDim.x) {
+    if (!(kind[k] & 1)) {
+      int k0 = prevp[k], k1 = nextp[k];
+      float2 g0 = s_gain[k0];
+      float2 tg = cdiv(csub(s_gain[k1], g0), make_float2(11.0f, 0.0f));
+      float2 step = cmul(tg, make_float2((float)(k - k0), 0.0f));
+      s_gain[k] = cadd(g0, step);
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < md.ntps) {  // :929-945
+    int k = md.tps[threadIdx.x];
+    tpsval[(long long)s * md.ntps + threadIdx.x] = cmul(cmul(rot, x[k]), s_gain[k]);
+  }
+  const short *pay = md.payload + r * md.P;
+  for (int i = threadIdx.x; i < md.P; i += blockDim.x) {  // :1104-1113
+    int k = pay[i];
+    float2 y = cmul(cmul(rot, x[k]), s_gain[k]);
+    if (Y) Y[(long long)s * md.P + i] = y;
+    if (do_demap) dm[(long long)s * md.P + i] = demap_cell_dev(dt, y);
+  }
+}
+
+// TPS DBPSK majority vote against the previous symbol (:929-948)
+__global__ void demod_vote_kernel(int ntps, int nparse, const float2 *__restrict__ tpsval,
+                                  const DemodState *__restrict__ state, int *__restrict__ vote) {
+  int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= nparse) return;
+  const float2 *cur = tpsval + (long long)s * ntps;
+  int v = 0;
+  for (int k = 0; k < ntps; k++) {
+    float2 prev = s > 0 ? tpsval[(long long)(s - 1) * ntps + k] : state->prev_tps[k];
+    float2 ph = cmul_conj(cur[k], prev);
+    v += (ph.x >= 0.0f) ? 1 : -1;
+  }
+  vote[s] = v;
+}
+
+// BCH(127,113) shortened to (67,53): verify_bch_code (:384-425)
+__device__ bool tps_bch_ok(const unsigned char *f) {
+  unsigned reg = 0;
+  for (int i = 0; i < 113; i++) {
+    unsigned bit = i < 60 ? 0u : f[1 + (i - 60)];
+    unsigned fb = 1u & (bit ^ reg);
+    reg >>= 1;
+    reg |= fb << 13;
+    reg ^= (fb << 12) ^ (fb << 11) ^ (fb << 9) ^ (fb << 8) ^ (fb << 7) ^ (fb << 5) ^ (fb << 4);
+  }
+  for (int i = 0; i < 14; i++)
+    if (f[i + 54] != (1u & (reg >> i))) return false;
+  return true;
+}
+
+// The sequential bookkeeping of parse_input (:1188-1248) and of the block (:108-149).
+__global__ void demod_scan_kernel(int ntps, int nparse, int fi_start, int sync_start_at0, const int *__restrict__ mod_in,
+                                  const int *__restrict__ vote, const float2 *__restrict__ tpsval, DemodState *st,
+                                  int *__restrict__ out_symidx, int *__restrict__ out_src) {
+  if (blockIdx.x != 0 || threadIdx.x != 0) return;
+  static const unsigned char sync_even[16] = {0, 0, 1, 1, 0, 1, 0, 1, 1, 1, 1, 0, 1, 1, 1, 0};
+  DemodState S = *st;
+  S.first_out = -1;
+  S.n_out = 0;
+  S.sf_tag_at = -1;
+  if (sync_start_at0) S.d_init = 0;  // :115-116
+  for (int s = 0; s < nparse; s++) {
+    int mod = mod_in[s] >= 0 ? mod_in[s] : S.mod;
+    S.mod = mod;
+    int diff = (mod - S.prev_mod + 4) % 4;  // :684-688
+    S.prev_mod = mod;
+    S.symbol_index = (S.symbol_index + diff) % 68;  // :1228
+    int sym_out = S.symbol_index, frame_out = S.frame_index;
+    // process_tps_data
+    bool cond = !S.known || S.symbol_index != 0;
+    for (int i = 0; i < diff; i++) {  // :957-972
+      for (int b = 0; b < 67; b++) S.fifo[b] = S.fifo[b + 1];
+      S.fifo[67] = cond ? (vote[s] >= 0 ? 0 : 1) : 0;
+    }
+    // std::equal(begin+1, begin+16, sync.begin()): 15 elements (:975, :1002)
+    bool even = true, odd = true;
+    for (int i = 0; i < 15; i++) {
+      if (S.fifo[1 + i] != sync_even[i]) even = false;
+      if (S.fifo[1 + i] != (1 - sync_even[i])) odd = false;
+    }
+    int end_frame = 0;
+    if (even || odd) {
+      if (tps_bch_ok(S.fifo)) {
+        S.frame_index = (S.fifo[23] << 1) | S.fifo[24];
+        S.known = 1;
+        end_frame = 1;
+      } else {
+        S.known = 0;
+      }
+      for (int b = 0; b < 68; b++) S.fifo[b] = 0;
+    }
+    if (end_frame) S.symbol_index = 67;  // :1240-1241
+    // block level (demod_reference_signals_impl.cc:118-143)
+    if (S.d_init == 0) {
+      if ((sym_out % 68) == 0 && (frame_out % 4) == fi_start) {
+        S.d_init = 1;
+        S.sf_tag_at = S.n_out;
+      } else {
+        continue;
+      }
+    }
+    if (S.first_out < 0) S.first_out = s;
+    out_symidx[S.n_out] = sym_out;
+    out_src[S.n_out] = s;
+    S.n_out++;
+  }
+  if (nparse > 0)
+    for (int k = 0; k < ntps; k++) S.prev_tps[k] = tpsval[(long long)(nparse - 1) * ntps + k];
+  *st = S;
+}
+
+int demod_run(const ModeDev &md, const DemapTable *demap, const float2 *X, int nparse, DemodBuffers b, DemodState *d_state,
+              int fi_start, int sync_start_at0, float2 *Y, uint8_t *dm, cudaStream_t st) {
+  if (nparse <= 0) return 0;
+  {
+    int threads = 128;
+    long long total = (long long)nparse * 32;
+    demod_stage1_kernel<<<(unsigned)((total + threads - 1) / threads), threads, 0, st>>>(md, X, nparse, b.fo, b.rot, b.modidx);
+    DVBT_CUDA_TRY(cudaGetLastError());
+  }
+  {
+    size_t smem = (size_t)md.K * sizeof(float2);
+    static bool attr_set = false;
+    if (!attr_set) {
+      DVBT_CUDA_TRY(cudaFuncSetAttribute(demod_equalise_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+      attr_set = true;
+    }
+    DemapTable dummy;
+    dummy.size = 0;
+    demod_equalise_kernel<<<nparse, 256, smem, st>>>(md, demap ? *demap : dummy, (demap && dm) ? 1 : 0, X, b.fo, b.rot, b.modidx,
+                                                    b.tpsval, Y, dm);
+    DVBT_CUDA_TRY(cudaGetLastError());
+  }
+  demod_vote_kernel<<<(nparse + 127) / 128, 128, 0, st>>>(md.ntps, nparse, b.tpsval, d_state, b.vote);
+  DVBT_CUDA_TRY(cudaGetLastError());
+  demod_scan_kernel<<<1, 32, 0, st>>>(md.ntps, nparse, fi_start, sync_start_at0, b.modidx, b.vote, b.tpsval, d_state, b.out_symidx, b.out_src);
+  DVBT_CUDA_TRY(cudaGetLastError());
+  count_launch(4);
+  return 0;
+}
+
+}  // namespace dvbt
+
+// ---------------------------------------------------------------------------------------
+// block ABI
+// ---------------------------------------------------------------------------------------
+struct dvbt_b200_demod {
+  dvbt_b200_demod_params par;
+  dvbt::ModeTables tables;
+  cudaStream_t stream = nullptr;
+  dvbt::DevBuf d_X, d_Y, d_Yc, d_state, d_fo, d_rot, d_mod, d_tps, d_vote, d_osym, d_osrc, h_state;
+  int fi_start = 3;
+  bool pending_sync = false;
+};
+
+namespace {
+__global__ void demod_compact_kernel(int P, const int *__restrict__ src, const float2 *__restrict__ Y, float2 *__restrict__ out) {
+  int o = blockIdx.x;
+  const float2 *y = Y + (long long)src[o] * P;
+  for (int i = threadIdx.x; i < P; i += blockDim.x) out[(long long)o * P + i] = y[i];
+}
+}  // namespace
+
+extern "C" {
+
+int dvbt_b200_demod_create(const dvbt_b200_demod_params *p, dvbt_b200_demod **out) {
+  if (!p || !out) { dvbt::set_error("demod_create: null argument"); return DVBT_B200_EINVAL; }
+  *out = nullptr;
+  int rc = dvbt::ensure_device();
+  if (rc) return rc;
+  dvbt_b200_demod *h = new (std::nothrow) dvbt_b200_demod();
+  if (!h) { dvbt::set_error("demod_create: out of memory"); return DVBT_B200_ENOMEM; }
+  h->par = *p;
+  rc = h->tables.init(p->transmission_mode, p->guard_interval);
+  if (!rc && (p->ninput != h->tables.dev.N || p->noutput != h->tables.dev.P || p->itemsize != 8)) {
+    dvbt::set_error("demod_create: itemsize/ninput/noutput (%d,%d,%d) do not match the mode (8,%d,%d)", p->itemsize, p->ninput,
+                    p->noutput, h->tables.dev.N, h->tables.dev.P);
+    rc = DVBT_B200_EINVAL;
+  }
+  if (!rc && cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) {
+    dvbt::set_error("demod_create: cannot create stream");
+    rc = DVBT_B200_ECUDA;
+  }
+  if (!rc) rc = h->d_state.reserve(sizeof(dvbt::DemodState));
+  h->h_state.host = true;
+  if (!rc) rc = h->h_state.reserve(sizeof(dvbt::DemodState));
+  if (rc) { dvbt_b200_demod_destroy(h); return rc; }
+  cudaMemset(h->d_state.p, 0, sizeof(dvbt::DemodState));
+  // demod_reference_signals_impl.cc:73-77 ("TODO investigate" upstream)
+  h->fi_start = (p->constellation == DVBT_QAM64 && p->transmission_mode == DVBT_T8K) ? 2 : 3;
+  *out = h;
+  return 0;
+}
+
+void dvbt_b200_demod_destroy(dvbt_b200_demod *h) {
+  if (!h) return;
+  if (h->stream) { cudaStreamSynchronize(h->stream); cudaStreamDestroy(h->stream); }
+  dvbt::DevBuf *bufs[] = {&h->d_X, &h->d_Y, &h->d_Yc, &h->d_state, &h->d_fo, &h->d_rot, &h->d_mod, &h->d_tps, &h->d_vote, &h->d_osym, &h->d_osrc, &h->h_state};
+  for (auto *b : bufs) b->release();
+  h->tables.release();
+  delete h;
+}
+
+int dvbt_b200_demod_work(dvbt_b200_demod *h, const void *in, size_t n_in_items, void *out, size_t out_capacity_items,
+                         size_t *consumed, size_t *produced, const dvbt_b200_tag *tags_in, size_t n_tags_in,
+                         dvbt_b200_tag *tags_out, size_t tags_out_capacity, size_t *n_tags_out) {
+  if (!h || !consumed || !produced) { dvbt::set_error("demod_work: null argument"); return DVBT_B200_EINVAL; }
+  *consumed = *produced = 0;
+  if (n_tags_out) *n_tags_out = 0;
+  if (n_in_items < 2 || out_capacity_items == 0) return 0;  // forecast: 2 input items per output item
+  if (!in || !out) { dvbt::set_error("demod_work: null buffer"); return DVBT_B200_EINVAL; }
+  const dvbt::ModeDev &md = h->tables.dev;
+  size_t nparse = n_in_items - 1;
+  if (nparse > out_capacity_items) nparse = out_capacity_items;
+  // a sync_start tag anywhere in the window re-arms the gating (is_sync_start, :44-52); the reference
+  // parses one item per call, so honour only a tag on the first item and stop the window before a later one
+  bool sync0 = false;
+  for (size_t i = 0; i < n_tags_in; i++) {
+    if (tags_in[i].key != DVBT_TAG_SYNC_START) continue;
+    if (tags_in[i].offset == 0) sync0 = true;
+    else if (tags_in[i].offset < nparse) nparse = (size_t)tags_in[i].offset;
+  }
+  int rc;
+  size_t nsym = nparse + 1;
+  if ((rc = h->d_X.reserve(nsym * md.N * 8))) return rc;
+  if ((rc = h->d_Y.reserve(nparse * md.P * 8))) return rc;
+  if ((rc = h->d_Yc.reserve(nparse * md.P * 8))) return rc;
+  if ((rc = h->d_fo.reserve(nparse * 4))) return rc;
+  if ((rc = h->d_rot.reserve(nparse * 8))) return rc;
+  if ((rc = h->d_mod.reserve(nparse * 4))) return rc;
+  if ((rc = h->d_tps.reserve(nparse * md.ntps * 8))) return rc;
+  if ((rc = h->d_vote.reserve(nparse * 4))) return rc;
+  if ((rc = h->d_osym.reserve(nparse * 4))) return rc;
+  if ((rc = h->d_osrc.reserve(nparse * 4))) return rc;
+  DVBT_CUDA_TRY(cudaMemcpyAsync(h->d_X.p, in, nsym * md.N * 8, cudaMemcpyHostToDevice, h->stream));
+  dvbt::DemodBuffers b{h->d_fo.as<int>(), h->d_rot.as<float2>(), h->d_mod.as<int>(), h->d_tps.as<float2>(), h->d_vote.as<int>(),
+                       h->d_osym.as<int>(), h->d_osrc.as<int>()};
+  rc = dvbt::demod_run(md, nullptr, h->d_X.as<float2>(), (int)nparse, b, h->d_state.as<dvbt::DemodState>(), h->fi_start, sync0 ? 1 : 0,
+                       h->d_Y.as<float2>(), nullptr, h->stream);
+  if (rc) return rc;
+  DVBT_CUDA_TRY(cudaMemcpyAsync(h->h_state.p, h->d_state.p, sizeof(dvbt::DemodState), cudaMemcpyDeviceToHost, h->stream));
+  DVBT_CUDA_TRY(cudaStreamSynchronize(h->stream));
+  const dvbt::DemodState *S = h->h_state.as<dvbt::DemodState>();
+  size_t nout = (size_t)S->n_out;
+  std::vector<int> symidx(nout);
+  if (nout) {
+    demod_compact_kernel<<<(unsigned)nout, 256, 0, h->stream>>>(md.P, h->d_osrc.as<int>(), h->d_Y.as<float2>(), h->d_Yc.as<float2>());
+    dvbt::count_launch();
+    DVBT_CUDA_TRY(cudaGetLastError());
+    DVBT_CUDA_TRY(cudaMemcpyAsync(out, h->d_Yc.p, nout * md.P * 8, cudaMemcpyDeviceToHost, h->stream));
+    DVBT_CUDA_TRY(cudaMemcpyAsync(symidx.data(), h->d_osym.p, nout * 4, cudaMemcpyDeviceToHost, h->stream));
+    DVBT_CUDA_TRY(cudaStreamSynchronize(h->stream));
+  }
+  // tags: superframe_start (0xaa) on the first output after sync, symbol_index on every output (:126-143)
+  size_t nt = 0;
+  if (tags_out && n_tags_out) {
+    if (S->sf_tag_at >= 0 && nt < tags_out_capacity) tags_out[nt++] = dvbt_b200_tag{(uint64_t)S->sf_tag_at, DVBT_TAG_SUPERFRAME_START, 0xaa};
+    for (size_t i = 0; i < nout && nt < tags_out_capacity; i++) tags_out[nt++] = dvbt_b200_tag{(uint64_t)i, DVBT_TAG_SYMBOL_INDEX, symidx[i]};
+    *n_tags_out = nt;
+  }
+  *consumed = nparse;
+  *produced = nout;
+  return 0;
+}
+
+}  // extern "C"

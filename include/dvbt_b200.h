@@ -178,6 +178,36 @@ int dvbt_b200_demap_work(dvbt_b200_demap *h, const void *in, size_t n_in_items, 
 /* ncells complex cells at d_in -> ncells bytes at d_out (device pointers, 16-byte aligned) */
 int dvbt_b200_demap_run_dev(dvbt_b200_demap *h, const void *d_in, size_t ncells, uint8_t *d_out);
 
+/* ------------------------------------------------------------------------------------
+ * demod_reference_signals — replaces gr::dvbt::demod_reference_signals
+ *   make():         include/dvbt/demod_reference_signals.h:50-54
+ *   forecast():     lib/demod_reference_signals_impl.cc:87-94 (2 input items per output item)
+ *   general_work(): lib/demod_reference_signals_impl.cc:96-150 -> pilot_gen::parse_input
+ *                   (lib/reference_signals_impl.cc:1188-1248 and callees)
+ * Items: ninput = N gr_complex (one FFT output, DC at bin N/2) in; noutput = P gr_complex
+ * (equalised payload cells) out.  Symbol i needs symbol i+1 to be visible.
+ * Tags in:  sync_start (re-arms the wait for a superframe start).
+ * Tags out: superframe_start (value 0xaa) on the first item produced after sync,
+ *           symbol_index (0..67) on every produced item.
+ * ------------------------------------------------------------------------------------ */
+typedef struct dvbt_b200_demod dvbt_b200_demod;
+typedef struct dvbt_b200_demod_params { /* the make() arguments, in order */
+  int itemsize;          /* sizeof(gr_complex) = 8 */
+  int ninput, noutput;   /* 2048/1512 or 8192/6048 */
+  int constellation, hierarchy, code_rate_HP, code_rate_LP, guard_interval, transmission_mode;
+  int include_cell_id, cell_id;
+} dvbt_b200_demod_params;
+
+int dvbt_b200_demod_create(const dvbt_b200_demod_params *p, dvbt_b200_demod **out);
+void dvbt_b200_demod_destroy(dvbt_b200_demod *h);
+/* One scheduler call on HOST buffers.  Parses up to min(n_in_items - 1, out_capacity_items)
+ * symbols (the reference parses one per call; the stream behaviour is the same): consumed =
+ * symbols parsed, produced = symbols emitted (none until the superframe start is found). */
+int dvbt_b200_demod_work(dvbt_b200_demod *h, const void *in, size_t n_in_items, void *out,
+                         size_t out_capacity_items, size_t *consumed, size_t *produced,
+                         const dvbt_b200_tag *tags_in, size_t n_tags_in, dvbt_b200_tag *tags_out,
+                         size_t tags_out_capacity, size_t *n_tags_out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,75 @@
+"""GPU parity: CUDA demod_reference_signals vs the reference block itself (oracle/_ref, the
+reference sources compiled verbatim) on reference-TX-generated OFDM symbols."""
+import numpy as np
+import pytest
+
+from oracle import refchain as R
+
+pytestmark = pytest.mark.gpu
+
+needs_ref = pytest.mark.skipif(not R.available(), reason="oracle/_ref not built (needs /root/reference at build time)")
+
+
+def run_case(con, cr, tm, nsym, noise, shift, seed):
+    import gr_dvbt_b200 as g
+    from dvbt_testlib import tx_frequency_domain, channel
+    N, P, _, _ = R.mode_dims(tm)
+    tx = tx_frequency_domain(con, cr, tm, nsym, seed)
+    X = channel(tx["X"], noise=noise, bin_shift=shift, seed=seed)
+    Yref, tags_ref = R.rx_demod(X, con, cr, tm)
+    d = g.demod_reference_signals(8, N, P, con, g.NH, cr, cr, g.G1_32, tm, 0, 0)
+    Y, cons, tags = d.general_work(X, tags=[(0, "sync_start", 1)])
+    assert cons == X.shape[0] - 1
+    assert sorted(tags) == sorted(tags_ref), (tags[:3], tags_ref[:3])
+    assert Y.shape == Yref.shape
+    same = np.array_equal(Y.view(np.uint32), Yref.view(np.uint32))
+    if not same:
+        err = np.abs(Y - Yref) / (np.abs(Yref) + 1e-12)
+        bad = np.argwhere(Y.view(np.uint64) != Yref.view(np.uint64))
+        print("max rel err %.3e, %d of %d cells differ, first at %s" % (err.max(), len(bad), Y.size, bad[:3].tolist()))
+    return Y, Yref, same
+
+
+@needs_ref
+@pytest.mark.parametrize("con,cr,tm,nsym", [(R.QAM16, R.C1_2, R.T2k, 300), (R.QAM64, R.C7_8, R.T2k, 292), (R.QAM16, R.C1_2, R.T8k, 284)])
+def test_clean_channel_bit_exact(con, cr, tm, nsym):
+    Y, Yref, same = run_case(con, cr, tm, nsym, 0.0, 0, 1)
+    assert Y.shape[0] >= 8
+    assert same
+
+
+@needs_ref
+def test_noise_and_integer_offset():
+    """AWGN (decisions near ties, TPS votes) and a +3 bin carrier offset (integer CFO path)."""
+    Y, Yref, same = run_case(R.QAM64, R.C7_8, R.T2k, 292, 0.05, 3, 7)
+    # sincosf/atan2f of the rotor may differ in the last ulp between glibc and CUDA: tolerance 1e-5 relative
+    err = np.abs(Y - Yref) / (np.abs(Yref) + 1e-9)
+    assert err.max() < 1e-5
+
+
+@needs_ref
+def test_streaming_calls_carry_state():
+    import gr_dvbt_b200 as g
+    from dvbt_testlib import tx_frequency_domain, channel
+    con, cr, tm = R.QAM16, R.C1_2, R.T2k
+    N, P, _, _ = R.mode_dims(tm)
+    X = channel(tx_frequency_domain(con, cr, tm, 300, 3)["X"])
+    Yref, tags_ref = R.rx_demod(X, con, cr, tm)
+    d = g.demod_reference_signals(8, N, P, con, g.NH, cr, cr, g.G1_32, tm, 0, 0)
+    pos, outs, tags, nwritten = 0, [], [], 0
+    sizes = [5, 17, 64, 3, 129, 40]
+    i = 0
+    first = True
+    while pos < X.shape[0] - 1:
+        n = min(sizes[i % len(sizes)], X.shape[0] - 1 - pos)
+        i += 1
+        Y, cons, t = d.general_work(X[pos: pos + n + 1], tags=[(0, "sync_start", 1)] if first else [])
+        first = False
+        for off, key, val in t:
+            tags.append((nwritten + off, key, val))
+        nwritten += Y.shape[0]
+        outs.append(Y)
+        pos += cons
+    Y = np.concatenate(outs)
+    assert np.array_equal(Y.view(np.uint32), Yref.view(np.uint32))
+    assert sorted(tags) == sorted(tags_ref)
