@@ -11,7 +11,7 @@ import numpy as np
 from . import capi
 from .capi import check, lib
 
-__all__ = ["viterbi_decoder", "reed_solomon_dec", "dvbt_demap", "demod_reference_signals", "QPSK", "QAM16", "QAM64", "NH", "C1_2", "C2_3", "C3_4", "C5_6", "C7_8", "T2k", "T8k", "G1_32"]
+__all__ = ["viterbi_decoder", "reed_solomon_dec", "dvbt_demap", "demod_reference_signals", "rx_chain", "QPSK", "QAM16", "QAM64", "NH", "C1_2", "C2_3", "C3_4", "C5_6", "C7_8", "T2k", "T8k", "G1_32"]
 
 QPSK, QAM16, QAM64 = 0, 1, 2
 NH = 0
@@ -198,3 +198,49 @@ class demod_reference_signals(_Handle):
                                          tin, len(tags), tout, cap + 4, C.byref(ntout)))
         otags = [(int(tout[i].offset), capi.TAG_NAMES[tout[i].key], int(tout[i].value)) for i in range(ntout.value)]
         return out[: prod.value].copy(), int(cons.value), otags
+
+
+class rx_chain(_Handle):
+    """Fused device-resident receive chain (include/dvbt_b200.h: dvbt_b200_rx_*): what apps/dvbt_rx_demo*.grc
+    does from the FFT output to the TS file."""
+    _destroy = "dvbt_b200_rx_destroy"
+    STAGES = dict(cells=(0, np.complex64), demap=(1, np.uint8), bitdeint=(2, np.uint8), viterbi=(3, np.uint8), rs=(4, np.uint8),
+                  rs_status=(5, np.int32), symbol_index=(6, np.int32))
+
+    def __init__(self, constellation, hierarchy, code_rate, guard_interval, transmission_mode):
+        self._h = C.c_void_p()
+        par = capi.RxParams(constellation, hierarchy, code_rate, guard_interval, transmission_mode)
+        check(lib().dvbt_b200_rx_create(C.byref(par), C.byref(self._h)))
+        self.N = 2048 if transmission_mode == T2k else 8192
+        self.P = 1512 if transmission_mode == T2k else 6048
+
+    def set_rs_compat(self, as_built):
+        check(lib().dvbt_b200_rx_set_rs_compat(self._h, int(as_built)))
+
+    def run_freq(self, X):
+        """X: (nsym, N) complex64 host array -> TS bytes (numpy)."""
+        X = np.ascontiguousarray(X, np.complex64).reshape(-1, self.N)
+        cap = X.shape[0] * self.P + 4096
+        ts = np.zeros(cap, np.uint8)
+        n = C.c_size_t(0)
+        check(lib().dvbt_b200_rx_run_freq_host(self._h, X.ctypes.data, X.shape[0], ts.ctypes.data, cap, C.byref(n)))
+        return ts[: n.value].copy()
+
+    def run_freq_dev(self, d_X, nsym, d_ts, ts_capacity):
+        n = C.c_size_t(0)
+        check(lib().dvbt_b200_rx_run_freq_dev(self._h, _addr(d_X), nsym, _addr(d_ts), ts_capacity, C.byref(n)))
+        return int(n.value)
+
+    def info(self):
+        i = capi.RxInfo()
+        check(lib().dvbt_b200_rx_last_info(self._h, C.byref(i)))
+        return {n: getattr(i, n) for n, _ in capi.RxInfo._fields_}
+
+    def stage(self, name):
+        sid, dt = self.STAGES[name]
+        inf = self.info()
+        cap = max(inf["symbols_parsed"], 1) * self.P * 8 + 4096
+        buf = np.zeros(cap, np.uint8)
+        n = C.c_size_t(0)
+        check(lib().dvbt_b200_rx_read_stage(self._h, sid, buf.ctypes.data, cap, C.byref(n)))
+        return buf[: n.value].view(dt).copy()

@@ -39,6 +39,16 @@ class DemodParams(C.Structure):
                                        "guard_interval", "transmission_mode", "include_cell_id", "cell_id")]
 
 
+class RxParams(C.Structure):
+    _fields_ = [(n, C.c_int) for n in ("constellation", "hierarchy", "code_rate", "guard_interval", "transmission_mode")]
+
+
+class RxInfo(C.Structure):
+    _fields_ = [(n, C.c_longlong) for n in ("symbols_parsed", "first_symbol", "symbols_out", "viterbi_bytes", "viterbi_repaired",
+                                             "rs_packets", "first_packet", "ts_bytes")] + \
+               [(n, C.c_float) for n in ("ms_demod", "ms_inner", "ms_viterbi", "ms_viterbi_acs", "ms_rs", "ms_descramble")]
+
+
 class ViterbiTuning(C.Structure):
     _fields_ = [("chunk_bytes", C.c_int), ("warmup_bytes", C.c_int), ("threads_per_block", C.c_int)]
 
@@ -84,6 +94,13 @@ def lib():
         L.dvbt_b200_demod_destroy.argtypes = [vp]
         L.dvbt_b200_demod_work.argtypes = [vp, vp, C.c_size_t, vp, C.c_size_t, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t),
                                            C.POINTER(Tag), C.c_size_t, C.POINTER(Tag), C.c_size_t, C.POINTER(C.c_size_t)]
+        L.dvbt_b200_rx_create.argtypes = [C.POINTER(RxParams), C.POINTER(vp)]
+        L.dvbt_b200_rx_destroy.argtypes = [vp]
+        L.dvbt_b200_rx_set_rs_compat.argtypes = [vp, C.c_int]
+        L.dvbt_b200_rx_run_freq_host.argtypes = [vp, vp, C.c_size_t, vp, C.c_size_t, C.POINTER(C.c_size_t)]
+        L.dvbt_b200_rx_run_freq_dev.argtypes = [vp, vp, C.c_size_t, vp, C.c_size_t, C.POINTER(C.c_size_t)]
+        L.dvbt_b200_rx_last_info.argtypes = [vp, C.POINTER(RxInfo)]
+        L.dvbt_b200_rx_read_stage.argtypes = [vp, C.c_int, vp, C.c_size_t, C.POINTER(C.c_size_t)]
         _lib = L
     return _lib
 

@@ -97,8 +97,15 @@ __device__ int rs_forney(const GfTables &gf, const uint8_t *syn, const uint8_t *
   return no_roots;
 }
 
+// GATHER: `in` is the Viterbi output stream (in_bytes long, index 0 = the byte carrying the
+// superframe_start tag) and the 12-branch Forney deinterleaver of
+// convolutional_deinterleaver_impl.cc:93-150 (branch b = t % 12 is delayed by 17*(11-b) cells,
+// i.e. 204*(11-b) stream positions; the FIFOs start zeroed) is applied as an index map while
+// the packet is loaded.
+template <bool GATHER>
 __global__ void __launch_bounds__(256) rs_decode_kernel(const uint8_t *__restrict__ in, uint8_t *__restrict__ out,
-                                                        int *__restrict__ status, long long npackets, int as_built) {
+                                                        int *__restrict__ status, long long npackets, int as_built,
+                                                        long long in_bytes) {
   __shared__ __align__(16) uint8_t s_exp2[512];
   __shared__ __align__(16) uint8_t s_log[256];
   __shared__ __align__(16) uint32_t s_pkt[8][52];
@@ -111,9 +118,21 @@ __global__ void __launch_bounds__(256) rs_decode_kernel(const uint8_t *__restric
   uint8_t *pkt = reinterpret_cast<uint8_t *>(s_pkt[warp]);
   uint8_t *syn = s_work[warp], *sigma = syn + 16, *root = sigma + 17, *loc = root + 17, *misc = loc + 17;
   for (long long p = (long long)blockIdx.x * 8 + warp; p < npackets; p += (long long)gridDim.x * 8) {
-    const uint32_t *src = reinterpret_cast<const uint32_t *>(in + p * kPktIn);
-    s_pkt[warp][lane] = src[lane];
-    if (lane + 32 < 51) s_pkt[warp][lane + 32] = src[lane + 32];
+    if (GATHER) {
+#pragma unroll
+      for (int t = 0; t < 7; t++) {
+        int j = lane + 32 * t;
+        if (j < kPktIn) {
+          long long pos = p * kPktIn + j;
+          long long srcpos = pos - 204 * (11 - (j % 12));
+          pkt[j] = (srcpos >= 0 && srcpos < in_bytes) ? in[srcpos] : (uint8_t)0;
+        }
+      }
+    } else {
+      const uint32_t *src = reinterpret_cast<const uint32_t *>(in + p * kPktIn);
+      s_pkt[warp][lane] = src[lane];
+      if (lane + 32 < 51) s_pkt[warp][lane + 32] = src[lane + 32];
+    }
     __syncwarp();
     // ---- syndromes: byte j carries x^(203-j); lane takes j = lane, lane+32, ...
     uint32_t S0 = 0, S1 = 0, S2 = 0, S3 = 0;
@@ -185,7 +204,7 @@ __global__ void __launch_bounds__(256) rs_decode_kernel(const uint8_t *__restric
     dst[lane] = s_pkt[warp][lane];
     if (lane + 32 < 47) dst[lane + 32] = s_pkt[warp][lane + 32];
     if (status && lane == 0) status[p] = st;
-    __syncwarp();
+    __syncwarp();  // pkt is rewritten by the next iteration
   }
 }
 
@@ -222,14 +241,17 @@ int rs_upload_tables() {
 }
 
 int rs_launch(const uint8_t *d_in, uint8_t *d_out, int *d_status, long long npackets, int as_built, int sm_count,
-              cudaStream_t st) {
+              cudaStream_t st, long long gather_stream_bytes) {
   if (npackets <= 0) return 0;
   int rc = rs_upload_tables();
   if (rc) return rc;
   long long blocks = (npackets + 7) / 8;
   long long cap = (long long)sm_count * 8;
   unsigned grid = (unsigned)(blocks < cap ? blocks : cap);
-  rs_decode_kernel<<<grid, 256, 0, st>>>(d_in, d_out, d_status, npackets, as_built);
+  if (gather_stream_bytes >= 0)
+    rs_decode_kernel<true><<<grid, 256, 0, st>>>(d_in, d_out, d_status, npackets, as_built, gather_stream_bytes);
+  else
+    rs_decode_kernel<false><<<grid, 256, 0, st>>>(d_in, d_out, d_status, npackets, as_built, 0);
   count_launch();
   DVBT_CUDA_TRY(cudaGetLastError());
   return 0;
@@ -278,7 +300,7 @@ int dvbt_b200_rsdec_set_compat(dvbt_b200_rsdec *h, int as_built) {
 
 int dvbt_b200_rsdec_decode_dev(dvbt_b200_rsdec *h, const uint8_t *d_in, size_t npackets, uint8_t *d_out, int *d_status) {
   if (!h || (npackets && (!d_in || !d_out))) { dvbt::set_error("rsdec_decode_dev: bad argument"); return DVBT_B200_EINVAL; }
-  int rc = dvbt::rs_launch(d_in, d_out, d_status, (long long)npackets, h->as_built, h->sm_count, h->stream);
+  int rc = dvbt::rs_launch(d_in, d_out, d_status, (long long)npackets, h->as_built, h->sm_count, h->stream, -1);
   if (rc) return rc;
   DVBT_CUDA_TRY(cudaStreamSynchronize(h->stream));
   return 0;
@@ -299,7 +321,7 @@ int dvbt_b200_rsdec_work(dvbt_b200_rsdec *h, const uint8_t *in, size_t n_in_item
   if ((rc = h->d_in.reserve(npk * kPktIn))) return rc;
   if ((rc = h->d_out.reserve(npk * kPktOut))) return rc;
   DVBT_CUDA_TRY(cudaMemcpyAsync(h->d_in.p, in, npk * kPktIn, cudaMemcpyHostToDevice, h->stream));
-  rc = dvbt::rs_launch(h->d_in.as<uint8_t>(), h->d_out.as<uint8_t>(), nullptr, (long long)npk, h->as_built, h->sm_count, h->stream);
+  rc = dvbt::rs_launch(h->d_in.as<uint8_t>(), h->d_out.as<uint8_t>(), nullptr, (long long)npk, h->as_built, h->sm_count, h->stream, -1);
   if (rc) return rc;
   DVBT_CUDA_TRY(cudaMemcpyAsync(out, h->d_out.p, npk * kPktOut, cudaMemcpyDeviceToHost, h->stream));
   DVBT_CUDA_TRY(cudaStreamSynchronize(h->stream));

@@ -1,0 +1,389 @@
+// Device-resident receive chain: post-FFT OFDM symbols -> transport stream, one H2D and one
+// D2H per batch.  Stages and the reference blocks they stand for:
+//
+//   demod_run (demod.cu)        demod_reference_signals + dvbt_demap (fused epilogue)
+//   rx_inner_codes_kernel       symbol_inner_interleaver (deinterleave,
+//                               symbol_inner_interleaver_impl.cc:161-219), bit_inner_deinterleaver
+//                               (bit_inner_deinterleaver_impl.cc:120-184), vector_to_stream and the
+//                               Viterbi block's unpack/depuncture (viterbi_decoder_impl.cc:241-256),
+//                               all as ONE index map from demapped cells to Viterbi step codes
+//   vit_* kernels (viterbi.cu)  viterbi_decoder
+//   rs_decode_kernel<GATHER>    convolutional_deinterleaver (index map while loading) +
+//                               reed_solomon_dec
+//   rx_descramble_kernel        energy_descramble (energy_descramble_impl.cc:108-174): NSYNC search
+//                               over 2 groups, PRBS 1 + x^14 + x^15 restarted every 8 packets
+//
+// Tags become batch metadata: symbol_index per output symbol, superframe_start = first output
+// symbol (the Viterbi reset and the outer deinterleaver alignment).
+#include "chain_internal.cuh"
+
+#include <string.h>
+#include <new>
+#include <vector>
+
+namespace {
+
+using dvbt::set_error;
+
+__constant__ uint8_t c_descr_prbs[1504];
+
+struct InnerMap {
+  const uint8_t *dm;        // demapped cells, P per parsed symbol
+  const int *out_src;       // batch symbol index of output symbol o
+  const int *out_symidx;    // symbol_index tag of output symbol o
+  const short *H, *Hinv;
+  int P, m, n_out;
+};
+
+// hard bit number `tbit` of the Viterbi block's input stream (m bits per cell, MSB first)
+__device__ __forceinline__ uint32_t inner_bit(const InnerMap &im, long long tbit) {
+  long long b = tbit / im.m;
+  int kbit = (int)(tbit - b * im.m);
+  int sym = (int)(b / im.P);
+  int i = (int)(b - (long long)sym * im.P);
+  int blk = i / 126, ii = i - blk * 126;
+  int half = im.m >> 1;
+  int e = kbit / half + 2 * (kbit % half);  // demultiplexer permutation (bit_inner_deinterleaver_impl.cc:91-99)
+  // bit interleaver e delays by H(e,w) = (w + off) % 126 (:34-58)
+  int off = e == 0 ? 0 : e == 1 ? 63 : e == 2 ? 105 : e == 3 ? 42 : e == 4 ? 21 : 84;
+  int w = ii - off;
+  if (w < 0) w += 126;
+  int x = blk * 126 + w;
+  // symbol deinterleaver: odd symbols out[H(q)] = in[q], even symbols out[q] = in[H(q)] (:202-208)
+  int q = (im.out_symidx[sym] & 1) ? im.Hinv[x] : im.H[x];
+  uint32_t cell = im.dm[(long long)im.out_src[sym] * im.P + q];
+  return (cell >> (im.m - 1 - e)) & 1u;
+}
+
+__host__ __device__ constexpr int rate_k(int r) { return r == 0 ? 1 : r == 1 ? 2 : r == 2 ? 3 : r == 3 ? 5 : 7; }
+__host__ __device__ constexpr unsigned rate_px(int r) { return r == 0 ? 0x1u : r == 1 ? 0x1u : r == 2 ? 0x5u : r == 3 ? 0x15u : 0x51u; }
+__host__ __device__ constexpr unsigned rate_py(int r) { return r == 0 ? 0x1u : r == 1 ? 0x3u : r == 2 ? 0x3u : r == 3 ? 0x0bu : 0x2fu; }
+
+template <int RATE>
+__global__ void rx_inner_codes_kernel(InnerMap im, uint32_t *__restrict__ codes, int nbt) {
+  constexpr int K = rate_k(RATE), N = K + 1;
+  constexpr unsigned PX = rate_px(RATE), PY = rate_py(RATE);
+  int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= nbt) return;
+  long long t = 8LL * j;
+  long long sp = t / K;
+  int ph = (int)(t - sp * K);
+  long long idx = sp * N + __popc(PX & ((1u << ph) - 1u)) + __popc(PY & ((1u << ph) - 1u));
+  uint32_t w = 0;
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    uint32_t nib = 0;
+    if ((PX >> ph) & 1u) { nib |= inner_bit(im, idx) | 2u; idx++; }
+    if ((PY >> ph) & 1u) { nib |= (inner_bit(im, idx) << 2) | 8u; idx++; }
+    w |= nib << (4 * i);
+    ph = (ph + 1 == K) ? 0 : ph + 1;
+  }
+  codes[j] = w;
+}
+
+// test tap: the bit_inner_deinterleaver output bytes (what the reference feeds its Viterbi block)
+__global__ void rx_inner_bytes_kernel(InnerMap im, uint8_t *__restrict__ out, long long nbytes) {
+  long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= nbytes) return;
+  uint32_t v = 0;
+  for (int k = 0; k < im.m; k++) v = (v << 1) | inner_bit(im, b * im.m + k);
+  out[b] = (uint8_t)v;
+}
+
+struct DescrInfo {
+  int p0;             // index of the first packet that is output (NSYNC found there), -1: none
+  long long ngroups;  // 8-packet groups written
+};
+
+// One block per 8-packet group.  Every block repeats the (tiny) NSYNC search of
+// energy_descramble_impl.cc:121-134: windows of 2 groups, first packet whose first byte is 0xB8.
+__global__ void __launch_bounds__(256) rx_descramble_kernel(const uint8_t *__restrict__ rs, long long npk, uint8_t *__restrict__ ts,
+                                                            long long ts_capacity, DescrInfo *info) {
+  __shared__ long long s_p0;
+  if (threadIdx.x == 0) {
+    long long p0 = -1;
+    for (long long w = 0; w + 16 <= npk && p0 < 0; w += 16)
+      for (int i = 0; i < 16; i++)
+        if (rs[(w + i) * 188] == 0xB8) { p0 = w + i; break; }
+    s_p0 = p0;
+  }
+  __syncthreads();
+  long long p0 = s_p0;
+  long long ngroups = p0 < 0 ? 0 : (npk - p0) / 8;
+  if (ngroups * 1504 > ts_capacity) ngroups = ts_capacity / 1504;
+  if (blockIdx.x == 0 && threadIdx.x == 0) { info->p0 = (int)p0; info->ngroups = ngroups; }
+  for (long long g = blockIdx.x; g < ngroups; g += gridDim.x) {
+    const uint8_t *src = rs + (p0 + g * 8) * 188;
+    uint8_t *dst = ts + g * 1504;
+    for (int i = threadIdx.x; i < 1504; i += blockDim.x) {
+      int k = i % 188;
+      dst[i] = k == 0 ? (uint8_t)0x47 : (uint8_t)(src[i] ^ c_descr_prbs[i]);  // :146-165
+    }
+  }
+}
+
+}  // namespace
+
+struct dvbt_b200_rx {
+  dvbt_b200_rx_params par;
+  dvbt::ModeTables tables;
+  dvbt::DemapTable demap;
+  dvbt_b200_viterbi *vit = nullptr;
+  cudaStream_t stream = nullptr;
+  int fi_start = 3, rs_as_built = 0, sm_count = 148;
+  int k = 1, n = 2, m = 4, ntb = 5, vit_in_block = 0, vit_out_block = 0;
+  dvbt::DevBuf d_X, d_state, d_fo, d_rot, d_mod, d_tps, d_vote, d_osym, d_osrc, d_dm, d_Y, d_vit, d_rs, d_rsst, d_ts, d_info, h_state, h_info;
+  dvbt_b200_rx_info info;
+  long long last_nparse = 0;
+  cudaEvent_t ev[8];
+};
+
+extern "C" {
+
+int dvbt_b200_rx_create(const dvbt_b200_rx_params *p, dvbt_b200_rx **out) {
+  if (!p || !out) { set_error("rx_create: null argument"); return DVBT_B200_EINVAL; }
+  *out = nullptr;
+  int rc = dvbt::ensure_device();
+  if (rc) return rc;
+  dvbt_b200_rx *h = new (std::nothrow) dvbt_b200_rx();
+  if (!h) { set_error("rx_create: out of memory"); return DVBT_B200_ENOMEM; }
+  for (auto &e : h->ev) e = nullptr;
+  h->par = *p;
+  rc = h->tables.init(p->transmission_mode, p->guard_interval);
+  if (!rc && dvbt::make_demap_table(p->constellation, p->hierarchy, 1.0f, &h->demap)) {
+    set_error("rx_create: bad constellation %d", p->constellation);
+    rc = DVBT_B200_EINVAL;
+  }
+  if (!rc) {
+    dvbt_b200_viterbi_params vp{p->constellation, p->hierarchy, p->code_rate, 768, 0, -1};
+    rc = dvbt_b200_viterbi_create(&vp, &h->vit);
+  }
+  if (rc) { dvbt_b200_rx_destroy(h); return rc; }
+  h->stream = dvbt::vit_stream(h->vit);
+  dvbt::vit_params(h->vit, &h->k, &h->n, &h->m, &h->ntb, &h->vit_in_block, &h->vit_out_block);
+  h->fi_start = (p->constellation == DVBT_QAM64 && p->transmission_mode == DVBT_T8K) ? 2 : 3;
+  h->h_state.host = h->h_info.host = true;
+  if ((rc = h->d_state.reserve(sizeof(dvbt::DemodState))) || (rc = h->h_state.reserve(sizeof(dvbt::DemodState))) ||
+      (rc = h->d_info.reserve(sizeof(DescrInfo))) || (rc = h->h_info.reserve(sizeof(DescrInfo)))) {
+    dvbt_b200_rx_destroy(h);
+    return rc;
+  }
+  for (auto &e : h->ev) cudaEventCreate(&e);
+  // energy_descramble PRBS (energy_descramble_impl.cc:46-67): 1 + x^14 + x^15, init 0xa9, 8 clocks per
+  // byte, clocked but unused on every sync byte except the first of the group
+  {
+    uint8_t tab[1504];
+    unsigned reg = 0xa9;
+    auto clock8 = [&]() {
+      unsigned res = 0;
+      for (int i = 0; i < 8; i++) {
+        unsigned fb = ((reg >> 13) ^ (reg >> 14)) & 1u;
+        reg = ((reg << 1) | fb) & 0x7fff;
+        res = (res << 1) | fb;
+      }
+      return (uint8_t)res;
+    };
+    for (int pk = 0; pk < 8; pk++) {
+      tab[pk * 188] = 0;
+      for (int k = 1; k < 188; k++) tab[pk * 188 + k] = clock8();
+      clock8();
+    }
+    cudaMemcpyToSymbol(c_descr_prbs, tab, 1504);
+  }
+  int dev = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, dev);
+  memset(&h->info, 0, sizeof h->info);
+  *out = h;
+  return 0;
+}
+
+void dvbt_b200_rx_destroy(dvbt_b200_rx *h) {
+  if (!h) return;
+  if (h->stream) cudaStreamSynchronize(h->stream);
+  dvbt::DevBuf *bufs[] = {&h->d_X, &h->d_state, &h->d_fo, &h->d_rot, &h->d_mod, &h->d_tps, &h->d_vote, &h->d_osym, &h->d_osrc, &h->d_dm,
+                          &h->d_Y, &h->d_vit, &h->d_rs, &h->d_rsst, &h->d_ts, &h->d_info, &h->h_state, &h->h_info};
+  for (auto *b : bufs) b->release();
+  for (auto &e : h->ev) if (e) cudaEventDestroy(e);
+  h->tables.release();
+  if (h->vit) dvbt_b200_viterbi_destroy(h->vit);  // owns the stream
+  delete h;
+}
+
+int dvbt_b200_rx_set_rs_compat(dvbt_b200_rx *h, int as_built) {
+  if (!h) { set_error("rx_set_rs_compat: null handle"); return DVBT_B200_EINVAL; }
+  h->rs_as_built = as_built ? 1 : 0;
+  return 0;
+}
+
+// X: nsym post-FFT symbols on the device.  TS goes to d_ts (device) and optionally to a host buffer.
+static int rx_run_freq(dvbt_b200_rx *h, const float2 *dX, size_t nsym, uint8_t *ts_host, uint8_t *ts_dev, size_t ts_capacity,
+                       size_t *ts_bytes, int keep_cells) {
+  const dvbt::ModeDev &md = h->tables.dev;
+  memset(&h->info, 0, sizeof h->info);
+  h->info.first_symbol = -1;
+  h->info.first_packet = -1;
+  if (ts_bytes) *ts_bytes = 0;
+  if (nsym < 2) return 0;
+  size_t nparse = nsym - 1;
+  int rc;
+  if ((rc = h->d_fo.reserve(nparse * 4)) || (rc = h->d_rot.reserve(nparse * 8)) || (rc = h->d_mod.reserve(nparse * 4)) ||
+      (rc = h->d_tps.reserve(nparse * md.ntps * 8)) || (rc = h->d_vote.reserve(nparse * 4)) || (rc = h->d_osym.reserve(nparse * 4)) ||
+      (rc = h->d_osrc.reserve(nparse * 4)) || (rc = h->d_dm.reserve(nparse * md.P)))
+    return rc;
+  if (keep_cells && (rc = h->d_Y.reserve(nparse * md.P * 8))) return rc;
+  cudaStream_t st = h->stream;
+  DVBT_CUDA_TRY(cudaEventRecord(h->ev[0], st));
+  DVBT_CUDA_TRY(cudaMemsetAsync(h->d_state.p, 0, sizeof(dvbt::DemodState), st));
+  dvbt::DemodBuffers b{h->d_fo.as<int>(), h->d_rot.as<float2>(), h->d_mod.as<int>(), h->d_tps.as<float2>(), h->d_vote.as<int>(),
+                       h->d_osym.as<int>(), h->d_osrc.as<int>()};
+  rc = dvbt::demod_run(md, &h->demap, dX, (int)nparse, b, h->d_state.as<dvbt::DemodState>(), h->fi_start, 1,
+                       keep_cells ? h->d_Y.as<float2>() : nullptr, h->d_dm.as<uint8_t>(), st);
+  if (rc) return rc;
+  DVBT_CUDA_TRY(cudaEventRecord(h->ev[1], st));
+  DVBT_CUDA_TRY(cudaMemcpyAsync(h->h_state.p, h->d_state.p, sizeof(dvbt::DemodState), cudaMemcpyDeviceToHost, st));
+  DVBT_CUDA_TRY(cudaStreamSynchronize(st));
+  const dvbt::DemodState *S = h->h_state.as<dvbt::DemodState>();
+  h->last_nparse = (long long)nparse;
+  h->info.symbols_parsed = (long long)nparse;
+  h->info.first_symbol = S->first_out;
+  h->info.symbols_out = S->n_out;
+  if (S->n_out <= 0) return 0;
+  // Viterbi: whole 768-blocks only (viterbi_decoder_impl.cc:198)
+  long long vin_bytes = (long long)S->n_out * md.P;
+  long long nblocks = vin_bytes / h->vit_in_block;
+  long long nbt = nblocks * h->vit_out_block;
+  if (nbt <= h->ntb) return 0;
+  if (nbt >= (1LL << 30)) { set_error("rx_run: batch too large (%lld byte times)", nbt); return DVBT_B200_EINVAL; }
+  uint32_t *codes = dvbt::vit_reserve_codes(h->vit, (size_t)nbt);
+  if (!codes) return DVBT_B200_ENOMEM;
+  InnerMap im{h->d_dm.as<uint8_t>(), h->d_osrc.as<int>(), h->d_osym.as<int>(), md.H, md.Hinv, md.P, h->m, S->n_out};
+  {
+    unsigned grid = (unsigned)((nbt + 255) / 256);
+    switch (h->par.code_rate) {
+      case 0: rx_inner_codes_kernel<0><<<grid, 256, 0, st>>>(im, codes, (int)nbt); break;
+      case 1: rx_inner_codes_kernel<1><<<grid, 256, 0, st>>>(im, codes, (int)nbt); break;
+      case 2: rx_inner_codes_kernel<2><<<grid, 256, 0, st>>>(im, codes, (int)nbt); break;
+      case 3: rx_inner_codes_kernel<3><<<grid, 256, 0, st>>>(im, codes, (int)nbt); break;
+      default: rx_inner_codes_kernel<4><<<grid, 256, 0, st>>>(im, codes, (int)nbt); break;
+    }
+    dvbt::count_launch();
+    DVBT_CUDA_TRY(cudaGetLastError());
+  }
+  DVBT_CUDA_TRY(cudaEventRecord(h->ev[2], st));
+  long long vout = nbt - h->ntb;
+  if ((rc = h->d_vit.reserve((size_t)vout + 16))) return rc;
+  if ((rc = dvbt::vit_decode_prepared(h->vit, (int)nbt, h->d_vit.as<uint8_t>()))) return rc;
+  DVBT_CUDA_TRY(cudaEventRecord(h->ev[3], st));
+  h->info.viterbi_bytes = vout;
+  long long npk = vout / 204;
+  h->info.rs_packets = npk;
+  if (npk <= 0) return dvbt::vit_collect_stats(h->vit);
+  if ((rc = h->d_rs.reserve((size_t)npk * 188)) || (rc = h->d_rsst.reserve((size_t)npk * 4))) return rc;
+  rc = dvbt::rs_launch(h->d_vit.as<uint8_t>(), h->d_rs.as<uint8_t>(), h->d_rsst.as<int>(), npk, h->rs_as_built, h->sm_count, st, vout);
+  if (rc) return rc;
+  DVBT_CUDA_TRY(cudaEventRecord(h->ev[4], st));
+  size_t cap = ts_capacity;
+  uint8_t *ts_out = ts_dev;
+  if (!ts_out) {
+    if ((rc = h->d_ts.reserve((size_t)npk * 188))) return rc;
+    ts_out = h->d_ts.as<uint8_t>();
+    if (cap > (size_t)npk * 188 || ts_host == nullptr) cap = (size_t)npk * 188;
+  }
+  {
+    long long groups = npk / 8 + 1;
+    unsigned grid = (unsigned)(groups < 4096 ? groups : 4096);
+    rx_descramble_kernel<<<grid, 256, 0, st>>>(h->d_rs.as<uint8_t>(), npk, ts_out, (long long)cap, h->d_info.as<DescrInfo>());
+    dvbt::count_launch();
+    DVBT_CUDA_TRY(cudaGetLastError());
+  }
+  DVBT_CUDA_TRY(cudaEventRecord(h->ev[5], st));
+  DVBT_CUDA_TRY(cudaMemcpyAsync(h->h_info.p, h->d_info.p, sizeof(DescrInfo), cudaMemcpyDeviceToHost, st));
+  if ((rc = dvbt::vit_collect_stats(h->vit))) return rc;  // synchronises the stream
+  const DescrInfo *di = h->h_info.as<DescrInfo>();
+  h->info.first_packet = di->p0;
+  h->info.ts_bytes = di->ngroups * 1504;
+  if (ts_host && h->info.ts_bytes > 0) {
+    DVBT_CUDA_TRY(cudaMemcpyAsync(ts_host, ts_out, (size_t)h->info.ts_bytes, cudaMemcpyDeviceToHost, st));
+    DVBT_CUDA_TRY(cudaStreamSynchronize(st));
+  }
+  if (ts_bytes) *ts_bytes = (size_t)h->info.ts_bytes;
+  float ms;
+  const int pairs[5][2] = {{0, 1}, {1, 2}, {2, 3}, {3, 4}, {4, 5}};
+  float *dst[5] = {&h->info.ms_demod, &h->info.ms_inner, &h->info.ms_viterbi, &h->info.ms_rs, &h->info.ms_descramble};
+  for (int i = 0; i < 5; i++)
+    if (cudaEventElapsedTime(&ms, h->ev[pairs[i][0]], h->ev[pairs[i][1]]) == cudaSuccess) *dst[i] = ms;
+  long long chunks = 0, rep = 0;
+  float acs = 0;
+  dvbt_b200_viterbi_last_stats(h->vit, &chunks, &rep, &acs);
+  h->info.ms_viterbi_acs = acs;
+  h->info.viterbi_repaired = rep;
+  return 0;
+}
+
+int dvbt_b200_rx_run_freq_host(dvbt_b200_rx *h, const void *X, size_t nsym, uint8_t *ts, size_t ts_capacity, size_t *ts_bytes) {
+  if (!h || (nsym && !X) || !ts) { set_error("rx_run_freq_host: bad argument"); return DVBT_B200_EINVAL; }
+  const dvbt::ModeDev &md = h->tables.dev;
+  int rc = h->d_X.reserve(nsym * md.N * 8);
+  if (rc) return rc;
+  DVBT_CUDA_TRY(cudaMemcpyAsync(h->d_X.p, X, nsym * md.N * 8, cudaMemcpyHostToDevice, h->stream));
+  return rx_run_freq(h, h->d_X.as<float2>(), nsym, ts, nullptr, ts_capacity, ts_bytes, 1);
+}
+
+int dvbt_b200_rx_run_freq_dev(dvbt_b200_rx *h, const void *dX, size_t nsym, uint8_t *d_ts, size_t ts_capacity, size_t *ts_bytes) {
+  if (!h || (nsym && !dX) || !d_ts) { set_error("rx_run_freq_dev: bad argument"); return DVBT_B200_EINVAL; }
+  return rx_run_freq(h, (const float2 *)dX, nsym, nullptr, d_ts, ts_capacity, ts_bytes, 0);
+}
+
+int dvbt_b200_rx_last_info(const dvbt_b200_rx *h, dvbt_b200_rx_info *info) {
+  if (!h || !info) { set_error("rx_last_info: null argument"); return DVBT_B200_EINVAL; }
+  *info = h->info;
+  return 0;
+}
+
+// stage taps of the last run, for stage-by-stage parity tests
+int dvbt_b200_rx_read_stage(dvbt_b200_rx *h, int stage, void *host_out, size_t capacity_bytes, size_t *nbytes) {
+  if (!h || !host_out || !nbytes) { set_error("rx_read_stage: null argument"); return DVBT_B200_EINVAL; }
+  const dvbt::ModeDev &md = h->tables.dev;
+  *nbytes = 0;
+  const void *src = nullptr;
+  size_t n = 0;
+  dvbt::DevBuf tmp;
+  long long nout = h->info.symbols_out, first = h->info.first_symbol;
+  switch (stage) {
+    case DVBT_RX_STAGE_CELLS:  // equalised cells of the output symbols (contiguous when no resync happened)
+      if (nout > 0 && h->d_Y.p) { src = h->d_Y.as<float2>() + first * md.P; n = (size_t)nout * md.P * 8; }
+      break;
+    case DVBT_RX_STAGE_DEMAP:
+      if (nout > 0) { src = h->d_dm.as<uint8_t>() + first * md.P; n = (size_t)nout * md.P; }
+      break;
+    case DVBT_RX_STAGE_BITDEINT: {
+      if (nout <= 0) break;
+      n = (size_t)nout * md.P;
+      int rc = tmp.reserve(n);
+      if (rc) return rc;
+      InnerMap im{h->d_dm.as<uint8_t>(), h->d_osrc.as<int>(), h->d_osym.as<int>(), md.H, md.Hinv, md.P, h->m, (int)nout};
+      rx_inner_bytes_kernel<<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>(im, tmp.as<uint8_t>(), (long long)n);
+      dvbt::count_launch();
+      DVBT_CUDA_TRY(cudaGetLastError());
+      src = tmp.p;
+      break;
+    }
+    case DVBT_RX_STAGE_VITERBI: src = h->d_vit.p; n = (size_t)h->info.viterbi_bytes; break;
+    case DVBT_RX_STAGE_RS: src = h->d_rs.p; n = (size_t)h->info.rs_packets * 188; break;
+    case DVBT_RX_STAGE_RS_STATUS: src = h->d_rsst.p; n = (size_t)h->info.rs_packets * 4; break;
+    case DVBT_RX_STAGE_SYMBOL_INDEX: src = h->d_osym.p; n = (size_t)(nout > 0 ? nout : 0) * 4; break;
+    default: set_error("rx_read_stage: unknown stage %d", stage); return DVBT_B200_EINVAL;
+  }
+  if (n > capacity_bytes) { tmp.release(); set_error("rx_read_stage: need %zu bytes, capacity %zu", n, capacity_bytes); return DVBT_B200_ENOSPC; }
+  if (n && src) {
+    cudaError_t e = cudaMemcpyAsync(host_out, src, n, cudaMemcpyDeviceToHost, h->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+    if (e != cudaSuccess) { tmp.release(); set_error("rx_read_stage: %s", cudaGetErrorString(e)); return DVBT_B200_ECUDA; }
+    *nbytes = n;
+  }
+  tmp.release();
+  return 0;
+}
+
+}  // extern "C"

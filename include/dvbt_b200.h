@@ -208,6 +208,46 @@ int dvbt_b200_demod_work(dvbt_b200_demod *h, const void *in, size_t n_in_items, 
                          const dvbt_b200_tag *tags_in, size_t n_tags_in, dvbt_b200_tag *tags_out,
                          size_t tags_out_capacity, size_t *n_tags_out);
 
+/* ------------------------------------------------------------------------------------
+ * Fused receive chain (device resident).  One call = what the RX flowgraph
+ * apps/dvbt_rx_demo*.grc does to a capture, from the FFT output onwards:
+ *   demod_reference_signals -> dvbt_demap -> symbol_inner_interleaver(deinterleave) ->
+ *   bit_inner_deinterleaver -> viterbi_decoder -> convolutional_deinterleaver(136,12,17) ->
+ *   reed_solomon_dec -> energy_descramble
+ * with the tags (sync_start at the first symbol, symbol_index, superframe_start) carried as
+ * batch metadata.  The TS written is every complete 8-packet group from the first NSYNC packet
+ * on; the reference flowgraph writes a scheduler-dependent prefix of the same bytes
+ * (energy_descramble_impl.cc:140-141 holds back two groups).
+ * ------------------------------------------------------------------------------------ */
+typedef struct dvbt_b200_rx dvbt_b200_rx;
+typedef struct dvbt_b200_rx_params {
+  int constellation, hierarchy, code_rate, guard_interval, transmission_mode;
+} dvbt_b200_rx_params;
+typedef struct dvbt_b200_rx_info {
+  long long symbols_parsed; /* OFDM symbols run through parse_input */
+  long long first_symbol;   /* batch index of the first symbol output by demod (superframe start), -1 */
+  long long symbols_out;
+  long long viterbi_bytes;  /* decoded bytes */
+  long long viterbi_repaired; /* chunks whose boundary state had to be re-decoded */
+  long long rs_packets;
+  long long first_packet;   /* RS packet index where the descrambler locked (NSYNC), -1 */
+  long long ts_bytes;
+  float ms_demod, ms_inner, ms_viterbi, ms_viterbi_acs, ms_rs, ms_descramble; /* device time per stage */
+} dvbt_b200_rx_info;
+enum { DVBT_RX_STAGE_CELLS = 0, DVBT_RX_STAGE_DEMAP = 1, DVBT_RX_STAGE_BITDEINT = 2, DVBT_RX_STAGE_VITERBI = 3,
+       DVBT_RX_STAGE_RS = 4, DVBT_RX_STAGE_RS_STATUS = 5, DVBT_RX_STAGE_SYMBOL_INDEX = 6 };
+
+int dvbt_b200_rx_create(const dvbt_b200_rx_params *p, dvbt_b200_rx **out);
+void dvbt_b200_rx_destroy(dvbt_b200_rx *h);
+int dvbt_b200_rx_set_rs_compat(dvbt_b200_rx *h, int as_built); /* see dvbt_b200_rsdec_set_compat */
+/* nsym post-FFT symbols (N gr_complex each, DC at bin N/2).  _host: X and ts are host buffers;
+ * _dev: device pointers.  *ts_bytes receives the TS bytes written (multiple of 1504). */
+int dvbt_b200_rx_run_freq_host(dvbt_b200_rx *h, const void *X, size_t nsym, uint8_t *ts, size_t ts_capacity, size_t *ts_bytes);
+int dvbt_b200_rx_run_freq_dev(dvbt_b200_rx *h, const void *dX, size_t nsym, uint8_t *d_ts, size_t ts_capacity, size_t *ts_bytes);
+int dvbt_b200_rx_last_info(const dvbt_b200_rx *h, dvbt_b200_rx_info *info);
+/* copies an intermediate of the last run to the host (parity tests): DVBT_RX_STAGE_* */
+int dvbt_b200_rx_read_stage(dvbt_b200_rx *h, int stage, void *host_out, size_t capacity_bytes, size_t *nbytes);
+
 #ifdef __cplusplus
 }
 #endif
