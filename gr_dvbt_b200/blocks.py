@@ -11,7 +11,7 @@ import numpy as np
 from . import capi
 from .capi import check, lib
 
-__all__ = ["viterbi_decoder", "reed_solomon_dec", "dvbt_demap", "demod_reference_signals", "rx_chain", "QPSK", "QAM16", "QAM64", "NH", "C1_2", "C2_3", "C3_4", "C5_6", "C7_8", "T2k", "T8k", "G1_32"]
+__all__ = ["viterbi_decoder", "reed_solomon_dec", "dvbt_demap", "demod_reference_signals", "rx_chain", "ofdm_sym_acquisition", "QPSK", "QAM16", "QAM64", "NH", "C1_2", "C2_3", "C3_4", "C5_6", "C7_8", "T2k", "T8k", "G1_32"]
 
 QPSK, QAM16, QAM64 = 0, 1, 2
 NH = 0
@@ -226,6 +226,20 @@ class rx_chain(_Handle):
         check(lib().dvbt_b200_rx_run_freq_host(self._h, X.ctypes.data, X.shape[0], ts.ctypes.data, cap, C.byref(n)))
         return ts[: n.value].copy()
 
+    def run_baseband(self, samples):
+        """samples: complex64 host array at the OFDM sample rate -> TS bytes."""
+        x = np.ascontiguousarray(samples, np.complex64).reshape(-1)
+        cap = len(x) + 4096
+        ts = np.zeros(cap, np.uint8)
+        n = C.c_size_t(0)
+        check(lib().dvbt_b200_rx_run_baseband_host(self._h, x.ctypes.data, len(x), ts.ctypes.data, cap, C.byref(n)))
+        return ts[: n.value].copy()
+
+    def run_baseband_dev(self, d_x, nsamples, d_ts, ts_capacity):
+        n = C.c_size_t(0)
+        check(lib().dvbt_b200_rx_run_baseband_dev(self._h, _addr(d_x), nsamples, _addr(d_ts), ts_capacity, C.byref(n)))
+        return int(n.value)
+
     def run_freq_dev(self, d_X, nsym, d_ts, ts_capacity):
         n = C.c_size_t(0)
         check(lib().dvbt_b200_rx_run_freq_dev(self._h, _addr(d_X), nsym, _addr(d_ts), ts_capacity, C.byref(n)))
@@ -244,3 +258,27 @@ class rx_chain(_Handle):
         n = C.c_size_t(0)
         check(lib().dvbt_b200_rx_read_stage(self._h, sid, buf.ctypes.data, cap, C.byref(n)))
         return buf[: n.value].view(dt).copy()
+
+
+class ofdm_sym_acquisition(_Handle):
+    """dvbt.ofdm_sym_acquisition(blocks, fft_length, occupied_tones, cp_length, snr) (include/dvbt/ofdm_sym_acquisition.h:49)."""
+    _destroy = "dvbt_b200_acq_destroy"
+
+    def __init__(self, blocks, fft_length, occupied_tones, cp_length, snr):
+        self._h = C.c_void_p()
+        par = capi.AcqParams(blocks, fft_length, occupied_tones, cp_length, snr)
+        check(lib().dvbt_b200_acq_create(C.byref(par), C.byref(self._h)))
+        self.N, self.cp = fft_length, cp_length
+
+    def general_work(self, samples, out_capacity=None, apply_fft=False):
+        """samples: complex64 host array.  Returns (symbols (nout, N), consumed, out_tags)."""
+        x = np.ascontiguousarray(samples, np.complex64).reshape(-1)
+        cap = out_capacity if out_capacity is not None else len(x) // (self.N + self.cp) + 1
+        out = np.zeros((cap, self.N), np.complex64)
+        tout = (capi.Tag * 4)()
+        ntout = C.c_size_t(0)
+        cons, prod = C.c_size_t(0), C.c_size_t(0)
+        check(lib().dvbt_b200_acq_work(self._h, x.ctypes.data, len(x), out.ctypes.data, cap, C.byref(cons), C.byref(prod),
+                                       tout, 4, C.byref(ntout), int(apply_fft)))
+        otags = [(int(tout[i].offset), capi.TAG_NAMES[tout[i].key], int(tout[i].value)) for i in range(ntout.value)]
+        return out[: prod.value].copy(), int(cons.value), otags

@@ -45,8 +45,12 @@ class RxParams(C.Structure):
 
 class RxInfo(C.Structure):
     _fields_ = [(n, C.c_longlong) for n in ("symbols_parsed", "first_symbol", "symbols_out", "viterbi_bytes", "viterbi_repaired",
-                                             "rs_packets", "first_packet", "ts_bytes")] + \
-               [(n, C.c_float) for n in ("ms_demod", "ms_inner", "ms_viterbi", "ms_viterbi_acs", "ms_rs", "ms_descramble")]
+                                             "rs_packets", "first_packet", "ts_bytes", "acq_symbols", "acq_cp_start", "acq_lost_at")] + \
+               [(n, C.c_float) for n in ("ms_acq_fft", "ms_demod", "ms_inner", "ms_viterbi", "ms_viterbi_acs", "ms_rs", "ms_descramble")]
+
+
+class AcqParams(C.Structure):
+    _fields_ = [("blocks", C.c_int), ("fft_length", C.c_int), ("occupied_tones", C.c_int), ("cp_length", C.c_int), ("snr", C.c_float)]
 
 
 class ViterbiTuning(C.Structure):
@@ -101,6 +105,12 @@ def lib():
         L.dvbt_b200_rx_run_freq_dev.argtypes = [vp, vp, C.c_size_t, vp, C.c_size_t, C.POINTER(C.c_size_t)]
         L.dvbt_b200_rx_last_info.argtypes = [vp, C.POINTER(RxInfo)]
         L.dvbt_b200_rx_read_stage.argtypes = [vp, C.c_int, vp, C.c_size_t, C.POINTER(C.c_size_t)]
+        L.dvbt_b200_acq_create.argtypes = [C.POINTER(AcqParams), C.POINTER(vp)]
+        L.dvbt_b200_acq_destroy.argtypes = [vp]
+        L.dvbt_b200_acq_work.argtypes = [vp, vp, C.c_size_t, vp, C.c_size_t, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t),
+                                         C.POINTER(Tag), C.c_size_t, C.POINTER(C.c_size_t), C.c_int]
+        L.dvbt_b200_rx_run_baseband_host.argtypes = [vp, vp, C.c_size_t, vp, C.c_size_t, C.POINTER(C.c_size_t)]
+        L.dvbt_b200_rx_run_baseband_dev.argtypes = [vp, vp, C.c_size_t, vp, C.c_size_t, C.POINTER(C.c_size_t)]
         _lib = L
     return _lib
 

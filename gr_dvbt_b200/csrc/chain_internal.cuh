@@ -15,4 +15,15 @@ int vit_collect_stats(dvbt_b200_viterbi *h);
 // is applied while loading; -1: d_in holds packed 204-byte packets
 int rs_launch(const uint8_t *d_in, uint8_t *d_out, int *d_status, long long npackets, int as_built, int sm_count,
               cudaStream_t st, long long gather_stream_bytes);
+
+struct AcqResult { long long consumed; int n_out, lost_at, fallback, cp_start; };
+}  // namespace dvbt
+struct dvbt_b200_acq;
+namespace dvbt {
+void acq_use_stream(dvbt_b200_acq *h, cudaStream_t st);
+int acq_reset(dvbt_b200_acq *h);
+// samples x[0..n) on the device -> up to out_capacity_syms symbols of N complex at d_out
+// (FFT applied, DC at bin N/2, when do_fft)
+int acq_run_simple(dvbt_b200_acq *h, const float2 *x, long long n, float2 *d_out, long long out_capacity_syms, int do_fft,
+                   AcqResult *res);
 }  // namespace dvbt

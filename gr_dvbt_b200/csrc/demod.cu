@@ -285,7 +285,7 @@ __global__ void __launch_bounds__(256) demod_equalise_kernel(ModeDev md, const _
                                                              const float2 *__restrict__ rot_in, const int *__restrict__ mod_in,
                                                              float2 *__restrict__ tpsval, float2 *__restrict__ Y,
                                                              uint8_t *__restrict__ dm) {
-  extern __shared__ float2 s_gain[];  // [K]
+  extern __shared__ float2 s_gain[];  // [K] gains, then [K] interval slopes
   const int s = blockIdx.x;
   const int fo = fo_in[s];
   const float2 rot = rot_in[s];
@@ -298,15 +298,19 @@ __global__ void __launch_bounds__(256) demod_equalise_kernel(ModeDev md, const _
     if (kind[k] & 1) s_gain[k] = cdiv(make_float2(md.pval[k], 0.f), cmul(rot, x[k]));
   }
   __syncthreads();
-  // linear interpolation with the reference's fixed /11 slope (:617-642)
+  // linear interpolation with the reference's fixed /11 slope (:617-642): the slope of an interval
+  // is computed once, by the thread that owns the pilot at its left end
   const short *prevp = md.prevp + r * md.K, *nextp = md.nextp + r * md.K;
+  float2 *s_slope = s_gain + md.K;
+  for (int k = threadIdx.x; k < md.K; k += blockDim.x) {
+    if (kind[k] & 1) s_slope[k] = cdiv(csub(s_gain[nextp[k]], s_gain[k]), make_float2(11.0f, 0.0f));
+  }
+  __syncthreads();
   for (int k = threadIdx.x; k < md.K; k += blockDim.x) {
     if (!(kind[k] & 1)) {
-      int k0 = prevp[k], k1 = nextp[k];
-      float2 g0 = s_gain[k0];
-      float2 tg = cdiv(csub(s_gain[k1], g0), make_float2(11.0f, 0.0f));
-      float2 step = cmul(tg, make_float2((float)(k - k0), 0.0f));
-      s_gain[k] = cadd(g0, step);
+      int k0 = prevp[k];
+      float2 step = cmul(s_slope[k0], make_float2((float)(k - k0), 0.0f));
+      s_gain[k] = cadd(s_gain[k0], step);
     }
   }
   __syncthreads();
@@ -338,80 +342,111 @@ __global__ void demod_vote_kernel(int ntps, int nparse, const float2 *__restrict
   vote[s] = v;
 }
 
-// BCH(127,113) shortened to (67,53): verify_bch_code (:384-425)
-__device__ bool tps_bch_ok(const unsigned char *f) {
+// BCH(127,113) shortened to (67,53): verify_bch_code (:384-425), on the bit-packed FIFO
+// The sequential bookkeeping of parse_input (:1188-1248) and of the block (:108-149).  One warp:
+// the lanes fetch 32 symbols' (phase, vote) with one coalesced load each, then every lane runs
+// the same state machine on shuffled values (no divergence); lane 0 writes the results.  The
+// 68-entry TPS FIFO (d_rcv_tps_data) is a bit set: entry i = bit i of (lo, hi).
+__device__ bool tps_bch_ok_bits(unsigned long long lo, unsigned hi) {
+  auto bit = [&](int i) -> unsigned { return i < 64 ? (unsigned)((lo >> i) & 1ull) : ((hi >> (i - 64)) & 1u); };
   unsigned reg = 0;
   for (int i = 0; i < 113; i++) {
-    unsigned bit = i < 60 ? 0u : f[1 + (i - 60)];
-    unsigned fb = 1u & (bit ^ reg);
+    unsigned b = i < 60 ? 0u : bit(1 + (i - 60));
+    unsigned fb = 1u & (b ^ reg);
     reg >>= 1;
     reg |= fb << 13;
     reg ^= (fb << 12) ^ (fb << 11) ^ (fb << 9) ^ (fb << 8) ^ (fb << 7) ^ (fb << 5) ^ (fb << 4);
   }
   for (int i = 0; i < 14; i++)
-    if (f[i + 54] != (1u & (reg >> i))) return false;
+    if (bit(i + 54) != (1u & (reg >> i))) return false;
   return true;
 }
 
-// The sequential bookkeeping of parse_input (:1188-1248) and of the block (:108-149).
-__global__ void demod_scan_kernel(int ntps, int nparse, int fi_start, int sync_start_at0, const int *__restrict__ mod_in,
-                                  const int *__restrict__ vote, const float2 *__restrict__ tpsval, DemodState *st,
-                                  int *__restrict__ out_symidx, int *__restrict__ out_src) {
-  if (blockIdx.x != 0 || threadIdx.x != 0) return;
-  static const unsigned char sync_even[16] = {0, 0, 1, 1, 0, 1, 0, 1, 1, 1, 1, 0, 1, 1, 1, 0};
-  DemodState S = *st;
-  S.first_out = -1;
-  S.n_out = 0;
-  S.sf_tag_at = -1;
-  if (sync_start_at0) S.d_init = 0;  // :115-116
-  for (int s = 0; s < nparse; s++) {
-    int mod = mod_in[s] >= 0 ? mod_in[s] : S.mod;
-    S.mod = mod;
-    int diff = (mod - S.prev_mod + 4) % 4;  // :684-688
-    S.prev_mod = mod;
-    S.symbol_index = (S.symbol_index + diff) % 68;  // :1228
-    int sym_out = S.symbol_index, frame_out = S.frame_index;
-    // process_tps_data
-    bool cond = !S.known || S.symbol_index != 0;
-    for (int i = 0; i < diff; i++) {  // :957-972
-      for (int b = 0; b < 67; b++) S.fifo[b] = S.fifo[b + 1];
-      S.fifo[67] = cond ? (vote[s] >= 0 ? 0 : 1) : 0;
-    }
-    // std::equal(begin+1, begin+16, sync.begin()): 15 elements (:975, :1002)
-    bool even = true, odd = true;
-    for (int i = 0; i < 15; i++) {
-      if (S.fifo[1 + i] != sync_even[i]) even = false;
-      if (S.fifo[1 + i] != (1 - sync_even[i])) odd = false;
-    }
-    int end_frame = 0;
-    if (even || odd) {
-      if (tps_bch_ok(S.fifo)) {
-        S.frame_index = (S.fifo[23] << 1) | S.fifo[24];
-        S.known = 1;
-        end_frame = 1;
-      } else {
-        S.known = 0;
+__global__ void __launch_bounds__(32) demod_scan_kernel(int ntps, int nparse, int fi_start, int sync_start_at0,
+                                                        const int *__restrict__ mod_in, const int *__restrict__ vote,
+                                                        const float2 *__restrict__ tpsval, DemodState *st,
+                                                        int *__restrict__ out_symidx, int *__restrict__ out_src) {
+  const int lane = threadIdx.x;
+  // sync words of :121-126 as FIFO entries 1..15 (std::equal compares 15 elements, :975/:1002)
+  // even: 0,0,1,1,0,1,0,1,1,1,1,0,1,1,1 -> entry i+1 = value
+  const unsigned long long kEven = (0ull << 1) | (0ull << 2) | (1ull << 3) | (1ull << 4) | (0ull << 5) | (1ull << 6) | (0ull << 7) |
+                                   (1ull << 8) | (1ull << 9) | (1ull << 10) | (1ull << 11) | (0ull << 12) | (1ull << 13) |
+                                   (1ull << 14) | (1ull << 15);
+  const unsigned long long kMask = 0xFFFEull;
+  int symbol_index = st->symbol_index, known = st->known, frame_index = st->frame_index, prev_mod = st->prev_mod,
+      cur_mod = st->mod, d_init = st->d_init;
+  unsigned long long lo = 0;
+  unsigned hi = 0;
+  for (int i = 0; i < 64; i++) lo |= (unsigned long long)(st->fifo[i] & 1) << i;
+  for (int i = 64; i < 68; i++) hi |= (unsigned)(st->fifo[i] & 1) << (i - 64);
+  int first_out = -1, n_out = 0, sf_tag_at = -1;
+  if (sync_start_at0) d_init = 0;  // :115-116
+  for (int base = 0; base < nparse; base += 32) {
+    int s_l = base + lane;
+    int my_mod = s_l < nparse ? mod_in[s_l] : 0;
+    int my_vote = s_l < nparse ? vote[s_l] : 0;
+    int cnt = min(32, nparse - base);
+    int my_sym = 0, my_emit = 0;
+    for (int i = 0; i < cnt; i++) {
+      int m_in = __shfl_sync(0xffffffffu, my_mod, i);
+      int v_in = __shfl_sync(0xffffffffu, my_vote, i);
+      int mod = m_in >= 0 ? m_in : cur_mod;
+      cur_mod = mod;
+      int diff = (mod - prev_mod + 4) & 3;  // :684-688
+      prev_mod = mod;
+      symbol_index += diff;                 // :1228
+      if (symbol_index >= 68) symbol_index -= 68;
+      int sym_out = symbol_index, frame_out = frame_index;
+      bool cond = !known || symbol_index != 0;
+      unsigned long long bitv = cond ? (v_in >= 0 ? 0ull : 1ull) : 0ull;
+      for (int d = 0; d < diff; d++) {      // :957-972: pop front, push back
+        lo = (lo >> 1) | ((unsigned long long)(hi & 1u) << 63);
+        hi = (hi >> 1) | ((unsigned)bitv << 3);
       }
-      for (int b = 0; b < 68; b++) S.fifo[b] = 0;
-    }
-    if (end_frame) S.symbol_index = 67;  // :1240-1241
-    // block level (demod_reference_signals_impl.cc:118-143)
-    if (S.d_init == 0) {
-      if ((sym_out % 68) == 0 && (frame_out % 4) == fi_start) {
-        S.d_init = 1;
-        S.sf_tag_at = S.n_out;
-      } else {
-        continue;
+      bool even = (lo & kMask) == kEven, odd = (lo & kMask) == (kEven ^ kMask);
+      int end_frame = 0;
+      if (even || odd) {
+        if (tps_bch_ok_bits(lo, hi)) {
+          frame_index = (int)(((lo >> 23) & 1ull) << 1 | ((lo >> 24) & 1ull));
+          known = 1;
+          end_frame = 1;
+        } else {
+          known = 0;
+        }
+        lo = 0;
+        hi = 0;
+      }
+      if (end_frame) symbol_index = 67;     // :1240-1241
+      // block level (demod_reference_signals_impl.cc:118-143)
+      bool emit = true;
+      if (d_init == 0) {
+        if (sym_out == 0 && (frame_out & 3) == fi_start) {
+          d_init = 1;
+          sf_tag_at = n_out;
+        } else {
+          emit = false;
+        }
+      }
+      if (emit) {
+        if (first_out < 0) first_out = base + i;
+        if (lane == i) { my_sym = sym_out; my_emit = n_out + 1; }
+        n_out++;
       }
     }
-    if (S.first_out < 0) S.first_out = s;
-    out_symidx[S.n_out] = sym_out;
-    out_src[S.n_out] = s;
-    S.n_out++;
+    if (my_emit) {
+      out_symidx[my_emit - 1] = my_sym;
+      out_src[my_emit - 1] = s_l;
+    }
+  }
+  if (lane == 0) {
+    st->symbol_index = symbol_index; st->known = known; st->frame_index = frame_index; st->prev_mod = prev_mod;
+    st->mod = cur_mod; st->d_init = d_init;
+    for (int i = 0; i < 64; i++) st->fifo[i] = (unsigned char)((lo >> i) & 1ull);
+    for (int i = 64; i < 68; i++) st->fifo[i] = (unsigned char)((hi >> (i - 64)) & 1u);
+    st->first_out = first_out; st->n_out = n_out; st->sf_tag_at = sf_tag_at;
   }
   if (nparse > 0)
-    for (int k = 0; k < ntps; k++) S.prev_tps[k] = tpsval[(long long)(nparse - 1) * ntps + k];
-  *st = S;
+    for (int k = lane; k < ntps; k += 32) st->prev_tps[k] = tpsval[(long long)(nparse - 1) * ntps + k];
 }
 
 int demod_run(const ModeDev &md, const DemapTable *demap, const float2 *X, int nparse, DemodBuffers b, DemodState *d_state,
@@ -424,10 +459,10 @@ int demod_run(const ModeDev &md, const DemapTable *demap, const float2 *X, int n
     DVBT_CUDA_TRY(cudaGetLastError());
   }
   {
-    size_t smem = (size_t)md.K * sizeof(float2);
+    size_t smem = (size_t)md.K * sizeof(float2) * 2;
     static bool attr_set = false;
     if (!attr_set) {
-      DVBT_CUDA_TRY(cudaFuncSetAttribute(demod_equalise_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+      DVBT_CUDA_TRY(cudaFuncSetAttribute(demod_equalise_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
       attr_set = true;
     }
     DemapTable dummy;

@@ -59,8 +59,49 @@ __host__ __device__ constexpr int rate_k(int r) { return r == 0 ? 1 : r == 1 ? 2
 __host__ __device__ constexpr unsigned rate_px(int r) { return r == 0 ? 0x1u : r == 1 ? 0x1u : r == 2 ? 0x5u : r == 3 ? 0x15u : 0x51u; }
 __host__ __device__ constexpr unsigned rate_py(int r) { return r == 0 ? 0x1u : r == 1 ? 0x3u : r == 2 ? 0x3u : r == 3 ? 0x0bu : 0x2fu; }
 
+// Walks consecutive bits of the Viterbi input stream without re-dividing for every bit.
+struct InnerCursor {
+  int sym, blk126, ii, kbit;   // cell = sym*P + blk126 + ii, bit kbit (0 = MSB) of that cell
+  const uint8_t *cells;        // dm row of the current symbol
+  const short *perm;           // H or Hinv for the current symbol
+  __device__ __forceinline__ void load_symbol(const InnerMap &im) {
+    if (sym < im.n_out) {
+      cells = im.dm + (long long)im.out_src[sym] * im.P;
+      perm = (im.out_symidx[sym] & 1) ? im.Hinv : im.H;
+    }
+  }
+  __device__ __forceinline__ void seek(const InnerMap &im, long long tbit) {
+    long long b = tbit / im.m;
+    kbit = (int)(tbit - b * im.m);
+    sym = (int)(b / im.P);
+    int i = (int)(b - (long long)sym * im.P);
+    int blk = i / 126;
+    blk126 = blk * 126;
+    ii = i - blk126;
+    load_symbol(im);
+  }
+  __device__ __forceinline__ uint32_t next(const InnerMap &im) {
+    int half = im.m >> 1;
+    int e = (kbit >= half) ? 1 + 2 * (kbit - half) : 2 * kbit;  // kbit/half + 2*(kbit%half)
+    int off = (0x54152A693F00ull >> (8 * e)) & 0xff;            // {0,63,105,42,21,84}[e]
+    int w = ii - off;
+    if (w < 0) w += 126;
+    uint32_t cell = cells[perm[blk126 + w]];
+    uint32_t bit = (cell >> (im.m - 1 - e)) & 1u;
+    if (++kbit == im.m) {
+      kbit = 0;
+      if (++ii == 126) {
+        ii = 0;
+        blk126 += 126;
+        if (blk126 == im.P) { blk126 = 0; sym++; load_symbol(im); }
+      }
+    }
+    return bit;
+  }
+};
+
 template <int RATE>
-__global__ void rx_inner_codes_kernel(InnerMap im, uint32_t *__restrict__ codes, int nbt) {
+__global__ void __launch_bounds__(256) rx_inner_codes_kernel(InnerMap im, uint32_t *__restrict__ codes, int nbt) {
   constexpr int K = rate_k(RATE), N = K + 1;
   constexpr unsigned PX = rate_px(RATE), PY = rate_py(RATE);
   int j = blockIdx.x * blockDim.x + threadIdx.x;
@@ -69,12 +110,14 @@ __global__ void rx_inner_codes_kernel(InnerMap im, uint32_t *__restrict__ codes,
   long long sp = t / K;
   int ph = (int)(t - sp * K);
   long long idx = sp * N + __popc(PX & ((1u << ph) - 1u)) + __popc(PY & ((1u << ph) - 1u));
+  InnerCursor cur;
+  cur.seek(im, idx);
   uint32_t w = 0;
 #pragma unroll
   for (int i = 0; i < 8; i++) {
     uint32_t nib = 0;
-    if ((PX >> ph) & 1u) { nib |= inner_bit(im, idx) | 2u; idx++; }
-    if ((PY >> ph) & 1u) { nib |= (inner_bit(im, idx) << 2) | 8u; idx++; }
+    if ((PX >> ph) & 1u) nib |= cur.next(im) | 2u;
+    if ((PY >> ph) & 1u) nib |= (cur.next(im) << 2) | 8u;
     w |= nib << (4 * i);
     ph = (ph + 1 == K) ? 0 : ph + 1;
   }
@@ -129,6 +172,8 @@ struct dvbt_b200_rx {
   dvbt::ModeTables tables;
   dvbt::DemapTable demap;
   dvbt_b200_viterbi *vit = nullptr;
+  dvbt_b200_acq *acq = nullptr;
+  dvbt::DevBuf d_samples, d_sym;
   cudaStream_t stream = nullptr;
   int fi_start = 3, rs_as_built = 0, sm_count = 148;
   int k = 1, n = 2, m = 4, ntb = 5, vit_in_block = 0, vit_out_block = 0;
@@ -160,6 +205,12 @@ int dvbt_b200_rx_create(const dvbt_b200_rx_params *p, dvbt_b200_rx **out) {
   }
   if (rc) { dvbt_b200_rx_destroy(h); return rc; }
   h->stream = dvbt::vit_stream(h->vit);
+  {
+    dvbt_b200_acq_params ap{1, h->tables.dev.N, h->tables.dev.K, h->tables.dev.cp, 30.0f};
+    rc = dvbt_b200_acq_create(&ap, &h->acq);
+    if (rc) { dvbt_b200_rx_destroy(h); return rc; }
+    dvbt::acq_use_stream(h->acq, h->stream);
+  }
   dvbt::vit_params(h->vit, &h->k, &h->n, &h->m, &h->ntb, &h->vit_in_block, &h->vit_out_block);
   h->fi_start = (p->constellation == DVBT_QAM64 && p->transmission_mode == DVBT_T8K) ? 2 : 3;
   h->h_state.host = h->h_info.host = true;
@@ -206,6 +257,9 @@ void dvbt_b200_rx_destroy(dvbt_b200_rx *h) {
   for (auto *b : bufs) b->release();
   for (auto &e : h->ev) if (e) cudaEventDestroy(e);
   h->tables.release();
+  h->d_samples.release();
+  h->d_sym.release();
+  if (h->acq) dvbt_b200_acq_destroy(h->acq);
   if (h->vit) dvbt_b200_viterbi_destroy(h->vit);  // owns the stream
   delete h;
 }
@@ -333,6 +387,41 @@ int dvbt_b200_rx_run_freq_host(dvbt_b200_rx *h, const void *X, size_t nsym, uint
 int dvbt_b200_rx_run_freq_dev(dvbt_b200_rx *h, const void *dX, size_t nsym, uint8_t *d_ts, size_t ts_capacity, size_t *ts_bytes) {
   if (!h || (nsym && !dX) || !d_ts) { set_error("rx_run_freq_dev: bad argument"); return DVBT_B200_EINVAL; }
   return rx_run_freq(h, (const float2 *)dX, nsym, nullptr, d_ts, ts_capacity, ts_bytes, 0);
+}
+
+static int rx_run_baseband(dvbt_b200_rx *h, const float2 *d_x, size_t nsamples, uint8_t *ts_host, uint8_t *ts_dev, size_t ts_capacity,
+                           size_t *ts_bytes, int keep_cells) {
+  const dvbt::ModeDev &md = h->tables.dev;
+  if (ts_bytes) *ts_bytes = 0;
+  long long cap_syms = (long long)(nsamples / (size_t)(md.N + md.cp)) + 2;
+  int rc = h->d_sym.reserve((size_t)cap_syms * md.N * 8);
+  if (rc) return rc;
+  DVBT_CUDA_TRY(cudaEventRecord(h->ev[6], h->stream));
+  if ((rc = dvbt::acq_reset(h->acq))) return rc;
+  dvbt::AcqResult ar;
+  rc = dvbt::acq_run_simple(h->acq, d_x, (long long)nsamples, h->d_sym.as<float2>(), cap_syms, 1, &ar);
+  if (rc) return rc;
+  DVBT_CUDA_TRY(cudaEventRecord(h->ev[7], h->stream));
+  rc = rx_run_freq(h, h->d_sym.as<float2>(), (size_t)ar.n_out, ts_host, ts_dev, ts_capacity, ts_bytes, keep_cells);
+  h->info.acq_symbols = ar.n_out;
+  h->info.acq_cp_start = ar.cp_start;
+  h->info.acq_lost_at = ar.lost_at;
+  float ms;
+  if (cudaEventElapsedTime(&ms, h->ev[6], h->ev[7]) == cudaSuccess) h->info.ms_acq_fft = ms;
+  return rc;
+}
+
+int dvbt_b200_rx_run_baseband_host(dvbt_b200_rx *h, const void *samples, size_t nsamples, uint8_t *ts, size_t ts_capacity, size_t *ts_bytes) {
+  if (!h || (nsamples && !samples) || !ts) { set_error("rx_run_baseband_host: bad argument"); return DVBT_B200_EINVAL; }
+  int rc = h->d_samples.reserve(nsamples * 8);
+  if (rc) return rc;
+  DVBT_CUDA_TRY(cudaMemcpyAsync(h->d_samples.p, samples, nsamples * 8, cudaMemcpyHostToDevice, h->stream));
+  return rx_run_baseband(h, h->d_samples.as<float2>(), nsamples, ts, nullptr, ts_capacity, ts_bytes, 1);
+}
+
+int dvbt_b200_rx_run_baseband_dev(dvbt_b200_rx *h, const void *d_samples, size_t nsamples, uint8_t *d_ts, size_t ts_capacity, size_t *ts_bytes) {
+  if (!h || (nsamples && !d_samples) || !d_ts) { set_error("rx_run_baseband_dev: bad argument"); return DVBT_B200_EINVAL; }
+  return rx_run_baseband(h, (const float2 *)d_samples, nsamples, nullptr, d_ts, ts_capacity, ts_bytes, 0);
 }
 
 int dvbt_b200_rx_last_info(const dvbt_b200_rx *h, dvbt_b200_rx_info *info) {

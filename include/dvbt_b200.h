@@ -209,6 +209,35 @@ int dvbt_b200_demod_work(dvbt_b200_demod *h, const void *in, size_t n_in_items, 
                          size_t tags_out_capacity, size_t *n_tags_out);
 
 /* ------------------------------------------------------------------------------------
+ * ofdm_sym_acquisition — replaces gr::dvbt::ofdm_sym_acquisition (and, with apply_fft, the
+ * fft_vxx(N, forward, rectangular, shift=True) block that follows it in every RX flowgraph)
+ *   make():         include/dvbt/ofdm_sym_acquisition.h:49
+ *   forecast():     lib/ofdm_sym_acquisition_impl.cc:473-481 ((2N+cp) samples per output item)
+ *   general_work(): lib/ofdm_sym_acquisition_impl.cc:488-568 (ml_sync :148-351,
+ *                   peak_detect_process :72-146)
+ * Items: gr_complex samples in (64/7 Msps), vectors of N gr_complex out (CP removed, derotated).
+ * Tags out: sync_start (value 1) on the first item after a (re)acquisition.
+ * ------------------------------------------------------------------------------------ */
+typedef struct dvbt_b200_acq dvbt_b200_acq;
+typedef struct dvbt_b200_acq_params { /* the make() arguments, in order */
+  int blocks;         /* 1 in every flowgraph */
+  int fft_length;     /* 2048 / 8192 */
+  int occupied_tones; /* 1705 / 6817 (unused by the reference algorithm) */
+  int cp_length;      /* N/32 ... N/4 */
+  float snr;          /* dB; 30 in every flowgraph */
+} dvbt_b200_acq_params;
+
+int dvbt_b200_acq_create(const dvbt_b200_acq_params *p, dvbt_b200_acq **out);
+void dvbt_b200_acq_destroy(dvbt_b200_acq *h);
+/* One scheduler call on HOST buffers, as many symbols as the input allows (the reference does
+ * one per call; the stream behaviour is the same).  consumed = samples consumed (N+cp per
+ * symbol; half of that once after a lost peak), produced = symbols written.  apply_fft != 0
+ * additionally applies the forward FFT with DC moved to bin N/2 (= fft_vxx shift=True). */
+int dvbt_b200_acq_work(dvbt_b200_acq *h, const void *in, size_t n_in_items, void *out, size_t out_capacity_items,
+                       size_t *consumed, size_t *produced, dvbt_b200_tag *tags_out, size_t tags_out_capacity,
+                       size_t *n_tags_out, int apply_fft);
+
+/* ------------------------------------------------------------------------------------
  * Fused receive chain (device resident).  One call = what the RX flowgraph
  * apps/dvbt_rx_demo*.grc does to a capture, from the FFT output onwards:
  *   demod_reference_signals -> dvbt_demap -> symbol_inner_interleaver(deinterleave) ->
@@ -232,6 +261,10 @@ typedef struct dvbt_b200_rx_info {
   long long rs_packets;
   long long first_packet;   /* RS packet index where the descrambler locked (NSYNC), -1 */
   long long ts_bytes;
+  long long acq_symbols;    /* symbols produced by acquisition (baseband entry) */
+  long long acq_cp_start;   /* d_cp_start after the run */
+  long long acq_lost_at;    /* symbol count at which tracking lost the peak, -1 never */
+  float ms_acq_fft;
   float ms_demod, ms_inner, ms_viterbi, ms_viterbi_acs, ms_rs, ms_descramble; /* device time per stage */
 } dvbt_b200_rx_info;
 enum { DVBT_RX_STAGE_CELLS = 0, DVBT_RX_STAGE_DEMAP = 1, DVBT_RX_STAGE_BITDEINT = 2, DVBT_RX_STAGE_VITERBI = 3,
@@ -244,6 +277,10 @@ int dvbt_b200_rx_set_rs_compat(dvbt_b200_rx *h, int as_built); /* see dvbt_b200_
  * _dev: device pointers.  *ts_bytes receives the TS bytes written (multiple of 1504). */
 int dvbt_b200_rx_run_freq_host(dvbt_b200_rx *h, const void *X, size_t nsym, uint8_t *ts, size_t ts_capacity, size_t *ts_bytes);
 int dvbt_b200_rx_run_freq_dev(dvbt_b200_rx *h, const void *dX, size_t nsym, uint8_t *d_ts, size_t ts_capacity, size_t *ts_bytes);
+/* The same from time-domain baseband at the OFDM sample rate (64/7 Msps for 8 MHz channels), i.e.
+ * including ofdm_sym_acquisition and the FFT: nsamples gr_complex. */
+int dvbt_b200_rx_run_baseband_host(dvbt_b200_rx *h, const void *samples, size_t nsamples, uint8_t *ts, size_t ts_capacity, size_t *ts_bytes);
+int dvbt_b200_rx_run_baseband_dev(dvbt_b200_rx *h, const void *d_samples, size_t nsamples, uint8_t *d_ts, size_t ts_capacity, size_t *ts_bytes);
 int dvbt_b200_rx_last_info(const dvbt_b200_rx *h, dvbt_b200_rx_info *info);
 /* copies an intermediate of the last run to the host (parity tests): DVBT_RX_STAGE_* */
 int dvbt_b200_rx_read_stage(dvbt_b200_rx *h, int stage, void *host_out, size_t capacity_bytes, size_t *nbytes);

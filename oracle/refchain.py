@@ -294,3 +294,25 @@ def rx_outer(vo, vtags, fixed_rs=False):
         if cons == 0:
             break
     return cd, rd, out[:oo].copy()
+
+
+def rx_acquisition(x, tm, max_symbols=None):
+    """ofdm_sym_acquisition one symbol per call with >= 2N+cp+16 samples visible
+    (ofdm_sym_acquisition_impl.cc:488-568).  x: complex64 samples at the OFDM rate.
+    Returns (symbols (nout, N) complex64, consumed samples, tags)."""
+    N, P, K, cp = mode_dims(tm)
+    x = np.ascontiguousarray(x, np.complex64)
+    pad = np.zeros(64, np.complex64)
+    buf = np.concatenate([pad, x, pad])  # the reference reads in[-2] on initial acquisition (SURVEY 0.9)
+    b = RefBlock("ofdm_sym_acquisition", 1, N, K, cp, 30.0)
+    out = np.zeros((len(x) // (N + cp) + 2, N), np.complex64)
+    pos, nout = 0, 0
+    need = 2 * N + cp + 16
+    while pos + need <= len(x) and (max_symbols is None or nout < max_symbols):
+        r, cons = b.work(1, len(x) - pos, buf.ctypes.data + (64 + pos) * 8, out.ctypes.data + nout * N * 8)
+        if r > 0:
+            nout += r
+        pos += cons
+        if cons == 0:
+            break
+    return out[:nout].copy(), pos, b.out_tags()

@@ -37,3 +37,23 @@ def channel(X, scale=0.01, noise=0.0, bin_shift=0, seed=0):
     if noise > 0:
         Y = (Y + (rng.normal(0, noise * scale, Y.shape) + 1j * rng.normal(0, noise * scale, Y.shape))).astype(np.complex64)
     return np.ascontiguousarray(Y)
+
+
+def ofdm_modulate(X, tm, gain=None, offset=0, cfo_bins=0.0, noise=0.0, seed=0):
+    """What the TX flowgraph does after reference_signals (apps/dvbt_tx_demo*.grc): fft_vxx(reverse,
+    shift=True) = unnormalised inverse DFT of the half-swapped vector, cyclic prefix N/32,
+    multiply_const.  Plus a test channel: `offset` leading samples, carrier offset in bins, AWGN."""
+    N, P, K, cp = R.mode_dims(tm)
+    if gain is None:
+        gain = 0.0022097087 if tm == R.T2k else 0.00055242272
+    t = np.fft.ifft(np.fft.ifftshift(X.astype(np.complex128), axes=1), axis=1) * N
+    t = np.concatenate([t[:, N - cp:], t], axis=1).reshape(-1) * gain
+    rng = np.random.default_rng(seed)
+    lead = (rng.normal(0, 1e-4, offset) + 1j * rng.normal(0, 1e-4, offset)) if offset else np.zeros(0)
+    t = np.concatenate([lead, t])
+    if cfo_bins:
+        t = t * np.exp(2j * np.pi * cfo_bins * np.arange(len(t)) / N)
+    if noise > 0:
+        rms = np.sqrt(np.mean(np.abs(t) ** 2))
+        t = t + (rng.normal(0, noise * rms, len(t)) + 1j * rng.normal(0, noise * rms, len(t)))
+    return t.astype(np.complex64)

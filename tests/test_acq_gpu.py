@@ -1,0 +1,61 @@
+"""GPU parity of ofdm_sym_acquisition (+FFT) against the reference block (oracle/_ref).
+Timing decisions (consumed samples, symbol count, cp position) must be identical; the
+derotated samples agree to float tolerance (the reference's phase is a sequential float
+accumulation, the kernel evaluates it in closed form: DESIGN.md §K2)."""
+import numpy as np
+import pytest
+
+from oracle import refchain as R
+
+pytestmark = pytest.mark.gpu
+needs_ref = pytest.mark.skipif(not R.available(), reason="oracle/_ref not built")
+
+
+@needs_ref
+@pytest.mark.parametrize("tm,offset,cfo", [(R.T2k, 777, 0.0), (R.T2k, 1301, 0.11), (R.T8k, 4000, -0.07)])
+def test_acquisition_matches_reference(tm, offset, cfo):
+    import gr_dvbt_b200 as g
+    from dvbt_testlib import tx_frequency_domain, ofdm_modulate
+    con, cr = R.QAM16, R.C1_2
+    N, P, K, cp = R.mode_dims(tm)
+    nsym = 60 if tm == R.T2k else 24
+    tx = tx_frequency_domain(con, cr, tm, nsym, 2)
+    x = ofdm_modulate(tx["X"][:nsym], tm, offset=offset, cfo_bins=cfo, seed=1)
+    ref, cons_ref, tags_ref = R.rx_acquisition(x, tm)
+    acq = g.ofdm_sym_acquisition(1, N, K, cp, 30.0)
+    out, cons, tags = acq.general_work(x)
+    n = min(len(out), len(ref))
+    assert n >= nsym - 4 and abs(len(out) - len(ref)) <= 1  # the batch may see one more complete symbol
+    assert cons >= cons_ref and (cons - cons_ref) % (N + cp) == 0
+    assert tags and tags[0] == (0, "sync_start", 1) and tags_ref[0][1] == "sync_start"
+    err = np.abs(out[:n] - ref[:n]).max() / np.abs(ref[:n]).max()
+    assert err < 2e-5, err
+    # FFT with the shift folded in == fftshift(fft(.)) of the time-domain output
+    acq2 = g.ofdm_sym_acquisition(1, N, K, cp, 30.0)
+    X, _, _ = acq2.general_work(x, apply_fft=True)
+    want = np.fft.fftshift(np.fft.fft(out.astype(np.complex128), axis=1), axes=1)
+    assert np.abs(X - want).max() / np.abs(want).max() < 1e-5
+
+
+@needs_ref
+@pytest.mark.parametrize("con,cr,tm,nsym,first_ts_packet", [(R.QAM16, R.C1_2, R.T2k, 420, 504), (R.QAM64, R.C7_8, R.T2k, 330, 1328)])
+def test_baseband_chain_round_trip(con, cr, tm, nsym, first_ts_packet):
+    """time-domain loopback: TX symbols -> IFFT+CP -> offset/CFO -> GPU chain == transmitted TS,
+    and == the reference chain fed by the reference acquisition + numpy FFT"""
+    import gr_dvbt_b200 as g
+    from dvbt_testlib import tx_frequency_domain, ofdm_modulate
+    from test_rx_chain_gpu import reference_rx
+    N, P, K, cp = R.mode_dims(tm)
+    tx = tx_frequency_domain(con, cr, tm, nsym, 11)
+    x = ofdm_modulate(tx["X"], tm, offset=777, cfo_bins=0.1, seed=4)
+    rx = g.rx_chain(con, g.NH, cr, g.G1_32, tm)
+    ts = rx.run_baseband(x)
+    info = rx.info()
+    assert info["acq_lost_at"] == -1 and info["acq_symbols"] >= nsym - 2
+    src = tx["ts"]
+    assert len(ts) > 1504 * 4
+    assert np.array_equal(ts, src[first_ts_packet * 188: first_ts_packet * 188 + len(ts)])
+    sym, cons, _ = R.rx_acquisition(x, tm)
+    Xf = np.fft.fftshift(np.fft.fft(sym.astype(np.complex128), axis=1), axes=1).astype(np.complex64)
+    ref = reference_rx(Xf, con, cr, tm)
+    assert len(ref["ts"]) > 0 and np.array_equal(ts[: len(ref["ts"])], ref["ts"])

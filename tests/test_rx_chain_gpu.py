@@ -77,7 +77,7 @@ def test_chain_with_noise_uses_rs_and_matches_both_reference_builds():
     from dvbt_testlib import tx_frequency_domain, channel
     con, cr, tm = R.QAM16, R.C3_4, R.T2k
     tx = tx_frequency_domain(con, cr, tm, 400, 5)
-    X = channel(tx["X"], noise=0.16, seed=3)
+    X = channel(tx["X"], noise=0.12, seed=3)
     for as_built in (0, 1):
         ref = reference_rx(X, con, cr, tm, fixed_rs=not as_built)
         rx = g.rx_chain(con, g.NH, cr, g.G1_32, tm)
