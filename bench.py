@@ -199,6 +199,100 @@ class ViterbiWorkload:
         return len(out) * 8 / 1e6, dt, kind
 
 
+
+# ---------------------------------------------------------------------------------------------
+# workload: rx — configs[1] of BASELINE.json: 2k / QAM64 / rate 7/8 full receive chain from the
+# 10 Msps capture (resampler 64/70, multiply_const, acquisition, FFT, demod, demap, inner
+# deinterleavers, Viterbi, outer deinterleaver, RS, descrambler)
+# ---------------------------------------------------------------------------------------------
+class RxWorkload:
+    name = "rx"
+    CON, CR, TM = 2, 4, 0
+    GAIN = 0.0022097087
+    SUPERFRAMES_BASE = 4  # generated once with the reference TX blocks, then tiled
+
+    def __init__(self, tiles):
+        self.tiles = int(tiles)
+
+    def describe(self):
+        return {"workload": "configs[1]: 2k/QAM64/rate-7/8 RX, synthetic 10 Msps baseband capture -> TS (full flowgraph "
+                            "apps/dvbt_rx_demo_2k_QAM64_rate78.grc: resampler 64/70, multiply_const, ofdm_sym_acquisition, FFT, "
+                            "demod_reference_signals, dvbt_demap, symbol/bit deinterleavers, viterbi_decoder, convolutional_deinterleaver, "
+                            "reed_solomon_dec, energy_descramble)",
+                "samples_per_step": self.nfile, "ofdm_symbols_per_step": self.nsym, "input_bytes_per_step": self.nfile * 8,
+                "l2_policy": "input %.0f MB per step > 126 MB L2" % (self.nfile * 8 / 1e6),
+                "parallelism": "independent captures per GPU, no data-path collective"}
+
+    def build_capture(self, seed):
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        from oracle import refchain as R
+        from dvbt_testlib import tx_frequency_domain, ofdm_modulate, to_capture_rate
+        if not R.available():
+            raise RuntimeError("bench rx workload needs oracle/_ref (reference TX blocks) to synthesise the capture")
+        nbase = 272 * self.SUPERFRAMES_BASE
+        tx = tx_frequency_domain(self.CON, self.CR, self.TM, nbase, seed)
+        X0 = tx["X"][:nbase]
+        x0 = ofdm_modulate(X0, self.TM, gain=1.0)           # one block of whole superframes, 64/7 Msps
+        x = np.tile(x0, self.tiles)
+        self.nsym = nbase * self.tiles
+        cap = to_capture_rate(np.concatenate([np.zeros(300, np.complex64), x]))
+        self.nfile = len(cap)
+        self.ts_src = tx["ts"]
+        return cap
+
+    def setup_gpu(self, seed):
+        import torch
+        import gr_dvbt_b200 as g
+        self.torch, self.g = torch, g
+        self.rx = g.rx_chain(self.CON, g.NH, self.CR, g.G1_32, self.TM)
+        cap = self.build_capture(seed)
+        self.d_in = torch.from_numpy(cap).cuda()
+        self.pin_in = torch.from_numpy(cap).pin_memory()
+        self.ts_cap = self.nsym * 1512
+        self.d_ts = torch.zeros(self.ts_cap, dtype=torch.uint8, device="cuda")
+        self.pin_ts = torch.zeros(self.ts_cap, dtype=torch.uint8).pin_memory()
+        self.kernel_ms = []
+        self.stage_ms = []
+        self.ts_bytes = 0
+
+    def step_resident(self, i):
+        n = self.rx.run_file_dev(self.d_in.data_ptr(), self.nfile, self.GAIN, self.d_ts.data_ptr(), self.ts_cap)
+        inf = self.rx.info()
+        self.kernel_ms.append(inf["ms_viterbi_acs"])
+        self.stage_ms.append({k: v for k, v in inf.items() if k.startswith("ms_")})
+        self.ts_bytes = n
+        self.info = inf
+        return n
+
+    def step_e2e(self, i):
+        import ctypes as C
+        n = C.c_size_t(0)
+        self.g.capi.check(self.g.capi.lib().dvbt_b200_rx_run_file_host(self.rx._h, self.pin_in.data_ptr(), self.nfile, self.GAIN,
+                                                                      self.pin_ts.data_ptr(), self.ts_cap, C.byref(n)))
+        return int(n.value)
+
+    def check(self):
+        ts = self.d_ts[: min(self.ts_bytes, 188 * 4000)].cpu().numpy()
+        ref = self.ts_src[1328 * 188: 1328 * 188 + len(ts)]
+        n = min(len(ts), len(ref))
+        return bool(n > 188 * 100 and np.array_equal(ts[:n], ref[:n]) and self.info["acq_lost_at"] == -1)
+
+    def units_per_step(self):
+        return self.nfile / 1e6  # Msamples of the 10 Msps capture
+
+    h2d = property(lambda self: self.nfile * 8)
+    d2h = property(lambda self: int(self.ts_bytes))
+
+    @property
+    def viterbi_bits(self):
+        return self.info["viterbi_bytes"] * 8
+
+    @property
+    def alg_bytes(self):
+        # Viterbi stage in the reference I/O format: n/(k*m) B in + 1/8 B out per decoded bit
+        return self.viterbi_bits * (8.0 / (7 * 6) + 0.125)
+
+
 def cpu_worker(args):
     mbit, reps = args
     w = ViterbiWorkload(mbit)
@@ -210,11 +304,64 @@ def cpu_worker(args):
     return tot_bits, tot_t, kind
 
 
-def run_cpu_all_cores(reps):
+# ---- reference RX chain on the CPU (the reference's own blocks via oracle/_ref; numpy/scipy stand in for the
+# stock GNU Radio resampler and FFT, which are not part of gr-dvbt)
+_CPU_RX = {}
+
+
+def cpu_rx_prepare(seed=7, nsym=1904):
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from oracle import refchain as R
+    from dvbt_testlib import tx_frequency_domain, ofdm_modulate, to_capture_rate
+    tx = tx_frequency_domain(RxWorkload.CON, RxWorkload.CR, RxWorkload.TM, nsym, seed)
+    x = ofdm_modulate(tx["X"][:nsym], RxWorkload.TM, gain=1.0, offset=300)
+    _CPU_RX["cap"] = to_capture_rate(x)
+    _CPU_RX["ts"] = tx["ts"]
+
+
+def cpu_rx_chain(_=None):
+    """one pass of the reference flowgraph over the prepared capture; returns (Msamples, seconds, per-stage seconds)"""
+    from scipy.signal import resample_poly
+    from oracle import refchain as R
+    cap = _CPU_RX["cap"]
+    con, cr, tm = RxWorkload.CON, RxWorkload.CR, RxWorkload.TM
+    N, P, K, cp = R.mode_dims(tm)
+    st = {}
+    t0 = time.time()
+    x = (resample_poly(cap, 32, 35, window=("kaiser", 7.0)) * np.float32(RxWorkload.GAIN)).astype(np.complex64)
+    st["resample(scipy)"] = time.time() - t0; t = time.time()
+    sym, cons, _tags = R.rx_acquisition(x, tm)
+    st["ofdm_sym_acquisition"] = time.time() - t; t = time.time()
+    Xf = np.fft.fftshift(np.fft.fft(sym, axis=1), axes=1).astype(np.complex64)
+    st["fft(numpy)"] = time.time() - t; t = time.time()
+    Y, tags = R.rx_demod(Xf, con, cr, tm)
+    st["demod_reference_signals"] = time.time() - t; t = time.time()
+    dm = R.rx_demap(Y, con, tm)
+    st["dvbt_demap"] = time.time() - t; t = time.time()
+    sd, bd = R.rx_deinterleave(dm, tags, con, tm)
+    st["inner_deinterleavers"] = time.time() - t; t = time.time()
+    sf = [tg for tg in tags if tg[1] == "superframe_start"][0][0]
+    vo, vtags = R.rx_viterbi(bd, con, cr, sf * P)
+    st["viterbi_decoder"] = time.time() - t; t = time.time()
+    cd, rd, ts = R.rx_outer(vo, vtags)
+    st["outer(deint+rs+descramble)"] = time.time() - t
+    dt = time.time() - t0
+    ok = len(ts) > 0 and np.array_equal(ts, _CPU_RX["ts"][1328 * 188: 1328 * 188 + len(ts)])
+    return len(cap) / 1e6, dt, st, ok, len(vo) * 8 / 1e6
+
+
+def run_cpu_all_cores(reps, workload):
     import multiprocessing as mp
     cores = os.cpu_count() or 1
     ctx = mp.get_context("fork")
     t = time.time()
+    if workload == "rx":
+        with ctx.Pool(cores) as pool:
+            res = pool.map(cpu_rx_chain, range(cores))
+        wall = time.time() - t
+        units = sum(r[0] for r in res)
+        assert all(r[3] for r in res), "reference chain did not reproduce the transmitted TS"
+        return units / max(r[1] for r in res), cores, "reference", float(np.mean([r[0] / r[1] for r in res])), wall
     with ctx.Pool(cores) as pool:
         res = pool.map(cpu_worker, [(1.0, reps)] * cores)
     wall = time.time() - t
@@ -229,28 +376,41 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200")
-    ap.add_argument("--workload", default="viterbi")
+    ap.add_argument("--workload", default="rx", choices=["rx", "viterbi"])
     ap.add_argument("--mbit", type=float, default=640.0, help="decoded Mbit per GPU per step (viterbi workload)")
+    ap.add_argument("--tiles", type=int, default=16, help="rx workload: capture = tiles x 4 superframes (1088 OFDM symbols each)")
     a = ap.parse_args()
     a.warmup = max(a.warmup, 3)
     metric = "RX Msamples/s (baseband) & Viterbi Mbit/s @1/2/4/8 GPU vs SSE2 CPU; HBM GB/s %peak"
+    rx = a.workload == "rx"
+    unit = "Msamples/s (10 Msps-domain complex64 baseband, whole RX chain to TS)" if rx else "Mbit/s (Viterbi decoded bits)"
 
     if a.impl == "reference":
         if RANK != 0:
             return 0
-        w = ViterbiWorkload(a.mbit)
+        if rx:
+            from oracle import refchain as R
+            if not R.available():
+                print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref (reference sources compiled verbatim) was not built on this box"}))
+                return 0
+            cpu_rx_prepare()
+            w = RxWorkload(a.tiles)
+            w.nsym, w.nfile = 1904, len(_CPU_RX["cap"])
+            sample = "one capture of 1904 OFDM symbols (%.2f Msamples at 10 Msps) per process per step, one process per core (the reference keeps process-global Viterbi state)" % (len(_CPU_RX["cap"]) / 1e6)
+        else:
+            w = ViterbiWorkload(a.mbit)
+            sample = "150 x 768-blocks (%.2f Mbit) of the same rate-7/8 m=6 stream per process per step, one process per core" % (150 * 96 * 7 * 8 / 1e6)
         vals = []
         for i in range(a.warmup + a.steps):
-            agg, cores, kind, per_core, wall = run_cpu_all_cores(1)
+            agg, cores, kind, per_core, wall = run_cpu_all_cores(1, a.workload)
             if i >= a.warmup:
                 vals.append((agg, wall))
         v = float(np.mean([x[0] for x in vals]))
-        line = {"metric": metric, "value": v, "unit": "Mbit/s (Viterbi decoded bits, %d processes)" % cores, "impl": "reference", "n_gpus": a.gpus,
+        line = {"metric": metric, "value": v, "unit": unit + ", %d processes" % cores, "impl": "reference", "n_gpus": a.gpus,
                 "steps": a.steps, "warmup": a.warmup, "ms_per_step": float(np.mean([x[1] for x in vals]) * 1e3), "higher_is_better": True,
-                "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic", "config": w.describe(),
-                "cpu_baseline": {"value": v, "unit": "Mbit/s", "cores": cores, "kind": kind,
-                                 "sample": "150 x 768-blocks (%.2f Mbit) of the same rate-7/8 m=6 stream per process per step, one process per core" % (150 * 96 * 7 * 8 / 1e6)},
-                "e2e": {"value": v, "unit": "Mbit/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+                "scaling": "weak", "vs_baseline": None, "dtype": "u8/f32", "data": "synthetic", "config": w.describe(),
+                "cpu_baseline": {"value": v, "unit": unit.split(" (")[0], "cores": cores, "kind": kind, "sample": sample},
+                "e2e": {"value": v, "unit": unit.split(" (")[0], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
         print(json.dumps(line))
         return 0
 
@@ -262,11 +422,11 @@ def main():
     if WORLD > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", LOCAL_RANK))
         # the only collective on this path: the configuration
-        cfg = torch.tensor([a.mbit, a.steps, a.warmup], dtype=torch.float64, device="cuda")
+        cfg = torch.tensor([a.mbit, a.steps, a.warmup, a.tiles], dtype=torch.float64, device="cuda")
         dist.broadcast(cfg, 0)
-        a.mbit, a.steps, a.warmup = float(cfg[0]), int(cfg[1]), int(cfg[2])
+        a.mbit, a.steps, a.warmup, a.tiles = float(cfg[0]), int(cfg[1]), int(cfg[2]), int(cfg[3])
 
-    w = ViterbiWorkload(a.mbit)
+    w = RxWorkload(a.tiles) if rx else ViterbiWorkload(a.mbit)
     w.setup_gpu(seed=1 + RANK)
     lib = g.capi.lib()
 
@@ -315,19 +475,38 @@ def main():
         value = units / (ms / a.steps / 1e3)
         e2e = units / (ms_e2e / a.steps / 1e3)
         achieved = w.alg_bytes / (kms / 1e3) / 1e9
-        cb_bits, cb_t, cb_kind = w.cpu_sample(0)
-        line = {"metric": metric, "value": value, "unit": "Mbit/s (Viterbi decoded bits)", "n_gpus": WORLD, "steps": a.steps, "warmup": a.warmup,
-                "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
-                "data": "synthetic (seeded random TS bytes, K=7 encoded, punctured 7/8, error free)", "config": w.describe(),
-                "parity_check": ok, "gpu_launches": int(launches), "clocks": clocks,
-                "e2e": {"value": e2e, "unit": "Mbit/s", "h2d_bytes_per_step": w.h2d, "d2h_bytes_per_step": w.d2h, "ms_per_step": ms_e2e / a.steps,
-                        "api": "dvbt_b200_viterbi_decode_host on pinned host buffers"},
-                "roofline": {"kernel": "vit_acs_kernel", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                             "traffic": None, "peak_source": peak_src, "avg_launch_ms": kms,
-                             "note": "ALU/shared-memory bound kernel (64 add-compare-select per decoded bit): HBM fraction is reported as the metric demands; "
-                                     "ACS rate = %.1f T state-updates/s" % (w.info_bits * 64 / (kms / 1e3) / 1e12)},
-                "cpu_baseline": {"value": cb_bits / cb_t, "unit": "Mbit/s", "cores": 1, "kind": cb_kind,
-                                 "sample": "150 x 768-blocks (%.2f Mbit) of the same rate-7/8 m=6 stream, one thread" % cb_bits}}
+        line = {"metric": metric, "value": value, "unit": unit, "n_gpus": WORLD, "steps": a.steps, "warmup": a.warmup,
+                "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8/f32" if rx else "u8",
+                "config": w.describe(), "parity_check": ok, "gpu_launches": int(launches), "clocks": clocks}
+        if rx:
+            vbits = w.viterbi_bits
+            stage = {k: float(np.mean([s[k] for s in w.stage_ms[a.warmup:]])) for k in w.stage_ms[-1]}
+            line["data"] = "synthetic (seeded random TS -> reference TX blocks -> IFFT/CP -> 35/32 resampler -> 10 Msps capture, no added noise)"
+            line["viterbi_mbit_per_s"] = vbits * WORLD / (ms / a.steps / 1e3) / 1e6
+            line["realtime_factor"] = value / WORLD / 10.0
+            line["stage_ms"] = stage
+            line["e2e"] = {"value": e2e, "unit": "Msamples/s", "h2d_bytes_per_step": w.h2d, "d2h_bytes_per_step": w.d2h, "ms_per_step": ms_e2e / a.steps,
+                           "api": "dvbt_b200_rx_run_file_host on pinned host buffers"}
+            info_bits = vbits
+            cpu_rx_prepare()
+            cu, ct, cst, cok, cvit = cpu_rx_chain()
+            line["cpu_baseline"] = {"value": cu / ct, "unit": "Msamples/s", "cores": 1, "kind": "reference",
+                                    "sample": "one capture of 1904 OFDM symbols (%.2f Msamples at 10 Msps), one thread; the reference's own blocks "
+                                              "(oracle/_ref) with scipy/numpy standing in for the stock GNU Radio resampler and FFT" % cu,
+                                    "viterbi_mbit_per_s": cvit / cst["viterbi_decoder"], "ts_ok": cok,
+                                    "stage_share": {k: round(v / ct, 3) for k, v in cst.items()}}
+        else:
+            line["data"] = "synthetic (seeded random TS bytes, K=7 encoded, punctured 7/8, error free)"
+            line["e2e"] = {"value": e2e, "unit": "Mbit/s", "h2d_bytes_per_step": w.h2d, "d2h_bytes_per_step": w.d2h, "ms_per_step": ms_e2e / a.steps,
+                           "api": "dvbt_b200_viterbi_decode_host on pinned host buffers"}
+            info_bits = w.info_bits
+            cb_bits, cb_t, cb_kind = w.cpu_sample(0)
+            line["cpu_baseline"] = {"value": cb_bits / cb_t, "unit": "Mbit/s", "cores": 1, "kind": cb_kind,
+                                    "sample": "150 x 768-blocks (%.2f Mbit) of the same rate-7/8 m=6 stream, one thread" % cb_bits}
+        line["roofline"] = {"kernel": "vit_acs_kernel", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                            "traffic": None, "peak_source": peak_src, "avg_launch_ms": kms,
+                            "note": "dominant kernel of the step; ALU/shared-memory bound (64 add-compare-select per decoded bit), so the HBM "
+                                    "fraction is small by nature; ACS rate = %.1f T state-updates/s" % (info_bits * 64 / (kms / 1e3) / 1e12)}
         print(json.dumps(line))
     if WORLD > 1:
         dist.destroy_process_group()

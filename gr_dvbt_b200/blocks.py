@@ -235,6 +235,20 @@ class rx_chain(_Handle):
         check(lib().dvbt_b200_rx_run_baseband_host(self._h, x.ctypes.data, len(x), ts.ctypes.data, cap, C.byref(n)))
         return ts[: n.value].copy()
 
+    def run_file(self, samples, gain):
+        """samples: complex64 host array at 10 Msps (the capture file of the flowgraphs) -> TS bytes."""
+        x = np.ascontiguousarray(samples, np.complex64).reshape(-1)
+        cap = len(x) + 4096
+        ts = np.zeros(cap, np.uint8)
+        n = C.c_size_t(0)
+        check(lib().dvbt_b200_rx_run_file_host(self._h, x.ctypes.data, len(x), gain, ts.ctypes.data, cap, C.byref(n)))
+        return ts[: n.value].copy()
+
+    def run_file_dev(self, d_x, nsamples, gain, d_ts, ts_capacity):
+        n = C.c_size_t(0)
+        check(lib().dvbt_b200_rx_run_file_dev(self._h, _addr(d_x), nsamples, gain, _addr(d_ts), ts_capacity, C.byref(n)))
+        return int(n.value)
+
     def run_baseband_dev(self, d_x, nsamples, d_ts, ts_capacity):
         n = C.c_size_t(0)
         check(lib().dvbt_b200_rx_run_baseband_dev(self._h, _addr(d_x), nsamples, _addr(d_ts), ts_capacity, C.byref(n)))

@@ -46,7 +46,7 @@ class RxParams(C.Structure):
 class RxInfo(C.Structure):
     _fields_ = [(n, C.c_longlong) for n in ("symbols_parsed", "first_symbol", "symbols_out", "viterbi_bytes", "viterbi_repaired",
                                              "rs_packets", "first_packet", "ts_bytes", "acq_symbols", "acq_cp_start", "acq_lost_at")] + \
-               [(n, C.c_float) for n in ("ms_acq_fft", "ms_demod", "ms_inner", "ms_viterbi", "ms_viterbi_acs", "ms_rs", "ms_descramble")]
+               [(n, C.c_float) for n in ("ms_resample", "ms_acq_fft", "ms_demod", "ms_inner", "ms_viterbi", "ms_viterbi_acs", "ms_rs", "ms_descramble")]
 
 
 class AcqParams(C.Structure):
@@ -111,6 +111,9 @@ def lib():
                                          C.POINTER(Tag), C.c_size_t, C.POINTER(C.c_size_t), C.c_int]
         L.dvbt_b200_rx_run_baseband_host.argtypes = [vp, vp, C.c_size_t, vp, C.c_size_t, C.POINTER(C.c_size_t)]
         L.dvbt_b200_rx_run_baseband_dev.argtypes = [vp, vp, C.c_size_t, vp, C.c_size_t, C.POINTER(C.c_size_t)]
+        L.dvbt_b200_rx_run_file_host.argtypes = [vp, vp, C.c_size_t, C.c_float, vp, C.c_size_t, C.POINTER(C.c_size_t)]
+        L.dvbt_b200_rx_run_file_dev.argtypes = [vp, vp, C.c_size_t, C.c_float, vp, C.c_size_t, C.POINTER(C.c_size_t)]
+        L.dvbt_b200_resampler_taps.argtypes = [vp, C.c_int]
         _lib = L
     return _lib
 

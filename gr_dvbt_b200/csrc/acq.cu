@@ -184,7 +184,8 @@ __global__ void acq_lambda_kernel(AcqParams p, const float2 *__restrict__ x, lon
 
 // speculative per-symbol detector: window = candidates [kD-8, kD+8) (cp_start == c0)
 __global__ void acq_track_kernel(AcqParams p, int nsym, const float *__restrict__ lambda, const float *__restrict__ avg_in,
-                                 float avg_first, float *__restrict__ avg_out, int *__restrict__ peak_out) {
+                                 float avg_first, float *__restrict__ avg_out, int *__restrict__ peak_out,
+                                 const float2 *__restrict__ gamma, float *__restrict__ eps_out) {
   int n = blockIdx.x * blockDim.x + threadIdx.x;
   if (n >= nsym) return;
   float avg = avg_in ? (n == 0 ? avg_first : avg_in[n - 1]) : 0.f;
@@ -192,14 +193,94 @@ __global__ void acq_track_kernel(AcqParams p, int nsym, const float *__restrict_
   int np = peak_detect(lambda + (long long)n * kCand + (kD - 8), 16, &avg, p.rise, p.fall, p.alpha, &best);
   avg_out[n] = avg;
   if (peak_out) peak_out[n] = np > 0 ? best : -1;
+  if (eps_out) {
+    float2 g = gamma[(long long)n * kCand + (kD - 8) + best];
+    eps_out[n] = np > 0 ? atan2f(g.y, g.x) : 0.f;  // fast_atan2f(d_gamma[peak]) (:277)
+  }
+}
+
+// speculation holds for the whole batch iff every symbol found its peak at the centre of the window
+// (cp_start unchanged) and every average fed forward in pass 2 equals the one pass 2 produced
+__global__ void acq_verify_kernel(int nsym, const float *__restrict__ avg1, const float *__restrict__ avg2,
+                                  const int *__restrict__ peak2, int *first_bad) {
+  int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= nsym) return;
+  bool bad = peak2[n] != 8;
+  if (n + 1 < nsym && __float_as_uint(avg1[n]) != __float_as_uint(avg2[n])) bad = true;
+  if (bad) atomicMin(first_bad, n);
+}
+
+// whole batch verified: per-symbol output descriptors and the end state, one warp, no dependent loads
+__global__ void __launch_bounds__(32) acq_fast_kernel(AcqParams p, int nsym, long long base, int c0, const float *__restrict__ eps,
+                                                      const float *__restrict__ avg2, const int *first_bad, AcqState *st,
+                                                      SymOut *__restrict__ out) {
+  if (*first_bad < nsym) return;
+  const int lane = threadIdx.x;
+  const int total = p.N + p.cp;
+  const double invN = -1.0 / (double)p.N;
+  const int sw = c0 - total;                       // d_nextpos left by every symbol (:312)
+  const bool sw_ok = sw >= 0 && sw < total;
+  const int sw0 = st->nextpos;
+  const bool sw0_ok = sw0 >= 0 && sw0 < total;
+  const double inc_init = st->phaseinc, pend_init = st->nextphaseinc;
+  const double inc_after0 = sw0_ok ? pend_init : inc_init;  // d_phaseinc after symbol 0
+  double carry = st->phase;                         // phase before symbol `base_n`
+  double last_inc = inc_init;
+  for (int bn = 0; bn < nsym; bn += 32) {
+    int n = bn + lane;
+    double i0 = 0, i1 = 0, adv = 0;
+    int swn = total;
+    if (n < nsym) {
+      if (n == 0) {
+        i0 = inc_init; i1 = pend_init; swn = sw0_ok ? sw0 : total;
+      } else {
+        double e1 = invN * (double)eps[n - 1];
+        // increment in force when symbol n starts: what symbol n-1 switched to (or kept)
+        double start = (n == 1) ? inc_after0 : (sw_ok ? invN * (double)eps[n - 2] : inc_after0);
+        i0 = start; i1 = e1; swn = sw_ok ? sw : total;
+      }
+      adv = swn < total ? swn * i0 + (total - swn) * i1 : total * i0;
+    }
+    // inclusive warp scan of the advances
+    double incl = adv;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      double t = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += t;
+    }
+    if (n < nsym) {
+      SymOut so;
+      so.first = base + (long long)n * total + c0 - p.N + 1;
+      so.phase0 = remainder(carry + (incl - adv), 2.0 * M_PI);
+      so.inc0 = i0; so.inc1 = i1; so.switch_at = swn;
+      out[n] = so;
+    }
+    int lastl = min(31, nsym - 1 - bn);
+    carry = remainder(carry + __shfl_sync(0xffffffffu, incl, lastl), 2.0 * M_PI);
+    double li = (swn < total) ? i1 : i0;
+    last_inc = __shfl_sync(0xffffffffu, li, lastl);
+  }
+  if (lane == 0) {
+    st->avg = avg2[nsym - 1];
+    st->phase = (float)carry;
+    st->phaseinc = last_inc;
+    st->nextphaseinc = invN * (double)eps[nsym - 1];
+    st->nextpos = sw;
+    st->cp_start = c0;
+    st->n_out = nsym;
+    st->lost_at = -1;
+    st->fallback = 0;
+    st->consumed = (long long)nsym * total;
+  }
 }
 
 // verification + the light sequential bookkeeping; falls back to the sequential detector from the
 // first symbol whose speculation does not hold
 __global__ void acq_chain_kernel(AcqParams p, int nsym, long long base, int c0, const float *__restrict__ lambda,
                                  const float2 *__restrict__ gamma, const float *__restrict__ avg1, const float *__restrict__ avg2,
-                                 const int *__restrict__ peak2, AcqState *st, SymOut *__restrict__ out) {
+                                 const int *__restrict__ peak2, AcqState *st, SymOut *__restrict__ out, const int *first_bad) {
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  if (*first_bad >= nsym) return;  // acq_fast_kernel handled the batch
   const int total = p.N + p.cp;
   int cp_start = c0;
   float avg = st->avg;
@@ -267,7 +348,8 @@ __global__ void acq_chain_kernel(AcqParams p, int nsym, long long base, int c0, 
   st->cp_start = cp_start;
   st->n_out = n_out;
   st->lost_at = lost_at;
-  st->fallback = fallback;
+  st->fallback = 1;
+  (void)fallback;
   if (lost_at >= 0) {
     // symbols 0..lost_at-1 consumed N+cp each; the miss consumes N+cp (table overrun) or half of it (restart)
     st->consumed = (long long)lost_at * total;
@@ -302,7 +384,7 @@ struct dvbt_b200_acq {
   bool own_stream = true;
   cufftHandle plan = 0;
   int plan_batch = 0;
-  dvbt::DevBuf d_x, d_state, h_state, d_lambda, d_gamma, d_avg1, d_avg2, d_peak, d_sym, d_out, d_il, d_ig;
+  dvbt::DevBuf d_x, d_state, h_state, d_lambda, d_gamma, d_avg1, d_avg2, d_peak, d_sym, d_out, d_il, d_ig, d_eps, d_flag;
 };
 
 namespace dvbt {
@@ -355,12 +437,19 @@ int acq_run(dvbt_b200_acq *h, const float2 *x, long long n, float2 *d_out, long 
       acq_lambda_kernel<<<(unsigned)((threads + 127) / 128), 128, 0, st>>>(p, x, pos, c0, (int)nsym, h->d_lambda.as<float>(),
                                                                           h->d_gamma.as<float2>());
       unsigned g = (unsigned)((nsym + 127) / 128);
-      acq_track_kernel<<<g, 128, 0, st>>>(p, (int)nsym, h->d_lambda.as<float>(), nullptr, 0.f, h->d_avg1.as<float>(), nullptr);
+      if ((rc = h->d_eps.reserve((size_t)nsym * 4)) || (rc = h->d_flag.reserve(16))) return rc;
+      int big = 0x7fffffff;
+      DVBT_CUDA_TRY(cudaMemcpyAsync(h->d_flag.p, &big, 4, cudaMemcpyHostToDevice, st));
+      acq_track_kernel<<<g, 128, 0, st>>>(p, (int)nsym, h->d_lambda.as<float>(), nullptr, 0.f, h->d_avg1.as<float>(), nullptr, nullptr, nullptr);
       acq_track_kernel<<<g, 128, 0, st>>>(p, (int)nsym, h->d_lambda.as<float>(), h->d_avg1.as<float>(), hs->avg, h->d_avg2.as<float>(),
-                                          h->d_peak.as<int>());
+                                          h->d_peak.as<int>(), h->d_gamma.as<float2>(), h->d_eps.as<float>());
+      acq_verify_kernel<<<g, 128, 0, st>>>((int)nsym, h->d_avg1.as<float>(), h->d_avg2.as<float>(), h->d_peak.as<int>(), h->d_flag.as<int>());
+      acq_fast_kernel<<<1, 32, 0, st>>>(p, (int)nsym, pos, c0, h->d_eps.as<float>(), h->d_avg2.as<float>(), h->d_flag.as<int>(),
+                                        h->d_state.as<AcqState>(), h->d_sym.as<SymOut>());
       acq_chain_kernel<<<1, 32, 0, st>>>(p, (int)nsym, pos, c0, h->d_lambda.as<float>(), h->d_gamma.as<float2>(), h->d_avg1.as<float>(),
-                                         h->d_avg2.as<float>(), h->d_peak.as<int>(), h->d_state.as<AcqState>(), h->d_sym.as<SymOut>());
-      count_launch(4);
+                                         h->d_avg2.as<float>(), h->d_peak.as<int>(), h->d_state.as<AcqState>(), h->d_sym.as<SymOut>(),
+                                         h->d_flag.as<int>());
+      count_launch(6);
       DVBT_CUDA_TRY(cudaGetLastError());
     }
     DVBT_CUDA_TRY(cudaMemcpyAsync(hs, h->d_state.p, sizeof(AcqState), cudaMemcpyDeviceToHost, st));
@@ -475,7 +564,7 @@ void dvbt_b200_acq_destroy(dvbt_b200_acq *h) {
   if (!h) return;
   if (h->stream) cudaStreamSynchronize(h->stream);
   if (h->plan) cufftDestroy(h->plan);
-  dvbt::DevBuf *bufs[] = {&h->d_x, &h->d_state, &h->h_state, &h->d_lambda, &h->d_gamma, &h->d_avg1, &h->d_avg2, &h->d_peak, &h->d_sym, &h->d_out, &h->d_il, &h->d_ig};
+  dvbt::DevBuf *bufs[] = {&h->d_x, &h->d_state, &h->h_state, &h->d_lambda, &h->d_gamma, &h->d_avg1, &h->d_avg2, &h->d_peak, &h->d_sym, &h->d_out, &h->d_il, &h->d_ig, &h->d_eps, &h->d_flag};
   for (auto *b : bufs) b->release();
   if (h->stream && h->own_stream) cudaStreamDestroy(h->stream);
   delete h;

@@ -27,3 +27,9 @@ int acq_reset(dvbt_b200_acq *h);
 int acq_run_simple(dvbt_b200_acq *h, const float2 *x, long long n, float2 *d_out, long long out_capacity_syms, int do_fft,
                    AcqResult *res);
 }  // namespace dvbt
+
+namespace dvbt {
+// rational_resampler_ccc(64,70) + multiply_const(scale): nin samples -> resample_out_count(nin) samples
+long long resample_out_count(long long nin);
+int resample_launch(const float2 *d_x, long long nin, float2 *d_y, long long nout, float scale, cudaStream_t st);
+}  // namespace dvbt

@@ -48,20 +48,7 @@ int make_demap_table(int constellation, int hierarchy, float gain, DemapTable *t
   return 0;
 }
 
-// shared with the fused equalise+demap kernel
-__device__ __forceinline__ uint8_t demap_cell(const DemapTable &t, float2 v) {
-  float dr = __fsub_rn(v.x, t.pts[0].x), di = __fsub_rn(v.y, t.pts[0].y);
-  float min_dist = __fadd_rn(__fmul_rn(dr, dr), __fmul_rn(di, di));
-  int min_index = 0;
-#pragma unroll 8
-  for (int i = 1; i < t.size; i++) {  // i = 0 can never be strictly smaller than itself
-    dr = __fsub_rn(v.x, t.pts[i].x);
-    di = __fsub_rn(v.y, t.pts[i].y);
-    float d = __fadd_rn(__fmul_rn(dr, dr), __fmul_rn(di, di));
-    if (d < min_dist) { min_dist = d; min_index = i; }
-  }
-  return (uint8_t)min_index;
-}
+__device__ __forceinline__ uint8_t demap_cell(const DemapTable &t, float2 v) { return demap_cell_any(t, v); }
 
 __global__ void __launch_bounds__(256) demap_kernel(const float2 *__restrict__ in, uint8_t *__restrict__ out, long long n,
                                                     const __grid_constant__ DemapTable t) {

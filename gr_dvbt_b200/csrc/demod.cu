@@ -266,20 +266,6 @@ __global__ void __launch_bounds__(128) demod_stage1_kernel(ModeDev md, const flo
 // ---------------------------------------------------------------------------------------
 // stage 2: one block per symbol — gains, interpolation, TPS carriers, payload (+ demap)
 // ---------------------------------------------------------------------------------------
-__device__ __forceinline__ uint8_t demap_cell_dev(const DemapTable &t, float2 v) {
-  float dr = __fsub_rn(v.x, t.pts[0].x), di = __fsub_rn(v.y, t.pts[0].y);
-  float min_dist = __fadd_rn(__fmul_rn(dr, dr), __fmul_rn(di, di));
-  int min_index = 0;
-#pragma unroll 8
-  for (int i = 1; i < t.size; i++) {
-    dr = __fsub_rn(v.x, t.pts[i].x);
-    di = __fsub_rn(v.y, t.pts[i].y);
-    float d = __fadd_rn(__fmul_rn(dr, dr), __fmul_rn(di, di));
-    if (d < min_dist) { min_dist = d; min_index = i; }
-  }
-  return (uint8_t)min_index;
-}
-
 __global__ void __launch_bounds__(256) demod_equalise_kernel(ModeDev md, const __grid_constant__ DemapTable dt, int do_demap,
                                                              const float2 *__restrict__ X, const int *__restrict__ fo_in,
                                                              const float2 *__restrict__ rot_in, const int *__restrict__ mod_in,
@@ -323,7 +309,7 @@ __global__ void __launch_bounds__(256) demod_equalise_kernel(ModeDev md, const _
     int k = pay[i];
     float2 y = cmul(cmul(rot, x[k]), s_gain[k]);
     if (Y) Y[(long long)s * md.P + i] = y;
-    if (do_demap) dm[(long long)s * md.P + i] = demap_cell_dev(dt, y);
+    if (do_demap) dm[(long long)s * md.P + i] = demap_cell_any(dt, y);
   }
 }
 
@@ -362,16 +348,15 @@ __device__ bool tps_bch_ok_bits(unsigned long long lo, unsigned hi) {
   return true;
 }
 
+// parity of the BCH check as 14 linear forms would be faster still; the LFSR runs once per frame
 __global__ void __launch_bounds__(32) demod_scan_kernel(int ntps, int nparse, int fi_start, int sync_start_at0,
                                                         const int *__restrict__ mod_in, const int *__restrict__ vote,
                                                         const float2 *__restrict__ tpsval, DemodState *st,
                                                         int *__restrict__ out_symidx, int *__restrict__ out_src) {
   const int lane = threadIdx.x;
   // sync words of :121-126 as FIFO entries 1..15 (std::equal compares 15 elements, :975/:1002)
-  // even: 0,0,1,1,0,1,0,1,1,1,1,0,1,1,1 -> entry i+1 = value
-  const unsigned long long kEven = (0ull << 1) | (0ull << 2) | (1ull << 3) | (1ull << 4) | (0ull << 5) | (1ull << 6) | (0ull << 7) |
-                                   (1ull << 8) | (1ull << 9) | (1ull << 10) | (1ull << 11) | (0ull << 12) | (1ull << 13) |
-                                   (1ull << 14) | (1ull << 15);
+  const unsigned long long kEven = (1ull << 3) | (1ull << 4) | (1ull << 6) | (1ull << 8) | (1ull << 9) | (1ull << 10) | (1ull << 11) |
+                                   (1ull << 13) | (1ull << 14) | (1ull << 15);
   const unsigned long long kMask = 0xFFFEull;
   int symbol_index = st->symbol_index, known = st->known, frame_index = st->frame_index, prev_mod = st->prev_mod,
       cur_mod = st->mod, d_init = st->d_init;
@@ -381,62 +366,108 @@ __global__ void __launch_bounds__(32) demod_scan_kernel(int ntps, int nparse, in
   for (int i = 64; i < 68; i++) hi |= (unsigned)(st->fifo[i] & 1) << (i - 64);
   int first_out = -1, n_out = 0, sf_tag_at = -1;
   if (sync_start_at0) d_init = 0;  // :115-116
-  for (int base = 0; base < nparse; base += 32) {
-    int s_l = base + lane;
-    int my_mod = s_l < nparse ? mod_in[s_l] : 0;
-    int my_vote = s_l < nparse ? vote[s_l] : 0;
-    int cnt = min(32, nparse - base);
-    int my_sym = 0, my_emit = 0;
-    for (int i = 0; i < cnt; i++) {
-      int m_in = __shfl_sync(0xffffffffu, my_mod, i);
-      int v_in = __shfl_sync(0xffffffffu, my_vote, i);
-      int mod = m_in >= 0 ? m_in : cur_mod;
-      cur_mod = mod;
-      int diff = (mod - prev_mod + 4) & 3;  // :684-688
-      prev_mod = mod;
-      symbol_index += diff;                 // :1228
-      if (symbol_index >= 68) symbol_index -= 68;
-      int sym_out = symbol_index, frame_out = frame_index;
-      bool cond = !known || symbol_index != 0;
-      unsigned long long bitv = cond ? (v_in >= 0 ? 0ull : 1ull) : 0ull;
-      for (int d = 0; d < diff; d++) {      // :957-972: pop front, push back
-        lo = (lo >> 1) | ((unsigned long long)(hi & 1u) << 63);
-        hi = (hi >> 1) | ((unsigned)bitv << 3);
+  int cbase = -1000, my_mod = 0, my_vote = 0;  // cached chunk of 32 symbols for the symbol-by-symbol path
+  int s = 0;
+  while (s < nparse) {
+    // ---- whole-frame fast path: in lock (known, FIFO just cleared at a frame end), next 68 symbols available.
+    // Equivalent to 68 single steps provided every symbol advances the index by one, no sync word shows up
+    // early in the partly filled FIFO, and the frame ends with a valid sync word + BCH; otherwise fall through.
+    if (known && symbol_index == 67 && lo == 0ull && hi == 0u && s + 68 <= nparse) {
+      bool good = true;
+      unsigned w[3];
+#pragma unroll
+      for (int q = 0; q < 3; q++) {
+        int i = lane + 32 * q;
+        bool valid = i < 68;
+        int m = valid ? mod_in[s + i] : 0;
+        int v = valid ? vote[s + i] : 0;
+        if (valid && m != ((prev_mod + 1 + i) & 3)) good = false;
+        w[q] = __ballot_sync(0xffffffffu, valid && v < 0);
       }
-      bool even = (lo & kMask) == kEven, odd = (lo & kMask) == (kEven ^ kMask);
-      int end_frame = 0;
-      if (even || odd) {
-        if (tps_bch_ok_bits(lo, hi)) {
-          frame_index = (int)(((lo >> 23) & 1ull) << 1 | ((lo >> 24) & 1ull));
-          known = 1;
-          end_frame = 1;
-        } else {
-          known = 0;
+      good = __all_sync(0xffffffffu, good);
+      unsigned long long flo = (((unsigned long long)w[1] << 32) | w[0]) & ~1ull;  // entry 0: index 0 pushes 0 (:964-971)
+      unsigned fhi = w[2] & 0xFu;
+      bool early = false;
+#pragma unroll
+      for (int k = 1; k <= 3; k++) {
+        unsigned long long e = (flo << k) & kMask;
+        if (e == kEven || e == (kEven ^ kMask)) early = true;
+      }
+      bool match = ((flo & kMask) == kEven) || ((flo & kMask) == (kEven ^ kMask));
+      if (good && !early && match && tps_bch_ok_bits(flo, fhi)) {
+        bool emit = true;
+        if (d_init == 0) {
+          if ((frame_index & 3) == fi_start) { d_init = 1; sf_tag_at = n_out; }
+          else emit = false;
         }
-        lo = 0;
-        hi = 0;
-      }
-      if (end_frame) symbol_index = 67;     // :1240-1241
-      // block level (demod_reference_signals_impl.cc:118-143)
-      bool emit = true;
-      if (d_init == 0) {
-        if (sym_out == 0 && (frame_out & 3) == fi_start) {
-          d_init = 1;
-          sf_tag_at = n_out;
-        } else {
-          emit = false;
+        if (emit) {
+          if (first_out < 0) first_out = s;
+#pragma unroll
+          for (int q = 0; q < 3; q++) {
+            int i = lane + 32 * q;
+            if (i < 68) { out_symidx[n_out + i] = i; out_src[n_out + i] = s + i; }
+          }
+          n_out += 68;
         }
-      }
-      if (emit) {
-        if (first_out < 0) first_out = base + i;
-        if (lane == i) { my_sym = sym_out; my_emit = n_out + 1; }
-        n_out++;
+        frame_index = (int)((((flo >> 23) & 1ull) << 1) | ((flo >> 24) & 1ull));
+        cur_mod = (prev_mod + 68) & 3;
+        prev_mod = cur_mod;
+        s += 68;
+        continue;
       }
     }
-    if (my_emit) {
-      out_symidx[my_emit - 1] = my_sym;
-      out_src[my_emit - 1] = s_l;
+    // ---- one symbol (parse_input :1188-1248 bookkeeping)
+    if (s < cbase || s >= cbase + 32) {
+      cbase = s;
+      int sl = s + lane;
+      my_mod = sl < nparse ? mod_in[sl] : 0;
+      my_vote = sl < nparse ? vote[sl] : 0;
     }
+    int m_in = __shfl_sync(0xffffffffu, my_mod, s - cbase);
+    int v_in = __shfl_sync(0xffffffffu, my_vote, s - cbase);
+    int mod = m_in >= 0 ? m_in : cur_mod;
+    cur_mod = mod;
+    int diff = (mod - prev_mod + 4) & 3;  // :684-688
+    prev_mod = mod;
+    symbol_index += diff;                 // :1228
+    if (symbol_index >= 68) symbol_index -= 68;
+    int sym_out = symbol_index, frame_out = frame_index;
+    bool cond = !known || symbol_index != 0;
+    unsigned long long bitv = cond ? (v_in >= 0 ? 0ull : 1ull) : 0ull;
+    for (int d = 0; d < diff; d++) {      // :957-972: pop front, push back
+      lo = (lo >> 1) | ((unsigned long long)(hi & 1u) << 63);
+      hi = (hi >> 1) | ((unsigned)bitv << 3);
+    }
+    bool even = (lo & kMask) == kEven, odd = (lo & kMask) == (kEven ^ kMask);
+    int end_frame = 0;
+    if (even || odd) {
+      if (tps_bch_ok_bits(lo, hi)) {
+        frame_index = (int)((((lo >> 23) & 1ull) << 1) | ((lo >> 24) & 1ull));
+        known = 1;
+        end_frame = 1;
+      } else {
+        known = 0;
+      }
+      lo = 0;
+      hi = 0;
+    }
+    if (end_frame) symbol_index = 67;     // :1240-1241
+    // block level (demod_reference_signals_impl.cc:118-143)
+    bool emit = true;
+    if (d_init == 0) {
+      if (sym_out == 0 && (frame_out & 3) == fi_start) {
+        d_init = 1;
+        sf_tag_at = n_out;
+      } else {
+        emit = false;
+      }
+    }
+    if (emit) {
+      if (first_out < 0) first_out = s;
+      if (lane == 0) { out_symidx[n_out] = sym_out; out_src[n_out] = s; }
+      n_out++;
+    }
+    s++;
   }
   if (lane == 0) {
     st->symbol_index = symbol_index; st->known = known; st->frame_index = frame_index; st->prev_mod = prev_mod;

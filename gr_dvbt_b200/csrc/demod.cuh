@@ -10,6 +10,52 @@ struct DemapTable {
   int size;
 };
 int make_demap_table(int constellation, int hierarchy, float gain, DemapTable *t);
+
+#ifdef __CUDACC__
+// find_constellation_value (dvbt_demap_impl.cc:167-203): first index with the strictly smallest
+// squared distance, every float operation rounded on its own.  The index bits alternate between
+// the axes (b0 b2 b4 -> I, b1 b3 b5 -> Q, :141-156), so re - point.re takes only 2^(M/2) distinct
+// values: the per-axis squares are computed once and the scan over the 2^M points adds the same
+// two floats the reference adds — identical sums, identical comparisons, 2-3x fewer operations.
+template <int M>
+__device__ __forceinline__ uint8_t demap_cell_exact(const DemapTable &t, float2 v) {
+  constexpr int H = M / 2, L = 1 << H, SIZE = 1 << M;
+  float ax[L], ay[L];
+#pragma unroll
+  for (int a = 0; a < L; a++) {
+    int ix = 0, iy = 0;
+#pragma unroll
+    for (int j = 0; j < H; j++) {
+      int bit = (a >> (H - 1 - j)) & 1;
+      ix |= bit << (M - 1 - 2 * j);
+      iy |= bit << (M - 2 - 2 * j);
+    }
+    float dr = __fsub_rn(v.x, t.pts[ix].x), di = __fsub_rn(v.y, t.pts[iy].y);
+    ax[a] = __fmul_rn(dr, dr);
+    ay[a] = __fmul_rn(di, di);
+  }
+  float min_dist = __fadd_rn(ax[0], ay[0]);
+  int min_index = 0;
+#pragma unroll
+  for (int i = 1; i < SIZE; i++) {
+    int xa = 0, ya = 0;
+#pragma unroll
+    for (int j = 0; j < H; j++) {
+      xa |= ((i >> (M - 1 - 2 * j)) & 1) << (H - 1 - j);
+      ya |= ((i >> (M - 2 - 2 * j)) & 1) << (H - 1 - j);
+    }
+    float d = __fadd_rn(ax[xa], ay[ya]);
+    if (d < min_dist) { min_dist = d; min_index = i; }
+  }
+  return (uint8_t)min_index;
+}
+
+__device__ __forceinline__ uint8_t demap_cell_any(const DemapTable &t, float2 v) {
+  if (t.size == 64) return demap_cell_exact<6>(t, v);
+  if (t.size == 16) return demap_cell_exact<4>(t, v);
+  return demap_cell_exact<2>(t, v);
+}
+#endif
 int demap_launch(const DemapTable &t, const float2 *d_in, uint8_t *d_out, long long ncells, cudaStream_t st);
 
 // Per transmission mode constants and carrier tables (device pointers are owned by ModeTables).

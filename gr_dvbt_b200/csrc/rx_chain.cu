@@ -173,7 +173,7 @@ struct dvbt_b200_rx {
   dvbt::DemapTable demap;
   dvbt_b200_viterbi *vit = nullptr;
   dvbt_b200_acq *acq = nullptr;
-  dvbt::DevBuf d_samples, d_sym;
+  dvbt::DevBuf d_samples, d_sym, d_file;
   cudaStream_t stream = nullptr;
   int fi_start = 3, rs_as_built = 0, sm_count = 148;
   int k = 1, n = 2, m = 4, ntb = 5, vit_in_block = 0, vit_out_block = 0;
@@ -258,6 +258,7 @@ void dvbt_b200_rx_destroy(dvbt_b200_rx *h) {
   for (auto &e : h->ev) if (e) cudaEventDestroy(e);
   h->tables.release();
   h->d_samples.release();
+  h->d_file.release();
   h->d_sym.release();
   if (h->acq) dvbt_b200_acq_destroy(h->acq);
   if (h->vit) dvbt_b200_viterbi_destroy(h->vit);  // owns the stream
@@ -422,6 +423,40 @@ int dvbt_b200_rx_run_baseband_host(dvbt_b200_rx *h, const void *samples, size_t 
 int dvbt_b200_rx_run_baseband_dev(dvbt_b200_rx *h, const void *d_samples, size_t nsamples, uint8_t *d_ts, size_t ts_capacity, size_t *ts_bytes) {
   if (!h || (nsamples && !d_samples) || !d_ts) { set_error("rx_run_baseband_dev: bad argument"); return DVBT_B200_EINVAL; }
   return rx_run_baseband(h, (const float2 *)d_samples, nsamples, nullptr, d_ts, ts_capacity, ts_bytes, 0);
+}
+
+static int rx_run_file(dvbt_b200_rx *h, const float2 *d_file, size_t nfile, float gain, uint8_t *ts_host, uint8_t *ts_dev,
+                       size_t ts_capacity, size_t *ts_bytes, int keep_cells) {
+  long long nout = dvbt::resample_out_count((long long)nfile);
+  int rc = h->d_samples.reserve((size_t)nout * 8);
+  if (rc) return rc;
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  cudaEventRecord(e0, h->stream);
+  rc = dvbt::resample_launch(d_file, (long long)nfile, h->d_samples.as<float2>(), nout, gain, h->stream);
+  cudaEventRecord(e1, h->stream);
+  if (!rc) rc = rx_run_baseband(h, h->d_samples.as<float2>(), (size_t)nout, ts_host, ts_dev, ts_capacity, ts_bytes, keep_cells);
+  float ms = 0;
+  if (cudaEventElapsedTime(&ms, e0, e1) == cudaSuccess) h->info.ms_resample = ms;
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  return rc;
+}
+
+int dvbt_b200_rx_run_file_host(dvbt_b200_rx *h, const void *samples, size_t nsamples, float gain, uint8_t *ts, size_t ts_capacity,
+                               size_t *ts_bytes) {
+  if (!h || (nsamples && !samples) || !ts) { set_error("rx_run_file_host: bad argument"); return DVBT_B200_EINVAL; }
+  int rc = h->d_file.reserve(nsamples * 8);
+  if (rc) return rc;
+  DVBT_CUDA_TRY(cudaMemcpyAsync(h->d_file.p, samples, nsamples * 8, cudaMemcpyHostToDevice, h->stream));
+  return rx_run_file(h, h->d_file.as<float2>(), nsamples, gain, ts, nullptr, ts_capacity, ts_bytes, 0);
+}
+
+int dvbt_b200_rx_run_file_dev(dvbt_b200_rx *h, const void *d_samples, size_t nsamples, float gain, uint8_t *d_ts, size_t ts_capacity,
+                              size_t *ts_bytes) {
+  if (!h || (nsamples && !d_samples) || !d_ts) { set_error("rx_run_file_dev: bad argument"); return DVBT_B200_EINVAL; }
+  return rx_run_file(h, (const float2 *)d_samples, nsamples, gain, nullptr, d_ts, ts_capacity, ts_bytes, 0);
 }
 
 int dvbt_b200_rx_last_info(const dvbt_b200_rx *h, dvbt_b200_rx_info *info) {

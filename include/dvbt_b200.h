@@ -264,7 +264,7 @@ typedef struct dvbt_b200_rx_info {
   long long acq_symbols;    /* symbols produced by acquisition (baseband entry) */
   long long acq_cp_start;   /* d_cp_start after the run */
   long long acq_lost_at;    /* symbol count at which tracking lost the peak, -1 never */
-  float ms_acq_fft;
+  float ms_resample, ms_acq_fft;
   float ms_demod, ms_inner, ms_viterbi, ms_viterbi_acs, ms_rs, ms_descramble; /* device time per stage */
 } dvbt_b200_rx_info;
 enum { DVBT_RX_STAGE_CELLS = 0, DVBT_RX_STAGE_DEMAP = 1, DVBT_RX_STAGE_BITDEINT = 2, DVBT_RX_STAGE_VITERBI = 3,
@@ -281,6 +281,14 @@ int dvbt_b200_rx_run_freq_dev(dvbt_b200_rx *h, const void *dX, size_t nsym, uint
  * including ofdm_sym_acquisition and the FFT: nsamples gr_complex. */
 int dvbt_b200_rx_run_baseband_host(dvbt_b200_rx *h, const void *samples, size_t nsamples, uint8_t *ts, size_t ts_capacity, size_t *ts_bytes);
 int dvbt_b200_rx_run_baseband_dev(dvbt_b200_rx *h, const void *d_samples, size_t nsamples, uint8_t *d_ts, size_t ts_capacity, size_t *ts_bytes);
+/* The whole RX flowgraph from the capture file: complex samples at 10 Msps ->
+ * rational_resampler_ccc(64,70) -> multiply_const(gain) -> the chain above.  gain is the flowgraph's
+ * multiply_const value (0.0022097087 for 2k, 0.00055242272 for 8k).  The resampler and FFT are stock
+ * GNU Radio blocks (not part of gr-dvbt); they follow GNU Radio 3.7's documented behaviour. */
+int dvbt_b200_rx_run_file_host(dvbt_b200_rx *h, const void *samples, size_t nsamples, float gain, uint8_t *ts, size_t ts_capacity, size_t *ts_bytes);
+int dvbt_b200_rx_run_file_dev(dvbt_b200_rx *h, const void *d_samples, size_t nsamples, float gain, uint8_t *d_ts, size_t ts_capacity, size_t *ts_bytes);
+/* the 32/35 low-pass prototype used by the resampler; returns its length */
+int dvbt_b200_resampler_taps(float *taps, int capacity);
 int dvbt_b200_rx_last_info(const dvbt_b200_rx *h, dvbt_b200_rx_info *info);
 /* copies an intermediate of the last run to the host (parity tests): DVBT_RX_STAGE_* */
 int dvbt_b200_rx_read_stage(dvbt_b200_rx *h, int stage, void *host_out, size_t capacity_bytes, size_t *nbytes);

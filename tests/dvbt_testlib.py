@@ -57,3 +57,11 @@ def ofdm_modulate(X, tm, gain=None, offset=0, cfo_bins=0.0, noise=0.0, seed=0):
         rms = np.sqrt(np.mean(np.abs(t) ** 2))
         t = t + (rng.normal(0, noise * rms, len(t)) + 1j * rng.normal(0, noise * rms, len(t)))
     return t.astype(np.complex64)
+
+
+def to_capture_rate(x):
+    """64/7 Msps -> 10 Msps, the job of rational_resampler(70, 64) in the TX flowgraphs
+    (polyphase 35/32 with a Kaiser-windowed low-pass; scipy's design, not GNU Radio's taps)."""
+    from scipy.signal import resample_poly
+    y = resample_poly(x.astype(np.complex128), 35, 32, window=("kaiser", 7.0))
+    return y.astype(np.complex64)
