@@ -272,7 +272,7 @@ class RxWorkload:
         return int(n.value)
 
     def check(self):
-        ts = self.d_ts[: min(self.ts_bytes, 188 * 4000)].cpu().numpy()
+        ts = self.d_ts[: min(self.ts_bytes, 188 * 3000)].cpu().numpy()
         ref = self.ts_src[1328 * 188: 1328 * 188 + len(ts)]
         n = min(len(ts), len(ref))
         return bool(n > 188 * 100 and np.array_equal(ts[:n], ref[:n]) and self.info["acq_lost_at"] == -1)
@@ -478,6 +478,8 @@ def main():
         line = {"metric": metric, "value": value, "unit": unit, "n_gpus": WORLD, "steps": a.steps, "warmup": a.warmup,
                 "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8/f32" if rx else "u8",
                 "config": w.describe(), "parity_check": ok, "gpu_launches": int(launches), "clocks": clocks}
+        if rx:
+            line["chain_info"] = {k: v for k, v in w.info.items() if not k.startswith("ms_")}
         if rx:
             vbits = w.viterbi_bits
             stage = {k: float(np.mean([s[k] for s in w.stage_ms[a.warmup:]])) for k in w.stage_ms[-1]}

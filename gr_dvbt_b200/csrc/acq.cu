@@ -182,179 +182,170 @@ __global__ void acq_lambda_kernel(AcqParams p, const float2 *__restrict__ x, lon
   ml_point(x, base + (long long)n * (p.N + p.cp) + c0 - kD + c, p.N, p.cp, p.rho2, &lambda[t], &gamma[t]);
 }
 
-// speculative per-symbol detector: window = candidates [kD-8, kD+8) (cp_start == c0)
-__global__ void acq_track_kernel(AcqParams p, int nsym, const float *__restrict__ lambda, const float *__restrict__ avg_in,
-                                 float avg_first, float *__restrict__ avg_out, int *__restrict__ peak_out,
-                                 const float2 *__restrict__ gamma, float *__restrict__ eps_out) {
-  int n = blockIdx.x * blockDim.x + threadIdx.x;
-  if (n >= nsym) return;
-  float avg = avg_in ? (n == 0 ? avg_first : avg_in[n - 1]) : 0.f;
-  int best = 0;
-  int np = peak_detect(lambda + (long long)n * kCand + (kD - 8), 16, &avg, p.rise, p.fall, p.alpha, &best);
-  avg_out[n] = avg;
-  if (peak_out) peak_out[n] = np > 0 ? best : -1;
-  if (eps_out) {
-    float2 g = gamma[(long long)n * kCand + (kD - 8) + best];
-    eps_out[n] = np > 0 ? atan2f(g.y, g.x) : 0.f;  // fast_atan2f(d_gamma[peak]) (:277)
+// ---- speculative tracking tables --------------------------------------------------------------
+// The reference state that crosses symbols is (cp_start, d_avg) plus the phase schedule.  cp_start
+// moves by (best - 8) per symbol; the table covers window offsets c = 0..kNC-1 (window = candidates
+// [c, c+16), cp_start = c0 - kD + 8 + c).  d_avg after the 16 values of a window is, to float
+// precision, independent of the average it started from, so it is speculated:
+//   pass 1: avg1[n][c]      = average after window (n, c) starting from 0
+//   pass 2: best2/avg2[n][c][d] = detector result of window (n, c) starting from avg1[n-1][c+d], d in {-1,0,1}
+//           (the previous symbol sat at offset c+d); ok0[n][c] = "no timing move and avg2 == avg1" for d = 0
+// acq_walk_kernel then follows the true path, checking bit-for-bit that every speculated input equals
+// the true average, and runs the plain sequential detector for any symbol where it does not.
+constexpr int kNC = kCand - 16 + 1;  // 17 window offsets
+
+__global__ void acq_pass1_kernel(AcqParams p, int nsym, const float *__restrict__ lambda, float *__restrict__ avg1) {
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= nsym * kNC) return;
+  int n = t / kNC, c = t - n * kNC;
+  float avg = 0.f;
+  int best;
+  peak_detect(lambda + (long long)n * kCand + c, 16, &avg, p.rise, p.fall, p.alpha, &best);
+  avg1[t] = avg;
+}
+
+__global__ void acq_pass2_kernel(AcqParams p, int nsym, const float *__restrict__ lambda, const float *__restrict__ avg1, float avg_first,
+                                 signed char *__restrict__ best2, float *__restrict__ avg2, unsigned char *__restrict__ ok0) {
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= nsym * kNC * 3) return;
+  int n = t / (kNC * 3), r = t - n * (kNC * 3), c = r / 3, d = r - c * 3 - 1;
+  int cp = c + d;
+  signed char res = -2;  // -2: no speculation available
+  float avg = 0.f;
+  if (n == 0 || (cp >= 0 && cp < kNC)) {
+    avg = n == 0 ? avg_first : avg1[(n - 1) * kNC + cp];
+    int best;
+    int np = peak_detect(lambda + (long long)n * kCand + c, 16, &avg, p.rise, p.fall, p.alpha, &best);
+    res = np > 0 ? (signed char)best : (signed char)-1;
   }
+  best2[t] = res;
+  avg2[t] = avg;
+  if (d == 0) ok0[n * kNC + c] = (res == 8 && __float_as_uint(avg) == __float_as_uint(avg1[n * kNC + c])) ? 1 : 0;
 }
 
-// speculation holds for the whole batch iff every symbol found its peak at the centre of the window
-// (cp_start unchanged) and every average fed forward in pass 2 equals the one pass 2 produced
-__global__ void acq_verify_kernel(int nsym, const float *__restrict__ avg1, const float *__restrict__ avg2,
-                                  const int *__restrict__ peak2, int *first_bad) {
-  int n = blockIdx.x * blockDim.x + threadIdx.x;
-  if (n >= nsym) return;
-  bool bad = peak2[n] != 8;
-  if (n + 1 < nsym && __float_as_uint(avg1[n]) != __float_as_uint(avg2[n])) bad = true;
-  if (bad) atomicMin(first_bad, n);
-}
-
-// whole batch verified: per-symbol output descriptors and the end state, one warp, no dependent loads
-__global__ void __launch_bounds__(32) acq_fast_kernel(AcqParams p, int nsym, long long base, int c0, const float *__restrict__ eps,
-                                                      const float *__restrict__ avg2, const int *first_bad, AcqState *st,
-                                                      SymOut *__restrict__ out) {
-  if (*first_bad < nsym) return;
+// The sequential walk (one warp).  Runs of "nothing happens" symbols (ok0) are handled 32 at a time;
+// everything else one symbol at a time.  Produces the per-symbol output descriptors and the end state.
+__global__ void __launch_bounds__(32) acq_walk_kernel(AcqParams p, int nsym, long long base, int c0, const float *__restrict__ lambda,
+                                                      const float2 *__restrict__ gamma, const float *__restrict__ avg1,
+                                                      const signed char *__restrict__ best2, const float *__restrict__ avg2,
+                                                      const unsigned char *__restrict__ ok0, AcqState *st, SymOut *__restrict__ out) {
   const int lane = threadIdx.x;
   const int total = p.N + p.cp;
   const double invN = -1.0 / (double)p.N;
-  const int sw = c0 - total;                       // d_nextpos left by every symbol (:312)
-  const bool sw_ok = sw >= 0 && sw < total;
-  const int sw0 = st->nextpos;
-  const bool sw0_ok = sw0 >= 0 && sw0 < total;
-  const double inc_init = st->phaseinc, pend_init = st->nextphaseinc;
-  const double inc_after0 = sw0_ok ? pend_init : inc_init;  // d_phaseinc after symbol 0
-  double carry = st->phase;                         // phase before symbol `base_n`
-  double last_inc = inc_init;
-  for (int bn = 0; bn < nsym; bn += 32) {
-    int n = bn + lane;
-    double i0 = 0, i1 = 0, adv = 0;
-    int swn = total;
-    if (n < nsym) {
-      if (n == 0) {
-        i0 = inc_init; i1 = pend_init; swn = sw0_ok ? sw0 : total;
-      } else {
-        double e1 = invN * (double)eps[n - 1];
-        // increment in force when symbol n starts: what symbol n-1 switched to (or kept)
-        double start = (n == 1) ? inc_after0 : (sw_ok ? invN * (double)eps[n - 2] : inc_after0);
-        i0 = start; i1 = e1; swn = sw_ok ? sw : total;
-      }
-      adv = swn < total ? swn * i0 + (total - swn) * i1 : total * i0;
-    }
-    // inclusive warp scan of the advances
-    double incl = adv;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      double t = __shfl_up_sync(0xffffffffu, incl, o);
-      if (lane >= o) incl += t;
-    }
-    if (n < nsym) {
-      SymOut so;
-      so.first = base + (long long)n * total + c0 - p.N + 1;
-      so.phase0 = remainder(carry + (incl - adv), 2.0 * M_PI);
-      so.inc0 = i0; so.inc1 = i1; so.switch_at = swn;
-      out[n] = so;
-    }
-    int lastl = min(31, nsym - 1 - bn);
-    carry = remainder(carry + __shfl_sync(0xffffffffu, incl, lastl), 2.0 * M_PI);
-    double li = (swn < total) ? i1 : i0;
-    last_inc = __shfl_sync(0xffffffffu, li, lastl);
-  }
-  if (lane == 0) {
-    st->avg = avg2[nsym - 1];
-    st->phase = (float)carry;
-    st->phaseinc = last_inc;
-    st->nextphaseinc = invN * (double)eps[nsym - 1];
-    st->nextpos = sw;
-    st->cp_start = c0;
-    st->n_out = nsym;
-    st->lost_at = -1;
-    st->fallback = 0;
-    st->consumed = (long long)nsym * total;
-  }
-}
-
-// verification + the light sequential bookkeeping; falls back to the sequential detector from the
-// first symbol whose speculation does not hold
-__global__ void acq_chain_kernel(AcqParams p, int nsym, long long base, int c0, const float *__restrict__ lambda,
-                                 const float2 *__restrict__ gamma, const float *__restrict__ avg1, const float *__restrict__ avg2,
-                                 const int *__restrict__ peak2, AcqState *st, SymOut *__restrict__ out, const int *first_bad) {
-  if (threadIdx.x != 0 || blockIdx.x != 0) return;
-  if (*first_bad >= nsym) return;  // acq_fast_kernel handled the batch
-  const int total = p.N + p.cp;
-  int cp_start = c0;
+  int c = kD - 8;            // window offset of the current symbol (cp_start == c0)
+  int d = 0;                 // offset of the previous symbol minus c
+  bool spec_valid = true;    // the speculated input of entry (n, c, d) equals the true average (n == 0: avg_first is the truth)
   float avg = st->avg;
-  double ph = st->phase, inc = st->phaseinc, nextinc = st->nextphaseinc;
+  double ph = st->phase, inc = st->phaseinc, pend = st->nextphaseinc;
   int nextpos = st->nextpos;
-  int n_out = 0, lost_at = -1, fallback = 0;
-  bool spec_ok = true;
-  for (int n = 0; n < nsym; n++) {
-    int found, best;
-    float2 g;
-    // speculation holds for symbol n if (a) we are still on the speculated timing, (b) the average
-    // it started from is the true one.  avg2[n] was computed from avg1[n-1]; the true incoming average
-    // is `avg` (exact by induction).
-    float spec_in = n == 0 ? st->avg : avg1[n - 1];
-    if (spec_ok && cp_start == c0 && __float_as_uint(spec_in) == __float_as_uint(avg)) {
-      best = peak2[n];
-      found = best >= 0;
-      avg = avg2[n];
-    } else {
-      // sequential detector on the true state
-      int lo = cp_start - 8 - (c0 - kD);
-      if (lo < 0 || lo + 16 > kCand) { lost_at = n; break; }  // drifted out of the table: stop here
-      fallback = 1;
-      found = peak_detect(lambda + (long long)n * kCand + lo, 16, &avg, p.rise, p.fall, p.alpha, &best) > 0;
-      if (!found) best = -1;
-      spec_ok = false;
-    }
-    int lo = cp_start - 8 - (c0 - kD);
-    SymOut so;
-    so.phase0 = ph;
-    so.inc0 = inc;
-    so.inc1 = inc;
-    so.switch_at = total;
-    if (found) {
-      if (nextpos >= 0 && nextpos < total) {  // :287-288
-        so.inc1 = nextinc;
-        so.switch_at = nextpos;
-        ph += nextpos * inc;
-        inc = nextinc;
-        ph += (total - nextpos) * inc;
-      } else {
-        ph += total * inc;
+  int n = 0, n_out = 0, lost_at = -1, fallback = 0;
+  while (n < nsym) {
+    // ---------- run of quiet symbols: entry (m, c, 0) valid, best == 8, avg2 == avg1
+    if (spec_valid && d == 0) {
+      int m = n + lane;
+      bool q = m < nsym && ok0[m * kNC + c];
+      unsigned bal = __ballot_sync(0xffffffffu, q);
+      int run = bal == 0xffffffffu ? 32 : __ffs(~bal) - 1;
+      if (run > 0) {
+        // all symbols of the run: peak = cp_start (unchanged), nextpos = cp_start - total, eps from gamma at the peak
+        int cp_start = c0 - kD + 8 + c;
+        int sw = cp_start - total;
+        bool sw_ok = sw >= 0 && sw < total;
+        bool sw0_ok = nextpos >= 0 && nextpos < total;
+        float2 g = (lane < run) ? gamma[(long long)m * kCand + c + 8] : make_float2(1.f, 0.f);
+        double e = invN * (double)atan2f(g.y, g.x);           // nextphaseinc produced by symbol m
+        double e1 = __shfl_up_sync(0xffffffffu, e, 1), e2 = __shfl_up_sync(0xffffffffu, e, 2);
+        double inc_after0 = sw0_ok ? pend : inc;              // increment in force after the first symbol of the run
+        double i0, i1;
+        int swn;
+        if (lane == 0) { i0 = inc; i1 = pend; swn = sw0_ok ? nextpos : total; }
+        else {
+          i0 = lane == 1 ? inc_after0 : (sw_ok ? e2 : inc_after0);
+          i1 = e1;
+          swn = sw_ok ? sw : total;
+        }
+        double adv = lane < run ? (swn < total ? swn * i0 + (total - swn) * i1 : total * i0) : 0.0;
+        double incl = adv;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          double t = __shfl_up_sync(0xffffffffu, incl, o);
+          if (lane >= o) incl += t;
+        }
+        if (lane < run) {
+          SymOut so;
+          so.first = base + (long long)m * total + cp_start - p.N + 1;
+          so.phase0 = remainder(ph + (incl - adv), 2.0 * M_PI);
+          so.inc0 = i0; so.inc1 = i1; so.switch_at = swn;
+          out[n_out + lane] = so;
+        }
+        int lastl = run - 1;
+        ph = remainder(ph + __shfl_sync(0xffffffffu, incl, lastl), 2.0 * M_PI);
+        double li = (swn < total) ? i1 : i0;
+        inc = __shfl_sync(0xffffffffu, li, lastl);
+        pend = __shfl_sync(0xffffffffu, e, lastl);
+        nextpos = sw;
+        avg = avg1[(n + lastl) * kNC + c];  // == avg2 of the last symbol of the run
+        n_out += run;
+        n += run;
+        continue;
       }
-      ph = remainder(ph, 2.0 * M_PI);
-      int peak = best + cp_start - 8;
-      g = gamma[(long long)n * kCand + lo + best];
-      float eps = atan2f(g.y, g.x);
-      nextinc = (-1.0 / (double)p.N) * (double)eps;  // :311
-      nextpos = peak - total;                        // :312
-      cp_start = peak;
-      so.first = base + (long long)n * total + cp_start - p.N + 1;
-      out[n_out++] = so;
+    }
+    // ---------- one symbol
+    int best;
+    bool found;
+    signed char sp = spec_valid ? best2[(n * kNC + c) * 3 + (d + 1)] : (signed char)-2;
+    if (sp != -2) {
+      best = sp;
+      found = best >= 0;
+      avg = avg2[(n * kNC + c) * 3 + (d + 1)];
     } else {
-      // missed peak: phase still advances (:335-343); timeout is 0 so acquisition restarts (:545-558)
-      ph = remainder(ph + total * inc, 2.0 * M_PI);
+      fallback = 1;
+      found = peak_detect(lambda + (long long)n * kCand + c, 16, &avg, p.rise, p.fall, p.alpha, &best) > 0;
+    }
+    int cp_start = c0 - kD + 8 + c;
+    SymOut so;
+    so.phase0 = ph; so.inc0 = inc; so.inc1 = inc; so.switch_at = total;
+    if (!found) {
+      ph = remainder(ph + total * inc, 2.0 * M_PI);  // :335-343
       lost_at = n;
       break;
     }
+    if (nextpos >= 0 && nextpos < total) {           // :287-288
+      so.inc1 = pend; so.switch_at = nextpos;
+      ph += nextpos * inc;
+      inc = pend;
+      ph += (total - nextpos) * inc;
+    } else {
+      ph += total * inc;
+    }
+    ph = remainder(ph, 2.0 * M_PI);
+    int peak = best + cp_start - 8;
+    float2 g = gamma[(long long)n * kCand + c + best];
+    pend = invN * (double)atan2f(g.y, g.x);          // :311
+    nextpos = peak - total;                          // :312
+    so.first = base + (long long)n * total + peak - p.N + 1;
+    if (lane == 0) out[n_out] = so;
+    n_out++;
+    // next symbol's table entry: offset c' = c + best - 8, came from offset c (d' = c - c')
+    int cn = c + best - 8;
+    int dn = c - cn;
+    // its speculated input is avg1[n][c]; valid iff that is the true average now
+    bool next_valid = (dn >= -1 && dn <= 1) && __float_as_uint(avg1[n * kNC + c]) == __float_as_uint(avg);
+    n++;
+    if (cn < 0 || cn >= kNC) { c = cn; lost_at = n; break; }  // left the table: the host re-centres it
+    c = cn; d = dn; spec_valid = next_valid;
   }
-  st->avg = avg;
-  st->phase = (float)ph;
-  st->phaseinc = inc;
-  st->nextphaseinc = nextinc;
-  st->nextpos = nextpos;
-  st->cp_start = cp_start;
-  st->n_out = n_out;
-  st->lost_at = lost_at;
-  st->fallback = 1;
-  (void)fallback;
-  if (lost_at >= 0) {
-    // symbols 0..lost_at-1 consumed N+cp each; the miss consumes N+cp (table overrun) or half of it (restart)
-    st->consumed = (long long)lost_at * total;
-  } else {
-    st->consumed = (long long)nsym * total;
+  if (lane == 0) {
+    st->avg = avg;
+    st->phase = (float)ph;
+    st->phaseinc = inc;
+    st->nextphaseinc = pend;
+    st->nextpos = nextpos;
+    st->cp_start = c0 - kD + 8 + c;
+    st->n_out = n_out;
+    st->lost_at = lost_at;
+    st->fallback = fallback;
+    st->consumed = (long long)(lost_at >= 0 ? lost_at : nsym) * total;
   }
 }
 
@@ -436,20 +427,18 @@ int acq_run(dvbt_b200_acq *h, const float2 *x, long long n, float2 *d_out, long 
       long long threads = nsym * kCand;
       acq_lambda_kernel<<<(unsigned)((threads + 127) / 128), 128, 0, st>>>(p, x, pos, c0, (int)nsym, h->d_lambda.as<float>(),
                                                                           h->d_gamma.as<float2>());
-      unsigned g = (unsigned)((nsym + 127) / 128);
-      if ((rc = h->d_eps.reserve((size_t)nsym * 4)) || (rc = h->d_flag.reserve(16))) return rc;
-      int big = 0x7fffffff;
-      DVBT_CUDA_TRY(cudaMemcpyAsync(h->d_flag.p, &big, 4, cudaMemcpyHostToDevice, st));
-      acq_track_kernel<<<g, 128, 0, st>>>(p, (int)nsym, h->d_lambda.as<float>(), nullptr, 0.f, h->d_avg1.as<float>(), nullptr, nullptr, nullptr);
-      acq_track_kernel<<<g, 128, 0, st>>>(p, (int)nsym, h->d_lambda.as<float>(), h->d_avg1.as<float>(), hs->avg, h->d_avg2.as<float>(),
-                                          h->d_peak.as<int>(), h->d_gamma.as<float2>(), h->d_eps.as<float>());
-      acq_verify_kernel<<<g, 128, 0, st>>>((int)nsym, h->d_avg1.as<float>(), h->d_avg2.as<float>(), h->d_peak.as<int>(), h->d_flag.as<int>());
-      acq_fast_kernel<<<1, 32, 0, st>>>(p, (int)nsym, pos, c0, h->d_eps.as<float>(), h->d_avg2.as<float>(), h->d_flag.as<int>(),
+      if ((rc = h->d_avg1.reserve((size_t)nsym * kNC * 4)) || (rc = h->d_avg2.reserve((size_t)nsym * kNC * 3 * 4)) ||
+          (rc = h->d_peak.reserve((size_t)nsym * kNC * 3)) || (rc = h->d_flag.reserve((size_t)nsym * kNC)))
+        return rc;
+      long long t1 = nsym * kNC, t2 = t1 * 3;
+      acq_pass1_kernel<<<(unsigned)((t1 + 127) / 128), 128, 0, st>>>(p, (int)nsym, h->d_lambda.as<float>(), h->d_avg1.as<float>());
+      acq_pass2_kernel<<<(unsigned)((t2 + 127) / 128), 128, 0, st>>>(p, (int)nsym, h->d_lambda.as<float>(), h->d_avg1.as<float>(), hs->avg,
+                                                                    h->d_peak.as<signed char>(), h->d_avg2.as<float>(),
+                                                                    h->d_flag.as<unsigned char>());
+      acq_walk_kernel<<<1, 32, 0, st>>>(p, (int)nsym, pos, c0, h->d_lambda.as<float>(), h->d_gamma.as<float2>(), h->d_avg1.as<float>(),
+                                        h->d_peak.as<signed char>(), h->d_avg2.as<float>(), h->d_flag.as<unsigned char>(),
                                         h->d_state.as<AcqState>(), h->d_sym.as<SymOut>());
-      acq_chain_kernel<<<1, 32, 0, st>>>(p, (int)nsym, pos, c0, h->d_lambda.as<float>(), h->d_gamma.as<float2>(), h->d_avg1.as<float>(),
-                                         h->d_avg2.as<float>(), h->d_peak.as<int>(), h->d_state.as<AcqState>(), h->d_sym.as<SymOut>(),
-                                         h->d_flag.as<int>());
-      count_launch(6);
+      count_launch(4);
       DVBT_CUDA_TRY(cudaGetLastError());
     }
     DVBT_CUDA_TRY(cudaMemcpyAsync(hs, h->d_state.p, sizeof(AcqState), cudaMemcpyDeviceToHost, st));

@@ -333,19 +333,29 @@ __global__ void demod_vote_kernel(int ntps, int nparse, const float2 *__restrict
 // the lanes fetch 32 symbols' (phase, vote) with one coalesced load each, then every lane runs
 // the same state machine on shuffled values (no divergence); lane 0 writes the results.  The
 // 68-entry TPS FIFO (d_rcv_tps_data) is a bit set: entry i = bit i of (lo, hi).
-__device__ bool tps_bch_ok_bits(unsigned long long lo, unsigned hi) {
-  auto bit = [&](int i) -> unsigned { return i < 64 ? (unsigned)((lo >> i) & 1ull) : ((hi >> (i - 64)) & 1u); };
+// The BCH remainder is linear in the 53 data bits (FIFO entries 1..53): lane j keeps the 14-bit
+// remainder R[j] of the unit vector at data bit j (and j+32), computed once per launch with the
+// reference's LFSR; a check is then one masked XOR per lane and a 5-step warp reduction.
+__device__ unsigned tps_bch_unit_remainder(int j) {
   unsigned reg = 0;
   for (int i = 0; i < 113; i++) {
-    unsigned b = i < 60 ? 0u : bit(1 + (i - 60));
+    unsigned b = (i == 60 + j) ? 1u : 0u;
     unsigned fb = 1u & (b ^ reg);
     reg >>= 1;
     reg |= fb << 13;
     reg ^= (fb << 12) ^ (fb << 11) ^ (fb << 9) ^ (fb << 8) ^ (fb << 7) ^ (fb << 5) ^ (fb << 4);
   }
-  for (int i = 0; i < 14; i++)
-    if (bit(i + 54) != (1u & (reg >> i))) return false;
-  return true;
+  return reg;
+}
+// all 32 lanes must call this together
+__device__ bool tps_bch_ok_bits(unsigned long long lo, unsigned hi, unsigned r_lo, unsigned r_hi, int lane) {
+  unsigned long long data = lo >> 1;  // data bit j = FIFO entry 1 + j
+  unsigned acc = ((data >> lane) & 1ull) ? r_lo : 0u;
+  if (lane + 32 < 53 && ((data >> (lane + 32)) & 1ull)) acc ^= r_hi;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc ^= __shfl_xor_sync(0xffffffffu, acc, o);
+  unsigned parity = (unsigned)((lo >> 54) & 0x3FFull) | ((hi & 0xFu) << 10);  // entries 54..67
+  return parity == (acc & 0x3FFFu);
 }
 
 // parity of the BCH check as 14 linear forms would be faster still; the LFSR runs once per frame
@@ -366,6 +376,7 @@ __global__ void __launch_bounds__(32) demod_scan_kernel(int ntps, int nparse, in
   for (int i = 64; i < 68; i++) hi |= (unsigned)(st->fifo[i] & 1) << (i - 64);
   int first_out = -1, n_out = 0, sf_tag_at = -1;
   if (sync_start_at0) d_init = 0;  // :115-116
+  const unsigned r_lo = tps_bch_unit_remainder(lane), r_hi = lane + 32 < 53 ? tps_bch_unit_remainder(lane + 32) : 0u;
   int cbase = -1000, my_mod = 0, my_vote = 0;  // cached chunk of 32 symbols for the symbol-by-symbol path
   int s = 0;
   while (s < nparse) {
@@ -394,7 +405,7 @@ __global__ void __launch_bounds__(32) demod_scan_kernel(int ntps, int nparse, in
         if (e == kEven || e == (kEven ^ kMask)) early = true;
       }
       bool match = ((flo & kMask) == kEven) || ((flo & kMask) == (kEven ^ kMask));
-      if (good && !early && match && tps_bch_ok_bits(flo, fhi)) {
+      if (good && !early && match && tps_bch_ok_bits(flo, fhi, r_lo, r_hi, lane)) {
         bool emit = true;
         if (d_init == 0) {
           if ((frame_index & 3) == fi_start) { d_init = 1; sf_tag_at = n_out; }
@@ -441,7 +452,7 @@ __global__ void __launch_bounds__(32) demod_scan_kernel(int ntps, int nparse, in
     bool even = (lo & kMask) == kEven, odd = (lo & kMask) == (kEven ^ kMask);
     int end_frame = 0;
     if (even || odd) {
-      if (tps_bch_ok_bits(lo, hi)) {
+      if (tps_bch_ok_bits(lo, hi, r_lo, r_hi, lane)) {
         frame_index = (int)((((lo >> 23) & 1ull) << 1) | ((lo >> 24) & 1ull));
         known = 1;
         end_frame = 1;
