@@ -126,6 +126,7 @@ struct AcqState {
   int n_sync_tags;    // sync_start tags (first symbol of a (re)acquisition)
   int lost_at;        // symbol count at which tracking missed (restart), -1 if never
   int fallback;       // 1 if the sequential detector had to be used
+  int n_run, n_single, n_seq;  // symbols handled in quiet runs / one at a time / by the sequential detector
 };
 
 struct SymOut {
@@ -239,6 +240,7 @@ __global__ void __launch_bounds__(32) acq_walk_kernel(AcqParams p, int nsym, lon
   double ph = st->phase, inc = st->phaseinc, pend = st->nextphaseinc;
   int nextpos = st->nextpos;
   int n = 0, n_out = 0, lost_at = -1, fallback = 0;
+  int c_run = 0, c_single = 0, c_seq = 0;
   while (n < nsym) {
     // ---------- run of quiet symbols: entry (m, c, 0) valid, best == 8, avg2 == avg1
     if (spec_valid && d == 0) {
@@ -287,10 +289,12 @@ __global__ void __launch_bounds__(32) acq_walk_kernel(AcqParams p, int nsym, lon
         avg = avg1[(n + lastl) * kNC + c];  // == avg2 of the last symbol of the run
         n_out += run;
         n += run;
+        c_run += run;
         continue;
       }
     }
     // ---------- one symbol
+    c_single++;
     int best;
     bool found;
     signed char sp = spec_valid ? best2[(n * kNC + c) * 3 + (d + 1)] : (signed char)-2;
@@ -300,6 +304,7 @@ __global__ void __launch_bounds__(32) acq_walk_kernel(AcqParams p, int nsym, lon
       avg = avg2[(n * kNC + c) * 3 + (d + 1)];
     } else {
       fallback = 1;
+      c_seq++;
       found = peak_detect(lambda + (long long)n * kCand + c, 16, &avg, p.rise, p.fall, p.alpha, &best) > 0;
     }
     int cp_start = c0 - kD + 8 + c;
@@ -345,6 +350,7 @@ __global__ void __launch_bounds__(32) acq_walk_kernel(AcqParams p, int nsym, lon
     st->n_out = n_out;
     st->lost_at = lost_at;
     st->fallback = fallback;
+    st->n_run += c_run; st->n_single += c_single; st->n_seq += c_seq;
     st->consumed = (long long)(lost_at >= 0 ? lost_at : nsym) * total;
   }
 }
@@ -514,7 +520,7 @@ int acq_run_simple(dvbt_b200_acq *h, const float2 *x, long long n, float2 *d_out
   AcqState hs;
   int rc = acq_run(h, x, n, d_out, out_capacity_syms, do_fft, &hs);
   if (rc) return rc;
-  if (res) { res->consumed = hs.consumed; res->n_out = hs.n_out; res->lost_at = hs.lost_at; res->fallback = hs.fallback; res->cp_start = hs.cp_start; }
+  if (res) { res->n_run = hs.n_run; res->n_single = hs.n_single; res->n_seq = hs.n_seq; res->consumed = hs.consumed; res->n_out = hs.n_out; res->lost_at = hs.lost_at; res->fallback = hs.fallback; res->cp_start = hs.cp_start; }
   return 0;
 }
 

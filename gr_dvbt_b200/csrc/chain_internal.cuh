@@ -16,7 +16,7 @@ int vit_collect_stats(dvbt_b200_viterbi *h);
 int rs_launch(const uint8_t *d_in, uint8_t *d_out, int *d_status, long long npackets, int as_built, int sm_count,
               cudaStream_t st, long long gather_stream_bytes);
 
-struct AcqResult { long long consumed; int n_out, lost_at, fallback, cp_start; };
+struct AcqResult { long long consumed; int n_out, lost_at, fallback, cp_start, n_run, n_single, n_seq; };
 }  // namespace dvbt
 struct dvbt_b200_acq;
 namespace dvbt {

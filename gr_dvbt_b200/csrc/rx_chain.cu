@@ -407,6 +407,9 @@ static int rx_run_baseband(dvbt_b200_rx *h, const float2 *d_x, size_t nsamples, 
   h->info.acq_symbols = ar.n_out;
   h->info.acq_cp_start = ar.cp_start;
   h->info.acq_lost_at = ar.lost_at;
+  h->info.acq_run_symbols = ar.n_run;
+  h->info.acq_single_symbols = ar.n_single;
+  h->info.acq_sequential_symbols = ar.n_seq;
   float ms;
   if (cudaEventElapsedTime(&ms, h->ev[6], h->ev[7]) == cudaSuccess) h->info.ms_acq_fft = ms;
   return rc;

@@ -264,6 +264,7 @@ typedef struct dvbt_b200_rx_info {
   long long acq_symbols;    /* symbols produced by acquisition (baseband entry) */
   long long acq_cp_start;   /* d_cp_start after the run */
   long long acq_lost_at;    /* symbol count at which tracking lost the peak, -1 never */
+  long long acq_run_symbols, acq_single_symbols, acq_sequential_symbols; /* how the tracker handled the symbols */
   float ms_resample, ms_acq_fft;
   float ms_demod, ms_inner, ms_viterbi, ms_viterbi_acs, ms_rs, ms_descramble; /* device time per stage */
 } dvbt_b200_rx_info;

@@ -85,6 +85,8 @@ class block {
   bool is_unaligned() { return true; }
   void set_history(unsigned) {}
   void set_tag_propagation_policy(int) {}
+  void set_min_noutput_items(int) {}
+  void set_min_output_buffer(long) {}
 
   void consume_each(int n) { h_consumed = n; }
   uint64_t nitems_read(unsigned) { return h_nread; }

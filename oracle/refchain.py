@@ -17,6 +17,12 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 REF_SO = os.path.join(HERE, "_ref", "libdvbt_ref.so")
 REF_RSFIX_SO = os.path.join(HERE, "_ref", "libdvbt_ref_rsfix.so")
+# the B200 gr::block shims behind the same harness entry points (gr_dvbt_b200/shim/shim_harness.cc):
+# names listed in SHIM_BLOCKS are created from it instead of from the reference build, so a chain can
+# be run with the hot blocks swapped and every other block still the reference's
+SHIM_SO = os.path.join(os.path.dirname(HERE), "gr_dvbt_b200", "shim", "libdvbt_b200_shim_test.so")
+SHIM_BLOCKS = set()
+HOT_BLOCKS = ("ofdm_sym_acquisition", "demod_reference_signals", "dvbt_demap", "viterbi_decoder", "reed_solomon_dec")
 
 # enums of include/dvbt/dvbt_config.h:34-76 (values are the TPS codes)
 QPSK, QAM16, QAM64 = 0, 1, 2
@@ -37,8 +43,12 @@ def available(fixed_rs=False):
 _libs = {}
 
 
-def _lib(fixed_rs=False):
-    path = REF_RSFIX_SO if fixed_rs else REF_SO
+def shim_available():
+    return os.path.exists(SHIM_SO)
+
+
+def _lib(fixed_rs=False, shim=False):
+    path = SHIM_SO if shim else (REF_RSFIX_SO if fixed_rs else REF_SO)
     if path not in _libs:
         # RTLD_LOCAL: the two variants define the same symbols
         lib = C.CDLL(path, mode=os.RTLD_LOCAL | os.RTLD_NOW)
@@ -79,7 +89,7 @@ class RefBlock:
     """One reference block instance; args follow its make() signature."""
 
     def __init__(self, name, *args, fixed_rs=False, quiet=True):
-        self.lib = _lib(fixed_rs)
+        self.lib = _lib(fixed_rs, shim=name in SHIM_BLOCKS)
         self.name = name
         self.quiet = quiet
         arr = (C.c_double * max(1, len(args)))(*[float(a) for a in args])

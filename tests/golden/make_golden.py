@@ -1,0 +1,97 @@
+#!/usr/bin/env python3
+"""Generates the committed golden fixtures from the reference itself (oracle/_ref: the
+reference's sources compiled verbatim).  Run in the build container, where /root/reference
+exists:  python tests/golden/make_golden.py
+The fixtures pin the C restatements in oracle/port (tests/test_oracle_cpu.py) and are also
+used by the GPU tests, so parity does not depend on oracle/_ref being present at test time."""
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+from oracle import refchain as R, port as O  # noqa: E402
+
+
+def viterbi_vectors():
+    out = {}
+    for rate in range(5):
+        for m in (2, 4, 6):
+            k, n = O.RATE_KN[rate]
+            data = np.random.default_rng(1000 + 10 * rate + m).integers(0, 256, 3 * 96 * k, dtype=np.uint8)
+            # the encoder of the port is itself pinned here against the reference's inner_coder block
+            rx = O.conv_encode(data, m, rate)
+            for ber in (0.0, 0.02):
+                rxn = O.flip_bits(rx, m, ber, 7) if ber else rx
+                ref, _ = R.rx_viterbi(rxn, {2: 0, 4: 1, 6: 2}[m], rate, None, blocks_per_call=2)
+                out["vit_in_r%d_m%d_b%d" % (rate, m, int(ber * 100))] = rxn
+                out["vit_out_r%d_m%d_b%d" % (rate, m, int(ber * 100))] = ref
+    return out
+
+
+def rs_vectors():
+    rng = np.random.default_rng(42)
+    npk = 8 * 12
+    data = rng.integers(0, 256, (npk, 188), dtype=np.uint8)
+    cw = np.zeros(npk * 204, np.uint8)
+    R.RefBlock("reed_solomon_enc", 2, 8, 0x11D, 255, 239, 8, 51, 8).work(npk // 8, npk // 8, data.reshape(-1).copy(), cw)
+    rx = cw.reshape(npk, 204).copy()
+    nerr = np.arange(npk) % 12
+    for p in range(npk):
+        pos = rng.choice(204, nerr[p], replace=False)
+        rx[p, pos] ^= rng.integers(1, 256, nerr[p], dtype=np.uint8)
+    res = {"rs_data": data, "rs_codewords": cw.reshape(npk, 204), "rs_rx": rx}
+    for fixed in (False, True):
+        out = np.zeros(npk * 188, np.uint8)
+        R.RefBlock("reed_solomon_dec", 2, 8, 0x11D, 255, 239, 8, 51, 8, fixed_rs=fixed).work(npk // 8, npk // 8, rx.reshape(-1).copy(), out)
+        res["rs_out_fixed" if fixed else "rs_out_asbuilt"] = out.reshape(npk, 188)
+    return res
+
+
+def demap_vectors():
+    res = {}
+    rng = np.random.default_rng(3)
+    for con in (0, 1, 2):
+        pts = O.constellation_points(con)
+        n = 1512 * 2
+        idx = rng.integers(0, len(pts), n)
+        c = (pts[idx] + (rng.normal(0, 0.15, n) + 1j * rng.normal(0, 0.15, n))).astype(np.complex64)
+        mids = ((pts[:, None] + pts[None, :]) / 2).reshape(-1).astype(np.complex64)
+        c[: min(len(mids), n)] = mids[:n]
+        res["demap_in_c%d" % con] = c
+        res["demap_out_c%d" % con] = R.rx_demap(c.reshape(2, 1512), con, R.T2k).reshape(-1)
+    return res
+
+
+def inner_coder_vectors():
+    """reference inner_coder output for a known input: pins oracle.port.conv_encode"""
+    res = {}
+    for rate, con in ((0, 1), (4, 2), (2, 0)):
+        k, n = O.RATE_KN[rate]
+        m = R.BITS_PER_CELL[con]
+        nbytes = 4 * 1512 * k * m // (8 * n)  # inner_coder consumes this for 4 items (inner_coder_impl.cc:254)
+        data = np.random.default_rng(77 + rate).integers(0, 256, nbytes, dtype=np.uint8)
+        ic = np.zeros(4 * 1512, np.uint8)
+        R.RefBlock("inner_coder", 1, 1512, con, R.NH, rate).work(4, 0, data, ic)
+        res["ic_in_r%d_c%d" % (rate, con)] = data
+        res["ic_out_r%d_c%d" % (rate, con)] = ic
+    return res
+
+
+def main():
+    assert R.available() and R.available(True), "build oracle/_ref first (make -C oracle ref)"
+    d = {}
+    d.update(viterbi_vectors())
+    d.update(rs_vectors())
+    d.update(demap_vectors())
+    d.update(inner_coder_vectors())
+    path = os.path.join(HERE, "hotpath_golden.npz")
+    np.savez_compressed(path, **d)
+    print("wrote", path, os.path.getsize(path), "bytes,", len(d), "arrays")
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,91 @@
+"""CPU tests: the C restatements (oracle/port) against the committed golden fixtures that were
+generated from the reference itself (tests/golden/make_golden.py), and — where oracle/_ref was built —
+against the reference build directly."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import port as O, refchain as R
+
+G = np.load(os.path.join(os.path.dirname(__file__), "golden", "hotpath_golden.npz"))
+CON = {2: 0, 4: 1, 6: 2}
+
+
+@pytest.mark.parametrize("rate", range(5))
+@pytest.mark.parametrize("m", [2, 4, 6])
+@pytest.mark.parametrize("ber", [0, 2])
+def test_viterbi_port_matches_golden(rate, m, ber):
+    rx = G["vit_in_r%d_m%d_b%d" % (rate, m, ber)]
+    want = G["vit_out_r%d_m%d_b%d" % (rate, m, ber)]
+    got = O.Viterbi(m, rate).work(rx)
+    assert np.array_equal(got, want)
+
+
+def test_viterbi_port_block_calls_and_reset():
+    """general_work semantics: ntraceback bytes are withheld once after each reset"""
+    rate, m = 2, 4
+    k, n = O.RATE_KN[rate]
+    data = np.random.default_rng(5).integers(0, 256, 6 * 96 * k, dtype=np.uint8)
+    rx = O.conv_encode(data, m, rate)
+    v = O.Viterbi(m, rate)
+    a = v.work(rx[: 2 * v.in_per_block])
+    b = v.work(rx[2 * v.in_per_block:])
+    assert len(a) == 2 * v.out_per_block - v.ntb and len(b) == 4 * v.out_per_block
+    whole = O.Viterbi(m, rate).work(rx)
+    assert np.array_equal(np.concatenate([a, b]), whole)
+    assert np.array_equal(whole, data[: len(whole)])
+    v.reset()
+    c = v.work(rx[: v.in_per_block])
+    assert np.array_equal(c, data[: len(c)])
+
+
+@pytest.mark.parametrize("key,rate,con", [("r0_c1", 0, 1), ("r4_c2", 4, 2), ("r2_c0", 2, 0)])
+def test_conv_encoder_matches_reference_inner_coder(key, rate, con):
+    m = R.BITS_PER_CELL[con]
+    assert np.array_equal(O.conv_encode(G["ic_in_" + key], m, rate), G["ic_out_" + key])
+
+
+def test_rs_port_matches_golden_both_builds():
+    rx = G["rs_rx"]
+    out_fixed, st = O.rs_decode(rx, as_built=False)
+    out_asb, _ = O.rs_decode(rx, as_built=True)
+    assert np.array_equal(out_fixed, G["rs_out_fixed"])
+    assert np.array_equal(out_asb, G["rs_out_asbuilt"])
+    nerr = np.arange(len(rx)) % 12
+    good = nerr <= 8
+    assert np.array_equal(out_fixed[good], G["rs_data"][good])
+    assert (st[good] == nerr[good]).all() and (st[~good] == -1).all()
+    assert np.array_equal(O.rs_encode(G["rs_data"]), G["rs_codewords"])
+
+
+@pytest.mark.parametrize("con", [0, 1, 2])
+def test_demap_port_matches_golden(con):
+    assert np.array_equal(O.demap(G["demap_in_c%d" % con], con), G["demap_out_c%d" % con])
+
+
+@pytest.mark.skipif(not R.available(), reason="oracle/_ref not built")
+def test_ports_match_the_reference_build_on_fresh_inputs():
+    rate, m = 4, 6
+    k, n = O.RATE_KN[rate]
+    data = np.random.default_rng(99).integers(0, 256, 4 * 96 * k, dtype=np.uint8)
+    rx = O.flip_bits(O.conv_encode(data, m, rate), m, 0.006, 2)
+    ref, _ = R.rx_viterbi(rx, CON[m], rate, None, blocks_per_call=3)
+    assert np.array_equal(O.Viterbi(m, rate).work(rx), ref)
+
+
+@pytest.mark.skipif(not R.available(), reason="oracle/_ref not built")
+def test_reference_round_trip_on_random_ts():
+    """the reference chain itself (frequency-domain loopback) reproduces the transmitted TS"""
+    from dvbt_testlib import tx_frequency_domain, channel
+    con, cr, tm = R.QAM16, R.C1_2, R.T2k
+    tx = tx_frequency_domain(con, cr, tm, 300, 1)
+    X = channel(tx["X"])
+    Y, tags = R.rx_demod(X, con, cr, tm)
+    dm = R.rx_demap(Y, con, tm)
+    sd, bd = R.rx_deinterleave(dm, tags, con, tm)
+    sf = [t for t in tags if t[1] == "superframe_start"][0][0]
+    vo, vt = R.rx_viterbi(bd, con, cr, sf * 1512)
+    cd, rd, ts = R.rx_outer(vo, vt)
+    assert len(ts) >= 1504
+    assert np.array_equal(ts, tx["ts"][504 * 188: 504 * 188 + len(ts)])
