@@ -183,17 +183,28 @@ __global__ void acq_lambda_kernel(AcqParams p, const float2 *__restrict__ x, lon
   ml_point(x, base + (long long)n * (p.N + p.cp) + c0 - kD + c, p.N, p.cp, p.rho2, &lambda[t], &gamma[t]);
 }
 
-// ---- speculative tracking tables --------------------------------------------------------------
+// ---- tracking as a finite-state machine, evaluated in parallel -----------------------------------
 // The reference state that crosses symbols is (cp_start, d_avg) plus the phase schedule.  cp_start
 // moves by (best - 8) per symbol; the table covers window offsets c = 0..kNC-1 (window = candidates
 // [c, c+16), cp_start = c0 - kD + 8 + c).  d_avg after the 16 values of a window is, to float
-// precision, independent of the average it started from, so it is speculated:
-//   pass 1: avg1[n][c]      = average after window (n, c) starting from 0
-//   pass 2: best2/avg2[n][c][d] = detector result of window (n, c) starting from avg1[n-1][c+d], d in {-1,0,1}
-//           (the previous symbol sat at offset c+d); ok0[n][c] = "no timing move and avg2 == avg1" for d = 0
-// acq_walk_kernel then follows the true path, checking bit-for-bit that every speculated input equals
-// the true average, and runs the plain sequential detector for any symbol where it does not.
+// precision, independent of the average it started from, so it is speculated and then verified:
+//   pass 1: avg1[n][c] = average after window (n, c) starting from 0
+//   pass 2: for state s = (c, d), d = previous offset - c in [-2, 2]: run the detector on window (n, c)
+//           starting from avg1[n-1][c+d]; best[n][s], avg2[n][s], and the successor state
+//           next[n][s] = (c + best - 8, 8 - best) — or a stop code when the peak is missed, the next window
+//           leaves the table, or the speculation cannot be continued (|move| > 2, or avg2 != avg1[n][c]
+//           bit-for-bit, i.e. the successor's assumed input would not be the true average).
+// The true trajectory is then the composition next[n-1] o ... o next[0] applied to the start state:
+// acq_compose_kernel composes 32-symbol chunks for all 85 start states in parallel, chains the chunk
+// maps, re-walks every chunk from its now known start state, and acq_finish_kernel turns the per-symbol
+// (offset, best) into output descriptors with a warp scan of the phase schedule (:285-312).  A stop code
+// ends the batch early; the host loop continues from there with the true state (exactness never rests
+// on the speculation).
 constexpr int kNC = kCand - 16 + 1;  // 17 window offsets
+constexpr int kND = 5;               // previous-offset deltas -2..2
+constexpr int kNS = kNC * kND;       // 85 states
+constexpr unsigned char kLost = 0xFE, kOff = 0xFD, kSplit = 0xFC, kStop = 0xF0;
+constexpr int kChunk = 32;
 
 __global__ void acq_pass1_kernel(AcqParams p, int nsym, const float *__restrict__ lambda, float *__restrict__ avg1) {
   int t = blockIdx.x * blockDim.x + threadIdx.x;
@@ -206,152 +217,180 @@ __global__ void acq_pass1_kernel(AcqParams p, int nsym, const float *__restrict_
 }
 
 __global__ void acq_pass2_kernel(AcqParams p, int nsym, const float *__restrict__ lambda, const float *__restrict__ avg1, float avg_first,
-                                 signed char *__restrict__ best2, float *__restrict__ avg2, unsigned char *__restrict__ ok0) {
+                                 signed char *__restrict__ best2, float *__restrict__ avg2, unsigned char *__restrict__ next) {
   int t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= nsym * kNC * 3) return;
-  int n = t / (kNC * 3), r = t - n * (kNC * 3), c = r / 3, d = r - c * 3 - 1;
+  if (t >= nsym * kNS) return;
+  int n = t / kNS, s = t - n * kNS, c = s / kND, d = s - c * kND - 2;
   int cp = c + d;
-  signed char res = -2;  // -2: no speculation available
+  signed char res = -2;
   float avg = 0.f;
+  unsigned char nx = kSplit;
   if (n == 0 || (cp >= 0 && cp < kNC)) {
     avg = n == 0 ? avg_first : avg1[(n - 1) * kNC + cp];
     int best;
     int np = peak_detect(lambda + (long long)n * kCand + c, 16, &avg, p.rise, p.fall, p.alpha, &best);
-    res = np > 0 ? (signed char)best : (signed char)-1;
+    if (np <= 0) { res = -1; nx = kLost; }
+    else {
+      res = (signed char)best;
+      int cn = c + best - 8, dn = 8 - best;
+      if (cn < 0 || cn >= kNC) nx = kOff;
+      else if (dn < -2 || dn > 2 || __float_as_uint(avg) != __float_as_uint(avg1[n * kNC + c])) nx = kSplit;
+      else nx = (unsigned char)(cn * kND + dn + 2);
+    }
   }
   best2[t] = res;
   avg2[t] = avg;
-  if (d == 0) ok0[n * kNC + c] = (res == 8 && __float_as_uint(avg) == __float_as_uint(avg1[n * kNC + c])) ? 1 : 0;
+  next[t] = nx;
 }
 
-// The sequential walk (one warp).  Runs of "nothing happens" symbols (ok0) are handled 32 at a time;
-// everything else one symbol at a time.  Produces the per-symbol output descriptors and the end state.
-__global__ void __launch_bounds__(32) acq_walk_kernel(AcqParams p, int nsym, long long base, int c0, const float *__restrict__ lambda,
-                                                      const float2 *__restrict__ gamma, const float *__restrict__ avg1,
-                                                      const signed char *__restrict__ best2, const float *__restrict__ avg2,
-                                                      const unsigned char *__restrict__ ok0, AcqState *st, SymOut *__restrict__ out) {
+struct AcqWalk {
+  int n_found;        // symbols that produced output
+  int code;           // 0: all symbols processed, else kLost / kOff / kSplit
+  int last_state;     // state index of the last processed symbol
+};
+
+__global__ void __launch_bounds__(1024) acq_compose_kernel(int nsym, int per_thread, int start_state, const unsigned char *__restrict__ next,
+                                                           unsigned char *__restrict__ state_of, AcqWalk *walk) {
+  extern __shared__ unsigned char s_map[];  // [nthreads][kNS] chunk maps, then [nthreads] start states
+  const int t = threadIdx.x, nt = blockDim.x;
+  const int n0 = t * per_thread, n1 = min(nsym, n0 + per_thread);
+  // phase A: composite map of my chunk for every start state
+  // (all 85 chains advance together so that the loads of one symbol are independent)
+  unsigned char *mine = s_map + t * kNS;
+  for (int s0 = 0; s0 < kNS; s0++) mine[s0] = (unsigned char)s0;
+  for (int n = n0; n < n1; n++) {
+    const unsigned char *row = next + (long long)n * kNS;
+#pragma unroll 5
+    for (int s0 = 0; s0 < kNS; s0++) {
+      unsigned char cur = mine[s0];
+      if (cur < kStop) {
+        unsigned char nx = row[cur];
+        mine[s0] = nx >= kStop ? kStop : nx;
+      }
+    }
+  }
+  __syncthreads();
+  unsigned char *s_start = s_map + nt * kNS;
+  __shared__ int s_last_chunk;
+  if (t == 0) {
+    unsigned char st = (unsigned char)start_state;
+    int last = nt - 1;
+    for (int k = 0; k < nt; k++) {
+      s_start[k] = st;
+      if (k * per_thread >= nsym) { last = k - 1; break; }
+      unsigned char m = s_map[k * kNS + st];
+      if (m >= kStop) { last = k; break; }
+      st = m;
+    }
+    s_last_chunk = last;
+  }
+  __syncthreads();
+  // phase C: re-walk with the known start state, record the state used at every symbol
+  if (t <= s_last_chunk && n0 < nsym) {
+    unsigned char st = s_start[t];
+    int n = n0;
+    int code = 0;
+    for (; n < n1; n++) {
+      state_of[n] = st;
+      unsigned char nx = next[(long long)n * kNS + st];
+      if (nx >= kStop) { code = nx; break; }
+      st = nx;
+    }
+    if (code) {
+      walk->code = code;
+      walk->n_found = code == kLost ? n : n + 1;
+      walk->last_state = state_of[n];
+    } else if (t == s_last_chunk) {
+      walk->code = 0;
+      walk->n_found = n1;
+      walk->last_state = state_of[n1 - 1];
+    }
+  }
+}
+
+// per-symbol outputs + phase schedule (one warp, 32 symbols per iteration)
+__global__ void __launch_bounds__(32) acq_finish_kernel(AcqParams p, long long base, int c0, const float2 *__restrict__ gamma,
+                                                        const signed char *__restrict__ best2, const float *__restrict__ avg2,
+                                                        const unsigned char *__restrict__ state_of, const AcqWalk *walk, AcqState *st,
+                                                        SymOut *__restrict__ out) {
   const int lane = threadIdx.x;
   const int total = p.N + p.cp;
   const double invN = -1.0 / (double)p.N;
-  int c = kD - 8;            // window offset of the current symbol (cp_start == c0)
-  int d = 0;                 // offset of the previous symbol minus c
-  bool spec_valid = true;    // the speculated input of entry (n, c, d) equals the true average (n == 0: avg_first is the truth)
-  float avg = st->avg;
-  double ph = st->phase, inc = st->phaseinc, pend = st->nextphaseinc;
-  int nextpos = st->nextpos;
-  int n = 0, n_out = 0, lost_at = -1, fallback = 0;
-  int c_run = 0, c_single = 0, c_seq = 0;
-  while (n < nsym) {
-    // ---------- run of quiet symbols: entry (m, c, 0) valid, best == 8, avg2 == avg1
-    if (spec_valid && d == 0) {
-      int m = n + lane;
-      bool q = m < nsym && ok0[m * kNC + c];
-      unsigned bal = __ballot_sync(0xffffffffu, q);
-      int run = bal == 0xffffffffu ? 32 : __ffs(~bal) - 1;
-      if (run > 0) {
-        // all symbols of the run: peak = cp_start (unchanged), nextpos = cp_start - total, eps from gamma at the peak
-        int cp_start = c0 - kD + 8 + c;
-        int sw = cp_start - total;
-        bool sw_ok = sw >= 0 && sw < total;
-        bool sw0_ok = nextpos >= 0 && nextpos < total;
-        float2 g = (lane < run) ? gamma[(long long)m * kCand + c + 8] : make_float2(1.f, 0.f);
-        double e = invN * (double)atan2f(g.y, g.x);           // nextphaseinc produced by symbol m
-        double e1 = __shfl_up_sync(0xffffffffu, e, 1), e2 = __shfl_up_sync(0xffffffffu, e, 2);
-        double inc_after0 = sw0_ok ? pend : inc;              // increment in force after the first symbol of the run
-        double i0, i1;
-        int swn;
-        if (lane == 0) { i0 = inc; i1 = pend; swn = sw0_ok ? nextpos : total; }
-        else {
-          i0 = lane == 1 ? inc_after0 : (sw_ok ? e2 : inc_after0);
-          i1 = e1;
-          swn = sw_ok ? sw : total;
-        }
-        double adv = lane < run ? (swn < total ? swn * i0 + (total - swn) * i1 : total * i0) : 0.0;
-        double incl = adv;
+  const double twopi = 2.0 * M_PI;
+  const int nf = walk->n_found;
+  double ph = st->phase, inc = st->phaseinc;
+  double pend_prev = st->nextphaseinc;   // e_{m-1} for the first symbol of the iteration
+  int nextpos_prev = st->nextpos;
+  int last_peak = st->cp_start;
+  for (int bn = 0; bn < nf; bn += 32) {
+    int m = bn + lane;
+    bool live = m < nf;
+    int s = live ? state_of[m] : 0;
+    int c = s / kND;
+    int best = live ? best2[(long long)m * kNS + s] : 8;
+    int peak = c0 - kD + c + best;                     // cp_start_before - 8 + best
+    float2 g = live ? gamma[(long long)m * kCand + c + best] : make_float2(1.f, 0.f);
+    double e = invN * (double)atan2f(g.y, g.x);        // d_nextphaseinc left by symbol m (:311)
+    int npos = peak - total;                           // d_nextpos left by symbol m (:312)
+    // what symbol m sees: the schedule left by symbol m-1
+    double pendm = __shfl_up_sync(0xffffffffu, e, 1);
+    int swm = __shfl_up_sync(0xffffffffu, npos, 1);
+    if (lane == 0) { pendm = pend_prev; swm = nextpos_prev; }
+    bool okm = live && swm >= 0 && swm < total;
+    // increment in force when symbol m starts: switched value of the closest earlier symbol that switched
+    unsigned okbal = __ballot_sync(0xffffffffu, okm);
+    unsigned below = okbal & ((1u << lane) - 1u);
+    int src = below ? 31 - __clz(below) : 0;
+    double from_prev = __shfl_sync(0xffffffffu, pendm, src);
+    double i0 = below ? from_prev : inc;
+    double i1 = pendm;
+    double adv = live ? (okm ? swm * i0 + (total - swm) * i1 : total * i0) : 0.0;
+    double incl = adv;
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-          double t = __shfl_up_sync(0xffffffffu, incl, o);
-          if (lane >= o) incl += t;
-        }
-        if (lane < run) {
-          SymOut so;
-          so.first = base + (long long)m * total + cp_start - p.N + 1;
-          so.phase0 = remainder(ph + (incl - adv), 2.0 * M_PI);
-          so.inc0 = i0; so.inc1 = i1; so.switch_at = swn;
-          out[n_out + lane] = so;
-        }
-        int lastl = run - 1;
-        ph = remainder(ph + __shfl_sync(0xffffffffu, incl, lastl), 2.0 * M_PI);
-        double li = (swn < total) ? i1 : i0;
-        inc = __shfl_sync(0xffffffffu, li, lastl);
-        pend = __shfl_sync(0xffffffffu, e, lastl);
-        nextpos = sw;
-        avg = avg1[(n + lastl) * kNC + c];  // == avg2 of the last symbol of the run
-        n_out += run;
-        n += run;
-        c_run += run;
-        continue;
-      }
+    for (int o = 1; o < 32; o <<= 1) {
+      double t = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += t;
     }
-    // ---------- one symbol
-    c_single++;
-    int best;
-    bool found;
-    signed char sp = spec_valid ? best2[(n * kNC + c) * 3 + (d + 1)] : (signed char)-2;
-    if (sp != -2) {
-      best = sp;
-      found = best >= 0;
-      avg = avg2[(n * kNC + c) * 3 + (d + 1)];
-    } else {
-      fallback = 1;
-      c_seq++;
-      found = peak_detect(lambda + (long long)n * kCand + c, 16, &avg, p.rise, p.fall, p.alpha, &best) > 0;
+    if (live) {
+      SymOut so;
+      so.first = base + (long long)m * total + peak - p.N + 1;
+      double p0 = ph + (incl - adv);
+      so.phase0 = p0 - twopi * rint(p0 / twopi);
+      so.inc0 = i0; so.inc1 = i1; so.switch_at = okm ? swm : total;
+      out[m] = so;
     }
-    int cp_start = c0 - kD + 8 + c;
-    SymOut so;
-    so.phase0 = ph; so.inc0 = inc; so.inc1 = inc; so.switch_at = total;
-    if (!found) {
-      ph = remainder(ph + total * inc, 2.0 * M_PI);  // :335-343
-      lost_at = n;
-      break;
-    }
-    if (nextpos >= 0 && nextpos < total) {           // :287-288
-      so.inc1 = pend; so.switch_at = nextpos;
-      ph += nextpos * inc;
-      inc = pend;
-      ph += (total - nextpos) * inc;
-    } else {
-      ph += total * inc;
-    }
-    ph = remainder(ph, 2.0 * M_PI);
-    int peak = best + cp_start - 8;
-    float2 g = gamma[(long long)n * kCand + c + best];
-    pend = invN * (double)atan2f(g.y, g.x);          // :311
-    nextpos = peak - total;                          // :312
-    so.first = base + (long long)n * total + peak - p.N + 1;
-    if (lane == 0) out[n_out] = so;
-    n_out++;
-    // next symbol's table entry: offset c' = c + best - 8, came from offset c (d' = c - c')
-    int cn = c + best - 8;
-    int dn = c - cn;
-    // its speculated input is avg1[n][c]; valid iff that is the true average now
-    bool next_valid = (dn >= -1 && dn <= 1) && __float_as_uint(avg1[n * kNC + c]) == __float_as_uint(avg);
-    n++;
-    if (cn < 0 || cn >= kNC) { c = cn; lost_at = n; break; }  // left the table: the host re-centres it
-    c = cn; d = dn; spec_valid = next_valid;
+    int lastl = min(31, nf - 1 - bn);
+    double tot = __shfl_sync(0xffffffffu, incl, lastl);
+    ph += tot;
+    ph -= twopi * rint(ph / twopi);
+    double after = okm ? i1 : i0;                      // increment in force after symbol m
+    inc = __shfl_sync(0xffffffffu, after, lastl);
+    pend_prev = __shfl_sync(0xffffffffu, e, lastl);
+    nextpos_prev = __shfl_sync(0xffffffffu, npos, lastl);
+    last_peak = __shfl_sync(0xffffffffu, peak, lastl);
   }
   if (lane == 0) {
-    st->avg = avg;
+    int code = walk->code;
+    int cp_start = last_peak;
+    if (nf > 0) st->avg = avg2[(long long)(nf - 1) * kNS + state_of[nf - 1]];
+    if (code == kLost) {
+      // the missed symbol still runs the detector (its average is the entry's) and advances the phase (:335-343)
+      int sl = walk->last_state;
+      st->avg = avg2[(long long)nf * kNS + sl];
+      ph += total * inc;
+      ph -= twopi * rint(ph / twopi);
+    }
     st->phase = (float)ph;
     st->phaseinc = inc;
-    st->nextphaseinc = pend;
-    st->nextpos = nextpos;
-    st->cp_start = c0 - kD + 8 + c;
-    st->n_out = n_out;
-    st->lost_at = lost_at;
-    st->fallback = fallback;
-    st->n_run += c_run; st->n_single += c_single; st->n_seq += c_seq;
-    st->consumed = (long long)(lost_at >= 0 ? lost_at : nsym) * total;
+    st->nextphaseinc = pend_prev;
+    st->nextpos = nextpos_prev;
+    st->cp_start = cp_start;
+    st->n_out = nf;
+    st->lost_at = code == kLost ? nf : (code ? -2 - nf : -1);   // -2-nf: stopped after nf symbols without a miss
+    st->fallback = code == kSplit ? 1 : 0;
+    st->n_run += nf;
+    st->n_single += code ? 1 : 0;
+    st->consumed = (long long)nf * total;
   }
 }
 
@@ -401,7 +440,7 @@ int acq_run(dvbt_b200_acq *h, const float2 *x, long long n, float2 *d_out, long 
   DVBT_CUDA_TRY(cudaMemcpyAsync(hs, h->d_state.p, sizeof(AcqState), cudaMemcpyDeviceToHost, st));
   DVBT_CUDA_TRY(cudaStreamSynchronize(st));
   int guard = 0;
-  while (guard++ < 64) {
+  while (guard++ < 1000000) {
     // ---- initial acquisition (needs 2N+cp+8 samples visible)
     if (!hs->initial) {
       if (n - pos < 2LL * p.N + p.cp + 8 || produced >= out_capacity_syms) break;
@@ -433,17 +472,25 @@ int acq_run(dvbt_b200_acq *h, const float2 *x, long long n, float2 *d_out, long 
       long long threads = nsym * kCand;
       acq_lambda_kernel<<<(unsigned)((threads + 127) / 128), 128, 0, st>>>(p, x, pos, c0, (int)nsym, h->d_lambda.as<float>(),
                                                                           h->d_gamma.as<float2>());
-      if ((rc = h->d_avg1.reserve((size_t)nsym * kNC * 4)) || (rc = h->d_avg2.reserve((size_t)nsym * kNC * 3 * 4)) ||
-          (rc = h->d_peak.reserve((size_t)nsym * kNC * 3)) || (rc = h->d_flag.reserve((size_t)nsym * kNC)))
+      int per_thread = kChunk;
+      while ((nsym + per_thread - 1) / per_thread > 1024) per_thread *= 2;
+      int nthreads = (int)((nsym + per_thread - 1) / per_thread);
+      if ((rc = h->d_avg1.reserve((size_t)nsym * kNC * 4)) || (rc = h->d_avg2.reserve((size_t)nsym * kNS * 4)) ||
+          (rc = h->d_peak.reserve((size_t)nsym * kNS)) || (rc = h->d_flag.reserve((size_t)nsym * kNS)) ||
+          (rc = h->d_eps.reserve((size_t)nsym + 128)))
         return rc;
-      long long t1 = nsym * kNC, t2 = t1 * 3;
+      long long t1 = nsym * kNC, t2 = nsym * kNS;
       acq_pass1_kernel<<<(unsigned)((t1 + 127) / 128), 128, 0, st>>>(p, (int)nsym, h->d_lambda.as<float>(), h->d_avg1.as<float>());
       acq_pass2_kernel<<<(unsigned)((t2 + 127) / 128), 128, 0, st>>>(p, (int)nsym, h->d_lambda.as<float>(), h->d_avg1.as<float>(), hs->avg,
                                                                     h->d_peak.as<signed char>(), h->d_avg2.as<float>(),
                                                                     h->d_flag.as<unsigned char>());
-      acq_walk_kernel<<<1, 32, 0, st>>>(p, (int)nsym, pos, c0, h->d_lambda.as<float>(), h->d_gamma.as<float2>(), h->d_avg1.as<float>(),
-                                        h->d_peak.as<signed char>(), h->d_avg2.as<float>(), h->d_flag.as<unsigned char>(),
-                                        h->d_state.as<AcqState>(), h->d_sym.as<SymOut>());
+      size_t csmem = (size_t)nthreads * (kNS + 1) + 16;
+      DVBT_CUDA_TRY(cudaFuncSetAttribute(acq_compose_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+      AcqWalk *d_walk = reinterpret_cast<AcqWalk *>(h->d_eps.as<unsigned char>() + ((nsym + 15) / 16) * 16);
+      acq_compose_kernel<<<1, nthreads, csmem, st>>>((int)nsym, per_thread, (kD - 8) * kND + 2, h->d_flag.as<unsigned char>(),
+                                                     h->d_eps.as<unsigned char>(), d_walk);
+      acq_finish_kernel<<<1, 32, 0, st>>>(p, pos, c0, h->d_gamma.as<float2>(), h->d_peak.as<signed char>(), h->d_avg2.as<float>(),
+                                          h->d_eps.as<unsigned char>(), d_walk, h->d_state.as<AcqState>(), h->d_sym.as<SymOut>());
       count_launch(4);
       DVBT_CUDA_TRY(cudaGetLastError());
     }
@@ -459,21 +506,17 @@ int acq_run(dvbt_b200_acq *h, const float2 *x, long long n, float2 *d_out, long 
     fb |= hs->fallback;
     pos += hs->consumed;
     if (hs->lost_at >= 0) {
-      // either a missed peak (restart: consume half a symbol, :557) or the timing left the table
-      // (re-centre the table; nothing is consumed for the symbol that could not be evaluated)
-      int lo = hs->cp_start - 8 - (c0 - kD);
-      bool off_table = (lo < 0 || lo + 16 > kCand);
-      if (!off_table) {
-        if (lost_total < 0) lost_total = (int)produced;
-        AcqState s2 = *hs;
-        s2.initial = 0;
-        pos += total / 2;
-        DVBT_CUDA_TRY(cudaMemcpyAsync(h->d_state.p, &s2, sizeof(AcqState), cudaMemcpyHostToDevice, st));
-        DVBT_CUDA_TRY(cudaStreamSynchronize(st));
-        *hs = s2;
-      }
+      // missed peak: the reference restarts acquisition and consumes half a symbol for that call (:545-558)
+      if (lost_total < 0) lost_total = (int)produced;
+      AcqState s2 = *hs;
+      s2.initial = 0;
+      pos += total / 2;
+      DVBT_CUDA_TRY(cudaMemcpyAsync(h->d_state.p, &s2, sizeof(AcqState), cudaMemcpyHostToDevice, st));
+      DVBT_CUDA_TRY(cudaStreamSynchronize(st));
+      *hs = s2;
       continue;
     }
+    if (hs->lost_at <= -2) continue;  // stopped early (table re-centre or speculation split): carry on from the true state
     break;
   }
   if (do_fft && produced > 0) {

@@ -67,29 +67,44 @@ int resampler_taps(std::vector<float> *out, int *per_arm) {
   return 0;
 }
 
-// taps laid out arm-major: tap[phase * per_arm + j] = h[phase + 32 j]
+// taps laid out arm-major: tap[phase * per_arm + j] = h[phase + 32 j].  A block produces 512 outputs
+// (2 per thread); the 560 + per_arm input samples they need are staged in shared memory with coalesced
+// loads, so every input sample is read from HBM/L2 once.
+constexpr int kOutPerBlock = 512;
+constexpr int kTileIn = (kOutPerBlock * kDecim) / kInterp + 2;  // inputs advanced by a block (+ slack)
+
 __global__ void __launch_bounds__(256) resample_kernel(const float2 *__restrict__ x, long long nin, float2 *__restrict__ y, long long nout,
                                                        const float *__restrict__ taps_arm, int per_arm, float scale) {
-  extern __shared__ float s_taps[];
+  extern __shared__ float s_mem[];
+  float *s_taps = s_mem;                                        // [32][per_arm]
+  float2 *s_x = reinterpret_cast<float2 *>(s_mem + kInterp * per_arm);  // [kTileIn + per_arm]
   for (int i = threadIdx.x; i < kInterp * per_arm; i += blockDim.x) s_taps[i] = taps_arm[i];
+  long long m0 = (long long)blockIdx.x * kOutPerBlock;
+  long long a0 = (m0 * kDecim) / kInterp;                       // newest input of the block's first output
+  long long lo = a0 - (per_arm - 1);                            // oldest input needed
+  int span = kTileIn + per_arm;
+  for (int i = threadIdx.x; i < span; i += blockDim.x) {
+    long long idx = lo + i;
+    s_x[i] = (idx >= 0 && idx < nin) ? x[idx] : make_float2(0.f, 0.f);
+  }
   __syncthreads();
-  long long m = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (m >= nout) return;
-  long long t = m * kDecim;
-  long long a = t / kInterp;
-  int phase = (int)(t - a * kInterp);
-  const float *h = s_taps + phase * per_arm;
-  float accr = 0.f, acci = 0.f;
-  for (int j = 0; j < per_arm; j++) {
-    long long idx = a - j;
-    if (idx < 0) break;
-    if (idx < nin) {
-      float2 v = x[idx];
+#pragma unroll
+  for (int r = 0; r < 2; r++) {
+    long long m = m0 + threadIdx.x + 256 * r;
+    if (m >= nout) return;
+    long long t = m * kDecim;
+    long long a = t / kInterp;
+    int phase = (int)(t - a * kInterp);
+    const float *h = s_taps + phase * per_arm;
+    const float2 *xs = s_x + (int)(a - lo);                     // xs[-j] = x[a - j]
+    float accr = 0.f, acci = 0.f;
+    for (int j = 0; j < per_arm; j++) {
+      float2 v = xs[-j];
       accr = fmaf(h[j], v.x, accr);
       acci = fmaf(h[j], v.y, acci);
     }
+    y[m] = make_float2(accr * scale, acci * scale);
   }
-  y[m] = make_float2(accr * scale, acci * scale);
 }
 
 struct Resampler {
@@ -123,8 +138,8 @@ int resample_launch(const float2 *d_x, long long nin, float2 *d_y, long long nou
   }
   Resampler *r = g_res[dev];
   if (nout <= 0) return 0;
-  size_t smem = (size_t)kInterp * r->per_arm * 4;
-  resample_kernel<<<(unsigned)((nout + 255) / 256), 256, smem, st>>>(d_x, nin, d_y, nout, r->d_taps.as<float>(), r->per_arm, scale);
+  size_t smem = (size_t)kInterp * r->per_arm * 4 + (size_t)(kTileIn + r->per_arm) * 8;
+  resample_kernel<<<(unsigned)((nout + kOutPerBlock - 1) / kOutPerBlock), 256, smem, st>>>(d_x, nin, d_y, nout, r->d_taps.as<float>(), r->per_arm, scale);
   count_launch();
   DVBT_CUDA_TRY(cudaGetLastError());
   return 0;
