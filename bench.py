@@ -51,6 +51,35 @@ def load_peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+# ---- multi-GPU plumbing (no data-path collective; the configuration is the only broadcast) ----
+def broadcast_config(values, device):
+    """rank 0's list of numbers -> every rank (one torch.distributed broadcast)"""
+    import torch
+    import torch.distributed as dist
+    t = torch.tensor([float(v) for v in values], dtype=torch.float64, device=device)
+    if dist.is_initialized() and dist.get_world_size() > 1:
+        dist.broadcast(t, 0)
+    return [float(v) for v in t.cpu()]
+
+
+def max_over_ranks(ms, device):
+    import torch
+    import torch.distributed as dist
+    t = torch.tensor([float(ms)], dtype=torch.float64, device=device)
+    if dist.is_initialized() and dist.get_world_size() > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t[0])
+
+
+def streams_of_rank(nstreams, world, rank):
+    """stream s is decoded on GPU s mod G (config 4 of BASELINE.json)"""
+    return [s for s in range(nstreams) if s % world == rank]
+
+
+def seed_of_rank(rank, base=1):
+    return base + rank
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled during the timed region."""
 
@@ -422,12 +451,11 @@ def main():
     if WORLD > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", LOCAL_RANK))
         # the only collective on this path: the configuration
-        cfg = torch.tensor([a.mbit, a.steps, a.warmup, a.tiles], dtype=torch.float64, device="cuda")
-        dist.broadcast(cfg, 0)
+        cfg = broadcast_config([a.mbit, a.steps, a.warmup, a.tiles], "cuda")
         a.mbit, a.steps, a.warmup, a.tiles = float(cfg[0]), int(cfg[1]), int(cfg[2]), int(cfg[3])
 
     w = RxWorkload(a.tiles) if rx else ViterbiWorkload(a.mbit)
-    w.setup_gpu(seed=1 + RANK)
+    w.setup_gpu(seed=seed_of_rank(RANK))
     lib = g.capi.lib()
 
     def barrier():
@@ -452,11 +480,9 @@ def main():
         # every step synchronises its own stream inside the C ABI, so host wall time between the
         # barriers brackets the device work; take the larger of the two clocks
         ms = max(dev_ms, wall_ms)
-        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
-        if WORLD > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = max_over_ranks(ms, "cuda")
         barrier()
-        return float(t[0])
+        return ms
 
     sampler = ClockSampler(LOCAL_RANK)
     l0 = lib.dvbt_b200_kernel_launches()

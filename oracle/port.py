@@ -40,6 +40,21 @@ def lib():
         L.dvbt_oracle_rs_encode.argtypes = [C.c_void_p, C.c_long, C.c_void_p]
         L.dvbt_oracle_constellation.argtypes = [C.c_int, C.c_int, C.c_float, C.c_void_p]
         L.dvbt_oracle_demap.argtypes = [C.c_void_p, C.c_long, C.c_int, C.c_int, C.c_float, C.c_void_p]
+        L.dvbt_oracle_symbol_deinterleave.argtypes = [C.c_void_p, C.c_long, C.c_int, C.c_void_p, C.c_void_p]
+        L.dvbt_oracle_bit_deinterleave.argtypes = [C.c_void_p, C.c_long, C.c_int, C.c_void_p]
+        L.dvbt_oracle_conv_deinterleave.argtypes = [C.c_void_p, C.c_long, C.c_void_p]
+        L.dvbt_oracle_descramble.restype = C.c_long
+        L.dvbt_oracle_descramble.argtypes = [C.c_void_p, C.c_long, C.c_void_p, C.c_void_p]
+        L.dvbt_oracle_demod_create.restype = C.c_void_p
+        L.dvbt_oracle_demod_create.argtypes = [C.c_int, C.c_int]
+        L.dvbt_oracle_demod_destroy.argtypes = [C.c_void_p]
+        L.dvbt_oracle_demod_run.restype = C.c_long
+        L.dvbt_oracle_demod_run.argtypes = [C.c_void_p, C.c_void_p, C.c_long, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.dvbt_oracle_acq_create.restype = C.c_void_p
+        L.dvbt_oracle_acq_create.argtypes = [C.c_int, C.c_int, C.c_float]
+        L.dvbt_oracle_acq_destroy.argtypes = [C.c_void_p]
+        L.dvbt_oracle_acq_run.restype = C.c_long
+        L.dvbt_oracle_acq_run.argtypes = [C.c_void_p, C.c_void_p, C.c_long, C.c_void_p, C.c_long, C.c_void_p, C.c_void_p]
         _lib = L
     return _lib
 
@@ -129,3 +144,62 @@ def demap(cells, constellation, alpha=1, gain=1.0):
     out = np.zeros(len(c), np.uint8)
     lib().dvbt_oracle_demap(c.ctypes.data, len(c), constellation, alpha, gain, out.ctypes.data)
     return out
+
+
+def symbol_deinterleave(cells, tm, symbol_index):
+    P = 1512 if tm == 0 else 6048
+    c = np.ascontiguousarray(cells, np.uint8).reshape(-1, P)
+    si = np.ascontiguousarray(symbol_index, np.int32)
+    out = np.zeros_like(c)
+    lib().dvbt_oracle_symbol_deinterleave(c.ctypes.data, c.shape[0], tm, si.ctypes.data, out.ctypes.data)
+    return out
+
+
+def bit_deinterleave(cells, m):
+    c = np.ascontiguousarray(cells, np.uint8).reshape(-1)
+    out = np.zeros_like(c)
+    lib().dvbt_oracle_bit_deinterleave(c.ctypes.data, len(c), m, out.ctypes.data)
+    return out
+
+
+def conv_deinterleave(stream):
+    s = np.ascontiguousarray(stream, np.uint8).reshape(-1)
+    s = s[: len(s) // 12 * 12]
+    out = np.zeros_like(s)
+    lib().dvbt_oracle_conv_deinterleave(s.ctypes.data, len(s), out.ctypes.data)
+    return out
+
+
+def descramble(packets188):
+    p = np.ascontiguousarray(packets188, np.uint8).reshape(-1, 188)
+    out = np.zeros(p.size, np.uint8)
+    first = C.c_long(-1)
+    n = lib().dvbt_oracle_descramble(p.ctypes.data, p.shape[0], out.ctypes.data, C.byref(first))
+    return out[:n], int(first.value)
+
+
+def demod(X, constellation, tm, sync_start_at0=True):
+    """post-FFT symbols (nsym, N) -> (cells (nout, P) complex64, symbol_index tags, superframe tag index)"""
+    N, P = (2048, 1512) if tm == 0 else (8192, 6048)
+    X = np.ascontiguousarray(X, np.complex64).reshape(-1, N)
+    pad = np.zeros((X.shape[0] + 1) * N + 64, np.complex64)   # the reference reads up to 8 bins around an item
+    pad[32: 32 + X.size] = X.reshape(-1)
+    out = np.zeros((X.shape[0], P), np.complex64)
+    si = np.zeros(X.shape[0], np.int32)
+    tag = C.c_long(-1)
+    h = lib().dvbt_oracle_demod_create(constellation, tm)
+    n = lib().dvbt_oracle_demod_run(h, pad.ctypes.data + 32 * 8, X.shape[0], int(sync_start_at0), out.ctypes.data, si.ctypes.data, C.byref(tag))
+    lib().dvbt_oracle_demod_destroy(h)
+    return out[:n].copy(), si[:n].copy(), int(tag.value)
+
+
+def acquisition(x, N, cp, snr_db=30.0):
+    """samples -> (symbols (nout, N) complex64, consumed samples, sync_start on first item)"""
+    x = np.ascontiguousarray(x, np.complex64).reshape(-1)
+    cap = len(x) // (N + cp) + 2
+    out = np.zeros((cap, N), np.complex64)
+    cons, tag = C.c_long(0), C.c_int(0)
+    h = lib().dvbt_oracle_acq_create(N, cp, snr_db)
+    n = lib().dvbt_oracle_acq_run(h, x.ctypes.data, len(x), out.ctypes.data, cap, C.byref(cons), C.byref(tag))
+    lib().dvbt_oracle_acq_destroy(h)
+    return out[:n].copy(), int(cons.value), bool(tag.value)

@@ -53,6 +53,27 @@ void dvbt_oracle_rs_encode(const uint8_t *in, long npackets, uint8_t *out);
 int dvbt_oracle_constellation(int constellation, int alpha, float gain, float *points);
 void dvbt_oracle_demap(const float *in, long n, int constellation, int alpha, float gain, uint8_t *out);
 
+/* ---- glue blocks (glue_port.c) ------------------------------------------------------ */
+void dvbt_oracle_symbol_H(int tm, int *h);
+void dvbt_oracle_symbol_deinterleave(const uint8_t *in, long nsym, int tm, const int *symbol_index, uint8_t *out);
+void dvbt_oracle_bit_deinterleave(const uint8_t *in, long ncells, int v, uint8_t *out);
+void dvbt_oracle_conv_deinterleave(const uint8_t *in, long n, uint8_t *out);
+long dvbt_oracle_descramble(const uint8_t *in, long npackets, uint8_t *out, long *first_packet);
+
+/* ---- demod_reference_signals (demod_port.c) ------------------------------------------ */
+typedef struct dvbt_oracle_demod dvbt_oracle_demod;
+dvbt_oracle_demod *dvbt_oracle_demod_create(int constellation, int tm);
+void dvbt_oracle_demod_destroy(dvbt_oracle_demod *);
+long dvbt_oracle_demod_run(dvbt_oracle_demod *, const float *in_re_im, long nsym, int sync_start_at0, float *out_re_im,
+                           int *symbol_index_out, long *superframe_tag_at);
+
+/* ---- ofdm_sym_acquisition (acq_port.c) ----------------------------------------------- */
+typedef struct dvbt_oracle_acq dvbt_oracle_acq;
+dvbt_oracle_acq *dvbt_oracle_acq_create(int fft_length, int cp_length, float snr_db);
+void dvbt_oracle_acq_destroy(dvbt_oracle_acq *);
+long dvbt_oracle_acq_run(dvbt_oracle_acq *, const float *x_re_im, long n, float *out_re_im, long out_capacity, long *consumed,
+                         int *first_sync_tag);
+
 #ifdef __cplusplus
 }
 #endif

@@ -81,6 +81,27 @@ def inner_coder_vectors():
     return res
 
 
+def chain_fixture():
+    """frequency-domain loopback, 2k/QAM16/rate 1/2: input symbols + every reference stage output"""
+    from dvbt_testlib import tx_frequency_domain, channel
+    con, cr, tm = R.QAM16, R.C1_2, R.T2k
+    tx = tx_frequency_domain(con, cr, tm, 400, 5)
+    X = channel(tx["X"][:400])
+    Y, tags = R.rx_demod(X, con, cr, tm)
+    dm = R.rx_demap(Y, con, tm)
+    sd, bd = R.rx_deinterleave(dm, tags, con, tm)
+    sf = [t for t in tags if t[1] == "superframe_start"][0][0]
+    vo, vtags = R.rx_viterbi(bd, con, cr, sf * 1512)
+    cd, rd, ts = R.rx_outer(vo, vtags, fixed_rs=True)
+    assert np.array_equal(ts, tx["ts"][504 * 188: 504 * 188 + len(ts)]) and len(ts) >= 1504
+    d = dict(X=X, cells_head=Y[:3], symbol_index=np.array([t[2] for t in tags if t[1] == "symbol_index"], np.int32),
+             n_out=np.int64(Y.shape[0]), demap=dm, sym_deint_head=sd[:4], bit_deint=bd, viterbi=vo, conv_deint_head=cd[: 204 * 40], rs=rd, ts=ts,
+             ts_source=tx["ts"][504 * 188: 504 * 188 + len(ts) + 1504 * 4])
+    path = os.path.join(HERE, "chain_2k_qam16_r12.npz")
+    np.savez_compressed(path, **d)
+    print("wrote", path, os.path.getsize(path), "bytes")
+
+
 def main():
     assert R.available() and R.available(True), "build oracle/_ref first (make -C oracle ref)"
     d = {}
@@ -91,6 +112,7 @@ def main():
     path = os.path.join(HERE, "hotpath_golden.npz")
     np.savez_compressed(path, **d)
     print("wrote", path, os.path.getsize(path), "bytes,", len(d), "arrays")
+    chain_fixture()
 
 
 if __name__ == "__main__":

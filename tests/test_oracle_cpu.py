@@ -89,3 +89,41 @@ def test_reference_round_trip_on_random_ts():
     cd, rd, ts = R.rx_outer(vo, vt)
     assert len(ts) >= 1504
     assert np.array_equal(ts, tx["ts"][504 * 188: 504 * 188 + len(ts)])
+
+
+# ---- the rest of the chain: restatements against the committed reference outputs -----------------
+CH = np.load(os.path.join(os.path.dirname(__file__), "golden", "chain_2k_qam16_r12.npz"))
+
+
+def test_demod_port_matches_reference_fixture():
+    Y, si, tag = O.demod(CH["X"], 1, 0)
+    assert Y.shape[0] == int(CH["n_out"]) and tag == 0
+    assert np.array_equal(si, CH["symbol_index"])
+    assert np.array_equal(Y[:3].view(np.uint32), CH["cells_head"].view(np.uint32))   # bit-exact floats
+    assert np.array_equal(O.demap(Y, 1).reshape(Y.shape[0], -1), CH["demap"])
+
+
+def test_glue_ports_match_reference_fixture():
+    sd = O.symbol_deinterleave(CH["demap"], 0, CH["symbol_index"])
+    assert np.array_equal(sd[:4], CH["sym_deint_head"])
+    bd = O.bit_deinterleave(sd, 4)
+    assert np.array_equal(bd, CH["bit_deint"].reshape(-1))
+    vo = O.Viterbi(4, 0).work(bd)
+    assert np.array_equal(vo, CH["viterbi"][: len(vo)]) and len(vo) >= len(CH["viterbi"]) - 96
+    cd = O.conv_deinterleave(CH["viterbi"])
+    assert np.array_equal(cd[: len(CH["conv_deint_head"])], CH["conv_deint_head"])
+    rs, st = O.rs_decode(cd[: len(cd) // 204 * 204].reshape(-1, 204))
+    assert np.array_equal(rs.reshape(-1)[: len(CH["rs"])], CH["rs"])
+    ts, first = O.descramble(rs)
+    assert first == 11 and np.array_equal(ts[: len(CH["ts"])], CH["ts"])
+    assert np.array_equal(ts, CH["ts_source"][: len(ts)])
+
+
+@pytest.mark.skipif(not R.available(), reason="oracle/_ref not built")
+def test_acquisition_port_matches_the_reference_build():
+    from dvbt_testlib import tx_frequency_domain, ofdm_modulate
+    tx = tx_frequency_domain(R.QAM16, R.C1_2, R.T2k, 24, 2)
+    x = ofdm_modulate(tx["X"][:24], R.T2k, offset=1301, cfo_bins=0.11, seed=1)
+    ref, cons_ref, tags = R.rx_acquisition(x, R.T2k)
+    got, cons, tag = O.acquisition(x, 2048, 64)
+    assert cons == cons_ref and tag and np.array_equal(ref.view(np.uint32), got.view(np.uint32))
