@@ -283,6 +283,28 @@ class RxWorkload:
         self.kernel_ms = []
         self.stage_ms = []
         self.ts_bytes = 0
+        # e2e: two handles (two CUDA streams) so that the H2D copy of one capture overlaps the kernels of the other
+        self.rx2 = [self.rx, g.rx_chain(self.CON, g.NH, self.CR, g.G1_32, self.TM)]
+        self.pin_ts2 = [self.pin_ts, torch.zeros(self.ts_cap, dtype=torch.uint8).pin_memory()]
+
+    def e2e_pipelined(self, steps):
+        """`steps` host-buffer calls spread over two worker threads (one handle each); returns wall ms"""
+        import ctypes as C
+        lib = self.g.capi.lib()
+
+        def worker(k, count):
+            n = C.c_size_t(0)
+            for _ in range(count):
+                self.g.capi.check(lib.dvbt_b200_rx_run_file_host(self.rx2[k]._h, self.pin_in.data_ptr(), self.nfile, self.GAIN,
+                                                                 self.pin_ts2[k].data_ptr(), self.ts_cap, C.byref(n)))
+        counts = [steps - steps // 2, steps // 2]
+        th = [threading.Thread(target=worker, args=(k, counts[k])) for k in range(2)]
+        t0 = time.perf_counter()
+        for t in th:
+            t.start()
+        for t in th:
+            t.join()
+        return (time.perf_counter() - t0) * 1e3
 
     def step_resident(self, i):
         n = self.rx.run_file_dev(self.d_in.data_ptr(), self.nfile, self.GAIN, self.d_ts.data_ptr(), self.ts_cap)
@@ -494,6 +516,12 @@ def main():
     ok = w.check()
     kms = float(np.mean(w.kernel_ms[a.warmup:]))
     ms_e2e = timed(w.step_e2e, a.steps, a.warmup)
+    ms_e2e_pipe = None
+    if rx:
+        w.e2e_pipelined(2)
+        barrier()
+        ms_e2e_pipe = max_over_ranks(w.e2e_pipelined(a.steps), "cuda")
+        barrier()
 
     if RANK == 0:
         peak, peak_src = load_peaks()
@@ -513,8 +541,12 @@ def main():
             line["viterbi_mbit_per_s"] = vbits * WORLD / (ms / a.steps / 1e3) / 1e6
             line["realtime_factor"] = value / WORLD / 10.0
             line["stage_ms"] = stage
-            line["e2e"] = {"value": e2e, "unit": "Msamples/s", "h2d_bytes_per_step": w.h2d, "d2h_bytes_per_step": w.d2h, "ms_per_step": ms_e2e / a.steps,
-                           "api": "dvbt_b200_rx_run_file_host on pinned host buffers"}
+            e2e_pipe = units / (ms_e2e_pipe / a.steps / 1e3)
+            line["e2e"] = {"value": e2e_pipe, "unit": "Msamples/s", "h2d_bytes_per_step": w.h2d, "d2h_bytes_per_step": w.d2h,
+                           "ms_per_step": ms_e2e_pipe / a.steps,
+                           "api": "dvbt_b200_rx_run_file_host on pinned host buffers, two handles driven by two host threads "
+                                  "(copy of one capture overlaps the kernels of the other); every step copies its capture H2D and its TS D2H",
+                           "single_handle": {"value": e2e, "ms_per_step": ms_e2e / a.steps}}
             info_bits = vbits
             cpu_rx_prepare()
             cu, ct, cst, cok, cvit = cpu_rx_chain()

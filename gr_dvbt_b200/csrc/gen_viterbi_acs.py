@@ -81,16 +81,22 @@ class Gen:
                 if sel not in sel_cache:
                     r = self.new("bm")
                     self.emit("prmt", r, apk, "ZERO", sel)
-                    sel_cache[sel] = r
-            a, b = sel_cache[sel_a], sel_cache[sel_b]
+                    rh = self.new("bh")
+                    self.emit("addc", rh, r, H)  # addend + 0x80 per byte, shared by every pair of the step
+                    sel_cache[sel] = (r, rh)
+            (a, ah), (b, bh) = sel_cache[sel_a], sel_cache[sel_b]
             m0, m1, m2, m3 = self.new("m"), self.new("m"), self.new("m"), self.new("m")
             self.emit("add", m0, mi, a)
             self.emit("add", m1, mj, b)
             self.emit("add", m2, mi, b)
             self.emit("add", m3, mj, a)
+            # compare: t = (mj + b + H) - m0, both steps on the FMA pipe (IMAD) instead of one IADD3 on the ALU pipe
+            h1, h3 = self.new("h"), self.new("h")
+            self.emit("add", h1, mj, bh)
+            self.emit("add", h3, mj, ah)
             t0, t1 = self.new("c"), self.new("c")
-            self.emit("cmp", t0, m1, m0)  # t0 = m1 + H - m0
-            self.emit("cmp", t1, m3, m2)
+            self.emit("subm", t0, h1, m0)  # t0 = m1 + H - m0
+            self.emit("subm", t1, h3, m2)
             k0, k1 = self.new("k"), self.new("k")
             self.emit("signmask", k0, t0)
             self.emit("signmask", k1, t1)
@@ -104,7 +110,7 @@ class Gen:
                 pi, pj = idxP[st], idxP[hi]
                 si, sj = self.new("p"), self.new("p")
                 self.emit("add", si, pi, pi)
-                self.emit("add3c", sj, pj, pj, 0x01010101)
+                self.emit("mad2c", sj, pj, 0x01010101)   # 2*pj + 0x01010101
                 pe, po = self.new("P"), self.new("P")
                 self.emit("sel", pe, si, sj, k0)
                 self.emit("sel", po, si, sj, k1)
@@ -229,6 +235,12 @@ def run_ops(ops, env):
             env[d] = (env[op[2]] + env[op[3]] + u32(op[4])).astype(u32)
         elif k == "cmp":
             env[d] = (env[op[2]] + u32(H) - env[op[3]]).astype(u32)
+        elif k == "addc":
+            env[d] = (env[op[2]] + u32(op[3])).astype(u32)
+        elif k == "subm":
+            env[d] = (env[op[2]] - env[op[3]]).astype(u32)
+        elif k == "mad2c":
+            env[d] = (env[op[2]] * u32(2) + u32(op[3])).astype(u32)
         elif k == "signmask":
             env[d] = prmt(env[op[2]], env["ZERO"], 0xBA98)
         elif k == "sel":
@@ -269,6 +281,12 @@ def emit_cuda(ops, indent="  "):
             lines.append("%s = %s + %s + 0x%08xu;" % (dst(d), ref(op[2]), ref(op[3]), op[4]))
         elif k == "cmp":
             lines.append("%s = %s + 0x80808080u - %s;" % (dst(d), ref(op[2]), ref(op[3])))
+        elif k == "addc":
+            lines.append("%s = %s + 0x%08xu;" % (dst(d), ref(op[2]), op[3]))
+        elif k == "subm":
+            lines.append("%s = vit_mad(%s, vit_neg1, %s);" % (dst(d), ref(op[3]), ref(op[2])))
+        elif k == "mad2c":
+            lines.append("%s = vit_mad(%s, vit_two, 0x%08xu);" % (dst(d), ref(op[2]), op[3]))
         elif k == "signmask":
             lines.append("%s = vit_prmt(%s, 0u, 0xba98u);" % (dst(d), ref(op[2])))
         elif k == "sel":
@@ -289,6 +307,14 @@ HEADER = """// GENERATED by gr_dvbt_b200/csrc/gen_viterbi_acs.py -- do not edit 
 __device__ __forceinline__ uint32_t vit_prmt(uint32_t a, uint32_t b, uint32_t sel) {
   uint32_t r;
   asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(sel));
+  return r;
+}
+// a * b + c on the FMA pipe (IMAD).  b comes from a kernel parameter (vit_neg1 = 0xffffffff, vit_two = 2)
+// so that ptxas cannot fold it back into an ALU-pipe IADD3: the ALU pipe (LOP3/PRMT) is the bottleneck
+// of this kernel and the FMA pipe has twice its width (profiles/r01_viterbi_v1_ncu_summary.txt).
+__device__ __forceinline__ uint32_t vit_mad(uint32_t a, uint32_t b, uint32_t c) {
+  uint32_t r;
+  asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c));
   return r;
 }
 // per byte: mask ? y : x   (mask bytes are 0x00 or 0xff)
@@ -313,7 +339,7 @@ def main():
     out = [HEADER]
     out.append("// Steps 1..6 of a byte time.  In: M[16], P[16] in start layout (lane bits = state bits 2,3).\n"
                "// Out: M_ev[16], P_ev[16] in event layout: word w = (s5,s2,s1,s0), lane = (s4,s3).\n"
-               "#define VIT_ACS_PART1(M, P, M_ev, P_ev, apk0, apk1, apk2, apk3, apk4, apk5) \\\n")
+               "// (expects uint32_t vit_neg1, vit_two in scope)\n#define VIT_ACS_PART1(M, P, M_ev, P_ev, apk0, apk1, apk2, apk3, apk4, apk5) \\\n")
     body = emit_cuda(res["part1"], indent="  ")
     out.append("  do { \\\n" + "\n".join(l + " \\" for l in body.split("\n")) + "\n  } while (0)\n\n")
     out.append("// Event-layout metrics -> transposed to lane bits (0,1), then steps 7,8.  P must be all zero on entry\n"

@@ -8,8 +8,9 @@
 //     design_filter); polyphase arms h[phase + 32 j]; y[m] = sum_j h[(35 m mod 32) + 32 j] *
 //     x[floor(35 m / 32) - j] with zero history (rational_resampler_base_ccc::general_work);
 //   blocks.multiply_const_vcc((k,)): y * (k + 0j).
-// One thread per output sample, taps in shared memory (36 per arm), float accumulation in tap
-// order.  HBM bound: 8 B read (x 35/32) + 8 B written per output sample.
+// A block stages the inputs of 512 outputs in shared memory (each input read once), taps in shared
+// memory (36 per arm), float accumulation in tap order.  HBM bound: 8 B read (x 35/32) + 8 B written
+// per output sample.
 #include "chain_internal.cuh"
 
 #include <math.h>
