@@ -246,73 +246,131 @@ __global__ void acq_pass2_kernel(AcqParams p, int nsym, const float *__restrict_
 struct AcqWalk {
   int n_found;        // symbols that produced output
   int code;           // 0: all symbols processed, else kLost / kOff / kSplit
-  int last_state;     // state index of the last processed symbol
+  float avg;          // true detector average after the last processed symbol (incl. a missed one)
+  int n_override;     // symbols whose speculation did not hold and that were re-run sequentially
 };
 
-__global__ void __launch_bounds__(1024) acq_compose_kernel(int nsym, int per_thread, int start_state, const unsigned char *__restrict__ next,
-                                                           unsigned char *__restrict__ state_of, AcqWalk *walk) {
-  extern __shared__ unsigned char s_map[];  // [nthreads][kNS] chunk maps, then [nthreads] start states
-  const int t = threadIdx.x, nt = blockDim.x;
+// chunk maps: thread = one chunk of `per_thread` symbols, all 85 start states advanced together
+__global__ void acq_chunkmap_kernel(int nsym, int per_thread, int nchunks, const unsigned char *__restrict__ next,
+                                    unsigned char *__restrict__ maps) {
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= nchunks) return;
   const int n0 = t * per_thread, n1 = min(nsym, n0 + per_thread);
-  // phase A: composite map of my chunk for every start state
-  // (all 85 chains advance together so that the loads of one symbol are independent)
-  unsigned char *mine = s_map + t * kNS;
-  for (int s0 = 0; s0 < kNS; s0++) mine[s0] = (unsigned char)s0;
+  unsigned char cur[kNS];
+#pragma unroll
+  for (int s0 = 0; s0 < kNS; s0++) cur[s0] = (unsigned char)s0;
   for (int n = n0; n < n1; n++) {
     const unsigned char *row = next + (long long)n * kNS;
-#pragma unroll 5
+#pragma unroll
     for (int s0 = 0; s0 < kNS; s0++) {
-      unsigned char cur = mine[s0];
-      if (cur < kStop) {
-        unsigned char nx = row[cur];
-        mine[s0] = nx >= kStop ? kStop : nx;
+      if (cur[s0] < kStop) {
+        unsigned char nx = row[cur[s0]];
+        cur[s0] = nx >= kStop ? kStop : nx;
       }
     }
   }
-  __syncthreads();
-  unsigned char *s_start = s_map + nt * kNS;
-  __shared__ int s_last_chunk;
+#pragma unroll
+  for (int s0 = 0; s0 < kNS; s0++) maps[(long long)t * kNS + s0] = cur[s0];
+}
+
+// Chains the chunk maps (thread 0), then every thread re-walks its chunk from the now known start state
+// and writes (offset c, best) per symbol.  Where the speculation stops (kSplit) thread 0 continues on the
+// spot: it runs the reference detector sequentially on the next symbol from the true average, and keeps
+// doing so until a symbol's result re-validates the tables; those symbols are written by thread 0 itself.
+__global__ void __launch_bounds__(1024) acq_compose_kernel(AcqParams p, int nsym, int per_thread, int nchunks, int start_state, float avg_first,
+                                                           const float *__restrict__ lambda, const float *__restrict__ avg1,
+                                                           const signed char *__restrict__ best2, const float *__restrict__ avg2,
+                                                           const unsigned char *__restrict__ next, const unsigned char *__restrict__ maps,
+                                                           unsigned char *__restrict__ c_of, signed char *__restrict__ best_of, AcqWalk *walk) {
+  extern __shared__ unsigned char s_buf[];  // [nchunks] start state of each chunk, 0xFF = written by thread 0
+  __shared__ int s_n_end;                   // symbols handled (all chunks before it are complete)
+  const int t = threadIdx.x;
   if (t == 0) {
+    int n = 0, code = 0, n_found = 0, n_override = 0;
     unsigned char st = (unsigned char)start_state;
-    int last = nt - 1;
-    for (int k = 0; k < nt; k++) {
-      s_start[k] = st;
-      if (k * per_thread >= nsym) { last = k - 1; break; }
-      unsigned char m = s_map[k * kNS + st];
-      if (m >= kStop) { last = k; break; }
-      st = m;
+    float avg = avg_first;
+    bool avg_known = true;   // `avg` holds the true average before symbol n (only maintained where needed)
+    for (int k = 0; k < nchunks; k++) s_buf[k] = 0xFE;  // not reached
+    while (n < nsym && !code) {
+      int k = n / per_thread;
+      if (n == k * per_thread) {
+        unsigned char m = maps[(long long)k * kNS + st];
+        if (m < kStop) { s_buf[k] = st; st = m; n = min(nsym, n + per_thread); avg_known = false; n_found = n; continue; }
+      }
+      // symbol by symbol inside chunk k (this chunk is written here, not in the parallel re-walk)
+      s_buf[k] = 0xFF;
+      int nend = min(nsym, (k + 1) * per_thread);
+      while (n < nend && !code) {
+        int c = st / kND;
+        unsigned char nx = next[(long long)n * kNS + st];
+        signed char best = best2[(long long)n * kNS + st];
+        float a_out = avg2[(long long)n * kNS + st];
+        if (nx == kLost) { c_of[n] = (unsigned char)c; best_of[n] = -1; avg = a_out; avg_known = true; code = kLost; break; }
+        c_of[n] = (unsigned char)c;
+        best_of[n] = best;
+        avg = a_out;
+        avg_known = true;
+        n++;
+        n_found = n;
+        if (nx == kOff) { code = kOff; break; }
+        if (nx < kStop) { st = nx; continue; }
+        // kSplit: the tables cannot be trusted for the next symbol; run the detector from the true average
+        int cn = c + best - 8;
+        while (n < nsym && !code) {
+          if (cn < 0 || cn >= kNC) { code = kOff; break; }
+          int b2;
+          float a2 = avg;
+          int np = peak_detect(lambda + (long long)n * kCand + cn, 16, &a2, p.rise, p.fall, p.alpha, &b2);
+          n_override++;
+          int kk = n / per_thread;
+          if (s_buf[kk] != 0xFF) {
+            // entering a new chunk in sequential mode: it is ours now
+            s_buf[kk] = 0xFF;
+          }
+          c_of[n] = (unsigned char)cn;
+          avg = a2;
+          if (np <= 0) { best_of[n] = -1; code = kLost; break; }
+          best_of[n] = (signed char)b2;
+          n++;
+          n_found = n;
+          int c2 = cn + b2 - 8, d2 = 8 - b2;
+          if (c2 < 0 || c2 >= kNC) { code = kOff; break; }
+          bool ok = d2 >= -2 && d2 <= 2 && __float_as_uint(avg) == __float_as_uint(avg1[(long long)(n - 1) * kNC + cn]);
+          if (ok) { st = (unsigned char)(c2 * kND + d2 + 2); break; }   // tables valid again from symbol n
+          cn = c2;
+        }
+        if (n >= nsym || n == (n / per_thread) * per_thread) break;  // at a chunk boundary the maps take over again
+        nend = min(nsym, (n / per_thread + 1) * per_thread);
+        s_buf[n / per_thread] = 0xFF;
+      }
     }
-    s_last_chunk = last;
+    if (code == kLost) n_found = n;  // the missed symbol produces no output
+    walk->code = code;
+    walk->n_found = n_found;
+    walk->n_override = n_override;
+    // true average at the end: known if the last step was sequential, else the table entry of the last symbol
+    walk->avg = avg;
+    s_n_end = avg_known ? -1 : n_found;
+    (void)avg_known;
   }
   __syncthreads();
-  // phase C: re-walk with the known start state, record the state used at every symbol
-  if (t <= s_last_chunk && n0 < nsym) {
-    unsigned char st = s_start[t];
-    int n = n0;
-    int code = 0;
-    for (; n < n1; n++) {
-      state_of[n] = st;
-      unsigned char nx = next[(long long)n * kNS + st];
-      if (nx >= kStop) { code = nx; break; }
-      st = nx;
-    }
-    if (code) {
-      walk->code = code;
-      walk->n_found = code == kLost ? n : n + 1;
-      walk->last_state = state_of[n];
-    } else if (t == s_last_chunk) {
-      walk->code = 0;
-      walk->n_found = n1;
-      walk->last_state = state_of[n1 - 1];
+  // parallel re-walk of the chunks that were crossed by their map
+  if (t < nchunks && s_buf[t] < kStop) {
+    unsigned char st = s_buf[t];
+    const int n0 = t * per_thread, n1 = min(nsym, n0 + per_thread);
+    for (int n = n0; n < n1; n++) {
+      c_of[n] = (unsigned char)(st / kND);
+      best_of[n] = best2[(long long)n * kNS + st];
+      if (n == s_n_end - 1) walk->avg = avg2[(long long)n * kNS + st];
+      st = next[(long long)n * kNS + st];
     }
   }
 }
 
 // per-symbol outputs + phase schedule (one warp, 32 symbols per iteration)
 __global__ void __launch_bounds__(32) acq_finish_kernel(AcqParams p, long long base, int c0, const float2 *__restrict__ gamma,
-                                                        const signed char *__restrict__ best2, const float *__restrict__ avg2,
-                                                        const unsigned char *__restrict__ state_of, const AcqWalk *walk, AcqState *st,
-                                                        SymOut *__restrict__ out) {
+                                                        const unsigned char *__restrict__ c_of, const signed char *__restrict__ best_of,
+                                                        const AcqWalk *walk, AcqState *st, SymOut *__restrict__ out) {
   const int lane = threadIdx.x;
   const int total = p.N + p.cp;
   const double invN = -1.0 / (double)p.N;
@@ -325,9 +383,8 @@ __global__ void __launch_bounds__(32) acq_finish_kernel(AcqParams p, long long b
   for (int bn = 0; bn < nf; bn += 32) {
     int m = bn + lane;
     bool live = m < nf;
-    int s = live ? state_of[m] : 0;
-    int c = s / kND;
-    int best = live ? best2[(long long)m * kNS + s] : 8;
+    int c = live ? c_of[m] : 0;
+    int best = live ? best_of[m] : 8;
     int peak = c0 - kD + c + best;                     // cp_start_before - 8 + best
     float2 g = live ? gamma[(long long)m * kCand + c + best] : make_float2(1.f, 0.f);
     double e = invN * (double)atan2f(g.y, g.x);        // d_nextphaseinc left by symbol m (:311)
@@ -372,11 +429,9 @@ __global__ void __launch_bounds__(32) acq_finish_kernel(AcqParams p, long long b
   if (lane == 0) {
     int code = walk->code;
     int cp_start = last_peak;
-    if (nf > 0) st->avg = avg2[(long long)(nf - 1) * kNS + state_of[nf - 1]];
+    st->avg = walk->avg;
     if (code == kLost) {
-      // the missed symbol still runs the detector (its average is the entry's) and advances the phase (:335-343)
-      int sl = walk->last_state;
-      st->avg = avg2[(long long)nf * kNS + sl];
+      // the missed symbol still ran the detector (walk->avg includes it) and advances the phase (:335-343)
       ph += total * inc;
       ph -= twopi * rint(ph / twopi);
     }
@@ -390,6 +445,7 @@ __global__ void __launch_bounds__(32) acq_finish_kernel(AcqParams p, long long b
     st->fallback = code == kSplit ? 1 : 0;
     st->n_run += nf;
     st->n_single += code ? 1 : 0;
+    st->n_seq += walk->n_override;
     st->consumed = (long long)nf * total;
   }
 }
@@ -420,7 +476,7 @@ struct dvbt_b200_acq {
   bool own_stream = true;
   cufftHandle plan = 0;
   int plan_batch = 0;
-  dvbt::DevBuf d_x, d_state, h_state, d_lambda, d_gamma, d_avg1, d_avg2, d_peak, d_sym, d_out, d_il, d_ig, d_eps, d_flag;
+  dvbt::DevBuf d_x, d_state, h_state, d_lambda, d_gamma, d_avg1, d_avg2, d_peak, d_sym, d_out, d_il, d_ig, d_eps, d_flag, d_maps, d_cof, d_bof;
 };
 
 namespace dvbt {
@@ -477,21 +533,25 @@ int acq_run(dvbt_b200_acq *h, const float2 *x, long long n, float2 *d_out, long 
       int nthreads = (int)((nsym + per_thread - 1) / per_thread);
       if ((rc = h->d_avg1.reserve((size_t)nsym * kNC * 4)) || (rc = h->d_avg2.reserve((size_t)nsym * kNS * 4)) ||
           (rc = h->d_peak.reserve((size_t)nsym * kNS)) || (rc = h->d_flag.reserve((size_t)nsym * kNS)) ||
-          (rc = h->d_eps.reserve((size_t)nsym + 128)))
+          (rc = h->d_eps.reserve(256)))
         return rc;
       long long t1 = nsym * kNC, t2 = nsym * kNS;
       acq_pass1_kernel<<<(unsigned)((t1 + 127) / 128), 128, 0, st>>>(p, (int)nsym, h->d_lambda.as<float>(), h->d_avg1.as<float>());
       acq_pass2_kernel<<<(unsigned)((t2 + 127) / 128), 128, 0, st>>>(p, (int)nsym, h->d_lambda.as<float>(), h->d_avg1.as<float>(), hs->avg,
                                                                     h->d_peak.as<signed char>(), h->d_avg2.as<float>(),
                                                                     h->d_flag.as<unsigned char>());
-      size_t csmem = (size_t)nthreads * (kNS + 1) + 16;
-      DVBT_CUDA_TRY(cudaFuncSetAttribute(acq_compose_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-      AcqWalk *d_walk = reinterpret_cast<AcqWalk *>(h->d_eps.as<unsigned char>() + ((nsym + 15) / 16) * 16);
-      acq_compose_kernel<<<1, nthreads, csmem, st>>>((int)nsym, per_thread, (kD - 8) * kND + 2, h->d_flag.as<unsigned char>(),
-                                                     h->d_eps.as<unsigned char>(), d_walk);
-      acq_finish_kernel<<<1, 32, 0, st>>>(p, pos, c0, h->d_gamma.as<float2>(), h->d_peak.as<signed char>(), h->d_avg2.as<float>(),
-                                          h->d_eps.as<unsigned char>(), d_walk, h->d_state.as<AcqState>(), h->d_sym.as<SymOut>());
-      count_launch(4);
+      if ((rc = h->d_maps.reserve((size_t)nthreads * kNS)) || (rc = h->d_cof.reserve((size_t)nsym)) || (rc = h->d_bof.reserve((size_t)nsym)))
+        return rc;
+      acq_chunkmap_kernel<<<(nthreads + 63) / 64, 64, 0, st>>>((int)nsym, per_thread, nthreads, h->d_flag.as<unsigned char>(),
+                                                               h->d_maps.as<unsigned char>());
+      AcqWalk *d_walk = h->d_eps.as<AcqWalk>();
+      acq_compose_kernel<<<1, nthreads < 32 ? 32 : nthreads, (size_t)nthreads + 16, st>>>(
+          p, (int)nsym, per_thread, nthreads, (kD - 8) * kND + 2, hs->avg, h->d_lambda.as<float>(), h->d_avg1.as<float>(),
+          h->d_peak.as<signed char>(), h->d_avg2.as<float>(), h->d_flag.as<unsigned char>(), h->d_maps.as<unsigned char>(),
+          h->d_cof.as<unsigned char>(), h->d_bof.as<signed char>(), d_walk);
+      acq_finish_kernel<<<1, 32, 0, st>>>(p, pos, c0, h->d_gamma.as<float2>(), h->d_cof.as<unsigned char>(), h->d_bof.as<signed char>(), d_walk,
+                                          h->d_state.as<AcqState>(), h->d_sym.as<SymOut>());
+      count_launch(6);
       DVBT_CUDA_TRY(cudaGetLastError());
     }
     DVBT_CUDA_TRY(cudaMemcpyAsync(hs, h->d_state.p, sizeof(AcqState), cudaMemcpyDeviceToHost, st));
@@ -602,7 +662,7 @@ void dvbt_b200_acq_destroy(dvbt_b200_acq *h) {
   if (!h) return;
   if (h->stream) cudaStreamSynchronize(h->stream);
   if (h->plan) cufftDestroy(h->plan);
-  dvbt::DevBuf *bufs[] = {&h->d_x, &h->d_state, &h->h_state, &h->d_lambda, &h->d_gamma, &h->d_avg1, &h->d_avg2, &h->d_peak, &h->d_sym, &h->d_out, &h->d_il, &h->d_ig, &h->d_eps, &h->d_flag};
+  dvbt::DevBuf *bufs[] = {&h->d_x, &h->d_state, &h->h_state, &h->d_lambda, &h->d_gamma, &h->d_avg1, &h->d_avg2, &h->d_peak, &h->d_sym, &h->d_out, &h->d_il, &h->d_ig, &h->d_eps, &h->d_flag, &h->d_maps, &h->d_cof, &h->d_bof};
   for (auto *b : bufs) b->release();
   if (h->stream && h->own_stream) cudaStreamDestroy(h->stream);
   delete h;

@@ -78,8 +78,8 @@ __global__ void __launch_bounds__(256) resample_kernel(const float2 *__restrict_
                                                        const float *__restrict__ taps_arm, int per_arm, float scale) {
   extern __shared__ float s_mem[];
   float *s_taps = s_mem;                                        // [32][per_arm]
-  float2 *s_x = reinterpret_cast<float2 *>(s_mem + kInterp * per_arm);  // [kTileIn + per_arm]
-  for (int i = threadIdx.x; i < kInterp * per_arm; i += blockDim.x) s_taps[i] = taps_arm[i];
+  float2 *s_x = reinterpret_cast<float2 *>(s_mem + kInterp * (per_arm | 1));  // [kTileIn + per_arm], 8-byte aligned
+  for (int i = threadIdx.x; i < kInterp * per_arm; i += blockDim.x) s_taps[(i / per_arm) * (per_arm | 1) + i % per_arm] = taps_arm[i];
   long long m0 = (long long)blockIdx.x * kOutPerBlock;
   long long a0 = (m0 * kDecim) / kInterp;                       // newest input of the block's first output
   long long lo = a0 - (per_arm - 1);                            // oldest input needed
@@ -96,7 +96,7 @@ __global__ void __launch_bounds__(256) resample_kernel(const float2 *__restrict_
     long long t = m * kDecim;
     long long a = t / kInterp;
     int phase = (int)(t - a * kInterp);
-    const float *h = s_taps + phase * per_arm;
+    const float *h = s_taps + phase * (per_arm | 1);          // odd row stride: no bank conflicts between phases
     const float2 *xs = s_x + (int)(a - lo);                     // xs[-j] = x[a - j]
     float accr = 0.f, acci = 0.f;
     for (int j = 0; j < per_arm; j++) {
@@ -139,7 +139,7 @@ int resample_launch(const float2 *d_x, long long nin, float2 *d_y, long long nou
   }
   Resampler *r = g_res[dev];
   if (nout <= 0) return 0;
-  size_t smem = (size_t)kInterp * r->per_arm * 4 + (size_t)(kTileIn + r->per_arm) * 8;
+  size_t smem = (size_t)(kInterp * (r->per_arm | 1) + 2) * 4 + (size_t)(kTileIn + r->per_arm) * 8;
   resample_kernel<<<(unsigned)((nout + kOutPerBlock - 1) / kOutPerBlock), 256, smem, st>>>(d_x, nin, d_y, nout, r->d_taps.as<float>(), r->per_arm, scale);
   count_launch();
   DVBT_CUDA_TRY(cudaGetLastError());
