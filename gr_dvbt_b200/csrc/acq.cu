@@ -144,8 +144,13 @@ __global__ void acq_init_lambda_kernel(AcqParams p, const float2 *__restrict__ x
   ml_point(x, base + (p.N + p.cp - 1) + k, p.N, p.cp, p.rho2, &lambda[k], &gamma[k]);
 }
 
-__global__ void acq_init_peak_kernel(AcqParams p, const float *__restrict__ lambda, const float2 *__restrict__ gamma, AcqState *st) {
+__global__ void __launch_bounds__(256) acq_init_peak_kernel(AcqParams p, const float *__restrict__ lambda_g, const float2 *__restrict__ gamma,
+                                                            AcqState *st) {
+  extern __shared__ float s_lambda[];
+  for (int i = threadIdx.x; i < p.N; i += blockDim.x) s_lambda[i] = lambda_g[i];
+  __syncthreads();
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  const float *lambda = s_lambda;
   float avg = st->avg;
   int best = 0;
   int n = peak_detect(lambda, p.N, &avg, p.rise, p.fall, p.alpha, &best);
@@ -250,27 +255,21 @@ struct AcqWalk {
   int n_override;     // symbols whose speculation did not hold and that were re-run sequentially
 };
 
-// chunk maps: thread = one chunk of `per_thread` symbols, all 85 start states advanced together
-__global__ void acq_chunkmap_kernel(int nsym, int per_thread, int nchunks, const unsigned char *__restrict__ next,
-                                    unsigned char *__restrict__ maps) {
-  int t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= nchunks) return;
-  const int n0 = t * per_thread, n1 = min(nsym, n0 + per_thread);
-  unsigned char cur[kNS];
-#pragma unroll
-  for (int s0 = 0; s0 < kNS; s0++) cur[s0] = (unsigned char)s0;
-  for (int n = n0; n < n1; n++) {
-    const unsigned char *row = next + (long long)n * kNS;
-#pragma unroll
-    for (int s0 = 0; s0 < kNS; s0++) {
-      if (cur[s0] < kStop) {
-        unsigned char nx = row[cur[s0]];
-        cur[s0] = nx >= kStop ? kStop : nx;
-      }
+// chunk maps: one warp per chunk of `per_thread` symbols, lane = start state (85 states, 3 rounds)
+__global__ void __launch_bounds__(128) acq_chunkmap_kernel(int nsym, int per_thread, int nchunks, const unsigned char *__restrict__ next,
+                                                           unsigned char *__restrict__ maps) {
+  int w = (int)((blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
+  if (w >= nchunks) return;
+  const int n0 = w * per_thread, n1 = min(nsym, n0 + per_thread);
+  for (int s0 = lane; s0 < kNS; s0 += 32) {
+    unsigned char cur = (unsigned char)s0;
+    for (int n = n0; n < n1; n++) {
+      unsigned char nx = next[(long long)n * kNS + cur];
+      if (nx >= kStop) { cur = kStop; break; }
+      cur = nx;
     }
+    maps[(long long)w * kNS + s0] = cur;
   }
-#pragma unroll
-  for (int s0 = 0; s0 < kNS; s0++) maps[(long long)t * kNS + s0] = cur[s0];
 }
 
 // Chains the chunk maps (thread 0), then every thread re-walks its chunk from the now known start state
@@ -282,9 +281,12 @@ __global__ void __launch_bounds__(1024) acq_compose_kernel(AcqParams p, int nsym
                                                            const signed char *__restrict__ best2, const float *__restrict__ avg2,
                                                            const unsigned char *__restrict__ next, const unsigned char *__restrict__ maps,
                                                            unsigned char *__restrict__ c_of, signed char *__restrict__ best_of, AcqWalk *walk) {
-  extern __shared__ unsigned char s_buf[];  // [nchunks] start state of each chunk, 0xFF = written by thread 0
+  extern __shared__ unsigned char s_buf[];  // [nchunks] start state of each chunk, 0xFF = written by thread 0; then the chunk maps
   __shared__ int s_n_end;                   // symbols handled (all chunks before it are complete)
   const int t = threadIdx.x;
+  unsigned char *s_maps = s_buf + ((nchunks + 15) / 16) * 16;
+  for (int i = t; i < nchunks * kNS; i += blockDim.x) s_maps[i] = maps[i];
+  __syncthreads();
   if (t == 0) {
     int n = 0, code = 0, n_found = 0, n_override = 0;
     unsigned char st = (unsigned char)start_state;
@@ -294,7 +296,7 @@ __global__ void __launch_bounds__(1024) acq_compose_kernel(AcqParams p, int nsym
     while (n < nsym && !code) {
       int k = n / per_thread;
       if (n == k * per_thread) {
-        unsigned char m = maps[(long long)k * kNS + st];
+        unsigned char m = s_maps[k * kNS + st];
         if (m < kStop) { s_buf[k] = st; st = m; n = min(nsym, n + per_thread); avg_known = false; n_found = n; continue; }
       }
       // symbol by symbol inside chunk k (this chunk is written here, not in the parallel re-walk)
@@ -367,27 +369,40 @@ __global__ void __launch_bounds__(1024) acq_compose_kernel(AcqParams p, int nsym
   }
 }
 
-// per-symbol outputs + phase schedule (one warp, 32 symbols per iteration)
-__global__ void __launch_bounds__(32) acq_finish_kernel(AcqParams p, long long base, int c0, const float2 *__restrict__ gamma,
-                                                        const unsigned char *__restrict__ c_of, const signed char *__restrict__ best_of,
-                                                        const AcqWalk *walk, AcqState *st, SymOut *__restrict__ out) {
+// per-symbol quantities that need no ordering: peak position and the phase increment it leaves behind
+__global__ void acq_post_kernel(AcqParams p, int c0, const float2 *__restrict__ gamma, const unsigned char *__restrict__ c_of,
+                                const signed char *__restrict__ best_of, const AcqWalk *walk, int *__restrict__ peak_of,
+                                double *__restrict__ e_of) {
+  int m = blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= walk->n_found) return;
+  int c = c_of[m], best = best_of[m];
+  peak_of[m] = c0 - kD + c + best;                         // cp_start_before - 8 + best
+  float2 g = gamma[(long long)m * kCand + c + best];
+  e_of[m] = (-1.0 / (double)p.N) * (double)atan2f(g.y, g.x);  // d_nextphaseinc left by symbol m (:311)
+}
+
+// phase schedule (:285-312) as a warp scan, 32 symbols per iteration, next iteration's inputs prefetched
+__global__ void __launch_bounds__(32) acq_finish_kernel(AcqParams p, long long base, const int *__restrict__ peak_of,
+                                                        const double *__restrict__ e_of, const AcqWalk *walk, AcqState *st,
+                                                        SymOut *__restrict__ out) {
   const int lane = threadIdx.x;
   const int total = p.N + p.cp;
-  const double invN = -1.0 / (double)p.N;
   const double twopi = 2.0 * M_PI;
   const int nf = walk->n_found;
   double ph = st->phase, inc = st->phaseinc;
   double pend_prev = st->nextphaseinc;   // e_{m-1} for the first symbol of the iteration
   int nextpos_prev = st->nextpos;
   int last_peak = st->cp_start;
+  int peak_n = lane < nf ? peak_of[lane] : 0;
+  double e_n = lane < nf ? e_of[lane] : 0.0;
   for (int bn = 0; bn < nf; bn += 32) {
     int m = bn + lane;
     bool live = m < nf;
-    int c = live ? c_of[m] : 0;
-    int best = live ? best_of[m] : 8;
-    int peak = c0 - kD + c + best;                     // cp_start_before - 8 + best
-    float2 g = live ? gamma[(long long)m * kCand + c + best] : make_float2(1.f, 0.f);
-    double e = invN * (double)atan2f(g.y, g.x);        // d_nextphaseinc left by symbol m (:311)
+    int peak = peak_n;
+    double e = e_n;
+    int mn = m + 32;
+    peak_n = mn < nf ? peak_of[mn] : 0;               // prefetch
+    e_n = mn < nf ? e_of[mn] : 0.0;
     int npos = peak - total;                           // d_nextpos left by symbol m (:312)
     // what symbol m sees: the schedule left by symbol m-1
     double pendm = __shfl_up_sync(0xffffffffu, e, 1);
@@ -428,7 +443,6 @@ __global__ void __launch_bounds__(32) acq_finish_kernel(AcqParams p, long long b
   }
   if (lane == 0) {
     int code = walk->code;
-    int cp_start = last_peak;
     st->avg = walk->avg;
     if (code == kLost) {
       // the missed symbol still ran the detector (walk->avg includes it) and advances the phase (:335-343)
@@ -439,7 +453,7 @@ __global__ void __launch_bounds__(32) acq_finish_kernel(AcqParams p, long long b
     st->phaseinc = inc;
     st->nextphaseinc = pend_prev;
     st->nextpos = nextpos_prev;
-    st->cp_start = cp_start;
+    st->cp_start = last_peak;
     st->n_out = nf;
     st->lost_at = code == kLost ? nf : (code ? -2 - nf : -1);   // -2-nf: stopped after nf symbols without a miss
     st->fallback = code == kSplit ? 1 : 0;
@@ -476,7 +490,7 @@ struct dvbt_b200_acq {
   bool own_stream = true;
   cufftHandle plan = 0;
   int plan_batch = 0;
-  dvbt::DevBuf d_x, d_state, h_state, d_lambda, d_gamma, d_avg1, d_avg2, d_peak, d_sym, d_out, d_il, d_ig, d_eps, d_flag, d_maps, d_cof, d_bof;
+  dvbt::DevBuf d_x, d_state, h_state, d_lambda, d_gamma, d_avg1, d_avg2, d_peak, d_sym, d_out, d_il, d_ig, d_eps, d_flag, d_maps, d_cof, d_bof, d_peakof, d_eof;
 };
 
 namespace dvbt {
@@ -502,7 +516,7 @@ int acq_run(dvbt_b200_acq *h, const float2 *x, long long n, float2 *d_out, long 
       if (n - pos < 2LL * p.N + p.cp + 8 || produced >= out_capacity_syms) break;
       if ((rc = h->d_il.reserve((size_t)p.N * 4)) || (rc = h->d_ig.reserve((size_t)p.N * 8))) return rc;
       acq_init_lambda_kernel<<<(p.N + 127) / 128, 128, 0, st>>>(p, x, pos, h->d_il.as<float>(), h->d_ig.as<float2>());
-      acq_init_peak_kernel<<<1, 32, 0, st>>>(p, h->d_il.as<float>(), h->d_ig.as<float2>(), h->d_state.as<AcqState>());
+      acq_init_peak_kernel<<<1, 256, (size_t)p.N * 4, st>>>(p, h->d_il.as<float>(), h->d_ig.as<float2>(), h->d_state.as<AcqState>());
       count_launch(2);
       DVBT_CUDA_TRY(cudaGetLastError());
       DVBT_CUDA_TRY(cudaMemcpyAsync(hs, h->d_state.p, sizeof(AcqState), cudaMemcpyDeviceToHost, st));
@@ -542,16 +556,20 @@ int acq_run(dvbt_b200_acq *h, const float2 *x, long long n, float2 *d_out, long 
                                                                     h->d_flag.as<unsigned char>());
       if ((rc = h->d_maps.reserve((size_t)nthreads * kNS)) || (rc = h->d_cof.reserve((size_t)nsym)) || (rc = h->d_bof.reserve((size_t)nsym)))
         return rc;
-      acq_chunkmap_kernel<<<(nthreads + 63) / 64, 64, 0, st>>>((int)nsym, per_thread, nthreads, h->d_flag.as<unsigned char>(),
+      acq_chunkmap_kernel<<<(nthreads * 32 + 127) / 128, 128, 0, st>>>((int)nsym, per_thread, nthreads, h->d_flag.as<unsigned char>(),
                                                                h->d_maps.as<unsigned char>());
       AcqWalk *d_walk = h->d_eps.as<AcqWalk>();
-      acq_compose_kernel<<<1, nthreads < 32 ? 32 : nthreads, (size_t)nthreads + 16, st>>>(
+      DVBT_CUDA_TRY(cudaFuncSetAttribute(acq_compose_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+      acq_compose_kernel<<<1, nthreads < 32 ? 32 : nthreads, (size_t)nthreads * (kNS + 1) + 64, st>>>(
           p, (int)nsym, per_thread, nthreads, (kD - 8) * kND + 2, hs->avg, h->d_lambda.as<float>(), h->d_avg1.as<float>(),
           h->d_peak.as<signed char>(), h->d_avg2.as<float>(), h->d_flag.as<unsigned char>(), h->d_maps.as<unsigned char>(),
           h->d_cof.as<unsigned char>(), h->d_bof.as<signed char>(), d_walk);
-      acq_finish_kernel<<<1, 32, 0, st>>>(p, pos, c0, h->d_gamma.as<float2>(), h->d_cof.as<unsigned char>(), h->d_bof.as<signed char>(), d_walk,
-                                          h->d_state.as<AcqState>(), h->d_sym.as<SymOut>());
-      count_launch(6);
+      if ((rc = h->d_peakof.reserve((size_t)nsym * 4)) || (rc = h->d_eof.reserve((size_t)nsym * 8))) return rc;
+      acq_post_kernel<<<(unsigned)((nsym + 127) / 128), 128, 0, st>>>(p, c0, h->d_gamma.as<float2>(), h->d_cof.as<unsigned char>(),
+                                                                     h->d_bof.as<signed char>(), d_walk, h->d_peakof.as<int>(), h->d_eof.as<double>());
+      acq_finish_kernel<<<1, 32, 0, st>>>(p, pos, h->d_peakof.as<int>(), h->d_eof.as<double>(), d_walk, h->d_state.as<AcqState>(),
+                                          h->d_sym.as<SymOut>());
+      count_launch(7);
       DVBT_CUDA_TRY(cudaGetLastError());
     }
     DVBT_CUDA_TRY(cudaMemcpyAsync(hs, h->d_state.p, sizeof(AcqState), cudaMemcpyDeviceToHost, st));
@@ -662,7 +680,7 @@ void dvbt_b200_acq_destroy(dvbt_b200_acq *h) {
   if (!h) return;
   if (h->stream) cudaStreamSynchronize(h->stream);
   if (h->plan) cufftDestroy(h->plan);
-  dvbt::DevBuf *bufs[] = {&h->d_x, &h->d_state, &h->h_state, &h->d_lambda, &h->d_gamma, &h->d_avg1, &h->d_avg2, &h->d_peak, &h->d_sym, &h->d_out, &h->d_il, &h->d_ig, &h->d_eps, &h->d_flag, &h->d_maps, &h->d_cof, &h->d_bof};
+  dvbt::DevBuf *bufs[] = {&h->d_x, &h->d_state, &h->h_state, &h->d_lambda, &h->d_gamma, &h->d_avg1, &h->d_avg2, &h->d_peak, &h->d_sym, &h->d_out, &h->d_il, &h->d_ig, &h->d_eps, &h->d_flag, &h->d_maps, &h->d_cof, &h->d_bof, &h->d_peakof, &h->d_eof};
   for (auto *b : bufs) b->release();
   if (h->stream && h->own_stream) cudaStreamDestroy(h->stream);
   delete h;

