@@ -272,98 +272,110 @@ __global__ void __launch_bounds__(128) acq_chunkmap_kernel(int nsym, int per_thr
   }
 }
 
-// Chains the chunk maps (thread 0), then every thread re-walks its chunk from the now known start state
-// and writes (offset c, best) per symbol.  Where the speculation stops (kSplit) thread 0 continues on the
-// spot: it runs the reference detector sequentially on the next symbol from the true average, and keeps
-// doing so until a symbol's result re-validates the tables; those symbols are written by thread 0 itself.
+// Chains the chunk maps (thread 0) into a list of table segments (first symbol, end, start state); every
+// thread then re-walks one segment and writes (offset c, best) per symbol.  Where the speculation stops
+// (kSplit) thread 0 continues on the spot: it runs the reference detector sequentially on the next symbol
+// from the true average, and keeps doing so until a symbol's result re-validates the tables; those few
+// symbols are written by thread 0 itself.  Thread 0 touches one table byte per symbol at most.
+constexpr int kMaxSeg = 2048;
+
 __global__ void __launch_bounds__(1024) acq_compose_kernel(AcqParams p, int nsym, int per_thread, int nchunks, int start_state, float avg_first,
                                                            const float *__restrict__ lambda, const float *__restrict__ avg1,
                                                            const signed char *__restrict__ best2, const float *__restrict__ avg2,
                                                            const unsigned char *__restrict__ next, const unsigned char *__restrict__ maps,
                                                            unsigned char *__restrict__ c_of, signed char *__restrict__ best_of, AcqWalk *walk) {
-  extern __shared__ unsigned char s_buf[];  // [nchunks] start state of each chunk, 0xFF = written by thread 0; then the chunk maps
-  __shared__ int s_n_end;                   // symbols handled (all chunks before it are complete)
+  extern __shared__ unsigned char s_maps[];  // [nchunks][kNS]
+  __shared__ int s_seg_n0[kMaxSeg], s_seg_n1[kMaxSeg];
+  __shared__ unsigned char s_seg_st[kMaxSeg];
+  __shared__ int s_nseg, s_avg_from;        // s_avg_from: symbol whose table entry holds the final average, or -1
   const int t = threadIdx.x;
-  unsigned char *s_maps = s_buf + ((nchunks + 15) / 16) * 16;
   for (int i = t; i < nchunks * kNS; i += blockDim.x) s_maps[i] = maps[i];
   __syncthreads();
   if (t == 0) {
-    int n = 0, code = 0, n_found = 0, n_override = 0;
+    int n = 0, code = 0, n_found = 0, n_override = 0, nseg = 0, avg_from = -1;
     unsigned char st = (unsigned char)start_state;
     float avg = avg_first;
-    bool avg_known = true;   // `avg` holds the true average before symbol n (only maintained where needed)
-    for (int k = 0; k < nchunks; k++) s_buf[k] = 0xFE;  // not reached
     while (n < nsym && !code) {
       int k = n / per_thread;
+      int nend = min(nsym, (k + 1) * per_thread);
       if (n == k * per_thread) {
         unsigned char m = s_maps[k * kNS + st];
-        if (m < kStop) { s_buf[k] = st; st = m; n = min(nsym, n + per_thread); avg_known = false; n_found = n; continue; }
+        if (m < kStop && nseg < kMaxSeg) {   // whole chunk by its map
+          s_seg_n0[nseg] = n; s_seg_n1[nseg] = nend; s_seg_st[nseg] = st; nseg++;
+          st = m; n = nend; n_found = n; avg_from = n - 1;
+          continue;
+        }
       }
-      // symbol by symbol inside chunk k (this chunk is written here, not in the parallel re-walk)
-      s_buf[k] = 0xFF;
-      int nend = min(nsym, (k + 1) * per_thread);
-      while (n < nend && !code) {
-        int c = st / kND;
-        unsigned char nx = next[(long long)n * kNS + st];
-        signed char best = best2[(long long)n * kNS + st];
-        float a_out = avg2[(long long)n * kNS + st];
-        if (nx == kLost) { c_of[n] = (unsigned char)c; best_of[n] = -1; avg = a_out; avg_known = true; code = kLost; break; }
-        c_of[n] = (unsigned char)c;
-        best_of[n] = best;
-        avg = a_out;
-        avg_known = true;
+      if (nseg >= kMaxSeg - 2) { code = kSplit; break; }  // segment list full: end the batch here (the host loop continues)
+      // table walk inside chunk k until its end or a stop code
+      int seg0 = n;
+      unsigned char seg_st = st, nx = 0, st_at = st;
+      while (n < nend) {
+        st_at = st;
+        nx = next[(long long)n * kNS + st];
+        if (nx >= kStop) break;
+        st = nx;
+        n++;
+      }
+      if (n == nend) {  // reached the chunk end without a stop
+        s_seg_n0[nseg] = seg0; s_seg_n1[nseg] = n; s_seg_st[nseg] = seg_st; nseg++;
+        n_found = n; avg_from = n - 1;
+        continue;
+      }
+      // stop code at symbol n, reached in state st_at
+      if (nx == kLost) {
+        if (n > seg0) { s_seg_n0[nseg] = seg0; s_seg_n1[nseg] = n; s_seg_st[nseg] = seg_st; nseg++; }
+        avg = avg2[(long long)n * kNS + st_at];  // the missed symbol still updated the average
+        avg_from = -1;
+        n_found = n;
+        code = kLost;
+        break;
+      }
+      // kOff / kSplit: symbol n itself is good (table entry valid)
+      s_seg_n0[nseg] = seg0; s_seg_n1[nseg] = n + 1; s_seg_st[nseg] = seg_st; nseg++;
+      int c = st_at / kND;
+      int best = best2[(long long)n * kNS + st_at];
+      avg = avg2[(long long)n * kNS + st_at];
+      avg_from = -1;
+      n++;
+      n_found = n;
+      if (nx == kOff) { code = kOff; break; }
+      // kSplit: the tables cannot be trusted for the next symbol; run the detector from the true average
+      int cn = c + best - 8;
+      while (n < nsym && !code) {
+        if (cn < 0 || cn >= kNC) { code = kOff; break; }
+        int b2;
+        float a2 = avg;
+        int np = peak_detect(lambda + (long long)n * kCand + cn, 16, &a2, p.rise, p.fall, p.alpha, &b2);
+        n_override++;
+        c_of[n] = (unsigned char)cn;
+        avg = a2;
+        if (np <= 0) { best_of[n] = -1; code = kLost; break; }
+        best_of[n] = (signed char)b2;
         n++;
         n_found = n;
-        if (nx == kOff) { code = kOff; break; }
-        if (nx < kStop) { st = nx; continue; }
-        // kSplit: the tables cannot be trusted for the next symbol; run the detector from the true average
-        int cn = c + best - 8;
-        while (n < nsym && !code) {
-          if (cn < 0 || cn >= kNC) { code = kOff; break; }
-          int b2;
-          float a2 = avg;
-          int np = peak_detect(lambda + (long long)n * kCand + cn, 16, &a2, p.rise, p.fall, p.alpha, &b2);
-          n_override++;
-          int kk = n / per_thread;
-          if (s_buf[kk] != 0xFF) {
-            // entering a new chunk in sequential mode: it is ours now
-            s_buf[kk] = 0xFF;
-          }
-          c_of[n] = (unsigned char)cn;
-          avg = a2;
-          if (np <= 0) { best_of[n] = -1; code = kLost; break; }
-          best_of[n] = (signed char)b2;
-          n++;
-          n_found = n;
-          int c2 = cn + b2 - 8, d2 = 8 - b2;
-          if (c2 < 0 || c2 >= kNC) { code = kOff; break; }
-          bool ok = d2 >= -2 && d2 <= 2 && __float_as_uint(avg) == __float_as_uint(avg1[(long long)(n - 1) * kNC + cn]);
-          if (ok) { st = (unsigned char)(c2 * kND + d2 + 2); break; }   // tables valid again from symbol n
-          cn = c2;
-        }
-        if (n >= nsym || n == (n / per_thread) * per_thread) break;  // at a chunk boundary the maps take over again
-        nend = min(nsym, (n / per_thread + 1) * per_thread);
-        s_buf[n / per_thread] = 0xFF;
+        int c2 = cn + b2 - 8, d2 = 8 - b2;
+        if (c2 < 0 || c2 >= kNC) { code = kOff; break; }
+        bool ok = d2 >= -2 && d2 <= 2 && __float_as_uint(avg) == __float_as_uint(avg1[(long long)(n - 1) * kNC + cn]);
+        if (ok) { st = (unsigned char)(c2 * kND + d2 + 2); break; }   // tables valid again from symbol n
+        cn = c2;
       }
     }
-    if (code == kLost) n_found = n;  // the missed symbol produces no output
     walk->code = code;
     walk->n_found = n_found;
     walk->n_override = n_override;
-    // true average at the end: known if the last step was sequential, else the table entry of the last symbol
     walk->avg = avg;
-    s_n_end = avg_known ? -1 : n_found;
-    (void)avg_known;
+    s_nseg = nseg;
+    s_avg_from = avg_from;
   }
   __syncthreads();
-  // parallel re-walk of the chunks that were crossed by their map
-  if (t < nchunks && s_buf[t] < kStop) {
-    unsigned char st = s_buf[t];
-    const int n0 = t * per_thread, n1 = min(nsym, n0 + per_thread);
-    for (int n = n0; n < n1; n++) {
+  // parallel re-walk of the table segments
+  for (int i = t; i < s_nseg; i += blockDim.x) {
+    unsigned char st = s_seg_st[i];
+    for (int n = s_seg_n0[i]; n < s_seg_n1[i]; n++) {
       c_of[n] = (unsigned char)(st / kND);
       best_of[n] = best2[(long long)n * kNS + st];
-      if (n == s_n_end - 1) walk->avg = avg2[(long long)n * kNS + st];
+      if (n == s_avg_from) walk->avg = avg2[(long long)n * kNS + st];
       st = next[(long long)n * kNS + st];
     }
   }
@@ -381,79 +393,70 @@ __global__ void acq_post_kernel(AcqParams p, int c0, const float2 *__restrict__ 
   e_of[m] = (-1.0 / (double)p.N) * (double)atan2f(g.y, g.x);  // d_nextphaseinc left by symbol m (:311)
 }
 
-// phase schedule (:285-312) as a warp scan, 32 symbols per iteration, next iteration's inputs prefetched
-__global__ void __launch_bounds__(32) acq_finish_kernel(AcqParams p, long long base, const int *__restrict__ peak_of,
-                                                        const double *__restrict__ e_of, const AcqWalk *walk, AcqState *st,
-                                                        SymOut *__restrict__ out) {
-  const int lane = threadIdx.x;
+// phase schedule (:285-312): one block, every thread owns a run of consecutive symbols.  Two small
+// scans over the per-thread summaries give (a) the increment in force when a run starts ("value switched
+// to by the last earlier symbol that switched", :287-288) and (b) the phase at the start of the run.
+__global__ void __launch_bounds__(1024) acq_finish_kernel(AcqParams p, long long base, const int *__restrict__ peak_of,
+                                                          const double *__restrict__ e_of, const AcqWalk *walk, AcqState *st,
+                                                          SymOut *__restrict__ out) {
+  __shared__ double s_val[1024], s_sum[1024];
+  __shared__ unsigned char s_has[1024];
+  const int t = threadIdx.x, nt = blockDim.x;
   const int total = p.N + p.cp;
   const double twopi = 2.0 * M_PI;
   const int nf = walk->n_found;
-  double ph = st->phase, inc = st->phaseinc;
-  double pend_prev = st->nextphaseinc;   // e_{m-1} for the first symbol of the iteration
-  int nextpos_prev = st->nextpos;
-  int last_peak = st->cp_start;
-  int peak_n = lane < nf ? peak_of[lane] : 0;
-  double e_n = lane < nf ? e_of[lane] : 0.0;
-  for (int bn = 0; bn < nf; bn += 32) {
-    int m = bn + lane;
-    bool live = m < nf;
-    int peak = peak_n;
-    double e = e_n;
-    int mn = m + 32;
-    peak_n = mn < nf ? peak_of[mn] : 0;               // prefetch
-    e_n = mn < nf ? e_of[mn] : 0.0;
-    int npos = peak - total;                           // d_nextpos left by symbol m (:312)
-    // what symbol m sees: the schedule left by symbol m-1
-    double pendm = __shfl_up_sync(0xffffffffu, e, 1);
-    int swm = __shfl_up_sync(0xffffffffu, npos, 1);
-    if (lane == 0) { pendm = pend_prev; swm = nextpos_prev; }
-    bool okm = live && swm >= 0 && swm < total;
-    // increment in force when symbol m starts: switched value of the closest earlier symbol that switched
-    unsigned okbal = __ballot_sync(0xffffffffu, okm);
-    unsigned below = okbal & ((1u << lane) - 1u);
-    int src = below ? 31 - __clz(below) : 0;
-    double from_prev = __shfl_sync(0xffffffffu, pendm, src);
-    double i0 = below ? from_prev : inc;
-    double i1 = pendm;
-    double adv = live ? (okm ? swm * i0 + (total - swm) * i1 : total * i0) : 0.0;
-    double incl = adv;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      double t = __shfl_up_sync(0xffffffffu, incl, o);
-      if (lane >= o) incl += t;
-    }
-    if (live) {
-      SymOut so;
-      so.first = base + (long long)m * total + peak - p.N + 1;
-      double p0 = ph + (incl - adv);
-      so.phase0 = p0 - twopi * rint(p0 / twopi);
-      so.inc0 = i0; so.inc1 = i1; so.switch_at = okm ? swm : total;
-      out[m] = so;
-    }
-    int lastl = min(31, nf - 1 - bn);
-    double tot = __shfl_sync(0xffffffffu, incl, lastl);
-    ph += tot;
-    ph -= twopi * rint(ph / twopi);
-    double after = okm ? i1 : i0;                      // increment in force after symbol m
-    inc = __shfl_sync(0xffffffffu, after, lastl);
-    pend_prev = __shfl_sync(0xffffffffu, e, lastl);
-    nextpos_prev = __shfl_sync(0xffffffffu, npos, lastl);
-    last_peak = __shfl_sync(0xffffffffu, peak, lastl);
+  const int per = (nf + nt - 1) / nt;
+  const int a = min(nf, t * per), b = min(nf, a + per);
+  const double inc_init = st->phaseinc, pend_init = st->nextphaseinc;
+  const int nextpos_init = st->nextpos;
+  // (a) does a symbol of my run switch the increment, and to what
+  bool has = false;
+  double val = 0.0;
+  for (int m = a; m < b; m++) {
+    int swm = m == 0 ? nextpos_init : peak_of[m - 1] - total;
+    if (swm >= 0 && swm < total) { has = true; val = m == 0 ? pend_init : e_of[m - 1]; }
   }
-  if (lane == 0) {
-    int code = walk->code;
-    st->avg = walk->avg;
-    if (code == kLost) {
-      // the missed symbol still ran the detector (walk->avg includes it) and advances the phase (:335-343)
-      ph += total * inc;
-      ph -= twopi * rint(ph / twopi);
+  s_has[t] = has; s_val[t] = val;
+  __syncthreads();
+  if (t == 0) {  // exclusive "last switched value" scan
+    double cur = inc_init;
+    for (int i = 0; i < nt; i++) {
+      double mine = cur;
+      if (s_has[i]) cur = s_val[i];
+      s_val[i] = mine;
     }
+    s_val[nt - 1 + 0] = s_val[nt - 1];
+    s_sum[0] = cur;  // increment in force after the last symbol (stashed, re-read below)
+  }
+  __syncthreads();
+  const double inc_end = s_sum[0];
+  __syncthreads();
+  // (b) phase advance of my run
+  double inc = s_val[t], sum = 0.0;
+  for (int m = a; m < b; m++) {
+    int swm = m == 0 ? nextpos_init : peak_of[m - 1] - total;
+    double pendm = m == 0 ? pend_init : e_of[m - 1];
+    bool ok = swm >= 0 && swm < total;
+    sum += ok ? swm * inc + (total - swm) * pendm : total * inc;
+    if (ok) inc = pendm;
+  }
+  s_sum[t] = sum;
+  __syncthreads();
+  if (t == 0) {
+    double cur = st->phase;
+    for (int i = 0; i < nt; i++) { double mine = cur; cur += s_sum[i]; s_sum[i] = mine; }
+    s_val[nt - 1] = s_val[nt - 1];
+    // end state
+    int code = walk->code;
+    double ph = cur;
+    if (code == kLost) ph += total * inc_end;  // the missed symbol still advances the phase (:335-343)
+    ph -= twopi * rint(ph / twopi);
+    st->avg = walk->avg;
     st->phase = (float)ph;
-    st->phaseinc = inc;
-    st->nextphaseinc = pend_prev;
-    st->nextpos = nextpos_prev;
-    st->cp_start = last_peak;
+    st->phaseinc = inc_end;
+    st->nextphaseinc = nf > 0 ? e_of[nf - 1] : pend_init;
+    st->nextpos = nf > 0 ? peak_of[nf - 1] - total : nextpos_init;
+    if (nf > 0) st->cp_start = peak_of[nf - 1];
     st->n_out = nf;
     st->lost_at = code == kLost ? nf : (code ? -2 - nf : -1);   // -2-nf: stopped after nf symbols without a miss
     st->fallback = code == kSplit ? 1 : 0;
@@ -461,6 +464,22 @@ __global__ void __launch_bounds__(32) acq_finish_kernel(AcqParams p, long long b
     st->n_single += code ? 1 : 0;
     st->n_seq += walk->n_override;
     st->consumed = (long long)nf * total;
+  }
+  __syncthreads();
+  // (c) descriptors
+  inc = s_val[t];
+  double ph = s_sum[t];
+  for (int m = a; m < b; m++) {
+    int swm = m == 0 ? nextpos_init : peak_of[m - 1] - total;
+    double pendm = m == 0 ? pend_init : e_of[m - 1];
+    bool ok = swm >= 0 && swm < total;
+    SymOut so;
+    so.first = base + (long long)m * total + peak_of[m] - p.N + 1;
+    so.phase0 = ph - twopi * rint(ph / twopi);
+    so.inc0 = inc; so.inc1 = pendm; so.switch_at = ok ? swm : total;
+    out[m] = so;
+    ph += ok ? swm * inc + (total - swm) * pendm : total * inc;
+    if (ok) inc = pendm;
   }
 }
 
@@ -473,7 +492,7 @@ __global__ void __launch_bounds__(256) acq_derot_kernel(int N, int nsym, const f
   SymOut s = so[n];
   int steps = j + 1;  // the phase is incremented before it is used (:291-307)
   double ph = s.phase0 + (steps <= s.switch_at ? steps * s.inc0 : s.switch_at * s.inc0 + (steps - s.switch_at) * s.inc1);
-  ph = remainder(ph, 2.0 * M_PI);
+  ph -= (2.0 * M_PI) * rint(ph * (1.0 / (2.0 * M_PI)));
   float sn, cs;
   sincosf((float)ph, &sn, &cs);
   float2 v = cmulf(make_float2(cs, sn), x[s.first + j]);
@@ -560,14 +579,14 @@ int acq_run(dvbt_b200_acq *h, const float2 *x, long long n, float2 *d_out, long 
                                                                h->d_maps.as<unsigned char>());
       AcqWalk *d_walk = h->d_eps.as<AcqWalk>();
       DVBT_CUDA_TRY(cudaFuncSetAttribute(acq_compose_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-      acq_compose_kernel<<<1, nthreads < 32 ? 32 : nthreads, (size_t)nthreads * (kNS + 1) + 64, st>>>(
+      acq_compose_kernel<<<1, nthreads < 32 ? 32 : nthreads, (size_t)nthreads * kNS + 64, st>>>(
           p, (int)nsym, per_thread, nthreads, (kD - 8) * kND + 2, hs->avg, h->d_lambda.as<float>(), h->d_avg1.as<float>(),
           h->d_peak.as<signed char>(), h->d_avg2.as<float>(), h->d_flag.as<unsigned char>(), h->d_maps.as<unsigned char>(),
           h->d_cof.as<unsigned char>(), h->d_bof.as<signed char>(), d_walk);
       if ((rc = h->d_peakof.reserve((size_t)nsym * 4)) || (rc = h->d_eof.reserve((size_t)nsym * 8))) return rc;
       acq_post_kernel<<<(unsigned)((nsym + 127) / 128), 128, 0, st>>>(p, c0, h->d_gamma.as<float2>(), h->d_cof.as<unsigned char>(),
                                                                      h->d_bof.as<signed char>(), d_walk, h->d_peakof.as<int>(), h->d_eof.as<double>());
-      acq_finish_kernel<<<1, 32, 0, st>>>(p, pos, h->d_peakof.as<int>(), h->d_eof.as<double>(), d_walk, h->d_state.as<AcqState>(),
+      acq_finish_kernel<<<1, 1024, 0, st>>>(p, pos, h->d_peakof.as<int>(), h->d_eof.as<double>(), d_walk, h->d_state.as<AcqState>(),
                                           h->d_sym.as<SymOut>());
       count_launch(7);
       DVBT_CUDA_TRY(cudaGetLastError());
