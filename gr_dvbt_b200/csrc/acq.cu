@@ -346,7 +346,10 @@ __global__ void __launch_bounds__(1024) acq_compose_kernel(AcqParams p, int nsym
         if (cn < 0 || cn >= kNC) { code = kOff; break; }
         int b2;
         float a2 = avg;
-        int np = peak_detect(lambda + (long long)n * kCand + cn, 16, &a2, p.rise, p.fall, p.alpha, &b2);
+        float win[16];  // one round trip for the 16 values instead of 16 dependent ones
+#pragma unroll
+        for (int i = 0; i < 16; i++) win[i] = lambda[(long long)n * kCand + cn + i];
+        int np = peak_detect(win, 16, &a2, p.rise, p.fall, p.alpha, &b2);
         n_override++;
         c_of[n] = (unsigned char)cn;
         avg = a2;

@@ -10,6 +10,13 @@ pytestmark = pytest.mark.gpu
 CON = {2: 0, 4: 1, 6: 2}
 
 
+@pytest.fixture(autouse=True, params=["2", "1"], ids=["two-lane-acs", "one-lane-acs"])
+def acs_variant(request, monkeypatch):
+    """every test runs with both ACS kernels (the variant is read when a decoder is created)"""
+    monkeypatch.setenv("DVBT_B200_VIT_LANES", request.param)
+    return request.param
+
+
 def make_case(rate, m, nblocks, ber, seed):
     k, n = O.RATE_KN[rate]
     data = np.random.default_rng(seed).integers(0, 256, nblocks * 96 * k, dtype=np.uint8)
