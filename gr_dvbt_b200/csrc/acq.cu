@@ -287,44 +287,57 @@ __global__ void __launch_bounds__(1024) acq_compose_kernel(AcqParams p, int nsym
   extern __shared__ unsigned char s_maps[];  // [nchunks][kNS]
   __shared__ int s_seg_n0[kMaxSeg], s_seg_n1[kMaxSeg];
   __shared__ unsigned char s_seg_st[kMaxSeg];
+  __shared__ unsigned char s_rows[kChunk * 8 * kNS];  // `next` rows of the chunk being walked symbol by symbol
+  __shared__ float s_win[16];
   __shared__ int s_nseg, s_avg_from;        // s_avg_from: symbol whose table entry holds the final average, or -1
   const int t = threadIdx.x;
   for (int i = t; i < nchunks * kNS; i += blockDim.x) s_maps[i] = maps[i];
   __syncthreads();
-  if (t == 0) {
+  // The sequential part runs on warp 0 with warp-uniform control flow: every lane executes the same scalar
+  // logic (so any lane's copy of the state is valid), lanes cooperate only to fetch table rows / lambda
+  // windows with one coalesced round trip, and lane 0 alone writes results.
+  if (t < 32) {
+    const int lane = t;
     int n = 0, code = 0, n_found = 0, n_override = 0, nseg = 0, avg_from = -1;
     unsigned char st = (unsigned char)start_state;
     float avg = avg_first;
+    const int rows_cap = kChunk * 8;
     while (n < nsym && !code) {
       int k = n / per_thread;
       int nend = min(nsym, (k + 1) * per_thread);
       if (n == k * per_thread) {
         unsigned char m = s_maps[k * kNS + st];
         if (m < kStop && nseg < kMaxSeg) {   // whole chunk by its map
-          s_seg_n0[nseg] = n; s_seg_n1[nseg] = nend; s_seg_st[nseg] = st; nseg++;
+          if (lane == 0) { s_seg_n0[nseg] = n; s_seg_n1[nseg] = nend; s_seg_st[nseg] = st; }
+          nseg++;
           st = m; n = nend; n_found = n; avg_from = n - 1;
           continue;
         }
       }
       if (nseg >= kMaxSeg - 2) { code = kSplit; break; }  // segment list full: end the batch here (the host loop continues)
-      // table walk inside chunk k until its end or a stop code
+      // table walk inside chunk k until its end or a stop code; the rows are staged in shared memory first
+      if (nend - n > rows_cap) nend = n + rows_cap;
+      for (int i = lane; i < (nend - n) * kNS; i += 32) s_rows[i] = next[(long long)n * kNS + i];
+      __syncwarp();
       int seg0 = n;
       unsigned char seg_st = st, nx = 0, st_at = st;
       while (n < nend) {
         st_at = st;
-        nx = next[(long long)n * kNS + st];
+        nx = s_rows[(n - seg0) * kNS + st];
         if (nx >= kStop) break;
         st = nx;
         n++;
       }
-      if (n == nend) {  // reached the chunk end without a stop
-        s_seg_n0[nseg] = seg0; s_seg_n1[nseg] = n; s_seg_st[nseg] = seg_st; nseg++;
+      __syncwarp();
+      if (n == nend) {  // reached the end of the staged rows without a stop
+        if (lane == 0) { s_seg_n0[nseg] = seg0; s_seg_n1[nseg] = n; s_seg_st[nseg] = seg_st; }
+        nseg++;
         n_found = n; avg_from = n - 1;
         continue;
       }
       // stop code at symbol n, reached in state st_at
       if (nx == kLost) {
-        if (n > seg0) { s_seg_n0[nseg] = seg0; s_seg_n1[nseg] = n; s_seg_st[nseg] = seg_st; nseg++; }
+        if (n > seg0) { if (lane == 0) { s_seg_n0[nseg] = seg0; s_seg_n1[nseg] = n; s_seg_st[nseg] = seg_st; } nseg++; }
         avg = avg2[(long long)n * kNS + st_at];  // the missed symbol still updated the average
         avg_from = -1;
         n_found = n;
@@ -332,7 +345,8 @@ __global__ void __launch_bounds__(1024) acq_compose_kernel(AcqParams p, int nsym
         break;
       }
       // kOff / kSplit: symbol n itself is good (table entry valid)
-      s_seg_n0[nseg] = seg0; s_seg_n1[nseg] = n + 1; s_seg_st[nseg] = seg_st; nseg++;
+      if (lane == 0) { s_seg_n0[nseg] = seg0; s_seg_n1[nseg] = n + 1; s_seg_st[nseg] = seg_st; }
+      nseg++;
       int c = st_at / kND;
       int best = best2[(long long)n * kNS + st_at];
       avg = avg2[(long long)n * kNS + st_at];
@@ -344,17 +358,17 @@ __global__ void __launch_bounds__(1024) acq_compose_kernel(AcqParams p, int nsym
       int cn = c + best - 8;
       while (n < nsym && !code) {
         if (cn < 0 || cn >= kNC) { code = kOff; break; }
+        if (lane < 16) s_win[lane] = lambda[(long long)n * kCand + cn + lane];
+        __syncwarp();
         int b2;
         float a2 = avg;
-        float win[16];  // one round trip for the 16 values instead of 16 dependent ones
-#pragma unroll
-        for (int i = 0; i < 16; i++) win[i] = lambda[(long long)n * kCand + cn + i];
-        int np = peak_detect(win, 16, &a2, p.rise, p.fall, p.alpha, &b2);
+        int np = peak_detect(s_win, 16, &a2, p.rise, p.fall, p.alpha, &b2);
+        __syncwarp();
         n_override++;
-        c_of[n] = (unsigned char)cn;
+        if (lane == 0) c_of[n] = (unsigned char)cn;
         avg = a2;
-        if (np <= 0) { best_of[n] = -1; code = kLost; break; }
-        best_of[n] = (signed char)b2;
+        if (np <= 0) { if (lane == 0) best_of[n] = -1; code = kLost; break; }
+        if (lane == 0) best_of[n] = (signed char)b2;
         n++;
         n_found = n;
         int c2 = cn + b2 - 8, d2 = 8 - b2;
@@ -364,12 +378,14 @@ __global__ void __launch_bounds__(1024) acq_compose_kernel(AcqParams p, int nsym
         cn = c2;
       }
     }
-    walk->code = code;
-    walk->n_found = n_found;
-    walk->n_override = n_override;
-    walk->avg = avg;
-    s_nseg = nseg;
-    s_avg_from = avg_from;
+    if (lane == 0) {
+      walk->code = code;
+      walk->n_found = n_found;
+      walk->n_override = n_override;
+      walk->avg = avg;
+      s_nseg = nseg;
+      s_avg_from = avg_from;
+    }
   }
   __syncthreads();
   // parallel re-walk of the table segments
@@ -506,6 +522,7 @@ __global__ void __launch_bounds__(256) acq_derot_kernel(int N, int nsym, const f
 }  // namespace
 
 struct dvbt_b200_acq {
+  int device = dvbt::current_device();
   dvbt_b200_acq_params par;
   AcqParams kp;
   cudaStream_t stream = nullptr;
@@ -699,6 +716,7 @@ int dvbt_b200_acq_create(const dvbt_b200_acq_params *p, dvbt_b200_acq **out) {
 }
 
 void dvbt_b200_acq_destroy(dvbt_b200_acq *h) {
+  dvbt::DeviceScope dev_scope__(h ? h->device : -1);
   if (!h) return;
   if (h->stream) cudaStreamSynchronize(h->stream);
   if (h->plan) cufftDestroy(h->plan);
@@ -710,6 +728,7 @@ void dvbt_b200_acq_destroy(dvbt_b200_acq *h) {
 
 int dvbt_b200_acq_work(dvbt_b200_acq *h, const void *in, size_t n_in_items, void *out, size_t out_capacity_items, size_t *consumed,
                        size_t *produced, dvbt_b200_tag *tags_out, size_t tags_out_capacity, size_t *n_tags_out, int apply_fft) {
+  dvbt::DeviceScope dev_scope__(h ? h->device : -1);
   if (!h || !consumed || !produced) { set_error("acq_work: null argument"); return DVBT_B200_EINVAL; }
   *consumed = *produced = 0;
   if (n_tags_out) *n_tags_out = 0;

@@ -23,6 +23,25 @@ int ensure_device();  // 0 or a negative DVBT_B200_E* code (sets the error text)
     }                                                                                    \
   } while (0)
 
+// A handle lives on the device that was current when it was created (dvbt_b200_set_device).  CUDA's
+// current device is per host thread, so every entry point that takes a handle enters this scope: a
+// handle may be driven from any thread (GNU Radio runs one thread per block) on a multi-GPU host.
+struct DeviceScope {
+  int prev = -1, dev = -1;
+  explicit DeviceScope(int device) : dev(device) {
+    if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+    if (dev >= 0 && prev != dev) cudaSetDevice(dev);
+  }
+  ~DeviceScope() {
+    if (prev >= 0 && dev >= 0 && prev != dev) cudaSetDevice(prev);
+  }
+};
+inline int current_device() {
+  int d = 0;
+  if (cudaGetDevice(&d) != cudaSuccess) d = 0;
+  return d;
+}
+
 // A growable device (or pinned-host) buffer; never shrinks.
 struct DevBuf {
   void *p = nullptr;

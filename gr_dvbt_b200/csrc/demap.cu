@@ -80,6 +80,7 @@ int demap_launch(const DemapTable &t, const float2 *d_in, uint8_t *d_out, long l
 }  // namespace dvbt
 
 struct dvbt_b200_demap {
+  int device = dvbt::current_device();
   dvbt_b200_demap_params par;
   dvbt::DemapTable table;
   cudaStream_t stream = nullptr;
@@ -113,6 +114,7 @@ int dvbt_b200_demap_create(const dvbt_b200_demap_params *p, dvbt_b200_demap **ou
 }
 
 void dvbt_b200_demap_destroy(dvbt_b200_demap *h) {
+  dvbt::DeviceScope dev_scope__(h ? h->device : -1);
   if (!h) return;
   if (h->stream) { cudaStreamSynchronize(h->stream); cudaStreamDestroy(h->stream); }
   h->d_in.release();
@@ -127,6 +129,7 @@ int dvbt_b200_demap_points(const dvbt_b200_demap *h, float *re_im, int capacity_
 }
 
 int dvbt_b200_demap_run_dev(dvbt_b200_demap *h, const void *d_in, size_t ncells, uint8_t *d_out) {
+  dvbt::DeviceScope dev_scope__(h ? h->device : -1);
   if (!h || (ncells && (!d_in || !d_out))) { dvbt::set_error("demap_run_dev: bad argument"); return DVBT_B200_EINVAL; }
   int rc = dvbt::demap_launch(h->table, (const float2 *)d_in, d_out, (long long)ncells, h->stream);
   if (rc) return rc;
@@ -136,6 +139,7 @@ int dvbt_b200_demap_run_dev(dvbt_b200_demap *h, const void *d_in, size_t ncells,
 
 int dvbt_b200_demap_work(dvbt_b200_demap *h, const void *in, size_t n_in_items, uint8_t *out, size_t noutput_items,
                          size_t *consumed, size_t *produced) {
+  dvbt::DeviceScope dev_scope__(h ? h->device : -1);
   if (!h || !consumed || !produced) { dvbt::set_error("demap_work: null argument"); return DVBT_B200_EINVAL; }
   *consumed = *produced = 0;
   if (n_in_items < noutput_items) { dvbt::set_error("demap_work: %zu input items for %zu output items", n_in_items, noutput_items); return DVBT_B200_EINVAL; }

@@ -549,6 +549,7 @@ int demod_run(const ModeDev &md, const DemapTable *demap, const float2 *X, int n
 // block ABI
 // ---------------------------------------------------------------------------------------
 struct dvbt_b200_demod {
+  int device = dvbt::current_device();
   dvbt_b200_demod_params par;
   dvbt::ModeTables tables;
   cudaStream_t stream = nullptr;
@@ -597,6 +598,7 @@ int dvbt_b200_demod_create(const dvbt_b200_demod_params *p, dvbt_b200_demod **ou
 }
 
 void dvbt_b200_demod_destroy(dvbt_b200_demod *h) {
+  dvbt::DeviceScope dev_scope__(h ? h->device : -1);
   if (!h) return;
   if (h->stream) { cudaStreamSynchronize(h->stream); cudaStreamDestroy(h->stream); }
   dvbt::DevBuf *bufs[] = {&h->d_X, &h->d_Y, &h->d_Yc, &h->d_state, &h->d_fo, &h->d_rot, &h->d_mod, &h->d_tps, &h->d_vote, &h->d_osym, &h->d_osrc, &h->h_state};
@@ -608,6 +610,7 @@ void dvbt_b200_demod_destroy(dvbt_b200_demod *h) {
 int dvbt_b200_demod_work(dvbt_b200_demod *h, const void *in, size_t n_in_items, void *out, size_t out_capacity_items,
                          size_t *consumed, size_t *produced, const dvbt_b200_tag *tags_in, size_t n_tags_in,
                          dvbt_b200_tag *tags_out, size_t tags_out_capacity, size_t *n_tags_out) {
+  dvbt::DeviceScope dev_scope__(h ? h->device : -1);
   if (!h || !consumed || !produced) { dvbt::set_error("demod_work: null argument"); return DVBT_B200_EINVAL; }
   *consumed = *produced = 0;
   if (n_tags_out) *n_tags_out = 0;

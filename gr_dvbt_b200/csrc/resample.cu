@@ -108,43 +108,56 @@ __global__ void __launch_bounds__(256) resample_kernel(const float2 *__restrict_
   }
 }
 
-// Fast path for the 36-taps-per-arm prototype: the phase of output m is (35 m) mod 32 = (3 m) mod 32, so a
-// thread that steps m by a multiple of 32 always uses the same arm: its 36 taps live in registers and
-// each output costs 36 8-byte loads (L1-resident, neighbouring lanes read neighbouring samples) and 72 FMAs.
-constexpr int kRegArm = 36, kRegOuts = 8;
+// Fast path for the 36-taps-per-arm prototype.  The phase of output m is (35 m) mod 32, so a thread that
+// steps m by a multiple of 32 always uses the same arms: it owns the output pair (2u, 2u+1), keeps both
+// arms' 36 taps in registers, and loads the 38 input samples the two overlapping windows span once
+// (the windows start 1 or 2 samples apart, fixed per thread): 19 8-byte loads and 72 FMAs per output.
+constexpr int kRegArm = 36, kRegPairs = 4;
+
+template <int DELTA>
+__device__ __forceinline__ void resample_pair_loop(const float2 *__restrict__ x, long long nin, float2 *__restrict__ y, long long nout,
+                                                   const float *__restrict__ taps_arm, float scale, long long u) {
+  float h0[kRegArm], h1[kRegArm];
+  {
+    int p0 = (int)(((2 * u) * kDecim) % kInterp), p1 = (int)(((2 * u + 1) * kDecim) % kInterp);
+#pragma unroll
+    for (int j = 0; j < kRegArm; j++) { h0[j] = taps_arm[p0 * kRegArm + j]; h1[j] = taps_arm[p1 * kRegArm + j]; }
+  }
+#pragma unroll 1
+  for (int r = 0; r < kRegPairs; r++, u += 256) {
+    long long m0 = 2 * u, m1 = m0 + 1;
+    if (m0 >= nout) return;
+    long long a1 = (m1 * kDecim) / kInterp;   // newest input of the second output; the first one's is a1 - DELTA
+    float2 xs[kRegArm + DELTA];
+    if (a1 >= kRegArm + DELTA - 1 && a1 < nin) {
+#pragma unroll
+      for (int k = 0; k < kRegArm + DELTA; k++) xs[k] = __ldg(x + a1 - k);
+    } else {
+#pragma unroll
+      for (int k = 0; k < kRegArm + DELTA; k++) {
+        long long idx = a1 - k;
+        xs[k] = (idx >= 0 && idx < nin) ? x[idx] : make_float2(0.f, 0.f);
+      }
+    }
+    float r0 = 0.f, i0 = 0.f, r1 = 0.f, i1 = 0.f;
+#pragma unroll
+    for (int j = 0; j < kRegArm; j++) {
+      r0 = fmaf(h0[j], xs[j + DELTA].x, r0);
+      i0 = fmaf(h0[j], xs[j + DELTA].y, i0);
+      r1 = fmaf(h1[j], xs[j].x, r1);
+      i1 = fmaf(h1[j], xs[j].y, i1);
+    }
+    y[m0] = make_float2(r0 * scale, i0 * scale);
+    if (m1 < nout) y[m1] = make_float2(r1 * scale, i1 * scale);
+  }
+}
 
 __global__ void __launch_bounds__(256) resample_reg_kernel(const float2 *__restrict__ x, long long nin, float2 *__restrict__ y, long long nout,
                                                            const float *__restrict__ taps_arm, float scale) {
-  long long m = (long long)blockIdx.x * (256 * kRegOuts) + threadIdx.x;
-  int phase = (int)((m * kDecim) % kInterp);
-  float h[kRegArm];
-#pragma unroll
-  for (int j = 0; j < kRegArm; j++) h[j] = taps_arm[phase * kRegArm + j];
-#pragma unroll 1
-  for (int r = 0; r < kRegOuts; r++, m += 256) {
-    if (m >= nout) return;
-    long long a = (m * kDecim) / kInterp;
-    float accr = 0.f, acci = 0.f;
-    if (a >= kRegArm - 1 && a < nin) {
-      const float2 *xs = x + a;
-#pragma unroll
-      for (int j = 0; j < kRegArm; j++) {
-        float2 v = __ldg(xs - j);
-        accr = fmaf(h[j], v.x, accr);
-        acci = fmaf(h[j], v.y, acci);
-      }
-    } else {
-      for (int j = 0; j < kRegArm; j++) {
-        long long idx = a - j;
-        if (idx >= 0 && idx < nin) {
-          float2 v = x[idx];
-          accr = fmaf(h[j], v.x, accr);
-          acci = fmaf(h[j], v.y, acci);
-        }
-      }
-    }
-    y[m] = make_float2(accr * scale, acci * scale);
-  }
+  long long u = (long long)blockIdx.x * (256 * kRegPairs) + threadIdx.x;
+  long long a0 = ((2 * u) * kDecim) / kInterp, a1 = ((2 * u + 1) * kDecim) / kInterp;
+  if (a1 - a0 == 1) resample_pair_loop<1>(x, nin, y, nout, taps_arm, scale, u);
+  else resample_pair_loop<2>(x, nin, y, nout, taps_arm, scale, u);
 }
 
 struct Resampler {
@@ -179,7 +192,7 @@ int resample_launch(const float2 *d_x, long long nin, float2 *d_y, long long nou
   Resampler *r = g_res[dev];
   if (nout <= 0) return 0;
   if (r->per_arm == kRegArm) {
-    long long per_block = 256 * kRegOuts;
+    long long per_block = 2LL * 256 * kRegPairs;
     resample_reg_kernel<<<(unsigned)((nout + per_block - 1) / per_block), 256, 0, st>>>(d_x, nin, d_y, nout, r->d_taps.as<float>(), scale);
     count_launch();
     DVBT_CUDA_TRY(cudaGetLastError());

@@ -211,6 +211,7 @@ __global__ void __launch_bounds__(256) rs_decode_kernel(const uint8_t *__restric
 }  // namespace
 
 struct dvbt_b200_rsdec {
+  int device = dvbt::current_device();
   dvbt_b200_rsdec_params par;
   int as_built = 0;
   cudaStream_t stream = nullptr;
@@ -285,6 +286,7 @@ int dvbt_b200_rsdec_create(const dvbt_b200_rsdec_params *p, dvbt_b200_rsdec **ou
 }
 
 void dvbt_b200_rsdec_destroy(dvbt_b200_rsdec *h) {
+  dvbt::DeviceScope dev_scope__(h ? h->device : -1);
   if (!h) return;
   if (h->stream) { cudaStreamSynchronize(h->stream); cudaStreamDestroy(h->stream); }
   h->d_in.release();
@@ -299,6 +301,7 @@ int dvbt_b200_rsdec_set_compat(dvbt_b200_rsdec *h, int as_built) {
 }
 
 int dvbt_b200_rsdec_decode_dev(dvbt_b200_rsdec *h, const uint8_t *d_in, size_t npackets, uint8_t *d_out, int *d_status) {
+  dvbt::DeviceScope dev_scope__(h ? h->device : -1);
   if (!h || (npackets && (!d_in || !d_out))) { dvbt::set_error("rsdec_decode_dev: bad argument"); return DVBT_B200_EINVAL; }
   int rc = dvbt::rs_launch(d_in, d_out, d_status, (long long)npackets, h->as_built, h->sm_count, h->stream, -1);
   if (rc) return rc;
@@ -308,6 +311,7 @@ int dvbt_b200_rsdec_decode_dev(dvbt_b200_rsdec *h, const uint8_t *d_in, size_t n
 
 int dvbt_b200_rsdec_work(dvbt_b200_rsdec *h, const uint8_t *in, size_t n_in_items, uint8_t *out, size_t noutput_items,
                          size_t *consumed, size_t *produced) {
+  dvbt::DeviceScope dev_scope__(h ? h->device : -1);
   if (!h || !consumed || !produced) { dvbt::set_error("rsdec_work: null argument"); return DVBT_B200_EINVAL; }
   *consumed = *produced = 0;
   if (n_in_items < noutput_items) {  // forecast: 1:1 (reed_solomon_dec_impl.cc:71-75)

@@ -168,6 +168,7 @@ __global__ void __launch_bounds__(256) rx_descramble_kernel(const uint8_t *__res
 }  // namespace
 
 struct dvbt_b200_rx {
+  int device = dvbt::current_device();
   dvbt_b200_rx_params par;
   dvbt::ModeTables tables;
   dvbt::DemapTable demap;
@@ -250,6 +251,7 @@ int dvbt_b200_rx_create(const dvbt_b200_rx_params *p, dvbt_b200_rx **out) {
 }
 
 void dvbt_b200_rx_destroy(dvbt_b200_rx *h) {
+  dvbt::DeviceScope dev_scope__(h ? h->device : -1);
   if (!h) return;
   if (h->stream) cudaStreamSynchronize(h->stream);
   dvbt::DevBuf *bufs[] = {&h->d_X, &h->d_state, &h->d_fo, &h->d_rot, &h->d_mod, &h->d_tps, &h->d_vote, &h->d_osym, &h->d_osrc, &h->d_dm,
@@ -377,6 +379,7 @@ static int rx_run_freq(dvbt_b200_rx *h, const float2 *dX, size_t nsym, uint8_t *
 }
 
 int dvbt_b200_rx_run_freq_host(dvbt_b200_rx *h, const void *X, size_t nsym, uint8_t *ts, size_t ts_capacity, size_t *ts_bytes) {
+  dvbt::DeviceScope dev_scope__(h ? h->device : -1);
   if (!h || (nsym && !X) || !ts) { set_error("rx_run_freq_host: bad argument"); return DVBT_B200_EINVAL; }
   const dvbt::ModeDev &md = h->tables.dev;
   int rc = h->d_X.reserve(nsym * md.N * 8);
@@ -386,6 +389,7 @@ int dvbt_b200_rx_run_freq_host(dvbt_b200_rx *h, const void *X, size_t nsym, uint
 }
 
 int dvbt_b200_rx_run_freq_dev(dvbt_b200_rx *h, const void *dX, size_t nsym, uint8_t *d_ts, size_t ts_capacity, size_t *ts_bytes) {
+  dvbt::DeviceScope dev_scope__(h ? h->device : -1);
   if (!h || (nsym && !dX) || !d_ts) { set_error("rx_run_freq_dev: bad argument"); return DVBT_B200_EINVAL; }
   return rx_run_freq(h, (const float2 *)dX, nsym, nullptr, d_ts, ts_capacity, ts_bytes, 0);
 }
@@ -416,6 +420,7 @@ static int rx_run_baseband(dvbt_b200_rx *h, const float2 *d_x, size_t nsamples, 
 }
 
 int dvbt_b200_rx_run_baseband_host(dvbt_b200_rx *h, const void *samples, size_t nsamples, uint8_t *ts, size_t ts_capacity, size_t *ts_bytes) {
+  dvbt::DeviceScope dev_scope__(h ? h->device : -1);
   if (!h || (nsamples && !samples) || !ts) { set_error("rx_run_baseband_host: bad argument"); return DVBT_B200_EINVAL; }
   int rc = h->d_samples.reserve(nsamples * 8);
   if (rc) return rc;
@@ -424,6 +429,7 @@ int dvbt_b200_rx_run_baseband_host(dvbt_b200_rx *h, const void *samples, size_t 
 }
 
 int dvbt_b200_rx_run_baseband_dev(dvbt_b200_rx *h, const void *d_samples, size_t nsamples, uint8_t *d_ts, size_t ts_capacity, size_t *ts_bytes) {
+  dvbt::DeviceScope dev_scope__(h ? h->device : -1);
   if (!h || (nsamples && !d_samples) || !d_ts) { set_error("rx_run_baseband_dev: bad argument"); return DVBT_B200_EINVAL; }
   return rx_run_baseband(h, (const float2 *)d_samples, nsamples, nullptr, d_ts, ts_capacity, ts_bytes, 0);
 }
@@ -449,6 +455,7 @@ static int rx_run_file(dvbt_b200_rx *h, const float2 *d_file, size_t nfile, floa
 
 int dvbt_b200_rx_run_file_host(dvbt_b200_rx *h, const void *samples, size_t nsamples, float gain, uint8_t *ts, size_t ts_capacity,
                                size_t *ts_bytes) {
+  dvbt::DeviceScope dev_scope__(h ? h->device : -1);
   if (!h || (nsamples && !samples) || !ts) { set_error("rx_run_file_host: bad argument"); return DVBT_B200_EINVAL; }
   int rc = h->d_file.reserve(nsamples * 8);
   if (rc) return rc;
@@ -458,6 +465,7 @@ int dvbt_b200_rx_run_file_host(dvbt_b200_rx *h, const void *samples, size_t nsam
 
 int dvbt_b200_rx_run_file_dev(dvbt_b200_rx *h, const void *d_samples, size_t nsamples, float gain, uint8_t *d_ts, size_t ts_capacity,
                               size_t *ts_bytes) {
+  dvbt::DeviceScope dev_scope__(h ? h->device : -1);
   if (!h || (nsamples && !d_samples) || !d_ts) { set_error("rx_run_file_dev: bad argument"); return DVBT_B200_EINVAL; }
   return rx_run_file(h, (const float2 *)d_samples, nsamples, gain, nullptr, d_ts, ts_capacity, ts_bytes, 0);
 }
@@ -470,6 +478,7 @@ int dvbt_b200_rx_last_info(const dvbt_b200_rx *h, dvbt_b200_rx_info *info) {
 
 // stage taps of the last run, for stage-by-stage parity tests
 int dvbt_b200_rx_read_stage(dvbt_b200_rx *h, int stage, void *host_out, size_t capacity_bytes, size_t *nbytes) {
+  dvbt::DeviceScope dev_scope__(h ? h->device : -1);
   if (!h || !host_out || !nbytes) { set_error("rx_read_stage: null argument"); return DVBT_B200_EINVAL; }
   const dvbt::ModeDev &md = h->tables.dev;
   *nbytes = 0;

@@ -52,7 +52,9 @@ typedef struct dvbt_b200_tag {
 const char *dvbt_b200_last_error(void);
 /* number of CUDA devices visible (0 if none / no driver); selects nothing */
 int dvbt_b200_device_count(void);
-/* bind the calling thread (and handles created afterwards) to a device */
+/* bind the calling thread to a device.  A handle belongs to the device that was current in the thread
+ * that created it; every later call on the handle switches to that device for its duration, so a handle
+ * may be driven from any host thread (one call at a time per handle). */
 int dvbt_b200_set_device(int device);
 /* how many kernels of this library have been launched by this process (bench evidence) */
 unsigned long long dvbt_b200_kernel_launches(void);

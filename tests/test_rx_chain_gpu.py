@@ -26,6 +26,8 @@ CASES = [
     (R.QAM64, R.C7_8, R.T2k, 330, 1328),
     (R.QPSK, R.C2_3, R.T2k, 480, None),
     (R.QAM64, R.C3_4, R.T8k, 300, None),
+    (R.QAM64, R.C7_8, R.T8k, 290, None),
+    (R.QAM16, R.C5_6, R.T8k, 290, None),
 ]
 
 

@@ -140,3 +140,29 @@ def test_large_stream_round_trip_and_chunk_invariance():
     assert np.array_equal(a, b)
     ref = O.Viterbi(m, rate).work(noisy[: 40 * 768 * n // m])
     assert np.array_equal(a[: len(ref)], ref)
+
+
+def test_handle_follows_its_device_across_host_threads():
+    """CUDA's current device is per thread; a handle created on the last visible device must work when
+    driven from a fresh thread (whose current device is 0) - the per-block-thread model of GNU Radio."""
+    import threading
+    import gr_dvbt_b200 as g
+    from gr_dvbt_b200 import capi
+    lib = capi.lib()
+    ndev = lib.dvbt_b200_device_count()
+    data, rx = make_case(4, 6, 12, 0.005, 3)
+    ref = O.Viterbi(6, 4).work(rx)
+    capi.check(lib.dvbt_b200_set_device(ndev - 1))
+    try:
+        dec = g.viterbi_decoder(CON[6], g.NH, 4)
+    finally:
+        capi.check(lib.dvbt_b200_set_device(0))
+    got = {}
+
+    def worker():
+        got["out"] = dec.decode(rx)[0]
+
+    t = threading.Thread(target=worker)
+    t.start()
+    t.join()
+    assert np.array_equal(got["out"], ref)
