@@ -51,8 +51,8 @@ class viterbi_decoder:
 
     __del__ = close
 
-    def set_tuning(self, chunk_bytes=0, warmup_bytes=0, threads_per_block=0):
-        t = capi.ViterbiTuning(chunk_bytes, warmup_bytes, threads_per_block)
+    def set_tuning(self, chunk_bytes=0, warmup_bytes=0, threads_per_block=0, ring_depth=0):
+        t = capi.ViterbiTuning(chunk_bytes, warmup_bytes, threads_per_block, ring_depth)
         check(lib().dvbt_b200_viterbi_set_tuning(self._h, C.byref(t)))
 
     def reset(self):

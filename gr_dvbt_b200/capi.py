@@ -54,7 +54,7 @@ class AcqParams(C.Structure):
 
 
 class ViterbiTuning(C.Structure):
-    _fields_ = [("chunk_bytes", C.c_int), ("warmup_bytes", C.c_int), ("threads_per_block", C.c_int)]
+    _fields_ = [("chunk_bytes", C.c_int), ("warmup_bytes", C.c_int), ("threads_per_block", C.c_int), ("ring_depth", C.c_int)]
 
 
 _lib = None

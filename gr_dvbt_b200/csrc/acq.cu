@@ -31,6 +31,7 @@
 
 #include <cufft.h>
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 #include <new>
 
@@ -253,6 +254,9 @@ struct AcqWalk {
   int code;           // 0: all symbols processed, else kLost / kOff / kSplit
   float avg;          // true detector average after the last processed symbol (incl. a missed one)
   int n_override;     // symbols whose speculation did not hold and that were re-run sequentially
+  int avg_from;       // symbol whose table entry holds the final average (acq_walk_kernel fetches it), or -1
+  int n_seg, n_staged;            // table segments; chunks walked symbol by symbol (trace)
+  long long cyc_maps, cyc_serial;  // trace: clock64 deltas of the three phases (DVBT_B200_ACQ_TRACE)
 };
 
 // chunk maps: one warp per chunk of `per_thread` symbols, lane = start state (85 states, 3 rounds)
@@ -272,131 +276,182 @@ __global__ void __launch_bounds__(128) acq_chunkmap_kernel(int nsym, int per_thr
   }
 }
 
-// Chains the chunk maps (thread 0) into a list of table segments (first symbol, end, start state); every
-// thread then re-walks one segment and writes (offset c, best) per symbol.  Where the speculation stops
-// (kSplit) thread 0 continues on the spot: it runs the reference detector sequentially on the next symbol
-// from the true average, and keeps doing so until a symbol's result re-validates the tables; those few
-// symbols are written by thread 0 itself.  Thread 0 touches one table byte per symbol at most.
+// Chains the chunk maps into a list of table segments (first symbol, end, start state) that
+// acq_walk_kernel then re-walks in parallel, writing (offset c, best) per symbol.  Where the speculation
+// stops (kSplit) the chain continues on the spot: the reference detector runs sequentially on the next
+// symbol from the true average, and keeps doing so until a symbol's result re-validates the tables; those
+// few symbols are written here.
+//
+// The chain is sequential, so it runs on warp 0 with warp-uniform control flow: every lane executes the
+// same scalar logic, the lanes cooperate only to fetch table rows / lambda windows with one coalesced
+// round trip (16-byte loads), and lane 0 alone writes results.
 constexpr int kMaxSeg = 2048;
+constexpr int kRowsCap = kChunk * 8;
 
-__global__ void __launch_bounds__(1024) acq_compose_kernel(AcqParams p, int nsym, int per_thread, int nchunks, int start_state, float avg_first,
-                                                           const float *__restrict__ lambda, const float *__restrict__ avg1,
-                                                           const signed char *__restrict__ best2, const float *__restrict__ avg2,
-                                                           const unsigned char *__restrict__ next, const unsigned char *__restrict__ maps,
-                                                           unsigned char *__restrict__ c_of, signed char *__restrict__ best_of, AcqWalk *walk) {
-  extern __shared__ unsigned char s_maps[];  // [nchunks][kNS]
-  __shared__ int s_seg_n0[kMaxSeg], s_seg_n1[kMaxSeg];
-  __shared__ unsigned char s_seg_st[kMaxSeg];
-  __shared__ unsigned char s_rows[kChunk * 8 * kNS];  // `next` rows of the chunk being walked symbol by symbol
+// 16-byte-granular copy of `bytes` bytes starting at byte offset `off` of `src` into shared memory;
+// returns the shift to add to indices into `dst` (the copy starts at the aligned address below `off`).
+// The DevBuf allocations are 256-byte aligned and carry >= 256 bytes of slack, so reading up to 15 bytes
+// either side of the range stays inside the allocation.
+__device__ __forceinline__ int stage_bytes16(const unsigned char *__restrict__ src, long long off, int bytes, unsigned char *dst, int lane,
+                                             int nlanes) {
+  long long a0 = off & ~15LL;
+  int shift = (int)(off - a0);
+  int n16 = (shift + bytes + 15) >> 4;
+  const uint4 *s4 = reinterpret_cast<const uint4 *>(src + a0);
+  uint4 *d4 = reinterpret_cast<uint4 *>(dst);
+  for (int i = lane; i < n16; i += nlanes) d4[i] = s4[i];
+  return shift;
+}
+
+__global__ void __launch_bounds__(256) acq_compose_kernel(AcqParams p, int nsym, int per_thread, int nchunks, int start_state, float avg_first,
+                                                          const float *__restrict__ lambda, const float *__restrict__ avg1,
+                                                          const signed char *__restrict__ best2, const float *__restrict__ avg2,
+                                                          const unsigned char *__restrict__ next, const unsigned char *__restrict__ maps,
+                                                          unsigned char *__restrict__ c_of, signed char *__restrict__ best_of, int4 *__restrict__ segs,
+                                                          AcqWalk *walk) {
+  extern __shared__ __align__(16) unsigned char s_maps[];  // [nchunks][kNS] (+ slack)
+  __shared__ __align__(16) unsigned char s_rows[kRowsCap * kNS + 32];  // `next` rows of the chunk being walked symbol by symbol
   __shared__ float s_win[16];
-  __shared__ int s_nseg, s_avg_from;        // s_avg_from: symbol whose table entry holds the final average, or -1
   const int t = threadIdx.x;
-  for (int i = t; i < nchunks * kNS; i += blockDim.x) s_maps[i] = maps[i];
+  const long long cyc0 = clock64();
+  stage_bytes16(maps, 0, nchunks * kNS, s_maps, t, blockDim.x);
   __syncthreads();
-  // The sequential part runs on warp 0 with warp-uniform control flow: every lane executes the same scalar
-  // logic (so any lane's copy of the state is valid), lanes cooperate only to fetch table rows / lambda
-  // windows with one coalesced round trip, and lane 0 alone writes results.
-  if (t < 32) {
-    const int lane = t;
-    int n = 0, code = 0, n_found = 0, n_override = 0, nseg = 0, avg_from = -1;
-    unsigned char st = (unsigned char)start_state;
-    float avg = avg_first;
-    const int rows_cap = kChunk * 8;
-    while (n < nsym && !code) {
-      int k = n / per_thread;
-      int nend = min(nsym, (k + 1) * per_thread);
-      if (n == k * per_thread) {
-        unsigned char m = s_maps[k * kNS + st];
-        if (m < kStop && nseg < kMaxSeg) {   // whole chunk by its map
-          if (lane == 0) { s_seg_n0[nseg] = n; s_seg_n1[nseg] = nend; s_seg_st[nseg] = st; }
-          nseg++;
-          st = m; n = nend; n_found = n; avg_from = n - 1;
-          continue;
-        }
-      }
-      if (nseg >= kMaxSeg - 2) { code = kSplit; break; }  // segment list full: end the batch here (the host loop continues)
-      // table walk inside chunk k until its end or a stop code; the rows are staged in shared memory first
-      if (nend - n > rows_cap) nend = n + rows_cap;
-      for (int i = lane; i < (nend - n) * kNS; i += 32) s_rows[i] = next[(long long)n * kNS + i];
-      __syncwarp();
-      int seg0 = n;
-      unsigned char seg_st = st, nx = 0, st_at = st;
-      while (n < nend) {
-        st_at = st;
-        nx = s_rows[(n - seg0) * kNS + st];
-        if (nx >= kStop) break;
-        st = nx;
-        n++;
-      }
-      __syncwarp();
-      if (n == nend) {  // reached the end of the staged rows without a stop
-        if (lane == 0) { s_seg_n0[nseg] = seg0; s_seg_n1[nseg] = n; s_seg_st[nseg] = seg_st; }
+  const long long cyc1 = clock64();
+  if (t >= 32) return;
+  const int lane = t;
+  int n = 0, code = 0, n_found = 0, n_override = 0, nseg = 0, avg_from = -1, n_staged = 0;
+  int st_n0 = 0, st_n1 = 0, st_shift = 0;   // symbols whose rows are in s_rows
+  unsigned char st = (unsigned char)start_state;
+  float avg = avg_first;
+  int k = 0, kstart = 0;                    // chunk of symbol n and its first symbol
+  while (n < nsym && !code) {
+    int nend = min(nsym, kstart + per_thread);
+    if (n == kstart) {
+      unsigned char m = s_maps[k * kNS + st];
+      if (m < kStop && nseg < kMaxSeg) {   // whole chunk by its map
+        if (lane == 0) segs[nseg] = make_int4(n, nend, st, 0);
         nseg++;
-        n_found = n; avg_from = n - 1;
+        st = m; n = nend; n_found = n; avg_from = n - 1;
+        k++; kstart += per_thread;
         continue;
       }
-      // stop code at symbol n, reached in state st_at
-      if (nx == kLost) {
-        if (n > seg0) { if (lane == 0) { s_seg_n0[nseg] = seg0; s_seg_n1[nseg] = n; s_seg_st[nseg] = seg_st; } nseg++; }
-        avg = avg2[(long long)n * kNS + st_at];  // the missed symbol still updated the average
-        avg_from = -1;
-        n_found = n;
-        code = kLost;
-        break;
-      }
-      // kOff / kSplit: symbol n itself is good (table entry valid)
-      if (lane == 0) { s_seg_n0[nseg] = seg0; s_seg_n1[nseg] = n + 1; s_seg_st[nseg] = seg_st; }
+    }
+    if (nseg >= kMaxSeg - 2) { code = kSplit; break; }  // segment list full: end the batch here (the host loop continues)
+    // table walk inside chunk k until its end or a stop code; the rows are staged in shared memory first
+    if (nend - n > kRowsCap) nend = n + kRowsCap;
+    if (n < st_n0 || nend > st_n1) {
+      __syncwarp();
+      st_shift = stage_bytes16(next, (long long)n * kNS, (nend - n) * kNS, s_rows, lane, 32);
+      st_n0 = n; st_n1 = nend;
+      n_staged++;
+      __syncwarp();
+    }
+    const unsigned char *rows = s_rows + st_shift - st_n0 * kNS;   // rows[n * kNS + state]
+    int seg0 = n;
+    unsigned char seg_st = st, nx = 0, st_at = st;
+    while (n < nend) {
+      st_at = st;
+      nx = rows[n * kNS + st];
+      if (nx >= kStop) break;
+      st = nx;
+      n++;
+    }
+    if (n == nend) {  // reached the end of the staged rows without a stop
+      if (lane == 0) segs[nseg] = make_int4(seg0, n, seg_st, 0);
       nseg++;
-      int c = st_at / kND;
-      int best = best2[(long long)n * kNS + st_at];
-      avg = avg2[(long long)n * kNS + st_at];
+      n_found = n; avg_from = n - 1;
+      if (n == kstart + per_thread) { k++; kstart += per_thread; }
+      continue;
+    }
+    // stop code at symbol n, reached in state st_at
+    if (nx == kLost) {
+      if (n > seg0) { if (lane == 0) segs[nseg] = make_int4(seg0, n, seg_st, 0); nseg++; }
+      avg = avg2[(long long)n * kNS + st_at];  // the missed symbol still updated the average
       avg_from = -1;
+      n_found = n;
+      code = kLost;
+      break;
+    }
+    // kOff / kSplit: symbol n itself is good (table entry valid)
+    if (lane == 0) segs[nseg] = make_int4(seg0, n + 1, seg_st, 0);
+    nseg++;
+    int c = st_at / kND;
+    int best = best2[(long long)n * kNS + st_at];
+    avg = avg2[(long long)n * kNS + st_at];
+    avg_from = -1;
+    n++;
+    n_found = n;
+    if (nx == kOff) { code = kOff; break; }
+    // kSplit: the tables cannot be trusted for the next symbol; run the detector from the true average
+    int cn = c + best - 8;
+    while (n < nsym && !code) {
+      if (cn < 0 || cn >= kNC) { code = kOff; break; }
+      __syncwarp();
+      if (lane < 16) s_win[lane] = lambda[(long long)n * kCand + cn + lane];
+      __syncwarp();
+      int b2;
+      float a2 = avg;
+      int np = peak_detect(s_win, 16, &a2, p.rise, p.fall, p.alpha, &b2);
+      n_override++;
+      if (lane == 0) c_of[n] = (unsigned char)cn;
+      avg = a2;
+      if (np <= 0) { if (lane == 0) best_of[n] = -1; code = kLost; break; }
+      if (lane == 0) best_of[n] = (signed char)b2;
       n++;
       n_found = n;
-      if (nx == kOff) { code = kOff; break; }
-      // kSplit: the tables cannot be trusted for the next symbol; run the detector from the true average
-      int cn = c + best - 8;
-      while (n < nsym && !code) {
-        if (cn < 0 || cn >= kNC) { code = kOff; break; }
-        if (lane < 16) s_win[lane] = lambda[(long long)n * kCand + cn + lane];
-        __syncwarp();
-        int b2;
-        float a2 = avg;
-        int np = peak_detect(s_win, 16, &a2, p.rise, p.fall, p.alpha, &b2);
-        __syncwarp();
-        n_override++;
-        if (lane == 0) c_of[n] = (unsigned char)cn;
-        avg = a2;
-        if (np <= 0) { if (lane == 0) best_of[n] = -1; code = kLost; break; }
-        if (lane == 0) best_of[n] = (signed char)b2;
-        n++;
-        n_found = n;
-        int c2 = cn + b2 - 8, d2 = 8 - b2;
-        if (c2 < 0 || c2 >= kNC) { code = kOff; break; }
-        bool ok = d2 >= -2 && d2 <= 2 && __float_as_uint(avg) == __float_as_uint(avg1[(long long)(n - 1) * kNC + cn]);
-        if (ok) { st = (unsigned char)(c2 * kND + d2 + 2); break; }   // tables valid again from symbol n
-        cn = c2;
-      }
+      int c2 = cn + b2 - 8, d2 = 8 - b2;
+      if (c2 < 0 || c2 >= kNC) { code = kOff; break; }
+      bool ok = d2 >= -2 && d2 <= 2 && __float_as_uint(avg) == __float_as_uint(avg1[(long long)(n - 1) * kNC + cn]);
+      if (ok) { st = (unsigned char)(c2 * kND + d2 + 2); break; }   // tables valid again from symbol n
+      cn = c2;
     }
-    if (lane == 0) {
-      walk->code = code;
-      walk->n_found = n_found;
-      walk->n_override = n_override;
-      walk->avg = avg;
-      s_nseg = nseg;
-      s_avg_from = avg_from;
+    k = n / per_thread;
+    kstart = k * per_thread;
+  }
+  if (lane == 0) {
+    walk->code = code;
+    walk->n_found = n_found;
+    walk->n_override = n_override;
+    walk->avg = avg;
+    walk->avg_from = avg_from;
+    walk->n_seg = nseg;
+    walk->n_staged = n_staged;
+    walk->cyc_maps = cyc1 - cyc0;
+    walk->cyc_serial = clock64() - cyc1;
+  }
+}
+
+// One warp per table segment: the segment's `next` rows are staged with one coalesced round trip, lane 0
+// walks the states through shared memory, then lane i writes (offset, best) of the segment's i-th symbol.
+__global__ void __launch_bounds__(128) acq_walk_kernel(int rows_cap, const signed char *__restrict__ best2, const float *__restrict__ avg2,
+                                                       const unsigned char *__restrict__ next, const int4 *__restrict__ segs,
+                                                       unsigned char *__restrict__ c_of, signed char *__restrict__ best_of, AcqWalk *walk) {
+  extern __shared__ __align__(16) unsigned char s_walk[];
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int seg = blockIdx.x * (blockDim.x >> 5) + w;
+  if (seg >= walk->n_seg) return;
+  const int per_warp = rows_cap * kNS + 32 + rows_cap;          // rows (16-byte granular) + one state per symbol
+  unsigned char *rows = s_walk + (size_t)w * ((per_warp + 15) & ~15);
+  unsigned char *states = rows + rows_cap * kNS + 32;
+  const int4 sg = segs[seg];
+  const int n0 = sg.x, cnt = sg.y - sg.x;
+  int shift = stage_bytes16(next, (long long)n0 * kNS, cnt * kNS, rows, lane, 32);
+  __syncwarp();
+  if (lane == 0) {
+    unsigned char st = (unsigned char)sg.z;
+    for (int i = 0; i < cnt; i++) {
+      states[i] = st;
+      st = rows[shift + i * kNS + st];
     }
   }
-  __syncthreads();
-  // parallel re-walk of the table segments
-  for (int i = t; i < s_nseg; i += blockDim.x) {
-    unsigned char st = s_seg_st[i];
-    for (int n = s_seg_n0[i]; n < s_seg_n1[i]; n++) {
-      c_of[n] = (unsigned char)(st / kND);
-      best_of[n] = best2[(long long)n * kNS + st];
-      if (n == s_avg_from) walk->avg = avg2[(long long)n * kNS + st];
-      st = next[(long long)n * kNS + st];
-    }
+  __syncwarp();
+  const int avg_from = walk->avg_from;
+  for (int i = lane; i < cnt; i += 32) {
+    int n = n0 + i;
+    unsigned char st = states[i];
+    c_of[n] = (unsigned char)(st / kND);
+    best_of[n] = best2[(long long)n * kNS + st];
+    if (n == avg_from) walk->avg = avg2[(long long)n * kNS + st];
   }
 }
 
@@ -529,7 +584,7 @@ struct dvbt_b200_acq {
   bool own_stream = true;
   cufftHandle plan = 0;
   int plan_batch = 0;
-  dvbt::DevBuf d_x, d_state, h_state, d_lambda, d_gamma, d_avg1, d_avg2, d_peak, d_sym, d_out, d_il, d_ig, d_eps, d_flag, d_maps, d_cof, d_bof, d_peakof, d_eof;
+  dvbt::DevBuf d_x, d_state, h_state, d_lambda, d_gamma, d_avg1, d_avg2, d_peak, d_sym, d_out, d_il, d_ig, d_eps, d_flag, d_maps, d_cof, d_bof, d_peakof, d_eof, d_seg;
 };
 
 namespace dvbt {
@@ -598,21 +653,36 @@ int acq_run(dvbt_b200_acq *h, const float2 *x, long long n, float2 *d_out, long 
       acq_chunkmap_kernel<<<(nthreads * 32 + 127) / 128, 128, 0, st>>>((int)nsym, per_thread, nthreads, h->d_flag.as<unsigned char>(),
                                                                h->d_maps.as<unsigned char>());
       AcqWalk *d_walk = h->d_eps.as<AcqWalk>();
+      if ((rc = h->d_seg.reserve((size_t)kMaxSeg * sizeof(int4)))) return rc;
       DVBT_CUDA_TRY(cudaFuncSetAttribute(acq_compose_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-      acq_compose_kernel<<<1, nthreads < 32 ? 32 : nthreads, (size_t)nthreads * kNS + 64, st>>>(
+      acq_compose_kernel<<<1, 256, (size_t)nthreads * kNS + 64, st>>>(
           p, (int)nsym, per_thread, nthreads, (kD - 8) * kND + 2, hs->avg, h->d_lambda.as<float>(), h->d_avg1.as<float>(),
           h->d_peak.as<signed char>(), h->d_avg2.as<float>(), h->d_flag.as<unsigned char>(), h->d_maps.as<unsigned char>(),
-          h->d_cof.as<unsigned char>(), h->d_bof.as<signed char>(), d_walk);
+          h->d_cof.as<unsigned char>(), h->d_bof.as<signed char>(), h->d_seg.as<int4>(), d_walk);
+      {
+        int rows_cap = per_thread < kRowsCap ? per_thread : kRowsCap;
+        size_t per_warp = (size_t)((rows_cap * kNS + 32 + rows_cap + 15) & ~15);
+        DVBT_CUDA_TRY(cudaFuncSetAttribute(acq_walk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(4 * per_warp)));
+        acq_walk_kernel<<<kMaxSeg / 4, 128, 4 * per_warp, st>>>(rows_cap, h->d_peak.as<signed char>(), h->d_avg2.as<float>(),
+                                                               h->d_flag.as<unsigned char>(), h->d_seg.as<int4>(), h->d_cof.as<unsigned char>(),
+                                                               h->d_bof.as<signed char>(), d_walk);
+      }
       if ((rc = h->d_peakof.reserve((size_t)nsym * 4)) || (rc = h->d_eof.reserve((size_t)nsym * 8))) return rc;
       acq_post_kernel<<<(unsigned)((nsym + 127) / 128), 128, 0, st>>>(p, c0, h->d_gamma.as<float2>(), h->d_cof.as<unsigned char>(),
                                                                      h->d_bof.as<signed char>(), d_walk, h->d_peakof.as<int>(), h->d_eof.as<double>());
       acq_finish_kernel<<<1, 1024, 0, st>>>(p, pos, h->d_peakof.as<int>(), h->d_eof.as<double>(), d_walk, h->d_state.as<AcqState>(),
                                           h->d_sym.as<SymOut>());
-      count_launch(7);
+      count_launch(8);
       DVBT_CUDA_TRY(cudaGetLastError());
     }
     DVBT_CUDA_TRY(cudaMemcpyAsync(hs, h->d_state.p, sizeof(AcqState), cudaMemcpyDeviceToHost, st));
     DVBT_CUDA_TRY(cudaStreamSynchronize(st));
+    if (getenv("DVBT_B200_ACQ_TRACE")) {
+      AcqWalk wk;
+      if (cudaMemcpy(&wk, h->d_eps.p, sizeof wk, cudaMemcpyDeviceToHost) == cudaSuccess)
+        fprintf(stderr, "acq batch: nsym %lld found %d code %d override %d segments %d staged %d cycles maps %lld serial %lld\n", nsym,
+                wk.n_found, wk.code, wk.n_override, wk.n_seg, wk.n_staged, wk.cyc_maps, wk.cyc_serial);
+    }
     if (hs->n_out > 0) {
       dim3 grid((p.N + 255) / 256, hs->n_out);
       acq_derot_kernel<<<grid, 256, 0, st>>>(p.N, hs->n_out, x, h->d_sym.as<SymOut>(), d_out + produced * p.N, do_fft ? 1 : 0);
@@ -720,7 +790,7 @@ void dvbt_b200_acq_destroy(dvbt_b200_acq *h) {
   if (!h) return;
   if (h->stream) cudaStreamSynchronize(h->stream);
   if (h->plan) cufftDestroy(h->plan);
-  dvbt::DevBuf *bufs[] = {&h->d_x, &h->d_state, &h->h_state, &h->d_lambda, &h->d_gamma, &h->d_avg1, &h->d_avg2, &h->d_peak, &h->d_sym, &h->d_out, &h->d_il, &h->d_ig, &h->d_eps, &h->d_flag, &h->d_maps, &h->d_cof, &h->d_bof, &h->d_peakof, &h->d_eof};
+  dvbt::DevBuf *bufs[] = {&h->d_x, &h->d_state, &h->h_state, &h->d_lambda, &h->d_gamma, &h->d_avg1, &h->d_avg2, &h->d_peak, &h->d_sym, &h->d_out, &h->d_il, &h->d_ig, &h->d_eps, &h->d_flag, &h->d_maps, &h->d_cof, &h->d_bof, &h->d_peakof, &h->d_eof, &h->d_seg};
   for (auto *b : bufs) b->release();
   if (h->stream && h->own_stream) cudaStreamDestroy(h->stream);
   delete h;

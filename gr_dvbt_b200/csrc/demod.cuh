@@ -15,8 +15,14 @@ int make_demap_table(int constellation, int hierarchy, float gain, DemapTable *t
 // find_constellation_value (dvbt_demap_impl.cc:167-203): first index with the strictly smallest
 // squared distance, every float operation rounded on its own.  The index bits alternate between
 // the axes (b0 b2 b4 -> I, b1 b3 b5 -> Q, :141-156), so re - point.re takes only 2^(M/2) distinct
-// values: the per-axis squares are computed once and the scan over the 2^M points adds the same
-// two floats the reference adds — identical sums, identical comparisons, 2-3x fewer operations.
+// values: the per-axis squares ax[], ay[] are computed once and every distance the reference
+// compares is fl(ax[xa] + ay[ya]) of the same two floats.
+//
+// Shortcut (exact): rounding is monotone, so the smallest distance is V = fl(min ax + min ay), and a
+// pair (xa, ya) can only reach V if fl(ax[xa] + min ay) == V and fl(min ax + ay[ya]) == V.  When
+// exactly one xa and one ya pass that test the argmin is unique and no scan is needed (2^(M/2+1)
+// additions instead of 2^M).  Otherwise - a tie between constellation points, or Inf/NaN input, for
+// which every comparison is false - the reference's scan in index order decides, as before.
 template <int M>
 __device__ __forceinline__ uint8_t demap_cell_exact(const DemapTable &t, float2 v) {
   constexpr int H = M / 2, L = 1 << H, SIZE = 1 << M;
@@ -34,6 +40,27 @@ __device__ __forceinline__ uint8_t demap_cell_exact(const DemapTable &t, float2 
     ax[a] = __fmul_rn(dr, dr);
     ay[a] = __fmul_rn(di, di);
   }
+  float mx = ax[0], my = ay[0];
+#pragma unroll
+  for (int a = 1; a < L; a++) { mx = fminf(mx, ax[a]); my = fminf(my, ay[a]); }
+  const float V = __fadd_rn(mx, my);
+  int cx = 0, cy = 0, bx = 0, by = 0;
+#pragma unroll
+  for (int a = 0; a < L; a++) {
+    int ix = 0, iy = 0;
+#pragma unroll
+    for (int j = 0; j < H; j++) {
+      int bit = (a >> (H - 1 - j)) & 1;
+      ix |= bit << (M - 1 - 2 * j);
+      iy |= bit << (M - 2 - 2 * j);
+    }
+    bool ex = __fadd_rn(ax[a], my) == V, ey = __fadd_rn(mx, ay[a]) == V;
+    cx += ex ? 1 : 0;
+    cy += ey ? 1 : 0;
+    bx = ex ? ix : bx;
+    by = ey ? iy : by;
+  }
+  if (cx == 1 && cy == 1) return (uint8_t)(bx | by);
   float min_dist = __fadd_rn(ax[0], ay[0]);
   int min_index = 0;
 #pragma unroll

@@ -108,61 +108,111 @@ __global__ void __launch_bounds__(256) resample_kernel(const float2 *__restrict_
   }
 }
 
-// Fast path for the 36-taps-per-arm prototype.  The phase of output m is (35 m) mod 32, so a thread that
-// steps m by a multiple of 32 always uses the same arms: it owns the output pair (2u, 2u+1), keeps both
-// arms' 36 taps in registers, and loads the 38 input samples the two overlapping windows span once
-// (the windows start 1 or 2 samples apart, fixed per thread): 19 8-byte loads and 72 FMAs per output.
-constexpr int kRegArm = 36, kRegPairs = 4;
+// Fast path for the 36-taps-per-arm prototype.
+//   * A thread owns four consecutive outputs 4v..4v+3: their windows overlap, so 36+off3 (<= 40) input
+//     samples held in registers feed 4 x 36 taps (10 shared-memory loads per output instead of 36).
+//   * The polyphase arm of output m is (35 m) mod 32, so the four arms - and the distances between the four
+//     windows - depend only on R = v mod 8.  Warp w of a block takes the quads with v mod 8 = w: arms and
+//     window offsets are compile-time constants of the instantiation resample_quad<w>; the warp reads its
+//     taps from shared memory with 16-byte broadcast loads (one address per warp: one wavefront each).
+//     (Taps as constant-bank operands were tried: 36 dependent LDCU.128 per iteration left the kernel
+//     latency bound at 0.59 ms.)
+//   * Lane i of warp w owns quad v = 256 T + 8 i + w of tile T: lane windows start exactly 35 samples apart,
+//     35 = 3 (mod 16), so the 8-byte shared-memory reads of a half-warp hit 16 different banks.
+//   * A tile (1024 outputs, 1120 + 40 inputs) is staged with coalesced loads, the next tile's loads are in
+//     flight during the FMAs, results leave through a padded shared-memory tile as coalesced 8-byte stores.
+// Accumulation order is tap 0..35 per output, one float FMA chain each for re and im, as in the generic kernel.
+constexpr int kRegArm = 36;
+constexpr int kQuadOut = 1024;                       // outputs per tile
+constexpr int kQuadIn = 1120;                        // inputs a tile advances by (1024 * 35 / 32)
+constexpr int kQuadSpan = 1160;                      // staged inputs: 35 history + 1120 + window slack
+constexpr int kQuadPerThread = (kQuadSpan + 255) / 256;
 
-template <int DELTA>
-__device__ __forceinline__ void resample_pair_loop(const float2 *__restrict__ x, long long nin, float2 *__restrict__ y, long long nout,
-                                                   const float *__restrict__ taps_arm, float scale, long long u) {
-  float h0[kRegArm], h1[kRegArm];
-  {
-    int p0 = (int)(((2 * u) * kDecim) % kInterp), p1 = (int)(((2 * u + 1) * kDecim) % kInterp);
+// o1, o2, o3: window starts of outputs 4v+1..4v+3 relative to output 4v.  Only three combinations occur
+// over the eight residues ((1,2,3) six times, (1,2,4) for R = 2, (1,3,4) for R = 5), so the kernel holds
+// three copies of the FMA block instead of eight (the eight-copy version was instruction-cache bound).
+template <int o1, int o2, int o3>
+__device__ __forceinline__ void resample_quad(const float2 *__restrict__ s_x, const float *__restrict__ s_taps, float4 *__restrict__ s_y, int lane,
+                                              int R, float scale) {
+  const int f = (12 * R) % 32;                       // (35 * 4v) mod 32 for v = R (mod 8)
+  const int p0 = f, p1 = (f + 3) % 32, p2 = (f + 6) % 32, p3 = (f + 9) % 32;
+  const int top = 35 * lane + (35 * R) / 8 + 35 + o3;  // tile-local index of the newest input of output 4v+3
+  float2 xs[kRegArm + o3];
 #pragma unroll
-    for (int j = 0; j < kRegArm; j++) { h0[j] = taps_arm[p0 * kRegArm + j]; h1[j] = taps_arm[p1 * kRegArm + j]; }
-  }
-#pragma unroll 1
-  for (int r = 0; r < kRegPairs; r++, u += 256) {
-    long long m0 = 2 * u, m1 = m0 + 1;
-    if (m0 >= nout) return;
-    long long a1 = (m1 * kDecim) / kInterp;   // newest input of the second output; the first one's is a1 - DELTA
-    float2 xs[kRegArm + DELTA];
-    if (a1 >= kRegArm + DELTA - 1 && a1 < nin) {
+  for (int k = 0; k < kRegArm + o3; k++) xs[k] = s_x[top - k];
+  float r0 = 0.f, i0 = 0.f, r1 = 0.f, i1 = 0.f, r2 = 0.f, i2 = 0.f, r3 = 0.f, i3 = 0.f;
+  const float4 *t0 = reinterpret_cast<const float4 *>(s_taps + p0 * kRegArm), *t1 = reinterpret_cast<const float4 *>(s_taps + p1 * kRegArm),
+               *t2 = reinterpret_cast<const float4 *>(s_taps + p2 * kRegArm), *t3 = reinterpret_cast<const float4 *>(s_taps + p3 * kRegArm);
 #pragma unroll
-      for (int k = 0; k < kRegArm + DELTA; k++) xs[k] = __ldg(x + a1 - k);
-    } else {
+  for (int jj = 0; jj < kRegArm / 4; jj++) {
+    const float4 h0 = t0[jj], h1 = t1[jj], h2 = t2[jj], h3 = t3[jj];
+    const float a0[4] = {h0.x, h0.y, h0.z, h0.w}, a1[4] = {h1.x, h1.y, h1.z, h1.w}, a2[4] = {h2.x, h2.y, h2.z, h2.w},
+                a3[4] = {h3.x, h3.y, h3.z, h3.w};
 #pragma unroll
-      for (int k = 0; k < kRegArm + DELTA; k++) {
-        long long idx = a1 - k;
-        xs[k] = (idx >= 0 && idx < nin) ? x[idx] : make_float2(0.f, 0.f);
-      }
+    for (int u = 0; u < 4; u++) {
+      const int j = 4 * jj + u;
+      r0 = fmaf(a0[u], xs[j + o3].x, r0);
+      i0 = fmaf(a0[u], xs[j + o3].y, i0);
+      r1 = fmaf(a1[u], xs[j + o3 - o1].x, r1);
+      i1 = fmaf(a1[u], xs[j + o3 - o1].y, i1);
+      r2 = fmaf(a2[u], xs[j + o3 - o2].x, r2);
+      i2 = fmaf(a2[u], xs[j + o3 - o2].y, i2);
+      r3 = fmaf(a3[u], xs[j].x, r3);
+      i3 = fmaf(a3[u], xs[j].y, i3);
     }
-    float r0 = 0.f, i0 = 0.f, r1 = 0.f, i1 = 0.f;
-#pragma unroll
-    for (int j = 0; j < kRegArm; j++) {
-      r0 = fmaf(h0[j], xs[j + DELTA].x, r0);
-      i0 = fmaf(h0[j], xs[j + DELTA].y, i0);
-      r1 = fmaf(h1[j], xs[j].x, r1);
-      i1 = fmaf(h1[j], xs[j].y, i1);
-    }
-    y[m0] = make_float2(r0 * scale, i0 * scale);
-    if (m1 < nout) y[m1] = make_float2(r1 * scale, i1 * scale);
   }
+  const int q = 8 * lane + R;                        // quad index inside the tile
+  const int unit = 2 * q + q / 8;                    // 16-byte units, one pad unit per 8 quads: conflict-free stores
+  s_y[unit] = make_float4(r0 * scale, i0 * scale, r1 * scale, i1 * scale);
+  s_y[unit + 1] = make_float4(r2 * scale, i2 * scale, r3 * scale, i3 * scale);
 }
 
-__global__ void __launch_bounds__(256) resample_reg_kernel(const float2 *__restrict__ x, long long nin, float2 *__restrict__ y, long long nout,
-                                                           const float *__restrict__ taps_arm, float scale) {
-  long long u = (long long)blockIdx.x * (256 * kRegPairs) + threadIdx.x;
-  long long a0 = ((2 * u) * kDecim) / kInterp, a1 = ((2 * u + 1) * kDecim) / kInterp;
-  if (a1 - a0 == 1) resample_pair_loop<1>(x, nin, y, nout, taps_arm, scale, u);
-  else resample_pair_loop<2>(x, nin, y, nout, taps_arm, scale, u);
+__global__ void __launch_bounds__(256, 3) resample_quad_kernel(const float2 *__restrict__ x, long long nin, float2 *__restrict__ y, long long nout,
+                                                               const float *__restrict__ taps_arm, long long ntiles, float scale) {
+  __shared__ float2 s_x[kQuadSpan];
+  __shared__ __align__(16) float s_taps[kInterp * kRegArm];
+  __shared__ float4 s_y[kQuadOut / 2 + kQuadOut / 32];
+  const int t = threadIdx.x, lane = t & 31, w = t >> 5;
+  float2 pre[kQuadPerThread];
+  auto fetch = [&](long long tile) {
+    long long lo = tile * kQuadIn - 35;
+#pragma unroll
+    for (int k = 0; k < kQuadPerThread; k++) {
+      int i = t + 256 * k;
+      long long idx = lo + i;
+      pre[k] = (i < kQuadSpan && idx >= 0 && idx < nin) ? __ldg(x + idx) : make_float2(0.f, 0.f);
+    }
+  };
+  for (int i = t; i < kInterp * kRegArm; i += 256) s_taps[i] = taps_arm[i];
+  long long tile = blockIdx.x;
+  if (tile < ntiles) fetch(tile);
+  for (; tile < ntiles; tile += gridDim.x) {
+#pragma unroll
+    for (int k = 0; k < kQuadPerThread; k++) {
+      int i = t + 256 * k;
+      if (i < kQuadSpan) s_x[i] = pre[k];
+    }
+    __syncthreads();
+    if (tile + gridDim.x < ntiles) fetch(tile + gridDim.x);
+    if (w == 2) resample_quad<1, 2, 4>(s_x, s_taps, s_y, lane, w, scale);
+    else if (w == 5) resample_quad<1, 3, 4>(s_x, s_taps, s_y, lane, w, scale);
+    else resample_quad<1, 2, 3>(s_x, s_taps, s_y, lane, w, scale);
+    __syncthreads();
+    const float2 *s_y2 = reinterpret_cast<const float2 *>(s_y);
+    long long m0 = tile * kQuadOut;
+#pragma unroll
+    for (int k = 0; k < kQuadOut / 256; k++) {
+      int o = t + 256 * k;
+      int q = o >> 2;
+      long long m = m0 + o;
+      if (m < nout) y[m] = s_y2[2 * (2 * q + (q >> 3) + ((o >> 1) & 1)) + (o & 1)];
+    }
+  }
 }
 
 struct Resampler {
   DevBuf d_taps;
-  int per_arm = 0;
+  int per_arm = 0, sm_count = 148;
   int init() {
     std::vector<float> t;
     resampler_taps(&t, &per_arm);
@@ -172,6 +222,9 @@ struct Resampler {
     int rc = d_taps.reserve(arm.size() * 4);
     if (rc) return rc;
     DVBT_CUDA_TRY(cudaMemcpy(d_taps.p, arm.data(), arm.size() * 4, cudaMemcpyHostToDevice));
+    int dev = 0;
+    cudaGetDevice(&dev);
+    DVBT_CUDA_TRY(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
     return 0;
   }
 };
@@ -192,8 +245,9 @@ int resample_launch(const float2 *d_x, long long nin, float2 *d_y, long long nou
   Resampler *r = g_res[dev];
   if (nout <= 0) return 0;
   if (r->per_arm == kRegArm) {
-    long long per_block = 2LL * 256 * kRegPairs;
-    resample_reg_kernel<<<(unsigned)((nout + per_block - 1) / per_block), 256, 0, st>>>(d_x, nin, d_y, nout, r->d_taps.as<float>(), scale);
+    long long ntiles = (nout + kQuadOut - 1) / kQuadOut;
+    long long grid = ntiles < 3LL * r->sm_count ? ntiles : 3LL * r->sm_count;  // persistent: three resident blocks per SM
+    resample_quad_kernel<<<(unsigned)grid, 256, 0, st>>>(d_x, nin, d_y, nout, r->d_taps.as<float>(), ntiles, scale);
     count_launch();
     DVBT_CUDA_TRY(cudaGetLastError());
     return 0;

@@ -59,69 +59,78 @@ __host__ __device__ constexpr int rate_k(int r) { return r == 0 ? 1 : r == 1 ? 2
 __host__ __device__ constexpr unsigned rate_px(int r) { return r == 0 ? 0x1u : r == 1 ? 0x1u : r == 2 ? 0x5u : r == 3 ? 0x15u : 0x51u; }
 __host__ __device__ constexpr unsigned rate_py(int r) { return r == 0 ? 0x1u : r == 1 ? 0x3u : r == 2 ? 0x3u : r == 3 ? 0x0bu : 0x2fu; }
 
-// Walks consecutive bits of the Viterbi input stream without re-dividing for every bit.
-struct InnerCursor {
-  int sym, blk126, ii, kbit;   // cell = sym*P + blk126 + ii, bit kbit (0 = MSB) of that cell
-  const uint8_t *cells;        // dm row of the current symbol
-  const short *perm;           // H or Hinv for the current symbol
-  __device__ __forceinline__ void load_symbol(const InnerMap &im) {
-    if (sym < im.n_out) {
-      cells = im.dm + (long long)im.out_src[sym] * im.P;
-      perm = (im.out_symidx[sym] & 1) ? im.Hinv : im.H;
-    }
-  }
-  __device__ __forceinline__ void seek(const InnerMap &im, long long tbit) {
-    long long b = tbit / im.m;
-    kbit = (int)(tbit - b * im.m);
-    sym = (int)(b / im.P);
-    int i = (int)(b - (long long)sym * im.P);
-    int blk = i / 126;
-    blk126 = blk * 126;
-    ii = i - blk126;
-    load_symbol(im);
-  }
-  __device__ __forceinline__ uint32_t next(const InnerMap &im) {
-    int half = im.m >> 1;
-    int e = (kbit >= half) ? 1 + 2 * (kbit - half) : 2 * kbit;  // kbit/half + 2*(kbit%half)
-    int off = (0x54152A693F00ull >> (8 * e)) & 0xff;            // {0,63,105,42,21,84}[e]
-    int w = ii - off;
-    if (w < 0) w += 126;
-    uint32_t cell = cells[perm[blk126 + w]];
-    uint32_t bit = (cell >> (im.m - 1 - e)) & 1u;
-    if (++kbit == im.m) {
-      kbit = 0;
-      if (++ii == 126) {
-        ii = 0;
-        blk126 += 126;
-        if (blk126 == im.P) { blk126 = 0; sym++; load_symbol(im); }
-      }
-    }
-    return bit;
-  }
-};
+// bits of the Viterbi input stream consumed by the first `steps` trellis steps (puncturing matrix of RATE)
+template <int RATE>
+__device__ __forceinline__ long long inner_bits_before(long long steps) {
+  constexpr int K = rate_k(RATE), N = K + 1;
+  constexpr unsigned PX = rate_px(RATE), PY = rate_py(RATE);
+  long long sp = steps / K;
+  int ph = (int)(steps - sp * K);
+  return sp * N + __popc(PX & ((1u << ph) - 1u)) + __popc(PY & ((1u << ph) - 1u));
+}
+
+// One block per tile of 6048 cells (4 symbols in 2k mode, 1 in 8k mode).
+//   phase A  one thread per cell of the symbol-deinterleaved tile: ONE gather through H / H^-1 from the
+//            demapped cells, then the cell's m bits are scattered to the places the bit deinterleaver and
+//            the demultiplexer give them in the Viterbi block's input stream - one byte per bit in
+//            shared memory.  (A gather per stream bit, as a straight index map would do, costs m times
+//            the loads.)
+//   phase B  one thread per Viterbi byte time whose first bit lies in the tile: 8 trellis steps, the bits
+//            each takes (puncturing) read from shared memory -> one 32-bit step code.
+// Step codes that straddle the end of the tile need <= 16 bits of the next one: those few are fetched
+// with the bit-wise index map.
+constexpr int kInnerTileCells = 6048, kInnerTail = 64;
 
 template <int RATE>
 __global__ void __launch_bounds__(256) rx_inner_codes_kernel(InnerMap im, uint32_t *__restrict__ codes, int nbt) {
+  extern __shared__ uint8_t s_bit[];  // [tile cells * m + kInnerTail]
+  const int G = kInnerTileCells / im.P;
+  const int sym0 = blockIdx.x * G;
+  const int nsym = min(G, im.n_out - sym0);
+  const int m = im.m, half = m >> 1;
+  const int ncell = nsym * im.P, nbits = ncell * m;
+  const long long lo = (long long)sym0 * im.P * m, hi = lo + nbits;
+  for (int c = threadIdx.x; c < ncell; c += blockDim.x) {
+    int ls = c / im.P, x = c - ls * im.P, sym = sym0 + ls;
+    const short *perm = (im.out_symidx[sym] & 1) ? im.Hinv : im.H;   // symbol_inner_interleaver_impl.cc:202-208
+    uint32_t cell = im.dm[(long long)im.out_src[sym] * im.P + perm[x]];
+    int blk126 = (x / 126) * 126, w = x - blk126;
+    uint8_t *dst = s_bit + (ls * im.P + blk126) * m;
+    for (int e = 0; e < m; e++) {
+      int off = (int)((0x54152A693F00ull >> (8 * e)) & 0xff);          // bit interleaver e: H(e,w) = (w + off) % 126
+      int ii = w + off;
+      if (ii >= 126) ii -= 126;
+      int kbit = (e & 1) * half + (e >> 1);                            // inverse of the demultiplexer permutation
+      dst[ii * m + kbit] = (uint8_t)((cell >> (m - 1 - e)) & 1u);
+    }
+  }
+  const long long total_bits = (long long)im.n_out * im.P * m;
+  for (int b = threadIdx.x; b < kInnerTail; b += blockDim.x) s_bit[nbits + b] = (hi + b < total_bits) ? (uint8_t)inner_bit(im, hi + b) : 0;
+  __syncthreads();
   constexpr int K = rate_k(RATE), N = K + 1;
   constexpr unsigned PX = rate_px(RATE), PY = rate_py(RATE);
-  int j = blockIdx.x * blockDim.x + threadIdx.x;
-  if (j >= nbt) return;
-  long long t = 8LL * j;
-  long long sp = t / K;
-  int ph = (int)(t - sp * K);
-  long long idx = sp * N + __popc(PX & ((1u << ph) - 1u)) + __popc(PY & ((1u << ph) - 1u));
-  InnerCursor cur;
-  cur.seek(im, idx);
-  uint32_t w = 0;
+  // first byte time whose first bit is at or after `lo`, and the same for `hi`
+  long long jlo = (lo * K / N) / 8 - 2, jhi = (hi * K / N) / 8 - 2;
+  if (jlo < 0) jlo = 0;
+  if (jhi < 0) jhi = 0;
+  while (inner_bits_before<RATE>(8 * jlo) < lo) jlo++;
+  while (inner_bits_before<RATE>(8 * jhi) < hi) jhi++;
+  if (jhi > nbt) jhi = nbt;
+  for (long long j = jlo + threadIdx.x; j < jhi; j += blockDim.x) {
+    long long t = 8 * j;
+    int ph = (int)(t % K);
+    const uint8_t *src = s_bit + (int)(inner_bits_before<RATE>(t) - lo);
+    uint32_t wv = 0;
 #pragma unroll
-  for (int i = 0; i < 8; i++) {
-    uint32_t nib = 0;
-    if ((PX >> ph) & 1u) nib |= cur.next(im) | 2u;
-    if ((PY >> ph) & 1u) nib |= (cur.next(im) << 2) | 8u;
-    w |= nib << (4 * i);
-    ph = (ph + 1 == K) ? 0 : ph + 1;
+    for (int i = 0; i < 8; i++) {
+      uint32_t nib = 0;
+      if ((PX >> ph) & 1u) nib |= (uint32_t)(*src++) | 2u;
+      if ((PY >> ph) & 1u) nib |= ((uint32_t)(*src++) << 2) | 8u;
+      wv |= nib << (4 * i);
+      ph = (ph + 1 == K) ? 0 : ph + 1;
+    }
+    codes[j] = wv;
   }
-  codes[j] = w;
 }
 
 // test tap: the bit_inner_deinterleaver output bytes (what the reference feeds its Viterbi block)
@@ -316,13 +325,15 @@ static int rx_run_freq(dvbt_b200_rx *h, const float2 *dX, size_t nsym, uint8_t *
   if (!codes) return DVBT_B200_ENOMEM;
   InnerMap im{h->d_dm.as<uint8_t>(), h->d_osrc.as<int>(), h->d_osym.as<int>(), md.H, md.Hinv, md.P, h->m, S->n_out};
   {
-    unsigned grid = (unsigned)((nbt + 255) / 256);
+    const int G = kInnerTileCells / md.P;
+    unsigned grid = (unsigned)((S->n_out + G - 1) / G);
+    size_t smem = (size_t)kInnerTileCells * h->m + kInnerTail;
     switch (h->par.code_rate) {
-      case 0: rx_inner_codes_kernel<0><<<grid, 256, 0, st>>>(im, codes, (int)nbt); break;
-      case 1: rx_inner_codes_kernel<1><<<grid, 256, 0, st>>>(im, codes, (int)nbt); break;
-      case 2: rx_inner_codes_kernel<2><<<grid, 256, 0, st>>>(im, codes, (int)nbt); break;
-      case 3: rx_inner_codes_kernel<3><<<grid, 256, 0, st>>>(im, codes, (int)nbt); break;
-      default: rx_inner_codes_kernel<4><<<grid, 256, 0, st>>>(im, codes, (int)nbt); break;
+      case 0: rx_inner_codes_kernel<0><<<grid, 256, smem, st>>>(im, codes, (int)nbt); break;
+      case 1: rx_inner_codes_kernel<1><<<grid, 256, smem, st>>>(im, codes, (int)nbt); break;
+      case 2: rx_inner_codes_kernel<2><<<grid, 256, smem, st>>>(im, codes, (int)nbt); break;
+      case 3: rx_inner_codes_kernel<3><<<grid, 256, smem, st>>>(im, codes, (int)nbt); break;
+      default: rx_inner_codes_kernel<4><<<grid, 256, smem, st>>>(im, codes, (int)nbt); break;
     }
     dvbt::count_launch();
     DVBT_CUDA_TRY(cudaGetLastError());

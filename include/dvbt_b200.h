@@ -84,6 +84,7 @@ typedef struct dvbt_b200_viterbi_tuning {
   int chunk_bytes; /* output bytes decoded by one GPU thread */
   int warmup_bytes; /* byte times of warm-up before a chunk's first output */
   int threads_per_block;
+  int ring_depth; /* newest byte times whose survivor rows stay in shared memory (older ones: global ring) */
 } dvbt_b200_viterbi_tuning;
 
 int dvbt_b200_viterbi_create(const dvbt_b200_viterbi_params *p, dvbt_b200_viterbi **out);

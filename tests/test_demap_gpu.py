@@ -18,6 +18,18 @@ def cells_for(con, n, seed, sigma=0.12):
     k = min(len(mids), n - 100)
     c[100: 100 + k] = mids[:k]
     c[-4:] = np.array([0, 1e6 + 1e6j, -1e-30, np.complex64(complex(3.0, -7.5))], np.complex64)
+    # one ulp either side of the ties, and non-finite cells (every comparison false in the reference's scan)
+    near = mids[:k].copy()
+    re = near.real.copy()
+    im = near.imag.copy()
+    re[0::2] = np.nextafter(re[0::2], np.float32(10))
+    im[1::3] = np.nextafter(im[1::3], np.float32(-10))
+    j = 100 + k
+    m = min(k, n - j - 20)
+    if m > 0:
+        c[j: j + m] = (re + 1j * im).astype(np.complex64)[:m]
+    c[-12:-4] = np.array([complex(np.nan, 0.3), complex(0.2, np.nan), complex(np.inf, 1), complex(-1, -np.inf), complex(np.inf, np.inf),
+                          complex(np.nan, np.nan), complex(3.4e38, 3.4e38), complex(-3.4e38, 1e-38)], np.complex64)
     return c
 
 

@@ -166,3 +166,17 @@ def test_handle_follows_its_device_across_host_threads():
     t.start()
     t.join()
     assert np.array_equal(got["out"], ref)
+
+
+@pytest.mark.parametrize("rate,m,ber,depth", [(4, 6, 0.0, 1), (4, 6, 0.008, 2), (3, 4, 0.012, 3), (0, 2, 0.05, 1), (4, 2, 0.004, 12)])
+def test_split_survivor_ring_is_exact(rate, m, ber, depth):
+    """ring_depth < ntraceback: the older survivor rows live in the global ring and are only read by
+    tracebacks that have not merged with the previous one - noisy input makes that happen."""
+    import gr_dvbt_b200 as g
+    data, rx = make_case(rate, m, 14, ber, 31 + depth)
+    ref = O.Viterbi(m, rate).work(rx)
+    dec = g.viterbi_decoder(CON[m], g.NH, rate)
+    for tpb, chunk in ((64, 80), (128, 0)):
+        dec.set_tuning(chunk_bytes=chunk, warmup_bytes=40 if chunk else 0, threads_per_block=tpb, ring_depth=depth)
+        out = dec.decode(rx)[0]
+        assert np.array_equal(out, ref), (tpb, chunk)
