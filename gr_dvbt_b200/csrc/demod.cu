@@ -358,7 +358,7 @@ __device__ bool tps_bch_ok_bits(unsigned long long lo, unsigned hi, unsigned r_l
   return parity == (acc & 0x3FFFu);
 }
 
-// parity of the BCH check as 14 linear forms would be faster still; the LFSR runs once per frame
+constexpr int kScanChunk = 4096;
 __global__ void __launch_bounds__(32) demod_scan_kernel(int ntps, int nparse, int fi_start, int sync_start_at0,
                                                         const int *__restrict__ mod_in, const int *__restrict__ vote,
                                                         const float2 *__restrict__ tpsval, DemodState *st,
@@ -377,8 +377,29 @@ __global__ void __launch_bounds__(32) demod_scan_kernel(int ntps, int nparse, in
   int first_out = -1, n_out = 0, sf_tag_at = -1;
   if (sync_start_at0) d_init = 0;  // :115-116
   const unsigned r_lo = tps_bch_unit_remainder(lane), r_hi = lane + 32 < 53 ? tps_bch_unit_remainder(lane + 32) : 0u;
-  int pf_s = -1, pf_m[3] = {0, 0, 0}, pf_v[3] = {0, 0, 0};  // prefetched frame (fast path)
-  int cbase = -1000, my_mod = 0, my_vote = 0;  // cached chunk of 32 symbols for the symbol-by-symbol path
+  // (phase, vote) of kScanChunk symbols at a time are staged in shared memory with many loads in flight: a
+  // global load per frame, even prefetched one frame ahead, left the loop bound by L2 latency.
+  __shared__ signed char s_mod[kScanChunk], s_vote[kScanChunk];   // phase in -1..3, |vote| <= 68
+  int cbase = -(1 << 30);
+  auto load_chunk = [&](int s0) {
+    __syncwarp();
+    for (int i0 = 0; i0 < kScanChunk && s0 + i0 < nparse; i0 += 32 * 8) {
+      int m[8], v[8];
+#pragma unroll
+      for (int u = 0; u < 8; u++) {
+        int idx = s0 + i0 + lane + 32 * u;
+        m[u] = idx < nparse ? mod_in[idx] : 0;
+        v[u] = idx < nparse ? vote[idx] : 0;
+      }
+#pragma unroll
+      for (int u = 0; u < 8; u++) {
+        s_mod[i0 + lane + 32 * u] = (signed char)m[u];
+        s_vote[i0 + lane + 32 * u] = (signed char)v[u];
+      }
+    }
+    cbase = s0;
+    __syncwarp();
+  };
   int s = 0;
   while (s < nparse) {
     // ---- whole-frame fast path: in lock (known, FIFO just cleared at a frame end), next 68 symbols available.
@@ -387,28 +408,13 @@ __global__ void __launch_bounds__(32) demod_scan_kernel(int ntps, int nparse, in
     if (known && symbol_index == 67 && lo == 0ull && hi == 0u && s + 68 <= nparse) {
       bool good = true;
       unsigned w[3];
-      if (pf_s != s) {  // not prefetched: load this frame now
-#pragma unroll
-        for (int q = 0; q < 3; q++) {
-          int i = lane + 32 * q;
-          pf_m[q] = i < 68 ? mod_in[s + i] : 0;
-          pf_v[q] = i < 68 ? vote[s + i] : 0;
-        }
-      }
+      if (s < cbase || s + 68 > cbase + kScanChunk) load_chunk(s);
       int cm[3], cv[3];
 #pragma unroll
-      for (int q = 0; q < 3; q++) { cm[q] = pf_m[q]; cv[q] = pf_v[q]; }
-      // prefetch the next frame while this one is processed (in lock, frames are 68 symbols apart)
-      pf_s = s + 68;
-      if (pf_s + 68 <= nparse) {
-#pragma unroll
-        for (int q = 0; q < 3; q++) {
-          int i = lane + 32 * q;
-          pf_m[q] = i < 68 ? mod_in[pf_s + i] : 0;
-          pf_v[q] = i < 68 ? vote[pf_s + i] : 0;
-        }
-      } else {
-        pf_s = -1;
+      for (int q = 0; q < 3; q++) {
+        int i = lane + 32 * q;
+        cm[q] = i < 68 ? s_mod[s - cbase + i] : 0;
+        cv[q] = i < 68 ? s_vote[s - cbase + i] : 0;
       }
 #pragma unroll
       for (int q = 0; q < 3; q++) {
@@ -450,14 +456,9 @@ __global__ void __launch_bounds__(32) demod_scan_kernel(int ntps, int nparse, in
       }
     }
     // ---- one symbol (parse_input :1188-1248 bookkeeping)
-    if (s < cbase || s >= cbase + 32) {
-      cbase = s;
-      int sl = s + lane;
-      my_mod = sl < nparse ? mod_in[sl] : 0;
-      my_vote = sl < nparse ? vote[sl] : 0;
-    }
-    int m_in = __shfl_sync(0xffffffffu, my_mod, s - cbase);
-    int v_in = __shfl_sync(0xffffffffu, my_vote, s - cbase);
+    if (s < cbase || s >= cbase + kScanChunk) load_chunk(s);
+    int m_in = s_mod[s - cbase];
+    int v_in = s_vote[s - cbase];
     int mod = m_in >= 0 ? m_in : cur_mod;
     cur_mod = mod;
     int diff = (mod - prev_mod + 4) & 3;  // :684-688

@@ -39,10 +39,10 @@ import sys
 
 POLYA, POLYB = 0x4F, 0x6D
 H = 0x80808080
-# Variant that moves the compare and the 2p+1 path update to the FMA pipe (IMAD via mad.lo with run-time
-# multipliers).  Measured on B200 (profiles/r01_bench_rx_v4.json vs v3): 3 % SLOWER — the extra IMADs cost
-# more issue slots than the ALU pipe relief wins back with one warp per scheduler.  Kept for reference, off.
-USE_IMAD = False
+# The compare (t = m1 + H - m0) and the path update (2p + 1) are emitted as macros (VIT_CMP / VIT_PATH2) so that
+# the kernel can choose, per instantiation, between one ALU-pipe IADD3 and an FMA-pipe form (IMAD with run-time
+# multipliers, one extra addition per compare).  With one warp per scheduler the FMA form measured 3 % slower
+# (profiles/r01_bench_rx_v4.json vs v3); it is meant for the multi-warp configurations (split survivor ring).
 
 
 def parity(v):
@@ -85,28 +85,21 @@ class Gen:
                 if sel not in sel_cache:
                     r = self.new("bm")
                     self.emit("prmt", r, apk, "ZERO", sel)
-                    rh = None
-                    if USE_IMAD:
-                        rh = self.new("bh")
-                        self.emit("addc", rh, r, H)  # addend + 0x80 per byte, shared by every pair of the step
+                    rh = self.new("bh")
+                    self.emit("addc", rh, r, H)  # addend + 0x80 per byte, shared by every pair of the step (dead code in the ALU form)
                     sel_cache[sel] = (r, rh)
             (a, ah), (b, bh) = sel_cache[sel_a], sel_cache[sel_b]
             m0, m1, m2, m3 = self.new("m"), self.new("m"), self.new("m"), self.new("m")
-            self.emit("add", m0, mi, a)
-            self.emit("add", m1, mj, b)
-            self.emit("add", m2, mi, b)
-            self.emit("add", m3, mj, a)
+            # the four branch-metric additions of a butterfly pair are tagged so that the kernel can route two or all
+            # four of them to the FMA pipe (VIT_ADDF / VIT_ADDG, see the header text below)
+            self.emit("addf", m0, mi, a)
+            self.emit("addf", m1, mj, b)
+            self.emit("addg", m2, mi, b)
+            self.emit("addg", m3, mj, a)
             # compare: t = (mj + b + H) - m0, both steps on the FMA pipe (IMAD) instead of one IADD3 on the ALU pipe
             t0, t1 = self.new("c"), self.new("c")
-            if USE_IMAD:
-                h1, h3 = self.new("h"), self.new("h")
-                self.emit("add", h1, mj, bh)
-                self.emit("add", h3, mj, ah)
-                self.emit("subm", t0, h1, m0)  # t0 = m1 + H - m0
-                self.emit("subm", t1, h3, m2)
-            else:
-                self.emit("cmp", t0, m1, m0)   # t0 = m1 + H - m0 (one IADD3)
-                self.emit("cmp", t1, m3, m2)
+            self.emit("cmpx", t0, m1, mj, bh, m0)   # t0 = m1 + H - m0 = (mj + bh) - m0
+            self.emit("cmpx", t1, m3, mj, ah, m2)
             k0, k1 = self.new("k"), self.new("k")
             self.emit("signmask", k0, t0)
             self.emit("signmask", k1, t1)
@@ -120,10 +113,7 @@ class Gen:
                 pi, pj = idxP[st], idxP[hi]
                 si, sj = self.new("p"), self.new("p")
                 self.emit("add", si, pi, pi)
-                if USE_IMAD:
-                    self.emit("mad2c", sj, pj, 0x01010101)   # 2*pj + 0x01010101
-                else:
-                    self.emit("add3c", sj, pj, pj, 0x01010101)
+                self.emit("path2", sj, pj)   # 2*pj + 0x01010101
                 pe, po = self.new("P"), self.new("P")
                 self.emit("sel", pe, si, sj, k0)
                 self.emit("sel", po, si, sj, k1)
@@ -242,12 +232,17 @@ def run_ops(ops, env):
         k, d = op[0], op[1]
         if k == "prmt":
             env[d] = prmt(env[op[2]], env[op[3]], op[4])
-        elif k == "add":
+        elif k in ("add", "addf", "addg"):
             env[d] = (env[op[2]] + env[op[3]]).astype(u32)
         elif k == "add3c":
             env[d] = (env[op[2]] + env[op[3]] + u32(op[4])).astype(u32)
         elif k == "cmp":
             env[d] = (env[op[2]] + u32(H) - env[op[3]]).astype(u32)
+        elif k == "cmpx":
+            env[d] = (env[op[2]] + u32(H) - env[op[5]]).astype(u32)
+            assert np.array_equal(env[d], (env[op[3]] + env[op[4]] - env[op[5]]).astype(u32))
+        elif k == "path2":
+            env[d] = (env[op[2]] + env[op[2]] + u32(0x01010101)).astype(u32)
         elif k == "addc":
             env[d] = (env[op[2]] + u32(op[3])).astype(u32)
         elif k == "subm":
@@ -290,10 +285,18 @@ def emit_cuda(ops, indent="  "):
             lines.append("%s = vit_prmt(%s, %s, 0x%04xu);" % (dst(d), ref(op[2]), b, op[4]))
         elif k == "add":
             lines.append("%s = %s + %s;" % (dst(d), ref(op[2]), ref(op[3])))
+        elif k == "addf":
+            lines.append("%s = VIT_ADDF(%s, %s);" % (dst(d), ref(op[2]), ref(op[3])))
+        elif k == "addg":
+            lines.append("%s = VIT_ADDG(%s, %s);" % (dst(d), ref(op[2]), ref(op[3])))
         elif k == "add3c":
             lines.append("%s = %s + %s + 0x%08xu;" % (dst(d), ref(op[2]), ref(op[3]), op[4]))
         elif k == "cmp":
             lines.append("%s = %s + 0x80808080u - %s;" % (dst(d), ref(op[2]), ref(op[3])))
+        elif k == "cmpx":
+            lines.append("%s = VIT_CMP(%s, %s, %s, %s);" % (dst(d), ref(op[2]), ref(op[3]), ref(op[4]), ref(op[5])))
+        elif k == "path2":
+            lines.append("%s = VIT_PATH2(%s);" % (dst(d), ref(op[2])))
         elif k == "addc":
             lines.append("%s = %s + 0x%08xu;" % (dst(d), ref(op[2]), op[3]))
         elif k == "subm":
@@ -330,6 +333,23 @@ __device__ __forceinline__ uint32_t vit_mad(uint32_t a, uint32_t b, uint32_t c) 
   asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c));
   return r;
 }
+// The branch-metric additions of the schedule.  The including kernel may define VIT_ADDF / VIT_ADDG as
+// vit_mad(a, vit_one, b) to issue half or all of them on the FMA pipe; the default is a plain addition.
+#ifndef VIT_ADDF
+#define VIT_ADDF(a, b) ((a) + (b))
+#endif
+#ifndef VIT_ADDG
+#define VIT_ADDG(a, b) ((a) + (b))
+#endif
+// Compare word t = m1 + 0x80808080 - m0, where m1 = mj + b and bh = b + 0x80808080: bit 7 of a byte = (m1 >= m0).
+// Default: one 3-input addition.  FMA form: vit_mad(m0, vit_neg1, mj + bh).
+#ifndef VIT_CMP
+#define VIT_CMP(m1, mj, bh, m0) ((m1) + 0x80808080u - (m0))
+#endif
+// Path of the odd predecessor: 2 p + 1 per byte.  FMA form: vit_mad(p, vit_two, 0x01010101).
+#ifndef VIT_PATH2
+#define VIT_PATH2(p) ((p) + (p) + 0x01010101u)
+#endif
 // per byte: mask ? y : x   (mask bytes are 0x00 or 0xff)
 __device__ __forceinline__ uint32_t vit_sel(uint32_t x, uint32_t y, uint32_t mask) {
   return (y & mask) | (x & ~mask);

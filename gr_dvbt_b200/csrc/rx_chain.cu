@@ -25,8 +25,6 @@ namespace {
 
 using dvbt::set_error;
 
-__constant__ uint8_t c_descr_prbs[1504];
-
 struct InnerMap {
   const uint8_t *dm;        // demapped cells, P per parsed symbol
   const int *out_src;       // batch symbol index of output symbol o
@@ -147,29 +145,49 @@ struct DescrInfo {
   long long ngroups;  // 8-packet groups written
 };
 
-// One block per 8-packet group.  Every block repeats the (tiny) NSYNC search of
-// energy_descramble_impl.cc:121-134: windows of 2 groups, first packet whose first byte is 0xB8.
-__global__ void __launch_bounds__(256) rx_descramble_kernel(const uint8_t *__restrict__ rs, long long npk, uint8_t *__restrict__ ts,
-                                                            long long ts_capacity, DescrInfo *info) {
+// Every block repeats the (tiny) NSYNC search of energy_descramble_impl.cc:121-134 - windows of 2 groups,
+// first packet whose first byte is 0xB8 - with one packet per thread, then descrambles 8-packet groups a
+// 32-bit word per thread (packets are 47 words; the PRBS table sits in shared memory).
+__global__ void __launch_bounds__(256) rx_descramble_kernel(const uint8_t *__restrict__ rs, long long npk, const uint32_t *__restrict__ prbs,
+                                                            uint8_t *__restrict__ ts, long long ts_capacity, DescrInfo *info) {
   __shared__ long long s_p0;
-  if (threadIdx.x == 0) {
-    long long p0 = -1;
-    for (long long w = 0; w + 16 <= npk && p0 < 0; w += 16)
-      for (int i = 0; i < 16; i++)
-        if (rs[(w + i) * 188] == 0xB8) { p0 = w + i; break; }
-    s_p0 = p0;
-  }
+  __shared__ uint32_t s_prbs[376];
+  for (int i = threadIdx.x; i < 376; i += blockDim.x) s_prbs[i] = prbs[i];
+  if (threadIdx.x == 0) s_p0 = -1;
   __syncthreads();
+  const long long limit = (npk / 16) * 16;   // only whole 16-packet windows are searched
+  for (long long base = 0; base < limit; base += blockDim.x) {
+    long long pk = base + threadIdx.x;
+    bool hit = pk < limit && rs[pk * 188] == 0xB8;
+    unsigned any = __syncthreads_or(hit ? 1 : 0);
+    if (any) {
+      if (hit) atomicMin((unsigned long long *)&s_p0, (unsigned long long)pk);  // -1 reads as the largest value
+      __syncthreads();
+      break;
+    }
+  }
   long long p0 = s_p0;
   long long ngroups = p0 < 0 ? 0 : (npk - p0) / 8;
   if (ngroups * 1504 > ts_capacity) ngroups = ts_capacity / 1504;
   if (blockIdx.x == 0 && threadIdx.x == 0) { info->p0 = (int)p0; info->ngroups = ngroups; }
-  for (long long g = blockIdx.x; g < ngroups; g += gridDim.x) {
-    const uint8_t *src = rs + (p0 + g * 8) * 188;
-    uint8_t *dst = ts + g * 1504;
-    for (int i = threadIdx.x; i < 1504; i += blockDim.x) {
-      int k = i % 188;
-      dst[i] = k == 0 ? (uint8_t)0x47 : (uint8_t)(src[i] ^ c_descr_prbs[i]);  // :146-165
+  if (ngroups <= 0) return;
+  const uint8_t *src0 = rs + p0 * 188;
+  if (((((uintptr_t)src0) | ((uintptr_t)ts)) & 3u) == 0) {
+    const uint32_t *src = reinterpret_cast<const uint32_t *>(src0);
+    uint32_t *dst = reinterpret_cast<uint32_t *>(ts);
+    const long long nwords = ngroups * 376;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nwords; i += (long long)gridDim.x * blockDim.x) {
+      int k = (int)(i % 376);
+      uint32_t v = src[i] ^ s_prbs[k];                       // :146-165
+      if (k % 47 == 0) v = (v & 0xffffff00u) | 0x47u;          // sync byte of every packet
+      dst[i] = v;
+    }
+  } else {
+    const uint8_t *pb = reinterpret_cast<const uint8_t *>(s_prbs);
+    const long long nbytes = ngroups * 1504;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nbytes; i += (long long)gridDim.x * blockDim.x) {
+      int k = (int)(i % 1504);
+      ts[i] = (k % 188 == 0) ? (uint8_t)0x47 : (uint8_t)(src0[i] ^ pb[k]);
     }
   }
 }
@@ -187,7 +205,7 @@ struct dvbt_b200_rx {
   cudaStream_t stream = nullptr;
   int fi_start = 3, rs_as_built = 0, sm_count = 148;
   int k = 1, n = 2, m = 4, ntb = 5, vit_in_block = 0, vit_out_block = 0;
-  dvbt::DevBuf d_X, d_state, d_fo, d_rot, d_mod, d_tps, d_vote, d_osym, d_osrc, d_dm, d_Y, d_vit, d_rs, d_rsst, d_ts, d_info, h_state, h_info;
+  dvbt::DevBuf d_X, d_state, d_fo, d_rot, d_mod, d_tps, d_vote, d_osym, d_osrc, d_dm, d_Y, d_vit, d_rs, d_rsst, d_ts, d_info, d_prbs, h_state, h_info;
   dvbt_b200_rx_info info;
   long long last_nparse = 0;
   cudaEvent_t ev[8];
@@ -249,7 +267,8 @@ int dvbt_b200_rx_create(const dvbt_b200_rx_params *p, dvbt_b200_rx **out) {
       for (int k = 1; k < 188; k++) tab[pk * 188 + k] = clock8();
       clock8();
     }
-    cudaMemcpyToSymbol(c_descr_prbs, tab, 1504);
+    if ((rc = h->d_prbs.reserve(1504))) { dvbt_b200_rx_destroy(h); return rc; }
+    if (cudaMemcpy(h->d_prbs.p, tab, 1504, cudaMemcpyHostToDevice) != cudaSuccess) { set_error("rx_create: PRBS table upload failed"); dvbt_b200_rx_destroy(h); return DVBT_B200_ECUDA; }
   }
   int dev = 0;
   cudaGetDevice(&dev);
@@ -264,7 +283,7 @@ void dvbt_b200_rx_destroy(dvbt_b200_rx *h) {
   if (!h) return;
   if (h->stream) cudaStreamSynchronize(h->stream);
   dvbt::DevBuf *bufs[] = {&h->d_X, &h->d_state, &h->d_fo, &h->d_rot, &h->d_mod, &h->d_tps, &h->d_vote, &h->d_osym, &h->d_osrc, &h->d_dm,
-                          &h->d_Y, &h->d_vit, &h->d_rs, &h->d_rsst, &h->d_ts, &h->d_info, &h->h_state, &h->h_info};
+                          &h->d_Y, &h->d_vit, &h->d_rs, &h->d_rsst, &h->d_ts, &h->d_info, &h->d_prbs, &h->h_state, &h->h_info};
   for (auto *b : bufs) b->release();
   for (auto &e : h->ev) if (e) cudaEventDestroy(e);
   h->tables.release();
@@ -359,9 +378,10 @@ static int rx_run_freq(dvbt_b200_rx *h, const float2 *dX, size_t nsym, uint8_t *
     if (cap > (size_t)npk * 188 || ts_host == nullptr) cap = (size_t)npk * 188;
   }
   {
-    long long groups = npk / 8 + 1;
-    unsigned grid = (unsigned)(groups < 4096 ? groups : 4096);
-    rx_descramble_kernel<<<grid, 256, 0, st>>>(h->d_rs.as<uint8_t>(), npk, ts_out, (long long)cap, h->d_info.as<DescrInfo>());
+    long long blocks = (npk / 8 + 1) * 376 / 256 / 4 + 1;   // ~4 words per thread
+    unsigned grid = (unsigned)(blocks < 8LL * h->sm_count ? blocks : 8LL * h->sm_count);
+    rx_descramble_kernel<<<grid, 256, 0, st>>>(h->d_rs.as<uint8_t>(), npk, h->d_prbs.as<uint32_t>(), ts_out, (long long)cap,
+                                               h->d_info.as<DescrInfo>());
     dvbt::count_launch();
     DVBT_CUDA_TRY(cudaGetLastError());
   }

@@ -20,17 +20,24 @@ def main():
         sigma = (p_sig / (10.0 ** (snr / 10.0)) / 2.0) ** 0.5
         x = torch.view_as_complex((torch.view_as_real(x) + torch.randn(x.shape[0], 2, device="cuda") * sigma).contiguous())
     ref = None
-    for tpsm, depth in [(128, 24), (256, 0), (256, 8), (384, 0), (384, 4), (512, 0), (512, 2), (640, 0), (768, 0)]:
+    configs = [(128, 24, 128, 0), (256, 0, 256, 0), (256, 0, 128, 0), (320, 0, 320, 0), (384, 0, 384, 0), (384, 0, 128, 0), (384, 0, 384, 4), (448, 0, 448, 0),
+               (512, 0, 512, 0), (512, 0, 256, 0), (512, 0, 512, 4), (512, 3, 512, 0), (384, 4, 384, 0), (256, 6, 256, 0)]
+    if os.environ.get("SWEEP_ONLY"):
+        configs = [tuple(int(v) for v in c.split(",")) for c in os.environ["SWEEP_ONLY"].split(";")]
+    for cfg in configs:
+        tpsm, depth, bd = cfg[:3]
+        os.environ["DVBT_B200_VIT_FMAADD"] = str(cfg[3] if len(cfg) > 3 else 0)
         os.environ["DVBT_B200_VIT_TPSM"] = str(tpsm)
         os.environ["DVBT_B200_VIT_DEPTH"] = str(depth)
+        os.environ["DVBT_B200_VIT_BD"] = str(bd)
         ms = []
-        for i in range(6):
+        for i in range(int(os.environ.get("SWEEP_REPS", "6"))):
             n = w.rx.run_file_dev(x.data_ptr(), w.nfile, w.GAIN, w.d_ts.data_ptr(), w.ts_cap)
             ms.append(w.rx.info()["ms_viterbi_acs"])
         ts = w.d_ts[:n].cpu().numpy()
         if ref is None:
             ref = ts.copy()
-        print("tpsm %4d depth %2d: acs %.3f ms (min %.3f)  same_ts=%s repaired=%d" % (tpsm, depth, float(np.median(ms[2:])), min(ms), bool(np.array_equal(ts, ref)), w.rx.info()["viterbi_repaired"]), flush=True)
+        print("tpsm %4d depth %2d bd %3d fma %s: acs %.3f ms (min %.3f)  same_ts=%s repaired=%d" % (tpsm, depth, bd, os.environ["DVBT_B200_VIT_FMAADD"], float(np.median(ms[2:])), min(ms), bool(np.array_equal(ts, ref)), w.rx.info()["viterbi_repaired"]), flush=True)
 
 
 if __name__ == "__main__":
