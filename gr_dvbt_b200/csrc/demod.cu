@@ -107,6 +107,18 @@ int ModeTables::init(int tm, int gi) {
       }
     if (n != P) { set_error("mode tables: %d payload carriers for scattered phase %d, expected %d", n, r, P); return DVBT_B200_EINVAL; }
   }
+  // dense list of the channel-estimation carriers of every scattered phase (the kernels loop over these
+  // instead of testing kind[] on all K carriers: the gain computation is a double-precision complex division,
+  // and with one pilot in twelve it would otherwise run with three lanes of a warp active)
+  d.pil_stride = (K + 11) / 12 + d.ncp + 8;
+  std::vector<short> pil((size_t)4 * d.pil_stride, 0);
+  for (int r = 0; r < 4; r++) {
+    int n = 0;
+    for (int k = 0; k < K; k++)
+      if (kind[r * K + k] & 1) pil[(size_t)r * d.pil_stride + n++] = (short)k;
+    if (n > d.pil_stride) { set_error("mode tables: %d pilots for phase %d", n, r); return DVBT_B200_EINVAL; }
+    d.npil[r] = n;
+  }
   // symbol interleaver H(q) (symbol_inner_interleaver_impl.cc:35-96)
   std::vector<short> H(P), Hinv(P);
   {
@@ -139,7 +151,7 @@ int ModeTables::init(int tm, int gi) {
   auto place = [&](size_t bytes) { size_t o = off; off += (bytes + 15) & ~(size_t)15; return o; };
   size_t o_cp = place(cpl.size() * 2), o_tps = place(tpl.size() * 2), o_known = place(known.size() * 4), o_pval = place(pval.size() * 4),
          o_kind = place(kind.size()), o_prev = place(prevp.size() * 2), o_next = place(nextp.size() * 2), o_pay = place(payload.size() * 2),
-         o_H = place(H.size() * 2), o_Hi = place(Hinv.size() * 2);
+         o_H = place(H.size() * 2), o_Hi = place(Hinv.size() * 2), o_pil = place(pil.size() * 2);
   std::vector<unsigned char> host(off);
   memcpy(&host[o_cp], cpl.data(), cpl.size() * 2);
   memcpy(&host[o_tps], tpl.data(), tpl.size() * 2);
@@ -151,6 +163,7 @@ int ModeTables::init(int tm, int gi) {
   memcpy(&host[o_pay], payload.data(), payload.size() * 2);
   memcpy(&host[o_H], H.data(), H.size() * 2);
   memcpy(&host[o_Hi], Hinv.data(), Hinv.size() * 2);
+  memcpy(&host[o_pil], pil.data(), pil.size() * 2);
   int rc = blob.reserve(off);
   if (rc) return rc;
   DVBT_CUDA_TRY(cudaMemcpy(blob.p, host.data(), off, cudaMemcpyHostToDevice));
@@ -165,6 +178,7 @@ int ModeTables::init(int tm, int gi) {
   d.payload = (const short *)(base + o_pay);
   d.H = (const short *)(base + o_H);
   d.Hinv = (const short *)(base + o_Hi);
+  d.pilots = (const short *)(base + o_pil);
   return 0;
 }
 
@@ -280,16 +294,20 @@ __global__ void __launch_bounds__(256) demod_equalise_kernel(ModeDev md, const _
   const float2 *x = X + (long long)s * md.N + md.zl + fo;
   const unsigned char *kind = md.kind + r * md.K;
   // pilot gains: gain = tx / rx (:484-489 set_channel_gain)
-  for (int k = threadIdx.x; k < md.K; k += blockDim.x) {
-    if (kind[k] & 1) s_gain[k] = cdiv(make_float2(md.pval[k], 0.f), cmul(rot, x[k]));
+  const short *pil = md.pilots + r * md.pil_stride;
+  const int npil = md.npil[r];
+  for (int i = threadIdx.x; i < npil; i += blockDim.x) {
+    int k = pil[i];
+    s_gain[k] = cdiv(make_float2(md.pval[k], 0.f), cmul(rot, x[k]));
   }
   __syncthreads();
   // linear interpolation with the reference's fixed /11 slope (:617-642): the slope of an interval
   // is computed once, by the thread that owns the pilot at its left end
   const short *prevp = md.prevp + r * md.K, *nextp = md.nextp + r * md.K;
   float2 *s_slope = s_gain + md.K;
-  for (int k = threadIdx.x; k < md.K; k += blockDim.x) {
-    if (kind[k] & 1) s_slope[k] = cdiv(csub(s_gain[nextp[k]], s_gain[k]), make_float2(11.0f, 0.0f));
+  for (int i = threadIdx.x; i < npil; i += blockDim.x) {
+    int k = pil[i];
+    s_slope[k] = cdiv(csub(s_gain[nextp[k]], s_gain[k]), make_float2(11.0f, 0.0f));
   }
   __syncthreads();
   for (int k = threadIdx.x; k < md.K; k += blockDim.x) {

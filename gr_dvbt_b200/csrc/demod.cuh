@@ -99,6 +99,8 @@ struct ModeDev {
   const short *payload;    // [4][P] payload carriers in increasing order
   const short *H;          // [P] symbol interleaver permutation H(q) (symbol_inner_interleaver_impl.cc:35-96)
   const short *Hinv;       // [P]
+  const short *pilots;     // [4][pil_stride] channel-estimation carriers of scattered phase r, increasing
+  int npil[4], pil_stride;
 };
 
 struct ModeTables {

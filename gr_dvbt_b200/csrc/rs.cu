@@ -8,12 +8,13 @@
 // (:376-403), error evaluator and Forney values (:419-486) including the "uncorrectable:
 // leave the packet alone" and "null denominator: keep what was already corrected" exits.
 //
-// Mapping: the 32 lanes split the 204 bytes (7 per lane); each lane accumulates its 16
-// partial syndromes from log/exp tables in shared memory; a butterfly of warp shuffles
-// XOR-reduces them (16 syndromes packed in 4 registers).  Clean packets — the common case —
-// are then copied out by the same warp.  Packets with errors run the locator iteration on
-// lane 0, the Chien search on all lanes (8 positions per lane, ballots keep the order) and
-// Forney on lane 0.
+// Mapping: a block takes 128 packets.  The clean-packet test is a division by the generator polynomial,
+// one packet per thread (rs_decode_kernel); only packets with a non-zero remainder go through the
+// syndrome / locator / Chien / Forney path, one warp per packet (rs_warp_decode): the 32 lanes split the 204
+// bytes (7 per lane), each lane accumulates its 16 partial syndromes from log/exp tables in shared memory, a
+// butterfly of warp shuffles XOR-reduces them (16 syndromes packed in 4 registers), the locator iteration
+// runs on lane 0, the Chien search on all lanes (8 positions per lane, ballots keep the order) and Forney on
+// lane 0.
 #include "common.cuh"
 
 #include <new>
@@ -97,113 +98,193 @@ __device__ int rs_forney(const GfTables &gf, const uint8_t *syn, const uint8_t *
   return no_roots;
 }
 
-// GATHER: `in` is the Viterbi output stream (in_bytes long, index 0 = the byte carrying the
-// superframe_start tag) and the 12-branch Forney deinterleaver of
-// convolutional_deinterleaver_impl.cc:93-150 (branch b = t % 12 is delayed by 17*(11-b) cells,
-// i.e. 204*(11-b) stream positions; the FIFOs start zeroed) is applied as an index map while
-// the packet is loaded.
-template <bool GATHER>
-__global__ void __launch_bounds__(256) rs_decode_kernel(const uint8_t *__restrict__ in, uint8_t *__restrict__ out,
-                                                        int *__restrict__ status, long long npackets, int as_built,
-                                                        long long in_bytes) {
-  __shared__ __align__(16) uint8_t s_exp2[512];
-  __shared__ __align__(16) uint8_t s_log[256];
-  __shared__ __align__(16) uint32_t s_pkt[8][52];
-  __shared__ uint8_t s_work[8][80];  // per warp: syn[16] | sigma[17] | root[17] | loc[17] | deg, status
-  for (int i = threadIdx.x; i < 512; i += blockDim.x) s_exp2[i] = c_exp2[i];
-  for (int i = threadIdx.x; i < 256; i += blockDim.x) s_log[i] = c_log[i];
-  __syncthreads();
-  GfTables gf{s_exp2, s_log};
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  uint8_t *pkt = reinterpret_cast<uint8_t *>(s_pkt[warp]);
-  uint8_t *syn = s_work[warp], *sigma = syn + 16, *root = sigma + 17, *loc = root + 17, *misc = loc + 17;
-  for (long long p = (long long)blockIdx.x * 8 + warp; p < npackets; p += (long long)gridDim.x * 8) {
-    if (GATHER) {
+// Syndromes, locator, Chien and Forney for one packet held in shared memory (204 bytes at `pkt`), by one
+// warp; returns the reference's per-packet result (0 clean, > 0 corrected symbols, -1 uncorrectable) in
+// every lane.  `work`: 80 bytes of per-warp scratch.
+__device__ int rs_warp_decode(const GfTables &gf, uint8_t *pkt, uint8_t *work, int lane, int as_built) {
+  uint8_t *syn = work, *sigma = syn + 16, *root = sigma + 17, *loc = root + 17, *misc = loc + 17;
+  // ---- syndromes: byte j carries x^(203-j); lane takes j = lane, lane+32, ...
+  uint32_t S0 = 0, S1 = 0, S2 = 0, S3 = 0;
 #pragma unroll
-      for (int t = 0; t < 7; t++) {
-        int j = lane + 32 * t;
-        if (j < kPktIn) {
-          long long pos = p * kPktIn + j;
-          long long srcpos = pos - 204 * (11 - (j % 12));
-          pkt[j] = (srcpos >= 0 && srcpos < in_bytes) ? in[srcpos] : (uint8_t)0;
+  for (int t = 0; t < 7; t++) {
+    int j = lane + 32 * t;
+    if (j < kPktIn) {
+      int v = pkt[j];
+      if (v) {
+        int ex = 203 - j;
+        int e = gf.log[v];
+        uint32_t acc[4] = {0, 0, 0, 0};
+#pragma unroll
+        for (int i = 0; i < 16; i++) {
+          acc[i >> 2] |= (uint32_t)gf.exp2[e] << (8 * (i & 3));
+          e += ex;
+          if (e >= 255) e -= 255;
         }
+        S0 ^= acc[0]; S1 ^= acc[1]; S2 ^= acc[2]; S3 ^= acc[3];
       }
-    } else {
-      const uint32_t *src = reinterpret_cast<const uint32_t *>(in + p * kPktIn);
-      s_pkt[warp][lane] = src[lane];
-      if (lane + 32 < 51) s_pkt[warp][lane + 32] = src[lane + 32];
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    S0 ^= __shfl_xor_sync(0xffffffffu, S0, o);
+    S1 ^= __shfl_xor_sync(0xffffffffu, S1, o);
+    S2 ^= __shfl_xor_sync(0xffffffffu, S2, o);
+    S3 ^= __shfl_xor_sync(0xffffffffu, S3, o);
+  }
+  int st = 0;
+  if ((S0 | S1 | S2 | S3) != 0u) {  // warp-uniform
+    if (lane == 0) {
+      uint32_t S[4] = {S0, S1, S2, S3};
+      for (int i = 0; i < 16; i++) syn[i] = (uint8_t)(S[i >> 2] >> (8 * (i & 3)));
+      misc[0] = (uint8_t)rs_locator(gf, syn, sigma);
     }
     __syncwarp();
-    // ---- syndromes: byte j carries x^(203-j); lane takes j = lane, lane+32, ...
-    uint32_t S0 = 0, S1 = 0, S2 = 0, S3 = 0;
-#pragma unroll
-    for (int t = 0; t < 7; t++) {
-      int j = lane + 32 * t;
-      if (j < kPktIn) {
-        int v = pkt[j];
-        if (v) {
-          int ex = 203 - j;
-          int e = s_log[v];
-          uint32_t acc[4] = {0, 0, 0, 0};
-#pragma unroll
-          for (int i = 0; i < 16; i++) {
-            acc[i >> 2] |= (uint32_t)s_exp2[e] << (8 * (i & 3));
-            e += ex;
-            if (e >= 255) e -= 255;
-          }
-          S0 ^= acc[0]; S1 ^= acc[1]; S2 ^= acc[2]; S3 ^= acc[3];
-        }
+    int deg = misc[0];
+    // ---- Chien: q(i) = 1 + sum_j sigma[j] a^(j*i), i = 1..255 in increasing order
+    int nroots = 0;
+    for (int t = 0; t < 8; t++) {
+      int i = 32 * t + lane + 1;
+      int q = 1;
+      if (i <= kN) {
+        for (int j = deg; j > 0; j--) q ^= gf.mulpow(sigma[j], j * i);
       }
+      unsigned hit = __ballot_sync(0xffffffffu, i <= kN && q == 0);
+      if (q == 0 && i <= kN) {
+        int idx = nroots + __popc(hit & ((1u << lane) - 1u));
+        if (idx < 17) { root[idx] = (uint8_t)i; loc[idx] = (uint8_t)(i - 1); }
+      }
+      nroots += __popc(hit);
     }
+    __syncwarp();
+    if (lane == 0) {
+      if (nroots != deg) {
+        st = -1;  // uncorrectable: data untouched (:405-415)
+      } else {
+        // the reference's out-of-bounds omega[2t] = 0 lands on loc[0] with gcc 13.3
+        if (as_built) loc[0] = 0;
+        st = rs_forney(gf, syn, sigma, deg, root, loc, nroots, pkt);
+      }
+      misc[1] = (uint8_t)(st & 0xff);
+    }
+    __syncwarp();
+    st = (int)(int8_t)misc[1];
+  }
+  return st;
+}
+
+// Row f of the division table: the 16 bytes f * g_k, k = 0..15, of the generator polynomial
+// g(x) = prod_{i=0..15} (x + a^i) (reed_solomon.cc:95-133 builds the same g), as 4 little-endian words.
+__device__ uint32_t d_lfsr[256 * 4];
+
+constexpr int kTilePk = 128;            // packets per block
+constexpr int kHalo = 204 * 11;         // bytes of stream history the deepest deinterleaver branch reaches back
+
+// One block per 128 packets.
+//   1. The contiguous input range of the tile is staged in shared memory with coalesced loads.  GATHER: `in` is
+//      the Viterbi output stream (in_bytes long, index 0 = the byte carrying the superframe_start tag) and the
+//      12-branch Forney deinterleaver of convolutional_deinterleaver_impl.cc:93-150 (branch b = t % 12 is delayed
+//      by 17*(11-b) cells, i.e. 204*(11-b) stream positions; the FIFOs start zeroed) is the index map
+//      packet q, byte j  ->  staged[q*204 + j + 204*(j % 12)]  applied when a byte is read.
+//   2. One THREAD per packet divides the received word by g(x) (LFSR, one 16-byte table row per byte): the
+//      remainder is zero exactly when all 16 syndromes r(a^i) are zero.  This is the whole cost of a clean
+//      packet - 204 table rows instead of 204 x 16 log/exp lookups.
+//   3. All packets are copied out (bytes 0..187) with coalesced stores.
+//   4. Packets with a non-zero remainder are decoded by a warp each exactly as before (rs_warp_decode) and
+//      written over their copy.
+template <bool GATHER>
+__global__ void __launch_bounds__(kTilePk) rs_decode_kernel(const uint8_t *__restrict__ in, uint8_t *__restrict__ out,
+                                                            int *__restrict__ status, long long npackets, int as_built,
+                                                            long long in_bytes) {
+  extern __shared__ __align__(16) uint8_t s_raw[];   // [kTilePk*204 (+ kHalo)]
+  __shared__ __align__(16) uint4 s_lfsr[256];
+  __shared__ __align__(16) uint8_t s_exp2[512];
+  __shared__ __align__(16) uint8_t s_log[256];
+  __shared__ __align__(16) uint32_t s_pkt[kTilePk / 32][52];
+  __shared__ uint8_t s_work[kTilePk / 32][80];
+  __shared__ int s_dirty[kTilePk];
+  __shared__ int s_ndirty;
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  for (int i = t; i < 512; i += blockDim.x) s_exp2[i] = c_exp2[i];
+  for (int i = t; i < 256; i += blockDim.x) s_log[i] = c_log[i];
+  for (int i = t; i < 256; i += blockDim.x) s_lfsr[i] = reinterpret_cast<const uint4 *>(d_lfsr)[i];
+  if (t == 0) s_ndirty = 0;
+  const long long p0 = (long long)blockIdx.x * kTilePk;
+  const int np = (int)((npackets - p0) < kTilePk ? (npackets - p0) : kTilePk);
+  const int halo = GATHER ? kHalo : 0;
+  const long long total = GATHER ? in_bytes : npackets * (long long)kPktIn;
+  {
+    const long long src0 = p0 * kPktIn - halo;             // multiple of 4
+    const int nwords = (np * kPktIn + halo) / 4;
+    uint32_t *raw32 = reinterpret_cast<uint32_t *>(s_raw);
+    for (int i = t; i < nwords; i += blockDim.x) {
+      long long pos = src0 + 4LL * i;
+      uint32_t v = 0;
+      if (pos >= 0 && pos + 4 <= total) {
+        v = *reinterpret_cast<const uint32_t *>(in + pos);
+      } else {
+        for (int b = 0; b < 4; b++)
+          if (pos + b >= 0 && pos + b < total) v |= (uint32_t)in[pos + b] << (8 * b);
+      }
+      raw32[i] = v;
+    }
+  }
+  __syncthreads();
+  // ---- division by g(x), one packet per thread
+  if (t < np) {
+    const uint8_t *src = s_raw + t * kPktIn;
+    uint32_t r0 = 0, r1 = 0, r2 = 0, r3 = 0;
+    int jm = 0;  // j % 12
+    for (int j = 0; j < kPktIn; j++) {
+      uint32_t d = src[j + (GATHER ? kPktIn * jm : 0)];
+      if (++jm == 12) jm = 0;
+      uint32_t fb = d ^ (r3 >> 24);
+      r3 = __funnelshift_l(r2, r3, 8);
+      r2 = __funnelshift_l(r1, r2, 8);
+      r1 = __funnelshift_l(r0, r1, 8);
+      r0 <<= 8;
+      uint4 row = s_lfsr[fb];
+      r0 ^= row.x; r1 ^= row.y; r2 ^= row.z; r3 ^= row.w;
+    }
+    if ((r0 | r1 | r2 | r3) != 0u) s_dirty[atomicAdd(&s_ndirty, 1)] = t;
+    if (status) status[p0 + t] = 0;
+  }
+  __syncthreads();
+  // ---- copy out the 188 data bytes of every packet (47 words each)
+  {
+    uint32_t *dst = reinterpret_cast<uint32_t *>(out + p0 * kPktOut);
+    const int nwords = np * 47;
+    for (int k = t; k < nwords; k += blockDim.x) {
+      int q = k / 47, j = 4 * (k - q * 47);
+      const uint8_t *src = s_raw + q * kPktIn;
+      uint32_t v = 0;
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      S0 ^= __shfl_xor_sync(0xffffffffu, S0, o);
-      S1 ^= __shfl_xor_sync(0xffffffffu, S1, o);
-      S2 ^= __shfl_xor_sync(0xffffffffu, S2, o);
-      S3 ^= __shfl_xor_sync(0xffffffffu, S3, o);
+      for (int b = 0; b < 4; b++) {
+        int jj = j + b;
+        v |= (uint32_t)src[jj + (GATHER ? kPktIn * (jj % 12) : 0)] << (8 * b);
+      }
+      dst[k] = v;
     }
-    int st = 0;
-    if ((S0 | S1 | S2 | S3) != 0u) {  // warp-uniform
-      if (lane == 0) {
-        uint32_t S[4] = {S0, S1, S2, S3};
-        for (int i = 0; i < 16; i++) syn[i] = (uint8_t)(S[i >> 2] >> (8 * (i & 3)));
-        misc[0] = (uint8_t)rs_locator(gf, syn, sigma);
-      }
-      __syncwarp();
-      int deg = misc[0];
-      // ---- Chien: q(i) = 1 + sum_j sigma[j] a^(j*i), i = 1..255 in increasing order
-      int nroots = 0;
-      for (int t = 0; t < 8; t++) {
-        int i = 32 * t + lane + 1;
-        int q = 1;
-        if (i <= kN) {
-          for (int j = deg; j > 0; j--) q ^= gf.mulpow(sigma[j], j * i);
-        }
-        unsigned hit = __ballot_sync(0xffffffffu, i <= kN && q == 0);
-        if (q == 0 && i <= kN) {
-          int idx = nroots + __popc(hit & ((1u << lane) - 1u));
-          if (idx < 17) { root[idx] = (uint8_t)i; loc[idx] = (uint8_t)(i - 1); }
-        }
-        nroots += __popc(hit);
-      }
-      __syncwarp();
-      if (lane == 0) {
-        if (nroots != deg) {
-          st = -1;  // uncorrectable: data untouched (:405-415)
-        } else {
-          // the reference's out-of-bounds omega[2t] = 0 lands on loc[0] with gcc 13.3
-          if (as_built) loc[0] = 0;
-          st = rs_forney(gf, syn, sigma, deg, root, loc, nroots, pkt);
-        }
-        misc[1] = (uint8_t)(st & 0xff);
-      }
-      __syncwarp();
-      st = (int)(int8_t)misc[1];
+  }
+  __syncthreads();
+  // ---- packets with errors: one warp each
+  GfTables gf{s_exp2, s_log};
+  const int ndirty = s_ndirty;
+  uint8_t *pkt = reinterpret_cast<uint8_t *>(s_pkt[warp]);
+  for (int d = warp; d < ndirty; d += kTilePk / 32) {
+    const int q = s_dirty[d];
+    const uint8_t *src = s_raw + q * kPktIn;
+#pragma unroll
+    for (int u = 0; u < 7; u++) {
+      int j = lane + 32 * u;
+      if (j < kPktIn) pkt[j] = src[j + (GATHER ? kPktIn * (j % 12) : 0)];
     }
-    uint32_t *dst = reinterpret_cast<uint32_t *>(out + p * kPktOut);
+    __syncwarp();
+    int st = rs_warp_decode(gf, pkt, s_work[warp], lane, as_built);
+    __syncwarp();
+    uint32_t *dst = reinterpret_cast<uint32_t *>(out + (p0 + q) * kPktOut);
     dst[lane] = s_pkt[warp][lane];
     if (lane + 32 < 47) dst[lane + 32] = s_pkt[warp][lane + 32];
-    if (status && lane == 0) status[p] = st;
+    if (status && lane == 0) status[p0 + q] = st;
     __syncwarp();  // pkt is rewritten by the next iteration
   }
 }
@@ -237,6 +318,21 @@ int rs_upload_tables() {
   for (int i = 255; i < 512; i++) e2[i] = e2[i - 255];
   DVBT_CUDA_TRY(cudaMemcpyToSymbol(c_exp2, e2, 512));
   DVBT_CUDA_TRY(cudaMemcpyToSymbol(c_log, lg, 256));
+  {
+    auto mul = [&](int a, int b) { return (a && b) ? (int)e2[lg[a] + lg[b]] : 0; };
+    uint8_t g[17] = {1};          // g(x) = prod (x + a^i), i = 0..15; g[k] = coefficient of x^k
+    int deg = 0;
+    for (int i = 0; i < 16; i++) {
+      int root = e2[i];
+      for (int k = deg + 1; k > 0; k--) g[k] = (uint8_t)(g[k - 1] ^ mul(g[k], root));
+      g[0] = (uint8_t)mul(g[0], root);
+      deg++;
+    }
+    static uint8_t rows[256 * 16];
+    for (int f = 0; f < 256; f++)
+      for (int k = 0; k < 16; k++) rows[f * 16 + k] = (uint8_t)mul(f, g[k]);
+    DVBT_CUDA_TRY(cudaMemcpyToSymbol(d_lfsr, rows, sizeof rows));
+  }
   if (dev < 64) g_tables_ready[dev] = true;
   return 0;
 }
@@ -246,13 +342,12 @@ int rs_launch(const uint8_t *d_in, uint8_t *d_out, int *d_status, long long npac
   if (npackets <= 0) return 0;
   int rc = rs_upload_tables();
   if (rc) return rc;
-  long long blocks = (npackets + 7) / 8;
-  long long cap = (long long)sm_count * 8;
-  unsigned grid = (unsigned)(blocks < cap ? blocks : cap);
+  unsigned grid = (unsigned)((npackets + kTilePk - 1) / kTilePk);
+  (void)sm_count;
   if (gather_stream_bytes >= 0)
-    rs_decode_kernel<true><<<grid, 256, 0, st>>>(d_in, d_out, d_status, npackets, as_built, gather_stream_bytes);
+    rs_decode_kernel<true><<<grid, kTilePk, (size_t)kTilePk * kPktIn + kHalo, st>>>(d_in, d_out, d_status, npackets, as_built, gather_stream_bytes);
   else
-    rs_decode_kernel<false><<<grid, 256, 0, st>>>(d_in, d_out, d_status, npackets, as_built, 0);
+    rs_decode_kernel<false><<<grid, kTilePk, (size_t)kTilePk * kPktIn, st>>>(d_in, d_out, d_status, npackets, as_built, 0);
   count_launch();
   DVBT_CUDA_TRY(cudaGetLastError());
   return 0;

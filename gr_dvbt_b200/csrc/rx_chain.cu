@@ -71,42 +71,81 @@ __device__ __forceinline__ long long inner_bits_before(long long steps) {
 //   phase A  one thread per cell of the symbol-deinterleaved tile: ONE gather through H / H^-1 from the
 //            demapped cells, then the cell's m bits are scattered to the places the bit deinterleaver and
 //            the demultiplexer give them in the Viterbi block's input stream - one byte per bit in
-//            shared memory.  (A gather per stream bit, as a straight index map would do, costs m times
-//            the loads.)
-//   phase B  one thread per Viterbi byte time whose first bit lies in the tile: 8 trellis steps, the bits
-//            each takes (puncturing) read from shared memory -> one 32-bit step code.
+//            shared memory (m, the interleaver offsets and the demultiplexer map are compile-time).
+//            (A gather per stream bit, as a straight index map would do, costs m times the loads.)
+//   phase A' the bit bytes are packed 32 to a word: stream bit i = bit (i & 31) of word i >> 5.
+//   phase B  one thread per Viterbi byte time whose first bit lies in the tile: a 32-bit window of the
+//            stream at the byte time's first bit, then 8 trellis steps whose bit positions in the window
+//            are compile-time for each puncturing phase -> one 32-bit step code.
 // Step codes that straddle the end of the tile need <= 16 bits of the next one: those few are fetched
 // with the bit-wise index map.
 constexpr int kInnerTileCells = 6048, kInnerTail = 64;
 
-template <int RATE>
+// step code of 8 trellis steps starting in puncturing phase PH0, from a window whose bit k is stream bit idx + k
+template <int RATE, int PH0>
+__device__ __forceinline__ uint32_t inner_code_from_window(uint32_t win) {
+  constexpr int K = rate_k(RATE);
+  constexpr unsigned PX = rate_px(RATE), PY = rate_py(RATE);
+  uint32_t wv = 0;
+  int pos = 0, ph = PH0;
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    if ((PX >> ph) & 1u) { wv |= (((win >> pos) & 1u) | 2u) << (4 * i); pos++; }
+    if ((PY >> ph) & 1u) { wv |= ((((win >> pos) & 1u) << 2) | 8u) << (4 * i); pos++; }
+    ph = (ph + 1 == K) ? 0 : ph + 1;
+  }
+  return wv;
+}
+
+template <int RATE, int M>
 __global__ void __launch_bounds__(256) rx_inner_codes_kernel(InnerMap im, uint32_t *__restrict__ codes, int nbt) {
-  extern __shared__ uint8_t s_bit[];  // [tile cells * m + kInnerTail]
+  extern __shared__ __align__(16) uint8_t s_bit[];  // [tile cells * M + kInnerTail] bit bytes, then the packed words
+  constexpr int HALF = M / 2;
   const int G = kInnerTileCells / im.P;
   const int sym0 = blockIdx.x * G;
   const int nsym = min(G, im.n_out - sym0);
-  const int m = im.m, half = m >> 1;
-  const int ncell = nsym * im.P, nbits = ncell * m;
-  const long long lo = (long long)sym0 * im.P * m, hi = lo + nbits;
-  for (int c = threadIdx.x; c < ncell; c += blockDim.x) {
-    int ls = c / im.P, x = c - ls * im.P, sym = sym0 + ls;
+  const int ncell = nsym * im.P, nbits = ncell * M;
+  const long long lo = (long long)sym0 * im.P * M, hi = lo + nbits;
+  uint32_t *s_words = reinterpret_cast<uint32_t *>(s_bit + ((kInnerTileCells * M + kInnerTail + 15) & ~15));
+  for (int ls = 0; ls < nsym; ls++) {
+    const int sym = sym0 + ls;
     const short *perm = (im.out_symidx[sym] & 1) ? im.Hinv : im.H;   // symbol_inner_interleaver_impl.cc:202-208
-    uint32_t cell = im.dm[(long long)im.out_src[sym] * im.P + perm[x]];
-    int blk126 = (x / 126) * 126, w = x - blk126;
-    uint8_t *dst = s_bit + (ls * im.P + blk126) * m;
-    for (int e = 0; e < m; e++) {
-      int off = (int)((0x54152A693F00ull >> (8 * e)) & 0xff);          // bit interleaver e: H(e,w) = (w + off) % 126
-      int ii = w + off;
-      if (ii >= 126) ii -= 126;
-      int kbit = (e & 1) * half + (e >> 1);                            // inverse of the demultiplexer permutation
-      dst[ii * m + kbit] = (uint8_t)((cell >> (m - 1 - e)) & 1u);
+    const uint8_t *row = im.dm + (long long)im.out_src[sym] * im.P;
+    uint8_t *base = s_bit + ls * im.P * M;
+    for (int x = threadIdx.x; x < im.P; x += blockDim.x) {
+      uint32_t cell = row[perm[x]];
+      int blk126 = (x / 126) * 126, w = x - blk126;
+      uint8_t *dst = base + blk126 * M;
+#pragma unroll
+      for (int e = 0; e < M; e++) {
+        constexpr int kOff[6] = {0, 63, 105, 42, 21, 84};              // bit interleaver e: H(e,w) = (w + off) % 126 (:34-58)
+        int ii = w + kOff[e];
+        if (ii >= 126) ii -= 126;
+        const int kbit = (e & 1) * HALF + (e >> 1);                    // inverse of the demultiplexer permutation (:91-99)
+        dst[ii * M + kbit] = (uint8_t)((cell >> (M - 1 - e)) & 1u);
+      }
     }
   }
-  const long long total_bits = (long long)im.n_out * im.P * m;
+  const long long total_bits = (long long)im.n_out * im.P * M;
   for (int b = threadIdx.x; b < kInnerTail; b += blockDim.x) s_bit[nbits + b] = (hi + b < total_bits) ? (uint8_t)inner_bit(im, hi + b) : 0;
   __syncthreads();
+  // ---- A': pack (4 bit bytes -> 4 bits with one multiply: bytes are 0/1, so no carries meet)
+  {
+    const int nw = (nbits + kInnerTail + 31) / 32;
+    const uint32_t *b4 = reinterpret_cast<const uint32_t *>(s_bit);
+    for (int wi = threadIdx.x; wi < nw; wi += blockDim.x) {
+      uint32_t word = 0;
+#pragma unroll
+      for (int q = 0; q < 8; q++) {
+        uint32_t v = b4[wi * 8 + q];                       // bit bytes 4q..4q+3 of this word
+        uint32_t nib = ((v * 0x01020408u) >> 24) & 0xFu;   // byte k (bit 8k) -> bit 24 + k; no two partial products share a bit
+        word |= nib << (4 * q);
+      }
+      s_words[wi] = word;
+    }
+  }
+  __syncthreads();
   constexpr int K = rate_k(RATE), N = K + 1;
-  constexpr unsigned PX = rate_px(RATE), PY = rate_py(RATE);
   // first byte time whose first bit is at or after `lo`, and the same for `hi`
   long long jlo = (lo * K / N) / 8 - 2, jhi = (hi * K / N) / 8 - 2;
   if (jlo < 0) jlo = 0;
@@ -117,15 +156,18 @@ __global__ void __launch_bounds__(256) rx_inner_codes_kernel(InnerMap im, uint32
   for (long long j = jlo + threadIdx.x; j < jhi; j += blockDim.x) {
     long long t = 8 * j;
     int ph = (int)(t % K);
-    const uint8_t *src = s_bit + (int)(inner_bits_before<RATE>(t) - lo);
-    uint32_t wv = 0;
-#pragma unroll
-    for (int i = 0; i < 8; i++) {
-      uint32_t nib = 0;
-      if ((PX >> ph) & 1u) nib |= (uint32_t)(*src++) | 2u;
-      if ((PY >> ph) & 1u) nib |= ((uint32_t)(*src++) << 2) | 8u;
-      wv |= nib << (4 * i);
-      ph = (ph + 1 == K) ? 0 : ph + 1;
+    int local = (int)(inner_bits_before<RATE>(t) - lo);
+    uint32_t w0 = s_words[local >> 5], w1 = s_words[(local >> 5) + 1];
+    uint32_t win = __funnelshift_r(w0, w1, local & 31);
+    uint32_t wv;
+    switch (ph) {
+      case 0: wv = inner_code_from_window<RATE, 0>(win); break;
+      case 1: wv = inner_code_from_window<RATE, 1 % K>(win); break;
+      case 2: wv = inner_code_from_window<RATE, 2 % K>(win); break;
+      case 3: wv = inner_code_from_window<RATE, 3 % K>(win); break;
+      case 4: wv = inner_code_from_window<RATE, 4 % K>(win); break;
+      case 5: wv = inner_code_from_window<RATE, 5 % K>(win); break;
+      default: wv = inner_code_from_window<RATE, 6 % K>(win); break;
     }
     codes[j] = wv;
   }
@@ -346,14 +388,18 @@ static int rx_run_freq(dvbt_b200_rx *h, const float2 *dX, size_t nsym, uint8_t *
   {
     const int G = kInnerTileCells / md.P;
     unsigned grid = (unsigned)((S->n_out + G - 1) / G);
-    size_t smem = (size_t)kInnerTileCells * h->m + kInnerTail;
+    size_t smem = (size_t)((kInnerTileCells * h->m + kInnerTail + 15) & ~15) + (size_t)(kInnerTileCells * h->m + kInnerTail) / 8 + 16;
+#define RX_INNER_LAUNCH(R, M) rx_inner_codes_kernel<R, M><<<grid, 256, smem, st>>>(im, codes, (int)nbt)
+#define RX_INNER_RATE(R) (h->m == 2 ? RX_INNER_LAUNCH(R, 2) : h->m == 4 ? RX_INNER_LAUNCH(R, 4) : RX_INNER_LAUNCH(R, 6))
     switch (h->par.code_rate) {
-      case 0: rx_inner_codes_kernel<0><<<grid, 256, smem, st>>>(im, codes, (int)nbt); break;
-      case 1: rx_inner_codes_kernel<1><<<grid, 256, smem, st>>>(im, codes, (int)nbt); break;
-      case 2: rx_inner_codes_kernel<2><<<grid, 256, smem, st>>>(im, codes, (int)nbt); break;
-      case 3: rx_inner_codes_kernel<3><<<grid, 256, smem, st>>>(im, codes, (int)nbt); break;
-      default: rx_inner_codes_kernel<4><<<grid, 256, smem, st>>>(im, codes, (int)nbt); break;
+      case 0: RX_INNER_RATE(0); break;
+      case 1: RX_INNER_RATE(1); break;
+      case 2: RX_INNER_RATE(2); break;
+      case 3: RX_INNER_RATE(3); break;
+      default: RX_INNER_RATE(4); break;
     }
+#undef RX_INNER_RATE
+#undef RX_INNER_LAUNCH
     dvbt::count_launch();
     DVBT_CUDA_TRY(cudaGetLastError());
   }
