@@ -347,11 +347,8 @@ __global__ void demod_vote_kernel(int ntps, int nparse, const float2 *__restrict
 }
 
 // BCH(127,113) shortened to (67,53): verify_bch_code (:384-425), on the bit-packed FIFO
-// The sequential bookkeeping of parse_input (:1188-1248) and of the block (:108-149).  One warp:
-// the lanes fetch 32 symbols' (phase, vote) with one coalesced load each, then every lane runs
-// the same state machine on shuffled values (no divergence); lane 0 writes the results.  The
-// 68-entry TPS FIFO (d_rcv_tps_data) is a bit set: entry i = bit i of (lo, hi).
-// The BCH remainder is linear in the 53 data bits (FIFO entries 1..53): lane j keeps the 14-bit
+// TPS helpers of the scan kernel below.  The 68-entry TPS FIFO (d_rcv_tps_data) is a bit set: entry i = bit i
+// of (lo, hi).  The BCH remainder is linear in the 53 data bits (FIFO entries 1..53): lane j keeps the 14-bit
 // remainder R[j] of the unit vector at data bit j (and j+32), computed once per launch with the
 // reference's LFSR; a check is then one masked XOR per lane and a 5-step warp reduction.
 __device__ unsigned tps_bch_unit_remainder(int j) {
@@ -376,30 +373,54 @@ __device__ bool tps_bch_ok_bits(unsigned long long lo, unsigned hi, unsigned r_l
   return parity == (acc & 0x3FFFu);
 }
 
-constexpr int kScanChunk = 4096;
-__global__ void __launch_bounds__(32) demod_scan_kernel(int ntps, int nparse, int fi_start, int sync_start_at0,
-                                                        const int *__restrict__ mod_in, const int *__restrict__ vote,
-                                                        const float2 *__restrict__ tpsval, DemodState *st,
-                                                        int *__restrict__ out_symidx, int *__restrict__ out_src) {
-  const int lane = threadIdx.x;
+constexpr int kScanChunk = 4096;     // symbols staged in shared memory for the symbol-by-symbol path
+constexpr int kScanFrames = 2048;    // frames validated per parallel round
+constexpr int kScanWarps = 8;
+
+// The sequential bookkeeping of parse_input (:1188-1248) and of the block (:108-149) as one block of 8 warps.
+//   * Warp 0 runs the reference's per-symbol state machine (all lanes the same scalar code, lane 0 writes)
+//     until the receiver is in lock at a frame boundary: known, symbol_index == 67, FIFO just cleared.
+//   * From there on a whole 68-symbol frame is equivalent to 68 single steps provided every symbol advances
+//     the index by one, no sync word shows up early in the partly filled FIFO, and the frame ends with a
+//     valid sync word + BCH.  A good frame leaves the scattered-pilot phase where it was (68 = 0 mod 4), so
+//     these conditions do not depend on the frames before: ALL following frames are checked in parallel
+//     (one warp per frame: ballots build the 68 TPS bits, the BCH remainder is a warp XOR-reduce).
+//   * Warp 0 then walks the per-frame verdicts (superframe gating is the only state), all threads write the
+//     output descriptors of the accepted frames, and the first rejected frame is handed back to the
+//     per-symbol machine, exactly as the one-frame-at-a-time loop did.
+__global__ void __launch_bounds__(32 * kScanWarps) demod_scan_kernel(int ntps, int nparse, int fi_start, int sync_start_at0,
+                                                                     const int *__restrict__ mod_in, const int *__restrict__ vote,
+                                                                     const float2 *__restrict__ tpsval, DemodState *st,
+                                                                     int *__restrict__ out_symidx, int *__restrict__ out_src) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   // sync words of :121-126 as FIFO entries 1..15 (std::equal compares 15 elements, :975/:1002)
   const unsigned long long kEven = (1ull << 3) | (1ull << 4) | (1ull << 6) | (1ull << 8) | (1ull << 9) | (1ull << 10) | (1ull << 11) |
                                    (1ull << 13) | (1ull << 14) | (1ull << 15);
   const unsigned long long kMask = 0xFFFEull;
-  int symbol_index = st->symbol_index, known = st->known, frame_index = st->frame_index, prev_mod = st->prev_mod,
-      cur_mod = st->mod, d_init = st->d_init;
+  __shared__ signed char s_mod[kScanChunk], s_vote[kScanChunk];   // phase in -1..3, |vote| <= 68
+  __shared__ unsigned char s_ok[kScanFrames], s_fi[kScanFrames];
+  __shared__ int s_lock, s_prev_mod, s_nframes, s_emit_from, s_nf, s_out_base;
+  const unsigned r_lo = tps_bch_unit_remainder(lane), r_hi = lane + 32 < 53 ? tps_bch_unit_remainder(lane + 32) : 0u;
+
+  // ---- state of the sequential machine (meaningful in warp 0 only)
+  int symbol_index = 0, known = 0, frame_index = 0, prev_mod = 0, cur_mod = 0, d_init = 0;
   unsigned long long lo = 0;
   unsigned hi = 0;
-  for (int i = 0; i < 64; i++) lo |= (unsigned long long)(st->fifo[i] & 1) << i;
-  for (int i = 64; i < 68; i++) hi |= (unsigned)(st->fifo[i] & 1) << (i - 64);
   int first_out = -1, n_out = 0, sf_tag_at = -1;
-  if (sync_start_at0) d_init = 0;  // :115-116
-  const unsigned r_lo = tps_bch_unit_remainder(lane), r_hi = lane + 32 < 53 ? tps_bch_unit_remainder(lane + 32) : 0u;
-  // (phase, vote) of kScanChunk symbols at a time are staged in shared memory with many loads in flight: a
-  // global load per frame, even prefetched one frame ahead, left the loop bound by L2 latency.
-  __shared__ signed char s_mod[kScanChunk], s_vote[kScanChunk];   // phase in -1..3, |vote| <= 68
   int cbase = -(1 << 30);
-  auto load_chunk = [&](int s0) {
+  int s = 0;
+  bool skip_fast = false;
+  if (warp == 0) {
+    symbol_index = st->symbol_index; known = st->known; frame_index = st->frame_index; prev_mod = st->prev_mod;
+    cur_mod = st->mod; d_init = st->d_init;
+    unsigned long long b0 = lane < 32 ? (unsigned long long)(st->fifo[lane] & 1) : 0ull, b1 = (unsigned long long)(st->fifo[32 + lane] & 1);
+    unsigned b2 = lane < 4 ? (unsigned)(st->fifo[64 + lane] & 1) : 0u;
+    unsigned w0 = __ballot_sync(0xffffffffu, b0 != 0), w1 = __ballot_sync(0xffffffffu, b1 != 0), w2 = __ballot_sync(0xffffffffu, b2 != 0);
+    lo = ((unsigned long long)w1 << 32) | w0;
+    hi = w2 & 0xFu;
+    if (sync_start_at0) d_init = 0;  // :115-116
+  }
+  auto load_chunk = [&](int s0) {   // warp 0 only
     __syncwarp();
     for (int i0 = 0; i0 < kScanChunk && s0 + i0 < nparse; i0 += 32 * 8) {
       int m[8], v[8];
@@ -418,28 +439,85 @@ __global__ void __launch_bounds__(32) demod_scan_kernel(int ntps, int nparse, in
     cbase = s0;
     __syncwarp();
   };
-  int s = 0;
-  while (s < nparse) {
-    // ---- whole-frame fast path: in lock (known, FIFO just cleared at a frame end), next 68 symbols available.
-    // Equivalent to 68 single steps provided every symbol advances the index by one, no sync word shows up
-    // early in the partly filled FIFO, and the frame ends with a valid sync word + BCH; otherwise fall through.
-    if (known && symbol_index == 67 && lo == 0ull && hi == 0u && s + 68 <= nparse) {
+
+  for (;;) {
+    // ================= warp 0: symbol by symbol until in lock at a frame boundary (or out of input)
+    if (warp == 0) {
+      while (s < nparse) {
+        if (!skip_fast && known && symbol_index == 67 && lo == 0ull && hi == 0u && s + 68 <= nparse) break;
+        skip_fast = false;
+        // ---- one symbol (parse_input :1188-1248 bookkeeping)
+        if (s < cbase || s >= cbase + kScanChunk) load_chunk(s);
+        int m_in = s_mod[s - cbase];
+        int v_in = s_vote[s - cbase];
+        int mod = m_in >= 0 ? m_in : cur_mod;
+        cur_mod = mod;
+        int diff = (mod - prev_mod + 4) & 3;  // :684-688
+        prev_mod = mod;
+        symbol_index += diff;                 // :1228
+        if (symbol_index >= 68) symbol_index -= 68;
+        int sym_out = symbol_index, frame_out = frame_index;
+        bool cond = !known || symbol_index != 0;
+        unsigned long long bitv = cond ? (v_in >= 0 ? 0ull : 1ull) : 0ull;
+        for (int d = 0; d < diff; d++) {      // :957-972: pop front, push back
+          lo = (lo >> 1) | ((unsigned long long)(hi & 1u) << 63);
+          hi = (hi >> 1) | ((unsigned)bitv << 3);
+        }
+        bool even = (lo & kMask) == kEven, odd = (lo & kMask) == (kEven ^ kMask);
+        int end_frame = 0;
+        if (even || odd) {
+          if (tps_bch_ok_bits(lo, hi, r_lo, r_hi, lane)) {
+            frame_index = (int)((((lo >> 23) & 1ull) << 1) | ((lo >> 24) & 1ull));
+            known = 1;
+            end_frame = 1;
+          } else {
+            known = 0;
+          }
+          lo = 0;
+          hi = 0;
+        }
+        if (end_frame) symbol_index = 67;     // :1240-1241
+        // block level (demod_reference_signals_impl.cc:118-143)
+        bool emit = true;
+        if (d_init == 0) {
+          if (sym_out == 0 && (frame_out & 3) == fi_start) {
+            d_init = 1;
+            sf_tag_at = n_out;
+          } else {
+            emit = false;
+          }
+        }
+        if (emit) {
+          if (first_out < 0) first_out = s;
+          if (lane == 0) { out_symidx[n_out] = sym_out; out_src[n_out] = s; }
+          n_out++;
+        }
+        s++;
+      }
+      if (lane == 0) {
+        s_lock = s < nparse ? s : -1;
+        s_prev_mod = prev_mod;
+        int nfr = s < nparse ? (nparse - s) / 68 : 0;
+        s_nframes = nfr < kScanFrames ? nfr : kScanFrames;
+      }
+    }
+    __syncthreads();
+    const int lock = s_lock;
+    if (lock < 0) break;
+    const int nframes = s_nframes, pm = s_prev_mod;
+    // ================= all warps: verdict of every frame that follows
+    for (int f = warp; f < nframes; f += kScanWarps) {
+      const int fs = lock + 68 * f;
       bool good = true;
       unsigned w[3];
-      if (s < cbase || s + 68 > cbase + kScanChunk) load_chunk(s);
-      int cm[3], cv[3];
-#pragma unroll
-      for (int q = 0; q < 3; q++) {
-        int i = lane + 32 * q;
-        cm[q] = i < 68 ? s_mod[s - cbase + i] : 0;
-        cv[q] = i < 68 ? s_vote[s - cbase + i] : 0;
-      }
 #pragma unroll
       for (int q = 0; q < 3; q++) {
         int i = lane + 32 * q;
         bool valid = i < 68;
-        if (valid && cm[q] != ((prev_mod + 1 + i) & 3)) good = false;
-        w[q] = __ballot_sync(0xffffffffu, valid && cv[q] < 0);
+        int cm = valid ? mod_in[fs + i] : 0;
+        int cv = valid ? vote[fs + i] : 0;
+        if (valid && cm != ((pm + 1 + i) & 3)) good = false;
+        w[q] = __ballot_sync(0xffffffffu, valid && cv < 0);
       }
       good = __all_sync(0xffffffffu, good);
       unsigned long long flo = (((unsigned long long)w[1] << 32) | w[0]) & ~1ull;  // entry 0: index 0 pushes 0 (:964-971)
@@ -451,85 +529,62 @@ __global__ void __launch_bounds__(32) demod_scan_kernel(int ntps, int nparse, in
         if (e == kEven || e == (kEven ^ kMask)) early = true;
       }
       bool match = ((flo & kMask) == kEven) || ((flo & kMask) == (kEven ^ kMask));
-      if (good && !early && match && tps_bch_ok_bits(flo, fhi, r_lo, r_hi, lane)) {
+      bool ok = good && !early && match && tps_bch_ok_bits(flo, fhi, r_lo, r_hi, lane);
+      if (lane == 0) {
+        s_ok[f] = ok ? 1 : 0;
+        s_fi[f] = (unsigned char)((((flo >> 23) & 1ull) << 1) | ((flo >> 24) & 1ull));
+      }
+    }
+    __syncthreads();
+    // ================= warp 0: walk the verdicts (superframe gating), first rejected frame ends the run
+    if (warp == 0) {
+      int f = 0, emit_from = -1;
+      const int out_base = n_out;
+      while (f < nframes && s_ok[f]) {
         bool emit = true;
         if (d_init == 0) {
           if ((frame_index & 3) == fi_start) { d_init = 1; sf_tag_at = n_out; }
           else emit = false;
         }
         if (emit) {
-          if (first_out < 0) first_out = s;
-#pragma unroll
-          for (int q = 0; q < 3; q++) {
-            int i = lane + 32 * q;
-            if (i < 68) { out_symidx[n_out + i] = i; out_src[n_out + i] = s + i; }
-          }
+          if (first_out < 0) first_out = lock + 68 * f;
+          if (emit_from < 0) emit_from = f;
           n_out += 68;
         }
-        frame_index = (int)((((flo >> 23) & 1ull) << 1) | ((flo >> 24) & 1ull));
-        cur_mod = (prev_mod + 68) & 3;
-        prev_mod = cur_mod;
-        s += 68;
-        continue;
+        frame_index = s_fi[f];
+        f++;
+      }
+      // every accepted frame: cur_mod = prev_mod = (prev_mod + 68) & 3, FIFO cleared, symbol_index 67 - all as they were
+      s = lock + 68 * f;
+      if (f > 0) cur_mod = prev_mod;       // (:684-688 over 68 symbols; 68 = 0 mod 4)
+      if (f < nframes) skip_fast = true;   // the frame at s is not a clean one: the per-symbol machine takes it
+      if (lane == 0) { s_nf = f; s_emit_from = emit_from; s_out_base = out_base; }
+    }
+    __syncthreads();
+    // ================= all threads: descriptors of the accepted, emitted frames
+    {
+      const int nf = s_nf, ef = s_emit_from, ob = s_out_base;
+      if (ef >= 0) {
+        const int count = (nf - ef) * 68;
+        for (int i = threadIdx.x; i < count; i += blockDim.x) {
+          out_symidx[ob + i] = i % 68;
+          out_src[ob + i] = lock + 68 * ef + i;
+        }
       }
     }
-    // ---- one symbol (parse_input :1188-1248 bookkeeping)
-    if (s < cbase || s >= cbase + kScanChunk) load_chunk(s);
-    int m_in = s_mod[s - cbase];
-    int v_in = s_vote[s - cbase];
-    int mod = m_in >= 0 ? m_in : cur_mod;
-    cur_mod = mod;
-    int diff = (mod - prev_mod + 4) & 3;  // :684-688
-    prev_mod = mod;
-    symbol_index += diff;                 // :1228
-    if (symbol_index >= 68) symbol_index -= 68;
-    int sym_out = symbol_index, frame_out = frame_index;
-    bool cond = !known || symbol_index != 0;
-    unsigned long long bitv = cond ? (v_in >= 0 ? 0ull : 1ull) : 0ull;
-    for (int d = 0; d < diff; d++) {      // :957-972: pop front, push back
-      lo = (lo >> 1) | ((unsigned long long)(hi & 1u) << 63);
-      hi = (hi >> 1) | ((unsigned)bitv << 3);
-    }
-    bool even = (lo & kMask) == kEven, odd = (lo & kMask) == (kEven ^ kMask);
-    int end_frame = 0;
-    if (even || odd) {
-      if (tps_bch_ok_bits(lo, hi, r_lo, r_hi, lane)) {
-        frame_index = (int)((((lo >> 23) & 1ull) << 1) | ((lo >> 24) & 1ull));
-        known = 1;
-        end_frame = 1;
-      } else {
-        known = 0;
-      }
-      lo = 0;
-      hi = 0;
-    }
-    if (end_frame) symbol_index = 67;     // :1240-1241
-    // block level (demod_reference_signals_impl.cc:118-143)
-    bool emit = true;
-    if (d_init == 0) {
-      if (sym_out == 0 && (frame_out & 3) == fi_start) {
-        d_init = 1;
-        sf_tag_at = n_out;
-      } else {
-        emit = false;
-      }
-    }
-    if (emit) {
-      if (first_out < 0) first_out = s;
-      if (lane == 0) { out_symidx[n_out] = sym_out; out_src[n_out] = s; }
-      n_out++;
-    }
-    s++;
+    __syncthreads();
   }
-  if (lane == 0) {
-    st->symbol_index = symbol_index; st->known = known; st->frame_index = frame_index; st->prev_mod = prev_mod;
-    st->mod = cur_mod; st->d_init = d_init;
-    for (int i = 0; i < 64; i++) st->fifo[i] = (unsigned char)((lo >> i) & 1ull);
-    for (int i = 64; i < 68; i++) st->fifo[i] = (unsigned char)((hi >> (i - 64)) & 1u);
-    st->first_out = first_out; st->n_out = n_out; st->sf_tag_at = sf_tag_at;
+  if (warp == 0) {
+    if (lane == 0) {
+      st->symbol_index = symbol_index; st->known = known; st->frame_index = frame_index; st->prev_mod = prev_mod;
+      st->mod = cur_mod; st->d_init = d_init;
+      for (int i = 0; i < 64; i++) st->fifo[i] = (unsigned char)((lo >> i) & 1ull);
+      for (int i = 64; i < 68; i++) st->fifo[i] = (unsigned char)((hi >> (i - 64)) & 1u);
+      st->first_out = first_out; st->n_out = n_out; st->sf_tag_at = sf_tag_at;
+    }
+    if (nparse > 0)
+      for (int k = lane; k < ntps; k += 32) st->prev_tps[k] = tpsval[(long long)(nparse - 1) * ntps + k];
   }
-  if (nparse > 0)
-    for (int k = lane; k < ntps; k += 32) st->prev_tps[k] = tpsval[(long long)(nparse - 1) * ntps + k];
 }
 
 int demod_run(const ModeDev &md, const DemapTable *demap, const float2 *X, int nparse, DemodBuffers b, DemodState *d_state,
@@ -556,7 +611,7 @@ int demod_run(const ModeDev &md, const DemapTable *demap, const float2 *X, int n
   }
   demod_vote_kernel<<<(nparse + 127) / 128, 128, 0, st>>>(md.ntps, nparse, b.tpsval, d_state, b.vote);
   DVBT_CUDA_TRY(cudaGetLastError());
-  demod_scan_kernel<<<1, 32, 0, st>>>(md.ntps, nparse, fi_start, sync_start_at0, b.modidx, b.vote, b.tpsval, d_state, b.out_symidx, b.out_src);
+  demod_scan_kernel<<<1, 32 * kScanWarps, 0, st>>>(md.ntps, nparse, fi_start, sync_start_at0, b.modidx, b.vote, b.tpsval, d_state, b.out_symidx, b.out_src);
   DVBT_CUDA_TRY(cudaGetLastError());
   count_launch(4);
   return 0;
