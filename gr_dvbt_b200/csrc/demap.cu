@@ -45,6 +45,39 @@ int make_demap_table(int constellation, int hierarchy, float gain, DemapTable *t
     t->pts[val] = make_float2(g * (float)(sign0 * xval), g * (float)(sign1 * yval));
   }
   t->size = size;
+  // per-axis view (see demap_cell_near): levels g * n in ascending order and the index bits each one stands for
+  t->g = g;
+  t->alpha = alpha;
+  t->inv_step = 1.0f / (2.0f * g);
+  t->bx = t->by = 0;
+  t->near_ok = g > 0.f ? 1 : 0;
+  {
+    const int H = m / 2, L = 1 << H, half = L / 2;
+    for (int a = 0; a < L; a++) {
+      int ix = 0, iy = 0;
+      for (int j = 0; j < H; j++) {
+        int bit = (a >> (H - 1 - j)) & 1;
+        ix |= bit << (m - 1 - 2 * j);
+        iy |= bit << (m - 2 - 2 * j);
+      }
+      int kx = -1, ky = -1;
+      for (int k = 0; k < L; k++) {
+        int n = k >= half ? alpha + 2 * (k - half) : -(alpha + 2 * (half - 1 - k));
+        float lv = g * (float)n;
+        if (lv == t->pts[ix].x) kx = k;
+        if (lv == t->pts[iy].y) ky = k;
+      }
+      if (kx < 0 || ky < 0) { t->near_ok = 0; break; }
+      t->bx |= (unsigned long long)ix << (8 * kx);
+      t->by |= (unsigned long long)iy << (8 * ky);
+    }
+    // every point must be the product of its two axis levels (separable constellation)
+    for (int i = 0; i < size && t->near_ok; i++) {
+      int xm = 0, ym = 0;
+      for (int j = 0; j < H; j++) { xm |= 1 << (m - 1 - 2 * j); ym |= 1 << (m - 2 - 2 * j); }
+      if (t->pts[i].x != t->pts[i & xm].x || t->pts[i].y != t->pts[i & ym].y) t->near_ok = 0;
+    }
+  }
   return 0;
 }
 

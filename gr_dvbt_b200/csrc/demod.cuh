@@ -8,6 +8,12 @@ namespace dvbt {
 struct DemapTable {
   float2 pts[64];
   int size;
+  // per-axis view for demap_cell_near: the 2^(m/2) levels of an axis are g * n, n = ..., -(alpha+2), -alpha,
+  // alpha, alpha+2, ... (dvbt_demap_impl.cc:98-159); level k (ascending) contributes the index bits
+  // (bx >> 8k) & 0xff on the I axis, (by >> 8k) & 0xff on the Q axis.  near_ok = 0 disables the shortcut.
+  float g, inv_step;
+  int alpha, near_ok;
+  unsigned long long bx, by;
 };
 int make_demap_table(int constellation, int hierarchy, float gain, DemapTable *t);
 
@@ -77,7 +83,43 @@ __device__ __forceinline__ uint8_t demap_cell_exact(const DemapTable &t, float2 
   return (uint8_t)min_index;
 }
 
+// Nearest-level shortcut in front of demap_cell_exact (same result, a third of the operations).  Along one
+// axis the squared distance fl(fl(v - level)^2) is unimodal in the (sorted) level index, because rounding is
+// monotone.  Guess the nearest level of each axis by division, compute its squared distance c and those of
+// its two neighbours l, r, and V = fl(cx + cy).  If fl(lx + cy), fl(rx + cy), fl(cx + ly), fl(cx + ry) are
+// all > V, then cx and cy are the strict per-axis minima and every other point of the constellation is at a
+// distance >= one of those four sums > V: the reference's scan (first strictly smallest distance) returns
+// exactly the guessed point.  Anything else - a tie, a guess off by one, Inf/NaN - goes to demap_cell_exact.
+template <int M>
+__device__ __forceinline__ uint8_t demap_cell_near(const DemapTable &t, float2 v) {
+  constexpr int L = 1 << (M / 2), HALF = L / 2;
+  auto level = [&](int k) {
+    int n = k >= HALF ? t.alpha + 2 * (k - HALF) : -(t.alpha + 2 * (HALF - 1 - k));
+    return __fmul_rn(t.g, (float)n);
+  };
+  auto sq = [&](float a, int k) {
+    float d = __fsub_rn(a, level(k));
+    return __fmul_rn(d, d);
+  };
+  int gx = __float2int_rd(v.x * t.inv_step) + HALF, gy = __float2int_rd(v.y * t.inv_step) + HALF;
+  gx = min(max(gx, 0), L - 1);
+  gy = min(max(gy, 0), L - 1);
+  const float inf = __int_as_float(0x7f800000);
+  float cx = sq(v.x, gx), cy = sq(v.y, gy);
+  float lx = gx > 0 ? sq(v.x, gx - 1) : inf, rx = gx < L - 1 ? sq(v.x, gx + 1) : inf;
+  float ly = gy > 0 ? sq(v.y, gy - 1) : inf, ry = gy < L - 1 ? sq(v.y, gy + 1) : inf;
+  float V = __fadd_rn(cx, cy);
+  bool ok = (__fadd_rn(lx, cy) > V) & (__fadd_rn(rx, cy) > V) & (__fadd_rn(cx, ly) > V) & (__fadd_rn(cx, ry) > V);
+  if (ok) return (uint8_t)(((t.bx >> (8 * gx)) | (t.by >> (8 * gy))) & 0xffull);
+  return demap_cell_exact<M>(t, v);
+}
+
 __device__ __forceinline__ uint8_t demap_cell_any(const DemapTable &t, float2 v) {
+  if (t.near_ok) {
+    if (t.size == 64) return demap_cell_near<6>(t, v);
+    if (t.size == 16) return demap_cell_near<4>(t, v);
+    return demap_cell_near<2>(t, v);
+  }
   if (t.size == 64) return demap_cell_exact<6>(t, v);
   if (t.size == 16) return demap_cell_exact<4>(t, v);
   return demap_cell_exact<2>(t, v);

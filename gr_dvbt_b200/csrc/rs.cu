@@ -216,16 +216,28 @@ __global__ void __launch_bounds__(kTilePk) rs_decode_kernel(const uint8_t *__res
     const long long src0 = p0 * kPktIn - halo;             // multiple of 4
     const int nwords = (np * kPktIn + halo) / 4;
     uint32_t *raw32 = reinterpret_cast<uint32_t *>(s_raw);
-    for (int i = t; i < nwords; i += blockDim.x) {
-      long long pos = src0 + 4LL * i;
-      uint32_t v = 0;
-      if (pos >= 0 && pos + 4 <= total) {
-        v = *reinterpret_cast<const uint32_t *>(in + pos);
-      } else {
-        for (int b = 0; b < 4; b++)
-          if (pos + b >= 0 && pos + b < total) v |= (uint32_t)in[pos + b] << (8 * b);
+    // eight loads in flight per thread (a load-then-store loop waits one full memory latency per word)
+    for (int i0 = t; i0 < nwords; i0 += 8 * kTilePk) {
+      uint32_t v[8];
+#pragma unroll
+      for (int u = 0; u < 8; u++) {
+        int i = i0 + u * kTilePk;
+        long long pos = src0 + 4LL * i;
+        v[u] = 0;
+        if (i < nwords) {
+          if (pos >= 0 && pos + 4 <= total) {
+            v[u] = __ldg(reinterpret_cast<const uint32_t *>(in + pos));
+          } else {
+            for (int b = 0; b < 4; b++)
+              if (pos + b >= 0 && pos + b < total) v[u] |= (uint32_t)in[pos + b] << (8 * b);
+          }
+        }
       }
-      raw32[i] = v;
+#pragma unroll
+      for (int u = 0; u < 8; u++) {
+        int i = i0 + u * kTilePk;
+        if (i < nwords) raw32[i] = v[u];
+      }
     }
   }
   __syncthreads();

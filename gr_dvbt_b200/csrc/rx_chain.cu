@@ -153,24 +153,36 @@ __global__ void __launch_bounds__(256) rx_inner_codes_kernel(InnerMap im, uint32
   while (inner_bits_before<RATE>(8 * jlo) < lo) jlo++;
   while (inner_bits_before<RATE>(8 * jhi) < hi) jhi++;
   if (jhi > nbt) jhi = nbt;
-  for (long long j = jlo + threadIdx.x; j < jhi; j += blockDim.x) {
-    long long t = 8 * j;
-    int ph = (int)(t % K);
-    int local = (int)(inner_bits_before<RATE>(t) - lo);
-    uint32_t w0 = s_words[local >> 5], w1 = s_words[(local >> 5) + 1];
-    uint32_t win = __funnelshift_r(w0, w1, local & 31);
-    uint32_t wv;
-    switch (ph) {
-      case 0: wv = inner_code_from_window<RATE, 0>(win); break;
-      case 1: wv = inner_code_from_window<RATE, 1 % K>(win); break;
-      case 2: wv = inner_code_from_window<RATE, 2 % K>(win); break;
-      case 3: wv = inner_code_from_window<RATE, 3 % K>(win); break;
-      case 4: wv = inner_code_from_window<RATE, 4 % K>(win); break;
-      case 5: wv = inner_code_from_window<RATE, 5 % K>(win); break;
-      default: wv = inner_code_from_window<RATE, 6 % K>(win); break;
+  // The puncturing phase of byte time j is (8 j) mod K.  Byte times are taken class by class (j = jlo + c + K i):
+  // within a class the phase is the same for every thread (no divergence in the switch below) and the first
+  // bit advances by exactly 8 N per i (no division).  The step codes go through shared memory (the bit
+  // bytes are dead after packing) so that the global stores are contiguous.
+  uint32_t *s_codes = reinterpret_cast<uint32_t *>(s_bit);
+  const int nj = jhi > jlo ? (int)(jhi - jlo) : 0;
+  for (int c = 0; c < K; c++) {
+    const long long t0 = 8 * (jlo + c);
+    const int ph = (int)(t0 % K);
+    const int local0 = (int)(inner_bits_before<RATE>(t0) - lo);
+    const int cnt = (nj - c + K - 1) / K;
+#define INNER_CLASS(PH)                                                              \
+    for (int i = threadIdx.x; i < cnt; i += blockDim.x) {                            \
+      int local = local0 + 8 * N * i;                                                \
+      uint32_t win = __funnelshift_r(s_words[local >> 5], s_words[(local >> 5) + 1], local & 31); \
+      s_codes[c + K * i] = inner_code_from_window<RATE, (PH) % K>(win);              \
     }
-    codes[j] = wv;
+    switch (ph) {
+      case 0: INNER_CLASS(0) break;
+      case 1: INNER_CLASS(1) break;
+      case 2: INNER_CLASS(2) break;
+      case 3: INNER_CLASS(3) break;
+      case 4: INNER_CLASS(4) break;
+      case 5: INNER_CLASS(5) break;
+      default: INNER_CLASS(6) break;
+    }
+#undef INNER_CLASS
   }
+  __syncthreads();
+  for (int i = threadIdx.x; i < nj; i += blockDim.x) codes[jlo + i] = s_codes[i];
 }
 
 // test tap: the bit_inner_deinterleaver output bytes (what the reference feeds its Viterbi block)
