@@ -371,6 +371,13 @@ __global__ void __launch_bounds__(256) acq_compose_kernel(AcqParams p, int nsym,
                                                           AcqWalk *walk) {
   extern __shared__ __align__(16) unsigned char s_maps[];  // [nchunks][kNS] (+ slack)
   __shared__ __align__(16) unsigned char s_rows[kRowsCap * kNS + 32];  // `next` rows of the chunk being walked symbol by symbol
+  // everything else a speculation split can ask for, staged together with the rows when the chunk is short
+  // (one round trip to L2 instead of four dependent ones): best2 / avg2 / lambda / avg1 rows of the chunk
+  constexpr int kExt = kChunk;
+  __shared__ __align__(16) unsigned char s_best[kExt * kNS + 32];
+  __shared__ __align__(16) unsigned char s_avg2[kExt * kNS * 4 + 32];
+  __shared__ __align__(16) unsigned char s_lam[kExt * kCand * 4 + 32];
+  __shared__ __align__(16) unsigned char s_avg1[kExt * kNC * 4 + 32];
   __shared__ float s_win[16];
   const int t = threadIdx.x;
   const long long cyc0 = clock64();
@@ -381,6 +388,22 @@ __global__ void __launch_bounds__(256) acq_compose_kernel(AcqParams p, int nsym,
   const int lane = t;
   int n = 0, code = 0, n_found = 0, n_override = 0, nseg = 0, avg_from = -1, n_staged = 0;
   int st_n0 = 0, st_n1 = 0, st_shift = 0;   // symbols whose rows are in s_rows
+  int ex_n0 = 0, ex_n1 = 0, sh_best = 0, sh_avg2 = 0, sh_lam = 0, sh_avg1 = 0;   // symbols covered by the extended staging
+  auto ld_best2 = [&](int nn, int state) -> int {
+    return (nn >= ex_n0 && nn < ex_n1) ? (int)(signed char)s_best[sh_best + (nn - ex_n0) * kNS + state] : (int)best2[(long long)nn * kNS + state];
+  };
+  auto ld_avg2 = [&](int nn, int state) -> float {
+    return (nn >= ex_n0 && nn < ex_n1) ? *reinterpret_cast<const float *>(s_avg2 + sh_avg2 + ((nn - ex_n0) * kNS + state) * 4)
+                                       : avg2[(long long)nn * kNS + state];
+  };
+  auto ld_lambda = [&](int nn, int cand) -> float {
+    return (nn >= ex_n0 && nn < ex_n1) ? *reinterpret_cast<const float *>(s_lam + sh_lam + ((nn - ex_n0) * kCand + cand) * 4)
+                                       : lambda[(long long)nn * kCand + cand];
+  };
+  auto ld_avg1 = [&](int nn, int c) -> float {
+    return (nn >= ex_n0 && nn < ex_n1) ? *reinterpret_cast<const float *>(s_avg1 + sh_avg1 + ((nn - ex_n0) * kNC + c) * 4)
+                                       : avg1[(long long)nn * kNC + c];
+  };
   unsigned char st = (unsigned char)start_state;
   float avg = avg_first;
   int k = 0, kstart = 0;                    // chunk of symbol n and its first symbol
@@ -403,6 +426,16 @@ __global__ void __launch_bounds__(256) acq_compose_kernel(AcqParams p, int nsym,
       __syncwarp();
       st_shift = stage_bytes16(next, (long long)n * kNS, (nend - n) * kNS, s_rows, lane, 32);
       st_n0 = n; st_n1 = nend;
+      if (nend - n <= kExt) {
+        const int r = nend - n;
+        sh_best = stage_bytes16(reinterpret_cast<const unsigned char *>(best2), (long long)n * kNS, r * kNS, s_best, lane, 32);
+        sh_avg2 = stage_bytes16(reinterpret_cast<const unsigned char *>(avg2), (long long)n * kNS * 4, r * kNS * 4, s_avg2, lane, 32);
+        sh_lam = stage_bytes16(reinterpret_cast<const unsigned char *>(lambda), (long long)n * kCand * 4, r * kCand * 4, s_lam, lane, 32);
+        sh_avg1 = stage_bytes16(reinterpret_cast<const unsigned char *>(avg1), (long long)n * kNC * 4, r * kNC * 4, s_avg1, lane, 32);
+        ex_n0 = n; ex_n1 = nend;
+      } else {
+        ex_n0 = ex_n1 = 0;
+      }
       n_staged++;
       __syncwarp();
     }
@@ -426,7 +459,7 @@ __global__ void __launch_bounds__(256) acq_compose_kernel(AcqParams p, int nsym,
     // stop code at symbol n, reached in state st_at
     if (nx == kLost) {
       if (n > seg0) { if (lane == 0) segs[nseg] = make_int4(seg0, n, seg_st, 0); nseg++; }
-      avg = avg2[(long long)n * kNS + st_at];  // the missed symbol still updated the average
+      avg = ld_avg2(n, st_at);  // the missed symbol still updated the average
       avg_from = -1;
       n_found = n;
       code = kLost;
@@ -436,8 +469,8 @@ __global__ void __launch_bounds__(256) acq_compose_kernel(AcqParams p, int nsym,
     if (lane == 0) segs[nseg] = make_int4(seg0, n + 1, seg_st, 0);
     nseg++;
     int c = st_at / kND;
-    int best = best2[(long long)n * kNS + st_at];
-    avg = avg2[(long long)n * kNS + st_at];
+    int best = ld_best2(n, st_at);
+    avg = ld_avg2(n, st_at);
     avg_from = -1;
     n++;
     n_found = n;
@@ -447,7 +480,7 @@ __global__ void __launch_bounds__(256) acq_compose_kernel(AcqParams p, int nsym,
     while (n < nsym && !code) {
       if (cn < 0 || cn >= kNC) { code = kOff; break; }
       __syncwarp();
-      if (lane < 16) s_win[lane] = lambda[(long long)n * kCand + cn + lane];
+      if (lane < 16) s_win[lane] = ld_lambda(n, cn + lane);
       __syncwarp();
       int b2;
       float a2 = avg;
@@ -461,7 +494,7 @@ __global__ void __launch_bounds__(256) acq_compose_kernel(AcqParams p, int nsym,
       n_found = n;
       int c2 = cn + b2 - 8, d2 = 8 - b2;
       if (c2 < 0 || c2 >= kNC) { code = kOff; break; }
-      bool ok = d2 >= -2 && d2 <= 2 && __float_as_uint(avg) == __float_as_uint(avg1[(long long)(n - 1) * kNC + cn]);
+      bool ok = d2 >= -2 && d2 <= 2 && __float_as_uint(avg) == __float_as_uint(ld_avg1(n - 1, cn));
       if (ok) { st = (unsigned char)(c2 * kND + d2 + 2); break; }   // tables valid again from symbol n
       cn = c2;
     }

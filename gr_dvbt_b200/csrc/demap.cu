@@ -50,7 +50,7 @@ int make_demap_table(int constellation, int hierarchy, float gain, DemapTable *t
   t->alpha = alpha;
   t->inv_step = 1.0f / (2.0f * g);
   t->bx = t->by = 0;
-  t->near_ok = g > 0.f ? 1 : 0;
+  t->near_ok = (g > 0.f && alpha == 1) ? 1 : 0;   // the shortcut's level arithmetic assumes the uniform grid
   {
     const int H = m / 2, L = 1 << H, half = L / 2;
     for (int a = 0; a < L; a++) {

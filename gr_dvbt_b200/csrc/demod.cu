@@ -375,9 +375,9 @@ __device__ bool tps_bch_ok_bits(unsigned long long lo, unsigned hi, unsigned r_l
 
 constexpr int kScanChunk = 4096;     // symbols staged in shared memory for the symbol-by-symbol path
 constexpr int kScanFrames = 2048;    // frames validated per parallel round
-constexpr int kScanWarps = 8;
+constexpr int kScanWarps = 32;
 
-// The sequential bookkeeping of parse_input (:1188-1248) and of the block (:108-149) as one block of 8 warps.
+// The sequential bookkeeping of parse_input (:1188-1248) and of the block (:108-149) as one block of 32 warps.
 //   * Warp 0 runs the reference's per-symbol state machine (all lanes the same scalar code, lane 0 writes)
 //     until the receiver is in lock at a frame boundary: known, symbol_index == 67, FIFO just cleared.
 //   * From there on a whole 68-symbol frame is equivalent to 68 single steps provided every symbol advances

@@ -92,25 +92,25 @@ __device__ __forceinline__ uint8_t demap_cell_exact(const DemapTable &t, float2 
 // exactly the guessed point.  Anything else - a tie, a guess off by one, Inf/NaN - goes to demap_cell_exact.
 template <int M>
 __device__ __forceinline__ uint8_t demap_cell_near(const DemapTable &t, float2 v) {
-  constexpr int L = 1 << (M / 2), HALF = L / 2;
-  auto level = [&](int k) {
-    int n = k >= HALF ? t.alpha + 2 * (k - HALF) : -(t.alpha + 2 * (HALF - 1 - k));
-    return __fmul_rn(t.g, (float)n);
-  };
-  auto sq = [&](float a, int k) {
-    float d = __fsub_rn(a, level(k));
+  constexpr float TOP = (float)((1 << (M / 2)) - 1);   // the levels of an axis are g * n, n = -TOP, ..., -1, 1, ..., TOP (alpha = 1)
+  const float inf = __int_as_float(0x7f800000);
+  // nearest level as a float odd integer (no int<->float conversions on the hot path), its two neighbours
+  float nx = fminf(fmaxf(fmaf(2.0f, floorf(v.x * t.inv_step), 1.0f), -TOP), TOP);
+  float ny = fminf(fmaxf(fmaf(2.0f, floorf(v.y * t.inv_step), 1.0f), -TOP), TOP);
+  auto sq = [&](float a, float n) {
+    float d = __fsub_rn(a, __fmul_rn(t.g, n));   // the level exactly as make_demap_table rounds it
     return __fmul_rn(d, d);
   };
-  int gx = __float2int_rd(v.x * t.inv_step) + HALF, gy = __float2int_rd(v.y * t.inv_step) + HALF;
-  gx = min(max(gx, 0), L - 1);
-  gy = min(max(gy, 0), L - 1);
-  const float inf = __int_as_float(0x7f800000);
-  float cx = sq(v.x, gx), cy = sq(v.y, gy);
-  float lx = gx > 0 ? sq(v.x, gx - 1) : inf, rx = gx < L - 1 ? sq(v.x, gx + 1) : inf;
-  float ly = gy > 0 ? sq(v.y, gy - 1) : inf, ry = gy < L - 1 ? sq(v.y, gy + 1) : inf;
+  float cx = sq(v.x, nx), cy = sq(v.y, ny);
+  float lx = nx > -TOP ? sq(v.x, nx - 2.0f) : inf, rx = nx < TOP ? sq(v.x, nx + 2.0f) : inf;
+  float ly = ny > -TOP ? sq(v.y, ny - 2.0f) : inf, ry = ny < TOP ? sq(v.y, ny + 2.0f) : inf;
   float V = __fadd_rn(cx, cy);
   bool ok = (__fadd_rn(lx, cy) > V) & (__fadd_rn(rx, cy) > V) & (__fadd_rn(cx, ly) > V) & (__fadd_rn(cx, ry) > V);
-  if (ok) return (uint8_t)(((t.bx >> (8 * gx)) | (t.by >> (8 * gy))) & 0xffull);
+  if (ok) {
+    int kx = __float2int_rn((nx + TOP) * 0.5f), ky = __float2int_rn((ny + TOP) * 0.5f);   // level number 0 .. 2^(M/2)-1, ascending
+    unsigned bx = __byte_perm((unsigned)t.bx, (unsigned)(t.bx >> 32), kx), by = __byte_perm((unsigned)t.by, (unsigned)(t.by >> 32), ky);
+    return (uint8_t)((bx | by) & 0xffu);
+  }
   return demap_cell_exact<M>(t, v);
 }
 
