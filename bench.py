@@ -470,7 +470,7 @@ def main():
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--workload", default="rx", choices=["rx", "viterbi"])
     ap.add_argument("--mbit", type=float, default=640.0, help="decoded Mbit per GPU per step (viterbi workload)")
-    ap.add_argument("--tiles", type=int, default=16, help="rx workload: capture = tiles x 4 superframes (1088 OFDM symbols each)")
+    ap.add_argument("--tiles", type=int, default=20, help="rx workload: capture = tiles x 4 superframes (1088 OFDM symbols each); 20 tiles = 50.3 M samples (SURVEY §8d config 2: >= 50 M)")
     a = ap.parse_args()
     a.warmup = max(a.warmup, 3)
     metric = "RX Msamples/s (baseband) & Viterbi Mbit/s @1/2/4/8 GPU vs SSE2 CPU; HBM GB/s %peak"

@@ -359,7 +359,20 @@ __device__ __forceinline__ int stage_bytes16(const unsigned char *__restrict__ s
   int n16 = (shift + bytes + 15) >> 4;
   const uint4 *s4 = reinterpret_cast<const uint4 *>(src + a0);
   uint4 *d4 = reinterpret_cast<uint4 *>(dst);
-  for (int i = lane; i < n16; i += nlanes) d4[i] = s4[i];
+  // eight loads in flight per lane: a load-then-store loop would wait one full memory latency per 16 bytes
+  for (int i0 = lane; i0 < n16; i0 += 8 * nlanes) {
+    uint4 v[8];
+#pragma unroll
+    for (int u = 0; u < 8; u++) {
+      int i = i0 + u * nlanes;
+      v[u] = i < n16 ? s4[i] : make_uint4(0u, 0u, 0u, 0u);
+    }
+#pragma unroll
+    for (int u = 0; u < 8; u++) {
+      int i = i0 + u * nlanes;
+      if (i < n16) d4[i] = v[u];
+    }
+  }
   return shift;
 }
 

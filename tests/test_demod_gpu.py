@@ -73,3 +73,34 @@ def test_streaming_calls_carry_state():
     Y = np.concatenate(outs)
     assert np.array_equal(Y.view(np.uint32), Yref.view(np.uint32))
     assert sorted(tags) == sorted(tags_ref)
+
+
+@needs_ref
+@pytest.mark.parametrize("damage", ["tps_frame", "dropped_symbol", "zero_symbols"])
+def test_lock_loss_in_the_middle_matches_reference(damage):
+    """The scan kernel validates whole TPS frames in parallel once in lock; a frame that fails (corrupted TPS
+    carriers -> BCH error, a missing symbol -> scattered-pilot phase jump, blank symbols) must hand control
+    back to the per-symbol machine exactly where the reference loses and regains lock."""
+    import gr_dvbt_b200 as g
+    from dvbt_testlib import tx_frequency_domain, channel
+    con, cr, tm = R.QAM16, R.C1_2, R.T2k
+    N, P, _, _ = R.mode_dims(tm)
+    X = channel(tx_frequency_domain(con, cr, tm, 68 * 11 + 20, 5)["X"]).copy()
+    rng = np.random.default_rng(9)
+    if damage == "tps_frame":
+        # flip the sign of a dozen symbols' worth of TPS carriers inside frame 6 (DBPSK votes flip -> BCH fails)
+        tps = np.array([34, 50, 209, 346, 413, 569, 595, 688, 790, 901, 1073, 1219, 1262, 1286, 1469, 1594, 1687])
+        zl = (N - 1705 + 1) // 2
+        for s in range(68 * 6 + 20, 68 * 6 + 32, 2):
+            X[s, zl + tps] *= -1
+    elif damage == "dropped_symbol":
+        X = np.delete(X, 68 * 5 + 33, axis=0)
+    else:
+        X[68 * 7 + 10: 68 * 7 + 13] = 0
+    Yref, tags_ref = R.rx_demod(X, con, cr, tm)
+    d = g.demod_reference_signals(8, N, P, con, g.NH, cr, cr, g.G1_32, tm, 0, 0)
+    Y, cons, tags = d.general_work(X, tags=[(0, "sync_start", 1)])
+    assert cons == X.shape[0] - 1
+    assert sorted(tags) == sorted(tags_ref), (len(tags), len(tags_ref))
+    assert Y.shape == Yref.shape and Y.shape[0] > 68 * 3
+    assert np.array_equal(Y.view(np.uint32), Yref.view(np.uint32))
