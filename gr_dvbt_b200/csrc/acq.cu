@@ -316,7 +316,8 @@ struct AcqWalk {
   int n_override;     // symbols whose speculation did not hold and that were re-run sequentially
   int avg_from;       // symbol whose table entry holds the final average (acq_walk_kernel fetches it), or -1
   int n_seg, n_staged;            // table segments; chunks walked symbol by symbol (trace)
-  long long cyc_maps, cyc_serial;  // trace: clock64 deltas of the three phases (DVBT_B200_ACQ_TRACE)
+  long long cyc_maps, cyc_serial;
+  long long cyc_fin[6];   // trace: phase boundaries of acq_finish_kernel  // trace: clock64 deltas of the three phases (DVBT_B200_ACQ_TRACE)
 };
 
 // chunk maps: one warp per chunk of `per_thread` symbols, lane = start state (85 states, 3 rounds)
@@ -397,7 +398,29 @@ __global__ void __launch_bounds__(256) acq_compose_kernel(AcqParams p, int nsym,
   stage_bytes16(maps, 0, nchunks * kNS, s_maps, t, blockDim.x);
   __syncthreads();
   const long long cyc1 = clock64();
-  if (t >= 32) return;
+  // Warps 1..7 serve warp 0: when the chain needs table rows they are fetched by all 256 threads (one round trip
+  // to L2 for ~20 KB instead of one per 4 KB).  Protocol: warp 0 posts (first symbol, end) and everybody meets at
+  // a block barrier, copies, meets again; end < 0 dismisses the helpers.
+  __shared__ int s_cmd_n0, s_cmd_n1;
+  auto stage_chunk = [&](int n0, int n1) {
+    const int r = n1 - n0;
+    stage_bytes16(next, (long long)n0 * kNS, r * kNS, s_rows, t, blockDim.x);
+    if (r <= kExt) {
+      stage_bytes16(reinterpret_cast<const unsigned char *>(best2), (long long)n0 * kNS, r * kNS, s_best, t, blockDim.x);
+      stage_bytes16(reinterpret_cast<const unsigned char *>(avg2), (long long)n0 * kNS * 4, r * kNS * 4, s_avg2, t, blockDim.x);
+      stage_bytes16(reinterpret_cast<const unsigned char *>(lambda), (long long)n0 * kCand * 4, r * kCand * 4, s_lam, t, blockDim.x);
+      stage_bytes16(reinterpret_cast<const unsigned char *>(avg1), (long long)n0 * kNC * 4, r * kNC * 4, s_avg1, t, blockDim.x);
+    }
+  };
+  if (t >= 32) {
+    for (;;) {
+      __syncthreads();
+      const int n1 = s_cmd_n1;
+      if (n1 < 0) return;
+      stage_chunk(s_cmd_n0, n1);
+      __syncthreads();
+    }
+  }
   const int lane = t;
   int n = 0, code = 0, n_found = 0, n_override = 0, nseg = 0, avg_from = -1, n_staged = 0;
   int st_n0 = 0, st_n1 = 0, st_shift = 0;   // symbols whose rows are in s_rows
@@ -436,15 +459,18 @@ __global__ void __launch_bounds__(256) acq_compose_kernel(AcqParams p, int nsym,
     // table walk inside chunk k until its end or a stop code; the rows are staged in shared memory first
     if (nend - n > kRowsCap) nend = n + kRowsCap;
     if (n < st_n0 || nend > st_n1) {
-      __syncwarp();
-      st_shift = stage_bytes16(next, (long long)n * kNS, (nend - n) * kNS, s_rows, lane, 32);
+      if (lane == 0) { s_cmd_n0 = n; s_cmd_n1 = nend; }
+      __syncthreads();
+      stage_chunk(n, nend);
+      __syncthreads();
+      auto shift_of = [](long long off) { return (int)(off & 15LL); };
+      st_shift = shift_of((long long)n * kNS);
       st_n0 = n; st_n1 = nend;
       if (nend - n <= kExt) {
-        const int r = nend - n;
-        sh_best = stage_bytes16(reinterpret_cast<const unsigned char *>(best2), (long long)n * kNS, r * kNS, s_best, lane, 32);
-        sh_avg2 = stage_bytes16(reinterpret_cast<const unsigned char *>(avg2), (long long)n * kNS * 4, r * kNS * 4, s_avg2, lane, 32);
-        sh_lam = stage_bytes16(reinterpret_cast<const unsigned char *>(lambda), (long long)n * kCand * 4, r * kCand * 4, s_lam, lane, 32);
-        sh_avg1 = stage_bytes16(reinterpret_cast<const unsigned char *>(avg1), (long long)n * kNC * 4, r * kNC * 4, s_avg1, lane, 32);
+        sh_best = shift_of((long long)n * kNS);
+        sh_avg2 = shift_of((long long)n * kNS * 4);
+        sh_lam = shift_of((long long)n * kCand * 4);
+        sh_avg1 = shift_of((long long)n * kNC * 4);
         ex_n0 = n; ex_n1 = nend;
       } else {
         ex_n0 = ex_n1 = 0;
@@ -524,7 +550,9 @@ __global__ void __launch_bounds__(256) acq_compose_kernel(AcqParams p, int nsym,
     walk->n_staged = n_staged;
     walk->cyc_maps = cyc1 - cyc0;
     walk->cyc_serial = clock64() - cyc1;
+    s_cmd_n1 = -1;   // dismiss the helper warps
   }
+  __syncthreads();
 }
 
 // One warp per table segment: the segment's `next` rows are staged with one coalesced round trip, lane 0
@@ -584,6 +612,8 @@ __global__ void __launch_bounds__(1024) acq_finish_kernel(AcqParams p, long long
   const int t = threadIdx.x, nt = blockDim.x;
   const int total = p.N + p.cp;
   const double twopi = 2.0 * M_PI;
+  long long *trace = const_cast<AcqWalk *>(walk)->cyc_fin;
+  const long long tr0 = clock64();
   const int nf = walk->n_found;
   const int per = (nf + nt - 1) / nt;
   const int a = min(nf, t * per), b = min(nf, a + per);
@@ -598,6 +628,7 @@ __global__ void __launch_bounds__(1024) acq_finish_kernel(AcqParams p, long long
   }
   s_has[t] = has; s_val[t] = val;
   __syncthreads();
+  if (t == 0) trace[0] = clock64() - tr0;
   if (t == 0) {  // exclusive "last switched value" scan
     // serial on purpose (the order defines the result); unrolled in groups of 16 so that the shared-memory
     // loads are issued ahead of the dependent chain
@@ -619,6 +650,7 @@ __global__ void __launch_bounds__(1024) acq_finish_kernel(AcqParams p, long long
   __syncthreads();
   const double inc_end = s_sum[0];
   __syncthreads();
+  if (t == 0) trace[1] = clock64() - tr0;
   // (b) phase advance of my run
   double inc = s_val[t], sum = 0.0;
   for (int m = a; m < b; m++) {
@@ -630,6 +662,7 @@ __global__ void __launch_bounds__(1024) acq_finish_kernel(AcqParams p, long long
   }
   s_sum[t] = sum;
   __syncthreads();
+  if (t == 0) trace[2] = clock64() - tr0;
   if (t == 0) {
     double cur = st->phase;
     for (int i0 = 0; i0 < nt; i0 += 16) {
@@ -658,6 +691,7 @@ __global__ void __launch_bounds__(1024) acq_finish_kernel(AcqParams p, long long
     st->n_single += code ? 1 : 0;
     st->n_seq += walk->n_override;
     st->consumed = (long long)nf * total;
+    trace[3] = clock64() - tr0;
   }
   __syncthreads();
   // (c) descriptors
@@ -675,6 +709,8 @@ __global__ void __launch_bounds__(1024) acq_finish_kernel(AcqParams p, long long
     ph += ok ? swm * inc + (total - swm) * pendm : total * inc;
     if (ok) inc = pendm;
   }
+  __syncthreads();
+  if (t == 0) trace[4] = clock64() - tr0;
 }
 
 // out[n][j] = (-1)^j * expj(phase_j) * x[first + j].  A thread takes four samples 256 apart: four independent
@@ -814,8 +850,9 @@ int acq_run(dvbt_b200_acq *h, const float2 *x, long long n, float2 *d_out, long 
     if (getenv("DVBT_B200_ACQ_TRACE")) {
       AcqWalk wk;
       if (cudaMemcpy(&wk, h->d_eps.p, sizeof wk, cudaMemcpyDeviceToHost) == cudaSuccess)
-        fprintf(stderr, "acq batch: nsym %lld found %d code %d override %d segments %d staged %d cycles maps %lld serial %lld\n", nsym,
-                wk.n_found, wk.code, wk.n_override, wk.n_seg, wk.n_staged, wk.cyc_maps, wk.cyc_serial);
+        fprintf(stderr, "acq batch: nsym %lld found %d code %d override %d segments %d staged %d cycles maps %lld serial %lld | finish %lld %lld %lld %lld %lld\n", nsym,
+                wk.n_found, wk.code, wk.n_override, wk.n_seg, wk.n_staged, wk.cyc_maps, wk.cyc_serial, wk.cyc_fin[0], wk.cyc_fin[1],
+                wk.cyc_fin[2], wk.cyc_fin[3], wk.cyc_fin[4]);
     }
     if (hs->n_out > 0) {
       dim3 grid((p.N + 256 * kDerotPer - 1) / (256 * kDerotPer), hs->n_out);

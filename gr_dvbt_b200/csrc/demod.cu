@@ -310,11 +310,22 @@ __global__ void __launch_bounds__(256) demod_equalise_kernel(ModeDev md, const _
     s_slope[k] = cdiv(csub(s_gain[nextp[k]], s_gain[k]), make_float2(11.0f, 0.0f));
   }
   __syncthreads();
-  for (int k = threadIdx.x; k < md.K; k += blockDim.x) {
-    if (!(kind[k] & 1)) {
-      int k0 = prevp[k];
-      float2 step = cmul(s_slope[k0], make_float2((float)(k - k0), 0.0f));
-      s_gain[k] = cadd(s_gain[k0], step);
+  // (loops below: the table loads of four iterations are issued together, then the dependent work)
+  for (int kb = threadIdx.x; kb < md.K; kb += 4 * blockDim.x) {
+    int kd[4], k0[4];
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      int k = kb + u * blockDim.x;
+      kd[u] = k < md.K ? kind[k] : 1;
+      k0[u] = k < md.K ? prevp[k] : 0;
+    }
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      int k = kb + u * blockDim.x;
+      if (!(kd[u] & 1)) {
+        float2 step = cmul(s_slope[k0[u]], make_float2((float)(k - k0[u]), 0.0f));
+        s_gain[k] = cadd(s_gain[k0[u]], step);
+      }
     }
   }
   __syncthreads();
@@ -323,11 +334,25 @@ __global__ void __launch_bounds__(256) demod_equalise_kernel(ModeDev md, const _
     tpsval[(long long)s * md.ntps + threadIdx.x] = cmul(cmul(rot, x[k]), s_gain[k]);
   }
   const short *pay = md.payload + r * md.P;
-  for (int i = threadIdx.x; i < md.P; i += blockDim.x) {  // :1104-1113
-    int k = pay[i];
-    float2 y = cmul(cmul(rot, x[k]), s_gain[k]);
-    if (Y) Y[(long long)s * md.P + i] = y;
-    if (do_demap) dm[(long long)s * md.P + i] = demap_cell_any(dt, y);
+  for (int ib = threadIdx.x; ib < md.P; ib += 3 * blockDim.x) {  // :1104-1113
+    int k[3];
+    float2 xv[3];
+#pragma unroll
+    for (int u = 0; u < 3; u++) {
+      int i = ib + u * blockDim.x;
+      k[u] = i < md.P ? pay[i] : 0;
+    }
+#pragma unroll
+    for (int u = 0; u < 3; u++) xv[u] = x[k[u]];
+#pragma unroll
+    for (int u = 0; u < 3; u++) {
+      int i = ib + u * blockDim.x;
+      if (i < md.P) {
+        float2 y = cmul(cmul(rot, xv[u]), s_gain[k[u]]);
+        if (Y) Y[(long long)s * md.P + i] = y;
+        if (do_demap) dm[(long long)s * md.P + i] = demap_cell_any(dt, y);
+      }
+    }
   }
 }
 

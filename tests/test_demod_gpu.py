@@ -103,4 +103,9 @@ def test_lock_loss_in_the_middle_matches_reference(damage):
     assert cons == X.shape[0] - 1
     assert sorted(tags) == sorted(tags_ref), (len(tags), len(tags_ref))
     assert Y.shape == Yref.shape and Y.shape[0] > 68 * 3
-    assert np.array_equal(Y.view(np.uint32), Yref.view(np.uint32))
+    # blank symbols equalise to NaN (0 * inf); x86 and CUDA produce different NaN bit patterns, so NaNs only have
+    # to sit in the same places - every other cell is compared bit for bit
+    a, b = Y.view(np.float32), Yref.view(np.float32)
+    nan_a, nan_b = np.isnan(a), np.isnan(b)
+    assert np.array_equal(nan_a, nan_b), (int(nan_a.sum()), int(nan_b.sum()))
+    assert np.array_equal(a.view(np.uint32)[~nan_a], b.view(np.uint32)[~nan_b])
