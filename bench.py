@@ -382,7 +382,7 @@ def ncu_traffic(workload, tiles):
         return None, None
     if not t or (workload == "rx" and t.get("tiles") != tiles):
         return None, None
-    return float(t["dram_bytes_read"] + t["dram_bytes_write"]), t.get("source")
+    return float(t["dram_bytes_read"] + t["dram_bytes_write"]), {k: t[k] for k in ("source", "alu_pipe_active_pct", "issue_active_pct", "dram_throughput_pct") if k in t}
 
 
 def cpu_worker(args):
@@ -608,10 +608,12 @@ def main():
                                     "sample": "150 x 768-blocks (%.2f Mbit) of the same rate-7/8 m=6 stream, one thread" % cb_bits}
         traffic, traffic_src = ncu_traffic(a.workload, a.tiles)
         line["roofline"] = {"kernel": "vit_acs_kernel", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                            "traffic": traffic, "traffic_source": traffic_src, "algorithmic_bytes": w.alg_bytes,
+                            "traffic": traffic, "ncu": traffic_src, "algorithmic_bytes": w.alg_bytes,
                             "peak_source": peak_src, "avg_launch_ms": kms,
-                            "note": "dominant kernel of the step; ALU/shared-memory bound (64 add-compare-select per decoded bit), so the HBM "
-                                    "fraction is small by nature; ACS rate = %.1f T state-updates/s" % (info_bits * 64 / (kms / 1e3) / 1e12)}
+                            "note": "dominant kernel of the step; bound by the integer ALU pipe (64 add-compare-select per decoded bit as byte-SWAR "
+                                    "LOP3/PRMT/IADD3; ncu: see the `ncu` object), so the HBM fraction is small by nature; DRAM traffic above the "
+                                    "algorithmic bytes is the survivor-row write-through to the global ring (deliberate: it frees shared memory "
+                                    "for 3x the resident warps); ACS rate = %.1f T state-updates/s" % (info_bits * 64 / (kms / 1e3) / 1e12)}
         print(json.dumps(line))
     if WORLD > 1:
         dist.destroy_process_group()

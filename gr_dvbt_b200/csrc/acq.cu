@@ -402,14 +402,43 @@ __global__ void __launch_bounds__(256) acq_compose_kernel(AcqParams p, int nsym,
   // to L2 for ~20 KB instead of one per 4 KB).  Protocol: warp 0 posts (first symbol, end) and everybody meets at
   // a block barrier, copies, meets again; end < 0 dismisses the helpers.
   __shared__ int s_cmd_n0, s_cmd_n1;
+  // all five tables in ONE batch of loads: the 16-byte units of the five source ranges are numbered consecutively
+  // and dealt to the threads, every thread issues its (<= 8) loads before the first store
   auto stage_chunk = [&](int n0, int n1) {
     const int r = n1 - n0;
-    stage_bytes16(next, (long long)n0 * kNS, r * kNS, s_rows, t, blockDim.x);
-    if (r <= kExt) {
-      stage_bytes16(reinterpret_cast<const unsigned char *>(best2), (long long)n0 * kNS, r * kNS, s_best, t, blockDim.x);
-      stage_bytes16(reinterpret_cast<const unsigned char *>(avg2), (long long)n0 * kNS * 4, r * kNS * 4, s_avg2, t, blockDim.x);
-      stage_bytes16(reinterpret_cast<const unsigned char *>(lambda), (long long)n0 * kCand * 4, r * kCand * 4, s_lam, t, blockDim.x);
-      stage_bytes16(reinterpret_cast<const unsigned char *>(avg1), (long long)n0 * kNC * 4, r * kNC * 4, s_avg1, t, blockDim.x);
+    const unsigned char *srcs[5] = {next, reinterpret_cast<const unsigned char *>(best2), reinterpret_cast<const unsigned char *>(avg2),
+                                    reinterpret_cast<const unsigned char *>(lambda), reinterpret_cast<const unsigned char *>(avg1)};
+    unsigned char *dsts[5] = {s_rows, s_best, s_avg2, s_lam, s_avg1};
+    const int rowb[5] = {kNS, kNS, kNS * 4, kCand * 4, kNC * 4};
+    const int ntab = r <= kExt ? 5 : 1;
+    long long a0[5];
+    int first[6];
+    first[0] = 0;
+#pragma unroll
+    for (int q = 0; q < 5; q++) {
+      long long off = (long long)n0 * rowb[q];
+      a0[q] = off & ~15LL;
+      int n16 = q < ntab ? (int)((off - a0[q]) + (long long)r * rowb[q] + 15) >> 4 : 0;
+      first[q + 1] = first[q] + n16;
+    }
+    const int total = first[5];
+    for (int u0 = t; u0 < total; u0 += 8 * blockDim.x) {
+      uint4 v[8];
+      int tab[8], idx[8];
+#pragma unroll
+      for (int k = 0; k < 8; k++) {
+        int u = u0 + k * blockDim.x;
+        int q = 0;
+#pragma unroll
+        for (int qq = 1; qq < 5; qq++) q += (u >= first[qq]) ? 1 : 0;
+        tab[k] = q; idx[k] = u - first[q];
+        v[k] = u < total ? reinterpret_cast<const uint4 *>(srcs[q] + a0[q])[idx[k]] : make_uint4(0u, 0u, 0u, 0u);
+      }
+#pragma unroll
+      for (int k = 0; k < 8; k++) {
+        int u = u0 + k * blockDim.x;
+        if (u < total) reinterpret_cast<uint4 *>(dsts[tab[k]])[idx[k]] = v[k];
+      }
     }
   };
   if (t >= 32) {
@@ -589,42 +618,69 @@ __global__ void __launch_bounds__(128) acq_walk_kernel(int rows_cap, const signe
   }
 }
 
-// per-symbol quantities that need no ordering: peak position and the phase increment it leaves behind
+// per-symbol quantities that need no ordering: peak position and the carrier-offset estimate it leaves behind
 __global__ void acq_post_kernel(AcqParams p, int c0, const float2 *__restrict__ gamma, const unsigned char *__restrict__ c_of,
                                 const signed char *__restrict__ best_of, const AcqWalk *walk, int *__restrict__ peak_of,
-                                double *__restrict__ e_of) {
+                                float *__restrict__ eps_of) {
   int m = blockIdx.x * blockDim.x + threadIdx.x;
   if (m >= walk->n_found) return;
   int c = c_of[m], best = best_of[m];
   peak_of[m] = c0 - kD + c + best;                         // cp_start_before - 8 + best
   float2 g = gamma[(long long)m * kCand + c + best];
-  e_of[m] = (-1.0 / (double)p.N) * (double)atan2f(g.y, g.x);  // d_nextphaseinc left by symbol m (:311)
+  eps_of[m] = atan2f(g.y, g.x);                            // d_nextphaseinc left by symbol m = -eps / N (:311)
 }
 
-// phase schedule (:285-312): one block, every thread owns a run of consecutive symbols.  Two small
-// scans over the per-thread summaries give (a) the increment in force when a run starts ("value switched
-// to by the last earlier symbol that switched", :287-288) and (b) the phase at the start of the run.
+// phase schedule (:285-312): one block.  (peak, eps) of all symbols are staged in shared memory with coalesced
+// loads (kFinishMax symbols at most: the host splits longer batches).  Every thread owns a run of consecutive
+// symbols; two small scans over the per-thread summaries give (a) the increment in force when a run starts
+// ("value switched to by the last earlier symbol that switched", :287-288) and (b) the phase at the start of the
+// run.  The output descriptors are then written one symbol per thread (coalesced), each thread re-adding its
+// run's increments from the run start in the same order as the run owner did.
+constexpr int kFinishMax = 24576;
+
 __global__ void __launch_bounds__(1024) acq_finish_kernel(AcqParams p, long long base, const int *__restrict__ peak_of,
-                                                          const double *__restrict__ e_of, const AcqWalk *walk, AcqState *st,
+                                                          const float *__restrict__ eps_of, const AcqWalk *walk, AcqState *st,
                                                           SymOut *__restrict__ out) {
+  extern __shared__ __align__(16) unsigned char s_fin[];   // [nf] int peak, [nf] float eps
   __shared__ double s_val[1024], s_sum[1024];
   __shared__ unsigned char s_has[1024];
   const int t = threadIdx.x, nt = blockDim.x;
   const int total = p.N + p.cp;
-  const double twopi = 2.0 * M_PI;
+  const double twopi = 2.0 * M_PI, minus_inv_n = -1.0 / (double)p.N;
   long long *trace = const_cast<AcqWalk *>(walk)->cyc_fin;
   const long long tr0 = clock64();
   const int nf = walk->n_found;
+  int *s_pk = reinterpret_cast<int *>(s_fin);
+  float *s_ep = reinterpret_cast<float *>(s_fin) + nf;
+  for (int m0 = t; m0 < nf; m0 += 8 * nt) {
+    int pk[8];
+    float ep[8];
+#pragma unroll
+    for (int u = 0; u < 8; u++) {
+      int m = m0 + u * nt;
+      pk[u] = m < nf ? peak_of[m] : 0;
+      ep[u] = m < nf ? eps_of[m] : 0.f;
+    }
+#pragma unroll
+    for (int u = 0; u < 8; u++) {
+      int m = m0 + u * nt;
+      if (m < nf) { s_pk[m] = pk[u]; s_ep[m] = ep[u]; }
+    }
+  }
   const int per = (nf + nt - 1) / nt;
   const int a = min(nf, t * per), b = min(nf, a + per);
   const double inc_init = st->phaseinc, pend_init = st->nextphaseinc;
   const int nextpos_init = st->nextpos;
+  __syncthreads();
+  // symbol m switches the increment at sample swm (if inside the symbol) to pend
+  auto swm_of = [&](int m) { return m == 0 ? nextpos_init : s_pk[m - 1] - total; };
+  auto pend_of = [&](int m) { return m == 0 ? pend_init : minus_inv_n * (double)s_ep[m - 1]; };
   // (a) does a symbol of my run switch the increment, and to what
   bool has = false;
   double val = 0.0;
   for (int m = a; m < b; m++) {
-    int swm = m == 0 ? nextpos_init : peak_of[m - 1] - total;
-    if (swm >= 0 && swm < total) { has = true; val = m == 0 ? pend_init : e_of[m - 1]; }
+    int swm = swm_of(m);
+    if (swm >= 0 && swm < total) { has = true; val = pend_of(m); }
   }
   s_has[t] = has; s_val[t] = val;
   __syncthreads();
@@ -644,7 +700,6 @@ __global__ void __launch_bounds__(1024) acq_finish_kernel(AcqParams p, long long
         if (hs[u]) cur = v[u];
       }
     }
-    s_val[nt - 1 + 0] = s_val[nt - 1];
     s_sum[0] = cur;  // increment in force after the last symbol (stashed, re-read below)
   }
   __syncthreads();
@@ -654,8 +709,8 @@ __global__ void __launch_bounds__(1024) acq_finish_kernel(AcqParams p, long long
   // (b) phase advance of my run
   double inc = s_val[t], sum = 0.0;
   for (int m = a; m < b; m++) {
-    int swm = m == 0 ? nextpos_init : peak_of[m - 1] - total;
-    double pendm = m == 0 ? pend_init : e_of[m - 1];
+    int swm = swm_of(m);
+    double pendm = pend_of(m);
     bool ok = swm >= 0 && swm < total;
     sum += ok ? swm * inc + (total - swm) * pendm : total * inc;
     if (ok) inc = pendm;
@@ -672,7 +727,6 @@ __global__ void __launch_bounds__(1024) acq_finish_kernel(AcqParams p, long long
 #pragma unroll
       for (int u = 0; u < 16; u++) { s_sum[i0 + u] = cur; cur += v[u]; }
     }
-    s_val[nt - 1] = s_val[nt - 1];
     // end state
     int code = walk->code;
     double ph = cur;
@@ -681,9 +735,9 @@ __global__ void __launch_bounds__(1024) acq_finish_kernel(AcqParams p, long long
     st->avg = walk->avg;
     st->phase = (float)ph;
     st->phaseinc = inc_end;
-    st->nextphaseinc = nf > 0 ? e_of[nf - 1] : pend_init;
-    st->nextpos = nf > 0 ? peak_of[nf - 1] - total : nextpos_init;
-    if (nf > 0) st->cp_start = peak_of[nf - 1];
+    st->nextphaseinc = nf > 0 ? minus_inv_n * (double)s_ep[nf - 1] : pend_init;
+    st->nextpos = nf > 0 ? s_pk[nf - 1] - total : nextpos_init;
+    if (nf > 0) st->cp_start = s_pk[nf - 1];
     st->n_out = nf;
     st->lost_at = code == kLost ? nf : (code ? -2 - nf : -1);   // -2-nf: stopped after nf symbols without a miss
     st->fallback = code == kSplit ? 1 : 0;
@@ -694,20 +748,24 @@ __global__ void __launch_bounds__(1024) acq_finish_kernel(AcqParams p, long long
     trace[3] = clock64() - tr0;
   }
   __syncthreads();
-  // (c) descriptors
-  inc = s_val[t];
-  double ph = s_sum[t];
-  for (int m = a; m < b; m++) {
-    int swm = m == 0 ? nextpos_init : peak_of[m - 1] - total;
-    double pendm = m == 0 ? pend_init : e_of[m - 1];
+  // (c) descriptors, one symbol per thread
+  for (int m = t; m < nf; m += nt) {
+    const int r = m / per;
+    double inc_m = s_val[r], ph = s_sum[r];
+    for (int mm = r * per; mm < m; mm++) {
+      int swm = swm_of(mm);
+      double pendm = pend_of(mm);
+      bool ok = swm >= 0 && swm < total;
+      ph += ok ? swm * inc_m + (total - swm) * pendm : total * inc_m;
+      if (ok) inc_m = pendm;
+    }
+    int swm = swm_of(m);
     bool ok = swm >= 0 && swm < total;
     SymOut so;
-    so.first = base + (long long)m * total + peak_of[m] - p.N + 1;
+    so.first = base + (long long)m * total + s_pk[m] - p.N + 1;
     so.phase0 = ph - twopi * rint(ph / twopi);
-    so.inc0 = inc; so.inc1 = pendm; so.switch_at = ok ? swm : total;
+    so.inc0 = inc_m; so.inc1 = pend_of(m); so.switch_at = ok ? swm : total;
     out[m] = so;
-    ph += ok ? swm * inc + (total - swm) * pendm : total * inc;
-    if (ok) inc = pendm;
   }
   __syncthreads();
   if (t == 0) trace[4] = clock64() - tr0;
@@ -798,6 +856,8 @@ int acq_run(dvbt_b200_acq *h, const float2 *x, long long n, float2 *d_out, long 
     long long nsym = avail < 0 ? 0 : avail / total + 1;
     if (nsym > out_capacity_syms - produced) nsym = out_capacity_syms - produced;
     if (nsym <= 0) break;
+    bool capped = false;   // the finish kernel stages one batch in shared memory: longer inputs go in several batches
+    if (nsym > kFinishMax) { nsym = kFinishMax; capped = true; }
     if ((rc = h->d_lambda.reserve((size_t)nsym * kCand * 4)) || (rc = h->d_gamma.reserve((size_t)nsym * kCand * 8)) ||
         (rc = h->d_avg1.reserve((size_t)nsym * 4)) || (rc = h->d_avg2.reserve((size_t)nsym * 4)) ||
         (rc = h->d_peak.reserve((size_t)nsym * 4)) || (rc = h->d_sym.reserve((size_t)nsym * sizeof(SymOut))))
@@ -837,10 +897,11 @@ int acq_run(dvbt_b200_acq *h, const float2 *x, long long n, float2 *d_out, long 
                                                                h->d_flag.as<unsigned char>(), h->d_seg.as<int4>(), h->d_cof.as<unsigned char>(),
                                                                h->d_bof.as<signed char>(), d_walk);
       }
-      if ((rc = h->d_peakof.reserve((size_t)nsym * 4)) || (rc = h->d_eof.reserve((size_t)nsym * 8))) return rc;
+      if ((rc = h->d_peakof.reserve((size_t)nsym * 4)) || (rc = h->d_eof.reserve((size_t)nsym * 4))) return rc;
       acq_post_kernel<<<(unsigned)((nsym + 127) / 128), 128, 0, st>>>(p, c0, h->d_gamma.as<float2>(), h->d_cof.as<unsigned char>(),
-                                                                     h->d_bof.as<signed char>(), d_walk, h->d_peakof.as<int>(), h->d_eof.as<double>());
-      acq_finish_kernel<<<1, 1024, 0, st>>>(p, pos, h->d_peakof.as<int>(), h->d_eof.as<double>(), d_walk, h->d_state.as<AcqState>(),
+                                                                     h->d_bof.as<signed char>(), d_walk, h->d_peakof.as<int>(), h->d_eof.as<float>());
+      DVBT_CUDA_TRY(cudaFuncSetAttribute(acq_finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFinishMax * 8));
+      acq_finish_kernel<<<1, 1024, (size_t)nsym * 8, st>>>(p, pos, h->d_peakof.as<int>(), h->d_eof.as<float>(), d_walk, h->d_state.as<AcqState>(),
                                           h->d_sym.as<SymOut>());
       count_launch(8);
       DVBT_CUDA_TRY(cudaGetLastError());
@@ -875,6 +936,7 @@ int acq_run(dvbt_b200_acq *h, const float2 *x, long long n, float2 *d_out, long 
       continue;
     }
     if (hs->lost_at <= -2) continue;  // stopped early (table re-centre or speculation split): carry on from the true state
+    if (capped) continue;             // batch limit: the rest of the input follows from the state just written
     break;
   }
   if (do_fft && produced > 0) {

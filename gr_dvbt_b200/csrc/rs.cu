@@ -36,71 +36,79 @@ struct GfTables {
   __device__ __forceinline__ int mulpow(int a, int p) const { return a ? exp2[(log[a] + p) % 255] : 0; }
 };
 
-// Berlekamp-Massey exactly as reed_solomon.cc:307-364 (no erasures).  Returns deg(sigma).
-__device__ int rs_locator(const GfTables &gf, const uint8_t *syn, uint8_t *sigma) {
-  uint8_t b[2 * kT + 1], T[2 * kT + 1];
-  for (int i = 0; i <= 2 * kT; i++) { sigma[i] = 0; }
-  sigma[0] = 1;
-  for (int i = 0; i <= 2 * kT; i++) b[i] = sigma[i];
-  int r = 0, el = 0;
-  while (++r <= 2 * kT) {
-    int discr = 0;
-    for (int i = 0; i < r; i++) discr ^= gf.mul(sigma[i], syn[r - i - 1]);
+// Berlekamp-Massey exactly as reed_solomon.cc:307-364 (no erasures), one polynomial coefficient per lane:
+// lane i holds sigma[i] and b[i] (i <= 16).  Every step of the reference's loop is element-wise in i except the
+// discrepancy (a warp XOR-reduce) and the shift b[i] = b[i-1] (a shuffle), so the 16 iterations are the same
+// arithmetic in the same order.  Writes sigma[0..16] to shared memory; returns deg(sigma) in every lane.
+__device__ int rs_locator_warp(const GfTables &gf, const uint8_t *syn, uint8_t *sigma_out, int lane) {
+  int sg = lane == 0 ? 1 : 0, bb = sg;
+  int el = 0;
+  for (int r = 1; r <= 2 * kT; r++) {
+    int term = (lane < r && lane <= 2 * kT) ? gf.mul(sg, syn[r - lane - 1]) : 0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) term ^= __shfl_xor_sync(0xffffffffu, term, o);
+    const int discr = term;
+    int b_up = __shfl_up_sync(0xffffffffu, bb, 1);   // b[i-1]
+    if (lane == 0) b_up = 0;
     if (discr == 0) {
-      for (int i = 2 * kT; i > 0; i--) b[i] = b[i - 1];
-      b[0] = 0;
+      bb = b_up;
     } else {
-      T[0] = sigma[0];
-      for (int i = 0; i < 2 * kT; i++) T[i + 1] = (uint8_t)(sigma[i + 1] ^ gf.mul(discr, b[i]));
+      int T = lane == 0 ? sg : (sg ^ gf.mul(discr, b_up));   // T[0] = sigma[0]; T[i+1] = sigma[i+1] ^ discr * b[i]
       if (2 * el <= r - 1) {
         el = r - el;
-        for (int i = 0; i <= 2 * kT; i++) b[i] = (uint8_t)gf.div(sigma[i], discr);
+        bb = gf.div(sg, discr);
       } else {
-        for (int i = 2 * kT; i > 0; i--) b[i] = b[i - 1];
-        b[0] = 0;
+        bb = b_up;
       }
-      for (int i = 0; i <= 2 * kT; i++) sigma[i] = T[i];
+      sg = T;
     }
+    if (lane > 2 * kT) { sg = 0; bb = 0; }
   }
-  int deg = 0;
-  for (int i = 0; i <= 2 * kT; i++)
-    if (sigma[i]) deg = i;
-  return deg;
+  if (lane <= 2 * kT) sigma_out[lane] = (uint8_t)sg;
+  unsigned nz = __ballot_sync(0xffffffffu, lane <= 2 * kT && sg != 0);
+  return nz ? 31 - __clz(nz) : 0;
 }
 
-// Forney, reed_solomon.cc:417-486.  root[]/loc[] hold no_roots == deg_sigma entries.
-// pkt = the 204 received bytes (positions 51..254 of the code word).
-__device__ int rs_forney(const GfTables &gf, const uint8_t *syn, const uint8_t *sigma, int deg_sigma,
-                         const uint8_t *root, const uint8_t *loc, int no_roots, uint8_t *pkt) {
-  uint8_t omega[2 * kT + 1];
-  int deg_omega = 0;
-  for (int i = 0; i < 2 * kT; i++) {
-    int tmp = 0;
-    int j = (deg_sigma < i) ? deg_sigma : i;
-    for (; j >= 0; j--) tmp ^= gf.mul(syn[i - j], sigma[j]);
-    if (tmp) deg_omega = i;
-    omega[i] = (uint8_t)tmp;
+// Forney, reed_solomon.cc:417-486, one root per lane.  root[]/loc[] hold no_roots == deg_sigma entries.
+// pkt = the 204 received bytes (positions 51..254 of the code word).  The reference walks the roots from the
+// last to the first and stops at the first null denominator, keeping the corrections made so far (:470-479):
+// here every lane evaluates its root, the highest root index with a null denominator is found by ballot, and
+// only the roots above it are applied.
+__device__ int rs_forney_warp(const GfTables &gf, const uint8_t *syn, const uint8_t *sigma, int deg_sigma, const uint8_t *root,
+                              const uint8_t *loc, int no_roots, uint8_t *pkt, uint8_t *omega, int lane) {
+  // omega[i] = sum_j syn[i-j] sigma[j], i < 2t: lane i
+  int om = 0;
+  if (lane < 2 * kT) {
+    int j = deg_sigma < lane ? deg_sigma : lane;
+    for (; j >= 0; j--) om ^= gf.mul(syn[lane - j], sigma[j]);
+    omega[lane] = (uint8_t)om;
   }
-  for (int j = no_roots - 1; j >= 0; j--) {
-    int rt = root[j];
+  unsigned onz = __ballot_sync(0xffffffffu, lane < 2 * kT && om != 0);
+  const int deg_omega = onz ? 31 - __clz(onz) : 0;
+  __syncwarp();
+  int den = 1, err = 0, pos = 0;
+  if (lane < no_roots) {
+    int rt = root[lane];
     int num1 = 0;
     for (int i = deg_omega; i >= 0; i--) num1 ^= gf.mulpow(omega[i], i * rt);
     int num2 = gf.exp2[(kN - rt) % kN];
-    int den = 0;
+    den = 0;
     int deg_max = deg_sigma < 2 * kT - 1 ? deg_sigma : 2 * kT - 1;
     for (int i = 1; i <= deg_max; i += 2)
       if (sigma[i]) den ^= gf.exp2[(gf.log[sigma[i]] + (i - 1) * rt) % kN];
-    if (den == 0) return -1;  // :470-479, earlier corrections stay
-    int err = gf.div(gf.mul(num1, num2), den);
-    int pos = loc[j];
-    if (pos >= kS) pkt[pos - kS] ^= (uint8_t)err;  // positions < 51 are the discarded zero prefix
+    err = den ? gf.div(gf.mul(num1, num2), den) : 0;
+    pos = loc[lane];
   }
-  return no_roots;
+  unsigned zero_den = __ballot_sync(0xffffffffu, lane < no_roots && den == 0);
+  const int first_ok = zero_den ? 32 - __clz(zero_den) : 0;   // roots first_ok .. no_roots-1 are applied
+  if (lane < no_roots && lane >= first_ok && pos >= kS) pkt[pos - kS] ^= (uint8_t)err;  // positions < 51 are the discarded zero prefix
+  __syncwarp();
+  return zero_den ? -1 : no_roots;
 }
 
 // Syndromes, locator, Chien and Forney for one packet held in shared memory (204 bytes at `pkt`), by one
 // warp; returns the reference's per-packet result (0 clean, > 0 corrected symbols, -1 uncorrectable) in
-// every lane.  `work`: 80 bytes of per-warp scratch.
+// every lane.  `work`: 96 bytes of per-warp scratch.
 __device__ int rs_warp_decode(const GfTables &gf, uint8_t *pkt, uint8_t *work, int lane, int as_built) {
   uint8_t *syn = work, *sigma = syn + 16, *root = sigma + 17, *loc = root + 17, *misc = loc + 17;
   // ---- syndromes: byte j carries x^(203-j); lane takes j = lane, lane+32, ...
@@ -136,10 +144,10 @@ __device__ int rs_warp_decode(const GfTables &gf, uint8_t *pkt, uint8_t *work, i
     if (lane == 0) {
       uint32_t S[4] = {S0, S1, S2, S3};
       for (int i = 0; i < 16; i++) syn[i] = (uint8_t)(S[i >> 2] >> (8 * (i & 3)));
-      misc[0] = (uint8_t)rs_locator(gf, syn, sigma);
     }
     __syncwarp();
-    int deg = misc[0];
+    const int deg = rs_locator_warp(gf, syn, sigma, lane);
+    __syncwarp();
     // ---- Chien: q(i) = 1 + sum_j sigma[j] a^(j*i), i = 1..255 in increasing order
     int nroots = 0;
     for (int t = 0; t < 8; t++) {
@@ -156,18 +164,14 @@ __device__ int rs_warp_decode(const GfTables &gf, uint8_t *pkt, uint8_t *work, i
       nroots += __popc(hit);
     }
     __syncwarp();
-    if (lane == 0) {
-      if (nroots != deg) {
-        st = -1;  // uncorrectable: data untouched (:405-415)
-      } else {
-        // the reference's out-of-bounds omega[2t] = 0 lands on loc[0] with gcc 13.3
-        if (as_built) loc[0] = 0;
-        st = rs_forney(gf, syn, sigma, deg, root, loc, nroots, pkt);
-      }
-      misc[1] = (uint8_t)(st & 0xff);
+    if (nroots != deg) {
+      st = -1;  // uncorrectable: data untouched (:405-415)
+    } else {
+      // the reference's out-of-bounds omega[2t] = 0 lands on loc[0] with gcc 13.3
+      if (as_built && lane == 0) loc[0] = 0;
+      __syncwarp();
+      st = rs_forney_warp(gf, syn, sigma, deg, root, loc, nroots, pkt, misc, lane);
     }
-    __syncwarp();
-    st = (int)(int8_t)misc[1];
   }
   return st;
 }
@@ -200,7 +204,7 @@ __global__ void __launch_bounds__(kTilePk) rs_decode_kernel(const uint8_t *__res
   __shared__ __align__(16) uint8_t s_exp2[512];
   __shared__ __align__(16) uint8_t s_log[256];
   __shared__ __align__(16) uint32_t s_pkt[kTilePk / 32][52];
-  __shared__ uint8_t s_work[kTilePk / 32][80];
+  __shared__ uint8_t s_work[kTilePk / 32][96];
   __shared__ int s_dirty[kTilePk];
   __shared__ int s_ndirty;
   const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
