@@ -317,7 +317,8 @@ struct AcqWalk {
   int avg_from;       // symbol whose table entry holds the final average (acq_walk_kernel fetches it), or -1
   int n_seg, n_staged;            // table segments; chunks walked symbol by symbol (trace)
   long long cyc_maps, cyc_serial;
-  long long cyc_fin[6];   // trace: phase boundaries of acq_finish_kernel  // trace: clock64 deltas of the three phases (DVBT_B200_ACQ_TRACE)
+  long long cyc_fin[6];   // trace: phase boundaries of acq_finish_kernel
+  long long cyc_cmp[4];   // trace: compose chain - staging, table walks, detector re-runs, everything else  // trace: clock64 deltas of the three phases (DVBT_B200_ACQ_TRACE)
 };
 
 // chunk maps: one warp per chunk of `per_thread` symbols, lane = start state (85 states, 3 rounds)
@@ -472,6 +473,7 @@ __global__ void __launch_bounds__(256) acq_compose_kernel(AcqParams p, int nsym,
   unsigned char st = (unsigned char)start_state;
   float avg = avg_first;
   int k = 0, kstart = 0;                    // chunk of symbol n and its first symbol
+  long long c_stage = 0, c_walk = 0, c_over = 0;
   while (n < nsym && !code) {
     int nend = min(nsym, kstart + per_thread);
     if (n == kstart) {
@@ -488,10 +490,12 @@ __global__ void __launch_bounds__(256) acq_compose_kernel(AcqParams p, int nsym,
     // table walk inside chunk k until its end or a stop code; the rows are staged in shared memory first
     if (nend - n > kRowsCap) nend = n + kRowsCap;
     if (n < st_n0 || nend > st_n1) {
+      const long long cs0 = clock64();
       if (lane == 0) { s_cmd_n0 = n; s_cmd_n1 = nend; }
       __syncthreads();
       stage_chunk(n, nend);
       __syncthreads();
+      c_stage += clock64() - cs0;
       auto shift_of = [](long long off) { return (int)(off & 15LL); };
       st_shift = shift_of((long long)n * kNS);
       st_n0 = n; st_n1 = nend;
@@ -510,6 +514,7 @@ __global__ void __launch_bounds__(256) acq_compose_kernel(AcqParams p, int nsym,
     const unsigned char *rows = s_rows + st_shift - st_n0 * kNS;   // rows[n * kNS + state]
     int seg0 = n;
     unsigned char seg_st = st, nx = 0, st_at = st;
+    const long long cw0 = clock64();
     while (n < nend) {
       st_at = st;
       nx = rows[n * kNS + st];
@@ -517,6 +522,7 @@ __global__ void __launch_bounds__(256) acq_compose_kernel(AcqParams p, int nsym,
       st = nx;
       n++;
     }
+    c_walk += clock64() - cw0;
     if (n == nend) {  // reached the end of the staged rows without a stop
       if (lane == 0) segs[nseg] = make_int4(seg0, n, seg_st, 0);
       nseg++;
@@ -545,6 +551,7 @@ __global__ void __launch_bounds__(256) acq_compose_kernel(AcqParams p, int nsym,
     if (nx == kOff) { code = kOff; break; }
     // kSplit: the tables cannot be trusted for the next symbol; run the detector from the true average
     int cn = c + best - 8;
+    const long long co0 = clock64();
     while (n < nsym && !code) {
       if (cn < 0 || cn >= kNC) { code = kOff; break; }
       __syncwarp();
@@ -566,6 +573,7 @@ __global__ void __launch_bounds__(256) acq_compose_kernel(AcqParams p, int nsym,
       if (ok) { st = (unsigned char)(c2 * kND + d2 + 2); break; }   // tables valid again from symbol n
       cn = c2;
     }
+    c_over += clock64() - co0;
     k = n / per_thread;
     kstart = k * per_thread;
   }
@@ -579,6 +587,8 @@ __global__ void __launch_bounds__(256) acq_compose_kernel(AcqParams p, int nsym,
     walk->n_staged = n_staged;
     walk->cyc_maps = cyc1 - cyc0;
     walk->cyc_serial = clock64() - cyc1;
+    walk->cyc_cmp[0] = c_stage; walk->cyc_cmp[1] = c_walk; walk->cyc_cmp[2] = c_over;
+    walk->cyc_cmp[3] = walk->cyc_serial - c_stage - c_walk - c_over;
     s_cmd_n1 = -1;   // dismiss the helper warps
   }
   __syncthreads();
@@ -640,7 +650,7 @@ constexpr int kFinishMax = 24576;
 
 __global__ void __launch_bounds__(1024) acq_finish_kernel(AcqParams p, long long base, const int *__restrict__ peak_of,
                                                           const float *__restrict__ eps_of, const AcqWalk *walk, AcqState *st,
-                                                          SymOut *__restrict__ out) {
+                                                          double *__restrict__ run_start) {
   extern __shared__ __align__(16) unsigned char s_fin[];   // [nf] int peak, [nf] float eps
   __shared__ double s_val[1024], s_sum[1024];
   __shared__ unsigned char s_has[1024];
@@ -748,27 +758,42 @@ __global__ void __launch_bounds__(1024) acq_finish_kernel(AcqParams p, long long
     trace[3] = clock64() - tr0;
   }
   __syncthreads();
-  // (c) descriptors, one symbol per thread
-  for (int m = t; m < nf; m += nt) {
-    const int r = m / per;
-    double inc_m = s_val[r], ph = s_sum[r];
-    for (int mm = r * per; mm < m; mm++) {
-      int swm = swm_of(mm);
-      double pendm = pend_of(mm);
-      bool ok = swm >= 0 && swm < total;
-      ph += ok ? swm * inc_m + (total - swm) * pendm : total * inc_m;
-      if (ok) inc_m = pendm;
-    }
-    int swm = swm_of(m);
-    bool ok = swm >= 0 && swm < total;
-    SymOut so;
-    so.first = base + (long long)m * total + s_pk[m] - p.N + 1;
-    so.phase0 = ph - twopi * rint(ph / twopi);
-    so.inc0 = inc_m; so.inc1 = pend_of(m); so.switch_at = ok ? swm : total;
-    out[m] = so;
-  }
-  __syncthreads();
+  // run starts for acq_desc_kernel: increment in force and phase when run t begins
+  run_start[2 * t] = s_val[t];
+  run_start[2 * t + 1] = s_sum[t];
   if (t == 0) trace[4] = clock64() - tr0;
+}
+
+// (c) output descriptors, one symbol per thread over the whole GPU (the double-precision work of this step on a
+// single SM was the longest part of the phase schedule): each thread re-adds its run's increments from the run
+// start in the same order as the run owner did in acq_finish_kernel.
+__global__ void __launch_bounds__(128) acq_desc_kernel(AcqParams p, long long base, const int *__restrict__ peak_of,
+                                                       const float *__restrict__ eps_of, const AcqWalk *walk, int nextpos_init,
+                                                       double pend_init, const double *__restrict__ run_start, SymOut *__restrict__ out) {
+  const int nf = walk->n_found;
+  const int m = blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= nf) return;
+  const int total = p.N + p.cp;
+  const double twopi = 2.0 * M_PI, minus_inv_n = -1.0 / (double)p.N;
+  const int per = (nf + 1023) / 1024;
+  const int r = m / per;
+  auto swm_of = [&](int mm) { return mm == 0 ? nextpos_init : peak_of[mm - 1] - total; };
+  auto pend_of = [&](int mm) { return mm == 0 ? pend_init : minus_inv_n * (double)eps_of[mm - 1]; };
+  double inc_m = run_start[2 * r], ph = run_start[2 * r + 1];
+  for (int mm = r * per; mm < m; mm++) {
+    int swm = swm_of(mm);
+    double pendm = pend_of(mm);
+    bool ok = swm >= 0 && swm < total;
+    ph += ok ? swm * inc_m + (total - swm) * pendm : total * inc_m;
+    if (ok) inc_m = pendm;
+  }
+  int swm = swm_of(m);
+  bool ok = swm >= 0 && swm < total;
+  SymOut so;
+  so.first = base + (long long)m * total + peak_of[m] - p.N + 1;
+  so.phase0 = ph - twopi * rint(ph / twopi);
+  so.inc0 = inc_m; so.inc1 = pend_of(m); so.switch_at = ok ? swm : total;
+  out[m] = so;
 }
 
 // out[n][j] = (-1)^j * expj(phase_j) * x[first + j].  A thread takes four samples 256 apart: four independent
@@ -811,7 +836,7 @@ struct dvbt_b200_acq {
   bool own_stream = true;
   cufftHandle plan = 0;
   int plan_batch = 0;
-  dvbt::DevBuf d_x, d_state, h_state, d_lambda, d_gamma, d_avg1, d_avg2, d_peak, d_sym, d_out, d_il, d_ig, d_eps, d_flag, d_maps, d_cof, d_bof, d_peakof, d_eof, d_seg;
+  dvbt::DevBuf d_x, d_state, h_state, d_lambda, d_gamma, d_avg1, d_avg2, d_peak, d_sym, d_out, d_il, d_ig, d_eps, d_flag, d_maps, d_cof, d_bof, d_peakof, d_eof, d_seg, d_runs;
 };
 
 namespace dvbt {
@@ -900,10 +925,14 @@ int acq_run(dvbt_b200_acq *h, const float2 *x, long long n, float2 *d_out, long 
       if ((rc = h->d_peakof.reserve((size_t)nsym * 4)) || (rc = h->d_eof.reserve((size_t)nsym * 4))) return rc;
       acq_post_kernel<<<(unsigned)((nsym + 127) / 128), 128, 0, st>>>(p, c0, h->d_gamma.as<float2>(), h->d_cof.as<unsigned char>(),
                                                                      h->d_bof.as<signed char>(), d_walk, h->d_peakof.as<int>(), h->d_eof.as<float>());
+      if ((rc = h->d_runs.reserve(1024 * 2 * 8))) return rc;
       DVBT_CUDA_TRY(cudaFuncSetAttribute(acq_finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFinishMax * 8));
       acq_finish_kernel<<<1, 1024, (size_t)nsym * 8, st>>>(p, pos, h->d_peakof.as<int>(), h->d_eof.as<float>(), d_walk, h->d_state.as<AcqState>(),
-                                          h->d_sym.as<SymOut>());
-      count_launch(8);
+                                                         h->d_runs.as<double>());
+      // the schedule's initial values are the host's copy of the state this batch started from
+      acq_desc_kernel<<<(unsigned)((nsym + 127) / 128), 128, 0, st>>>(p, pos, h->d_peakof.as<int>(), h->d_eof.as<float>(), d_walk, hs->nextpos,
+                                                                     hs->nextphaseinc, h->d_runs.as<double>(), h->d_sym.as<SymOut>());
+      count_launch(9);
       DVBT_CUDA_TRY(cudaGetLastError());
     }
     DVBT_CUDA_TRY(cudaMemcpyAsync(hs, h->d_state.p, sizeof(AcqState), cudaMemcpyDeviceToHost, st));
@@ -911,9 +940,9 @@ int acq_run(dvbt_b200_acq *h, const float2 *x, long long n, float2 *d_out, long 
     if (getenv("DVBT_B200_ACQ_TRACE")) {
       AcqWalk wk;
       if (cudaMemcpy(&wk, h->d_eps.p, sizeof wk, cudaMemcpyDeviceToHost) == cudaSuccess)
-        fprintf(stderr, "acq batch: nsym %lld found %d code %d override %d segments %d staged %d cycles maps %lld serial %lld | finish %lld %lld %lld %lld %lld\n", nsym,
-                wk.n_found, wk.code, wk.n_override, wk.n_seg, wk.n_staged, wk.cyc_maps, wk.cyc_serial, wk.cyc_fin[0], wk.cyc_fin[1],
-                wk.cyc_fin[2], wk.cyc_fin[3], wk.cyc_fin[4]);
+        fprintf(stderr, "acq batch: nsym %lld found %d code %d override %d segments %d staged %d cycles maps %lld serial %lld (stage %lld walk %lld detect %lld rest %lld) | finish %lld %lld %lld %lld %lld\n", nsym,
+                wk.n_found, wk.code, wk.n_override, wk.n_seg, wk.n_staged, wk.cyc_maps, wk.cyc_serial, wk.cyc_cmp[0], wk.cyc_cmp[1], wk.cyc_cmp[2],
+                wk.cyc_cmp[3], wk.cyc_fin[0], wk.cyc_fin[1], wk.cyc_fin[2], wk.cyc_fin[3], wk.cyc_fin[4]);
     }
     if (hs->n_out > 0) {
       dim3 grid((p.N + 256 * kDerotPer - 1) / (256 * kDerotPer), hs->n_out);
@@ -1023,7 +1052,7 @@ void dvbt_b200_acq_destroy(dvbt_b200_acq *h) {
   if (!h) return;
   if (h->stream) cudaStreamSynchronize(h->stream);
   if (h->plan) cufftDestroy(h->plan);
-  dvbt::DevBuf *bufs[] = {&h->d_x, &h->d_state, &h->h_state, &h->d_lambda, &h->d_gamma, &h->d_avg1, &h->d_avg2, &h->d_peak, &h->d_sym, &h->d_out, &h->d_il, &h->d_ig, &h->d_eps, &h->d_flag, &h->d_maps, &h->d_cof, &h->d_bof, &h->d_peakof, &h->d_eof, &h->d_seg};
+  dvbt::DevBuf *bufs[] = {&h->d_x, &h->d_state, &h->h_state, &h->d_lambda, &h->d_gamma, &h->d_avg1, &h->d_avg2, &h->d_peak, &h->d_sym, &h->d_out, &h->d_il, &h->d_ig, &h->d_eps, &h->d_flag, &h->d_maps, &h->d_cof, &h->d_bof, &h->d_peakof, &h->d_eof, &h->d_seg, &h->d_runs};
   for (auto *b : bufs) b->release();
   if (h->stream && h->own_stream) cudaStreamDestroy(h->stream);
   delete h;

@@ -180,7 +180,7 @@ __device__ int rs_warp_decode(const GfTables &gf, uint8_t *pkt, uint8_t *work, i
 // g(x) = prod_{i=0..15} (x + a^i) (reed_solomon.cc:95-133 builds the same g), as 4 little-endian words.
 __device__ uint32_t d_lfsr[256 * 4];
 
-constexpr int kTilePk = 128;            // packets per block
+constexpr int kTilePk = 256;            // packets per block
 constexpr int kHalo = 204 * 11;         // bytes of stream history the deepest deinterleaver branch reaches back
 
 // One block per 128 packets.
@@ -199,8 +199,12 @@ template <bool GATHER>
 __global__ void __launch_bounds__(kTilePk) rs_decode_kernel(const uint8_t *__restrict__ in, uint8_t *__restrict__ out,
                                                             int *__restrict__ status, long long npackets, int as_built,
                                                             long long in_bytes) {
-  extern __shared__ __align__(16) uint8_t s_raw[];   // [kTilePk*204 (+ kHalo)]
-  __shared__ __align__(16) uint4 s_lfsr[256];
+  extern __shared__ __align__(16) uint8_t s_dyn[];   // division table (8 copies), then the staged input [kTilePk*204 (+ kHalo)]
+  // Copy c of row f sits at 16-byte slot 8 f + c: lane l reads copy l & 7, so the eight lanes of a quarter warp -
+  // what a 128-bit shared-memory access serves per pass - always hit eight different bank groups, whatever their
+  // rows (one shared copy cost ~3 passes per quarter warp and left the kernel LSU bound).
+  uint4 *s_lfsr = reinterpret_cast<uint4 *>(s_dyn);
+  uint8_t *s_raw = s_dyn + 256 * 8 * 16;
   __shared__ __align__(16) uint8_t s_exp2[512];
   __shared__ __align__(16) uint8_t s_log[256];
   __shared__ __align__(16) uint32_t s_pkt[kTilePk / 32][52];
@@ -210,7 +214,7 @@ __global__ void __launch_bounds__(kTilePk) rs_decode_kernel(const uint8_t *__res
   const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
   for (int i = t; i < 512; i += blockDim.x) s_exp2[i] = c_exp2[i];
   for (int i = t; i < 256; i += blockDim.x) s_log[i] = c_log[i];
-  for (int i = t; i < 256; i += blockDim.x) s_lfsr[i] = reinterpret_cast<const uint4 *>(d_lfsr)[i];
+  for (int i = t; i < 256 * 8; i += blockDim.x) s_lfsr[i] = reinterpret_cast<const uint4 *>(d_lfsr)[i >> 3];
   if (t == 0) s_ndirty = 0;
   const long long p0 = (long long)blockIdx.x * kTilePk;
   const int np = (int)((npackets - p0) < kTilePk ? (npackets - p0) : kTilePk);
@@ -258,7 +262,7 @@ __global__ void __launch_bounds__(kTilePk) rs_decode_kernel(const uint8_t *__res
       r2 = __funnelshift_l(r1, r2, 8);
       r1 = __funnelshift_l(r0, r1, 8);
       r0 <<= 8;
-      uint4 row = s_lfsr[fb];
+      uint4 row = s_lfsr[fb * 8 + (lane & 7)];
       r0 ^= row.x; r1 ^= row.y; r2 ^= row.z; r3 ^= row.w;
     }
     if ((r0 | r1 | r2 | r3) != 0u) s_dirty[atomicAdd(&s_ndirty, 1)] = t;
@@ -360,10 +364,16 @@ int rs_launch(const uint8_t *d_in, uint8_t *d_out, int *d_status, long long npac
   if (rc) return rc;
   unsigned grid = (unsigned)((npackets + kTilePk - 1) / kTilePk);
   (void)sm_count;
-  if (gather_stream_bytes >= 0)
-    rs_decode_kernel<true><<<grid, kTilePk, (size_t)kTilePk * kPktIn + kHalo, st>>>(d_in, d_out, d_status, npackets, as_built, gather_stream_bytes);
-  else
-    rs_decode_kernel<false><<<grid, kTilePk, (size_t)kTilePk * kPktIn, st>>>(d_in, d_out, d_status, npackets, as_built, 0);
+  const size_t table = 256 * 8 * 16;
+  if (gather_stream_bytes >= 0) {
+    const size_t smem = (size_t)kTilePk * kPktIn + kHalo + table;
+    DVBT_CUDA_TRY(cudaFuncSetAttribute(rs_decode_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    rs_decode_kernel<true><<<grid, kTilePk, smem, st>>>(d_in, d_out, d_status, npackets, as_built, gather_stream_bytes);
+  } else {
+    const size_t smem = (size_t)kTilePk * kPktIn + table;
+    DVBT_CUDA_TRY(cudaFuncSetAttribute(rs_decode_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    rs_decode_kernel<false><<<grid, kTilePk, smem, st>>>(d_in, d_out, d_status, npackets, as_built, 0);
+  }
   count_launch();
   DVBT_CUDA_TRY(cudaGetLastError());
   return 0;
