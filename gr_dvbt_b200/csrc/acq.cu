@@ -34,6 +34,7 @@
 #include <stdlib.h>
 #include <string.h>
 #include <new>
+#include <vector>
 
 namespace {
 
@@ -394,6 +395,7 @@ __global__ void __launch_bounds__(256) acq_compose_kernel(AcqParams p, int nsym,
   __shared__ __align__(16) unsigned char s_lam[kExt * kCand * 4 + 32];
   __shared__ __align__(16) unsigned char s_avg1[kExt * kNC * 4 + 32];
   __shared__ float s_win[16];
+  __shared__ unsigned char s_cst[1024];   // start state of every chunk taken whole
   const int t = threadIdx.x;
   const long long cyc0 = clock64();
   stage_bytes16(maps, 0, nchunks * kNS, s_maps, t, blockDim.x);
@@ -475,17 +477,30 @@ __global__ void __launch_bounds__(256) acq_compose_kernel(AcqParams p, int nsym,
   int k = 0, kstart = 0;                    // chunk of symbol n and its first symbol
   long long c_stage = 0, c_walk = 0, c_over = 0;
   while (n < nsym && !code) {
-    int nend = min(nsym, kstart + per_thread);
     if (n == kstart) {
-      unsigned char m = s_maps[k * kNS + st];
-      if (m < kStop && nseg < kMaxSeg) {   // whole chunk by its map
-        if (lane == 0) segs[nseg] = make_int4(n, nend, st, 0);
-        nseg++;
-        st = m; n = nend; n_found = n; avg_from = n - 1;
-        k++; kstart += per_thread;
+      // whole chunks by their maps, as far as they go: the loop carries only the state (one shared-memory byte
+      // per chunk in, one out); the segments of the run are written afterwards, one per lane
+      const int k0 = k, room = kMaxSeg - 2 - nseg;
+      while (kstart < nsym && k - k0 < room) {
+        unsigned char m = s_maps[k * kNS + st];
+        if (m >= kStop) break;
+        s_cst[k] = st;
+        st = m;
+        k++;
+        kstart += per_thread;
+      }
+      if (k > k0) {
+        __syncwarp();
+        for (int kk = k0 + lane; kk < k; kk += 32)
+          segs[nseg + kk - k0] = make_int4(kk * per_thread, min(nsym, (kk + 1) * per_thread), s_cst[kk], 0);
+        __syncwarp();
+        nseg += k - k0;
+        n = min(nsym, kstart);
+        n_found = n; avg_from = n - 1;
         continue;
       }
     }
+    int nend = min(nsym, kstart + per_thread);
     if (nseg >= kMaxSeg - 2) { code = kSplit; break; }  // segment list full: end the batch here (the host loop continues)
     // table walk inside chunk k until its end or a stop code; the rows are staged in shared memory first
     if (nend - n > kRowsCap) nend = n + kRowsCap;
@@ -826,6 +841,110 @@ __global__ void __launch_bounds__(256) acq_derot_kernel(int N, int nsym, const f
   }
 }
 
+// ---- derotation fused with the forward FFT (one block per OFDM symbol) ------------------------------------------
+// Replaces acq_derot_kernel + cufftExecC2C when the block delivers frequency-domain symbols: the derotated
+// samples never go to HBM (8N B read + 8N B written per symbol instead of 4 x 8N).  Stockham autosort passes in
+// shared memory, radix 8 (8,8,8,4 for N = 2048; 8,8,8,8,2 for N = 8192): pass with radix R and p = product of the
+// earlier radices, butterfly i (0 <= i < N/R): k = i mod p, inputs in[i + r N/R] * W_N^(r k N/(p R)), outputs to
+// out[(i - k) R + k + q p].  The first pass reads global memory (derotation and (-1)^j applied on the fly, the
+// eight inputs of a thread are N/8 apart = coalesced across the block), the last one writes global memory
+// (q N/R + i: coalesced).  Twiddles come from a table W_N^n computed in double precision on the host.
+__device__ __forceinline__ float2 cadd2(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ float2 csub2(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+__device__ __forceinline__ float2 cmul2(float2 a, float2 b) { return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
+__device__ __forceinline__ float2 cmulmi(float2 a) { return make_float2(a.y, -a.x); }   // a * (-i)
+
+__device__ __forceinline__ void dft8(float2 *u) {
+  const float h = 0.70710678118654752440f;
+  float2 a0 = cadd2(u[0], u[4]), a4 = csub2(u[0], u[4]), a1 = cadd2(u[1], u[5]), a5 = csub2(u[1], u[5]);
+  float2 a2 = cadd2(u[2], u[6]), a6 = csub2(u[2], u[6]), a3 = cadd2(u[3], u[7]), a7 = csub2(u[3], u[7]);
+  a5 = make_float2(h * (a5.x + a5.y), h * (a5.y - a5.x));      // * W8^1 = (1 - i)/sqrt2
+  a6 = cmulmi(a6);                                             // * W8^2 = -i
+  a7 = make_float2(h * (a7.y - a7.x), -h * (a7.x + a7.y));     // * W8^3 = (-1 - i)/sqrt2
+  float2 b0 = cadd2(a0, a2), b2 = csub2(a0, a2), b1 = cadd2(a1, a3), b3 = cmulmi(csub2(a1, a3));
+  float2 b4 = cadd2(a4, a6), b6 = csub2(a4, a6), b5 = cadd2(a5, a7), b7 = cmulmi(csub2(a5, a7));
+  u[0] = cadd2(b0, b1); u[4] = csub2(b0, b1); u[2] = cadd2(b2, b3); u[6] = csub2(b2, b3);
+  u[1] = cadd2(b4, b5); u[5] = csub2(b4, b5); u[3] = cadd2(b6, b7); u[7] = csub2(b6, b7);
+}
+__device__ __forceinline__ void dft4(float2 *u) {
+  float2 a0 = cadd2(u[0], u[2]), a2 = csub2(u[0], u[2]), a1 = cadd2(u[1], u[3]), a3 = cmulmi(csub2(u[1], u[3]));
+  u[0] = cadd2(a0, a1); u[1] = cadd2(a2, a3); u[2] = csub2(a0, a1); u[3] = csub2(a2, a3);
+}
+__device__ __forceinline__ void dft2(float2 *u) {
+  float2 a = u[0];
+  u[0] = cadd2(a, u[1]); u[1] = csub2(a, u[1]);
+}
+template <int R> __device__ __forceinline__ void dftR(float2 *u) {
+  if (R == 8) dft8(u); else if (R == 4) dft4(u); else dft2(u);
+}
+
+// one Stockham pass from `in` to `out` (shared or global), radix R, p = product of the earlier radices
+template <int N, int R, bool LAST>
+__device__ __forceinline__ void fft_pass(const float2 *__restrict__ in, float2 *__restrict__ out, int p, const float2 *__restrict__ W, int t) {
+  constexpr int T = N / 8, NB = N / R;     // threads, butterflies
+#pragma unroll
+  for (int rep = 0; rep < 8 / R; rep++) {
+    const int i = t + rep * T;
+    const int k = i & (p - 1);
+    const int j = (i - k) * R + k;
+    float2 u[R];
+#pragma unroll
+    for (int r = 0; r < R; r++) u[r] = in[i + r * NB];
+    const int wstep = k * (N / R) / p;     // W_N^(r k N / (p R))
+#pragma unroll
+    for (int r = 1; r < R; r++) u[r] = cmul2(u[r], W[(r * wstep) & (N - 1)]);
+    dftR<R>(u);
+#pragma unroll
+    for (int q = 0; q < R; q++) out[j + q * p] = u[q];
+    (void)NB;
+  }
+  if (!LAST) __syncthreads();
+}
+
+template <int N>
+__global__ void __launch_bounds__(N / 8) acq_fftd_kernel(int nsym, const float2 *__restrict__ x, const SymOut *__restrict__ so,
+                                                         float2 *__restrict__ out, const float2 *__restrict__ W) {
+  extern __shared__ __align__(16) float2 s_fft[];   // two buffers of N
+  float2 *bufA = s_fft, *bufB = s_fft + N;
+  constexpr int T = N / 8;
+  const int n = blockIdx.x, t = threadIdx.x;
+  if (n >= nsym) return;
+  const SymOut s = so[n];
+  // pass 0 (radix 8, p = 1) straight from global memory with the derotation
+  {
+    float2 u[8];
+#pragma unroll
+    for (int r = 0; r < 8; r++) u[r] = __ldg(x + s.first + t + r * T);
+#pragma unroll
+    for (int r = 0; r < 8; r++) {
+      const int j = t + r * T;
+      const int steps = j + 1;  // the phase is incremented before it is used (:291-307)
+      double ph = s.phase0 + (steps <= s.switch_at ? steps * s.inc0 : s.switch_at * s.inc0 + (steps - s.switch_at) * s.inc1);
+      ph -= (2.0 * M_PI) * rint(ph * (1.0 / (2.0 * M_PI)));
+      float sn, cs;
+      sincosf((float)ph, &sn, &cs);
+      float2 v = cmulf(make_float2(cs, sn), u[r]);
+      if (j & 1) v = make_float2(-v.x, -v.y);     // fft_vxx(shift = true)
+      u[r] = v;
+    }
+    dft8(u);
+#pragma unroll
+    for (int q = 0; q < 8; q++) bufA[8 * t + q] = u[q];
+    __syncthreads();
+  }
+  float2 *dst = out + (long long)n * N;
+  if (N == 2048) {
+    fft_pass<N, 8, false>(bufA, bufB, 8, W, t);
+    fft_pass<N, 8, false>(bufB, bufA, 64, W, t);
+    fft_pass<N, 4, true>(bufA, dst, 512, W, t);
+  } else {
+    fft_pass<N, 8, false>(bufA, bufB, 8, W, t);
+    fft_pass<N, 8, false>(bufB, bufA, 64, W, t);
+    fft_pass<N, 8, false>(bufA, bufB, 512, W, t);
+    fft_pass<N, 2, true>(bufB, dst, 4096, W, t);
+  }
+}
+
 }  // namespace
 
 struct dvbt_b200_acq {
@@ -836,7 +955,8 @@ struct dvbt_b200_acq {
   bool own_stream = true;
   cufftHandle plan = 0;
   int plan_batch = 0;
-  dvbt::DevBuf d_x, d_state, h_state, d_lambda, d_gamma, d_avg1, d_avg2, d_peak, d_sym, d_out, d_il, d_ig, d_eps, d_flag, d_maps, d_cof, d_bof, d_peakof, d_eof, d_seg, d_runs;
+  dvbt::DevBuf d_x, d_state, h_state, d_lambda, d_gamma, d_avg1, d_avg2, d_peak, d_sym, d_out, d_il, d_ig, d_eps, d_flag, d_maps, d_cof, d_bof, d_peakof, d_eof, d_seg, d_runs, d_tw;
+  int tw_n = 0;
 };
 
 namespace dvbt {
@@ -855,6 +975,19 @@ int acq_run(dvbt_b200_acq *h, const float2 *x, long long n, float2 *d_out, long 
   int rc;
   DVBT_CUDA_TRY(cudaMemcpyAsync(hs, h->d_state.p, sizeof(AcqState), cudaMemcpyDeviceToHost, st));
   DVBT_CUDA_TRY(cudaStreamSynchronize(st));
+  // frequency-domain output: derotation + FFT in one kernel for the two DVB-T sizes (cuFFT otherwise)
+  const bool fused_fft = do_fft && (p.N == 2048 || p.N == 8192) && !getenv("DVBT_B200_ACQ_CUFFT");
+  if (fused_fft && h->tw_n != p.N) {
+    std::vector<float2> tw(p.N);
+    for (int i = 0; i < p.N; i++) {
+      double a = -2.0 * M_PI * (double)i / (double)p.N;
+      tw[i] = make_float2((float)cos(a), (float)sin(a));
+    }
+    if ((rc = h->d_tw.reserve((size_t)p.N * sizeof(float2)))) return rc;
+    DVBT_CUDA_TRY(cudaMemcpyAsync(h->d_tw.p, tw.data(), (size_t)p.N * sizeof(float2), cudaMemcpyHostToDevice, st));
+    DVBT_CUDA_TRY(cudaStreamSynchronize(st));
+    h->tw_n = p.N;
+  }
   int guard = 0;
   while (guard++ < 1000000) {
     // ---- initial acquisition (needs 2N+cp+8 samples visible)
@@ -944,7 +1077,18 @@ int acq_run(dvbt_b200_acq *h, const float2 *x, long long n, float2 *d_out, long 
                 wk.n_found, wk.code, wk.n_override, wk.n_seg, wk.n_staged, wk.cyc_maps, wk.cyc_serial, wk.cyc_cmp[0], wk.cyc_cmp[1], wk.cyc_cmp[2],
                 wk.cyc_cmp[3], wk.cyc_fin[0], wk.cyc_fin[1], wk.cyc_fin[2], wk.cyc_fin[3], wk.cyc_fin[4]);
     }
-    if (hs->n_out > 0) {
+    if (hs->n_out > 0 && fused_fft) {
+      if (p.N == 2048) {
+        acq_fftd_kernel<2048><<<hs->n_out, 256, 2 * 2048 * sizeof(float2), st>>>(hs->n_out, x, h->d_sym.as<SymOut>(), d_out + produced * p.N,
+                                                                                 h->d_tw.as<float2>());
+      } else {
+        DVBT_CUDA_TRY(cudaFuncSetAttribute(acq_fftd_kernel<8192>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 8192 * (int)sizeof(float2)));
+        acq_fftd_kernel<8192><<<hs->n_out, 1024, 2 * 8192 * sizeof(float2), st>>>(hs->n_out, x, h->d_sym.as<SymOut>(), d_out + produced * p.N,
+                                                                                  h->d_tw.as<float2>());
+      }
+      count_launch();
+      DVBT_CUDA_TRY(cudaGetLastError());
+    } else if (hs->n_out > 0) {
       dim3 grid((p.N + 256 * kDerotPer - 1) / (256 * kDerotPer), hs->n_out);
       acq_derot_kernel<<<grid, 256, 0, st>>>(p.N, hs->n_out, x, h->d_sym.as<SymOut>(), d_out + produced * p.N, do_fft ? 1 : 0);
       count_launch();
@@ -968,7 +1112,7 @@ int acq_run(dvbt_b200_acq *h, const float2 *x, long long n, float2 *d_out, long 
     if (capped) continue;             // batch limit: the rest of the input follows from the state just written
     break;
   }
-  if (do_fft && produced > 0) {
+  if (do_fft && !fused_fft && produced > 0) {
     if (h->plan == 0 || h->plan_batch != (int)produced) {
       if (h->plan) cufftDestroy(h->plan);
       h->plan = 0;
@@ -1052,7 +1196,7 @@ void dvbt_b200_acq_destroy(dvbt_b200_acq *h) {
   if (!h) return;
   if (h->stream) cudaStreamSynchronize(h->stream);
   if (h->plan) cufftDestroy(h->plan);
-  dvbt::DevBuf *bufs[] = {&h->d_x, &h->d_state, &h->h_state, &h->d_lambda, &h->d_gamma, &h->d_avg1, &h->d_avg2, &h->d_peak, &h->d_sym, &h->d_out, &h->d_il, &h->d_ig, &h->d_eps, &h->d_flag, &h->d_maps, &h->d_cof, &h->d_bof, &h->d_peakof, &h->d_eof, &h->d_seg, &h->d_runs};
+  dvbt::DevBuf *bufs[] = {&h->d_x, &h->d_state, &h->h_state, &h->d_lambda, &h->d_gamma, &h->d_avg1, &h->d_avg2, &h->d_peak, &h->d_sym, &h->d_out, &h->d_il, &h->d_ig, &h->d_eps, &h->d_flag, &h->d_maps, &h->d_cof, &h->d_bof, &h->d_peakof, &h->d_eof, &h->d_seg, &h->d_runs, &h->d_tw};
   for (auto *b : bufs) b->release();
   if (h->stream && h->own_stream) cudaStreamDestroy(h->stream);
   delete h;
