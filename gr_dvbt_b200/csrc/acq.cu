@@ -879,7 +879,9 @@ template <int R> __device__ __forceinline__ void dftR(float2 *u) {
 }
 
 // one Stockham pass from `in` to `out` (shared or global), radix R, p = product of the earlier radices
-template <int N, int R, bool LAST>
+// PADIN: the input buffer was written by pass 0 with one pad element per 8 (index i lives at i + (i >> 3)): pass 0
+// stores 8 consecutive elements per thread, which without the pad is a 16-way bank conflict.
+template <int N, int R, bool LAST, bool PADIN = false>
 __device__ __forceinline__ void fft_pass(const float2 *__restrict__ in, float2 *__restrict__ out, int p, const float2 *__restrict__ W, int t) {
   constexpr int T = N / 8, NB = N / R;     // threads, butterflies
 #pragma unroll
@@ -889,7 +891,7 @@ __device__ __forceinline__ void fft_pass(const float2 *__restrict__ in, float2 *
     const int j = (i - k) * R + k;
     float2 u[R];
 #pragma unroll
-    for (int r = 0; r < R; r++) u[r] = in[i + r * NB];
+    for (int r = 0; r < R; r++) u[r] = PADIN ? in[(i + r * NB) + ((i + r * NB) >> 3)] : in[i + r * NB];
     const int wstep = k * (N / R) / p;     // W_N^(r k N / (p R))
 #pragma unroll
     for (int r = 1; r < R; r++) u[r] = cmul2(u[r], W[(r * wstep) & (N - 1)]);
@@ -904,8 +906,8 @@ __device__ __forceinline__ void fft_pass(const float2 *__restrict__ in, float2 *
 template <int N>
 __global__ void __launch_bounds__(N / 8) acq_fftd_kernel(int nsym, const float2 *__restrict__ x, const SymOut *__restrict__ so,
                                                          float2 *__restrict__ out, const float2 *__restrict__ W) {
-  extern __shared__ __align__(16) float2 s_fft[];   // two buffers of N
-  float2 *bufA = s_fft, *bufB = s_fft + N;
+  extern __shared__ __align__(16) float2 s_fft[];   // two buffers of N (+ N/8 pad for the first)
+  float2 *bufA = s_fft, *bufB = s_fft + N + N / 8;
   constexpr int T = N / 8;
   const int n = blockIdx.x, t = threadIdx.x;
   if (n >= nsym) return;
@@ -929,16 +931,16 @@ __global__ void __launch_bounds__(N / 8) acq_fftd_kernel(int nsym, const float2 
     }
     dft8(u);
 #pragma unroll
-    for (int q = 0; q < 8; q++) bufA[8 * t + q] = u[q];
+    for (int q = 0; q < 8; q++) bufA[9 * t + q] = u[q];   // index 8t+q, padded: + (8t+q >> 3) = + t
     __syncthreads();
   }
   float2 *dst = out + (long long)n * N;
   if (N == 2048) {
-    fft_pass<N, 8, false>(bufA, bufB, 8, W, t);
+    fft_pass<N, 8, false, true>(bufA, bufB, 8, W, t);
     fft_pass<N, 8, false>(bufB, bufA, 64, W, t);
     fft_pass<N, 4, true>(bufA, dst, 512, W, t);
   } else {
-    fft_pass<N, 8, false>(bufA, bufB, 8, W, t);
+    fft_pass<N, 8, false, true>(bufA, bufB, 8, W, t);
     fft_pass<N, 8, false>(bufB, bufA, 64, W, t);
     fft_pass<N, 8, false>(bufA, bufB, 512, W, t);
     fft_pass<N, 2, true>(bufB, dst, 4096, W, t);
@@ -1079,11 +1081,11 @@ int acq_run(dvbt_b200_acq *h, const float2 *x, long long n, float2 *d_out, long 
     }
     if (hs->n_out > 0 && fused_fft) {
       if (p.N == 2048) {
-        acq_fftd_kernel<2048><<<hs->n_out, 256, 2 * 2048 * sizeof(float2), st>>>(hs->n_out, x, h->d_sym.as<SymOut>(), d_out + produced * p.N,
+        acq_fftd_kernel<2048><<<hs->n_out, 256, (2 * 2048 + 256) * sizeof(float2), st>>>(hs->n_out, x, h->d_sym.as<SymOut>(), d_out + produced * p.N,
                                                                                  h->d_tw.as<float2>());
       } else {
-        DVBT_CUDA_TRY(cudaFuncSetAttribute(acq_fftd_kernel<8192>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 8192 * (int)sizeof(float2)));
-        acq_fftd_kernel<8192><<<hs->n_out, 1024, 2 * 8192 * sizeof(float2), st>>>(hs->n_out, x, h->d_sym.as<SymOut>(), d_out + produced * p.N,
+        DVBT_CUDA_TRY(cudaFuncSetAttribute(acq_fftd_kernel<8192>, cudaFuncAttributeMaxDynamicSharedMemorySize, (2 * 8192 + 1024) * (int)sizeof(float2)));
+        acq_fftd_kernel<8192><<<hs->n_out, 1024, (2 * 8192 + 1024) * sizeof(float2), st>>>(hs->n_out, x, h->d_sym.as<SymOut>(), d_out + produced * p.N,
                                                                                   h->d_tw.as<float2>());
       }
       count_launch();
