@@ -7,22 +7,25 @@ import viterbi_model as VM
 from oracle import port as O
 
 
+@pytest.mark.parametrize("schedule", ["swar", "h16"])
 @pytest.mark.parametrize("rate,m,ber", [(0, 4, 0.03), (4, 6, 0.004), (2, 2, 0.02)])
-def test_schedule_model_matches_oracle(rate, m, ber):
+def test_schedule_model_matches_oracle(rate, m, ber, schedule):
     k, n = O.RATE_KN[rate]
     data = np.random.default_rng(rate).integers(0, 256, 96 * k, dtype=np.uint8)
     rx = O.flip_bits(O.conv_encode(data, m, rate), m, ber, 3)
     ref = O.Viterbi(m, rate).work(rx)
-    out, _ = VM.decode_stream(rx, m, rate, chunk_bytes=10 ** 9, warm=0)
+    out, _ = VM.decode_stream(rx, m, rate, chunk_bytes=10 ** 9, warm=0, schedule=schedule)
     assert np.array_equal(out, ref)
-    out, fix = VM.decode_stream(rx, m, rate, chunk_bytes=48, warm=1)
+    out, fix = VM.decode_stream(rx, m, rate, chunk_bytes=48, warm=1, schedule=schedule)
     assert np.array_equal(out, ref) and fix > 0  # boundary verification + repair is exact
 
 
-def test_generated_header_is_current():
+@pytest.mark.parametrize("mod,hdr", [("gen_viterbi_acs", "viterbi_acs_gen.cuh"), ("gen_viterbi_acs_h16", "viterbi_acs_h16_gen.cuh")])
+def test_generated_header_is_current(mod, hdr):
+    import importlib
     import os
-    import gen_viterbi_acs as G
-    path = os.path.join(os.path.dirname(G.__file__), "viterbi_acs_gen.cuh")
+    G = importlib.import_module(mod)
+    path = os.path.join(os.path.dirname(G.__file__), hdr)
     before = open(path).read()
     G.main()
-    assert open(path).read() == before, "viterbi_acs_gen.cuh is stale: run gr_dvbt_b200/csrc/gen_viterbi_acs.py"
+    assert open(path).read() == before, "%s is stale: run gr_dvbt_b200/csrc/%s.py" % (hdr, mod)

@@ -14,6 +14,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "gr_dvbt_b200", "csrc"))
 import gen_viterbi_acs as G  # noqa: E402
+import gen_viterbi_acs_h16 as H  # noqa: E402
 
 RATE_K = [1, 2, 3, 5, 7]
 RATE_N = [2, 3, 4, 6, 8]
@@ -151,13 +152,101 @@ def decode_chunk(codes, jstart, jend, first_real, ntb, out, save_at=(), init_met
     return saved
 
 
+_SCHED_H = None
+
+
+def sched_h16():
+    global _SCHED_H
+    if _SCHED_H is None:
+        _SCHED_H = H.build()
+    return _SCHED_H
+
+
+def brev8(b):
+    return int("{:08b}".format(int(b))[::-1], 2)
+
+
+def decode_chunk_h16(codes, jstart, jend, first_real, ntb, out, save_at=(), init_metrics=None):
+    """Same contract as decode_chunk for the halfword schedule (gen_viterbi_acs_h16.py): 32 registers of
+    (metric << 8 | path) halfwords, path bytes bit reversed, event layout of that generator."""
+    S = sched_h16()
+    lut = apk_lut()
+    one = lambda v: np.array([v], np.uint32)
+    V = [one(0) for _ in range(32)]
+    ring = np.zeros((ntb, 64), np.uint8)
+    trace = np.zeros(ntb, np.int64)
+    have_trace = False
+    saved = {}
+    resume = init_metrics is not None
+    j = jstart
+    if resume:
+        j = jstart - 1
+    while j < jend:
+        code = int(codes[j]) if j < len(codes) else 0
+        apk = [one(lut[(code >> (4 * i)) & 15]) for i in range(8)]
+        if resume:
+            Mev = [one(x) for x in init_metrics]
+            resume = False
+        else:
+            env = {"ZERO": one(0)}
+            for i in range(32):
+                env["V[%d]" % i] = V[i]
+            for i in range(6):
+                env["apk%d" % i] = apk[i]
+            H.run_ops(S["part1"], env)
+            Mev = [env["M_ev[%d]" % i] for i in range(16)]
+            Pev = [env["P_ev[%d]" % i] for i in range(16)]
+            slot = j % ntb
+            row = np.zeros(64, np.uint8)
+            for w in range(16):
+                for b in range(4):
+                    row[4 * w + b] = (int(Pev[w][0]) >> (8 * b)) & 0xFF
+            ring[slot] = row
+            met = np.zeros(64, np.int64)
+            for s in range(64):
+                bi = H.event_byte_index(s)
+                met[s] = (int(Mev[bi >> 2][0]) >> (8 * (bi & 3))) & 0xFF
+            assert met.max() < 128
+            if j >= first_real:
+                s = int(np.argmax(met))
+                merged = False
+                for h in range(ntb - 1):
+                    q = (j - h) % ntb
+                    if h > 0 and have_trace and trace[q] == s:
+                        merged = True
+                        break
+                    trace[q] = s
+                    s = brev8(ring[q][H.event_byte_index(s)]) >> 2
+                qf = (j - (ntb - 1)) % ntb
+                if merged:
+                    s = int(trace[qf])
+                else:
+                    trace[qf] = s
+                have_trace = True
+                out[j - ntb] = brev8(ring[qf][H.event_byte_index(s)])
+            x = int(Mev[0][0]) & 0xFF
+            sub = max(x, 12) - 12
+            Mev = [one((int(v[0]) - sub * 0x01010101) & 0xFFFFFFFF) for v in Mev]
+            if j in save_at:
+                saved[j] = np.array([int(v[0]) for v in Mev], np.uint32)
+        env = {"ZERO": one(0)}
+        for i in range(16):
+            env["M[%d]" % i] = Mev[i]
+        env["apk6"], env["apk7"] = apk[6], apk[7]
+        H.run_ops(S["part2"], env)
+        V = [env["V_nx[%d]" % i] for i in range(32)]
+        j += 1
+    return saved
+
+
 def normalised(words):
     b = np.array([(int(w) >> (8 * i)) & 0xFF for w in words for i in range(4)], np.int64)
     return b - b.min()
 
 
-def decode_stream(inp, m, rate, chunk_bytes, warm, force_fixup=False):
+def decode_stream(inp, m, rate, chunk_bytes, warm, force_fixup=False, schedule="swar"):
     """Whole stream from a reset, chunked like the kernel; returns (out bytes, n_fixups)."""
+    decode_chunk = globals()["decode_chunk_h16" if schedule == "h16" else "decode_chunk"]
     k, n, ntb = RATE_K[rate], RATE_N[rate], RATE_NTB[rate]
     nbt = len(inp) * m * k // (8 * n)  # byte times available
     codes = depuncture_codes(inp, m, rate, nbt)
