@@ -162,7 +162,35 @@ def build():
         va, vb = idx[(s0, s1)], idx[(s2, s3)]
         g.emit("prmt", "P_ev[%d]" % w, va, vb, 0x6420)   # path bytes of (va.lo, va.hi, vb.lo, vb.hi)
         g.emit("prmt", "M_ev[%d]" % w, va, vb, 0x7531)   # their metrics
+    # the registers themselves, for the best-state search: V_ev[r] holds states (r, r + 32)
+    for r in range(32):
+        g.emit("mov", "V_ev[%d]" % r, idx[(r, r + 32)])
     part1 = g.ops
+
+    # ---- best state (d_viterbi.c:699-711: lowest index with strictly greatest metric): replace the path byte of
+    # every halfword by 63 - state and take the 16-bit maximum of all 64 halfwords
+    g = Gen()
+    cur = []
+    for r in range(32):
+        t = g.new("q")
+        g.emit("lop3or", t, "V_ev[%d]" % r, 0xFF00FF00, (63 - r) | ((63 - (r + 32)) << 16))
+        cur.append(t)
+    while len(cur) > 1:
+        nxt = []
+        while len(cur) >= 3:
+            t = g.new("q")
+            g.emit("vimax3", t, cur[0], cur[1], cur[2])
+            nxt.append(t)
+            cur = cur[3:]
+        if len(cur) == 2 and not nxt:
+            t = g.new("q")
+            g.emit("vimax3", t, cur[0], cur[1], cur[1])
+            nxt.append(t)
+            cur = []
+        nxt += cur
+        cur = nxt
+    g.emit("mov", "BEST", cur[0])
+    argmax = g.ops
 
     # ---- part 2: zip the metric words (lane = bit 0, paths empty), steps 7, 8
     g = Gen()
@@ -180,7 +208,7 @@ def build():
     for i, st in enumerate(L_start):
         g.emit("mov", "V_nx[%d]" % i, idx[st])
     part2 = g.ops
-    return dict(part1=part1, part2=part2, L_start=L_start)
+    return dict(part1=part1, part2=part2, argmax=argmax, L_start=L_start)
 
 
 def event_byte_index(s):
@@ -222,6 +250,13 @@ def run_ops(ops, env):
             lo = np.maximum((a + b) & u32(0xFFFF), c & u32(0xFFFF))
             hi = np.maximum(((a >> u32(16)) + (b >> u32(16))) & u32(0xFFFF), c >> u32(16))
             env[d] = (lo | (hi << u32(16))).astype(u32)
+        elif k == "lop3or":
+            env[d] = ((env[op[2]] & u32(op[3])) | u32(op[4])).astype(u32)
+        elif k == "vimax3":
+            a, b, c = env[op[2]], env[op[3]], env[op[4]]
+            lo = np.maximum(np.maximum(a & u32(0xFFFF), b & u32(0xFFFF)), c & u32(0xFFFF))
+            hi = np.maximum(np.maximum(a >> u32(16), b >> u32(16)), c >> u32(16))
+            env[d] = (lo | (hi << u32(16))).astype(u32)
         elif k == "mov":
             env[d] = env[op[2]]
         else:
@@ -237,7 +272,7 @@ def emit_cuda(ops, indent="  "):
     declared = set()
 
     def dst(x):
-        if "[" in x or x in declared:
+        if "[" in x or x in declared or x == "BEST":   # arrays and macro parameters are declared by the caller
             return x
         declared.add(x)
         return "uint32_t " + x
@@ -250,9 +285,14 @@ def emit_cuda(ops, indent="  "):
         elif k == "add":
             lines.append("%s = VITH_ADD(%s, %s);" % (dst(d), op[2], op[3]))
         elif k == "addc":
-            lines.append("%s = %s + 0x%08xu;" % (dst(d), op[2], op[3]))
+            lines.append("%s = VITH_ADDC(%s, 0x%08xu);" % (dst(d), op[2], op[3]))
         elif k == "viaddmax":
             lines.append("%s = __viaddmax_u16x2(%s, %s, %s);" % (dst(d), op[2], op[3], op[4]))
+        elif k == "lop3or":
+            assert op[3] == 0xFF00FF00
+            lines.append("%s = (%s & VITH_HIMASK) | 0x%08xu;" % (dst(d), op[2], op[4]))
+        elif k == "vimax3":
+            lines.append("%s = __vimax3_u16x2(%s, %s, %s);" % (dst(d), op[2], op[3], op[4]))
         elif k == "mov":
             lines.append("%s = %s;" % (dst(d), op[2]))
         else:
@@ -272,6 +312,15 @@ HEADER = """// GENERATED by gr_dvbt_b200/csrc/gen_viterbi_acs_h16.py -- do not e
 #ifndef VITH_ADD
 #define VITH_ADD(a, b) ((a) + (b))
 #endif
+// branch-metric word + decision-bit constant (4 per step).  Plain by default; the kernel may force an IMAD.
+#ifndef VITH_ADDC
+#define VITH_ADDC(a, c) ((a) + (c))
+#endif
+// 0xff00ff00 (the metric bytes of a register).  The including kernel may define it as a run-time value held in a
+// register: with two immediates ptxas splits (x & mask) | k into two LOP3.
+#ifndef VITH_HIMASK
+#define VITH_HIMASK 0xff00ff00u
+#endif
 
 """
 
@@ -281,15 +330,21 @@ def main():
     out = [HEADER]
     out.append("// Steps 1..6 of a byte time.  In: V[32] in start layout (register r, lane l hold the state whose bit 2 is l and\n"
                "// whose other bits, low to high, are r).  Out: M_ev[16], P_ev[16] = metrics / path bytes, 4 states per word, in\n"
-               "// event layout: word w = state bits (4,3,2,1), byte = 2*bit0 + bit5.  Path bytes are bit reversed with respect\n"
-               "// to the reference's (first decision after the clear in bit 0).\n"
-               "#define VITH_ACS_PART1(V, M_ev, P_ev, apk0, apk1, apk2, apk3, apk4, apk5) \\\n")
+               "// event layout: word w = state bits (4,3,2,1), byte = 2*bit0 + bit5; V_ev[32] = the halfword registers at the\n"
+               "// event, V_ev[r] = states (r, r+32).  Path bytes are bit reversed with respect to the reference's (first\n"
+               "// decision after the clear in bit 0).\n"
+               "#define VITH_ACS_PART1(V, M_ev, P_ev, V_ev, apk0, apk1, apk2, apk3, apk4, apk5) \\\n")
     body = emit_cuda(res["part1"])
     out.append("  do { \\\n" + "\n".join(l + " \\" for l in body.split("\n")) + "\n  } while (0)\n\n")
     out.append("// Event-layout metric words M[16] (after renormalisation) -> halfword registers with empty paths, then steps 7, 8.\n"
                "// Out: V_nx[32] in start layout.\n"
                "#define VITH_ACS_PART2(M, V_nx, apk6, apk7) \\\n")
     body = emit_cuda(res["part2"])
+    out.append("  do { \\\n" + "\n".join(l + " \\" for l in body.split("\n")) + "\n  } while (0)\n\n")
+    out.append("// Best state at the event: BEST = 16-bit maximum over all states of (metric << 8 | 63 - state), in both halfwords\n"
+               "// of the result word (take the larger).  63 - (max & 63) is the lowest state with the greatest metric.\n"
+               "#define VITH_ARGMAX(V_ev, BEST) \\\n")
+    body = emit_cuda(res["argmax"])
     out.append("  do { \\\n" + "\n".join(l + " \\" for l in body.split("\n")) + "\n  } while (0)\n\n")
     for s in range(64):
         bi = event_byte_index(s)
@@ -304,7 +359,7 @@ def main():
                "__device__ __forceinline__ uint32_t vith_event_state(uint32_t w, uint32_t b) {\n"
                "  return (w << 1) | (b >> 1) | ((b & 1u) << 5);\n}\n")
     cnt = {}
-    for part in ("part1", "part2"):
+    for part in ("part1", "part2", "argmax"):
         for o in res[part]:
             if o[0] != "mov":
                 cnt[o[0]] = cnt.get(o[0], 0) + 1

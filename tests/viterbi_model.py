@@ -209,6 +209,10 @@ def decode_chunk_h16(codes, jstart, jend, first_real, ntb, out, save_at=(), init
             assert met.max() < 128
             if j >= first_real:
                 s = int(np.argmax(met))
+                # the generated best-state search (VITH_ARGMAX) must agree with the reference's scan
+                H.run_ops(S["argmax"], env)
+                bw = int(env["BEST"][0])
+                assert 63 - (max(bw & 0xFFFF, bw >> 16) & 63) == s
                 merged = False
                 for h in range(ntb - 1):
                     q = (j - h) % ntb
