@@ -843,17 +843,29 @@ __global__ void __launch_bounds__(256) acq_derot_kernel(int N, int nsym, const f
 
 // ---- derotation fused with the forward FFT (one block per OFDM symbol) ------------------------------------------
 // Replaces acq_derot_kernel + cufftExecC2C when the block delivers frequency-domain symbols: the derotated
-// samples never go to HBM (8N B read + 8N B written per symbol instead of 4 x 8N).  Stockham autosort passes in
-// shared memory, radix 8 (8,8,8,4 for N = 2048; 8,8,8,8,2 for N = 8192): pass with radix R and p = product of the
+// samples never go to HBM (8N B read + 8N B written per symbol instead of 4 x 8N).  Stockham autosort passes
+// through ONE shared-memory buffer, 16 points per thread and pass (N/16 threads): radices 16,16,8 for N = 2048 and
+// 16,16,16,2 for N = 8192, i.e. two (three) shared-memory round trips.  Pass with radix R and p = product of the
 // earlier radices, butterfly i (0 <= i < N/R): k = i mod p, inputs in[i + r N/R] * W_N^(r k N/(p R)), outputs to
-// out[(i - k) R + k + q p].  The first pass reads global memory (derotation and (-1)^j applied on the fly, the
-// eight inputs of a thread are N/8 apart = coalesced across the block), the last one writes global memory
-// (q N/R + i: coalesced).  Twiddles come from a table W_N^n computed in double precision on the host.
+// out[(i - k) R + k + q p].  The first pass reads global memory (derotation and (-1)^j applied on the fly; the 16
+// inputs of a thread are N/16 apart = coalesced across the block), the last one writes global memory
+// (q N/R + i: coalesced).  Index a of the buffer lives at a + a/16: with that padding every access pattern above
+// is conflict free.  Twiddles: W_N^n from a table computed in double precision on the host; a butterfly loads the
+// powers 1, 2, 4, 8 of its base twiddle and multiplies the others together (the first radix-8 version loaded all
+// of them and kept L1 92 % busy, profiles/r01_side_kernels_v20_ncu_summary.txt).
 __device__ __forceinline__ float2 cadd2(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
 __device__ __forceinline__ float2 csub2(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
 __device__ __forceinline__ float2 cmul2(float2 a, float2 b) { return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
 __device__ __forceinline__ float2 cmulmi(float2 a) { return make_float2(a.y, -a.x); }   // a * (-i)
 
+__device__ __forceinline__ void dft2(float2 *u) {
+  float2 a = u[0];
+  u[0] = cadd2(a, u[1]); u[1] = csub2(a, u[1]);
+}
+__device__ __forceinline__ void dft4(float2 *u) {
+  float2 a0 = cadd2(u[0], u[2]), a2 = csub2(u[0], u[2]), a1 = cadd2(u[1], u[3]), a3 = cmulmi(csub2(u[1], u[3]));
+  u[0] = cadd2(a0, a1); u[1] = cadd2(a2, a3); u[2] = csub2(a0, a1); u[3] = csub2(a2, a3);
+}
 __device__ __forceinline__ void dft8(float2 *u) {
   const float h = 0.70710678118654752440f;
   float2 a0 = cadd2(u[0], u[4]), a4 = csub2(u[0], u[4]), a1 = cadd2(u[1], u[5]), a5 = csub2(u[1], u[5]);
@@ -866,59 +878,95 @@ __device__ __forceinline__ void dft8(float2 *u) {
   u[0] = cadd2(b0, b1); u[4] = csub2(b0, b1); u[2] = cadd2(b2, b3); u[6] = csub2(b2, b3);
   u[1] = cadd2(b4, b5); u[5] = csub2(b4, b5); u[3] = cadd2(b6, b7); u[7] = csub2(b6, b7);
 }
-__device__ __forceinline__ void dft4(float2 *u) {
-  float2 a0 = cadd2(u[0], u[2]), a2 = csub2(u[0], u[2]), a1 = cadd2(u[1], u[3]), a3 = cmulmi(csub2(u[1], u[3]));
-  u[0] = cadd2(a0, a1); u[1] = cadd2(a2, a3); u[2] = csub2(a0, a1); u[3] = csub2(a2, a3);
-}
-__device__ __forceinline__ void dft2(float2 *u) {
-  float2 a = u[0];
-  u[0] = cadd2(a, u[1]); u[1] = csub2(a, u[1]);
+// 16 = 4 x 4: X[k1 + 4 k2] = sum_n2 W4^(n2 k2) W16^(n2 k1) sum_n1 W4^(n1 k1) x[4 n1 + n2]
+__device__ __forceinline__ void dft16(float2 *u) {
+  const float c1 = 0.92387953251128673848f, s1 = 0.38268343236508978178f, h = 0.70710678118654752440f;
+  float2 y[4][4];   // [n2][k1]
+#pragma unroll
+  for (int n2 = 0; n2 < 4; n2++) {
+    float2 a[4] = {u[n2], u[n2 + 4], u[n2 + 8], u[n2 + 12]};
+    dft4(a);
+#pragma unroll
+    for (int k1 = 0; k1 < 4; k1++) y[n2][k1] = a[k1];
+  }
+  // W16^(n2 k1), W16^m = (cos, -sin)(2 pi m / 16)
+  y[1][1] = cmul2(y[1][1], make_float2(c1, -s1));
+  y[1][2] = make_float2(h * (y[1][2].x + y[1][2].y), h * (y[1][2].y - y[1][2].x));     // W16^2 = (1 - i)/sqrt2
+  y[1][3] = cmul2(y[1][3], make_float2(s1, -c1));
+  y[2][1] = make_float2(h * (y[2][1].x + y[2][1].y), h * (y[2][1].y - y[2][1].x));
+  y[2][2] = cmulmi(y[2][2]);                                                            // W16^4 = -i
+  y[2][3] = make_float2(h * (y[2][3].y - y[2][3].x), -h * (y[2][3].x + y[2][3].y));    // W16^6 = (-1 - i)/sqrt2
+  y[3][1] = cmul2(y[3][1], make_float2(s1, -c1));
+  y[3][2] = make_float2(h * (y[3][2].y - y[3][2].x), -h * (y[3][2].x + y[3][2].y));
+  y[3][3] = cmul2(y[3][3], make_float2(-c1, s1));                                       // W16^9
+#pragma unroll
+  for (int k1 = 0; k1 < 4; k1++) {
+    float2 a[4] = {y[0][k1], y[1][k1], y[2][k1], y[3][k1]};
+    dft4(a);
+#pragma unroll
+    for (int k2 = 0; k2 < 4; k2++) u[k1 + 4 * k2] = a[k2];
+  }
 }
 template <int R> __device__ __forceinline__ void dftR(float2 *u) {
-  if (R == 8) dft8(u); else if (R == 4) dft4(u); else dft2(u);
+  if (R == 16) dft16(u); else if (R == 8) dft8(u); else if (R == 4) dft4(u); else dft2(u);
 }
 
-// one Stockham pass from `in` to `out` (shared or global), radix R, p = product of the earlier radices
-// PADIN: the input buffer was written by pass 0 with one pad element per 8 (index i lives at i + (i >> 3)): pass 0
-// stores 8 consecutive elements per thread, which without the pad is a 16-way bank conflict.
-template <int N, int R, bool LAST, bool PADIN = false>
-__device__ __forceinline__ void fft_pass(const float2 *__restrict__ in, float2 *__restrict__ out, int p, const float2 *__restrict__ W, int t) {
-  constexpr int T = N / 8, NB = N / R;     // threads, butterflies
+__device__ __forceinline__ int fft_pad(int a) { return a + (a >> 4); }
+
+// one Stockham pass over the shared buffer (or to global memory when LAST), radix R, p = product of the earlier radices
+template <int N, int R, bool LAST>
+__device__ __forceinline__ void fft16_pass(float2 *buf, float2 *__restrict__ gdst, int p, const float2 *__restrict__ W, int t) {
+  constexpr int T = N / 16, NB = N / R, REPS = 16 / R;
+  float2 u[REPS][R];
 #pragma unroll
-  for (int rep = 0; rep < 8 / R; rep++) {
+  for (int rep = 0; rep < REPS; rep++)
+#pragma unroll
+    for (int r = 0; r < R; r++) u[rep][r] = buf[fft_pad(t + rep * T + r * NB)];
+  if (!LAST) __syncthreads();    // every input is in registers before the buffer is overwritten
+#pragma unroll
+  for (int rep = 0; rep < REPS; rep++) {
     const int i = t + rep * T;
     const int k = i & (p - 1);
     const int j = (i - k) * R + k;
-    float2 u[R];
+    const int ws = k * (NB / p);             // W_N^(r ws), r = 1..R-1
+    float2 w[R];
+    w[1] = __ldg(W + (ws & (N - 1)));
+    if (R >= 4) w[2] = __ldg(W + ((2 * ws) & (N - 1)));
+    if (R >= 8) w[4] = __ldg(W + ((4 * ws) & (N - 1)));
+    if (R >= 16) w[8] = __ldg(W + ((8 * ws) & (N - 1)));
+    if (R >= 4) w[3] = cmul2(w[1], w[2]);
+    if (R >= 8) { w[5] = cmul2(w[1], w[4]); w[6] = cmul2(w[2], w[4]); w[7] = cmul2(w[3], w[4]); }
+    if (R >= 16) {
 #pragma unroll
-    for (int r = 0; r < R; r++) u[r] = PADIN ? in[(i + r * NB) + ((i + r * NB) >> 3)] : in[i + r * NB];
-    const int wstep = k * (N / R) / p;     // W_N^(r k N / (p R))
+      for (int r = 1; r < 8; r++) w[8 + r] = cmul2(w[r], w[8]);
+    }
 #pragma unroll
-    for (int r = 1; r < R; r++) u[r] = cmul2(u[r], W[(r * wstep) & (N - 1)]);
-    dftR<R>(u);
+    for (int r = 1; r < R; r++) u[rep][r] = cmul2(u[rep][r], w[r]);
+    dftR<R>(u[rep]);
 #pragma unroll
-    for (int q = 0; q < R; q++) out[j + q * p] = u[q];
-    (void)NB;
+    for (int q = 0; q < R; q++) {
+      if (LAST) gdst[j + q * p] = u[rep][q];
+      else buf[fft_pad(j + q * p)] = u[rep][q];
+    }
   }
   if (!LAST) __syncthreads();
 }
 
 template <int N>
-__global__ void __launch_bounds__(N / 8) acq_fftd_kernel(int nsym, const float2 *__restrict__ x, const SymOut *__restrict__ so,
-                                                         float2 *__restrict__ out, const float2 *__restrict__ W) {
-  extern __shared__ __align__(16) float2 s_fft[];   // two buffers of N (+ N/8 pad for the first)
-  float2 *bufA = s_fft, *bufB = s_fft + N + N / 8;
-  constexpr int T = N / 8;
+__global__ void __launch_bounds__(N / 16) acq_fftd_kernel(int nsym, const float2 *__restrict__ x, const SymOut *__restrict__ so,
+                                                          float2 *__restrict__ out, const float2 *__restrict__ W) {
+  extern __shared__ __align__(16) float2 s_fft[];   // N + N/16
+  constexpr int T = N / 16;
   const int n = blockIdx.x, t = threadIdx.x;
   if (n >= nsym) return;
   const SymOut s = so[n];
-  // pass 0 (radix 8, p = 1) straight from global memory with the derotation
+  // pass 0 (radix 16, p = 1) straight from global memory with the derotation
   {
-    float2 u[8];
+    float2 u[16];
 #pragma unroll
-    for (int r = 0; r < 8; r++) u[r] = __ldg(x + s.first + t + r * T);
+    for (int r = 0; r < 16; r++) u[r] = __ldg(x + s.first + t + r * T);
 #pragma unroll
-    for (int r = 0; r < 8; r++) {
+    for (int r = 0; r < 16; r++) {
       const int j = t + r * T;
       const int steps = j + 1;  // the phase is incremented before it is used (:291-307)
       double ph = s.phase0 + (steps <= s.switch_at ? steps * s.inc0 : s.switch_at * s.inc0 + (steps - s.switch_at) * s.inc1);
@@ -929,21 +977,19 @@ __global__ void __launch_bounds__(N / 8) acq_fftd_kernel(int nsym, const float2 
       if (j & 1) v = make_float2(-v.x, -v.y);     // fft_vxx(shift = true)
       u[r] = v;
     }
-    dft8(u);
+    dft16(u);
 #pragma unroll
-    for (int q = 0; q < 8; q++) bufA[9 * t + q] = u[q];   // index 8t+q, padded: + (8t+q >> 3) = + t
+    for (int q = 0; q < 16; q++) s_fft[17 * t + q] = u[q];   // fft_pad(16 t + q)
     __syncthreads();
   }
   float2 *dst = out + (long long)n * N;
   if (N == 2048) {
-    fft_pass<N, 8, false, true>(bufA, bufB, 8, W, t);
-    fft_pass<N, 8, false>(bufB, bufA, 64, W, t);
-    fft_pass<N, 4, true>(bufA, dst, 512, W, t);
+    fft16_pass<N, 16, false>(s_fft, dst, 16, W, t);
+    fft16_pass<N, 8, true>(s_fft, dst, 256, W, t);
   } else {
-    fft_pass<N, 8, false, true>(bufA, bufB, 8, W, t);
-    fft_pass<N, 8, false>(bufB, bufA, 64, W, t);
-    fft_pass<N, 8, false>(bufA, bufB, 512, W, t);
-    fft_pass<N, 2, true>(bufB, dst, 4096, W, t);
+    fft16_pass<N, 16, false>(s_fft, dst, 16, W, t);
+    fft16_pass<N, 16, false>(s_fft, dst, 256, W, t);
+    fft16_pass<N, 2, true>(s_fft, dst, 4096, W, t);
   }
 }
 
@@ -1081,12 +1127,12 @@ int acq_run(dvbt_b200_acq *h, const float2 *x, long long n, float2 *d_out, long 
     }
     if (hs->n_out > 0 && fused_fft) {
       if (p.N == 2048) {
-        acq_fftd_kernel<2048><<<hs->n_out, 256, (2 * 2048 + 256) * sizeof(float2), st>>>(hs->n_out, x, h->d_sym.as<SymOut>(), d_out + produced * p.N,
-                                                                                 h->d_tw.as<float2>());
+        acq_fftd_kernel<2048><<<hs->n_out, 128, (2048 + 128) * sizeof(float2), st>>>(hs->n_out, x, h->d_sym.as<SymOut>(), d_out + produced * p.N,
+                                                                             h->d_tw.as<float2>());
       } else {
-        DVBT_CUDA_TRY(cudaFuncSetAttribute(acq_fftd_kernel<8192>, cudaFuncAttributeMaxDynamicSharedMemorySize, (2 * 8192 + 1024) * (int)sizeof(float2)));
-        acq_fftd_kernel<8192><<<hs->n_out, 1024, (2 * 8192 + 1024) * sizeof(float2), st>>>(hs->n_out, x, h->d_sym.as<SymOut>(), d_out + produced * p.N,
-                                                                                  h->d_tw.as<float2>());
+        DVBT_CUDA_TRY(cudaFuncSetAttribute(acq_fftd_kernel<8192>, cudaFuncAttributeMaxDynamicSharedMemorySize, (8192 + 512) * (int)sizeof(float2)));
+        acq_fftd_kernel<8192><<<hs->n_out, 512, (8192 + 512) * sizeof(float2), st>>>(hs->n_out, x, h->d_sym.as<SymOut>(), d_out + produced * p.N,
+                                                                             h->d_tw.as<float2>());
       }
       count_launch();
       DVBT_CUDA_TRY(cudaGetLastError());

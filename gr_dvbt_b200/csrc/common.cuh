@@ -42,6 +42,20 @@ inline int current_device() {
   return d;
 }
 
+// Entry points that take DEVICE pointers run on the handle's own non-blocking stream, which does not order itself
+// against the legacy default stream - where cudaMemset/cudaMemcpy and PyTorch's allocations, fills and copies run.
+// Work the caller queued there before the call (e.g. zero-filling the output buffer) must not overtake or trail the
+// handle's kernels, so the handle's stream first waits for everything already queued on the default stream.
+inline int join_default_stream(cudaStream_t st) {
+  cudaEvent_t ev;
+  DVBT_CUDA_TRY(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+  cudaError_t e = cudaEventRecord(ev, cudaStreamLegacy);
+  if (e == cudaSuccess) e = cudaStreamWaitEvent(st, ev, 0);
+  cudaEventDestroy(ev);   // released once the wait has been satisfied
+  DVBT_CUDA_TRY(e);
+  return 0;
+}
+
 // A growable device (or pinned-host) buffer; never shrinks.
 struct DevBuf {
   void *p = nullptr;

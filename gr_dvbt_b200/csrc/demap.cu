@@ -164,7 +164,9 @@ int dvbt_b200_demap_points(const dvbt_b200_demap *h, float *re_im, int capacity_
 int dvbt_b200_demap_run_dev(dvbt_b200_demap *h, const void *d_in, size_t ncells, uint8_t *d_out) {
   dvbt::DeviceScope dev_scope__(h ? h->device : -1);
   if (!h || (ncells && (!d_in || !d_out))) { dvbt::set_error("demap_run_dev: bad argument"); return DVBT_B200_EINVAL; }
-  int rc = dvbt::demap_launch(h->table, (const float2 *)d_in, d_out, (long long)ncells, h->stream);
+  int rc = dvbt::join_default_stream(h->stream);
+  if (rc) return rc;
+  rc = dvbt::demap_launch(h->table, (const float2 *)d_in, d_out, (long long)ncells, h->stream);
   if (rc) return rc;
   DVBT_CUDA_TRY(cudaStreamSynchronize(h->stream));
   return 0;

@@ -36,9 +36,11 @@ between two lane moves there are at most 5 steps.  Per byte time (positions of t
 The unzip/zip pair costs what one lane move plus the two extractions would, clears the paths for free and
 gives the event code the same 4-states-per-word format as the byte-SWAR kernel.
 
-Branch metrics.  APK = bytes A[L], L = 2*c0 + c1 (see gen_viterbi_acs.py).  The two lanes of a register differ in
-one state bit, so their labels differ by a fixed XOR per lane position: 4 distinct addend words per step and
-kind, each one PRMT of APK (and one addition for the words that carry the decision bit).
+Branch metrics.  A[L], L = 2*c0 + c1, is the number of agreeing, non-erased code bits of a branch with label L
+(see gen_viterbi_acs.py).  The two lanes of a register differ in one state bit, so their labels differ by a fixed
+XOR f that depends only on the lane position: per step there are 4 distinct addend words
+Q[L] = A[L] << 8 | A[L ^ f] << 24.  The kernel reads all four with one 16-byte shared-memory load from a table
+indexed by (f, step code nibble); the words that also carry the decision bit cost one addition each.
 """
 import os
 
@@ -66,19 +68,18 @@ class Gen:
     def emit(self, *op):
         self.ops.append(op)
 
-    def butterfly_step(self, V, apk, jbit):
-        """V: list of (name, (s_lo, s_hi)).  One trellis step; the decision goes to path bit `jbit`."""
+    def butterfly_step(self, V, apk, jbit, lane_pos):
+        """V: list of (name, (s_lo, s_hi)).  One trellis step; the decision goes to path bit `jbit`.
+        apk: name of the uint4 holding the addend words Q[0..3] for this step and lane position."""
         idx = {w[1]: w[0] for w in V}
         out = []
         plain, withbit = {}, {}
         bitconst = 0x00010001 << jbit
+        f = lane_xor(lane_pos)
 
         def addend(labels, bit):
-            if labels not in plain:
-                r = self.new("bm")
-                # bytes: (0, A[L_lo], 0, A[L_hi]); selector nibble 4 reads the zero operand
-                self.emit("prmt", r, apk, "ZERO", 4 | (labels[0] << 4) | (4 << 8) | (labels[1] << 12))
-                plain[labels] = r
+            assert labels[1] == labels[0] ^ f
+            plain[labels] = "%s.%s" % (apk, "xyzw"[labels[0]])
             if not bit:
                 return plain[labels]
             if labels not in withbit:
@@ -124,6 +125,15 @@ class Gen:
         return out
 
 
+def lane_xor(lane_pos):
+    """label(state with bit lane_pos set) = label(state) ^ lane_xor(lane_pos)"""
+    return 2 * ((POLYA >> (lane_pos + 1)) & 1) + ((POLYB >> (lane_pos + 1)) & 1)
+
+
+# lane position before each step, in macro-argument order (steps 1..6 of part 1, then 7, 8 of part 2)
+STEP_LANE_POS = [2, 3, 4, 2, 3, 4, 0, 1]
+
+
 def layout(lane_pos):
     """canonical 32 registers for the lane bit at state position lane_pos, ordered by the other 5 bits"""
     rest = [p for p in range(6) if p != lane_pos]
@@ -149,13 +159,13 @@ def build():
     # ---- part 1: steps 1..6, lane move after step 3, unzip
     g = Gen()
     V = [("V[%d]" % i, st) for i, st in enumerate(L_start)]
-    V = g.butterfly_step(V, "apk0", 2); check_layout(V, 3)
-    V = g.butterfly_step(V, "apk1", 3); check_layout(V, 4)
-    V = g.butterfly_step(V, "apk2", 4); check_layout(V, 5)
+    V = g.butterfly_step(V, "apk0", 2, STEP_LANE_POS[0]); check_layout(V, 3)
+    V = g.butterfly_step(V, "apk1", 3, STEP_LANE_POS[1]); check_layout(V, 4)
+    V = g.butterfly_step(V, "apk2", 4, STEP_LANE_POS[2]); check_layout(V, 5)
     V = g.swap(V, 5, 2); check_layout(V, 2)
-    V = g.butterfly_step(V, "apk3", 5); check_layout(V, 3)
-    V = g.butterfly_step(V, "apk4", 6); check_layout(V, 4)
-    V = g.butterfly_step(V, "apk5", 7); check_layout(V, 5)
+    V = g.butterfly_step(V, "apk3", 5, STEP_LANE_POS[3]); check_layout(V, 3)
+    V = g.butterfly_step(V, "apk4", 6, STEP_LANE_POS[4]); check_layout(V, 4)
+    V = g.butterfly_step(V, "apk5", 7, STEP_LANE_POS[5]); check_layout(V, 5)
     idx = {w[1]: w[0] for w in V}
     for w in range(16):
         s0, s1, s2, s3 = event_word_states(w)
@@ -202,13 +212,20 @@ def build():
         g.emit("prmt", b, "M[%d]" % w, "ZERO", 0x3414)   # (0, m(s1), 0, m(s3)): bit 5 = 1
         V += [(a, (s0, s2)), (b, (s1, s3))]
     check_layout(V, 0)
-    V = g.butterfly_step(V, "apk6", 0); check_layout(V, 1)
-    V = g.butterfly_step(V, "apk7", 1); check_layout(V, 2)
+    V = g.butterfly_step(V, "apk6", 0, STEP_LANE_POS[6]); check_layout(V, 1)
+    V = g.butterfly_step(V, "apk7", 1, STEP_LANE_POS[7]); check_layout(V, 2)
     idx = {w[1]: w[0] for w in V}
     for i, st in enumerate(L_start):
         g.emit("mov", "V_nx[%d]" % i, idx[st])
     part2 = g.ops
     return dict(part1=part1, part2=part2, argmax=argmax, L_start=L_start)
+
+
+def addend_words(nib, f):
+    """Q[0..3] for step code nibble nib = sym0 | valid0<<1 | sym1<<2 | valid1<<3 and lane XOR f"""
+    s0, v0, s1, v1 = nib & 1, (nib >> 1) & 1, (nib >> 2) & 1, (nib >> 3) & 1
+    A = [v0 * int((L >> 1) == s0) + v1 * int((L & 1) == s1) for L in range(4)]
+    return [(A[L] << 8) | (A[L ^ f] << 24) for L in range(4)]
 
 
 def event_byte_index(s):
@@ -333,6 +350,7 @@ def main():
                "// event layout: word w = state bits (4,3,2,1), byte = 2*bit0 + bit5; V_ev[32] = the halfword registers at the\n"
                "// event, V_ev[r] = states (r, r+32).  Path bytes are bit reversed with respect to the reference's (first\n"
                "// decision after the clear in bit 0).\n"
+               "// apk0..apk5: uint4 of addend words Q[0..3] of steps 1..6 (table row f = VITH_STEP_F(step)).\n"
                "#define VITH_ACS_PART1(V, M_ev, P_ev, V_ev, apk0, apk1, apk2, apk3, apk4, apk5) \\\n")
     body = emit_cuda(res["part1"])
     out.append("  do { \\\n" + "\n".join(l + " \\" for l in body.split("\n")) + "\n  } while (0)\n\n")
@@ -346,6 +364,9 @@ def main():
                "#define VITH_ARGMAX(V_ev, BEST) \\\n")
     body = emit_cuda(res["argmax"])
     out.append("  do { \\\n" + "\n".join(l + " \\" for l in body.split("\n")) + "\n  } while (0)\n\n")
+    out.append("// lane XOR f of step i (0..5: steps 1..6, 6..7: steps 7, 8): row of the addend table to read\n"
+               "#define VITH_STEP_F(i) (%s)\n\n" % " : ".join(["(i) == %d ? %d" % (i, lane_xor(p)) for i, p in enumerate(STEP_LANE_POS[:-1])]
+                                                              + ["%d" % lane_xor(STEP_LANE_POS[-1])]))
     for s in range(64):
         bi = event_byte_index(s)
         assert event_word_states(bi >> 2)[bi & 3] == s and event_state(bi >> 2, bi & 3) == s

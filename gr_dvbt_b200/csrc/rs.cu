@@ -424,7 +424,9 @@ int dvbt_b200_rsdec_set_compat(dvbt_b200_rsdec *h, int as_built) {
 int dvbt_b200_rsdec_decode_dev(dvbt_b200_rsdec *h, const uint8_t *d_in, size_t npackets, uint8_t *d_out, int *d_status) {
   dvbt::DeviceScope dev_scope__(h ? h->device : -1);
   if (!h || (npackets && (!d_in || !d_out))) { dvbt::set_error("rsdec_decode_dev: bad argument"); return DVBT_B200_EINVAL; }
-  int rc = dvbt::rs_launch(d_in, d_out, d_status, (long long)npackets, h->as_built, h->sm_count, h->stream, -1);
+  int rc = dvbt::join_default_stream(h->stream);
+  if (rc) return rc;
+  rc = dvbt::rs_launch(d_in, d_out, d_status, (long long)npackets, h->as_built, h->sm_count, h->stream, -1);
   if (rc) return rc;
   DVBT_CUDA_TRY(cudaStreamSynchronize(h->stream));
   return 0;

@@ -480,6 +480,7 @@ int dvbt_b200_rx_run_freq_host(dvbt_b200_rx *h, const void *X, size_t nsym, uint
 int dvbt_b200_rx_run_freq_dev(dvbt_b200_rx *h, const void *dX, size_t nsym, uint8_t *d_ts, size_t ts_capacity, size_t *ts_bytes) {
   dvbt::DeviceScope dev_scope__(h ? h->device : -1);
   if (!h || (nsym && !dX) || !d_ts) { set_error("rx_run_freq_dev: bad argument"); return DVBT_B200_EINVAL; }
+  if (int rc = dvbt::join_default_stream(h->stream)) return rc;
   return rx_run_freq(h, (const float2 *)dX, nsym, nullptr, d_ts, ts_capacity, ts_bytes, 0);
 }
 
@@ -520,6 +521,7 @@ int dvbt_b200_rx_run_baseband_host(dvbt_b200_rx *h, const void *samples, size_t 
 int dvbt_b200_rx_run_baseband_dev(dvbt_b200_rx *h, const void *d_samples, size_t nsamples, uint8_t *d_ts, size_t ts_capacity, size_t *ts_bytes) {
   dvbt::DeviceScope dev_scope__(h ? h->device : -1);
   if (!h || (nsamples && !d_samples) || !d_ts) { set_error("rx_run_baseband_dev: bad argument"); return DVBT_B200_EINVAL; }
+  if (int rc = dvbt::join_default_stream(h->stream)) return rc;
   return rx_run_baseband(h, (const float2 *)d_samples, nsamples, nullptr, d_ts, ts_capacity, ts_bytes, 0);
 }
 
@@ -556,6 +558,7 @@ int dvbt_b200_rx_run_file_dev(dvbt_b200_rx *h, const void *d_samples, size_t nsa
                               size_t *ts_bytes) {
   dvbt::DeviceScope dev_scope__(h ? h->device : -1);
   if (!h || (nsamples && !d_samples) || !d_ts) { set_error("rx_run_file_dev: bad argument"); return DVBT_B200_EINVAL; }
+  if (int rc = dvbt::join_default_stream(h->stream)) return rc;
   return rx_run_file(h, (const float2 *)d_samples, nsamples, gain, nullptr, d_ts, ts_capacity, ts_bytes, 0);
 }
 

@@ -113,7 +113,10 @@ int dvbt_b200_viterbi_work(dvbt_b200_viterbi *h, const uint8_t *in, size_t n_in_
  * Stream s reads n_in bytes at in + s*in_stride and writes n_in*k*m/(8n) - ntraceback bytes
  * at out + s*out_stride (*n_out receives that count).  n_in*m*k must be a multiple of 8n.
  * _host: pageable or pinned host pointers (copies are inside the call).
- * _dev:  device pointers; returns after the stream has been synchronised. */
+ * _dev:  device pointers; returns after the stream has been synchronised.  Every *_dev entry
+ *        point of this library first makes its own (non-blocking) stream wait for the work
+ *        already queued on the legacy default stream, so buffers that the caller filled or
+ *        zeroed there (cudaMemset, cudaMemcpy, PyTorch) are ordered before the kernels. */
 int dvbt_b200_viterbi_decode_host(dvbt_b200_viterbi *h, const uint8_t *in, size_t in_stride,
                                   size_t n_in, int nstreams, uint8_t *out, size_t out_stride,
                                   size_t *n_out);

@@ -183,7 +183,11 @@ def decode_chunk_h16(codes, jstart, jend, first_real, ntb, out, save_at=(), init
         j = jstart - 1
     while j < jend:
         code = int(codes[j]) if j < len(codes) else 0
-        apk = [one(lut[(code >> (4 * i)) & 15]) for i in range(8)]
+        apk = {}
+        for i in range(8):
+            q = H.addend_words((code >> (4 * i)) & 15, H.lane_xor(H.STEP_LANE_POS[i]))
+            for c, v in zip("xyzw", q):
+                apk["apk%d.%s" % (i, c)] = one(v)
         if resume:
             Mev = [one(x) for x in init_metrics]
             resume = False
@@ -191,8 +195,7 @@ def decode_chunk_h16(codes, jstart, jend, first_real, ntb, out, save_at=(), init
             env = {"ZERO": one(0)}
             for i in range(32):
                 env["V[%d]" % i] = V[i]
-            for i in range(6):
-                env["apk%d" % i] = apk[i]
+            env.update(apk)
             H.run_ops(S["part1"], env)
             Mev = [env["M_ev[%d]" % i] for i in range(16)]
             Pev = [env["P_ev[%d]" % i] for i in range(16)]
@@ -236,7 +239,7 @@ def decode_chunk_h16(codes, jstart, jend, first_real, ntb, out, save_at=(), init
         env = {"ZERO": one(0)}
         for i in range(16):
             env["M[%d]" % i] = Mev[i]
-        env["apk6"], env["apk7"] = apk[6], apk[7]
+        env.update(apk)
         H.run_ops(S["part2"], env)
         V = [env["V_nx[%d]" % i] for i in range(32)]
         j += 1
