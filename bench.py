@@ -91,6 +91,8 @@ class ClockSampler:
         self.proc = None
 
     def start(self):
+        if os.environ.get("BENCH_SAMPLER", "1") == "0":   # diagnostic switch: no nvidia-smi process during the timed region
+            return
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
@@ -462,7 +464,18 @@ def run_cpu_all_cores(reps, workload):
     return bits / max(r[1] for r in res), cores, res[0][2], float(np.mean(per_core)), wall
 
 
+def claim_stdout():
+    """The contract is ONE JSON line on stdout.  Libraries loaded later print there too (NCCL's version banner, for
+    one), so file descriptor 1 is pointed at stderr for the rest of the run and the JSON line goes to a private copy of
+    the original stdout."""
+    sys.stdout.flush()
+    keep = os.dup(1)
+    os.dup2(2, 1)
+    return os.fdopen(keep, "w")
+
+
 def main():
+    out = claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
@@ -483,7 +496,7 @@ def main():
         if rx:
             from oracle import refchain as R
             if not R.available():
-                print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref (reference sources compiled verbatim) was not built on this box"}))
+                print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref (reference sources compiled verbatim) was not built on this box"}), file=out, flush=True)
                 return 0
             cpu_rx_prepare()
             w = RxWorkload(a.tiles)
@@ -503,7 +516,7 @@ def main():
                 "scaling": "weak", "vs_baseline": None, "dtype": "u8/f32", "data": "synthetic", "config": w.describe(),
                 "cpu_baseline": {"value": v, "unit": unit.split(" (")[0], "cores": cores, "kind": kind, "sample": sample},
                 "e2e": {"value": v, "unit": unit.split(" (")[0], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-        print(json.dumps(line))
+        print(json.dumps(line), file=out, flush=True)
         return 0
 
     import torch
@@ -533,8 +546,11 @@ def main():
         t0 = time.perf_counter()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
+        per_step = []
         for i in range(steps):
+            ts = time.perf_counter()
             stepfn(warm + i)
+            per_step.append((time.perf_counter() - ts) * 1e3)
             w.last_i = warm + i
         e1.record()
         torch.cuda.synchronize()
@@ -543,6 +559,8 @@ def main():
         # every step synchronises its own stream inside the C ABI, so host wall time between the
         # barriers brackets the device work; take the larger of the two clocks
         ms = max(dev_ms, wall_ms)
+        if os.environ.get("BENCH_VERBOSE"):
+            sys.stderr.write("[bench rank %d] per-step wall ms: %s\n" % (RANK, " ".join("%.2f" % v for v in per_step)))
         ms = max_over_ranks(ms, "cuda")
         barrier()
         return ms
@@ -553,6 +571,9 @@ def main():
     sampler.start()
     ms = timed(w.step_resident, a.steps, a.warmup)
     clocks = sampler.stop()
+    if rx:
+        sys.stderr.write("[bench rank %d] resident: %.3f ms/step (max over ranks), sum of this rank's stage times %.3f ms\n"
+                         % (RANK, ms / a.steps, float(np.mean([sum(v for k, v in s_.items() if k != "ms_viterbi_acs") for s_ in w.stage_ms[a.warmup:]]))))
     launches = (lib.dvbt_b200_kernel_launches() - l0) * a.steps // (a.steps + a.warmup)
     ok = w.check()
     kms = float(np.mean(w.kernel_ms[a.warmup:]))
@@ -614,7 +635,7 @@ def main():
                                     "LOP3/PRMT/IADD3; ncu: see the `ncu` object), so the HBM fraction is small by nature; DRAM traffic above the "
                                     "algorithmic bytes is the survivor-row write-through to the global ring (deliberate: it frees shared memory "
                                     "for 3x the resident warps); ACS rate = %.1f T state-updates/s" % (info_bits * 64 / (kms / 1e3) / 1e12)}
-        print(json.dumps(line))
+        print(json.dumps(line), file=out, flush=True)
     if WORLD > 1:
         dist.destroy_process_group()
     return 0
