@@ -77,7 +77,7 @@ def streams_of_rank(nstreams, world, rank):
 
 
 def seed_of_rank(rank, base=1):
-    return base + rank
+    return env_int("BENCH_SEED", base) + rank
 
 
 class ClockSampler:
@@ -572,6 +572,10 @@ def main():
     ms = timed(w.step_resident, a.steps, a.warmup)
     clocks = sampler.stop()
     if rx:
+        if os.environ.get("BENCH_VERBOSE"):
+            keys = [k for k in w.stage_ms[-1]]
+            sys.stderr.write("[bench rank %d] stages: %s | info: %s\n" % (RANK, " ".join("%s=%.3f" % (k[3:], float(np.mean([s_[k] for s_ in w.stage_ms[a.warmup:]]))) for k in keys),
+                                                                        json.dumps({k: v for k, v in w.info.items() if not k.startswith("ms_")})))
         sys.stderr.write("[bench rank %d] resident: %.3f ms/step (max over ranks), sum of this rank's stage times %.3f ms\n"
                          % (RANK, ms / a.steps, float(np.mean([sum(v for k, v in s_.items() if k != "ms_viterbi_acs") for s_ in w.stage_ms[a.warmup:]]))))
     launches = (lib.dvbt_b200_kernel_launches() - l0) * a.steps // (a.steps + a.warmup)

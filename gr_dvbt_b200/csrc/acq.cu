@@ -256,20 +256,22 @@ __global__ void acq_lambda_kernel(AcqParams p, const float2 *__restrict__ x, lon
 // [c, c+16), cp_start = c0 - kD + 8 + c).  d_avg after the 16 values of a window is, to float
 // precision, independent of the average it started from, so it is speculated and then verified:
 //   pass 1: avg1[n][c] = average after window (n, c) starting from 0
-//   pass 2: for state s = (c, d), d = previous offset - c in [-2, 2]: run the detector on window (n, c)
+//   pass 2: for state s = (c, d), d = previous offset - c in [-kHD, kHD]: run the detector on window (n, c)
 //           starting from avg1[n-1][c+d]; best[n][s], avg2[n][s], and the successor state
 //           next[n][s] = (c + best - 8, 8 - best) — or a stop code when the peak is missed, the next window
-//           leaves the table, or the speculation cannot be continued (|move| > 2, or avg2 != avg1[n][c]
+//           leaves the table, or the speculation cannot be continued (|move| > kHD, or avg2 != avg1[n][c]
 //           bit-for-bit, i.e. the successor's assumed input would not be the true average).
 // The true trajectory is then the composition next[n-1] o ... o next[0] applied to the start state:
-// acq_compose_kernel composes 32-symbol chunks for all 85 start states in parallel, chains the chunk
+// acq_compose_kernel composes 32-symbol chunks for all kNS start states in parallel, chains the chunk
 // maps, re-walks every chunk from its now known start state, and acq_finish_kernel turns the per-symbol
 // (offset, best) into output descriptors with a warp scan of the phase schedule (:285-312).  A stop code
 // ends the batch early; the host loop continues from there with the true state (exactness never rests
 // on the speculation).
 constexpr int kNC = kCand - 16 + 1;  // 17 window offsets
-constexpr int kND = 5;               // previous-offset deltas -2..2
-constexpr int kNS = kNC * kND;       // 85 states
+constexpr int kHD = 3;               // |previous offset - offset| covered by the tables (peaks 5..11 of 0..15: a noise-free
+                                     // QAM64 capture already jitters by +-3 through the resampler, measured in profiles/README.md)
+constexpr int kND = 2 * kHD + 1;     // previous-offset deltas -3..3
+constexpr int kNS = kNC * kND;       // 119 states
 constexpr unsigned char kLost = 0xFE, kOff = 0xFD, kSplit = 0xFC, kStop = 0xF0;
 constexpr int kChunk = 32;
 
@@ -287,7 +289,7 @@ __global__ void acq_pass2_kernel(AcqParams p, int nsym, const float *__restrict_
                                  signed char *__restrict__ best2, float *__restrict__ avg2, unsigned char *__restrict__ next) {
   int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= nsym * kNS) return;
-  int n = t / kNS, s = t - n * kNS, c = s / kND, d = s - c * kND - 2;
+  int n = t / kNS, s = t - n * kNS, c = s / kND, d = s - c * kND - kHD;
   int cp = c + d;
   signed char res = -2;
   float avg = 0.f;
@@ -301,8 +303,8 @@ __global__ void acq_pass2_kernel(AcqParams p, int nsym, const float *__restrict_
       res = (signed char)best;
       int cn = c + best - 8, dn = 8 - best;
       if (cn < 0 || cn >= kNC) nx = kOff;
-      else if (dn < -2 || dn > 2 || __float_as_uint(avg) != __float_as_uint(avg1[n * kNC + c])) nx = kSplit;
-      else nx = (unsigned char)(cn * kND + dn + 2);
+      else if (dn < -kHD || dn > kHD || __float_as_uint(avg) != __float_as_uint(avg1[n * kNC + c])) nx = kSplit;
+      else nx = (unsigned char)(cn * kND + dn + kHD);
     }
   }
   best2[t] = res;
@@ -322,7 +324,7 @@ struct AcqWalk {
   long long cyc_cmp[4];   // trace: compose chain - staging, table walks, detector re-runs, everything else  // trace: clock64 deltas of the three phases (DVBT_B200_ACQ_TRACE)
 };
 
-// chunk maps: one warp per chunk of `per_thread` symbols, lane = start state (85 states, 3 rounds)
+// chunk maps: one warp per chunk of `per_thread` symbols, lane = start state (kNS states, 4 rounds)
 __global__ void __launch_bounds__(128) acq_chunkmap_kernel(int nsym, int per_thread, int nchunks, const unsigned char *__restrict__ next,
                                                            unsigned char *__restrict__ maps) {
   int w = (int)((blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
@@ -349,7 +351,7 @@ __global__ void __launch_bounds__(128) acq_chunkmap_kernel(int nsym, int per_thr
 // same scalar logic, the lanes cooperate only to fetch table rows / lambda windows with one coalesced
 // round trip (16-byte loads), and lane 0 alone writes results.
 constexpr int kMaxSeg = 2048;
-constexpr int kRowsCap = kChunk * 8;
+constexpr int kRowsCap = kChunk * 2;
 
 // 16-byte-granular copy of `bytes` bytes starting at byte offset `off` of `src` into shared memory;
 // returns the shift to add to indices into `dst` (the copy starts at the aligned address below `off`).
@@ -584,8 +586,8 @@ __global__ void __launch_bounds__(256) acq_compose_kernel(AcqParams p, int nsym,
       n_found = n;
       int c2 = cn + b2 - 8, d2 = 8 - b2;
       if (c2 < 0 || c2 >= kNC) { code = kOff; break; }
-      bool ok = d2 >= -2 && d2 <= 2 && __float_as_uint(avg) == __float_as_uint(ld_avg1(n - 1, cn));
-      if (ok) { st = (unsigned char)(c2 * kND + d2 + 2); break; }   // tables valid again from symbol n
+      bool ok = d2 >= -kHD && d2 <= kHD && __float_as_uint(avg) == __float_as_uint(ld_avg1(n - 1, cn));
+      if (ok) { st = (unsigned char)(c2 * kND + d2 + kHD); break; }   // tables valid again from symbol n
       cn = c2;
     }
     c_over += clock64() - co0;
@@ -1090,9 +1092,9 @@ int acq_run(dvbt_b200_acq *h, const float2 *x, long long n, float2 *d_out, long 
                                                                h->d_maps.as<unsigned char>());
       AcqWalk *d_walk = h->d_eps.as<AcqWalk>();
       if ((rc = h->d_seg.reserve((size_t)kMaxSeg * sizeof(int4)))) return rc;
-      DVBT_CUDA_TRY(cudaFuncSetAttribute(acq_compose_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+      DVBT_CUDA_TRY(cudaFuncSetAttribute(acq_compose_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024));
       acq_compose_kernel<<<1, 256, (size_t)nthreads * kNS + 64, st>>>(
-          p, (int)nsym, per_thread, nthreads, (kD - 8) * kND + 2, hs->avg, h->d_lambda.as<float>(), h->d_avg1.as<float>(),
+          p, (int)nsym, per_thread, nthreads, (kD - 8) * kND + kHD, hs->avg, h->d_lambda.as<float>(), h->d_avg1.as<float>(),
           h->d_peak.as<signed char>(), h->d_avg2.as<float>(), h->d_flag.as<unsigned char>(), h->d_maps.as<unsigned char>(),
           h->d_cof.as<unsigned char>(), h->d_bof.as<signed char>(), h->d_seg.as<int4>(), d_walk);
       {
@@ -1124,6 +1126,35 @@ int acq_run(dvbt_b200_acq *h, const float2 *x, long long n, float2 *d_out, long 
         fprintf(stderr, "acq batch: nsym %lld found %d code %d override %d segments %d staged %d cycles maps %lld serial %lld (stage %lld walk %lld detect %lld rest %lld) | finish %lld %lld %lld %lld %lld\n", nsym,
                 wk.n_found, wk.code, wk.n_override, wk.n_seg, wk.n_staged, wk.cyc_maps, wk.cyc_serial, wk.cyc_cmp[0], wk.cyc_cmp[1], wk.cyc_cmp[2],
                 wk.cyc_cmp[3], wk.cyc_fin[0], wk.cyc_fin[1], wk.cyc_fin[2], wk.cyc_fin[3], wk.cyc_fin[4]);
+    }
+    if (getenv("DVBT_B200_ACQ_TRACE") && atoi(getenv("DVBT_B200_ACQ_TRACE")) >= 2) {
+      // symbols whose peak is off centre, with their lambda windows (diagnostic)
+      std::vector<unsigned char> hc((size_t)nsym);
+      std::vector<signed char> hb((size_t)nsym);
+      std::vector<float> hl((size_t)nsym * kCand), ha1((size_t)nsym * kNC);
+      cudaMemcpy(hc.data(), h->d_cof.p, (size_t)nsym, cudaMemcpyDeviceToHost);
+      cudaMemcpy(hb.data(), h->d_bof.p, (size_t)nsym, cudaMemcpyDeviceToHost);
+      cudaMemcpy(hl.data(), h->d_lambda.p, (size_t)nsym * kCand * 4, cudaMemcpyDeviceToHost);
+      cudaMemcpy(ha1.data(), h->d_avg1.p, (size_t)nsym * kNC * 4, cudaMemcpyDeviceToHost);
+      int shown = 0;
+      {
+        long long hist[17] = {0}, run_far = 0, far = 0;
+        for (long long m = 0; m < nsym; m++) {
+          int b = hb[m] < 0 ? 16 : hb[m];
+          hist[b]++;
+          if (b < 6 || b > 10) { far++; if (m > 0 && (hb[m - 1] < 6 || hb[m - 1] > 10)) run_far++; }
+        }
+        fprintf(stderr, "acq best histogram:");
+        for (int i = 0; i < 17; i++) fprintf(stderr, " %d:%lld", i, hist[i]);
+        fprintf(stderr, " | far %lld, far after far %lld\n", far, run_far);
+      }
+      for (long long m = 1; m < nsym && shown < 0; m++) {
+        if (hb[m] == 8 && hb[m - 1] == 8) continue;
+        shown++;
+        fprintf(stderr, "acq sym %lld c %d best %d avg1 %.9g | lambda:", m, hc[m], hb[m], ha1[m * kNC + hc[m]]);
+        for (int i = 0; i < 16; i++) fprintf(stderr, " %.4g", hl[m * kCand + hc[m] + i]);
+        fprintf(stderr, "\n");
+      }
     }
     if (hs->n_out > 0 && fused_fft) {
       if (p.N == 2048) {
