@@ -129,6 +129,7 @@ struct AcqState {
   int lost_at;        // symbol count at which tracking missed (restart), -1 if never
   int fallback;       // 1 if the sequential detector had to be used
   int n_run, n_single, n_seq;  // symbols handled in quiet runs / one at a time / by the sequential detector
+  int probe_lost1;    // acq_probe_kernel: 1 + index of the first of the next kProbe symbols that misses its peak, 0 = none
 };
 
 struct SymOut {
@@ -241,6 +242,39 @@ __global__ void __launch_bounds__(256) acq_init_peak_kernel(AcqParams p, const f
   }
 }
 
+// ---- look-ahead after an initial acquisition.  A peak found by the N-candidate search is sometimes lost again one or
+// two symbols later (the detector's average still carries the search), and the reference then restarts acquisition
+// half a symbol further on (:545-558).  The tracking tables of a whole capture would be computed for nothing, so this
+// kernel follows the first kProbe symbols the way the reference does (same lambda values, same detector) and tells the
+// host where the first miss is; the host then sizes the first tracking batch to end there.  Advisory only: the batch
+// kernels decide what is output, whatever this kernel says.
+constexpr int kProbe = 4;
+__global__ void __launch_bounds__(kProbe * kCand) acq_probe_kernel(AcqParams p, const float2 *__restrict__ x, long long base, long long nsamples,
+                                                                   AcqState *st) {
+  __shared__ float s_l[kProbe * kCand];
+  const int t = threadIdx.x, n = t / kCand, c = t % kCand;
+  if (!st->initial) { if (t == 0) st->probe_lost1 = 0; return; }
+  const int c0 = st->cp_start, total = p.N + p.cp;
+  long long q = base + (long long)n * total + c0 - kD + c;
+  float lam = -INFINITY;
+  float2 g;
+  if (q < nsamples && q - p.cp - p.N + 1 >= 0) ml_point(x, q, p.N, p.cp, p.rho2, &lam, &g);
+  s_l[t] = lam;
+  __syncthreads();
+  if (t != 0) return;
+  float avg = st->avg;
+  int off = kD - 8, lost1 = 0;
+  for (int m = 0; m < kProbe; m++) {
+    if (off < 0 || off > kCand - 16) break;
+    if (base + (long long)m * total + c0 - kD + off + 15 >= nsamples) break;   // beyond the input: the batch stops there as well
+    int best;
+    int np = peak_detect(s_l + m * kCand + off, 16, &avg, p.rise, p.fall, p.alpha, &best);
+    if (np <= 0) { lost1 = m + 1; break; }
+    off += best - 8;
+  }
+  st->probe_lost1 = lost1;
+}
+
 // ---- tracking table: symbol n, candidate c <-> symbol end at base + n*(N+cp) + c0 - kD + c
 __global__ void acq_lambda_kernel(AcqParams p, const float2 *__restrict__ x, long long base, int c0, int nsym,
                                   float *__restrict__ lambda, float2 *__restrict__ gamma) {
@@ -268,12 +302,13 @@ __global__ void acq_lambda_kernel(AcqParams p, const float2 *__restrict__ x, lon
 // ends the batch early; the host loop continues from there with the true state (exactness never rests
 // on the speculation).
 constexpr int kNC = kCand - 16 + 1;  // 17 window offsets
-constexpr int kHD = 3;               // |previous offset - offset| covered by the tables (peaks 5..11 of 0..15: a noise-free
-                                     // QAM64 capture already jitters by +-3 through the resampler, measured in profiles/README.md)
-constexpr int kND = 2 * kHD + 1;     // previous-offset deltas -3..3
-constexpr int kNS = kNC * kND;       // 119 states
+constexpr int kHD = 4;               // |previous offset - offset| covered by the tables (peaks 4..12 of 0..15: noise-free
+                                     // QAM64 captures already jitter by +-4 through the resampler, histograms in profiles/README.md)
+constexpr int kND = 2 * kHD + 1;     // previous-offset deltas -4..4
+constexpr int kNS = kNC * kND;       // 153 states (< kStop)
 constexpr unsigned char kLost = 0xFE, kOff = 0xFD, kSplit = 0xFC, kStop = 0xF0;
 constexpr int kChunk = 32;
+static_assert(kNS < kStop, "state ids and stop codes share one byte");
 
 __global__ void acq_pass1_kernel(AcqParams p, int nsym, const float *__restrict__ lambda, float *__restrict__ avg1) {
   int t = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1041,16 +1076,19 @@ int acq_run(dvbt_b200_acq *h, const float2 *x, long long n, float2 *d_out, long 
   int guard = 0;
   while (guard++ < 1000000) {
     // ---- initial acquisition (needs 2N+cp+8 samples visible)
+    int probe_lost1 = 0;
     if (!hs->initial) {
       if (n - pos < 2LL * p.N + p.cp + 8 || produced >= out_capacity_syms) break;
       if ((rc = h->d_il.reserve((size_t)p.N * 4)) || (rc = h->d_ig.reserve((size_t)p.N * 8))) return rc;
       acq_init_lambda_kernel<<<(p.N + 127) / 128, 128, 0, st>>>(p, x, pos, h->d_il.as<float>(), h->d_ig.as<float2>());
       DVBT_CUDA_TRY(cudaFuncSetAttribute(acq_init_peak_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, p.N * 8));
       acq_init_peak_kernel<<<1, 256, (size_t)p.N * 8, st>>>(p, h->d_il.as<float>(), h->d_ig.as<float2>(), h->d_state.as<AcqState>());
-      count_launch(2);
+      acq_probe_kernel<<<1, kProbe * kCand, 0, st>>>(p, x, pos, n, h->d_state.as<AcqState>());
+      count_launch(3);
       DVBT_CUDA_TRY(cudaGetLastError());
       DVBT_CUDA_TRY(cudaMemcpyAsync(hs, h->d_state.p, sizeof(AcqState), cudaMemcpyDeviceToHost, st));
       DVBT_CUDA_TRY(cudaStreamSynchronize(st));
+      probe_lost1 = hs->probe_lost1;
       sync_tags++;  // send_sync_start() on every attempt (:507)
       if (!hs->initial) {
         // nothing found: the reference consumes d_to_consume = N+cp (set by ml_sync's miss branch)
@@ -1066,6 +1104,10 @@ int acq_run(dvbt_b200_acq *h, const float2 *x, long long n, float2 *d_out, long 
     if (nsym <= 0) break;
     bool capped = false;   // the finish kernel stages one batch in shared memory: longer inputs go in several batches
     if (nsym > kFinishMax) { nsym = kFinishMax; capped = true; }
+    if (probe_lost1 > 0 && nsym > probe_lost1) {   // the look-ahead saw a miss: no tables beyond it (the miss ends the batch and
+      nsym = probe_lost1;                          // acquisition restarts; if it does not, the next batch simply carries on)
+      capped = true;
+    }
     if ((rc = h->d_lambda.reserve((size_t)nsym * kCand * 4)) || (rc = h->d_gamma.reserve((size_t)nsym * kCand * 8)) ||
         (rc = h->d_avg1.reserve((size_t)nsym * 4)) || (rc = h->d_avg2.reserve((size_t)nsym * 4)) ||
         (rc = h->d_peak.reserve((size_t)nsym * 4)) || (rc = h->d_sym.reserve((size_t)nsym * sizeof(SymOut))))
