@@ -114,6 +114,7 @@ def lib():
         L.dvbt_b200_rx_run_file_host.argtypes = [vp, vp, C.c_size_t, C.c_float, vp, C.c_size_t, C.POINTER(C.c_size_t)]
         L.dvbt_b200_rx_run_file_dev.argtypes = [vp, vp, C.c_size_t, C.c_float, vp, C.c_size_t, C.POINTER(C.c_size_t)]
         L.dvbt_b200_resampler_taps.argtypes = [vp, C.c_int]
+        L.dvbt_b200_resample_host.argtypes = [vp, C.c_size_t, C.c_float, vp, C.c_size_t, C.POINTER(C.c_size_t), C.c_int]
         _lib = L
     return _lib
 

@@ -14,6 +14,7 @@
 #include "chain_internal.cuh"
 
 #include <math.h>
+#include <stdlib.h>
 #include <vector>
 
 namespace dvbt {
@@ -210,6 +211,123 @@ __global__ void __launch_bounds__(256, 3) resample_quad_kernel(const float2 *__r
   }
 }
 
+// Two (NQ) quads per thread.  The quad kernel above is bound by shared-memory bandwidth, and two thirds of it are
+// tap loads: a 16-byte load costs the full four wavefronts even when every lane reads the same address, so the 36 tap
+// loads of a quad cost 144 cycles per warp against 80 for its 40 input samples (ncu: l1tex 91 %, mio throttle).  A
+// thread therefore takes NQ quads with the SAME residue - quads 256 apart, i.e. the same position in NQ consecutive
+// 1024-output sub-tiles - so that one set of tap loads feeds NQ x 4 outputs (lanes stay 35 samples apart: the 8-byte
+// input reads remain conflict free).  The input window of a quad slides through registers (4 + o3 samples live per
+// quad instead of 36 + o3), and the tile is staged with cp.async into a double buffer instead of through registers.
+template <int NQ> struct MultiCfg {
+  static constexpr int kOut = kQuadOut * NQ;            // outputs per tile
+  static constexpr int kIn = kQuadIn * NQ;              // inputs a tile advances by
+  static constexpr int kSpan = kQuadIn * NQ + 40;       // staged inputs: 35 history + kIn + window slack
+  static constexpr int kYUnits = kOut / 2 + kOut / 32;  // float4 units of the padded output tile
+  static constexpr size_t kSmem = (size_t)2 * kSpan * 8 + (size_t)kYUnits * 16 + (size_t)kInterp * kRegArm * 4;
+};
+
+template <int o1, int o2, int o3, int NQ>
+__device__ __forceinline__ void resample_multi(const float2 *__restrict__ s_x, const float *__restrict__ s_taps, float4 *__restrict__ s_y, int lane,
+                                               int R, float scale) {
+  const int f = (12 * R) % 32;                       // (35 * 4v) mod 32 for v = R (mod 8)
+  const int p0 = f, p1 = (f + 3) % 32, p2 = (f + 6) % 32, p3 = (f + 9) % 32;
+  const int top = 35 * lane + (35 * R) / 8 + 35 + o3;  // sub-tile-local index of the newest input of output 4v+3
+  float2 xs[NQ][kRegArm + o3];                       // compile-time indexed: only a sliding part is ever live
+  float acc[NQ][8];
+#pragma unroll
+  for (int q = 0; q < NQ; q++) {
+#pragma unroll
+    for (int k = 0; k < o3; k++) xs[q][k] = s_x[top + q * kQuadIn - k];
+#pragma unroll
+    for (int k = 0; k < 8; k++) acc[q][k] = 0.f;
+  }
+  const float4 *t0 = reinterpret_cast<const float4 *>(s_taps + p0 * kRegArm), *t1 = reinterpret_cast<const float4 *>(s_taps + p1 * kRegArm),
+               *t2 = reinterpret_cast<const float4 *>(s_taps + p2 * kRegArm), *t3 = reinterpret_cast<const float4 *>(s_taps + p3 * kRegArm);
+#pragma unroll
+  for (int jj = 0; jj < kRegArm / 4; jj++) {
+    const float4 h0 = t0[jj], h1 = t1[jj], h2 = t2[jj], h3 = t3[jj];
+    const float a0[4] = {h0.x, h0.y, h0.z, h0.w}, a1[4] = {h1.x, h1.y, h1.z, h1.w}, a2[4] = {h2.x, h2.y, h2.z, h2.w},
+                a3[4] = {h3.x, h3.y, h3.z, h3.w};
+#pragma unroll
+    for (int q = 0; q < NQ; q++) {
+#pragma unroll
+      for (int u = 0; u < 4; u++) xs[q][4 * jj + o3 + u] = s_x[top + q * kQuadIn - (4 * jj + o3 + u)];
+    }
+#pragma unroll
+    for (int q = 0; q < NQ; q++) {
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        const int j = 4 * jj + u;
+        acc[q][0] = fmaf(a0[u], xs[q][j + o3].x, acc[q][0]);
+        acc[q][1] = fmaf(a0[u], xs[q][j + o3].y, acc[q][1]);
+        acc[q][2] = fmaf(a1[u], xs[q][j + o3 - o1].x, acc[q][2]);
+        acc[q][3] = fmaf(a1[u], xs[q][j + o3 - o1].y, acc[q][3]);
+        acc[q][4] = fmaf(a2[u], xs[q][j + o3 - o2].x, acc[q][4]);
+        acc[q][5] = fmaf(a2[u], xs[q][j + o3 - o2].y, acc[q][5]);
+        acc[q][6] = fmaf(a3[u], xs[q][j].x, acc[q][6]);
+        acc[q][7] = fmaf(a3[u], xs[q][j].y, acc[q][7]);
+      }
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < NQ; q++) {
+    const int qi = 8 * lane + R + 256 * q;           // quad index inside the tile
+    const int unit = 2 * qi + qi / 8;                // 16-byte units, one pad unit per 8 quads: conflict-free stores
+    s_y[unit] = make_float4(acc[q][0] * scale, acc[q][1] * scale, acc[q][2] * scale, acc[q][3] * scale);
+    s_y[unit + 1] = make_float4(acc[q][4] * scale, acc[q][5] * scale, acc[q][6] * scale, acc[q][7] * scale);
+  }
+}
+
+template <int NQ>
+__global__ void __launch_bounds__(256, 3) resample_multi_kernel(const float2 *__restrict__ x, long long nin, float2 *__restrict__ y, long long nout,
+                                                                const float *__restrict__ taps_arm, long long ntiles, float scale) {
+  using Cfg = MultiCfg<NQ>;
+  extern __shared__ __align__(16) unsigned char s_raw[];
+  float4 *s_y = reinterpret_cast<float4 *>(s_raw);
+  float *s_taps = reinterpret_cast<float *>(s_raw + (size_t)Cfg::kYUnits * 16);
+  float2 *s_xbuf = reinterpret_cast<float2 *>(s_raw + (size_t)Cfg::kYUnits * 16 + (size_t)kInterp * kRegArm * 4);
+  const int t = threadIdx.x, lane = t & 31, w = t >> 5;
+  // stage the inputs of `tile` into buffer b: 8-byte cp.async, samples outside [0, nin) are zero filled (src-size 0)
+  auto stage = [&](long long tile, int b) {
+    const long long lo = tile * Cfg::kIn - 35;
+    float2 *dst = s_xbuf + (size_t)b * Cfg::kSpan;
+    for (int i = t; i < Cfg::kSpan; i += 256) {
+      const long long idx = lo + i;
+      const bool in = idx >= 0 && idx < nin;
+      const unsigned d = (unsigned)__cvta_generic_to_shared(dst + i);
+      const float2 *src = x + (in ? idx : 0);
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(d), "l"(src), "r"(in ? 8 : 0) : "memory");
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  for (int i = t; i < kInterp * kRegArm; i += 256) s_taps[i] = taps_arm[i];
+  long long tile = blockIdx.x;
+  int b = 0;
+  if (tile < ntiles) stage(tile, 0);
+  for (; tile < ntiles; tile += gridDim.x, b ^= 1) {
+    const bool more = tile + gridDim.x < ntiles;
+    if (more) stage(tile + gridDim.x, b ^ 1);        // the other buffer was last read before the barrier that ended the previous tile
+    if (more) asm volatile("cp.async.wait_group 1;" ::: "memory");
+    else asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();
+    const float2 *s_x = s_xbuf + (size_t)b * Cfg::kSpan;
+    if (w == 2) resample_multi<1, 2, 4, NQ>(s_x, s_taps, s_y, lane, w, scale);
+    else if (w == 5) resample_multi<1, 3, 4, NQ>(s_x, s_taps, s_y, lane, w, scale);
+    else resample_multi<1, 2, 3, NQ>(s_x, s_taps, s_y, lane, w, scale);
+    __syncthreads();
+    const float2 *s_y2 = reinterpret_cast<const float2 *>(s_y);
+    const long long m0 = tile * Cfg::kOut;
+#pragma unroll
+    for (int k = 0; k < Cfg::kOut / 256; k++) {
+      int o = t + 256 * k;
+      int q = o >> 2;
+      long long m = m0 + o;
+      if (m < nout) y[m] = s_y2[2 * (2 * q + (q >> 3) + ((o >> 1) & 1)) + (o & 1)];
+    }
+    // the next iteration's first barrier orders these reads of s_y before its writes
+  }
+}
+
 struct Resampler {
   DevBuf d_taps;
   int per_arm = 0, sm_count = 148;
@@ -233,7 +351,15 @@ static Resampler *g_res[64] = {nullptr};
 
 long long resample_out_count(long long nin) { return nin <= 0 ? 0 : ((nin - 1) * kInterp) / kDecim + 1; }
 
+int resample_launch_variant(const float2 *d_x, long long nin, float2 *d_y, long long nout, float scale, cudaStream_t st, int variant);
+
 int resample_launch(const float2 *d_x, long long nin, float2 *d_y, long long nout, float scale, cudaStream_t st) {
+  static const int nq = getenv("DVBT_B200_RESAMPLE_NQ") ? atoi(getenv("DVBT_B200_RESAMPLE_NQ")) : 2;
+  return resample_launch_variant(d_x, nin, d_y, nout, scale, st, nq);
+}
+
+// variant: 0 generic kernel (any tap count), 1 quad kernel, 2 / 4 quads per thread (36 taps per arm)
+int resample_launch_variant(const float2 *d_x, long long nin, float2 *d_y, long long nout, float scale, cudaStream_t st, int nq) {
   int dev = 0;
   cudaGetDevice(&dev);
   if (dev >= 64) dev = 63;
@@ -244,7 +370,22 @@ int resample_launch(const float2 *d_x, long long nin, float2 *d_y, long long nou
   }
   Resampler *r = g_res[dev];
   if (nout <= 0) return 0;
-  if (r->per_arm == kRegArm) {
+  if (r->per_arm == kRegArm && (nq == 2 || nq == 4)) {
+    const long long out_per_tile = (long long)kQuadOut * nq;
+    long long ntiles = (nout + out_per_tile - 1) / out_per_tile;
+    long long grid = ntiles < 3LL * r->sm_count ? ntiles : 3LL * r->sm_count;
+    if (nq == 2) {
+      DVBT_CUDA_TRY(cudaFuncSetAttribute(resample_multi_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MultiCfg<2>::kSmem));
+      resample_multi_kernel<2><<<(unsigned)grid, 256, MultiCfg<2>::kSmem, st>>>(d_x, nin, d_y, nout, r->d_taps.as<float>(), ntiles, scale);
+    } else {
+      DVBT_CUDA_TRY(cudaFuncSetAttribute(resample_multi_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MultiCfg<4>::kSmem));
+      resample_multi_kernel<4><<<(unsigned)grid, 256, MultiCfg<4>::kSmem, st>>>(d_x, nin, d_y, nout, r->d_taps.as<float>(), ntiles, scale);
+    }
+    count_launch();
+    DVBT_CUDA_TRY(cudaGetLastError());
+    return 0;
+  }
+  if (r->per_arm == kRegArm && nq == 1) {
     long long ntiles = (nout + kQuadOut - 1) / kQuadOut;
     long long grid = ntiles < 3LL * r->sm_count ? ntiles : 3LL * r->sm_count;  // persistent: three resident blocks per SM
     resample_quad_kernel<<<(unsigned)grid, 256, 0, st>>>(d_x, nin, d_y, nout, r->d_taps.as<float>(), ntiles, scale);
@@ -262,6 +403,33 @@ int resample_launch(const float2 *d_x, long long nin, float2 *d_y, long long nou
 }  // namespace dvbt
 
 extern "C" {
+
+// the front end alone on host buffers (parity tests of the resampler kernels): nin complex samples at 10 Msps ->
+// resample_out_count(nin) samples at 64/7 Msps times gain.  variant selects the kernel (0 generic, 1 quad, 2 / 4
+// quads per thread, -1 the default of the chain); all variants add the taps in the same order.
+int dvbt_b200_resample_host(const void *in, size_t nin, float gain, void *out, size_t out_capacity, size_t *nout, int variant) {
+  if ((nin && !in) || !out || !nout) { dvbt::set_error("resample_host: null argument"); return DVBT_B200_EINVAL; }
+  *nout = 0;
+  int rc = dvbt::ensure_device();
+  if (rc) return rc;
+  long long n = dvbt::resample_out_count((long long)nin);
+  if ((size_t)n > out_capacity) { dvbt::set_error("resample_host: need %lld output samples, capacity %zu", n, out_capacity); return DVBT_B200_ENOSPC; }
+  if (n <= 0) return 0;
+  dvbt::DevBuf d_in, d_out;
+  if ((rc = d_in.reserve(nin * 8)) || (rc = d_out.reserve((size_t)n * 8))) { d_in.release(); d_out.release(); return rc; }
+  cudaError_t e = cudaMemcpy(d_in.p, in, nin * 8, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) {
+    rc = variant < 0 ? dvbt::resample_launch(d_in.as<float2>(), (long long)nin, d_out.as<float2>(), n, gain, nullptr)
+                     : dvbt::resample_launch_variant(d_in.as<float2>(), (long long)nin, d_out.as<float2>(), n, gain, nullptr, variant);
+    if (!rc) e = cudaMemcpy(out, d_out.p, (size_t)n * 8, cudaMemcpyDeviceToHost);
+  }
+  d_in.release();
+  d_out.release();
+  if (rc) return rc;
+  if (e != cudaSuccess) { dvbt::set_error("resample_host: %s", cudaGetErrorString(e)); return DVBT_B200_ECUDA; }
+  *nout = (size_t)n;
+  return 0;
+}
 
 // test/inspection hook: the 32/35 low-pass prototype (length is a multiple of 32)
 int dvbt_b200_resampler_taps(float *taps, int capacity) {

@@ -296,6 +296,11 @@ int dvbt_b200_rx_run_file_host(dvbt_b200_rx *h, const void *samples, size_t nsam
 int dvbt_b200_rx_run_file_dev(dvbt_b200_rx *h, const void *d_samples, size_t nsamples, float gain, uint8_t *d_ts, size_t ts_capacity, size_t *ts_bytes);
 /* the 32/35 low-pass prototype used by the resampler; returns its length */
 int dvbt_b200_resampler_taps(float *taps, int capacity);
+/* The front end alone, host buffers: rational_resampler_ccc(64,70) + multiply_const(gain) (stock GNU Radio blocks of
+ * apps/dvbt_rx_demo*.grc, see above).  nin gr_complex at 10 Msps -> *nout gr_complex at 64/7 Msps,
+ * y[m] = gain * sum_j h[(35 m mod 32) + 32 j] * x[floor(35 m / 32) - j].  variant: -1 = the kernel the chain uses,
+ * 0 generic, 1 one quad per thread, 2 / 4 quads per thread (same summation order in all of them; parity tests). */
+int dvbt_b200_resample_host(const void *in, size_t nin, float gain, void *out, size_t out_capacity, size_t *nout, int variant);
 int dvbt_b200_rx_last_info(const dvbt_b200_rx *h, dvbt_b200_rx_info *info);
 /* copies an intermediate of the last run to the host (parity tests): DVBT_RX_STAGE_* */
 int dvbt_b200_rx_read_stage(dvbt_b200_rx *h, int stage, void *host_out, size_t capacity_bytes, size_t *nbytes);
