@@ -302,10 +302,10 @@ __global__ void acq_lambda_kernel(AcqParams p, const float2 *__restrict__ x, lon
 // ends the batch early; the host loop continues from there with the true state (exactness never rests
 // on the speculation).
 constexpr int kNC = kCand - 16 + 1;  // 17 window offsets
-constexpr int kHD = 4;               // |previous offset - offset| covered by the tables (peaks 4..12 of 0..15: noise-free
-                                     // QAM64 captures already jitter by +-4 through the resampler, histograms in profiles/README.md)
-constexpr int kND = 2 * kHD + 1;     // previous-offset deltas -4..4
-constexpr int kNS = kNC * kND;       // 153 states (< kStop)
+constexpr int kHD = 5;               // |previous offset - offset| covered by the tables (peaks 3..13 of 0..15: noise-free
+                                     // QAM64 captures already jitter by +-5 through the resampler, histograms in profiles/README.md)
+constexpr int kND = 2 * kHD + 1;     // previous-offset deltas -5..5
+constexpr int kNS = kNC * kND;       // 187 states (< kStop)
 constexpr unsigned char kLost = 0xFE, kOff = 0xFD, kSplit = 0xFC, kStop = 0xF0;
 constexpr int kChunk = 32;
 static_assert(kNS < kStop, "state ids and stop codes share one byte");
@@ -386,7 +386,7 @@ __global__ void __launch_bounds__(128) acq_chunkmap_kernel(int nsym, int per_thr
 // same scalar logic, the lanes cooperate only to fetch table rows / lambda windows with one coalesced
 // round trip (16-byte loads), and lane 0 alone writes results.
 constexpr int kMaxSeg = 2048;
-constexpr int kRowsCap = kChunk * 2;
+constexpr int kRowsCap = kChunk;
 
 // 16-byte-granular copy of `bytes` bytes starting at byte offset `off` of `src` into shared memory;
 // returns the shift to add to indices into `dst` (the copy starts at the aligned address below `off`).
@@ -1134,7 +1134,7 @@ int acq_run(dvbt_b200_acq *h, const float2 *x, long long n, float2 *d_out, long 
                                                                h->d_maps.as<unsigned char>());
       AcqWalk *d_walk = h->d_eps.as<AcqWalk>();
       if ((rc = h->d_seg.reserve((size_t)kMaxSeg * sizeof(int4)))) return rc;
-      DVBT_CUDA_TRY(cudaFuncSetAttribute(acq_compose_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024));
+      DVBT_CUDA_TRY(cudaFuncSetAttribute(acq_compose_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
       acq_compose_kernel<<<1, 256, (size_t)nthreads * kNS + 64, st>>>(
           p, (int)nsym, per_thread, nthreads, (kD - 8) * kND + kHD, hs->avg, h->d_lambda.as<float>(), h->d_avg1.as<float>(),
           h->d_peak.as<signed char>(), h->d_avg2.as<float>(), h->d_flag.as<unsigned char>(), h->d_maps.as<unsigned char>(),
