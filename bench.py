@@ -608,7 +608,7 @@ def main():
             sys.stderr.write("[bench rank %d] stages: %s | info: %s\n" % (RANK, " ".join("%s=%.3f" % (k[3:], float(np.mean([s_[k] for s_ in w.stage_ms[a.warmup:]]))) for k in keys),
                                                                         json.dumps({k: v for k, v in w.info.items() if not k.startswith("ms_")})))
         sys.stderr.write("[bench rank %d] resident: %.3f ms/step (max over ranks), sum of this rank's stage times %.3f ms\n"
-                         % (RANK, ms / a.steps, float(np.mean([sum(v for k, v in s_.items() if k != "ms_viterbi_acs") for s_ in w.stage_ms[a.warmup:]]))))
+                         % (RANK, ms / a.steps, float(np.mean([sum(v for k, v in s_.items() if k not in ("ms_viterbi_acs", "ms_fft", "ms_equalise")) for s_ in w.stage_ms[a.warmup:]]))))
     launches = (lib.dvbt_b200_kernel_launches() - l0) // (a.steps + a.warmup)   # kernels of this library per step
     ok = w.check()
     kms = float(np.mean(w.kernel_ms[a.warmup:]))
@@ -701,6 +701,17 @@ def main():
                                     "VIADDMNMX.U16x2 + IMAD; ncu: see the `ncu` object), so the HBM fraction is small by nature; DRAM traffic above the "
                                     "algorithmic bytes is the survivor-row write-through to the global ring (deliberate: it frees shared memory "
                                     "for 3x the resident warps); ACS rate = %.1f T state-updates/s" % (info_bits * 64 / (kms / 1e3) / 1e12)}
+        if rx:
+            # the HBM-bound kernels of the step against the same measured peak (algorithmic bytes of SURVEY §8d, CUDA-event
+            # times of the one-capture-at-a-time leg); the ACS kernel above is the dominant one but bound by the ALU pipe
+            inf = w.info
+            nout = (w.nfile - 1) * 32 // 35 + 1
+            others = [("resample_multi_kernel<2> (rational_resampler 64/70 + multiply_const)", "ms_resample", 8.0 * w.nfile + 8.0 * nout),
+                      ("acq_fftd_kernel<2048> (derotation + CP removal + forward FFT)", "ms_fft", inf["acq_symbols"] * (8.0 * (2048 + 64) + 8.0 * 2048)),
+                      ("demod_equalise_kernel (channel estimate + equalise + demap)", "ms_equalise", inf["symbols_parsed"] * (8.0 * 2048 + 1512.0))]
+            line["roofline_other"] = [{"kernel": nm, "bound": "hbm", "achieved": by / (stage[key] / 1e3) / 1e9, "peak": peak, "unit": "GB/s",
+                                       "frac": by / (stage[key] / 1e3) / 1e9 / peak, "algorithmic_bytes": by, "avg_launch_ms": stage[key]}
+                                      for nm, key, by in others if stage.get(key, 0) > 0]
         print(json.dumps(line), file=out, flush=True)
     if WORLD > 1:
         dist.destroy_process_group()

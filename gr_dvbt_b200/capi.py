@@ -46,7 +46,7 @@ class RxParams(C.Structure):
 class RxInfo(C.Structure):
     _fields_ = [(n, C.c_longlong) for n in ("symbols_parsed", "first_symbol", "symbols_out", "viterbi_bytes", "viterbi_repaired",
                                              "rs_packets", "first_packet", "ts_bytes", "acq_symbols", "acq_cp_start", "acq_lost_at", "acq_run_symbols", "acq_single_symbols", "acq_sequential_symbols")] + \
-               [(n, C.c_float) for n in ("ms_resample", "ms_acq_fft", "ms_demod", "ms_inner", "ms_viterbi", "ms_viterbi_acs", "ms_rs", "ms_descramble")]
+               [(n, C.c_float) for n in ("ms_resample", "ms_acq_fft", "ms_demod", "ms_inner", "ms_viterbi", "ms_viterbi_acs", "ms_rs", "ms_descramble", "ms_fft", "ms_equalise")]
 
 
 class AcqParams(C.Structure):

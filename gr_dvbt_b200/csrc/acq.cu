@@ -1042,6 +1042,9 @@ struct dvbt_b200_acq {
   int plan_batch = 0;
   dvbt::DevBuf d_x, d_state, h_state, d_lambda, d_gamma, d_avg1, d_avg2, d_peak, d_sym, d_out, d_il, d_ig, d_eps, d_flag, d_maps, d_cof, d_bof, d_peakof, d_eof, d_seg, d_runs, d_tw;
   int tw_n = 0;
+  static constexpr int kFftEv = 8;          // CUDA events around the derotation+FFT kernel of the first batches of a run
+  cudaEvent_t ev_fft[2 * kFftEv] = {nullptr};
+  int n_fft_ev = 0;
 };
 
 namespace dvbt {
@@ -1073,6 +1076,7 @@ int acq_run(dvbt_b200_acq *h, const float2 *x, long long n, float2 *d_out, long 
     DVBT_CUDA_TRY(cudaStreamSynchronize(st));
     h->tw_n = p.N;
   }
+  h->n_fft_ev = 0;
   int guard = 0;
   while (guard++ < 1000000) {
     // ---- initial acquisition (needs 2N+cp+8 samples visible)
@@ -1198,6 +1202,12 @@ int acq_run(dvbt_b200_acq *h, const float2 *x, long long n, float2 *d_out, long 
         fprintf(stderr, "\n");
       }
     }
+    const bool time_fft = hs->n_out > 0 && fused_fft && h->n_fft_ev < dvbt_b200_acq::kFftEv;
+    if (time_fft) {
+      for (int e = 2 * h->n_fft_ev; e < 2 * h->n_fft_ev + 2; e++)
+        if (!h->ev_fft[e]) DVBT_CUDA_TRY(cudaEventCreate(&h->ev_fft[e]));
+      DVBT_CUDA_TRY(cudaEventRecord(h->ev_fft[2 * h->n_fft_ev], st));
+    }
     if (hs->n_out > 0 && fused_fft) {
       if (p.N == 2048) {
         acq_fftd_kernel<2048><<<hs->n_out, 128, (2048 + 128) * sizeof(float2), st>>>(hs->n_out, x, h->d_sym.as<SymOut>(), d_out + produced * p.N,
@@ -1209,6 +1219,7 @@ int acq_run(dvbt_b200_acq *h, const float2 *x, long long n, float2 *d_out, long 
       }
       count_launch();
       DVBT_CUDA_TRY(cudaGetLastError());
+      if (time_fft) { DVBT_CUDA_TRY(cudaEventRecord(h->ev_fft[2 * h->n_fft_ev + 1], st)); h->n_fft_ev++; }
     } else if (hs->n_out > 0) {
       dim3 grid((p.N + 256 * kDerotPer - 1) / (256 * kDerotPer), hs->n_out);
       acq_derot_kernel<<<grid, 256, 0, st>>>(p.N, hs->n_out, x, h->d_sym.as<SymOut>(), d_out + produced * p.N, do_fft ? 1 : 0);
@@ -1258,6 +1269,14 @@ int acq_run(dvbt_b200_acq *h, const float2 *x, long long n, float2 *d_out, long 
   hs->fallback = fb;
   if (host_state_out) *host_state_out = *hs;
   return 0;
+}
+
+// device time of the derotation+FFT kernel(s) of the last run; call after the stream has been synchronised
+float acq_last_fft_ms(dvbt_b200_acq *h) {
+  float tot = 0.f, ms;
+  for (int i = 0; i < h->n_fft_ev; i++)
+    if (cudaEventElapsedTime(&ms, h->ev_fft[2 * i], h->ev_fft[2 * i + 1]) == cudaSuccess) tot += ms;
+  return tot;
 }
 
 void acq_use_stream(dvbt_b200_acq *h, cudaStream_t st) {
@@ -1319,6 +1338,7 @@ void dvbt_b200_acq_destroy(dvbt_b200_acq *h) {
   if (h->plan) cufftDestroy(h->plan);
   dvbt::DevBuf *bufs[] = {&h->d_x, &h->d_state, &h->h_state, &h->d_lambda, &h->d_gamma, &h->d_avg1, &h->d_avg2, &h->d_peak, &h->d_sym, &h->d_out, &h->d_il, &h->d_ig, &h->d_eps, &h->d_flag, &h->d_maps, &h->d_cof, &h->d_bof, &h->d_peakof, &h->d_eof, &h->d_seg, &h->d_runs, &h->d_tw};
   for (auto *b : bufs) b->release();
+  for (auto &e : h->ev_fft) if (e) cudaEventDestroy(e);
   if (h->stream && h->own_stream) cudaStreamDestroy(h->stream);
   delete h;
 }

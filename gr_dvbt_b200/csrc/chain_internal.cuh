@@ -21,6 +21,7 @@ struct AcqResult { long long consumed; int n_out, lost_at, fallback, cp_start, n
 struct dvbt_b200_acq;
 namespace dvbt {
 void acq_use_stream(dvbt_b200_acq *h, cudaStream_t st);
+float acq_last_fft_ms(dvbt_b200_acq *h);
 int acq_reset(dvbt_b200_acq *h);
 // samples x[0..n) on the device -> up to out_capacity_syms symbols of N complex at d_out
 // (FFT applied, DC at bin N/2, when do_fft)

@@ -630,9 +630,11 @@ int demod_run(const ModeDev &md, const DemapTable *demap, const float2 *X, int n
     }
     DemapTable dummy;
     dummy.size = 0;
+    if (b.ev_eq0) DVBT_CUDA_TRY(cudaEventRecord(b.ev_eq0, st));
     demod_equalise_kernel<<<nparse, 256, smem, st>>>(md, demap ? *demap : dummy, (demap && dm) ? 1 : 0, X, b.fo, b.rot, b.modidx,
                                                     b.tpsval, Y, dm);
     DVBT_CUDA_TRY(cudaGetLastError());
+    if (b.ev_eq1) DVBT_CUDA_TRY(cudaEventRecord(b.ev_eq1, st));
   }
   demod_vote_kernel<<<(nparse + 127) / 128, 128, 0, st>>>(md.ntps, nparse, b.tpsval, d_state, b.vote);
   DVBT_CUDA_TRY(cudaGetLastError());

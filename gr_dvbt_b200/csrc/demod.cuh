@@ -172,6 +172,7 @@ struct DemodBuffers {
   int *vote;        // tps_majority_zero
   int *out_symidx;  // [n_out] symbol_index tag value of each output symbol
   int *out_src;     // [n_out] batch index of each output symbol
+  cudaEvent_t ev_eq0 = nullptr, ev_eq1 = nullptr;   // optional: recorded around demod_equalise_kernel (bench timing)
 };
 
 // Runs process_cpilot_data / compute_oneshot_csft / frequency_correction / process_spilot_data

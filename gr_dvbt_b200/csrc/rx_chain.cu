@@ -262,7 +262,7 @@ struct dvbt_b200_rx {
   dvbt::DevBuf d_X, d_state, d_fo, d_rot, d_mod, d_tps, d_vote, d_osym, d_osrc, d_dm, d_Y, d_vit, d_rs, d_rsst, d_ts, d_info, d_prbs, h_state, h_info;
   dvbt_b200_rx_info info;
   long long last_nparse = 0;
-  cudaEvent_t ev[8];
+  cudaEvent_t ev[10];
 };
 
 extern "C" {
@@ -375,7 +375,7 @@ static int rx_run_freq(dvbt_b200_rx *h, const float2 *dX, size_t nsym, uint8_t *
   DVBT_CUDA_TRY(cudaEventRecord(h->ev[0], st));
   DVBT_CUDA_TRY(cudaMemsetAsync(h->d_state.p, 0, sizeof(dvbt::DemodState), st));
   dvbt::DemodBuffers b{h->d_fo.as<int>(), h->d_rot.as<float2>(), h->d_mod.as<int>(), h->d_tps.as<float2>(), h->d_vote.as<int>(),
-                       h->d_osym.as<int>(), h->d_osrc.as<int>()};
+                       h->d_osym.as<int>(), h->d_osrc.as<int>(), h->ev[8], h->ev[9]};
   rc = dvbt::demod_run(md, &h->demap, dX, (int)nparse, b, h->d_state.as<dvbt::DemodState>(), h->fi_start, 1,
                        keep_cells ? h->d_Y.as<float2>() : nullptr, h->d_dm.as<uint8_t>(), st);
   if (rc) return rc;
@@ -463,6 +463,7 @@ static int rx_run_freq(dvbt_b200_rx *h, const float2 *dX, size_t nsym, uint8_t *
   float acs = 0;
   dvbt_b200_viterbi_last_stats(h->vit, &chunks, &rep, &acs);
   h->info.ms_viterbi_acs = acs;
+  if (cudaEventElapsedTime(&ms, h->ev[8], h->ev[9]) == cudaSuccess) h->info.ms_equalise = ms;
   h->info.viterbi_repaired = rep;
   return 0;
 }
@@ -506,6 +507,7 @@ static int rx_run_baseband(dvbt_b200_rx *h, const float2 *d_x, size_t nsamples, 
   h->info.acq_sequential_symbols = ar.n_seq;
   float ms;
   if (cudaEventElapsedTime(&ms, h->ev[6], h->ev[7]) == cudaSuccess) h->info.ms_acq_fft = ms;
+  h->info.ms_fft = dvbt::acq_last_fft_ms(h->acq);
   return rc;
 }
 

@@ -273,6 +273,7 @@ typedef struct dvbt_b200_rx_info {
   long long acq_run_symbols, acq_single_symbols, acq_sequential_symbols; /* how the tracker handled the symbols */
   float ms_resample, ms_acq_fft;
   float ms_demod, ms_inner, ms_viterbi, ms_viterbi_acs, ms_rs, ms_descramble; /* device time per stage */
+  float ms_fft, ms_equalise; /* single kernels inside the stages above: derotation+FFT (in ms_acq_fft), equalise+demap (in ms_demod) */
 } dvbt_b200_rx_info;
 enum { DVBT_RX_STAGE_CELLS = 0, DVBT_RX_STAGE_DEMAP = 1, DVBT_RX_STAGE_BITDEINT = 2, DVBT_RX_STAGE_VITERBI = 3,
        DVBT_RX_STAGE_RS = 4, DVBT_RX_STAGE_RS_STATUS = 5, DVBT_RX_STAGE_SYMBOL_INDEX = 6 };
