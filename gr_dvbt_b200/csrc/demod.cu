@@ -107,6 +107,12 @@ int ModeTables::init(int tm, int gi) {
       }
     if (n != P) { set_error("mode tables: %d payload carriers for scattered phase %d, expected %d", n, r, P); return DVBT_B200_EINVAL; }
   }
+  std::vector<int> pay32(4 * P);
+  for (int r = 0; r < 4; r++)
+    for (int i = 0; i < P; i++) {
+      int k = payload[r * P + i];
+      pay32[r * P + i] = k | ((k - prevp[r * K + k]) << 16);
+    }
   // dense list of the channel-estimation carriers of every scattered phase (the kernels loop over these
   // instead of testing kind[] on all K carriers: the gain computation is a double-precision complex division,
   // and with one pilot in twelve it would otherwise run with three lanes of a warp active)
@@ -151,7 +157,7 @@ int ModeTables::init(int tm, int gi) {
   auto place = [&](size_t bytes) { size_t o = off; off += (bytes + 15) & ~(size_t)15; return o; };
   size_t o_cp = place(cpl.size() * 2), o_tps = place(tpl.size() * 2), o_known = place(known.size() * 4), o_pval = place(pval.size() * 4),
          o_kind = place(kind.size()), o_prev = place(prevp.size() * 2), o_next = place(nextp.size() * 2), o_pay = place(payload.size() * 2),
-         o_H = place(H.size() * 2), o_Hi = place(Hinv.size() * 2), o_pil = place(pil.size() * 2);
+         o_H = place(H.size() * 2), o_Hi = place(Hinv.size() * 2), o_pil = place(pil.size() * 2), o_pay32 = place(pay32.size() * 4);
   std::vector<unsigned char> host(off);
   memcpy(&host[o_cp], cpl.data(), cpl.size() * 2);
   memcpy(&host[o_tps], tpl.data(), tpl.size() * 2);
@@ -164,6 +170,7 @@ int ModeTables::init(int tm, int gi) {
   memcpy(&host[o_H], H.data(), H.size() * 2);
   memcpy(&host[o_Hi], Hinv.data(), Hinv.size() * 2);
   memcpy(&host[o_pil], pil.data(), pil.size() * 2);
+  memcpy(&host[o_pay32], pay32.data(), pay32.size() * 4);
   int rc = blob.reserve(off);
   if (rc) return rc;
   DVBT_CUDA_TRY(cudaMemcpy(blob.p, host.data(), off, cudaMemcpyHostToDevice));
@@ -179,6 +186,7 @@ int ModeTables::init(int tm, int gi) {
   d.H = (const short *)(base + o_H);
   d.Hinv = (const short *)(base + o_Hi);
   d.pilots = (const short *)(base + o_pil);
+  d.pay32 = (const int *)(base + o_pay32);
   return 0;
 }
 
@@ -310,37 +318,28 @@ __global__ void __launch_bounds__(256) demod_equalise_kernel(ModeDev md, const _
     s_slope[k] = cdiv(csub(s_gain[nextp[k]], s_gain[k]), make_float2(11.0f, 0.0f));
   }
   __syncthreads();
-  // (loops below: the table loads of four iterations are issued together, then the dependent work)
-  for (int kb = threadIdx.x; kb < md.K; kb += 4 * blockDim.x) {
-    int kd[4], k0[4];
-#pragma unroll
-    for (int u = 0; u < 4; u++) {
-      int k = kb + u * blockDim.x;
-      kd[u] = k < md.K ? kind[k] : 1;
-      k0[u] = k < md.K ? prevp[k] : 0;
-    }
-#pragma unroll
-    for (int u = 0; u < 4; u++) {
-      int k = kb + u * blockDim.x;
-      if (!(kd[u] & 1)) {
-        float2 step = cmul(s_slope[k0[u]], make_float2((float)(k - k0[u]), 0.0f));
-        s_gain[k] = cadd(s_gain[k0[u]], step);
-      }
-    }
-  }
-  __syncthreads();
+  // The gain of a data carrier is interpolated where it is used: g[k0] + (k - k0) * slope[k0] with k0 the channel-estimation
+  // carrier below k (:617-642: same operations in the same order as the reference's loop over the interval, so the same
+  // floats; materialising all K gains first cost a pass over the carriers with two table loads each and a barrier)
+  auto gain_at = [&](int k0, int dk) {
+    float2 step = cmul(s_slope[k0], make_float2((float)dk, 0.0f));
+    return cadd(s_gain[k0], step);
+  };
   if (threadIdx.x < md.ntps) {  // :929-945
     int k = md.tps[threadIdx.x];
-    tpsval[(long long)s * md.ntps + threadIdx.x] = cmul(cmul(rot, x[k]), s_gain[k]);
+    int k0 = prevp[k];
+    tpsval[(long long)s * md.ntps + threadIdx.x] = cmul(cmul(rot, x[k]), gain_at(k0, k - k0));
   }
-  const short *pay = md.payload + r * md.P;
+  const int *pay = md.pay32 + r * md.P;
   for (int ib = threadIdx.x; ib < md.P; ib += 3 * blockDim.x) {  // :1104-1113
-    int k[3];
+    int k[3], dk[3];
     float2 xv[3];
 #pragma unroll
     for (int u = 0; u < 3; u++) {
       int i = ib + u * blockDim.x;
-      k[u] = i < md.P ? pay[i] : 0;
+      int e = i < md.P ? pay[i] : (1 << 16);
+      k[u] = e & 0xffff;
+      dk[u] = e >> 16;
     }
 #pragma unroll
     for (int u = 0; u < 3; u++) xv[u] = x[k[u]];
@@ -348,7 +347,7 @@ __global__ void __launch_bounds__(256) demod_equalise_kernel(ModeDev md, const _
     for (int u = 0; u < 3; u++) {
       int i = ib + u * blockDim.x;
       if (i < md.P) {
-        float2 y = cmul(cmul(rot, xv[u]), s_gain[k[u]]);
+        float2 y = cmul(cmul(rot, xv[u]), gain_at(k[u] - dk[u], dk[u]));
         if (Y) Y[(long long)s * md.P + i] = y;
         if (do_demap) dm[(long long)s * md.P + i] = demap_cell_any(dt, y);
       }
