@@ -310,18 +310,29 @@ constexpr unsigned char kLost = 0xFE, kOff = 0xFD, kSplit = 0xFC, kStop = 0xF0;
 constexpr int kChunk = 32;
 static_assert(kNS < kStop, "state ids and stop codes share one byte");
 
+// The running average does not depend on the detector's state (:88-118), so for a window and a start value it is a
+// straight-line float recurrence, and the detector only sees it through the 16 + 16 threshold tests "v > avg * rise",
+// "v > avg * fall".  Pass 1 needs the recurrence alone; pass 2 replays the state machine on the two bit masks (same
+// visits per element as peak_detect() above, a third of its instructions: ncu had pass 2 issue bound at 700
+// instructions per thread).
 __global__ void acq_pass1_kernel(AcqParams p, int nsym, const float *__restrict__ lambda, float *__restrict__ avg1) {
   int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= nsym * kNC) return;
   int n = t / kNC, c = t - n * kNC;
+  const float *d = lambda + (long long)n * kCand + c;
+  const float one_minus = 1.0f - p.alpha;
+  float v[16];
+#pragma unroll
+  for (int i = 0; i < 16; i++) v[i] = d[i];
   float avg = 0.f;
-  int best;
-  peak_detect(lambda + (long long)n * kCand + c, 16, &avg, p.rise, p.fall, p.alpha, &best);
+#pragma unroll
+  for (int i = 0; i < 16; i++) avg = __fadd_rn(__fmul_rn(p.alpha, v[i]), __fmul_rn(one_minus, avg));
   avg1[t] = avg;
 }
 
-__global__ void acq_pass2_kernel(AcqParams p, int nsym, const float *__restrict__ lambda, const float *__restrict__ avg1, float avg_first,
-                                 signed char *__restrict__ best2, float *__restrict__ avg2, unsigned char *__restrict__ next) {
+__global__ void __launch_bounds__(128) acq_pass2_kernel(AcqParams p, int nsym, const float *__restrict__ lambda, const float *__restrict__ avg1,
+                                                        float avg_first, signed char *__restrict__ best2, float *__restrict__ avg2,
+                                                        unsigned char *__restrict__ next) {
   int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= nsym * kNS) return;
   int n = t / kNS, s = t - n * kNS, c = s / kND, d = s - c * kND - kHD;
@@ -331,9 +342,38 @@ __global__ void acq_pass2_kernel(AcqParams p, int nsym, const float *__restrict_
   unsigned char nx = kSplit;
   if (n == 0 || (cp >= 0 && cp < kNC)) {
     avg = n == 0 ? avg_first : avg1[(n - 1) * kNC + cp];
-    int best;
-    int np = peak_detect(lambda + (long long)n * kCand + c, 16, &avg, p.rise, p.fall, p.alpha, &best);
-    if (np <= 0) { res = -1; nx = kLost; }
+    const float *w = lambda + (long long)n * kCand + c;
+    const float one_minus = 1.0f - p.alpha;
+    float v[16];
+#pragma unroll
+    for (int i = 0; i < 16; i++) v[i] = w[i];
+    unsigned rise = 0, fall = 0;
+#pragma unroll
+    for (int i = 0; i < 16; i++) {
+      rise |= (v[i] > __fmul_rn(avg, p.rise) ? 1u : 0u) << i;
+      fall |= (v[i] > __fmul_rn(avg, p.fall) ? 1u : 0u) << i;
+      avg = __fadd_rn(__fmul_rn(p.alpha, v[i]), __fmul_rn(one_minus, avg));
+    }
+    int state = 0, npeaks = 0, peak_index = 0, best = 0;
+    float peak_val = -INFINITY, peak_at = 0.f, best_val = 0.f;
+#pragma unroll
+    for (int i = 0; i < 16; i++) {
+      const float vi = v[i];
+      for (;;) {
+        if (state == 0) {
+          if ((rise >> i) & 1u) { state = 1; continue; }
+          break;
+        }
+        if (vi > peak_val) { peak_val = vi; peak_at = vi; peak_index = i; break; }
+        if ((fall >> i) & 1u) break;
+        // record the peak; the first strictly greatest recorded peak wins (:127-137)
+        if (npeaks == 0 || peak_at > best_val) { best_val = peak_at; best = peak_index; }
+        npeaks++;
+        state = 0;
+        peak_val = -INFINITY;
+      }
+    }
+    if (npeaks <= 0) { res = -1; nx = kLost; }
     else {
       res = (signed char)best;
       int cn = c + best - 8, dn = 8 - best;
@@ -359,18 +399,43 @@ struct AcqWalk {
   long long cyc_cmp[4];   // trace: compose chain - staging, table walks, detector re-runs, everything else  // trace: clock64 deltas of the three phases (DVBT_B200_ACQ_TRACE)
 };
 
-// chunk maps: one warp per chunk of `per_thread` symbols, lane = start state (kNS states, 4 rounds)
+// chunk maps: one warp per chunk of `per_thread` symbols, lane = start state (kNS states, 6 rounds).  The chunk's rows of
+// `next` are staged in shared memory with one coalesced round trip when they fit (32-symbol chunks: 6 KB per warp); walking
+// them in global memory is a chain of per_thread dependent L2 round trips per start state.
+constexpr int kMapRows = kChunk;
 __global__ void __launch_bounds__(128) acq_chunkmap_kernel(int nsym, int per_thread, int nchunks, const unsigned char *__restrict__ next,
                                                            unsigned char *__restrict__ maps) {
+  __shared__ __align__(16) unsigned char s_rows[4][kMapRows * kNS + 32];
   int w = (int)((blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
   if (w >= nchunks) return;
   const int n0 = w * per_thread, n1 = min(nsym, n0 + per_thread);
+  const bool staged = per_thread <= kMapRows;
+  unsigned char *rows = s_rows[threadIdx.x >> 5];
+  int shift = 0;
+  if (staged) {
+    // 16-byte units from the aligned address below the first row (the allocation carries slack at both ends)
+    const long long off = (long long)n0 * kNS, a0 = off & ~15LL;
+    shift = (int)(off - a0);
+    const int n16 = (shift + (n1 - n0) * kNS + 15) >> 4;
+    const uint4 *src = reinterpret_cast<const uint4 *>(next + a0);
+    uint4 *dst = reinterpret_cast<uint4 *>(rows);
+    for (int i = lane; i < n16; i += 32) dst[i] = src[i];
+    __syncwarp();
+  }
   for (int s0 = lane; s0 < kNS; s0 += 32) {
     unsigned char cur = (unsigned char)s0;
-    for (int n = n0; n < n1; n++) {
-      unsigned char nx = next[(long long)n * kNS + cur];
-      if (nx >= kStop) { cur = kStop; break; }
-      cur = nx;
+    if (staged) {
+      for (int n = n0; n < n1; n++) {
+        unsigned char nx = rows[shift + (n - n0) * kNS + cur];
+        if (nx >= kStop) { cur = kStop; break; }
+        cur = nx;
+      }
+    } else {
+      for (int n = n0; n < n1; n++) {
+        unsigned char nx = next[(long long)n * kNS + cur];
+        if (nx >= kStop) { cur = kStop; break; }
+        cur = nx;
+      }
     }
     maps[(long long)w * kNS + s0] = cur;
   }
