@@ -101,6 +101,23 @@ __device__ __forceinline__ uint8_t demap_cell_near(const DemapTable &t, float2 v
     float d = __fsub_rn(a, __fmul_rn(t.g, n));   // the level exactly as make_demap_table rounds it
     return __fmul_rn(d, d);
   };
+  // Clear cases first: the cell is within 0.49 level spacings of the guessed level on both axes (on the open side of
+  // an edge level: anywhere up to 16 spacings out).  With s = 2 g the spacing, every other level of an axis is then
+  // at least 0.5099 s away (the levels are fl(g n): spacing error < 1e-6 s), so its squared distance exceeds the
+  // guessed one by more than 0.0197 s^2, while fl(cx + cy) < 512 s^2: the gap is > 300 ulp of any sum the scan
+  // compares, every other point is strictly farther after rounding, and the reference's scan (first strictly
+  // smallest distance) returns the guessed point.  Inf/NaN fail the comparisons and take the paths below.
+  {
+    const float lim = 0.98f * t.g, far = 32.0f * t.g;
+    const float dx = __fsub_rn(v.x, __fmul_rn(t.g, nx)), dy = __fsub_rn(v.y, __fmul_rn(t.g, ny));
+    const bool okx = (dx > -lim || nx == -TOP) && (dx < lim || nx == TOP) && fabsf(dx) < far;
+    const bool oky = (dy > -lim || ny == -TOP) && (dy < lim || ny == TOP) && fabsf(dy) < far;
+    if (okx && oky) {
+      int kx = __float2int_rn((nx + TOP) * 0.5f), ky = __float2int_rn((ny + TOP) * 0.5f);
+      unsigned bx = __byte_perm((unsigned)t.bx, (unsigned)(t.bx >> 32), kx), by = __byte_perm((unsigned)t.by, (unsigned)(t.by >> 32), ky);
+      return (uint8_t)((bx | by) & 0xffu);
+    }
+  }
   float cx = sq(v.x, nx), cy = sq(v.y, ny);
   float lx = nx > -TOP ? sq(v.x, nx - 2.0f) : inf, rx = nx < TOP ? sq(v.x, nx + 2.0f) : inf;
   float ly = ny > -TOP ? sq(v.y, ny - 2.0f) : inf, ry = ny < TOP ? sq(v.y, ny + 2.0f) : inf;

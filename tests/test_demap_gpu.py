@@ -28,6 +28,20 @@ def cells_for(con, n, seed, sigma=0.12):
     m = min(k, n - j - 20)
     if m > 0:
         c[j: j + m] = (re + 1j * im).astype(np.complex64)[:m]
+    # around the 0.49-spacing limit of the kernel's clear-case shortcut, on either axis and beyond the edge levels
+    # (placed in the random region between the tie blocks and the non-finite cells)
+    lv = np.unique(pts.real)
+    step = float(lv[1] - lv[0]) if len(lv) > 1 else 2.0 * float(abs(lv[0]))
+    start = j + max(m, 0)
+    q = min(600, max(0, (n - 12 - start) // 2 - 2))
+    if q > 4:
+        fr = rng.uniform(0.47, 0.53, q) * rng.choice([-1.0, 1.0], q)
+        a = rng.choice(lv, q) + fr * step
+        b = rng.choice(lv, q) + rng.uniform(-0.6, 0.6, q) * step
+        c[start: start + q] = (a + 1j * b).astype(np.complex64)
+        c[start + q: start + 2 * q] = (b + 1j * a).astype(np.complex64)
+        c[start: start + 4] = np.array([complex(lv[-1] + 15.9 * step, 0.1), complex(lv[-1] + 16.1 * step, 0.1), complex(0.1, lv[0] - 15.9 * step),
+                                        complex(0.1, lv[0] - 16.1 * step)], np.complex64)
     c[-12:-4] = np.array([complex(np.nan, 0.3), complex(0.2, np.nan), complex(np.inf, 1), complex(-1, -np.inf), complex(np.inf, np.inf),
                           complex(np.nan, np.nan), complex(3.4e38, 3.4e38), complex(-3.4e38, 1e-38)], np.complex64)
     return c
