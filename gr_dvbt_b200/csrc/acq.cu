@@ -1067,17 +1067,34 @@ __global__ void __launch_bounds__(N / 16) acq_fftd_kernel(int nsym, const float2
     float2 u[16];
 #pragma unroll
     for (int r = 0; r < 16; r++) u[r] = __ldg(x + s.first + t + r * T);
+    // Derotation rotors.  The phase of sample j is linear in j on either side of switch_at (the phase is incremented
+    // before it is used, :291-307): phase0 + (j+1) inc0, then phase0 + switch_at inc0 + (j+1-switch_at) inc1.  A thread's
+    // 16 samples are T apart, so on each side its rotors are a geometric sequence: one sincos for the first sample and
+    // one for the ratio exp(i T inc) per side (phases in double, reduced to (-pi, pi]), then 15 complex multiplies -
+    // instead of 16 double-precision phases and 16 sincos, which were 35 % of this kernel's instructions
+    // (profiles/r01_side_kernels_v36_ncu_summary.txt; the kernel is issue bound).  Rounding: <= 15 float multiplies
+    // deep, ~1e-6 relative, inside the tolerance the closed-form phase already has against the reference's own
+    // float accumulation (tests/test_acq_gpu.py).
+    {
+      auto rotor = [](double ph) {
+        ph -= (2.0 * M_PI) * rint(ph * (1.0 / (2.0 * M_PI)));
+        float sn, cs;
+        sincosf((float)ph, &sn, &cs);
+        return make_float2(cs, sn);
+      };
+      const int sw = s.switch_at;
+      float2 ra = rotor(s.phase0 + (double)(t + 1) * s.inc0);
+      float2 rb = rotor(s.phase0 + (double)sw * s.inc0 + (double)(t + 1 - sw) * s.inc1);
+      const float2 sa = rotor((double)T * s.inc0), sb = rotor((double)T * s.inc1);
 #pragma unroll
-    for (int r = 0; r < 16; r++) {
-      const int j = t + r * T;
-      const int steps = j + 1;  // the phase is incremented before it is used (:291-307)
-      double ph = s.phase0 + (steps <= s.switch_at ? steps * s.inc0 : s.switch_at * s.inc0 + (steps - s.switch_at) * s.inc1);
-      ph -= (2.0 * M_PI) * rint(ph * (1.0 / (2.0 * M_PI)));
-      float sn, cs;
-      sincosf((float)ph, &sn, &cs);
-      float2 v = cmulf(make_float2(cs, sn), u[r]);
-      if (j & 1) v = make_float2(-v.x, -v.y);     // fft_vxx(shift = true)
-      u[r] = v;
+      for (int r = 0; r < 16; r++) {
+        const int j = t + r * T;
+        float2 v = cmul2(j + 1 <= sw ? ra : rb, u[r]);
+        if (j & 1) v = make_float2(-v.x, -v.y);     // fft_vxx(shift = true)
+        u[r] = v;
+        ra = cmul2(ra, sa);
+        rb = cmul2(rb, sb);
+      }
     }
     dft16(u);
 #pragma unroll
