@@ -1,11 +1,13 @@
 /* TEST INFRASTRUCTURE ONLY (oracle/): a minimal stand-in for the slice of the
  * GNU Radio 3.7 runtime API that the gr-dvbt block sources touch, so that the
- * reference's own lib/*.cc can be compiled *verbatim* (from /root/reference,
+ * reference's own lib .cc files can be compiled *verbatim* (from /root/reference,
  * never copied) into oracle/_ref/libdvbt_ref.so and driven one general_work()
  * call at a time by oracle/ref_harness.cc.  No scheduler, no buffers: the
  * harness owns the item counters and the tag lists.
  *
- * Nothing under gr_dvbt_b200/ may include this header.
+ * libdvbt_b200.so (the product) never sees this header.  Its only other user is the compile check /
+ * test build of the gr::block shims (gr_dvbt_b200/shim/Makefile -> libdvbt_b200_shim_test.so, loaded by
+ * tests/test_shim_gpu.py alone): the shims are written against the real gnuradio/block.h, and this image has none.
  */
 #ifndef DVBT_ORACLE_FAKE_GR_BLOCK_H
 #define DVBT_ORACLE_FAKE_GR_BLOCK_H
