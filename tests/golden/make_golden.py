@@ -102,6 +102,37 @@ def chain_fixture():
     print("wrote", path, os.path.getsize(path), "bytes")
 
 
+def apps_test_ts_fixture():
+    """The one known-answer the reference ships: apps/test.ts is what apps/dvbt_tx_demo.grc transmits and what
+    apps/dvbt_rx_demo.grc must give back (BASELINE.json configs[0], 2k/QAM16/rate 1/2; from TS packet 504 on: SURVEY §8c).
+    The head of the file is committed (data, not source) together with the sha256 of the whole file and the reference
+    RX chain's own output for it, so that the identity can be re-checked where /root/reference does not exist."""
+    import hashlib
+    path = "/root/reference/apps/test.ts"
+    raw = np.fromfile(path, np.uint8)
+    npk = 2016                                               # 4 superframes of 2k/QAM16/1-2 carry 504 packets each
+    head = raw[: npk * 188].copy()
+    assert np.all(head.reshape(-1, 188)[:, 0] == 0x47)
+    con, cr, tm = R.QAM16, R.C1_2, R.T2k
+    ed, rs, ci = R.tx_outer(head)
+    tx = R.tx_inner(ci, con, cr, tm, nsym=None)
+    nsym = tx["X"].shape[0]
+    from dvbt_testlib import channel
+    X = channel(tx["X"])
+    Y, tags = R.rx_demod(X, con, cr, tm)
+    dm = R.rx_demap(Y, con, tm)
+    sd, bd = R.rx_deinterleave(dm, tags, con, tm)
+    sf = [t for t in tags if t[1] == "superframe_start"][0][0]
+    vo, vtags = R.rx_viterbi(bd, con, cr, sf * 1512)
+    cd, rd, ts = R.rx_outer(vo, vtags, fixed_rs=True)
+    assert len(ts) >= 1504 * 20 and np.array_equal(ts, head[504 * 188: 504 * 188 + len(ts)])
+    out = os.path.join(HERE, "apps_test_ts_head.npz")
+    np.savez_compressed(out, ts_head=head, sha256_whole_file=np.frombuffer(hashlib.sha256(raw.tobytes()).digest(), np.uint8),
+                        whole_file_bytes=np.int64(len(raw)), first_packet=np.int64(504), nsym=np.int64(nsym),
+                        reference_rx_bytes=np.int64(len(ts)))
+    print("wrote", out, os.path.getsize(out), "bytes; reference RX returned", len(ts) // 188, "packets of", nsym, "symbols")
+
+
 def main():
     assert R.available() and R.available(True), "build oracle/_ref first (make -C oracle ref)"
     d = {}
@@ -113,6 +144,7 @@ def main():
     np.savez_compressed(path, **d)
     print("wrote", path, os.path.getsize(path), "bytes,", len(d), "arrays")
     chain_fixture()
+    apps_test_ts_fixture()
 
 
 if __name__ == "__main__":
