@@ -127,3 +127,53 @@ def test_acquisition_port_matches_the_reference_build():
     ref, cons_ref, tags = R.rx_acquisition(x, R.T2k)
     got, cons, tag = O.acquisition(x, 2048, 64)
     assert cons == cons_ref and tag and np.array_equal(ref.view(np.uint32), got.view(np.uint32))
+
+
+# ---- the whole restated chain against the reference build, mode by mode --------------------------
+# (the fixture above pins 2k / QAM16 / 1/2 only; here the reference itself is run, where oracle/_ref is built)
+PORT_CHAIN_CASES = [
+    (R.QPSK, R.C2_3, R.T2k, 300, 0.0),
+    (R.QAM64, R.C7_8, R.T2k, 300, 0.0),      # BASELINE configs[1]
+    (R.QAM16, R.C3_4, R.T2k, 300, 0.12),     # Viterbi and RS correcting
+    (R.QAM64, R.C7_8, R.T8k, 280, 0.0),      # configs[2]
+    (R.QAM16, R.C1_2, R.T8k, 280, 0.0),      # configs[3]
+    (R.QPSK, R.C5_6, R.T8k, 280, 0.05),
+]
+
+
+@pytest.mark.skipif(not R.available(), reason="oracle/_ref not built")
+@pytest.mark.parametrize("con,cr,tm,nsym,noise", PORT_CHAIN_CASES)
+def test_port_chain_matches_the_reference_build_stage_by_stage(con, cr, tm, nsym, noise):
+    """every restatement in oracle/port against the reference block it restates, on the same input, every stage
+    bit for bit (floats included), in both transmission modes, all three constellations, with and without noise"""
+    from dvbt_testlib import tx_frequency_domain, channel
+    N, P, _, _ = R.mode_dims(tm)
+    m = R.BITS_PER_CELL[con]
+    tx = tx_frequency_domain(con, cr, tm, nsym, 21)
+    X = channel(tx["X"], noise=noise, seed=4)
+    Yr, tags = R.rx_demod(X, con, cr, tm)
+    Yp, si, tag = O.demod(X, con, tm)
+    assert Yp.shape == Yr.shape and np.array_equal(Yp.view(np.uint32), Yr.view(np.uint32))
+    assert np.array_equal(si, np.array([t[2] for t in tags if t[1] == "symbol_index"], si.dtype))
+    sf = [t for t in tags if t[1] == "superframe_start"][0][0]
+    assert tag == sf
+    dmr = R.rx_demap(Yr, con, tm)
+    dmp = O.demap(Yp, con).reshape(Yp.shape[0], -1)
+    assert np.array_equal(dmp, dmr)
+    sdr, bdr = R.rx_deinterleave(dmr, tags, con, tm)
+    bdp = O.bit_deinterleave(O.symbol_deinterleave(dmp, tm, si), m)
+    assert np.array_equal(bdp.reshape(-1), bdr.reshape(-1))
+    vor, vtags = R.rx_viterbi(bdr, con, cr, sf * P)
+    vop = O.Viterbi(m, cr).work(bdp.reshape(-1)[sf * P:])
+    nv = min(len(vor), len(vop))
+    assert nv > 2000 and np.array_equal(vop[:nv], vor[:nv])
+    for fixed in (False, True):
+        cdr, rdr, tsr = R.rx_outer(vor, vtags, fixed_rs=fixed)
+        cdp = O.conv_deinterleave(vor)
+        rsp, st = O.rs_decode(cdp[: len(cdp) // 204 * 204].reshape(-1, 204), as_built=not fixed)
+        tsp, first = O.descramble(rsp)
+        assert len(tsr) >= 1504 and np.array_equal(tsp[: len(tsr)], tsr)
+        if noise == 0.0:
+            src = tx["ts"]
+            k0 = [c for c in range(0, len(src) // 188, 8) if np.array_equal(src[c * 188: c * 188 + 1504], tsr[:1504])]
+            assert k0 and np.array_equal(tsr, src[k0[0] * 188: k0[0] * 188 + len(tsr)])
