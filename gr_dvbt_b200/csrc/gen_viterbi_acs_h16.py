@@ -250,8 +250,10 @@ def run_ops(ops, env):
         out = np.zeros_like(a)
         for lane in range(4):
             nib = (sel >> (4 * lane)) & 0xF
-            assert nib < 8
-            out |= src[nib] << u32(8 * lane)
+            byte = src[nib & 7]
+            if nib & 8:   # prmt.b32 default mode: bit 3 of a selector nibble replicates the sign bit of the byte
+                byte = (byte >> u32(7)) * u32(0xFF)
+            out |= byte << u32(8 * lane)
         return out
 
     for op in ops:

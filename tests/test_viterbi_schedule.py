@@ -7,7 +7,7 @@ import viterbi_model as VM
 from oracle import port as O
 
 
-@pytest.mark.parametrize("schedule", ["swar", "h16"])
+@pytest.mark.parametrize("schedule", ["swar", "h16", "h16b"])
 @pytest.mark.parametrize("rate,m,ber", [(0, 4, 0.03), (4, 6, 0.004), (2, 2, 0.02)])
 def test_schedule_model_matches_oracle(rate, m, ber, schedule):
     k, n = O.RATE_KN[rate]
@@ -20,7 +20,8 @@ def test_schedule_model_matches_oracle(rate, m, ber, schedule):
     assert np.array_equal(out, ref) and fix > 0  # boundary verification + repair is exact
 
 
-@pytest.mark.parametrize("mod,hdr", [("gen_viterbi_acs", "viterbi_acs_gen.cuh"), ("gen_viterbi_acs_h16", "viterbi_acs_h16_gen.cuh")])
+@pytest.mark.parametrize("mod,hdr", [("gen_viterbi_acs", "viterbi_acs_gen.cuh"), ("gen_viterbi_acs_h16", "viterbi_acs_h16_gen.cuh"),
+                                     ("gen_viterbi_acs_h16b", "viterbi_acs_h16b_gen.cuh")])
 def test_generated_header_is_current(mod, hdr):
     import importlib
     import os

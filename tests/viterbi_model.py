@@ -246,6 +246,101 @@ def decode_chunk_h16(codes, jstart, jend, first_real, ntb, out, save_at=(), init
     return saved
 
 
+_SCHED_HB = None
+
+
+def sched_h16b():
+    global _SCHED_HB
+    if _SCHED_HB is None:
+        import gen_viterbi_acs_h16b as HB
+        _SCHED_HB = (HB, HB.build())
+    return _SCHED_HB
+
+
+def decode_chunk_h16b(codes, jstart, jend, first_real, ntb, out, save_at=(), init_metrics=None):
+    """Same contract for the second halfword schedule (gen_viterbi_acs_h16b.py): registers zipped directly at the
+    event (no metric words), best state on the zipped registers, renormalisation folded into step 7.  The saved
+    boundary vectors are the 32 un-renormalised zipped registers."""
+    HB, S = sched_h16b()
+    one = lambda v: np.array([v & 0xFFFFFFFF], np.uint32)
+    V = [one(0) for _ in range(32)]
+    ring = np.zeros((ntb, 64), np.uint8)
+    trace = np.zeros(ntb, np.int64)
+    have_trace = False
+    saved = {}
+    resume = init_metrics is not None
+    j = jstart
+    if resume:
+        j = jstart - 1
+    while j < jend:
+        code = int(codes[j]) if j < len(codes) else 0
+        apk = {}
+        for i in range(8):
+            q = H.addend_words((code >> (4 * i)) & 15, H.lane_xor(H.STEP_LANE_POS[i]))
+            for c, v in zip("xyzw", q):
+                apk["apk%d.%s" % (i, c)] = one(v)
+        if resume:
+            Z = [one(int(x)) for x in init_metrics]
+            resume = False
+        else:
+            env = {"ZERO": one(0)}
+            for i in range(32):
+                env["V[%d]" % i] = V[i]
+            env.update(apk)
+            H.run_ops(S["part1"], env)
+            Z = [env["Z[%d]" % i] for i in range(32)]
+            Pev = [env["P_ev[%d]" % i] for i in range(16)]
+            slot = j % ntb
+            row = np.zeros(64, np.uint8)
+            for w in range(16):
+                for b in range(4):
+                    row[4 * w + b] = (int(Pev[w][0]) >> (8 * b)) & 0xFF
+            ring[slot] = row
+            met = np.zeros(64, np.int64)
+            for s in range(64):
+                r, h = HB.z_position(s)
+                assert (int(Z[r][0]) >> (16 * h)) & 0xFF == 0          # empty path bytes
+                met[s] = (int(Z[r][0]) >> (8 + 16 * h)) & 0xFF
+            assert met.max() < 128                                      # what the sign-replicating zip relies on
+            if j >= first_real:
+                s = int(np.argmax(met))
+                H.run_ops(S["argmax"], env)
+                bw = int(env["BEST"][0])
+                assert 63 - (max(bw & 0xFFFF, bw >> 16) & 63) == s
+                merged = False
+                for h in range(ntb - 1):
+                    q = (j - h) % ntb
+                    if h > 0 and have_trace and trace[q] == s:
+                        merged = True
+                        break
+                    trace[q] = s
+                    s = brev8(ring[q][H.event_byte_index(s)]) >> 2
+                qf = (j - (ntb - 1)) % ntb
+                if merged:
+                    s = int(trace[qf])
+                else:
+                    trace[qf] = s
+                have_trace = True
+                out[j - ntb] = brev8(ring[qf][H.event_byte_index(s)])
+            if j in save_at:
+                saved[j] = np.array([int(v[0]) for v in Z], np.uint32)
+        x = (int(Z[0][0]) >> 8) & 0xFF                                  # metric of state 0
+        sub = max(x, 12) - 12
+        env = {"ZERO": one(0), "NEG2": one(((0 - sub) & 0xFF) * 0x01000100), "BITSUB": one(0x00010001 - sub * 0x01000100)}
+        for i in range(32):
+            env["Z[%d]" % i] = Z[i]
+        env.update(apk)
+        H.run_ops(S["part2"], env)
+        V = [env["V_nx[%d]" % i] for i in range(32)]
+        j += 1
+    return saved
+
+
+def normalised_h16b(words):
+    b = np.array([(int(w) >> sh) & 0xFF for w in words for sh in (8, 24)], np.int64)
+    return b - b.min()
+
+
 def normalised(words):
     b = np.array([(int(w) >> (8 * i)) & 0xFF for w in words for i in range(4)], np.int64)
     return b - b.min()
@@ -253,7 +348,8 @@ def normalised(words):
 
 def decode_stream(inp, m, rate, chunk_bytes, warm, force_fixup=False, schedule="swar"):
     """Whole stream from a reset, chunked like the kernel; returns (out bytes, n_fixups)."""
-    decode_chunk = globals()["decode_chunk_h16" if schedule == "h16" else "decode_chunk"]
+    decode_chunk = globals()[{"h16": "decode_chunk_h16", "h16b": "decode_chunk_h16b"}.get(schedule, "decode_chunk")]
+    norm = normalised_h16b if schedule == "h16b" else normalised
     k, n, ntb = RATE_K[rate], RATE_N[rate], RATE_NTB[rate]
     nbt = len(inp) * m * k // (8 * n)  # byte times available
     codes = depuncture_codes(inp, m, rate, nbt)
@@ -272,7 +368,7 @@ def decode_stream(inp, m, rate, chunk_bytes, warm, force_fixup=False, schedule="
     fix = 0
     for c in range(1, len(bounds) - 1):
         A, B = bounds[c], bounds[c + 1]
-        if c in G_ and (force_fixup or not np.array_equal(normalised(G_[c]), normalised(F_[c - 1]))):
+        if c in G_ and (force_fixup or not np.array_equal(norm(G_[c]), norm(F_[c - 1]))):
             fix += 1
             sv = decode_chunk(codes, A + 1, B + ntb, A + ntb, ntb, out, save_at=(B,), init_metrics=F_[c - 1])
             if B in sv:
