@@ -512,8 +512,13 @@ def acs_variants_child(mbit, out):
     d_out = torch.zeros(w.nbytes_out, dtype=torch.uint8, device="cuda")
     res = {"workload": "rate 7/8, m=6, %d x 768-blocks (%.1f Mbit) per launch, %d input buffers cycled" % (w.nblocks, w.info_bits / 1e6, len(d_in))}
     noisy_out = {}
-    for variant in ("h16", "h16b"):
-        os.environ["DVBT_B200_VIT_ACS"] = variant
+    knobs = ("DVBT_B200_VIT_ACS", "DVBT_B200_VIT_TPSM", "DVBT_B200_VIT_BD")
+    variants = [("h16", {"DVBT_B200_VIT_ACS": "h16"}), ("h16b", {"DVBT_B200_VIT_ACS": "h16b"}),
+                ("h16b_512", {"DVBT_B200_VIT_ACS": "h16b", "DVBT_B200_VIT_TPSM": "512", "DVBT_B200_VIT_BD": "512"})]
+    for variant, env in variants:
+        for k in knobs:
+            os.environ.pop(k, None)
+        os.environ.update(env)
         try:
             dec = g.viterbi_decoder(w.CON, g.NH, w.RATE)
             ms = []
