@@ -26,3 +26,11 @@ def test_cuda_chain_reproduces_test_ts_from_packet_504():
     k0 = int(FX["first_packet"])
     assert len(ts) >= int(FX["reference_rx_bytes"])
     assert np.array_equal(ts, head[k0 * 188: k0 * 188 + len(ts)])
+
+
+@pytest.mark.skipif(not R.available(), reason="oracle/_ref not built")
+def test_cuda_chain_config3_8k_qam16_rate12_stage_by_stage():
+    """BASELINE.json configs[3] (8k / QAM16 / rate 1/2) through the stage-by-stage comparison of tests/test_rx_chain_gpu.py;
+    the reference chain starts its TS at packet 2016 in this mode (re-derived with oracle/_ref on the CPU)."""
+    import test_rx_chain_gpu as T
+    T.test_chain_matches_reference_stage_by_stage(R.QAM16, R.C1_2, R.T8k, 290, 2016)
