@@ -339,6 +339,32 @@ class RxWorkload:
             t.join()
         return (time.perf_counter() - t0) * 1e3
 
+    def in_flight_sweep(self, counts, steps):
+        """informational: the resident leg with other numbers of captures in flight (same kernels, more handles)"""
+        res = {}
+        keep = self.NCONC
+        try:
+            for ns in counts:
+                if ns <= len(self.d_in2):
+                    continue
+                g = self.g
+                while len(self.rx2) < ns:
+                    self.rx2.append(g.rx_chain(self.CON, g.NH, self.CR, g.G1_32, self.TM))
+                while len(self.d_in2) < ns:
+                    self.d_in2.append(self.d_in.clone())
+                    self.d_ts2.append(self.torch.zeros_like(self.d_ts))
+                self.torch.cuda.synchronize()
+                self.NCONC = ns
+                self.resident_pair(2)
+                ms = self.resident_pair(steps)
+                same = all(b == self.ts_bytes for b in self.pair_bytes) and all(self.torch.equal(self.d_ts2[0][: self.ts_bytes], t[: self.ts_bytes]) for t in self.d_ts2[1:ns])
+                res[str(ns)] = {"ms_per_capture": ms / steps / ns, "value": self.nfile / 1e6 * ns / (ms / steps / 1e3), "outputs_identical": bool(same)}
+        except Exception as e:   # informational leg: never fatal
+            res["error"] = repr(e)[:200]
+        finally:
+            self.NCONC = keep
+        return res
+
     def step_resident(self, i):
         n = self.rx.run_file_dev(self.d_in.data_ptr(), self.nfile, self.GAIN, self.d_ts.data_ptr(), self.ts_cap)
         inf = self.rx.info()
@@ -738,6 +764,9 @@ def main():
                               "in this leg with CUDA events; `value` is the same chain with %d captures in flight" % w.NCONC)
             line["one_capture_at_a_time"] = single
             line["awgn"] = noisy   # informational: not the metric's configuration (BASELINE configs[1] is noise free)
+            if WORLD == 1 and not os.environ.get("BENCH_NO_SWEEP") and (os.cpu_count() or 1) >= 8:
+                # informational: more captures in flight than the headline's NCONC (single-GPU value per count)
+                line["in_flight_sweep"] = w.in_flight_sweep((6, 8), max(3, a.steps // 4))
             if WORLD == 1 and not os.environ.get("BENCH_NO_ACS_AB"):
                 # informational: the opt-in ACS schedule beside the default one on the Viterbi stage alone (child process)
                 line["acs_variants"] = acs_variants_leg(vbits / 1e6)
