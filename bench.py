@@ -339,14 +339,16 @@ class RxWorkload:
             t.join()
         return (time.perf_counter() - t0) * 1e3
 
-    def in_flight_sweep(self, counts, steps):
-        """informational: the resident leg with other numbers of captures in flight (same kernels, more handles)"""
+    def in_flight_sweep(self, legs, steps):
+        """informational: the resident leg with other numbers of captures in flight (same kernels, more handles) and with
+        launch-geometry knobs of the library that are read at every launch; legs = [(label, captures in flight, env)]"""
         res = {}
         keep = self.NCONC
         try:
-            for ns in counts:
-                if ns <= len(self.d_in2):
-                    continue
+            for label, ns, env in legs:
+                for k in ("DVBT_B200_VIT_SM_DIV",):
+                    os.environ.pop(k, None)
+                os.environ.update(env)
                 g = self.g
                 while len(self.rx2) < ns:
                     self.rx2.append(g.rx_chain(self.CON, g.NH, self.CR, g.G1_32, self.TM))
@@ -358,11 +360,12 @@ class RxWorkload:
                 self.resident_pair(2)
                 ms = self.resident_pair(steps)
                 same = all(b == self.ts_bytes for b in self.pair_bytes) and all(self.torch.equal(self.d_ts2[0][: self.ts_bytes], t[: self.ts_bytes]) for t in self.d_ts2[1:ns])
-                res[str(ns)] = {"ms_per_capture": ms / steps / ns, "value": self.nfile / 1e6 * ns / (ms / steps / 1e3), "outputs_identical": bool(same)}
+                res[label] = {"captures_in_flight": ns, "env": env, "ms_per_capture": ms / steps / ns, "value": self.nfile / 1e6 * ns / (ms / steps / 1e3), "outputs_identical": bool(same)}
         except Exception as e:   # informational leg: never fatal
             res["error"] = repr(e)[:200]
         finally:
             self.NCONC = keep
+            os.environ.pop("DVBT_B200_VIT_SM_DIV", None)
         return res
 
     def step_resident(self, i):
@@ -766,7 +769,11 @@ def main():
             line["awgn"] = noisy   # informational: not the metric's configuration (BASELINE configs[1] is noise free)
             if WORLD == 1 and not os.environ.get("BENCH_NO_SWEEP") and (os.cpu_count() or 1) >= 8:
                 # informational: more captures in flight than the headline's NCONC (single-GPU value per count)
-                line["in_flight_sweep"] = w.in_flight_sweep((6, 8), max(3, a.steps // 4))
+                nc = w.NCONC
+                line["in_flight_sweep"] = w.in_flight_sweep(
+                    [("%d_again" % nc, nc, {}), ("%d_acs_on_half_the_sms" % nc, nc, {"DVBT_B200_VIT_SM_DIV": "2"}),
+                     ("%d_acs_on_a_quarter_of_the_sms" % nc, nc, {"DVBT_B200_VIT_SM_DIV": "4"}), ("6", 6, {}), ("8", 8, {}),
+                     ("8_acs_on_a_quarter_of_the_sms", 8, {"DVBT_B200_VIT_SM_DIV": "4"})], max(3, a.steps // 4))
             if WORLD == 1 and not os.environ.get("BENCH_NO_ACS_AB"):
                 # informational: the opt-in ACS schedule beside the default one on the Viterbi stage alone (child process)
                 line["acs_variants"] = acs_variants_leg(vbits / 1e6)
