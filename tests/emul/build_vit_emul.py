@@ -1,0 +1,120 @@
+"""Builds tests/emul/_build/libvit_emul.so: the DEVICE code of gr_dvbt_b200/csrc/viterbi.cu (depuncture, the one-lane ACS
+kernels of every schedule, verify, repair - text taken from the file as it is) compiled for the host on top of
+tests/emul/cuda_host_emul.h, plus a launcher that mirrors run_decode()'s geometry.  Test infrastructure: it lets a
+CPU-only box run the kernels' own source against the oracle (tests/test_viterbi_host_emul_cpu.py).  What it cannot show:
+anything that depends on the hardware (PRMT / VIADDMNMX semantics are restated in the shim from the PTX ISA and from
+CUDA's own host fallback), launch limits, shared-memory sizes, timing."""
+import os
+import re
+import subprocess
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+CSRC = os.path.join(ROOT, "gr_dvbt_b200", "csrc")
+BUILD = os.path.join(HERE, "_build")
+LIB = os.path.join(BUILD, "libvit_emul.so")
+
+LAUNCHER = r'''
+// ---------------------------------------------------------------------------------------------------------------
+// launcher (mirrors run_decode() of viterbi.cu: one stream, from a reset)
+// ---------------------------------------------------------------------------------------------------------------
+namespace {
+template <int RATE>
+void emul_depuncture(int m, const uint8_t *in, uint32_t *codes, long long nbt) {
+  unsigned grid = (unsigned)((nbt + 63) / 64);
+  if (m == 2) emul_launch(vit_depuncture_kernel<RATE, 2>, grid, 64u, in, 0LL, codes, 0LL, nbt, 1, 0LL);
+  else if (m == 4) emul_launch(vit_depuncture_kernel<RATE, 4>, grid, 64u, in, 0LL, codes, 0LL, nbt, 1, 0LL);
+  else emul_launch(vit_depuncture_kernel<RATE, 6>, grid, 64u, in, 0LL, codes, 0LL, nbt, 1, 0LL);
+}
+template <int V>
+void emul_acs(bool gring, unsigned grid, unsigned bd, VitGeom g) {
+  if (gring) emul_launch(vit_acs_kernel<true, 0, V, 0>, grid, bd, g);
+  else emul_launch(vit_acs_kernel<false, 0, V, 0>, grid, bd, g);
+}
+}  // namespace
+
+extern "C" int emul_viterbi(const uint8_t *in, long long n_in, int rate, int m, int variant, int L, int W, int bd, int depth,
+                            uint8_t *out, long long *n_out, unsigned *counters_out) {
+  const int k = rate_k(rate), n = rate_n(rate), ntb = kNtb[rate];
+  const long long nbt = n_in * m * k / (8 * n);
+  const int O1 = (int)nbt - ntb;
+  *n_out = O1 > 0 ? O1 : 0;
+  if (O1 <= 0) return 0;
+  std::vector<uint32_t> codes((size_t)nbt + 1);
+  switch (rate) {
+    case 0: emul_depuncture<0>(m, in, codes.data(), nbt); break;
+    case 1: emul_depuncture<1>(m, in, codes.data(), nbt); break;
+    case 2: emul_depuncture<2>(m, in, codes.data(), nbt); break;
+    case 3: emul_depuncture<3>(m, in, codes.data(), nbt); break;
+    default: emul_depuncture<4>(m, in, codes.data(), nbt); break;
+  }
+  if (depth <= 0 || depth > ntb) depth = ntb;
+  const bool gring = depth < ntb;
+  if (gring) L = (L + ntb - 1) / ntb * ntb;      // run_decode: chunk length a multiple of ntb with the split ring
+  const int nchunks = (O1 + L - 1) / L;
+  const int gfw = variant == 2 ? 32 : 16;
+  const unsigned grid = (unsigned)((nchunks + bd - 1) / bd);
+  std::vector<uint32_t> G((size_t)nchunks * gfw), F((size_t)nchunks * gfw), gr(gring ? (size_t)grid * ntb * 16 * bd : 1);
+  std::vector<uint8_t> bad((size_t)nchunks);
+  unsigned counters[4] = {0, 0, 0, 0};
+  VitGeom g;
+  g.codes = codes.data(); g.codes_stride = nbt; g.out = out; g.out_stride = 0;
+  g.G = G.data(); g.F = F.data(); g.prevF = nullptr; g.bad = bad.data(); g.counters = counters;
+  g.nstreams = 1; g.nchunks = nchunks; g.L = L; g.W = W; g.ntb = ntb; g.nbt = (int)nbt; g.O0 = 0; g.O1 = O1; g.reset_at_0 = 1;
+  g.neg1 = 0xffffffffu; g.two = 2u; g.one = 1u; g.ring_depth = depth; g.gring = gring ? gr.data() : nullptr; g.gf_words = gfw;
+  if ((size_t)(kLutWords + (ntb + 16 * depth) * bd) > sizeof(smem) / 4 || (size_t)(kLutWords + ntb * kRowWords * 32) > sizeof(smem) / 4) return -1;
+  if (variant == 2) emul_acs<2>(gring, grid, (unsigned)bd, g);
+  else if (variant == 1) emul_acs<1>(gring, grid, (unsigned)bd, g);
+  else emul_acs<0>(gring, grid, (unsigned)bd, g);
+  if (gfw == 32) emul_launch(vit_verify_kernel<32>, (unsigned)((nchunks + 63) / 64), 64u, g);
+  else emul_launch(vit_verify_kernel<16>, (unsigned)((nchunks + 63) / 64), 64u, g);
+  if (variant == 2) emul_launch(vit_repair_kernel<2>, 1u, 32u, g);
+  else if (variant == 1) emul_launch(vit_repair_kernel<1>, 1u, 32u, g);
+  else emul_launch(vit_repair_kernel<0>, 1u, 32u, g);
+  for (int i = 0; i < 4; i++) counters_out[i] = counters[i];
+  return 0;
+}
+'''
+
+
+def device_text():
+    src = open(os.path.join(CSRC, "viterbi.cu")).read()
+    a = src.index('#include "common.cuh"') + len('#include "common.cuh"')
+    b = src.index("\nstruct dvbt_b200_viterbi {")
+    text = src[a:b]
+    # the banner of the host part trails the device part: cut after the namespace that holds the kernels
+    text = text[: text.rindex("}  // namespace") + len("}  // namespace")] + "\n"
+    for needle in ("vit_acs_kernel(VitGeom g)", "vit_repair_kernel(VitGeom g)", "vit_verify_kernel(VitGeom g)", "vit_decode_range("):
+        assert needle in text, "viterbi.cu changed shape: %r not in the extracted device part" % needle
+    assert "cudaMalloc" not in text and "cudaStream" not in text
+    return text
+
+
+def build(force=False):
+    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.startswith("viterbi")] + [os.path.join(HERE, "cuda_host_emul.h"), __file__]
+    if not force and os.path.exists(LIB) and all(os.path.getmtime(d) <= os.path.getmtime(LIB) for d in deps):
+        return LIB
+    os.makedirs(BUILD, exist_ok=True)
+    for h in ("viterbi_acs_gen.cuh", "viterbi_acs2_gen.cuh", "viterbi_acs_h16_gen.cuh", "viterbi_acs_h16b_gen.cuh"):
+        t = open(os.path.join(CSRC, h)).read()
+        if h == "viterbi_acs_gen.cuh":   # the two inline-PTX helpers, restated for the host
+            t, n1 = re.subn(r'asm\("prmt\.b32 [^;]*;"[^;]*;', "r = emul_prmt(a, b, sel);", t)
+            t, n2 = re.subn(r'asm\("mad\.lo\.u32 [^;]*;"[^;]*;', "r = a * b + c;", t)
+            assert n1 == 1 and n2 == 1, (n1, n2)
+        assert "asm(" not in t, h
+        open(os.path.join(BUILD, h), "w").write(t)
+    tu = ('// GENERATED by tests/emul/build_vit_emul.py from gr_dvbt_b200/csrc/viterbi.cu -- test infrastructure\n'
+          '#include "../cuda_host_emul.h"\n'
+          'namespace { alignas(16) uint32_t smem[1 << 17]; }   // the dynamic shared memory of the running block\n'
+          + device_text() + LAUNCHER)
+    path = os.path.join(BUILD, "vit_emul.cpp")
+    open(path, "w").write(tu)
+    cmd = ["g++", "-std=c++20", "-O1", "-fPIC", "-shared", "-pthread", "-Wno-unknown-pragmas", "-Wno-unused", "-o", LIB, path]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("host build of the Viterbi device code failed:\n" + (r.stdout + r.stderr)[-6000:])
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build(force=True))
