@@ -84,6 +84,7 @@ def device_text():
     text = src[a:b]
     # the banner of the host part trails the device part: cut after the namespace that holds the kernels
     text = text[: text.rindex("}  // namespace") + len("}  // namespace")] + "\n"
+    text = text.replace("extern __shared__", "extern")
     for needle in ("vit_acs_kernel(VitGeom g)", "vit_repair_kernel(VitGeom g)", "vit_verify_kernel(VitGeom g)", "vit_decode_range("):
         assert needle in text, "viterbi.cu changed shape: %r not in the extracted device part" % needle
     assert "cudaMalloc" not in text and "cudaStream" not in text
@@ -116,5 +117,70 @@ def build(force=False):
     return LIB
 
 
+RX_LIB = os.path.join(BUILD, "librx_emul.so")
+
+RX_LAUNCHER = r'''
+extern "C" int emul_inner_codes(const uint8_t *dm, const int *out_src, const int *out_symidx, const short *H, const short *Hinv, int P, int m,
+                                int n_out, int rate, uint32_t *codes, int nbt) {
+  InnerMap im{dm, out_src, out_symidx, H, Hinv, P, m, n_out};
+  const int G = kInnerTileCells / P;
+  const unsigned grid = (unsigned)((n_out + G - 1) / G);
+#define EMUL_INNER(R, M) emul_launch(rx_inner_codes_kernel<R, M>, grid, 256u, im, codes, nbt)
+#define EMUL_RATE(R) (m == 2 ? EMUL_INNER(R, 2) : m == 4 ? EMUL_INNER(R, 4) : EMUL_INNER(R, 6))
+  switch (rate) {
+    case 0: EMUL_RATE(0); break;
+    case 1: EMUL_RATE(1); break;
+    case 2: EMUL_RATE(2); break;
+    case 3: EMUL_RATE(3); break;
+    default: EMUL_RATE(4); break;
+  }
+  return 0;
+}
+
+extern "C" int emul_descramble(const uint8_t *rs, long long npk, const uint32_t *prbs, uint8_t *ts, long long ts_capacity, int grid,
+                               int *p0, long long *ngroups) {
+  DescrInfo info{-1, 0};
+  emul_launch(rx_descramble_kernel, (unsigned)grid, 256u, rs, npk, prbs, ts, ts_capacity, &info);
+  *p0 = info.p0;
+  *ngroups = info.ngroups;
+  return 0;
+}
+'''
+
+
+def rx_device_text():
+    src = open(os.path.join(CSRC, "rx_chain.cu")).read()
+    a = src.index("struct InnerMap {")
+    b = src.index("\nstruct dvbt_b200_rx {")
+    text = src[a:b]
+    text = text[: text.rindex("}  // namespace")]
+    for needle in ("rx_inner_codes_kernel(InnerMap im", "rx_descramble_kernel(", "struct DescrInfo"):
+        assert needle in text, "rx_chain.cu changed shape: %r not in the extracted device part" % needle
+    assert "cudaMalloc" not in text and "cudaStream" not in text
+    return text.replace("extern __shared__", "extern")
+
+
+def build_rx(force=False):
+    """tests/emul/_build/librx_emul.so: rx_inner_codes_kernel and rx_descramble_kernel of rx_chain.cu for the host"""
+    deps = [os.path.join(CSRC, "rx_chain.cu"), os.path.join(HERE, "cuda_host_emul.h"), __file__]
+    if not force and os.path.exists(RX_LIB) and all(os.path.getmtime(d) <= os.path.getmtime(RX_LIB) for d in deps):
+        return RX_LIB
+    os.makedirs(BUILD, exist_ok=True)
+    tu = ('// GENERATED by tests/emul/build_vit_emul.py from gr_dvbt_b200/csrc/rx_chain.cu -- test infrastructure\n'
+          '#include <string.h>\n#include "../cuda_host_emul.h"\n'
+          'namespace {\nalignas(16) uint8_t s_bit[1 << 17];   // the dynamic shared memory of the running block\n'
+          + rx_device_text() + RX_LAUNCHER + "}  // namespace\n")
+    # the launchers are extern "C": they must sit outside the unnamed namespace
+    tu = tu.replace(RX_LAUNCHER + "}  // namespace\n", "}  // namespace\n" + RX_LAUNCHER)
+    path = os.path.join(BUILD, "rx_emul.cpp")
+    open(path, "w").write(tu)
+    cmd = ["g++", "-std=c++20", "-O1", "-fPIC", "-shared", "-pthread", "-Wno-unknown-pragmas", "-Wno-unused", "-o", RX_LIB, path]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("host build of the rx_chain device code failed:\n" + (r.stdout + r.stderr)[-6000:])
+    return RX_LIB
+
+
 if __name__ == "__main__":
     print(build(force=True))
+    print(build_rx(force=True))

@@ -20,7 +20,8 @@
 #define __device__
 #define __host__
 #define __forceinline__ inline
-#define __shared__
+#define __shared__ static   /* function-local shared variables; `extern __shared__` is rewritten to `extern` by the builder */
+#define __align__(n) __attribute__((aligned(n)))
 #define __launch_bounds__(...)
 
 struct emul_dim3 { unsigned x = 0, y = 0, z = 0; };
@@ -44,6 +45,24 @@ static inline uint32_t __shfl_xor_sync(unsigned, uint32_t, int) { emul_unsupport
 static inline uint32_t __shfl_sync(unsigned, uint32_t, int) { emul_unsupported("__shfl_sync"); }
 
 static inline unsigned atomicAdd(unsigned *p, unsigned v) { return __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
+static inline unsigned long long atomicMin(unsigned long long *p, unsigned long long v) {
+  unsigned long long old = __atomic_load_n(p, __ATOMIC_RELAXED);
+  while (v < old && !__atomic_compare_exchange_n(p, &old, v, false, __ATOMIC_RELAXED, __ATOMIC_RELAXED)) {}
+  return old;
+}
+static int emul_block_or = 0;
+static inline int __syncthreads_or(int pred) {
+  if (pred) __atomic_fetch_or(&emul_block_or, 1, __ATOMIC_RELAXED);
+  __syncthreads();
+  const int r = __atomic_load_n(&emul_block_or, __ATOMIC_RELAXED);
+  __syncthreads();
+  if (threadIdx.x == 0) __atomic_store_n(&emul_block_or, 0, __ATOMIC_RELAXED);
+  __syncthreads();
+  return r;
+}
+static inline uint32_t __funnelshift_r(uint32_t lo, uint32_t hi, uint32_t shift) {
+  return (uint32_t)((((uint64_t)hi << 32) | lo) >> (shift & 31u));
+}
 static inline int __popc(unsigned v) { return __builtin_popcount(v); }
 static inline unsigned __brev(unsigned v) {
   v = ((v >> 1) & 0x55555555u) | ((v & 0x55555555u) << 1);
