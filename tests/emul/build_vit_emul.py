@@ -181,6 +181,51 @@ def build_rx(force=False):
     return RX_LIB
 
 
+RS_LIB = os.path.join(BUILD, "librs_emul.so")
+
+RS_LAUNCHER = r'''
+extern "C" int emul_rs(const uint8_t *in, uint8_t *out, int *status, long long npackets, int as_built, long long gather_stream_bytes) {
+  if (npackets <= 0) return 0;
+  if (dvbt::rs_upload_tables()) return -1;
+  const unsigned grid = (unsigned)((npackets + kTilePk - 1) / kTilePk);
+  if (gather_stream_bytes >= 0) emul_launch(rs_decode_kernel<true>, grid, (unsigned)kTilePk, in, out, status, npackets, as_built, gather_stream_bytes);
+  else emul_launch(rs_decode_kernel<false>, grid, (unsigned)kTilePk, in, out, status, npackets, as_built, 0LL);
+  return 0;
+}
+'''
+
+
+def build_rs(force=False):
+    """tests/emul/_build/librs_emul.so: rs_decode_kernel (both load paths) and the table construction of rs.cu for the host"""
+    deps = [os.path.join(CSRC, "rs.cu"), os.path.join(HERE, "cuda_host_emul.h"), __file__]
+    if not force and os.path.exists(RS_LIB) and all(os.path.getmtime(d) <= os.path.getmtime(RS_LIB) for d in deps):
+        return RS_LIB
+    os.makedirs(BUILD, exist_ok=True)
+    src = open(os.path.join(CSRC, "rs.cu")).read()
+    a = src.index("namespace {\n\nconstexpr int kN = 255")
+    b = src.index("\nstruct dvbt_b200_rsdec {")
+    kernels = src[a:b]
+    kernels = kernels[: kernels.rindex("}  // namespace") + len("}  // namespace")] + "\n"
+    c = src.index("int rs_upload_tables() {")
+    tables = src[c: src.index("\n}\n", c) + 3]
+    assert "rs_decode_kernel(" in kernels and "rs_warp_decode(" in kernels and "cudaMemcpyToSymbol(d_lfsr" in tables
+    tu = ('// GENERATED by tests/emul/build_vit_emul.py from gr_dvbt_b200/csrc/rs.cu -- test infrastructure\n'
+          '#include "../cuda_host_emul.h"\n'
+          '#define DVBT_CUDA_TRY(x) (void)(x)\n'
+          '#define cudaMemcpyToSymbol(sym, src, n) (memcpy((void *)&(sym), (src), (n)), 0)\n'
+          'static inline int cudaGetDevice(int *d) { *d = 0; return 0; }\n'
+          'namespace { alignas(16) uint8_t s_dyn[1 << 18]; }   // the dynamic shared memory of the running block\n'
+          + kernels.replace("extern __shared__", "extern") + "namespace dvbt {\n" + tables + "}  // namespace dvbt\n" + RS_LAUNCHER)
+    path = os.path.join(BUILD, "rs_emul.cpp")
+    open(path, "w").write(tu)
+    cmd = ["g++", "-std=c++20", "-O1", "-fPIC", "-shared", "-pthread", "-Wno-unknown-pragmas", "-Wno-unused", "-o", RS_LIB, path]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("host build of the RS device code failed:\n" + (r.stdout + r.stderr)[-6000:])
+    return RS_LIB
+
+
 if __name__ == "__main__":
     print(build(force=True))
     print(build_rx(force=True))
+    print(build_rs(force=True))

@@ -3,12 +3,13 @@
 //
 // One CUDA thread = one host thread (threadIdx / blockIdx are thread_local), the threads of a block run
 // concurrently and __syncthreads() is a barrier over them; blocks run one after another; dynamic shared memory is
-// one static buffer per process.  Warp-level primitives are NOT emulated (the one-lane ACS kernels, the verify and
-// repair kernels and the depuncture kernel do not use any); calling one aborts.
+// one static buffer per process.  Warp shuffles / ballots / __syncwarp are lock-step exchanges over a per-warp barrier
+// (converged, full-mask use only).
 #pragma once
 #include <stdint.h>
 #include <stdio.h>
 #include <stdlib.h>
+#include <string.h>
 
 #include <algorithm>
 #include <barrier>
@@ -28,7 +29,7 @@ struct emul_dim3 { unsigned x = 0, y = 0, z = 0; };
 static thread_local emul_dim3 threadIdx, blockIdx;
 static emul_dim3 blockDim, gridDim;
 
-struct alignas(16) uint4 { uint32_t x, y, z, w; };
+struct uint4 { uint32_t x, y, z, w; };   // not over-aligned: the host compiler then never assumes 16-byte alignment
 
 using std::max;
 using std::min;
@@ -36,15 +37,51 @@ using std::min;
 static std::barrier<> *emul_block_barrier = nullptr;
 static inline void __syncthreads() { emul_block_barrier->arrive_and_wait(); }
 
-[[noreturn]] static inline void emul_unsupported(const char *what) {
-  fprintf(stderr, "cuda_host_emul: %s is not emulated\n", what);
-  abort();
+// Warp primitives: the threads of a warp (32 consecutive threads of the block) meet at a per-warp barrier and exchange
+// through a per-warp buffer.  Every live thread of the warp must take part (the member masks are not interpreted: the
+// kernels that are emulated call them converged, with full masks).
+struct EmulWarp {
+  std::barrier<> bar;
+  uint32_t x[32];
+  explicit EmulWarp(int n) : bar(n) {}
+};
+static thread_local EmulWarp *emul_warp = nullptr;
+static inline void __syncwarp(unsigned = 0xffffffffu) { emul_warp->bar.arrive_and_wait(); }
+template <class T, class F>
+static inline T emul_exchange(T v, F pick) {
+  static_assert(sizeof(T) == 4, "32-bit values only");
+  const int lane = (int)(threadIdx.x & 31u);
+  uint32_t u;
+  memcpy(&u, &v, 4);
+  emul_warp->x[lane] = u;
+  emul_warp->bar.arrive_and_wait();
+  const int src = pick(lane);
+  uint32_t r = (src >= 0 && src < 32) ? emul_warp->x[src] : u;
+  emul_warp->bar.arrive_and_wait();
+  T out;
+  memcpy(&out, &r, 4);
+  return out;
 }
-static inline void __syncwarp(unsigned = 0xffffffffu) { emul_unsupported("__syncwarp"); }
-static inline uint32_t __shfl_xor_sync(unsigned, uint32_t, int) { emul_unsupported("__shfl_xor_sync"); }
-static inline uint32_t __shfl_sync(unsigned, uint32_t, int) { emul_unsupported("__shfl_sync"); }
+template <class T> static inline T __shfl_xor_sync(unsigned, T v, int lanemask) { return emul_exchange(v, [=](int l) { return l ^ lanemask; }); }
+template <class T> static inline T __shfl_up_sync(unsigned, T v, int delta) { return emul_exchange(v, [=](int l) { return l - delta; }); }
+template <class T> static inline T __shfl_down_sync(unsigned, T v, int delta) { return emul_exchange(v, [=](int l) { return l + delta < 32 ? l + delta : -1; }); }
+template <class T> static inline T __shfl_sync(unsigned, T v, int src) { return emul_exchange(v, [=](int) { return src & 31; }); }
+static inline unsigned __ballot_sync(unsigned, int pred) {
+  const int lane = (int)(threadIdx.x & 31u);
+  emul_warp->x[lane] = pred ? 1u : 0u;
+  emul_warp->bar.arrive_and_wait();
+  unsigned r = 0;
+  const int n = (int)std::min(32u, blockDim.x - (threadIdx.x & ~31u));
+  for (int i = 0; i < n; i++) r |= emul_warp->x[i] << i;
+  emul_warp->bar.arrive_and_wait();
+  return r;
+}
+static inline int __clz(int v) { return v ? __builtin_clz((unsigned)v) : 32; }
+template <class T> static inline T __ldg(const T *p) { return *p; }
+#define __constant__
 
 static inline unsigned atomicAdd(unsigned *p, unsigned v) { return __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
+static inline int atomicAdd(int *p, int v) { return __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
 static inline unsigned long long atomicMin(unsigned long long *p, unsigned long long v) {
   unsigned long long old = __atomic_load_n(p, __ATOMIC_RELAXED);
   while (v < old && !__atomic_compare_exchange_n(p, &old, v, false, __ATOMIC_RELAXED, __ATOMIC_RELAXED)) {}
@@ -59,6 +96,10 @@ static inline int __syncthreads_or(int pred) {
   if (threadIdx.x == 0) __atomic_store_n(&emul_block_or, 0, __ATOMIC_RELAXED);
   __syncthreads();
   return r;
+}
+// funnel shift left: the upper 32 bits of (hi:lo) << (shift & 31)
+static inline uint32_t __funnelshift_l(uint32_t lo, uint32_t hi, uint32_t shift) {
+  return (uint32_t)(((((uint64_t)hi << 32) | lo) << (shift & 31u)) >> 32);
 }
 static inline uint32_t __funnelshift_r(uint32_t lo, uint32_t hi, uint32_t shift) {
   return (uint32_t)((((uint64_t)hi << 32) | lo) >> (shift & 31u));
@@ -103,14 +144,18 @@ static void emul_launch(Kernel kern, unsigned grid, unsigned block, Args... args
   for (unsigned b = 0; b < grid; b++) {
     std::barrier<> bar((std::ptrdiff_t)block);
     emul_block_barrier = &bar;
+    std::vector<std::unique_ptr<EmulWarp>> warps;
+    for (unsigned w = 0; w * 32 < block; w++) warps.emplace_back(new EmulWarp((int)std::min(32u, block - 32 * w)));
     std::vector<std::thread> th;
     th.reserve(block);
     for (unsigned t = 0; t < block; t++)
-      th.emplace_back([=, &bar]() {
+      th.emplace_back([=, &bar, &warps]() {
         threadIdx.x = t;
         blockIdx.x = b;
+        emul_warp = warps[t >> 5].get();
         kern(args...);
-        bar.arrive_and_drop();   // a thread that has returned no longer takes part in later barriers
+        emul_warp->bar.arrive_and_drop();   // a thread that has returned no longer takes part in later barriers
+        bar.arrive_and_drop();
       });
     for (auto &x : th) x.join();
   }
