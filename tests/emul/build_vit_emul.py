@@ -225,7 +225,64 @@ def build_rs(force=False):
     return RS_LIB
 
 
+DEMAP_LIB = os.path.join(BUILD, "libdemap_emul.so")
+
+DEMAP_SHIM = r'''
+#include <math.h>
+#include "../../../include/dvbt_b200.h"
+struct float2 { float x, y; };
+struct float4 { float x, y, z, w; };
+struct uchar4 { unsigned char x, y, z, w; };
+static inline float2 make_float2(float x, float y) { return float2{x, y}; }
+// round-to-nearest single operations: plain operators (the TU is built with -ffp-contract=off, SSE arithmetic)
+static inline float __fadd_rn(float a, float b) { return a + b; }
+static inline float __fsub_rn(float a, float b) { return a - b; }
+static inline float __fmul_rn(float a, float b) { return a * b; }
+static inline float __int_as_float(int v) { float f; memcpy(&f, &v, 4); return f; }
+static inline int __float2int_rn(float f) { return (int)lrintf(f); }   // default rounding mode: to nearest even
+#define __grid_constant__
+'''
+
+DEMAP_LAUNCHER = r'''
+extern "C" int emul_demap(const float *in, long long ncells, int constellation, int hierarchy, float gain, uint8_t *out, float *pts_out) {
+  dvbt::DemapTable t;
+  if (dvbt::make_demap_table(constellation, hierarchy, gain, &t)) return -1;
+  for (int i = 0; i < t.size; i++) { pts_out[2 * i] = t.pts[i].x; pts_out[2 * i + 1] = t.pts[i].y; }
+  const long long threads = (ncells + 3) / 4;
+  emul_launch(dvbt::demap_kernel, (unsigned)((threads + 63) / 64), 64u, (const float2 *)in, out, ncells, t);
+  return t.near_ok;
+}
+'''
+
+
+def build_demap(force=False):
+    """tests/emul/_build/libdemap_emul.so: make_demap_table + demap_kernel (demap.cu) with the cell decision of demod.cuh"""
+    deps = [os.path.join(CSRC, "demap.cu"), os.path.join(CSRC, "demod.cuh"), os.path.join(HERE, "cuda_host_emul.h"), __file__]
+    if not force and os.path.exists(DEMAP_LIB) and all(os.path.getmtime(d) <= os.path.getmtime(DEMAP_LIB) for d in deps):
+        return DEMAP_LIB
+    os.makedirs(BUILD, exist_ok=True)
+    hdr = open(os.path.join(CSRC, "demod.cuh")).read()
+    a = hdr.index("namespace dvbt {")
+    b = hdr.index("#endif", hdr.index("#ifdef __CUDACC__"))
+    cells = hdr[a:b].replace("#ifdef __CUDACC__", "") + "}  // namespace dvbt\n"
+    src = open(os.path.join(CSRC, "demap.cu")).read()
+    c = src.index("namespace dvbt {")
+    d = src.index("int demap_launch(")
+    kern = src[c:d] + "}  // namespace dvbt\n"
+    assert "demap_cell_exact" in cells and "demap_cell_near" in cells and "demap_kernel(" in kern and "make_demap_table(" in kern
+    tu = ('// GENERATED by tests/emul/build_vit_emul.py from gr_dvbt_b200/csrc/demap.cu and demod.cuh -- test infrastructure\n'
+          '#include "../cuda_host_emul.h"\n' + DEMAP_SHIM + cells + kern + DEMAP_LAUNCHER)
+    path = os.path.join(BUILD, "demap_emul.cpp")
+    open(path, "w").write(tu)
+    cmd = ["g++", "-std=c++20", "-O1", "-ffp-contract=off", "-fPIC", "-shared", "-pthread", "-Wno-unknown-pragmas", "-Wno-unused", "-o", DEMAP_LIB, path]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("host build of the demap device code failed:\n" + (r.stdout + r.stderr)[-6000:])
+    return DEMAP_LIB
+
+
 if __name__ == "__main__":
     print(build(force=True))
     print(build_rx(force=True))
     print(build_rs(force=True))
+    print(build_demap(force=True))

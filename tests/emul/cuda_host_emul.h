@@ -124,6 +124,8 @@ static inline uint32_t emul_prmt(uint32_t a, uint32_t b, uint32_t sel) {
   }
   return r;
 }
+// __byte_perm(x, y, s): selector indices are the low three bits of each of the four low nibbles of s
+static inline uint32_t __byte_perm(uint32_t x, uint32_t y, uint32_t s) { return emul_prmt(x, y, s & 0x7777u); }
 // add.u16x2 + max.u16x2 (what __viaddmax_u16x2 expands to on sm_90+): per halfword max((a + b) mod 2^16, c)
 static inline uint32_t __viaddmax_u16x2(uint32_t a, uint32_t b, uint32_t c) {
   const uint32_t lo = max((a + b) & 0xffffu, c & 0xffffu);

@@ -177,3 +177,19 @@ def test_port_chain_matches_the_reference_build_stage_by_stage(con, cr, tm, nsym
             src = tx["ts"]
             k0 = [c for c in range(0, len(src) // 188, 8) if np.array_equal(src[c * 188: c * 188 + 1504], tsr[:1504])]
             assert k0 and np.array_equal(tsr, src[k0[0] * 188: k0[0] * 188 + len(tsr)])
+
+
+@pytest.mark.skipif(not R.available(), reason="oracle/_ref not built")
+@pytest.mark.parametrize("con,hier,alpha", [(1, 2, 2), (1, 3, 4), (2, 2, 2), (2, 3, 4), (1, 1, 1)])
+def test_demap_port_matches_the_reference_build_on_hierarchical_constellations(con, hier, alpha):
+    """dvbt_demap with hierarchy ALPHA1 / ALPHA2 / ALPHA4 (non-uniform constellations): the reference block itself against
+    the restatement, which in turn checks the CUDA table and kernel (tests/test_demap_host_emul_cpu.py)"""
+    pts = O.constellation_points(con, alpha, 1.0)
+    rng = np.random.default_rng(con * 10 + alpha)
+    n = 1512 * 2
+    c = (pts[rng.integers(0, len(pts), n)] + (rng.normal(0, 0.2, n) + 1j * rng.normal(0, 0.2, n))).astype(np.complex64)
+    mids = ((pts[:, None] + pts[None, :]) / 2).reshape(-1).astype(np.complex64)
+    c[: min(len(mids), n)] = mids[:n]
+    ref = np.zeros(n, np.uint8)
+    R.RefBlock("dvbt_demap", 1512, con, hier, R.T2k, 1.0).work(2, 2, np.ascontiguousarray(c), ref)
+    assert np.array_equal(O.demap(c, con, alpha, 1.0), ref)
