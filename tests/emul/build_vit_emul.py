@@ -281,7 +281,93 @@ def build_demap(force=False):
     return DEMAP_LIB
 
 
+DEMOD_LIB = os.path.join(BUILD, "libdemod_emul.so")
+
+DEMOD_SHIM = r'''
+#include <new>
+#include <vector>
+typedef void *cudaStream_t;
+typedef void *cudaEvent_t;
+static inline double __dadd_rn(double a, double b) { return a + b; }
+static inline double __dsub_rn(double a, double b) { return a - b; }
+static inline double __dmul_rn(double a, double b) { return a * b; }
+static inline double __ddiv_rn(double a, double b) { return a / b; }
+enum { cudaMemcpyHostToDevice = 1 };
+static inline int cudaMemcpy(void *d, const void *s, size_t n, int) { memcpy(d, s, n); return 0; }
+#define DVBT_CUDA_TRY(x) (void)(x)
+namespace dvbt {
+static inline void set_error(const char *, ...) {}
+struct DevBuf {            // "device" memory is host memory here
+  void *p = nullptr;
+  size_t cap = 0;
+  int reserve(size_t bytes) { if (bytes > cap) { free(p); p = calloc(bytes + 64, 1); cap = bytes; } return p ? 0 : -1; }
+  void release() { free(p); p = nullptr; cap = 0; }
+  template <class T> T *as() const { return (T *)p; }
+};
+}  // namespace dvbt
+'''
+
+DEMOD_LAUNCHER = r'''
+// mirrors demod_run() of demod.cu (the four launches in order) on host buffers, from a fresh receiver state
+extern "C" int emul_demod(const float *Xf, int nsym, int constellation, int tm, int fi_start, int sync_start_at0, float *Y_out, uint8_t *dm_out,
+                          int *symidx_out, int *src_out, int *n_out, int *first_out, int *sf_tag_at) {
+  using namespace dvbt;
+  ModeTables tabs;
+  if (tabs.init(tm, DVBT_G1_32)) return -1;
+  const ModeDev &md = tabs.dev;
+  DemapTable dt;
+  if (make_demap_table(constellation, DVBT_NH, 1.0f, &dt)) return -2;
+  const int nparse = nsym - 1;
+  if (nparse <= 0) return -3;
+  const float2 *X = (const float2 *)Xf;
+  std::vector<int> fo(nparse), mod(nparse), vote(nparse), osym(nparse), osrc(nparse);
+  std::vector<float2> rot(nparse), tps((size_t)nparse * md.ntps);
+  DemodState st;
+  memset(&st, 0, sizeof st);
+  emul_launch(demod_stage1_kernel, (unsigned)(((long long)nparse * 32 + 127) / 128), 128u, md, X, nparse, fo.data(), rot.data(), mod.data());
+  emul_launch(demod_equalise_kernel, (unsigned)nparse, 256u, md, dt, 1, X, (const int *)fo.data(), (const float2 *)rot.data(), (const int *)mod.data(),
+              tps.data(), (float2 *)Y_out, dm_out);
+  emul_launch(demod_vote_kernel, (unsigned)((nparse + 127) / 128), 128u, md.ntps, nparse, (const float2 *)tps.data(), &st, vote.data());
+  emul_launch(demod_scan_kernel, 1u, (unsigned)(32 * kScanWarps), md.ntps, nparse, fi_start, sync_start_at0, (const int *)mod.data(), (const int *)vote.data(),
+              (const float2 *)tps.data(), &st, osym.data(), osrc.data());
+  *n_out = st.n_out; *first_out = st.first_out; *sf_tag_at = st.sf_tag_at;
+  for (int i = 0; i < st.n_out; i++) { symidx_out[i] = osym[i]; src_out[i] = osrc[i]; }
+  tabs.release();
+  return 0;
+}
+'''
+
+
+def build_demod(force=False):
+    """tests/emul/_build/libdemod_emul.so: ModeTables::init and the four demod_reference_signals kernels of demod.cu"""
+    deps = [os.path.join(CSRC, "demod.cu"), os.path.join(CSRC, "demap.cu"), os.path.join(CSRC, "demod.cuh"), os.path.join(HERE, "cuda_host_emul.h"), __file__]
+    if not force and os.path.exists(DEMOD_LIB) and all(os.path.getmtime(d) <= os.path.getmtime(DEMOD_LIB) for d in deps):
+        return DEMOD_LIB
+    os.makedirs(BUILD, exist_ok=True)
+    hdr = open(os.path.join(CSRC, "demod.cuh")).read()
+    hdr = hdr[hdr.index("namespace dvbt {"):].replace("#ifdef __CUDACC__", "").replace("#endif", "")
+    dm = open(os.path.join(CSRC, "demap.cu")).read()
+    dm = dm[dm.index("namespace dvbt {"): dm.index("__device__ __forceinline__ uint8_t demap_cell(")] + "}  // namespace dvbt\n"
+    src = open(os.path.join(CSRC, "demod.cu")).read()
+    body = src[src.index("namespace dvbt {"): src.index("int demod_run(")] + "}  // namespace dvbt\n"
+    for needle in ("demod_stage1_kernel(", "demod_equalise_kernel(", "demod_vote_kernel(", "demod_scan_kernel(", "ModeTables::init("):
+        assert needle in body, "demod.cu changed shape: %r" % needle
+    tu = ('// GENERATED by tests/emul/build_vit_emul.py from gr_dvbt_b200/csrc/demod.cu, demod.cuh, demap.cu -- test infrastructure\n'
+          '#include "../cuda_host_emul.h"\n' + DEMAP_SHIM + DEMOD_SHIM + hdr + dm
+          + 'namespace dvbt { alignas(16) float2 s_gain[1 << 15]; }   // the dynamic shared memory of the running block\n'
+          + body.replace("extern __shared__", "extern") + DEMOD_LAUNCHER)
+    path = os.path.join(BUILD, "demod_emul.cpp")
+    open(path, "w").write(tu)
+    cmd = ["g++", "-std=c++20", "-O1", "-ffp-contract=off", "-D_GNU_SOURCE", "-fPIC", "-shared", "-pthread", "-Wno-unknown-pragmas", "-Wno-unused",
+           "-o", DEMOD_LIB, path]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("host build of the demod device code failed:\n" + (r.stdout + r.stderr)[-8000:])
+    return DEMOD_LIB
+
+
 if __name__ == "__main__":
+    print(build_demod(force=True))
     print(build(force=True))
     print(build_rx(force=True))
     print(build_rs(force=True))

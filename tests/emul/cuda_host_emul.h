@@ -76,6 +76,11 @@ static inline unsigned __ballot_sync(unsigned, int pred) {
   emul_warp->bar.arrive_and_wait();
   return r;
 }
+static inline int __all_sync(unsigned m, int pred) {
+  const unsigned n = std::min(32u, blockDim.x - (threadIdx.x & ~31u));
+  return __ballot_sync(m, pred) == (n == 32 ? 0xffffffffu : ((1u << n) - 1u));
+}
+static inline int __any_sync(unsigned m, int pred) { return __ballot_sync(m, pred) != 0; }
 static inline int __clz(int v) { return v ? __builtin_clz((unsigned)v) : 32; }
 template <class T> static inline T __ldg(const T *p) { return *p; }
 #define __constant__
