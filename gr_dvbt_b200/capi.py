@@ -67,7 +67,13 @@ def lib():
         if not os.path.exists(LIB_PATH):
             raise ImportError("gr_dvbt_b200/libdvbt_b200.so is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
                               "(nvcc, sm_100a).  There is no CPU fallback.")
-        L = C.CDLL(LIB_PATH)
+        _lib = declare(C.CDLL(LIB_PATH))
+    return _lib
+
+
+def declare(L):
+    """argument types of every entry point of include/dvbt_b200.h on a loaded library object"""
+    if True:
         vp = C.c_void_p
         L.dvbt_b200_last_error.restype = C.c_char_p
         L.dvbt_b200_kernel_launches.restype = C.c_ulonglong
@@ -115,8 +121,7 @@ def lib():
         L.dvbt_b200_rx_run_file_dev.argtypes = [vp, vp, C.c_size_t, C.c_float, vp, C.c_size_t, C.POINTER(C.c_size_t)]
         L.dvbt_b200_resampler_taps.argtypes = [vp, C.c_int]
         L.dvbt_b200_resample_host.argtypes = [vp, C.c_size_t, C.c_float, vp, C.c_size_t, C.POINTER(C.c_size_t), C.c_int]
-        _lib = L
-    return _lib
+    return L
 
 
 def check(rc):

@@ -366,7 +366,111 @@ def build_demod(force=False):
     return DEMOD_LIB
 
 
+# ---------------------------------------------------------------------------------------------------------------
+# whole-file builds: a .cu file with its host orchestration, on the stand-in runtime of tests/emul/fake_cuda/
+# ---------------------------------------------------------------------------------------------------------------
+def rewrite_cuda(text):
+    """`kernel<<<grid, block[, smem[, stream]]>>>(args)` -> `emul_launch(kernel, grid, block, args)`;
+    `extern __shared__ T name[];` -> `T *name = (T *)emul_dyn_smem;`"""
+    out, i = [], 0
+    while True:
+        j = text.find("<<<", i)
+        if j < 0:
+            out.append(text[i:])
+            break
+        k = j                                  # kernel name (with template arguments) ends at j
+        depth = 0
+        while k > 0:
+            c = text[k - 1]
+            if c == ">":
+                depth += 1
+            elif c == "<":
+                depth -= 1
+            elif depth == 0 and not (c.isalnum() or c in "_:"):
+                break
+            k -= 1
+        name = text[k:j]
+        e = text.index(">>>", j)
+        cfg, parts, depth, cur = text[j + 3: e], [], 0, ""
+        for c in cfg:
+            if c in "([":
+                depth += 1
+            elif c in ")]":
+                depth -= 1
+            if c == "," and depth == 0:
+                parts.append(cur)
+                cur = ""
+            else:
+                cur += c
+        parts.append(cur)
+        assert text[e + 3] == "(", text[j - 40: e + 10]
+        close = text[e + 4:].lstrip().startswith(")")
+        out.append(text[i:k])
+        out.append("emul_launch(%s, %s, (unsigned)(%s)%s" % (name, parts[0].strip(), parts[1].strip(), "" if close else ", "))
+        i = e + 4
+    text = "".join(out)
+    text = re.sub(r"extern __shared__\s+(?:__align__\(\d+\)\s+)?([\w ]+?)\s+(\w+)\[\];", r"\1 *\2 = (\1 *)emul_dyn_smem;", text)
+    assert "<<<" not in text and "extern __shared__" not in text
+    return text
+
+
+def build_whole(libname, files, force=False):
+    lib = os.path.join(BUILD, libname)
+    srcs = [os.path.join(CSRC, f) for f in files]
+    deps = srcs + [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".cuh")] + [
+        os.path.join(HERE, "cuda_host_emul.h"), os.path.join(HERE, "fake_cuda", "cuda_runtime.h"), os.path.join(HERE, "fake_cuda", "cufft.h"), __file__]
+    if not force and os.path.exists(lib) and all(os.path.getmtime(d) <= os.path.getmtime(lib) for d in deps):
+        return lib
+    wdir = os.path.join(BUILD, "whole")
+    os.makedirs(wdir, exist_ok=True)
+    # headers: copies next to the generated sources (a quoted #include looks there first), patched where they hold inline PTX
+    # or hide device functions from a host compiler
+    for h in os.listdir(CSRC):
+        if not h.endswith(".cuh"):
+            continue
+        t = open(os.path.join(CSRC, h)).read()
+        if h == "viterbi_acs_gen.cuh":
+            t, n1 = re.subn(r'asm\("prmt\.b32 [^;]*;"[^;]*;', "r = emul_prmt(a, b, sel);", t)
+            t, n2 = re.subn(r'asm\("mad\.lo\.u32 [^;]*;"[^;]*;', "r = a * b + c;", t)
+            assert n1 == 1 and n2 == 1
+        if h == "demod.cuh":
+            t = t.replace("#ifdef __CUDACC__", "#if 1")
+        assert "asm(" not in t and "asm volatile" not in t, h
+        open(os.path.join(wdir, h), "w").write(rewrite_cuda(t))
+    cpps = []
+    for f in srcs:
+        out = os.path.join(wdir, os.path.basename(f).replace(".cu", "_emul.cpp"))
+        t = open(f).read()
+        if f.endswith("resample.cu"):   # cp.async staging: a synchronous copy is one of its legal executions
+            t, n1 = re.subn(r'asm volatile\("cp\.async\.ca\.shared\.global [^;]*;"[^;]*;', "dst[i] = in ? *src : make_float2(0.f, 0.f);", t)
+            t, n2 = re.subn(r'asm volatile\("cp\.async\.(?:commit_group|wait_group \d)+;" ::: "memory"\);', "(void)0;", t)
+            assert n1 == 1 and n2 == 3, (n1, n2)
+        assert "asm" not in re.sub(r"//.*", "", t), f
+        open(out, "w").write("// GENERATED by tests/emul/build_vit_emul.py from %s -- test infrastructure\n" % os.path.relpath(f, ROOT) + rewrite_cuda(t))
+        cpps.append(out)
+    cmd = ["g++", "-std=c++20", "-O1", "-ffp-contract=off", "-D_GNU_SOURCE", "-fPIC", "-shared", "-pthread", "-Wno-unknown-pragmas", "-Wno-unused",
+           "-Wno-attributes", "-I", os.path.join(HERE, "fake_cuda"), "-I", CSRC, "-o", lib] + cpps
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("whole-file host build failed:\n" + (r.stdout + r.stderr)[-8000:])
+    return lib
+
+
+def build_acq(force=False):
+    """tests/emul/_build/libacq_emul.so: acq.cu (ofdm_sym_acquisition: kernels AND host orchestration) + common.cu, exporting
+    the same C ABI (dvbt_b200_acq_*) on the stand-in runtime"""
+    return build_whole("libacq_emul.so", ["acq.cu", "common.cu"], force)
+
+
+def build_all(force=False):
+    """tests/emul/_build/libdvbt_b200_emul.so: EVERY source file of the library (kernels and host code) on the stand-in
+    runtime - the whole C ABI of include/dvbt_b200.h, running on the CPU.  Loaded by tests only, by explicit path."""
+    return build_whole("libdvbt_b200_emul.so", sorted(f for f in os.listdir(CSRC) if f.endswith(".cu")), force)
+
+
 if __name__ == "__main__":
+    print(build_all(force=True))
+    print(build_acq(force=True))
     print(build_demod(force=True))
     print(build(force=True))
     print(build_rx(force=True))

@@ -34,6 +34,11 @@ struct uint4 { uint32_t x, y, z, w; };   // not over-aligned: the host compiler 
 using std::max;
 using std::min;
 
+// dynamic shared memory of the running block for whole-file builds: `extern __shared__ T name[];` becomes
+// `T *name = (T *)emul_dyn_smem;`
+alignas(128) static unsigned char emul_dyn_smem[256 * 1024];
+
+static unsigned emul_cur_block_y = 0;   // second grid dimension: set by the dim3 overload of emul_launch
 static std::barrier<> *emul_block_barrier = nullptr;
 static inline void __syncthreads() { emul_block_barrier->arrive_and_wait(); }
 
@@ -159,6 +164,7 @@ static void emul_launch(Kernel kern, unsigned grid, unsigned block, Args... args
       th.emplace_back([=, &bar, &warps]() {
         threadIdx.x = t;
         blockIdx.x = b;
+        blockIdx.y = emul_cur_block_y;
         emul_warp = warps[t >> 5].get();
         kern(args...);
         emul_warp->bar.arrive_and_drop();   // a thread that has returned no longer takes part in later barriers
