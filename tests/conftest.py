@@ -9,8 +9,22 @@ if ROOT not in sys.path:
 sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 
 
+def pytest_addoption(parser):
+    parser.addoption("--emulated-library", action="store_true", default=False,
+                     help="run the `gpu` tests on the CPU against tests/emul/_build/libdvbt_b200_emul.so (the library's own "
+                          "sources compiled for the host on a stand-in CUDA runtime; test infrastructure, see tests/emul/)")
+
+
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+    if config.getoption("--emulated-library"):
+        import ctypes
+        sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "emul"))
+        import build_vit_emul
+        import gr_dvbt_b200.capi as capi
+        capi._lib = capi.declare(ctypes.CDLL(build_vit_emul.build_all()))
+        global HAVE_GPU
+        HAVE_GPU = True
 
 
 def _have_gpu():
