@@ -148,29 +148,43 @@ static inline uint32_t __vimax3_u16x2(uint32_t a, uint32_t b, uint32_t c) {
   return lo | (hi << 16);
 }
 
-// kernel<<<grid, block, smem>>>(args...)
+// kernel<<<grid, block, smem>>>(args...): `block` host threads live for the whole launch and walk the blocks together
+// (creating them per block cost more than the kernels themselves); between two blocks they meet twice at an outer
+// barrier while thread 0 renews the per-block and per-warp barriers, which exited threads had dropped out of.
 template <class Kernel, class... Args>
 static void emul_launch(Kernel kern, unsigned grid, unsigned block, Args... args) {
   gridDim.x = grid;
   blockDim.x = block;
-  for (unsigned b = 0; b < grid; b++) {
-    std::barrier<> bar((std::ptrdiff_t)block);
-    emul_block_barrier = &bar;
-    std::vector<std::unique_ptr<EmulWarp>> warps;
-    for (unsigned w = 0; w * 32 < block; w++) warps.emplace_back(new EmulWarp((int)std::min(32u, block - 32 * w)));
-    std::vector<std::thread> th;
-    th.reserve(block);
-    for (unsigned t = 0; t < block; t++)
-      th.emplace_back([=, &bar, &warps]() {
-        threadIdx.x = t;
+  if (grid == 0 || block == 0) return;
+  std::barrier<> outer((std::ptrdiff_t)block);
+  std::unique_ptr<std::barrier<>> inner;
+  std::vector<std::unique_ptr<EmulWarp>> warps((block + 31) / 32);
+  const unsigned y = emul_cur_block_y;
+  auto renew = [&]() {
+    inner.reset(new std::barrier<>((std::ptrdiff_t)block));
+    emul_block_barrier = inner.get();
+    for (unsigned w = 0; w < warps.size(); w++) warps[w].reset(new EmulWarp((int)std::min(32u, block - 32 * w)));
+  };
+  renew();
+  std::vector<std::thread> th;
+  th.reserve(block);
+  for (unsigned t = 0; t < block; t++)
+    th.emplace_back([&, t]() {
+      threadIdx.x = t;
+      blockIdx.y = y;
+      for (unsigned b = 0; b < grid; b++) {
         blockIdx.x = b;
-        blockIdx.y = emul_cur_block_y;
         emul_warp = warps[t >> 5].get();
         kern(args...);
         emul_warp->bar.arrive_and_drop();   // a thread that has returned no longer takes part in later barriers
-        bar.arrive_and_drop();
-      });
-    for (auto &x : th) x.join();
-  }
+        inner->arrive_and_drop();
+        if (b + 1 < grid) {
+          outer.arrive_and_wait();          // every thread has left block b
+          if (t == 0) renew();
+          outer.arrive_and_wait();          // the barriers of block b + 1 are in place
+        }
+      }
+    });
+  for (auto &x : th) x.join();
   emul_block_barrier = nullptr;
 }
