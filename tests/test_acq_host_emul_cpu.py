@@ -16,6 +16,10 @@ from oracle import port as O, refchain as R
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "emul"))
 import build_vit_emul  # noqa: E402
 
+# a kernel that is not warp-converged would dead-lock the lock-step emulation: never hang the suite (the host threads sit
+# inside a C call, so only the thread method of pytest-timeout can end the run)
+pytestmark = pytest.mark.timeout(900, method="thread")
+
 
 @pytest.fixture(scope="module")
 def acq_work():

@@ -13,6 +13,10 @@ from oracle import port as O
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "emul"))
 import build_vit_emul  # noqa: E402
 
+# a kernel that is not warp-converged would dead-lock the lock-step emulation: never hang the suite (the host threads sit
+# inside a C call, so only the thread method of pytest-timeout can end the run)
+pytestmark = pytest.mark.timeout(900, method="thread")
+
 G = np.load(os.path.join(os.path.dirname(__file__), "golden", "hotpath_golden.npz"))
 HIER = {1: 0, 2: 2, 4: 3}   # alpha -> dvbt_hierarchy_t (NH and ALPHA1 both mean alpha = 1)
 
