@@ -64,7 +64,11 @@ struct DevBuf {
   int reserve(size_t bytes) {
     if (bytes <= cap) return 0;
     release();
+#ifdef DVBT_B200_EXACT_ALLOC   // memcheck builds (tests/emul under AddressSanitizer): no slack that would hide an overrun
+    size_t want = bytes;
+#else
     size_t want = bytes + bytes / 8 + 256;
+#endif
     cudaError_t e = host ? cudaMallocHost(&p, want) : cudaMalloc(&p, want);
     if (e != cudaSuccess) {
       p = nullptr;

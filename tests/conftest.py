@@ -22,7 +22,8 @@ def pytest_configure(config):
         sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "emul"))
         import build_vit_emul
         import gr_dvbt_b200.capi as capi
-        capi._lib = capi.declare(ctypes.CDLL(build_vit_emul.build_all()))
+        asan = os.environ.get("DVBT_EMUL_ASAN") == "1"   # AddressSanitizer build: needs LD_PRELOAD of libasan, see build_all_asan()
+        capi._lib = capi.declare(ctypes.CDLL(build_vit_emul.build_all_asan() if asan else build_vit_emul.build_all()))
         global HAVE_GPU
         HAVE_GPU = True
 

@@ -414,7 +414,7 @@ def rewrite_cuda(text):
     return text
 
 
-def build_whole(libname, files, force=False):
+def build_whole(libname, files, force=False, extra_flags=()):
     lib = os.path.join(BUILD, libname)
     srcs = [os.path.join(CSRC, f) for f in files]
     deps = srcs + [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".cuh")] + [
@@ -449,7 +449,7 @@ def build_whole(libname, files, force=False):
         open(out, "w").write("// GENERATED by tests/emul/build_vit_emul.py from %s -- test infrastructure\n" % os.path.relpath(f, ROOT) + rewrite_cuda(t))
         cpps.append(out)
     cmd = ["g++", "-std=c++20", "-O1", "-ffp-contract=off", "-D_GNU_SOURCE", "-fPIC", "-shared", "-pthread", "-Wno-unknown-pragmas", "-Wno-unused",
-           "-Wno-attributes", "-I", os.path.join(HERE, "fake_cuda"), "-I", CSRC, "-o", lib] + cpps
+           "-Wno-attributes", "-I", os.path.join(HERE, "fake_cuda"), "-I", CSRC, "-o", lib] + list(extra_flags) + cpps
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError("whole-file host build failed:\n" + (r.stdout + r.stderr)[-8000:])
@@ -466,6 +466,14 @@ def build_all(force=False):
     """tests/emul/_build/libdvbt_b200_emul.so: EVERY source file of the library (kernels and host code) on the stand-in
     runtime - the whole C ABI of include/dvbt_b200.h, running on the CPU.  Loaded by tests only, by explicit path."""
     return build_whole("libdvbt_b200_emul.so", sorted(f for f in os.listdir(CSRC) if f.endswith(".cu")), force)
+
+
+def build_all_asan(force=False):
+    """the same with AddressSanitizer and exact-size "device" allocations: a memcheck of kernels and host code.
+    Run with  LD_PRELOAD=$(gcc -print-file-name=libasan.so) ASAN_OPTIONS=detect_leaks=0 DVBT_EMUL_ASAN=1 python -m pytest
+    tests -m gpu --emulated-library  (see tests/conftest.py)"""
+    return build_whole("libdvbt_b200_emul_asan.so", sorted(f for f in os.listdir(CSRC) if f.endswith(".cu")), force,
+                       ("-fsanitize=address", "-fno-omit-frame-pointer", "-g", "-DDVBT_B200_EXACT_ALLOC"))
 
 
 if __name__ == "__main__":

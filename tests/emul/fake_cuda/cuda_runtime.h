@@ -60,7 +60,11 @@ static inline cudaError_t cudaGetDeviceCount(int *n) { *n = 1; return cudaSucces
 static inline cudaError_t cudaGetDevice(int *d) { *d = 0; return cudaSuccess; }
 static inline cudaError_t cudaSetDevice(int) { return cudaSuccess; }
 static inline cudaError_t cudaDeviceGetAttribute(int *v, int attr, int) { *v = attr == cudaDevAttrMultiProcessorCount ? 148 : 1965000; return cudaSuccess; }
+#ifdef DVBT_B200_EXACT_ALLOC
+static inline cudaError_t cudaMalloc(void **p, size_t n) { *p = calloc(n ? n : 1, 1); return *p ? cudaSuccess : cudaErrorEmul; }
+#else
 static inline cudaError_t cudaMalloc(void **p, size_t n) { *p = calloc(n + 256, 1); return *p ? cudaSuccess : cudaErrorEmul; }
+#endif
 template <class T> static inline cudaError_t cudaMalloc(T **p, size_t n) { return cudaMalloc((void **)p, n); }
 static inline cudaError_t cudaMallocHost(void **p, size_t n) { return cudaMalloc(p, n); }
 static inline cudaError_t cudaFree(void *p) { free(p); return cudaSuccess; }
