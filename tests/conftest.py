@@ -23,7 +23,9 @@ def pytest_configure(config):
         import build_vit_emul
         import gr_dvbt_b200.capi as capi
         asan = os.environ.get("DVBT_EMUL_ASAN") == "1"   # AddressSanitizer build: needs LD_PRELOAD of libasan, see build_all_asan()
-        capi._lib = capi.declare(ctypes.CDLL(build_vit_emul.build_all_asan() if asan else build_vit_emul.build_all()))
+        tsan = os.environ.get("DVBT_EMUL_TSAN") == "1"   # ThreadSanitizer build (racecheck): LD_PRELOAD of libtsan
+        path = build_vit_emul.build_all_asan() if asan else build_vit_emul.build_all_tsan() if tsan else build_vit_emul.build_all()
+        capi._lib = capi.declare(ctypes.CDLL(path))
         global HAVE_GPU
         HAVE_GPU = True
 

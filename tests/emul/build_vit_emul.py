@@ -476,6 +476,14 @@ def build_all_asan(force=False):
                        ("-fsanitize=address", "-fno-omit-frame-pointer", "-g", "-DDVBT_B200_EXACT_ALLOC"))
 
 
+def build_all_tsan(force=False):
+    """the same with ThreadSanitizer: CUDA threads are host threads and __syncthreads / warp primitives are barriers, so a
+    missing barrier between a shared-memory write and a read by another thread is a data race TSan can see (a racecheck).
+    Run with LD_PRELOAD=$(gcc -print-file-name=libtsan.so) DVBT_EMUL_TSAN=1 ... --emulated-library"""
+    return build_whole("libdvbt_b200_emul_tsan.so", sorted(f for f in os.listdir(CSRC) if f.endswith(".cu")), force,
+                       ("-fsanitize=thread", "-fno-omit-frame-pointer", "-g"))
+
+
 if __name__ == "__main__":
     print(build_all(force=True))
     print(build_acq(force=True))
