@@ -638,7 +638,7 @@ def main():
             if i >= a.warmup:
                 vals.append((agg, wall))
         v = float(np.mean([x[0] for x in vals]))
-        line = {"metric": metric, "value": v, "unit": unit + ", %d processes" % cores, "impl": "reference", "n_gpus": a.gpus,
+        line = {"metric": metric, "value": v, "unit": unit, "impl": "reference", "n_gpus": a.gpus,
                 "steps": a.steps, "warmup": a.warmup, "ms_per_step": float(np.mean([x[1] for x in vals]) * 1e3), "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "u8/f32", "data": "synthetic", "config": w.describe(),
                 "cpu_baseline": {"value": v, "unit": unit.split(" (")[0], "cores": cores, "kind": kind, "sample": sample},

@@ -31,7 +31,8 @@ def build_native(force=False, verbose=False):
     if not force and not needs_build():
         return LIB
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + ["-o", LIB] + sources() + ["-lcufft"]
+    tmp = LIB + ".building"   # the finished library replaces the old one atomically (a GPU-box snapshot never sees half a file)
+    cmd = [nvcc] + NVCC_FLAGS + ["-o", tmp] + sources() + ["-lcufft"]
     if verbose:
         cmd.insert(1, "-Xptxas")
         cmd.insert(2, "-v")
@@ -41,6 +42,7 @@ def build_native(force=False, verbose=False):
         raise RuntimeError("nvcc failed building libdvbt_b200.so")
     if verbose:
         sys.stderr.write(r.stderr)
+    os.replace(tmp, LIB)
     return LIB
 
 

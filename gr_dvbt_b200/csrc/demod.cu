@@ -43,6 +43,7 @@ static const short kTps2k[17] = {34, 50, 209, 346, 413, 569, 595, 688, 790, 901,
 
 int ModeTables::init(int tm, int gi) {
   if (tm != DVBT_T2K && tm != DVBT_T8K) { set_error("mode tables: bad transmission mode %d", tm); return DVBT_B200_EINVAL; }
+  if (gi < DVBT_G1_32 || gi > DVBT_G1_4) { set_error("mode tables: bad guard interval %d (dvbt_config.cc:194-208 knows 1/32 .. 1/4)", gi); return DVBT_B200_EINVAL; }
   ModeDev &d = dev;
   d.N = tm == DVBT_T2K ? 2048 : 8192;
   d.P = tm == DVBT_T2K ? 1512 : 6048;
@@ -622,11 +623,8 @@ int demod_run(const ModeDev &md, const DemapTable *demap, const float2 *X, int n
   }
   {
     size_t smem = (size_t)md.K * sizeof(float2) * 2;
-    static bool attr_set = false;
-    if (!attr_set) {
-      DVBT_CUDA_TRY(cudaFuncSetAttribute(demod_equalise_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
-      attr_set = true;
-    }
+    // per launch, like every other kernel of the library: the attribute is per device and handles live on any device
+    DVBT_CUDA_TRY(cudaFuncSetAttribute(demod_equalise_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
     DemapTable dummy;
     dummy.size = 0;
     if (b.ev_eq0) DVBT_CUDA_TRY(cudaEventRecord(b.ev_eq0, st));

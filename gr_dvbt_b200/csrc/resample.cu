@@ -15,6 +15,8 @@
 
 #include <math.h>
 #include <stdlib.h>
+#include <mutex>
+#include <new>
 #include <vector>
 
 namespace dvbt {
@@ -347,7 +349,22 @@ struct Resampler {
   }
 };
 
+// one per device, built under a lock and published only when complete (several handles are driven from
+// concurrent host threads); a failed init is not cached
 static Resampler *g_res[64] = {nullptr};
+static std::mutex g_res_mutex;
+static int resampler_for_device(int dev, Resampler **out) {
+  std::lock_guard<std::mutex> lock(g_res_mutex);
+  if (!g_res[dev]) {
+    Resampler *r = new (std::nothrow) Resampler();
+    if (!r) { set_error("resampler: out of memory"); return DVBT_B200_ENOMEM; }
+    int rc = r->init();
+    if (rc) { r->d_taps.release(); delete r; return rc; }
+    g_res[dev] = r;
+  }
+  *out = g_res[dev];
+  return 0;
+}
 
 long long resample_out_count(long long nin) { return nin <= 0 ? 0 : ((nin - 1) * kInterp) / kDecim + 1; }
 
@@ -363,12 +380,8 @@ int resample_launch_variant(const float2 *d_x, long long nin, float2 *d_y, long 
   int dev = 0;
   cudaGetDevice(&dev);
   if (dev >= 64) dev = 63;
-  if (!g_res[dev]) {
-    g_res[dev] = new Resampler();
-    int rc = g_res[dev]->init();
-    if (rc) return rc;
-  }
-  Resampler *r = g_res[dev];
+  Resampler *r = nullptr;
+  if (int rc = resampler_for_device(dev, &r)) return rc;
   if (nout <= 0) return 0;
   if (r->per_arm == kRegArm && (nq == 2 || nq == 4)) {
     const long long out_per_tile = (long long)kQuadOut * nq;

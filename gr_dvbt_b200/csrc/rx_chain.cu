@@ -270,6 +270,11 @@ extern "C" {
 int dvbt_b200_rx_create(const dvbt_b200_rx_params *p, dvbt_b200_rx **out) {
   if (!p || !out) { set_error("rx_create: null argument"); return DVBT_B200_EINVAL; }
   *out = nullptr;
+  // the fused inner index map implements the non-hierarchical demultiplexer only (bit_inner_deinterleaver_impl.cc:91-99,
+  // NH branch); a hierarchical stream needs the HP/LP split of the reference flowgraph, which the block-level entry points keep
+  if (p->hierarchy != DVBT_NH) { set_error("rx_create: hierarchy %d: the fused chain is non-hierarchical only", p->hierarchy); return DVBT_B200_EINVAL; }
+  if (p->guard_interval < DVBT_G1_32 || p->guard_interval > DVBT_G1_4) { set_error("rx_create: bad guard interval %d", p->guard_interval); return DVBT_B200_EINVAL; }
+  if (p->code_rate < DVBT_C1_2 || p->code_rate > DVBT_C7_8) { set_error("rx_create: bad code rate %d", p->code_rate); return DVBT_B200_EINVAL; }
   int rc = dvbt::ensure_device();
   if (rc) return rc;
   dvbt_b200_rx *h = new (std::nothrow) dvbt_b200_rx();
