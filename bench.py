@@ -17,6 +17,7 @@ Workloads
 import argparse
 import json
 import os
+import re
 import subprocess
 import sys
 import threading
@@ -236,23 +237,48 @@ class ViterbiWorkload:
 # 10 Msps capture (resampler 64/70, multiply_const, acquisition, FFT, demod, demap, inner
 # deinterleavers, Viterbi, outer deinterleaver, RS, descrambler)
 # ---------------------------------------------------------------------------------------------
+GAIN_2K, GAIN_8K = 0.0022097087, 0.00055242272   # multiply_const of apps/dvbt_rx_demo*.grc (2k / 8k)
+# the RX flowgraphs BASELINE.json names: constellation, code rate, transmission mode (enum values of dvbt_config.h), first TS
+# packet of the round trip, capture = tiles x base_superframes (default 4) superframes.  A tile holds a multiple of
+# 8 TS packets (1323 per superframe at 2k/QAM64/7-8, hence 8 superframes there), so the 8-packet NSYNC cadence of
+# energy_dispersal runs on across the tile seams the way it does in a continuous broadcast
+RX_CONFIGS = {
+    "configs[0]": dict(con=1, cr=0, tm=0, gain=GAIN_2K, first_packet=504, tiles=20, grc="apps/dvbt_rx_demo.grc", mode="2k/QAM16/rate-1/2",
+                       source="apps/test.ts"),
+    "configs[1]": dict(con=2, cr=4, tm=0, gain=GAIN_2K, first_packet=1328, tiles=10, base_superframes=8, grc="apps/dvbt_rx_demo_2k_QAM64_rate78.grc", mode="2k/QAM64/rate-7/8",
+                       source="random"),
+    "configs[2]": dict(con=2, cr=4, tm=1, gain=GAIN_8K, first_packet=3976, tiles=5, grc="apps/dvbt_rx_demo_8k_QAM64_rate78.grc", mode="8k/QAM64/rate-7/8",
+                       source="random"),
+    "configs[3]": dict(con=1, cr=0, tm=1, gain=GAIN_8K, first_packet=2016, tiles=5, grc="apps/dvbt_rx_demo_8k.grc", mode="8k/QAM16/rate-1/2",
+                       source="random"),
+}
+
+
 class RxWorkload:
     name = "rx"
-    CON, CR, TM = 2, 4, 0
-    GAIN = 0.0022097087
+    CON, CR, TM = 2, 4, 0          # configs[1] (the CPU legs below use these class defaults)
+    GAIN = GAIN_2K
     SUPERFRAMES_BASE = 4  # generated once with the reference TX blocks, then tiled
     # independent captures decoded concurrently per GPU (one handle = one CUDA stream + one host thread each): the
     # single-block control kernels of one capture overlap the wide kernels of the others.  Bounded by the host cores per rank.
     NCONC = max(1, env_int("BENCH_STREAMS", min(4, max(1, (os.cpu_count() or 1) // max(1, WORLD)))))
 
-    def __init__(self, tiles):
-        self.tiles = int(tiles)
+    def __init__(self, tiles, key="configs[1]", distinct=False):
+        cfg = RX_CONFIGS[key]
+        self.key, self.cfg = key, cfg
+        self.CON, self.CR, self.TM, self.GAIN = cfg["con"], cfg["cr"], cfg["tm"], cfg["gain"]
+        self.first_packet = cfg["first_packet"]
+        self.tiles = int(tiles) if tiles else cfg["tiles"]
+        self.SUPERFRAMES_BASE = cfg.get("base_superframes", 4)
+        self.distinct = distinct        # every 4-superframe block generated from its own TS (no tiling)
+        self.N, self.P = (2048, 1512) if self.TM == 0 else (8192, 6048)
+        self.k, self.n = {0: (1, 2), 1: (2, 3), 2: (3, 4), 3: (5, 6), 4: (7, 8)}[self.CR]
+        self.m = 2 * (self.CON + 1)
 
     def describe(self):
-        return {"workload": "configs[1]: 2k/QAM64/rate-7/8 RX, synthetic 10 Msps baseband capture -> TS (full flowgraph "
-                            "apps/dvbt_rx_demo_2k_QAM64_rate78.grc: resampler 64/70, multiply_const, ofdm_sym_acquisition, FFT, "
-                            "demod_reference_signals, dvbt_demap, symbol/bit deinterleavers, viterbi_decoder, convolutional_deinterleaver, "
-                            "reed_solomon_dec, energy_descramble)",
+        return {"workload": "%s: %s RX, synthetic 10 Msps baseband capture -> TS (full flowgraph %s: resampler 64/70, "
+                            "multiply_const, ofdm_sym_acquisition, FFT, demod_reference_signals, dvbt_demap, symbol/bit deinterleavers, "
+                            "viterbi_decoder, convolutional_deinterleaver, reed_solomon_dec, energy_descramble)" % (self.key, self.cfg["mode"], self.cfg["grc"]),
                 "captures_per_step": self.NCONC, "samples_per_capture": self.nfile,
                 "samples_per_step": self.nfile * self.NCONC, "ofdm_symbols_per_step": self.nsym * self.NCONC,
                 "input_bytes_per_step": self.nfile * 8 * self.NCONC,
@@ -267,10 +293,22 @@ class RxWorkload:
         if not R.available():
             raise RuntimeError("bench rx workload needs oracle/_ref (reference TX blocks) to synthesise the capture")
         nbase = 272 * self.SUPERFRAMES_BASE
-        tx = tx_frequency_domain(self.CON, self.CR, self.TM, nbase, seed)
-        X0 = tx["X"][:nbase]
-        x0 = ofdm_modulate(X0, self.TM, gain=1.0)           # one block of whole superframes, 64/7 Msps
-        x = np.tile(x0, self.tiles)
+        if self.cfg["source"] == "apps/test.ts":
+            # the head of the reference's own apps/test.ts (2016 packets = exactly 4 superframes in this mode)
+            head = np.load(os.path.join(ROOT, "tests", "golden", "apps_test_ts_head.npz"))["ts_head"]
+            ed, rs, ci = R.tx_outer(head)
+            tx = R.tx_inner(ci, self.CON, self.CR, self.TM, nsym=nbase)
+            tx["ts"] = head
+        else:
+            tx = tx_frequency_domain(self.CON, self.CR, self.TM, nbase, seed)
+        if self.distinct:
+            # one TS of tiles x 4 superframes, nothing repeats (the TX chain runs over the whole length)
+            tx = tx_frequency_domain(self.CON, self.CR, self.TM, nbase * self.tiles, seed)
+            x = ofdm_modulate(tx["X"][: nbase * self.tiles], self.TM, gain=1.0)
+        else:
+            X0 = tx["X"][:nbase]
+            x0 = ofdm_modulate(X0, self.TM, gain=1.0)           # one block of whole superframes, 64/7 Msps
+            x = np.tile(x0, self.tiles)
         self.nsym = nbase * self.tiles
         cap = to_capture_rate(np.concatenate([np.zeros(300, np.complex64), x]))
         self.nfile = len(cap)
@@ -285,7 +323,7 @@ class RxWorkload:
         cap = self.build_capture(seed)
         self.d_in = torch.from_numpy(cap).cuda()
         self.pin_in = torch.from_numpy(cap).pin_memory()
-        self.ts_cap = self.nsym * 1512
+        self.ts_cap = self.nsym * self.P
         self.d_ts = torch.zeros(self.ts_cap, dtype=torch.uint8, device="cuda")
         self.pin_ts = torch.zeros(self.ts_cap, dtype=torch.uint8).pin_memory()
         self.kernel_ms = []
@@ -405,19 +443,38 @@ class RxWorkload:
         ms = (time.perf_counter() - t0) * 1e3 / steps
         inf = self.rx.info()
         ts = self.d_ts[:n].cpu().numpy().reshape(-1, 188)
-        # the capture is one 4-superframe block tiled: only the first tile maps 1:1 onto the source TS (from packet 1328 on)
-        m = min(len(ts), 3900)
+        # a tiled capture maps 1:1 onto the source TS in its first tile only (from the mode's first packet on); a capture of
+        # distinct superframes over its whole length
         src = self.ts_src[: len(self.ts_src) // 188 * 188].reshape(-1, 188)
-        good = int((ts[:m] == src[1328:1328 + m]).all(axis=1).sum()) if m and inf["acq_lost_at"] == -1 else 0
-        return {"snr_db": snr_db, "ms_per_step": ms, "value": self.nfile / 1e6 / (ms / 1e3), "ms_viterbi_acs": inf["ms_viterbi_acs"],
-                "viterbi_repaired_chunks": inf["viterbi_repaired"], "ts_packets": int(len(ts)), "first_tile_packets_checked": int(m),
-                "first_tile_packets_equal_to_source": good}
+        m = min(len(ts), len(src) - self.first_packet) if self.distinct else min(len(ts), 3900)
+        good = int((ts[:m] == src[self.first_packet:self.first_packet + m]).all(axis=1).sum()) if m > 0 else 0
+        return {"snr_db": snr_db, "ms_per_capture": ms, "value": self.nfile / 1e6 / (ms / 1e3), "ms_viterbi_acs": inf["ms_viterbi_acs"],
+                "viterbi_repaired_chunks": inf["viterbi_repaired"], "acq_sequential_symbols": inf["acq_sequential_symbols"],
+                "acq_lost_at": inf["acq_lost_at"], "resyncs": max(0, inf["n_superframe_start"] - 1), "ts_packets": int(len(ts)),
+                "packets_checked": int(m), "packets_equal_to_source": good}
 
     def check(self):
-        ts = self.d_ts[: min(self.ts_bytes, 188 * 3000)].cpu().numpy()
-        ref = self.ts_src[1328 * 188: 1328 * 188 + len(ts)]
-        n = min(len(ts), len(ref))
-        return bool(n > 188 * 100 and np.array_equal(ts[:n], ref[:n]) and self.info["acq_lost_at"] == -1)
+        """the WHOLE transport stream of the last resident run against the transmitted one: the capture is one block of 4
+        superframes tiled, so TS packet j of the output is source packet first_packet + j modulo the packets of a block -
+        except the 11 packets behind each tile seam, where the outer deinterleaver mixes the end of a block with its
+        start (the transmitter's interleaver never saw that seam)"""
+        ts = self.d_ts[: self.ts_bytes].cpu().numpy().reshape(-1, 188)
+        if self.info["acq_lost_at"] != -1 and self.info["acq_lost_at"] >= self.info["first_symbol"]:
+            return False
+        per_block = 272 * self.SUPERFRAMES_BASE * self.P * self.m * self.k // (8 * self.n) // 204   # packets per tile (a multiple of 8)
+        src = self.ts_src[: per_block * 188].reshape(-1, 188)
+        if self.distinct:
+            src = self.ts_src[: len(self.ts_src) // 188 * 188].reshape(-1, 188)
+            n = min(len(ts), len(src) - self.first_packet)
+            return bool(n > 100 and np.array_equal(ts[:n], src[self.first_packet:self.first_packet + n]))
+        j = np.arange(len(ts))
+        idx = (self.first_packet + j) % per_block
+        eq = (ts == src[idx]).all(axis=1)
+        seam = idx >= per_block - 12          # the last 11 packets of a tile never left the transmitter's delay lines completely
+        bad = np.flatnonzero(~eq & ~seam)
+        self.check_stats = {"ts_packets": int(len(ts)), "packets_equal_to_source": int(eq.sum()), "seam_packets_excluded": int((seam & ~eq).sum()),
+                            "other_mismatches": int(len(bad)), "first_other_mismatch": (int(bad[0]), int(idx[bad[0]])) if len(bad) else None}
+        return bool(len(ts) > 100 and len(bad) == 0)
 
     def units_per_step(self):
         return self.nfile / 1e6  # Msamples of the 10 Msps capture
@@ -433,18 +490,6 @@ class RxWorkload:
     def alg_bytes(self):
         # Viterbi stage in the reference I/O format: n/(k*m) B in + 1/8 B out per decoded bit
         return self.viterbi_bits * (8.0 / (7 * 6) + 0.125)
-
-
-def ncu_traffic(workload, tiles):
-    """DRAM bytes per launch of the dominant kernel from the committed ncu capture (profiles/ncu_traffic.json), or None"""
-    try:
-        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
-            t = json.load(f).get(workload)
-    except (OSError, ValueError):
-        return None, None
-    if not t or (workload == "rx" and t.get("tiles") != tiles):
-        return None, None
-    return float(t["dram_bytes_read"] + t["dram_bytes_write"]), {k: t[k] for k in ("source", "alu_pipe_active_pct", "issue_active_pct", "dram_throughput_pct") if k in t}
 
 
 def cpu_worker(args):
@@ -598,6 +643,52 @@ def claim_stdout():
     return os.fdopen(keep, "w")
 
 
+def sass_facts():
+    """what the roofline record needs from the shipped library's SASS (cuobjdump, no GPU): the digest of the ACS kernel the
+    chain launches (a committed ncu traffic figure is only quoted for the build it was captured on) and its per-byte-time
+    instruction mix (tools/sass_loop_count.py's classification)"""
+    try:
+        sys.path.insert(0, os.path.join(ROOT, "tools"))
+        import sass_digest, sass_loop_count
+        fns = sass_loop_count.functions(sass_loop_count.LIB)
+        name = next(n for n in fns if re.search(r"vit_acs_kernelILb1ELi0ELi1ELi384", n))
+        ins = fns[name]
+        import hashlib
+        dig = hashlib.sha1("\n".join(t for _, t in ins).encode()).hexdigest()[:16]
+        # the byte-time loop = the largest loop that holds exactly 256 VIADDMNMX
+        best = None
+        for addr, text in ins:
+            m = re.search(r"BRA(?:\.U)?\s+(?:!?U?P\w+,\s*)?(0x[0-9a-f]+)", text)
+            if not m:
+                continue
+            tgt = int(m.group(1), 16)
+            if tgt >= addr:
+                continue
+            body = [sass_loop_count.mnemonic(t) for a_, t in ins if tgt <= a_ <= addr]
+            if body.count("VIADDMNMX") == 256 and (best is None or len(body) < len(best)):
+                best = body
+        if best is None:
+            return {"acs_sass_digest": dig}
+        return {"acs_sass_digest": dig, "instr_per_byte_time": len(best), "alu_pipe_instr_per_byte_time": sum(1 for b in best if b in sass_loop_count.ALU),
+                "fma_pipe_instr_per_byte_time": sum(1 for b in best if b in sass_loop_count.FMA), "viaddmnmx_per_byte_time": 256}
+    except Exception as e:
+        return {"error": repr(e)[:200]}
+
+
+def ncu_traffic(facts):
+    """DRAM bytes per launch of the ACS kernel from the committed ncu capture - quoted only when that capture was taken on the
+    kernel this library contains (same SASS digest); otherwise null"""
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+            t = json.load(f).get("rx")
+    except (OSError, ValueError):
+        return None, None
+    if not t or not facts or t.get("acs_sass_digest") != facts.get("acs_sass_digest"):
+        return None, {"note": "no ncu capture of this build's ACS kernel is committed (profiles/ncu_traffic.json digest %s, library %s)"
+                              % ((t or {}).get("acs_sass_digest"), (facts or {}).get("acs_sass_digest"))}
+    return float(t["dram_bytes_read"] + t["dram_bytes_write"]), {k: t[k] for k in ("source", "alu_pipe_active_pct", "issue_active_pct", "dram_throughput_pct", "acs_sass_digest") if k in t}
+
+
 def main():
     out = claim_stdout()
     ap = argparse.ArgumentParser()
@@ -607,7 +698,7 @@ def main():
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--workload", default="rx", choices=["rx", "viterbi"])
     ap.add_argument("--mbit", type=float, default=640.0, help="decoded Mbit per GPU per step (viterbi workload)")
-    ap.add_argument("--tiles", type=int, default=20, help="rx workload: capture = tiles x 4 superframes (1088 OFDM symbols each); 20 tiles = 50.3 M samples (SURVEY §8d config 2: >= 50 M)")
+    ap.add_argument("--tiles", type=int, default=0, help="rx workload: capture = tiles x base_superframes superframes (0 = the config's default: 21 760 OFDM symbols = 50.3 M samples in 2k, 5 440 symbols in 8k; SURVEY §8d config 2: >= 50 M samples)")
     ap.add_argument("--acs-ab-child", action="store_true", help=argparse.SUPPRESS)
     a = ap.parse_args()
     if a.acs_ab_child:
@@ -628,7 +719,9 @@ def main():
             cpu_rx_prepare()
             w = RxWorkload(a.tiles)
             w.nsym, w.nfile = 1904, len(_CPU_RX["cap"])
-            sample = "one capture of 1904 OFDM symbols (%.2f Msamples at 10 Msps) per process per step, one process per core (the reference keeps process-global Viterbi state)" % (len(_CPU_RX["cap"]) / 1e6)
+            sample = ("one capture of 1904 OFDM symbols (%.2f Msamples at 10 Msps, against %d symbols per capture in the GPU arm: throughput is per sample, so the "
+                      "shorter capture only bounds the run time) per process per step, one process per core (the reference keeps process-global Viterbi state); "
+                      "scipy/numpy stand in for the stock GNU Radio resampler and FFT, which gr-dvbt does not contain" % (len(_CPU_RX["cap"]) / 1e6, 21760))
         else:
             w = ViterbiWorkload(a.mbit)
             sample = "150 x 768-blocks (%.2f Mbit) of the same rate-7/8 m=6 stream per process per step, one process per core" % (150 * 96 * 7 * 8 / 1e6)
@@ -638,9 +731,11 @@ def main():
             if i >= a.warmup:
                 vals.append((agg, wall))
         v = float(np.mean([x[0] for x in vals]))
+        cfgd = w.describe()
+        cfgd["reference_arm"] = "%d processes, one per host core" % cores
         line = {"metric": metric, "value": v, "unit": unit, "impl": "reference", "n_gpus": a.gpus,
                 "steps": a.steps, "warmup": a.warmup, "ms_per_step": float(np.mean([x[1] for x in vals]) * 1e3), "higher_is_better": True,
-                "scaling": "weak", "vs_baseline": None, "dtype": "u8/f32", "data": "synthetic", "config": w.describe(),
+                "scaling": "weak", "vs_baseline": None, "dtype": "u8/f32", "data": "synthetic", "config": cfgd,
                 "cpu_baseline": {"value": v, "unit": unit.split(" (")[0], "cores": cores, "kind": kind, "sample": sample},
                 "e2e": {"value": v, "unit": unit.split(" (")[0], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
         print(json.dumps(line), file=out, flush=True)
@@ -656,9 +751,12 @@ def main():
         # the only collective on this path: the configuration
         cfg = broadcast_config([a.mbit, a.steps, a.warmup, a.tiles], "cuda")
         a.mbit, a.steps, a.warmup, a.tiles = float(cfg[0]), int(cfg[1]), int(cfg[2]), int(cfg[3])
+    facts_box = {}
+    facts_thread = None
+    if RANK == 0:
+        facts_thread = threading.Thread(target=lambda: facts_box.update(sass_facts()), daemon=True)
+        facts_thread.start()
 
-    w = RxWorkload(a.tiles) if rx else ViterbiWorkload(a.mbit)
-    w.setup_gpu(seed=seed_of_rank(RANK))
     lib = g.capi.lib()
 
     def barrier():
@@ -666,7 +764,7 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(stepfn, steps, warm):
+    def timed(stepfn, steps, warm, w):
         for i in range(warm):
             stepfn(i)
         barrier()
@@ -692,136 +790,364 @@ def main():
         barrier()
         return ms
 
-    sampler = ClockSampler(LOCAL_RANK)
-    l0 = lib.dvbt_b200_kernel_launches()
-    w.kernel_ms = []
-    sampler.start()
-    ms = timed(w.step_resident, a.steps, a.warmup)
-    clocks = sampler.stop()
-    if rx:
-        if os.environ.get("BENCH_VERBOSE"):
-            keys = [k for k in w.stage_ms[-1]]
-            sys.stderr.write("[bench rank %d] stages: %s | info: %s\n" % (RANK, " ".join("%s=%.3f" % (k[3:], float(np.mean([s_[k] for s_ in w.stage_ms[a.warmup:]]))) for k in keys),
-                                                                        json.dumps({k: v for k, v in w.info.items() if not k.startswith("ms_")})))
-        sys.stderr.write("[bench rank %d] resident: %.3f ms/step (max over ranks), sum of this rank's stage times %.3f ms\n"
-                         % (RANK, ms / a.steps, float(np.mean([sum(v for k, v in s_.items() if k not in ("ms_viterbi_acs", "ms_fft", "ms_equalise")) for s_ in w.stage_ms[a.warmup:]]))))
-    launches = (lib.dvbt_b200_kernel_launches() - l0) // (a.steps + a.warmup)   # kernels of this library per step
-    ok = w.check()
-    kms = float(np.mean(w.kernel_ms[a.warmup:]))
-    ms_pair = None
-    if rx:
-        # the headline step: NCONC captures in flight per GPU
-        w.resident_pair(a.warmup)
+    def h2d_roof(nbytes, reps=6):
+        """bare pinned cudaMemcpyAsync of one capture on every rank at once: what the box gives the e2e legs"""
+        h = torch.empty(nbytes, dtype=torch.uint8).pin_memory()
+        d = torch.empty(nbytes, dtype=torch.uint8, device="cuda")
+        for _ in range(2):
+            d.copy_(h, non_blocking=True)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            d.copy_(h, non_blocking=True)
+        torch.cuda.synchronize()
+        ms = max_over_ranks((time.perf_counter() - t0) * 1e3, "cuda")
+        barrier()
+        del h, d
+        return nbytes * reps * WORLD / (ms / 1e3) / 1e9
+
+    def rx_legs(w, steps, warm, sampler=None, full=True):
+        """resident (one capture at a time, then NCONC in flight) and host-buffer legs of one RX configuration"""
+        r = {}
+        w.kernel_ms, w.stage_ms = [], []
+        ms1 = timed(w.step_resident, steps, warm, w)
+        r["ok"] = w.check()
+        r["check"] = getattr(w, "check_stats", None)
+        r["kms"] = float(np.mean(w.kernel_ms[warm:]))
+        r["stage"] = {k: float(np.mean([s[k] for s in w.stage_ms[warm:]])) for k in w.stage_ms[-1]}
+        r["info"] = dict(w.info)
+        r["ms_single"] = ms1 / steps
+        w.resident_pair(warm)
         barrier()
         l1 = lib.dvbt_b200_kernel_launches()
-        sampler.start()
-        ms_pair = max_over_ranks(w.resident_pair(a.steps), "cuda")
-        clocks_pair = sampler.stop()
-        if clocks_pair.get("samples"):
-            clocks = clocks_pair
-        launches = (lib.dvbt_b200_kernel_launches() - l1) // a.steps
+        if sampler:
+            sampler.start()
+        r["ms_pair"] = max_over_ranks(w.resident_pair(steps), "cuda") / steps
+        if sampler:
+            r["clocks"] = sampler.stop()
+        r["launches"] = (lib.dvbt_b200_kernel_launches() - l1) // steps
         barrier()
         same = bool(all(b == w.ts_bytes for b in w.pair_bytes) and all(w.torch.equal(w.d_ts2[0][: w.ts_bytes], t[: w.ts_bytes]) for t in w.d_ts2[1:]))
-        if os.environ.get("BENCH_VERBOSE"):
-            sys.stderr.write("[bench rank %d] %d concurrent captures: %.3f ms per batch, outputs identical: %s\n" % (RANK, w.NCONC, ms_pair / a.steps, same))
-        ok = ok and same
+        r["ok"] = bool(r["ok"] and same)
+        if full:
+            w.e2e_pipelined(2)
+            barrier()
+            r["ms_e2e"] = max_over_ranks(w.e2e_pipelined(steps), "cuda") / steps
+            barrier()
+            n = w.step_e2e(0)
+            r["e2e_ok"] = bool(n == w.ts_bytes and np.array_equal(w.pin_ts[:n].numpy(), w.d_ts[:n].cpu().numpy()))
+        return r
+
+    def hbm_kernels(w, stage, info, peak):
+        """the HBM-bound kernels of the step against the measured copy peak: algorithmic bytes of SURVEY §8d per mode"""
+        N, cp, P = w.N, w.N // 32, w.P
+        nout = (w.nfile - 1) * 32 // 35 + 1
+        rows = [("resample_multi_kernel<2> (rational_resampler 64/70 + multiply_const)", "ms_resample", 8.0 * w.nfile + 8.0 * nout),
+                ("acq_fftd_kernel<%d> (derotation + CP removal + forward FFT)" % N, "ms_fft", info["acq_symbols"] * (8.0 * (N + cp) + 8.0 * N)),
+                ("demod_equalise_kernel (channel estimate + equalise + demap)", "ms_equalise", info["symbols_parsed"] * (8.0 * N + float(P)))]
+        return [{"kernel": nm, "bound": "hbm", "achieved": by / (stage[key] / 1e3) / 1e9, "peak": peak, "unit": "GB/s",
+                 "frac": by / (stage[key] / 1e3) / 1e9 / peak, "algorithmic_bytes": by, "avg_launch_ms": stage[key]}
+                for nm, key, by in rows if stage.get(key, 0) > 0]
+
+    peak, peak_src = load_peaks()
+    if not rx:
+        return main_viterbi(a, out, metric, unit, g, lib, timed, barrier, peak, peak_src, facts_thread, facts_box)
+
+    # ------------------------------------------------------------------ headline: configs[1]
+    w = RxWorkload(a.tiles)
+    w.setup_gpu(seed=seed_of_rank(RANK))
+    sampler = ClockSampler(LOCAL_RANK)
+    head = rx_legs(w, a.steps, a.warmup, sampler)
+    clocks = head.get("clocks") or {}
+    if os.environ.get("BENCH_VERBOSE"):
+        sys.stderr.write("[bench rank %d] stages: %s | info: %s | check %s\n" % (RANK, " ".join("%s=%.3f" % (k[3:], v) for k, v in head["stage"].items()),
+                                                                                 json.dumps({k: v for k, v in head["info"].items() if not k.startswith("ms_")}), head["check"]))
     if os.environ.get("BENCH_QUICK"):   # tuning runs: resident legs only, no JSON line
         if RANK == 0:
-            sys.stderr.write("[bench quick] one capture %.3f ms, %d concurrent %.3f ms per capture, acs %.3f ms, parity %s\n"
-                             % (ms / a.steps, w.NCONC if rx else 1, (ms_pair / a.steps / w.NCONC) if rx else 0.0, kms, ok))
+            sys.stderr.write("[bench quick] one capture %.3f ms, %d concurrent %.3f ms per capture, acs %.3f ms, e2e %.3f ms, parity %s %s\n"
+                             % (head["ms_single"], w.NCONC, head["ms_pair"] / w.NCONC, head["kms"], head["ms_e2e"], head["ok"], head["check"]))
         if WORLD > 1:
             dist.destroy_process_group()
         return 0
-    noisy = w.noisy_leg(27.0, max(3, a.steps // 4), 4242 + RANK) if rx and RANK == 0 else None
-    ms_e2e = timed(w.step_e2e, a.steps, a.warmup)
-    ms_e2e_pipe = None
-    if rx:
-        w.e2e_pipelined(2)
-        barrier()
-        ms_e2e_pipe = max_over_ranks(w.e2e_pipelined(a.steps), "cuda")
-        barrier()
+    roof_gbs = h2d_roof(w.nfile * 8)
+    units = w.units_per_step() * WORLD
+    value = units * w.NCONC / (head["ms_pair"] / 1e3)
+    e2e_value = units / (head["ms_e2e"] / 1e3)
+    stage, info = head["stage"], head["info"]
+    vbits = info["viterbi_bytes"] * 8
+    line = {"metric": metric, "value": value, "unit": unit, "n_gpus": WORLD, "steps": a.steps, "warmup": a.warmup,
+            "ms_per_step": head["ms_pair"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8/f32",
+            "config": w.describe(), "parity_check": bool(head["ok"] and head["e2e_ok"]), "parity_detail": head["check"], "gpu_launches": int(head["launches"]), "clocks": clocks,
+            "data": "synthetic (seeded random TS -> reference TX blocks -> IFFT/CP -> 35/32 resampler -> 10 Msps capture, no added noise; robustness.* adds AWGN)",
+            "chain_info": {k: v for k, v in info.items() if not k.startswith("ms_")},
+            "viterbi_mbit_per_s": vbits * w.NCONC * WORLD / (head["ms_pair"] / 1e3) / 1e6,
+            "realtime_factor": value / WORLD / 10.0, "stage_ms": stage,
+            "one_capture_at_a_time": {"ms_per_capture": head["ms_single"], "value": units / (head["ms_single"] / 1e3),
+                                      "note": "one capture at a time on one handle (one stream): the stage_ms / roofline kernel times are measured in this leg "
+                                              "with CUDA events; `value` is the same chain with %d captures in flight" % w.NCONC},
+            "e2e": {"value": e2e_value, "unit": "Msamples/s", "h2d_bytes_per_step": w.h2d, "d2h_bytes_per_step": w.d2h, "ms_per_step": head["ms_e2e"],
+                    "h2d_roof_gbs": roof_gbs, "h2d_achieved_gbs": w.h2d * WORLD / (head["ms_e2e"] / 1e3) / 1e9,
+                    "frac_of_h2d_roof": w.h2d * WORLD / (head["ms_e2e"] / 1e3) / 1e9 / roof_gbs,
+                    "api": "dvbt_b200_rx_run_file_host on pinned host buffers, two handles driven by two host threads (the copy of one capture overlaps "
+                           "the kernels of the other); every step copies its capture H2D and its TS D2H.  h2d_roof_gbs: a bare pinned cudaMemcpyAsync of "
+                           "the same capture on all %d ranks at once, measured in this run" % WORLD}}
+
+    # ------------------------------------------------------------------ the other RX configurations of BASELINE.json
+    per_config = {}
+    if not os.environ.get("BENCH_NO_CONFIGS"):
+        psteps = max(3, a.steps // 4)
+        for key in ("configs[0]", "configs[2]", "configs[3]"):
+            try:
+                wc = RxWorkload(0, key)
+                wc.setup_gpu(seed=seed_of_rank(RANK, base=101))
+                rc = rx_legs(wc, psteps, 3)
+                uc = wc.units_per_step() * WORLD
+                if RANK == 0:
+                    per_config[key] = {"workload": wc.describe()["workload"], "samples_per_capture": wc.nfile, "ofdm_symbols_per_capture": wc.nsym,
+                                       "captures_in_flight": wc.NCONC, "steps": psteps,
+                                       "value": uc * wc.NCONC / (rc["ms_pair"] / 1e3), "unit": "Msamples/s", "ms_per_capture_one_at_a_time": rc["ms_single"],
+                                       "e2e": {"value": uc / (rc["ms_e2e"] / 1e3), "ms_per_capture": rc["ms_e2e"], "h2d_bytes_per_step": wc.h2d, "d2h_bytes_per_step": wc.d2h},
+                                       "viterbi_mbit_per_s": rc["info"]["viterbi_bytes"] * 8 * wc.NCONC * WORLD / (rc["ms_pair"] / 1e3) / 1e6,
+                                       "parity_check": bool(rc["ok"] and rc["e2e_ok"]), "parity_detail": rc["check"], "first_ts_packet": wc.first_packet,
+                                       "stage_ms": rc["stage"], "roofline_hbm_kernels": hbm_kernels(wc, rc["stage"], rc["info"], peak),
+                                       "acs_kernel_ms": rc["kms"], "viterbi_repaired": rc["info"]["viterbi_repaired"]}
+                del wc
+                torch.cuda.empty_cache()
+            except Exception as e:   # a side configuration must not cost the run its line
+                if RANK == 0:
+                    per_config[key] = {"error": repr(e)[:300]}
+    line["per_config"] = per_config
+
+    # ------------------------------------------------------------------ config 5: Viterbi sweep (every rank decodes its own copy)
+    if not os.environ.get("BENCH_NO_VITERBI_SWEEP"):
+        line["viterbi_sweep"] = viterbi_sweep(g, torch, timed, barrier)
 
     if RANK == 0:
-        peak, peak_src = load_peaks()
-        units = w.units_per_step() * WORLD
-        value = units / (ms / a.steps / 1e3)
-        e2e = units / (ms_e2e / a.steps / 1e3)
-        single = {"ms_per_capture": ms / a.steps, "value": value}
-        if rx:
-            ms = ms_pair
-            value = units * w.NCONC / (ms / a.steps / 1e3)
-        achieved = w.alg_bytes / (kms / 1e3) / 1e9
-        line = {"metric": metric, "value": value, "unit": unit, "n_gpus": WORLD, "steps": a.steps, "warmup": a.warmup,
-                "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8/f32" if rx else "u8",
-                "config": w.describe(), "parity_check": ok, "gpu_launches": int(launches), "clocks": clocks}
-        if rx:
-            line["chain_info"] = {k: v for k, v in w.info.items() if not k.startswith("ms_")}
-        if rx:
-            vbits = w.viterbi_bits
-            stage = {k: float(np.mean([s[k] for s in w.stage_ms[a.warmup:]])) for k in w.stage_ms[-1]}
-            line["data"] = "synthetic (seeded random TS -> reference TX blocks -> IFFT/CP -> 35/32 resampler -> 10 Msps capture, no added noise)"
-            line["viterbi_mbit_per_s"] = vbits * w.NCONC * WORLD / (ms / a.steps / 1e3) / 1e6
-            line["realtime_factor"] = value / WORLD / 10.0
-            line["stage_ms"] = stage
-            single["note"] = ("one capture at a time on one handle (one stream): the stage_ms / roofline kernel times below are measured "
-                              "in this leg with CUDA events; `value` is the same chain with %d captures in flight" % w.NCONC)
-            line["one_capture_at_a_time"] = single
-            line["awgn"] = noisy   # informational: not the metric's configuration (BASELINE configs[1] is noise free)
-            if WORLD == 1 and not os.environ.get("BENCH_NO_SWEEP") and (os.cpu_count() or 1) >= 8:
-                # informational: more captures in flight than the headline's NCONC (single-GPU value per count)
-                nc = w.NCONC
-                line["in_flight_sweep"] = w.in_flight_sweep(
-                    [("%d_again" % nc, nc, {}), ("%d_acs_on_half_the_sms" % nc, nc, {"DVBT_B200_VIT_SM_DIV": "2"}),
-                     ("%d_acs_on_a_quarter_of_the_sms" % nc, nc, {"DVBT_B200_VIT_SM_DIV": "4"}), ("6", 6, {}), ("8", 8, {}),
-                     ("8_acs_on_a_quarter_of_the_sms", 8, {"DVBT_B200_VIT_SM_DIV": "4"})], max(3, a.steps // 4))
-            if WORLD == 1 and not os.environ.get("BENCH_NO_ACS_AB"):
-                # informational: the opt-in ACS schedule beside the default one on the Viterbi stage alone (child process)
-                line["acs_variants"] = acs_variants_leg(vbits / 1e6)
-            e2e_pipe = units / (ms_e2e_pipe / a.steps / 1e3)
-            line["e2e"] = {"value": e2e_pipe, "unit": "Msamples/s", "h2d_bytes_per_step": w.h2d, "d2h_bytes_per_step": w.d2h,
-                           "ms_per_step": ms_e2e_pipe / a.steps,
-                           "api": "dvbt_b200_rx_run_file_host on pinned host buffers, two handles driven by two host threads "
-                                  "(copy of one capture overlaps the kernels of the other); every step copies its capture H2D and its TS D2H",
-                           "single_handle": {"value": e2e, "ms_per_step": ms_e2e / a.steps}}
-            info_bits = vbits
-            cpu_rx_prepare()
-            cu, ct, cst, cok, cvit = cpu_rx_chain()
-            line["cpu_baseline"] = {"value": cu / ct, "unit": "Msamples/s", "cores": 1, "kind": "reference",
-                                    "sample": "one capture of 1904 OFDM symbols (%.2f Msamples at 10 Msps), one thread; the reference's own blocks "
-                                              "(oracle/_ref) with scipy/numpy standing in for the stock GNU Radio resampler and FFT" % cu,
-                                    "viterbi_mbit_per_s": cvit / cst["viterbi_decoder"], "ts_ok": cok,
-                                    "stage_share": {k: round(v / ct, 3) for k, v in cst.items()}}
-        else:
-            line["data"] = "synthetic (seeded random TS bytes, K=7 encoded, punctured 7/8, error free)"
-            line["e2e"] = {"value": e2e, "unit": "Mbit/s", "h2d_bytes_per_step": w.h2d, "d2h_bytes_per_step": w.d2h, "ms_per_step": ms_e2e / a.steps,
-                           "api": "dvbt_b200_viterbi_decode_host on pinned host buffers"}
-            info_bits = w.info_bits
-            cb_bits, cb_t, cb_kind = w.cpu_sample(0)
-            line["cpu_baseline"] = {"value": cb_bits / cb_t, "unit": "Mbit/s", "cores": 1, "kind": cb_kind,
-                                    "sample": "150 x 768-blocks (%.2f Mbit) of the same rate-7/8 m=6 stream, one thread" % cb_bits}
-        traffic, traffic_src = ncu_traffic(a.workload, a.tiles)
-        line["roofline"] = {"kernel": "vit_acs_kernel", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                            "traffic": traffic, "ncu": traffic_src, "algorithmic_bytes": w.alg_bytes,
-                            "peak_source": peak_src, "avg_launch_ms": kms,
-                            "note": "dominant kernel of the step; bound by the integer ALU pipe (64 add-compare-select per decoded bit as halfword "
-                                    "VIADDMNMX.U16x2 + IMAD; ncu: see the `ncu` object), so the HBM fraction is small by nature; DRAM traffic above the "
-                                    "algorithmic bytes is the survivor-row write-through to the global ring (deliberate: it frees shared memory "
-                                    "for 3x the resident warps); ACS rate = %.1f T state-updates/s" % (info_bits * 64 / (kms / 1e3) / 1e12)}
-        if rx:
-            # the HBM-bound kernels of the step against the same measured peak (algorithmic bytes of SURVEY §8d, CUDA-event
-            # times of the one-capture-at-a-time leg); the ACS kernel above is the dominant one but bound by the ALU pipe
-            inf = w.info
-            nout = (w.nfile - 1) * 32 // 35 + 1
-            others = [("resample_multi_kernel<2> (rational_resampler 64/70 + multiply_const)", "ms_resample", 8.0 * w.nfile + 8.0 * nout),
-                      ("acq_fftd_kernel<2048> (derotation + CP removal + forward FFT)", "ms_fft", inf["acq_symbols"] * (8.0 * (2048 + 64) + 8.0 * 2048)),
-                      ("demod_equalise_kernel (channel estimate + equalise + demap)", "ms_equalise", inf["symbols_parsed"] * (8.0 * 2048 + 1512.0))]
-            line["roofline_other"] = [{"kernel": nm, "bound": "hbm", "achieved": by / (stage[key] / 1e3) / 1e9, "peak": peak, "unit": "GB/s",
-                                       "frac": by / (stage[key] / 1e3) / 1e9 / peak, "algorithmic_bytes": by, "avg_launch_ms": stage[key]}
-                                      for nm, key, by in others if stage.get(key, 0) > 0]
+        # ---- robustness: AWGN on the headline capture, then a capture whose superframes are all different
+        rob = {}
+        if not os.environ.get("BENCH_NO_ROBUSTNESS"):
+            try:
+                rob["awgn_tiled_capture"] = [w.noisy_leg(snr, max(3, a.steps // 4), 4242) for snr in (27.0, 25.0, 20.0)]
+            except Exception as e:
+                rob["awgn_tiled_capture"] = {"error": repr(e)[:300]}
+        if WORLD == 1 and not os.environ.get("BENCH_NO_SWEEP") and (os.cpu_count() or 1) >= 8:
+            nc = w.NCONC
+            line["in_flight_sweep"] = w.in_flight_sweep([("%d_again" % nc, nc, {}), ("6", 6, {}), ("8", 8, {})], max(3, a.steps // 4))
+        if WORLD == 1 and os.environ.get("BENCH_ACS_AB"):
+            line["acs_variants"] = acs_variants_leg(vbits / 1e6)
+        cpu_rx_prepare()
+        cu, ct, cst, cok, cvit = cpu_rx_chain()
+        line["cpu_baseline"] = {"value": cu / ct, "unit": "Msamples/s", "cores": 1, "kind": "reference",
+                                "sample": "one capture of 1904 OFDM symbols (%.2f Msamples at 10 Msps), one thread; the reference's own blocks "
+                                          "(oracle/_ref) with scipy/numpy standing in for the stock GNU Radio resampler and FFT" % cu,
+                                "viterbi_mbit_per_s": cvit / cst["viterbi_decoder"], "ts_ok": cok,
+                                "stage_share": {k: round(v / ct, 3) for k, v in cst.items()}}
+        if facts_thread:
+            facts_thread.join(timeout=60)
+        facts = dict(facts_box)
+        kms = head["kms"]
+        alg_bytes = vbits * (w.n * 8.0 / (w.k * w.m * 8.0) + 0.125)   # n/(k m) B in + 1/8 B out per decoded bit (SURVEY §8d)
+        traffic, traffic_src = ncu_traffic(facts)
+        sm_hz = (clocks.get("sm_mhz") or 1965.0) * 1e6
+        dpx_peak = 62.0 * 148 * sm_hz                     # VIADDMNMX.U16x2 thread-ops/s: 62 per clock and SM measured (profiles/r01_dpx_rate.txt)
+        dpx_need = 256.0 * info["viterbi_bytes"]          # 64 states x 8 steps / 2 states per instruction, per decoded byte
+        line["roofline"] = {
+            "kernel": "vit_acs_kernel", "bound": "alu",
+            "achieved": dpx_need / (kms / 1e3) / 1e12, "peak": dpx_peak / 1e12, "unit": "T VIADDMNMX.U16x2 thread-ops/s (ALU pipe)",
+            "frac": dpx_need / (kms / 1e3) / dpx_peak,
+            "traffic": traffic, "ncu": traffic_src, "avg_launch_ms": kms, "sass": facts,
+            "alu_pipe": None if "alu_pipe_instr_per_byte_time" not in facts else {
+                "instr_per_decoded_byte": facts["alu_pipe_instr_per_byte_time"], "issue_slots_per_decoded_byte": facts["instr_per_byte_time"],
+                "frac_of_alu_pipe": facts["alu_pipe_instr_per_byte_time"] * info["viterbi_bytes"] / (kms / 1e3) / (64.0 * 148 * sm_hz),
+                "frac_of_issue_slots": facts["instr_per_byte_time"] * info["viterbi_bytes"] / 32.0 / (kms / 1e3) / (4.0 * 148 * sm_hz),
+                "note": "useful work only: the warm-up + traceback overlap of the chunks (17 % more byte times) is not counted"},
+            "hbm": {"achieved": alg_bytes / (kms / 1e3) / 1e9, "peak": peak, "unit": "GB/s", "frac": alg_bytes / (kms / 1e3) / 1e9 / peak,
+                    "algorithmic_bytes": alg_bytes, "peak_source": peak_src},
+            "note": "the dominant kernel of the step (add-compare-select of 64 states x 8 steps per decoded byte as 256 VIADDMNMX.U16x2 + 256 IMAD) is bound by "
+                    "the integer ALU pipe and the issue slots, not by HBM: `achieved`/`peak` count the irreducible DPX instructions against their measured "
+                    "issue rate, `alu_pipe` every ALU-pipe instruction and issue slot of the loop; `hbm` is the figure BASELINE.json's metric asks for "
+                    "(algorithmic bytes of the stage against the measured copy peak - small by nature).  ACS rate %.1f T state-updates/s"
+                    % (vbits * 64 / (kms / 1e3) / 1e12)}
+        line["roofline_other"] = hbm_kernels(w, stage, info, peak)
+        if not os.environ.get("BENCH_NO_ROBUSTNESS"):
+            try:
+                wd = RxWorkload(5, "configs[1]", distinct=True)   # 5 x 8 = 40 different superframes, 10 880 symbols
+                wd.setup_gpu(seed=77)
+                wd.step_resident(0); wd.step_resident(1)
+                t0 = time.perf_counter()
+                for i in range(3):
+                    wd.step_resident(i)
+                torch.cuda.synchronize()
+                msd = (time.perf_counter() - t0) * 1e3 / 3
+                rob["distinct_superframes"] = {"superframes": 40, "ofdm_symbols": wd.nsym, "samples": wd.nfile, "ms_per_capture": msd, "value": wd.nfile / 1e6 / (msd / 1e3),
+                                               "whole_ts_equal_to_source": wd.check(), "acq_sequential_symbols": wd.info["acq_sequential_symbols"],
+                                               "awgn": [wd.noisy_leg(snr, 3, 99) for snr in (25.0, 20.0)]}
+                del wd
+                torch.cuda.empty_cache()
+            except Exception as e:
+                rob["distinct_superframes"] = {"error": repr(e)[:300]}
+            line["robustness"] = rob
+        if not os.environ.get("BENCH_NO_DROPIN"):
+            try:
+                line["drop_in_blocks"] = drop_in_leg(g, w)
+            except Exception as e:
+                line["drop_in_blocks"] = {"error": repr(e)[:300]}
         print(json.dumps(line), file=out, flush=True)
     if WORLD > 1:
         dist.destroy_process_group()
     return 0
+
+
+def viterbi_sweep(g, torch, timed, barrier):
+    """config 5 of BASELINE.json: 10^8 received code bits per code rate, error free and with channel bit errors at
+    1e-3 / 1e-2, m = 6 bits per cell (plus m = 2, 4 at rate 1/2); decoded with the block's own I/O format through
+    dvbt_b200_viterbi_decode_dev.  Parity: the error-free stream decodes to its source; every stream equals the oracle
+    on its first 40 blocks and equals itself decoded with another chunking (the chunk boundaries are verified, not assumed)."""
+    from oracle import port as O
+    res = {"code_bits_per_case": int(1e8), "cases": []}
+    cases = [(r, 6) for r in range(5)] + [(0, 2), (0, 4)]
+    for rate, m in cases:
+        k, n = O.RATE_KN[rate]
+        nblocks = int(1e8 * k / n / 8 / (96 * k))
+        nbytes_out = nblocks * 96 * k
+        nbytes_in = nblocks * 768 * n // m
+        data = np.random.default_rng(1).integers(0, 256, nbytes_out, dtype=np.uint8)
+        clean = O.conv_encode(data, m, rate)
+        con = m // 2 - 1
+        dec = g.viterbi_decoder(con, g.NH, rate)
+        d_out = torch.zeros(nbytes_out, dtype=torch.uint8, device="cuda")
+        for ber in (0.0, 1e-3, 1e-2):
+            rxb = clean if ber == 0.0 else O.flip_bits(clean, m, ber, 7)
+            d_in = torch.from_numpy(rxb).cuda()
+            ms, kms, rep = [], [], 0
+            for i in range(2 + 5):
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                nout = dec.decode_dev(d_in.data_ptr(), nbytes_in, nbytes_in, 1, d_out.data_ptr(), nbytes_out)
+                dt = (time.perf_counter() - t0) * 1e3
+                st = dec.last_stats()
+                if i >= 2:
+                    ms.append(dt); kms.append(st["acs_kernel_ms"]); rep = st["repaired"]
+            got = d_out[:nout].cpu().numpy()
+            want = O.Viterbi(m, rate).work(rxb[: 40 * 768 * n // m])
+            ok = bool(len(want) > 0 and np.array_equal(got[: len(want)], want))
+            if ber == 0.0:
+                ok = ok and bool(np.array_equal(got, data[:nout]))
+            dec2 = g.viterbi_decoder(con, g.NH, rate)
+            dec2.set_tuning(chunk_bytes=1000 + 24 * 7, warmup_bytes=48, threads_per_block=128)
+            d_out2 = torch.zeros(nbytes_out, dtype=torch.uint8, device="cuda")
+            dec2.decode_dev(d_in.data_ptr(), nbytes_in, nbytes_in, 1, d_out2.data_ptr(), nbytes_out)
+            ok = ok and bool(torch.equal(d_out[:nout], d_out2[:nout]))
+            byte_err = int((got != data[:nout]).sum())
+            bits = nout * 8
+            res["cases"].append({"rate": "%d/%d" % (k, n), "m": m, "channel_ber": ber, "info_mbit": bits / 1e6,
+                                 "mbit_per_s": bits / 1e6 / (float(np.mean(ms)) / 1e3) * WORLD, "mbit_per_s_acs_kernel": bits / 1e6 / (float(np.mean(kms)) / 1e3),
+                                 "ms_per_decode": float(np.mean(ms)), "acs_kernel_ms": float(np.mean(kms)), "repaired_chunks": int(rep),
+                                 "decoded_byte_errors_vs_source": byte_err, "parity": ok,
+                                 "hbm_gbs_algorithmic": (nbytes_in + nout) / (float(np.mean(kms)) / 1e3) / 1e9})
+            del d_in
+        del dec, d_out
+        torch.cuda.empty_cache()
+    barrier()
+    return res if RANK == 0 else None
+
+
+def drop_in_leg(g, w):
+    """What a gr-dvbt flowgraph gets with the five hot blocks swapped for the shims: the block-level `*_work` entry points
+    (include/dvbt_b200.h) called the way the GNU Radio scheduler calls them - pageable host buffers, one call per work item
+    batch (sizes: the shims' set_min_noutput_items / output multiples), H2D + kernels + D2H + stream sync inside every call.
+    Each block is timed on its own over the same 2176-symbol stretch (GNU Radio runs one thread per block, so the chain
+    runs at the pace of the slowest block); inputs of the later blocks come from the fused chain's stage taps."""
+    import ctypes as C
+    from gr_dvbt_b200 import capi
+    N, P, cp = w.N, w.P, w.N // 32
+    nsym = 2176
+    total = N + cp
+    # baseband for acquisition: the front end (a stock GNU Radio block in the flowgraph) run once on the GPU
+    ncap = (nsym + 8) * total * 35 // 32 + 4000
+    cap = w.pin_in[:ncap].numpy().copy()                      # pageable
+    bb = np.zeros(len(cap), np.complex64)
+    nbb = C.c_size_t(0)
+    capi.check(capi.lib().dvbt_b200_resample_host(cap.ctypes.data, len(cap), w.GAIN, bb.ctypes.data, len(bb), C.byref(nbb), -1))
+    bb = bb[: nbb.value].copy()
+    res = {"ofdm_symbols": nsym, "samples_10msps_equivalent": nsym * total * 35 / 32.0, "blocks": {}}
+    samples = res["samples_10msps_equivalent"]
+
+    def record(name, seconds, calls, items):
+        res["blocks"][name] = {"seconds": seconds, "calls": calls, "items_per_call": items, "msamples_per_s": samples / 1e6 / seconds, "us_per_call": seconds / max(calls, 1) * 1e6}
+
+    # ofdm_sym_acquisition (+ FFT folded in, as the shim does with apply_fft): 64 symbols per call (shim: set_min_noutput_items(64))
+    acq = g.ofdm_sym_acquisition(1, N, w.N * 0 + (1705 if N == 2048 else 6817), cp, 30.0)
+    pos, syms, calls, t = 0, [], 0, 0.0
+    while len(syms) < nsym // 64 and pos + 66 * total < len(bb):
+        chunk = bb[pos: pos + 2 * N + cp + 32 + 63 * total]
+        t0 = time.perf_counter()
+        o, cons, _tags = acq.general_work(chunk, out_capacity=64, apply_fft=True)
+        t += time.perf_counter() - t0
+        pos += cons; calls += 1
+        syms.append(o)
+        if cons == 0:
+            break
+    X = np.concatenate(syms)
+    record("ofdm_sym_acquisition+fft", t, calls, 64)
+    # demod_reference_signals: 64 symbols per call (65 visible)
+    dem = g.demod_reference_signals(8, N, P, w.CON, g.NH, w.CR, w.CR, g.G1_32, w.TM, 0, 0)
+    t, calls, ys, first = 0.0, 0, [], True
+    for i in range(0, len(X) - 65, 64):
+        t0 = time.perf_counter()
+        y, cons, tags = dem.general_work(X[i: i + 65], tags=[(0, "sync_start", 1)] if first else [])
+        t += time.perf_counter() - t0
+        first = False; calls += 1
+        ys.append(y)
+    record("demod_reference_signals", t, calls, 64)
+    Y = np.concatenate(ys) if ys else np.zeros((0, P), np.complex64)
+    if len(Y) < 64:
+        Y = np.tile((np.random.default_rng(3).normal(size=(64, P)) + 1j * np.random.default_rng(4).normal(size=(64, P))).astype(np.complex64), (nsym // 64, 1))
+    # dvbt_demap: 64 items per call
+    dm = g.dvbt_demap(P, w.CON, g.NH, w.TM, 1.0)
+    reps = max(1, nsym // max(len(Y), 1))
+    t, calls = 0.0, 0
+    for _ in range(reps):
+        for i in range(0, len(Y) - 63, 64):
+            t0 = time.perf_counter()
+            dm.general_work(64, Y[i: i + 64])
+            t += time.perf_counter() - t0
+            calls += 1
+    record("dvbt_demap", t * (nsym / (calls * 64.0)), calls, 64)
+    # viterbi_decoder: 64 x 768-blocks per call, input = the bit-deinterleaved bytes of the fused chain's last run
+    w.rx.run_file_dev(w.d_in.data_ptr(), w.nfile, w.GAIN, w.d_ts.data_ptr(), w.ts_cap)
+    vin = w.rx.stage("bitdeint")
+    vit = g.viterbi_decoder(w.CON, g.NH, w.CR)
+    nsymb, nout = 768 * w.n // w.m, 96 * w.k
+    need = nsym * P
+    t, calls, pos = 0.0, 0, 0
+    while pos + 64 * nsymb <= min(need, len(vin)):
+        t0 = time.perf_counter()
+        vit.general_work(64 * nout, vin[pos: pos + 64 * nsymb], tags=[(0, "superframe_start", 1)] if pos == 0 else [])
+        t += time.perf_counter() - t0
+        pos += 64 * nsymb; calls += 1
+    record("viterbi_decoder", t * (need / max(pos, 1)), calls, "64 x 768-blocks")
+    # reed_solomon_dec: 64 items of 8 packets per call on the deinterleaved Viterbi output
+    vo = w.rx.stage("viterbi")
+    npk = min(len(vo) // 204, nsym * P * w.m * w.k // (8 * w.n) // 204) // 8 * 8
+    tt = np.arange(npk * 204)
+    src = tt - 204 * (11 - tt % 12)
+    pk = np.where(src >= 0, vo[np.clip(src, 0, None)], 0).astype(np.uint8)
+    rs = g.reed_solomon_dec(2, 8, 0x11D, 255, 239, 8, 51, 8)
+    t, calls = 0.0, 0
+    for i in range(0, npk // 8 - 63, 64):
+        t0 = time.perf_counter()
+        rs.general_work(64, pk[i * 1632: (i + 64) * 1632])
+        t += time.perf_counter() - t0
+        calls += 1
+    record("reed_solomon_dec", t * (npk / 8.0 / max(calls * 64, 1)), calls, 64)
+    slow = min(res["blocks"].values(), key=lambda b: b["msamples_per_s"])
+    res["pipelined_msamples_per_s"] = slow["msamples_per_s"]
+    res["serial_msamples_per_s"] = samples / 1e6 / sum(b["seconds"] for b in res["blocks"].values())
+    res["realtime_factor_pipelined"] = slow["msamples_per_s"] / 10.0
+    res["note"] = ("block-level C-ABI calls on pageable host buffers, every call synchronous (H2D, kernels, D2H, stream sync): one thread per block "
+                   "as in GNU Radio => the flowgraph runs at the slowest block's pace (pipelined); serial = one thread calling all five")
+    return res
 
 
 if __name__ == "__main__":

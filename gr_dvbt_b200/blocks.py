@@ -244,6 +244,24 @@ class rx_chain(_Handle):
         check(lib().dvbt_b200_rx_run_file_host(self._h, x.ctypes.data, len(x), gain, ts.ctypes.data, cap, C.byref(n)))
         return ts[: n.value].copy()
 
+    LEVELS = dict(file=0, baseband=1, freq=2)
+
+    def stream_reset(self):
+        check(lib().dvbt_b200_rx_stream_reset(self._h))
+
+    def stream_push(self, level, data, gain=1.0, end=False):
+        """one piece of a stream (include/dvbt_b200.h: dvbt_b200_rx_stream_push_host).  level: 'file' (10 Msps capture
+        samples), 'baseband' (OFDM-rate samples) or 'freq' ((nsym, N) post-FFT symbols).  Returns the TS bytes that
+        became available."""
+        x = np.ascontiguousarray(data, np.complex64).reshape(-1)
+        lv = self.LEVELS[level]
+        count = len(x) // self.N if lv == 2 else len(x)
+        cap = len(x) + 2 * 16 * 204 * 64 + 4096
+        ts = np.zeros(cap, np.uint8)
+        n = C.c_size_t(0)
+        check(lib().dvbt_b200_rx_stream_push_host(self._h, lv, x.ctypes.data, count, gain, int(end), ts.ctypes.data, cap, C.byref(n)))
+        return ts[: n.value].copy()
+
     def run_file_dev(self, d_x, nsamples, gain, d_ts, ts_capacity):
         n = C.c_size_t(0)
         check(lib().dvbt_b200_rx_run_file_dev(self._h, _addr(d_x), nsamples, gain, _addr(d_ts), ts_capacity, C.byref(n)))

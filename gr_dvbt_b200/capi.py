@@ -46,7 +46,8 @@ class RxParams(C.Structure):
 class RxInfo(C.Structure):
     _fields_ = [(n, C.c_longlong) for n in ("symbols_parsed", "first_symbol", "symbols_out", "viterbi_bytes", "viterbi_repaired",
                                              "rs_packets", "first_packet", "ts_bytes", "acq_symbols", "acq_cp_start", "acq_lost_at", "acq_run_symbols", "acq_single_symbols", "acq_sequential_symbols")] + \
-               [(n, C.c_float) for n in ("ms_resample", "ms_acq_fft", "ms_demod", "ms_inner", "ms_viterbi", "ms_viterbi_acs", "ms_rs", "ms_descramble", "ms_fft", "ms_equalise")]
+               [(n, C.c_float) for n in ("ms_resample", "ms_acq_fft", "ms_demod", "ms_inner", "ms_viterbi", "ms_viterbi_acs", "ms_rs", "ms_descramble", "ms_fft", "ms_equalise")] + \
+               [(n, C.c_longlong) for n in ("n_sync_start", "n_superframe_start", "n_viterbi_runs", "ts_total")]
 
 
 class AcqParams(C.Structure):
@@ -119,6 +120,9 @@ def declare(L):
         L.dvbt_b200_rx_run_baseband_dev.argtypes = [vp, vp, C.c_size_t, vp, C.c_size_t, C.POINTER(C.c_size_t)]
         L.dvbt_b200_rx_run_file_host.argtypes = [vp, vp, C.c_size_t, C.c_float, vp, C.c_size_t, C.POINTER(C.c_size_t)]
         L.dvbt_b200_rx_run_file_dev.argtypes = [vp, vp, C.c_size_t, C.c_float, vp, C.c_size_t, C.POINTER(C.c_size_t)]
+        L.dvbt_b200_rx_stream_reset.argtypes = [vp]
+        for name in ("dvbt_b200_rx_stream_push_host", "dvbt_b200_rx_stream_push_dev"):
+            getattr(L, name).argtypes = [vp, C.c_int, vp, C.c_size_t, C.c_float, C.c_int, vp, C.c_size_t, C.POINTER(C.c_size_t)]
         L.dvbt_b200_resampler_taps.argtypes = [vp, C.c_int]
         L.dvbt_b200_resample_host.argtypes = [vp, C.c_size_t, C.c_float, vp, C.c_size_t, C.POINTER(C.c_size_t), C.c_int]
     return L

@@ -9,21 +9,29 @@
 // and the stock fft_vxx(N, forward, rectangular, shift=True) that follows it in the flowgraphs.
 //
 // The reference handles one symbol per call and re-sums cp products for each of the 16
-// candidates.  Here a whole capture is processed at once:
+// candidates.  Here a whole capture (or one piece of a stream) is processed at once:
+//   acq_init_lambda_kernel / acq_init_peak_kernel / acq_probe_kernel
+//                       the one-off search over N candidates (same lambda values, same detector)
+//                       and a 4-symbol look-ahead that sizes the first tracking batch;
 //   acq_lambda_kernel   one thread per (symbol, candidate): gamma, phi, lambda with the
 //                       reference's summation order (so lambda is bit-identical: it depends only
 //                       on the absolute sample position);
-//   acq_initial_kernel  the one-off search over N candidates (sequential peak detector);
-//   acq_track_kernel    one thread per symbol runs the 16-step peak detector.  The detector's
-//                       running average d_avg is the only state that crosses symbols; it is
-//                       speculated (pass 1: from zero, pass 2: from the previous symbol's pass-1
-//                       value) and acq_chain_kernel verifies the chain bit-for-bit, falling back to
-//                       the sequential detector from the first symbol where speculation, the peak
-//                       position or a missed peak breaks the assumption;
-//   acq_chain_kernel    also carries cp_start and the phase-increment schedule (:285-312) and
-//                       produces per-symbol (first sample, start phase, increments);
-//   acq_derot_kernel    out[j] = expj(phase_j) * in[cp_start-N+1+j], times (-1)^j so that the
-//                       unshifted cuFFT output equals fft_vxx's shifted output.
+//   acq_pass1_kernel / acq_pass2_kernel
+//                       the detector's running average d_avg is the only state that crosses symbols
+//                       besides cp_start; it is speculated (pass 1: from zero per window offset,
+//                       pass 2: the detector for every (offset, previous offset) state from the pass-1
+//                       value) and every speculated input is verified bit-for-bit;
+//   acq_chunkmap_kernel / acq_compose_kernel / acq_walk_kernel
+//                       tracking = composition of 187-state maps over 32-symbol chunks; where the
+//                       speculation stops, the reference's sequential detector continues on the spot;
+//   acq_post_kernel / acq_finish_kernel / acq_desc_kernel
+//                       peak, epsilon and the phase-increment schedule (:285-312) as scans, giving
+//                       per-symbol (first sample, start phase, increments);
+//   acq_fftd_kernel     out = FFT((-1)^j expj(phase_j) in[cp_start-N+1+j]): derotation, CP removal,
+//                       fft_vxx's shift and the forward FFT in one kernel (acq_derot_kernel + cuFFT
+//                       for other sizes or time-domain output).
+// A missed peak restarts acquisition half a symbol later (:545-558); every acquisition attempt sends
+// sync_start at the current output position (:507) - acq_run records those offsets for the caller.
 // Difference to the reference, by construction: the derotation phase is evaluated in closed
 // form in double instead of N+cp sequential float additions per symbol (:285-309), so the
 // output samples agree to ~1e-6 relative, not bit-for-bit; decisions (timing, peaks) are exact.
@@ -1127,6 +1135,7 @@ struct dvbt_b200_acq {
   static constexpr int kFftEv = 8;          // CUDA events around the derotation+FFT kernel of the first batches of a run
   cudaEvent_t ev_fft[2 * kFftEv] = {nullptr};
   int n_fft_ev = 0;
+  bool pending_sync = false;                // a sync_start whose item the next acq_work call produces
 };
 
 namespace dvbt {
@@ -1134,7 +1143,7 @@ namespace dvbt {
 // Runs acquisition + derotation (+ optional FFT) over device samples x[0..n).  Output symbols go to
 // d_out (N complex each).  Returns counts through the host copy of the state.
 int acq_run(dvbt_b200_acq *h, const float2 *x, long long n, float2 *d_out, long long out_capacity_syms, int do_fft,
-            AcqState *host_state_out) {
+            AcqState *host_state_out, std::vector<long long> *sync_at = nullptr) {
   const AcqParams &p = h->kp;
   const int total = p.N + p.cp;
   cudaStream_t st = h->stream;
@@ -1175,7 +1184,8 @@ int acq_run(dvbt_b200_acq *h, const float2 *x, long long n, float2 *d_out, long 
       DVBT_CUDA_TRY(cudaMemcpyAsync(hs, h->d_state.p, sizeof(AcqState), cudaMemcpyDeviceToHost, st));
       DVBT_CUDA_TRY(cudaStreamSynchronize(st));
       probe_lost1 = hs->probe_lost1;
-      sync_tags++;  // send_sync_start() on every attempt (:507)
+      sync_tags++;  // send_sync_start() on every attempt (:507), tagged at nitems_written = symbols produced so far
+      if (sync_at && (sync_at->empty() || sync_at->back() != produced)) sync_at->push_back(produced);
       if (!hs->initial) {
         // nothing found: the reference consumes d_to_consume = N+cp (set by ml_sync's miss branch)
         pos += total;
@@ -1374,9 +1384,9 @@ int acq_reset(dvbt_b200_acq *h) {
 }
 
 int acq_run_simple(dvbt_b200_acq *h, const float2 *x, long long n, float2 *d_out, long long out_capacity_syms, int do_fft,
-                   AcqResult *res) {
+                   AcqResult *res, std::vector<long long> *sync_at) {
   AcqState hs;
-  int rc = acq_run(h, x, n, d_out, out_capacity_syms, do_fft, &hs);
+  int rc = acq_run(h, x, n, d_out, out_capacity_syms, do_fft, &hs, sync_at);
   if (rc) return rc;
   if (res) { res->n_run = hs.n_run; res->n_single = hs.n_single; res->n_seq = hs.n_seq; res->consumed = hs.consumed; res->n_out = hs.n_out; res->lost_at = hs.lost_at; res->fallback = hs.fallback; res->cp_start = hs.cp_start; }
   return 0;
@@ -1437,21 +1447,23 @@ int dvbt_b200_acq_work(dvbt_b200_acq *h, const void *in, size_t n_in_items, void
   if ((rc = h->d_x.reserve(n_in_items * 8)) || (rc = h->d_out.reserve(out_capacity_items * N * 8))) return rc;
   DVBT_CUDA_TRY(cudaMemcpyAsync(h->d_x.p, in, n_in_items * 8, cudaMemcpyHostToDevice, h->stream));
   AcqState hs;
-  bool was_initial = false;
-  {
-    DVBT_CUDA_TRY(cudaMemcpyAsync(&hs, h->d_state.p, sizeof hs, cudaMemcpyDeviceToHost, h->stream));
-    DVBT_CUDA_TRY(cudaStreamSynchronize(h->stream));
-    was_initial = hs.initial != 0;
-  }
-  rc = dvbt::acq_run(h, h->d_x.as<float2>(), (long long)n_in_items, h->d_out.as<float2>(), (long long)out_capacity_items, apply_fft, &hs);
+  std::vector<long long> sync_at;
+  rc = dvbt::acq_run(h, h->d_x.as<float2>(), (long long)n_in_items, h->d_out.as<float2>(), (long long)out_capacity_items, apply_fft, &hs, &sync_at);
   if (rc) return rc;
   if (hs.n_out > 0) DVBT_CUDA_TRY(cudaMemcpyAsync(out, h->d_out.p, (size_t)hs.n_out * N * 8, cudaMemcpyDeviceToHost, h->stream));
   DVBT_CUDA_TRY(cudaStreamSynchronize(h->stream));
   *consumed = (size_t)hs.consumed;
   *produced = (size_t)hs.n_out;
-  if (tags_out && n_tags_out && tags_out_capacity > 0 && !was_initial && hs.n_sync_tags > 0) {
-    tags_out[0] = dvbt_b200_tag{0, DVBT_TAG_SYNC_START, 1};  // :353-360
-    *n_tags_out = 1;
+  // send_sync_start() (:353-360) on every acquisition attempt (:507), at the output position it happened at: the first
+  // item of the call for a fresh or still unlocked receiver, later items when the lock was lost and regained inside the
+  // call.  A tag beyond the last produced item belongs to the next call's first item (the attempt is repeated there).
+  if (h->pending_sync && (sync_at.empty() || sync_at.front() != 0)) sync_at.insert(sync_at.begin(), 0);
+  h->pending_sync = !sync_at.empty() && sync_at.back() >= (long long)hs.n_out;
+  if (tags_out && n_tags_out) {
+    size_t nt = 0;
+    for (long long off : sync_at)
+      if (off < (long long)hs.n_out && nt < tags_out_capacity) tags_out[nt++] = dvbt_b200_tag{(uint64_t)off, DVBT_TAG_SYNC_START, 1};
+    *n_tags_out = nt;
   }
   return 0;
 }

@@ -356,11 +356,16 @@ __global__ void __launch_bounds__(256) demod_equalise_kernel(ModeDev md, const _
   }
 }
 
-// TPS DBPSK majority vote against the previous symbol (:929-948)
+// TPS DBPSK majority vote against the previous symbol (:929-948).  The low half of vote[s] is the vote (|v| <= 68);
+// bit 16 marks a symbol that carries a sync_start tag (demod_reference_signals_impl.cc:44-52), so that the scan
+// below finds the (rare) tags in the data it stages anyway.
 __global__ void demod_vote_kernel(int ntps, int nparse, const float2 *__restrict__ tpsval,
-                                  const DemodState *__restrict__ state, int *__restrict__ vote) {
+                                  const DemodState *__restrict__ state, int *__restrict__ vote,
+                                  int sync_start_at0, const int *__restrict__ sync_at, int nsync) {
   int s = blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= nparse) return;
+  int flag = (sync_start_at0 && s == 0) ? 1 : 0;
+  for (int q = 0; q < nsync; q++) flag |= (sync_at[q] == s) ? 1 : 0;
   const float2 *cur = tpsval + (long long)s * ntps;
   int v = 0;
   for (int k = 0; k < ntps; k++) {
@@ -368,7 +373,7 @@ __global__ void demod_vote_kernel(int ntps, int nparse, const float2 *__restrict
     float2 ph = cmul_conj(cur[k], prev);
     v += (ph.x >= 0.0f) ? 1 : -1;
   }
-  vote[s] = v;
+  vote[s] = (v & 0xffff) | (flag << 16);
 }
 
 // BCH(127,113) shortened to (67,53): verify_bch_code (:384-425), on the bit-packed FIFO
@@ -413,7 +418,9 @@ constexpr int kScanWarps = 32;
 //   * Warp 0 then walks the per-frame verdicts (superframe gating is the only state), all threads write the
 //     output descriptors of the accepted frames, and the first rejected frame is handed back to the
 //     per-symbol machine, exactly as the one-frame-at-a-time loop did.
-__global__ void __launch_bounds__(32 * kScanWarps) demod_scan_kernel(int ntps, int nparse, int fi_start, int sync_start_at0,
+//   * A sync_start tag (bit 16 of vote[], see demod_vote_kernel) re-arms the wait for a superframe start on the symbol
+//     that carries it (demod_reference_signals_impl.cc:112-116); a frame that contains one is never taken whole.
+__global__ void __launch_bounds__(32 * kScanWarps) demod_scan_kernel(int ntps, int nparse, int fi_start, int src_base,
                                                                      const int *__restrict__ mod_in, const int *__restrict__ vote,
                                                                      const float2 *__restrict__ tpsval, DemodState *st,
                                                                      int *__restrict__ out_symidx, int *__restrict__ out_src) {
@@ -422,7 +429,8 @@ __global__ void __launch_bounds__(32 * kScanWarps) demod_scan_kernel(int ntps, i
   const unsigned long long kEven = (1ull << 3) | (1ull << 4) | (1ull << 6) | (1ull << 8) | (1ull << 9) | (1ull << 10) | (1ull << 11) |
                                    (1ull << 13) | (1ull << 14) | (1ull << 15);
   const unsigned long long kMask = 0xFFFEull;
-  __shared__ signed char s_mod[kScanChunk], s_vote[kScanChunk];   // phase in -1..3, |vote| <= 68
+  __shared__ signed char s_mod[kScanChunk];   // phase in -1..3
+  __shared__ short s_vote[kScanChunk];        // |vote| <= 68 in the low byte (sign extended), bit 8: sync_start on this symbol
   __shared__ unsigned char s_ok[kScanFrames], s_fi[kScanFrames];
   __shared__ int s_lock, s_prev_mod, s_nframes, s_emit_from, s_nf, s_out_base;
   const unsigned r_lo = tps_bch_unit_remainder(lane), r_hi = lane + 32 < 53 ? tps_bch_unit_remainder(lane + 32) : 0u;
@@ -431,7 +439,12 @@ __global__ void __launch_bounds__(32 * kScanWarps) demod_scan_kernel(int ntps, i
   int symbol_index = 0, known = 0, frame_index = 0, prev_mod = 0, cur_mod = 0, d_init = 0;
   unsigned long long lo = 0;
   unsigned hi = 0;
-  int first_out = -1, n_out = 0, sf_tag_at = -1;
+  int first_out = -1, n_out = 0, sf_tag_at = -1, n_sf = 0;
+  auto record_sf = [&](int at) {   // warp 0, all lanes the same value
+    if (sf_tag_at < 0) sf_tag_at = at;
+    if (n_sf < kMaxSfTags && lane == 0) st->sf_at[n_sf] = at;
+    n_sf++;
+  };
   int cbase = -(1 << 30);
   int s = 0;
   bool skip_fast = false;
@@ -443,7 +456,6 @@ __global__ void __launch_bounds__(32 * kScanWarps) demod_scan_kernel(int ntps, i
     unsigned w0 = __ballot_sync(0xffffffffu, b0 != 0), w1 = __ballot_sync(0xffffffffu, b1 != 0), w2 = __ballot_sync(0xffffffffu, b2 != 0);
     lo = ((unsigned long long)w1 << 32) | w0;
     hi = w2 & 0xFu;
-    if (sync_start_at0) d_init = 0;  // :115-116
   }
   auto load_chunk = [&](int s0) {   // warp 0 only
     __syncwarp();
@@ -458,7 +470,7 @@ __global__ void __launch_bounds__(32 * kScanWarps) demod_scan_kernel(int ntps, i
 #pragma unroll
       for (int u = 0; u < 8; u++) {
         s_mod[i0 + lane + 32 * u] = (signed char)m[u];
-        s_vote[i0 + lane + 32 * u] = (signed char)v[u];
+        s_vote[i0 + lane + 32 * u] = (short)(((int)(signed char)(v[u] & 0xff) & 0xff) | (((v[u] >> 16) & 1) << 8));
       }
     }
     cbase = s0;
@@ -474,7 +486,9 @@ __global__ void __launch_bounds__(32 * kScanWarps) demod_scan_kernel(int ntps, i
         // ---- one symbol (parse_input :1188-1248 bookkeeping)
         if (s < cbase || s >= cbase + kScanChunk) load_chunk(s);
         int m_in = s_mod[s - cbase];
-        int v_in = s_vote[s - cbase];
+        int v_pk = s_vote[s - cbase];
+        int v_in = (int)(signed char)(v_pk & 0xff);
+        if (v_pk & 0x100) d_init = 0;           // sync_start on this item (demod_reference_signals_impl.cc:115-116)
         int mod = m_in >= 0 ? m_in : cur_mod;
         cur_mod = mod;
         int diff = (mod - prev_mod + 4) & 3;  // :684-688
@@ -507,14 +521,14 @@ __global__ void __launch_bounds__(32 * kScanWarps) demod_scan_kernel(int ntps, i
         if (d_init == 0) {
           if (sym_out == 0 && (frame_out & 3) == fi_start) {
             d_init = 1;
-            sf_tag_at = n_out;
+            record_sf(n_out);
           } else {
             emit = false;
           }
         }
         if (emit) {
           if (first_out < 0) first_out = s;
-          if (lane == 0) { out_symidx[n_out] = sym_out; out_src[n_out] = s; }
+          if (lane == 0) { out_symidx[n_out] = sym_out; out_src[n_out] = src_base + s; }
           n_out++;
         }
         s++;
@@ -542,7 +556,8 @@ __global__ void __launch_bounds__(32 * kScanWarps) demod_scan_kernel(int ntps, i
         int cm = valid ? mod_in[fs + i] : 0;
         int cv = valid ? vote[fs + i] : 0;
         if (valid && cm != ((pm + 1 + i) & 3)) good = false;
-        w[q] = __ballot_sync(0xffffffffu, valid && cv < 0);
+        if (valid && (cv & (1 << 16))) good = false;        // a sync_start inside the frame: symbol by symbol
+        w[q] = __ballot_sync(0xffffffffu, valid && (cv & 0x8000));
       }
       good = __all_sync(0xffffffffu, good);
       unsigned long long flo = (((unsigned long long)w[1] << 32) | w[0]) & ~1ull;  // entry 0: index 0 pushes 0 (:964-971)
@@ -568,7 +583,7 @@ __global__ void __launch_bounds__(32 * kScanWarps) demod_scan_kernel(int ntps, i
       while (f < nframes && s_ok[f]) {
         bool emit = true;
         if (d_init == 0) {
-          if ((frame_index & 3) == fi_start) { d_init = 1; sf_tag_at = n_out; }
+          if ((frame_index & 3) == fi_start) { d_init = 1; record_sf(n_out); }
           else emit = false;
         }
         if (emit) {
@@ -593,7 +608,7 @@ __global__ void __launch_bounds__(32 * kScanWarps) demod_scan_kernel(int ntps, i
         const int count = (nf - ef) * 68;
         for (int i = threadIdx.x; i < count; i += blockDim.x) {
           out_symidx[ob + i] = i % 68;
-          out_src[ob + i] = lock + 68 * ef + i;
+          out_src[ob + i] = src_base + lock + 68 * ef + i;
         }
       }
     }
@@ -605,7 +620,7 @@ __global__ void __launch_bounds__(32 * kScanWarps) demod_scan_kernel(int ntps, i
       st->mod = cur_mod; st->d_init = d_init;
       for (int i = 0; i < 64; i++) st->fifo[i] = (unsigned char)((lo >> i) & 1ull);
       for (int i = 64; i < 68; i++) st->fifo[i] = (unsigned char)((hi >> (i - 64)) & 1u);
-      st->first_out = first_out; st->n_out = n_out; st->sf_tag_at = sf_tag_at;
+      st->first_out = first_out; st->n_out = n_out; st->sf_tag_at = sf_tag_at; st->n_sf = n_sf;
     }
     if (nparse > 0)
       for (int k = lane; k < ntps; k += 32) st->prev_tps[k] = tpsval[(long long)(nparse - 1) * ntps + k];
@@ -613,7 +628,7 @@ __global__ void __launch_bounds__(32 * kScanWarps) demod_scan_kernel(int ntps, i
 }
 
 int demod_run(const ModeDev &md, const DemapTable *demap, const float2 *X, int nparse, DemodBuffers b, DemodState *d_state,
-              int fi_start, int sync_start_at0, float2 *Y, uint8_t *dm, cudaStream_t st) {
+              int fi_start, int sync_start_at0, float2 *Y, uint8_t *dm, cudaStream_t st, const int *sync_at, int nsync, int src_base) {
   if (nparse <= 0) return 0;
   {
     int threads = 128;
@@ -633,9 +648,9 @@ int demod_run(const ModeDev &md, const DemapTable *demap, const float2 *X, int n
     DVBT_CUDA_TRY(cudaGetLastError());
     if (b.ev_eq1) DVBT_CUDA_TRY(cudaEventRecord(b.ev_eq1, st));
   }
-  demod_vote_kernel<<<(nparse + 127) / 128, 128, 0, st>>>(md.ntps, nparse, b.tpsval, d_state, b.vote);
+  demod_vote_kernel<<<(nparse + 127) / 128, 128, 0, st>>>(md.ntps, nparse, b.tpsval, d_state, b.vote, sync_start_at0, sync_at, sync_at ? nsync : 0);
   DVBT_CUDA_TRY(cudaGetLastError());
-  demod_scan_kernel<<<1, 32 * kScanWarps, 0, st>>>(md.ntps, nparse, fi_start, sync_start_at0, b.modidx, b.vote, b.tpsval, d_state, b.out_symidx, b.out_src);
+  demod_scan_kernel<<<1, 32 * kScanWarps, 0, st>>>(md.ntps, nparse, fi_start, src_base, b.modidx, b.vote, b.tpsval, d_state, b.out_symidx, b.out_src);
   DVBT_CUDA_TRY(cudaGetLastError());
   count_launch(4);
   return 0;

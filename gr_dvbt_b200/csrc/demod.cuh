@@ -170,6 +170,8 @@ struct ModeTables {
   void release() { blob.release(); }
 };
 
+constexpr int kMaxSfTags = 64;   // superframe_start tags one scan can report (one per re-synchronisation inside the batch)
+
 // Sequential receiver state of pilot_gen + demod_reference_signals_impl (device resident).
 struct DemodState {
   int symbol_index, known, frame_index, prev_mod, mod, d_init;
@@ -178,7 +180,9 @@ struct DemodState {
   // results of the last scan
   int first_out;   // index (within the batch) of the first symbol that was output, -1 if none
   int n_out;       // symbols output by the last scan
-  int sf_tag_at;   // output index carrying the superframe_start tag in the last scan, -1 if none
+  int sf_tag_at;   // output index carrying the (first) superframe_start tag in the last scan, -1 if none
+  int n_sf;        // superframe_start tags sent in the last scan (a sync_start inside the batch re-arms the gating,
+  int sf_at[kMaxSfTags];   // demod_reference_signals_impl.cc:112-116) and the output indices of the first kMaxSfTags
 };
 
 struct DemodBuffers {
@@ -198,7 +202,10 @@ struct DemodBuffers {
 // channel estimate + equalisation (+ optional demap) of every parsed symbol, the TPS votes and the
 // sequential scan.  Y (optional) receives P equalised cells per *parsed* symbol (not compacted);
 // dm (optional) the demapped bytes per parsed symbol.
+// sync_at / nsync: batch indices of the symbols that carry a sync_start tag (device array, may be null);
+// sync_start_at0 = 1 is the same as listing symbol 0.  src_base is added to the values written to out_src.
 int demod_run(const ModeDev &md, const DemapTable *demap, const float2 *X, int nparse, DemodBuffers b,
-              DemodState *d_state, int fi_start, int sync_start_at0, float2 *Y, uint8_t *dm, cudaStream_t st);
+              DemodState *d_state, int fi_start, int sync_start_at0, float2 *Y, uint8_t *dm, cudaStream_t st,
+              const int *sync_at = nullptr, int nsync = 0, int src_base = 0);
 
 }  // namespace dvbt

@@ -78,7 +78,7 @@ constexpr int kOutPerBlock = 512;
 constexpr int kTileIn = (kOutPerBlock * kDecim) / kInterp + 2;  // inputs advanced by a block (+ slack)
 
 __global__ void __launch_bounds__(256) resample_kernel(const float2 *__restrict__ x, long long nin, float2 *__restrict__ y, long long nout,
-                                                       const float *__restrict__ taps_arm, int per_arm, float scale) {
+                                                       const float *__restrict__ taps_arm, int per_arm, float scale, int nhist) {
   extern __shared__ float s_mem[];
   float *s_taps = s_mem;                                        // [32][per_arm]
   float2 *s_x = reinterpret_cast<float2 *>(s_mem + kInterp * (per_arm | 1));  // [kTileIn + per_arm], 8-byte aligned
@@ -89,7 +89,7 @@ __global__ void __launch_bounds__(256) resample_kernel(const float2 *__restrict_
   int span = kTileIn + per_arm;
   for (int i = threadIdx.x; i < span; i += blockDim.x) {
     long long idx = lo + i;
-    s_x[i] = (idx >= 0 && idx < nin) ? x[idx] : make_float2(0.f, 0.f);
+    s_x[i] = (idx >= -(long long)nhist && idx < nin) ? x[idx] : make_float2(0.f, 0.f);
   }
   __syncthreads();
 #pragma unroll
@@ -171,7 +171,7 @@ __device__ __forceinline__ void resample_quad(const float2 *__restrict__ s_x, co
 }
 
 __global__ void __launch_bounds__(256, 3) resample_quad_kernel(const float2 *__restrict__ x, long long nin, float2 *__restrict__ y, long long nout,
-                                                               const float *__restrict__ taps_arm, long long ntiles, float scale) {
+                                                               const float *__restrict__ taps_arm, long long ntiles, float scale, int nhist) {
   __shared__ float2 s_x[kQuadSpan];
   __shared__ __align__(16) float s_taps[kInterp * kRegArm];
   __shared__ float4 s_y[kQuadOut / 2 + kQuadOut / 32];
@@ -183,7 +183,7 @@ __global__ void __launch_bounds__(256, 3) resample_quad_kernel(const float2 *__r
     for (int k = 0; k < kQuadPerThread; k++) {
       int i = t + 256 * k;
       long long idx = lo + i;
-      pre[k] = (i < kQuadSpan && idx >= 0 && idx < nin) ? __ldg(x + idx) : make_float2(0.f, 0.f);
+      pre[k] = (i < kQuadSpan && idx >= -(long long)nhist && idx < nin) ? __ldg(x + idx) : make_float2(0.f, 0.f);
     }
   };
   for (int i = t; i < kInterp * kRegArm; i += 256) s_taps[i] = taps_arm[i];
@@ -282,7 +282,7 @@ __device__ __forceinline__ void resample_multi(const float2 *__restrict__ s_x, c
 
 template <int NQ>
 __global__ void __launch_bounds__(256, 3) resample_multi_kernel(const float2 *__restrict__ x, long long nin, float2 *__restrict__ y, long long nout,
-                                                                const float *__restrict__ taps_arm, long long ntiles, float scale) {
+                                                                const float *__restrict__ taps_arm, long long ntiles, float scale, int nhist) {
   using Cfg = MultiCfg<NQ>;
   extern __shared__ __align__(16) unsigned char s_raw[];
   float4 *s_y = reinterpret_cast<float4 *>(s_raw);
@@ -295,7 +295,7 @@ __global__ void __launch_bounds__(256, 3) resample_multi_kernel(const float2 *__
     float2 *dst = s_xbuf + (size_t)b * Cfg::kSpan;
     for (int i = t; i < Cfg::kSpan; i += 256) {
       const long long idx = lo + i;
-      const bool in = idx >= 0 && idx < nin;
+      const bool in = idx >= -(long long)nhist && idx < nin;
       const unsigned d = (unsigned)__cvta_generic_to_shared(dst + i);
       const float2 *src = x + (in ? idx : 0);
       asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(d), "l"(src), "r"(in ? 8 : 0) : "memory");
@@ -368,15 +368,15 @@ static int resampler_for_device(int dev, Resampler **out) {
 
 long long resample_out_count(long long nin) { return nin <= 0 ? 0 : ((nin - 1) * kInterp) / kDecim + 1; }
 
-int resample_launch_variant(const float2 *d_x, long long nin, float2 *d_y, long long nout, float scale, cudaStream_t st, int variant);
+int resample_launch_variant(const float2 *d_x, long long nin, float2 *d_y, long long nout, float scale, cudaStream_t st, int variant, int nhist = 0);
 
-int resample_launch(const float2 *d_x, long long nin, float2 *d_y, long long nout, float scale, cudaStream_t st) {
+int resample_launch(const float2 *d_x, long long nin, float2 *d_y, long long nout, float scale, cudaStream_t st, int nhist) {
   static const int nq = getenv("DVBT_B200_RESAMPLE_NQ") ? atoi(getenv("DVBT_B200_RESAMPLE_NQ")) : 2;
-  return resample_launch_variant(d_x, nin, d_y, nout, scale, st, nq);
+  return resample_launch_variant(d_x, nin, d_y, nout, scale, st, nq, nhist);
 }
 
 // variant: 0 generic kernel (any tap count), 1 quad kernel, 2 / 4 quads per thread (36 taps per arm)
-int resample_launch_variant(const float2 *d_x, long long nin, float2 *d_y, long long nout, float scale, cudaStream_t st, int nq) {
+int resample_launch_variant(const float2 *d_x, long long nin, float2 *d_y, long long nout, float scale, cudaStream_t st, int nq, int nhist) {
   int dev = 0;
   cudaGetDevice(&dev);
   if (dev >= 64) dev = 63;
@@ -389,10 +389,10 @@ int resample_launch_variant(const float2 *d_x, long long nin, float2 *d_y, long 
     long long grid = ntiles < 3LL * r->sm_count ? ntiles : 3LL * r->sm_count;
     if (nq == 2) {
       DVBT_CUDA_TRY(cudaFuncSetAttribute(resample_multi_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MultiCfg<2>::kSmem));
-      resample_multi_kernel<2><<<(unsigned)grid, 256, MultiCfg<2>::kSmem, st>>>(d_x, nin, d_y, nout, r->d_taps.as<float>(), ntiles, scale);
+      resample_multi_kernel<2><<<(unsigned)grid, 256, MultiCfg<2>::kSmem, st>>>(d_x, nin, d_y, nout, r->d_taps.as<float>(), ntiles, scale, nhist);
     } else {
       DVBT_CUDA_TRY(cudaFuncSetAttribute(resample_multi_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MultiCfg<4>::kSmem));
-      resample_multi_kernel<4><<<(unsigned)grid, 256, MultiCfg<4>::kSmem, st>>>(d_x, nin, d_y, nout, r->d_taps.as<float>(), ntiles, scale);
+      resample_multi_kernel<4><<<(unsigned)grid, 256, MultiCfg<4>::kSmem, st>>>(d_x, nin, d_y, nout, r->d_taps.as<float>(), ntiles, scale, nhist);
     }
     count_launch();
     DVBT_CUDA_TRY(cudaGetLastError());
@@ -401,13 +401,13 @@ int resample_launch_variant(const float2 *d_x, long long nin, float2 *d_y, long 
   if (r->per_arm == kRegArm && nq == 1) {
     long long ntiles = (nout + kQuadOut - 1) / kQuadOut;
     long long grid = ntiles < 3LL * r->sm_count ? ntiles : 3LL * r->sm_count;  // persistent: three resident blocks per SM
-    resample_quad_kernel<<<(unsigned)grid, 256, 0, st>>>(d_x, nin, d_y, nout, r->d_taps.as<float>(), ntiles, scale);
+    resample_quad_kernel<<<(unsigned)grid, 256, 0, st>>>(d_x, nin, d_y, nout, r->d_taps.as<float>(), ntiles, scale, nhist);
     count_launch();
     DVBT_CUDA_TRY(cudaGetLastError());
     return 0;
   }
   size_t smem = (size_t)(kInterp * (r->per_arm | 1) + 2) * 4 + (size_t)(kTileIn + r->per_arm) * 8;
-  resample_kernel<<<(unsigned)((nout + kOutPerBlock - 1) / kOutPerBlock), 256, smem, st>>>(d_x, nin, d_y, nout, r->d_taps.as<float>(), r->per_arm, scale);
+  resample_kernel<<<(unsigned)((nout + kOutPerBlock - 1) / kOutPerBlock), 256, smem, st>>>(d_x, nin, d_y, nout, r->d_taps.as<float>(), r->per_arm, scale, nhist);
   count_launch();
   DVBT_CUDA_TRY(cudaGetLastError());
   return 0;

@@ -198,7 +198,7 @@ constexpr int kHalo = 204 * 11;         // bytes of stream history the deepest d
 template <bool GATHER>
 __global__ void __launch_bounds__(kTilePk) rs_decode_kernel(const uint8_t *__restrict__ in, uint8_t *__restrict__ out,
                                                             int *__restrict__ status, long long npackets, int as_built,
-                                                            long long in_bytes) {
+                                                            long long in_bytes, long long in_lo) {
   extern __shared__ __align__(16) uint8_t s_dyn[];   // division table (8 copies), then the staged input [kTilePk*204 (+ kHalo)]
   // Copy c of row f sits at 16-byte slot 8 f + c: lane l reads copy l & 7, so the eight lanes of a quarter warp -
   // what a 128-bit shared-memory access serves per pass - always hit eight different bank groups, whatever their
@@ -233,11 +233,14 @@ __global__ void __launch_bounds__(kTilePk) rs_decode_kernel(const uint8_t *__res
         long long pos = src0 + 4LL * i;
         v[u] = 0;
         if (i < nwords) {
-          if (pos >= 0 && pos + 4 <= total) {
+          // in_lo <= 0: stream positions [in_lo, 0) before `in` hold real history (a continuing stream: the delay
+          // lines keep their contents, convolutional_deinterleaver_impl.cc:109-120); positions below read as the
+          // zeros the FIFOs start with
+          if (pos >= in_lo && pos + 4 <= total) {
             v[u] = __ldg(reinterpret_cast<const uint32_t *>(in + pos));
           } else {
             for (int b = 0; b < 4; b++)
-              if (pos + b >= 0 && pos + b < total) v[u] |= (uint32_t)in[pos + b] << (8 * b);
+              if (pos + b >= in_lo && pos + b < total) v[u] |= (uint32_t)in[pos + b] << (8 * b);
           }
         }
       }
@@ -358,7 +361,7 @@ int rs_upload_tables() {
 }
 
 int rs_launch(const uint8_t *d_in, uint8_t *d_out, int *d_status, long long npackets, int as_built, int sm_count,
-              cudaStream_t st, long long gather_stream_bytes) {
+              cudaStream_t st, long long gather_stream_bytes, long long history_bytes) {
   if (npackets <= 0) return 0;
   int rc = rs_upload_tables();
   if (rc) return rc;
@@ -368,11 +371,11 @@ int rs_launch(const uint8_t *d_in, uint8_t *d_out, int *d_status, long long npac
   if (gather_stream_bytes >= 0) {
     const size_t smem = (size_t)kTilePk * kPktIn + kHalo + table;
     DVBT_CUDA_TRY(cudaFuncSetAttribute(rs_decode_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    rs_decode_kernel<true><<<grid, kTilePk, smem, st>>>(d_in, d_out, d_status, npackets, as_built, gather_stream_bytes);
+    rs_decode_kernel<true><<<grid, kTilePk, smem, st>>>(d_in, d_out, d_status, npackets, as_built, gather_stream_bytes, -history_bytes);
   } else {
     const size_t smem = (size_t)kTilePk * kPktIn + table;
     DVBT_CUDA_TRY(cudaFuncSetAttribute(rs_decode_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    rs_decode_kernel<false><<<grid, kTilePk, smem, st>>>(d_in, d_out, d_status, npackets, as_built, 0);
+    rs_decode_kernel<false><<<grid, kTilePk, smem, st>>>(d_in, d_out, d_status, npackets, as_built, 0, 0);
   }
   count_launch();
   DVBT_CUDA_TRY(cudaGetLastError());
@@ -426,7 +429,7 @@ int dvbt_b200_rsdec_decode_dev(dvbt_b200_rsdec *h, const uint8_t *d_in, size_t n
   if (!h || (npackets && (!d_in || !d_out))) { dvbt::set_error("rsdec_decode_dev: bad argument"); return DVBT_B200_EINVAL; }
   int rc = dvbt::join_default_stream(h->stream);
   if (rc) return rc;
-  rc = dvbt::rs_launch(d_in, d_out, d_status, (long long)npackets, h->as_built, h->sm_count, h->stream, -1);
+  rc = dvbt::rs_launch(d_in, d_out, d_status, (long long)npackets, h->as_built, h->sm_count, h->stream, -1, 0);
   if (rc) return rc;
   DVBT_CUDA_TRY(cudaStreamSynchronize(h->stream));
   return 0;
@@ -448,7 +451,7 @@ int dvbt_b200_rsdec_work(dvbt_b200_rsdec *h, const uint8_t *in, size_t n_in_item
   if ((rc = h->d_in.reserve(npk * kPktIn))) return rc;
   if ((rc = h->d_out.reserve(npk * kPktOut))) return rc;
   DVBT_CUDA_TRY(cudaMemcpyAsync(h->d_in.p, in, npk * kPktIn, cudaMemcpyHostToDevice, h->stream));
-  rc = dvbt::rs_launch(h->d_in.as<uint8_t>(), h->d_out.as<uint8_t>(), nullptr, (long long)npk, h->as_built, h->sm_count, h->stream, -1);
+  rc = dvbt::rs_launch(h->d_in.as<uint8_t>(), h->d_out.as<uint8_t>(), nullptr, (long long)npk, h->as_built, h->sm_count, h->stream, -1, 0);
   if (rc) return rc;
   DVBT_CUDA_TRY(cudaMemcpyAsync(out, h->d_out.p, npk * kPktOut, cudaMemcpyDeviceToHost, h->stream));
   DVBT_CUDA_TRY(cudaStreamSynchronize(h->stream));

@@ -249,18 +249,19 @@ int dvbt_b200_acq_work(dvbt_b200_acq *h, const void *in, size_t n_in_items, void
  *   demod_reference_signals -> dvbt_demap -> symbol_inner_interleaver(deinterleave) ->
  *   bit_inner_deinterleaver -> viterbi_decoder -> convolutional_deinterleaver(136,12,17) ->
  *   reed_solomon_dec -> energy_descramble
- * with the tags (sync_start at the first symbol, symbol_index, superframe_start) carried as
- * batch metadata.  The TS written is every complete 8-packet group from the first NSYNC packet
- * on; the reference flowgraph writes a scheduler-dependent prefix of the same bytes
- * (energy_descramble_impl.cc:140-141 holds back two groups).
+ * with the tags (sync_start at the first symbol and at every re-acquisition, symbol_index,
+ * superframe_start) carried as batch metadata.  The TS written is what energy_descramble delivers when it
+ * is called with 4 items visible and its smallest output (pairs of 8-packet groups from the NSYNC packet
+ * on, energy_descramble_impl.cc:121-141); with larger calls the reference flowgraph writes a
+ * scheduler-dependent prefix of the same bytes (:140-141 holds back two groups per call).
  * ------------------------------------------------------------------------------------ */
 typedef struct dvbt_b200_rx dvbt_b200_rx;
 typedef struct dvbt_b200_rx_params {
   int constellation, hierarchy, code_rate, guard_interval, transmission_mode;
 } dvbt_b200_rx_params;
-typedef struct dvbt_b200_rx_info {
+typedef struct dvbt_b200_rx_info { /* counts since the stream was reset (= of the run, for the one-shot entry points) */
   long long symbols_parsed; /* OFDM symbols run through parse_input */
-  long long first_symbol;   /* batch index of the first symbol output by demod (superframe start), -1 */
+  long long first_symbol;   /* stream index of the first symbol output by demod (superframe start), -1 */
   long long symbols_out;
   long long viterbi_bytes;  /* decoded bytes */
   long long viterbi_repaired; /* chunks whose boundary state had to be re-decoded */
@@ -274,6 +275,10 @@ typedef struct dvbt_b200_rx_info {
   float ms_resample, ms_acq_fft;
   float ms_demod, ms_inner, ms_viterbi, ms_viterbi_acs, ms_rs, ms_descramble; /* device time per stage */
   float ms_fft, ms_equalise; /* single kernels inside the stages above: derotation+FFT (in ms_acq_fft), equalise+demap (in ms_demod) */
+  long long n_sync_start;        /* sync_start tags acquisition sent that demod has seen (1 + re-acquisitions) */
+  long long n_superframe_start;  /* superframe_start tags the Viterbi block honoured (decoder resets) */
+  long long n_viterbi_runs;      /* chunk-parallel decodes launched (one per call and stream segment) */
+  long long ts_total;            /* TS bytes written since the stream was reset (ts_bytes: by the last call) */
 } dvbt_b200_rx_info;
 enum { DVBT_RX_STAGE_CELLS = 0, DVBT_RX_STAGE_DEMAP = 1, DVBT_RX_STAGE_BITDEINT = 2, DVBT_RX_STAGE_VITERBI = 3,
        DVBT_RX_STAGE_RS = 4, DVBT_RX_STAGE_RS_STATUS = 5, DVBT_RX_STAGE_SYMBOL_INDEX = 6 };
@@ -295,6 +300,31 @@ int dvbt_b200_rx_run_baseband_dev(dvbt_b200_rx *h, const void *d_samples, size_t
  * GNU Radio blocks (not part of gr-dvbt); they follow GNU Radio 3.7's documented behaviour. */
 int dvbt_b200_rx_run_file_host(dvbt_b200_rx *h, const void *samples, size_t nsamples, float gain, uint8_t *ts, size_t ts_capacity, size_t *ts_bytes);
 int dvbt_b200_rx_run_file_dev(dvbt_b200_rx *h, const void *d_samples, size_t nsamples, float gain, uint8_t *d_ts, size_t ts_capacity, size_t *ts_bytes);
+/* Streaming: the same chain fed in pieces of any size, the way the GNU Radio scheduler feeds the flowgraph.  Every
+ * block's state is carried from call to call - the resampler's FIR history, the samples ofdm_sym_acquisition has not
+ * consumed and its tracking state, the symbol demod_reference_signals is still waiting to see the successor of
+ * (forecast: 2 items, demod_reference_signals_impl.cc:87-94) and its TPS/frame state, the cells short of a whole
+ * 768-block and the Viterbi decoder state, the outer deinterleaver's delay lines (never cleared,
+ * convolutional_deinterleaver_impl.cc:109-120), the packets energy_descramble has not consumed and its NSYNC index.
+ * level: 0 = capture file samples at 10 Msps (gain = the flowgraph's multiply_const), 1 = baseband at the OFDM rate,
+ * 2 = post-FFT symbols (count = symbols); a stream keeps its level until it ends or is reset.  Each call writes the TS
+ * bytes that became available (*ts_bytes) at the start of ts.  end_of_stream != 0: no more input follows (a tail that
+ * would need more input is dropped, exactly as at the end of a one-shot run); the next push starts a new stream.
+ * The concatenated output of the pieces is the output of the one-shot run on the concatenated input.
+ * Re-synchronisation inside a stream: a missed peak restarts acquisition (ofdm_sym_acquisition_impl.cc:545-558), every
+ * attempt sends sync_start (:507), demod re-arms on it and waits for the next superframe start
+ * (demod_reference_signals_impl.cc:112-116), whose tag resets the Viterbi decoder and re-aligns the outer
+ * deinterleaver.  What the reference drops at such a tag depends on the size of the scheduler's calls (input in front
+ * of a tag inside a call's window is consumed undecoded, viterbi_decoder_impl.cc:213-229,
+ * convolutional_deinterleaver_impl.cc:109-120; energy_descramble re-checks NSYNC once per call); this library behaves
+ * as the reference does with the smallest calls the scheduler can make (one 768-block, 2 deinterleaver items,
+ * 4 x 1504 descrambler output bytes), which lose the least. */
+int dvbt_b200_rx_stream_reset(dvbt_b200_rx *h);
+int dvbt_b200_rx_stream_push_host(dvbt_b200_rx *h, int level, const void *data, size_t count, float gain, int end_of_stream, uint8_t *ts,
+                                  size_t ts_capacity, size_t *ts_bytes);
+int dvbt_b200_rx_stream_push_dev(dvbt_b200_rx *h, int level, const void *d_data, size_t count, float gain, int end_of_stream, uint8_t *d_ts,
+                                 size_t ts_capacity, size_t *ts_bytes);
+enum { DVBT_RX_LEVEL_FILE = 0, DVBT_RX_LEVEL_BASEBAND = 1, DVBT_RX_LEVEL_FREQ = 2 };
 /* the 32/35 low-pass prototype used by the resampler; returns its length */
 int dvbt_b200_resampler_taps(float *taps, int capacity);
 /* The front end alone, host buffers: rational_resampler_ccc(64,70) + multiply_const(gain) (stock GNU Radio blocks of

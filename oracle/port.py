@@ -45,6 +45,8 @@ def lib():
         L.dvbt_oracle_conv_deinterleave.argtypes = [C.c_void_p, C.c_long, C.c_void_p]
         L.dvbt_oracle_descramble.restype = C.c_long
         L.dvbt_oracle_descramble.argtypes = [C.c_void_p, C.c_long, C.c_void_p, C.c_void_p]
+        L.dvbt_oracle_descramble_calls.restype = C.c_long
+        L.dvbt_oracle_descramble_calls.argtypes = [C.c_void_p, C.c_long, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.dvbt_oracle_demod_create.restype = C.c_void_p
         L.dvbt_oracle_demod_create.argtypes = [C.c_int, C.c_int]
         L.dvbt_oracle_demod_destroy.argtypes = [C.c_void_p]
@@ -176,6 +178,16 @@ def descramble(packets188):
     first = C.c_long(-1)
     n = lib().dvbt_oracle_descramble(p.ctypes.data, p.shape[0], out.ctypes.data, C.byref(first))
     return out[:n], int(first.value)
+
+
+def descramble_calls(packets188, pk=0, flush=False):
+    """energy_descramble at the scheduler's smallest call size over the pending packets (energy_descramble_impl.cc:108-174):
+    returns (ts bytes, items consumed, d_index in packets after the calls, index of the first packet output or -1)"""
+    p = np.ascontiguousarray(packets188, np.uint8).reshape(-1, 188)
+    out = np.zeros(p.size + 16, np.uint8)
+    first, used, pkc = C.c_long(-1), C.c_long(0), C.c_int(int(pk))
+    n = lib().dvbt_oracle_descramble_calls(p.ctypes.data, p.shape[0], int(flush), C.byref(pkc), out.ctypes.data, C.byref(used), C.byref(first))
+    return out[:n], int(used.value), int(pkc.value), int(first.value)
 
 
 def demod(X, constellation, tm, sync_start_at0=True):

@@ -59,6 +59,8 @@ void dvbt_oracle_symbol_deinterleave(const uint8_t *in, long nsym, int tm, const
 void dvbt_oracle_bit_deinterleave(const uint8_t *in, long ncells, int v, uint8_t *out);
 void dvbt_oracle_conv_deinterleave(const uint8_t *in, long n, uint8_t *out);
 long dvbt_oracle_descramble(const uint8_t *in, long npackets, uint8_t *out, long *first_packet);
+long dvbt_oracle_descramble_calls(const uint8_t *in, long npackets, int flush, int *pk_io, uint8_t *out, long *items_used,
+                                  long *first_packet);
 
 /* ---- demod_reference_signals (demod_port.c) ------------------------------------------ */
 typedef struct dvbt_oracle_demod dvbt_oracle_demod;

@@ -124,3 +124,69 @@ long dvbt_oracle_descramble(const uint8_t *in, long npackets, uint8_t *out, long
   }
   return count;
 }
+
+/* One group of 8 packets (:140-165): PRBS restarted, SYNC bytes restored */
+static long descramble_group(const uint8_t *src, uint8_t *out) {
+  unsigned reg = 0xa9; /* init_prbs, :46-49 */
+  long count = 0;
+  for (int pk = 0; pk < 8; pk++) {
+    out[count++] = 0x47;
+    for (int k = 1; k < 188; k++) {
+      unsigned res = 0;
+      for (int i = 0; i < 8; i++) { /* clock_prbs(8), :52-67 */
+        unsigned fb = ((reg >> 13) ^ (reg >> 14)) & 1u;
+        reg = ((reg << 1) | fb) & 0x7fff;
+        res = (res << 1) | fb;
+      }
+      out[count] = (uint8_t)(src[pk * 188 + k] ^ res);
+      count++;
+    }
+    for (int i = 0; i < 8; i++) { /* clocked on the next sync byte, output unused (:162-164) */
+      unsigned fb = ((reg >> 13) ^ (reg >> 14)) & 1u;
+      reg = ((reg << 1) | fb) & 0x7fff;
+    }
+  }
+  return count;
+}
+
+/* energy_descramble_impl::general_work (:108-174) the way the scheduler calls it with the smallest output it may ask for
+ * (noutput_items = 4 x 1504, set_output_multiple :84-87, i.e. to_consume = 2 items, to_out = 2 groups) whenever 4 items
+ * (forecast :102-106 asks for more; the data the call touches is 4 items) are visible.  The only state is d_index (here
+ * *pk_io = d_index / 188): the search starts where NSYNC was seen last (:121-123) and walks one packet at a time up to
+ * d_search = 2 groups; not found -> d_index = 0, consume 2 items, no output (:128-134); found -> the two groups at d_index
+ * are descrambled blindly (:140-165) and 2 items consumed.  Processes `npackets` pending packets (8 per item); returns bytes
+ * written, *items_used = items consumed, *first_packet = index of the first packet output (-1: none).
+ * flush != 0 (not part of the reference: what a run that knows its input has ended can still deliver): with d_index in
+ * place, keep descrambling complete pairs, then one last complete group. */
+long dvbt_oracle_descramble_calls(const uint8_t *in, long npackets, int flush, int *pk_io, uint8_t *out, long *items_used,
+                                  long *first_packet) {
+  long i = 0, count = 0, first = -1;
+  int pk = *pk_io;
+  while (8 * i + 32 <= npackets) {
+    while (in[(8 * i + pk) * 188] != 0xB8 && pk < 16) pk++; /* :121-123 (d_index < d_search tested second, as there) */
+    if (pk >= 16) {
+      pk = 0;
+    } else {
+      if (first < 0) first = 8 * i + pk;
+      count += descramble_group(in + (8 * i + pk) * 188, out + count);
+      count += descramble_group(in + (8 * i + pk + 8) * 188, out + count);
+    }
+    i += 2;
+  }
+  if (flush && pk < 16) {
+    while (8 * i + pk + 16 <= npackets && in[(8 * i + pk) * 188] == 0xB8) {
+      if (first < 0) first = 8 * i + pk;
+      count += descramble_group(in + (8 * i + pk) * 188, out + count);
+      count += descramble_group(in + (8 * i + pk + 8) * 188, out + count);
+      i += 2;
+    }
+    if (8 * i + pk + 8 <= npackets && in[(8 * i + pk) * 188] == 0xB8 && !(8 * i + pk + 16 <= npackets)) {
+      if (first < 0) first = 8 * i + pk;
+      count += descramble_group(in + (8 * i + pk) * 188, out + count);
+    }
+  }
+  *pk_io = pk;
+  if (items_used) *items_used = i;
+  if (first_packet) *first_packet = first;
+  return count;
+}

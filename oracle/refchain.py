@@ -200,17 +200,19 @@ def tx_inner(ci, con, cr, tm, nsym=None):
     return dict(ic=ic, bi=bi, si=si, ma=ma, X=X, nsym=nsym, per_item=per_item)
 
 
-def rx_demod(Xf, con, cr, tm):
-    """demod_reference_signals one item per call, two items visible, sync_start tag at 0
-    (demod_reference_signals_impl.cc:96-150).  Xf: (nsym, N) complex64 post-FFT symbols.
-    Returns (Y (nout,P) complex64, tags)."""
+def rx_demod(Xf, con, cr, tm, sync_offsets=(0,)):
+    """demod_reference_signals one item per call, two items visible, sync_start tags at the item
+    offsets `sync_offsets` (what ofdm_sym_acquisition sends on every acquisition attempt; a tag on the
+    item being parsed re-arms the wait for a superframe start, demod_reference_signals_impl.cc:96-150).
+    Xf: (nsym, N) complex64 post-FFT symbols.  Returns (Y (nout,P) complex64, tags)."""
     N, P, _, _ = mode_dims(tm)
     nsym = Xf.shape[0]
     buf = np.zeros((nsym + 1) * N + 64, np.complex64)
     buf[32 : 32 + nsym * N] = Xf.reshape(-1)
     Y = np.zeros(nsym * P, np.complex64)
     b = RefBlock("demod_reference_signals", 8, N, P, con, NH, cr, cr, G1_32, tm, 0, 0)
-    b.add_tag(0, "sync_start", 1)
+    for off in sorted(set(int(o) for o in sync_offsets)):
+        b.add_tag(off, "sync_start", 1)
     nout = 0
     base = buf.ctypes.data + 32 * 8
     for i in range(nsym - 1):
@@ -252,7 +254,12 @@ def rx_viterbi(vin, con, cr, sf_tag_offset=None, blocks_per_call=16, bsize=768):
     vo = np.zeros(len(vin) * k * m // (8 * n) + 4096, np.uint8)
     b = RefBlock("viterbi_decoder", con, NH, cr, bsize, 0, -1)
     if sf_tag_offset is not None:
-        b.add_tag(sf_tag_offset, "superframe_start", 0xAA)
+        # one offset or several (a receiver that re-synchronised mid-stream): with more than one tag the result
+        # depends on the call size - everything between the start of a call's window and a tag inside it is
+        # dropped (:213-229) - so multi-tag streams are driven one 768-block per call (blocks_per_call=1), the
+        # smallest call the scheduler can make (set_output_multiple, :141)
+        for off in ([sf_tag_offset] if np.isscalar(sf_tag_offset) else sf_tag_offset):
+            b.add_tag(int(off), "superframe_start", 0xAA)
     vout = 0
     while True:
         avail = len(vin) - b.nread
@@ -269,8 +276,13 @@ def rx_viterbi(vin, con, cr, sf_tag_offset=None, blocks_per_call=16, bsize=768):
     return vo[:vout].copy(), tags
 
 
-def rx_outer(vo, vtags, fixed_rs=False):
-    """convolutional_deinterleaver -> reed_solomon_dec -> energy_descramble."""
+def rx_outer(vo, vtags, fixed_rs=False, min_calls=False):
+    """convolutional_deinterleaver -> reed_solomon_dec -> energy_descramble.
+    min_calls: the smallest calls the scheduler can make - 2 items for the deinterleaver (set_output_multiple(2),
+    convolutional_deinterleaver_impl.cc:61), 4 x 1504 output bytes for the descrambler (energy_descramble_impl.cc:84-87).
+    With a single superframe_start at offset 0 and an undisturbed stream the call sizes do not matter; after a
+    mid-stream re-synchronisation they do (bytes in front of a tag inside a call's window are dropped, and the
+    descrambler re-checks NSYNC once per call), so those cases are pinned at the minimal call size."""
     vo = np.ascontiguousarray(vo, np.uint8)
     cd = np.zeros(len(vo) + 4096, np.uint8)
     b = RefBlock("convolutional_deinterleaver", 136, 12, 17)
@@ -279,7 +291,7 @@ def rx_outer(vo, vtags, fixed_rs=False):
     cdo = 0
     while True:
         avail = len(vo) - b.nread
-        ni = min(64, avail // 1632) // 2 * 2
+        ni = min(2 if min_calls else 64, avail // 1632) // 2 * 2
         if ni < 2:
             break
         r, cons = b.work(ni, avail, vo.ctypes.data + b.nread, cd.ctypes.data + cdo * 1632)
@@ -298,7 +310,8 @@ def rx_outer(vo, vtags, fixed_rs=False):
         avail = cdo - b.nread
         if avail < 4:
             break
-        r, cons = b.work(avail * 1504, avail, rd.ctypes.data + b.nread * 1504, out.ctypes.data + oo)
+        nitems = 4 if min_calls else avail
+        r, cons = b.work(nitems * 1504, avail, rd.ctypes.data + b.nread * 1504, out.ctypes.data + oo)
         if r > 0:
             oo += r
         if cons == 0:

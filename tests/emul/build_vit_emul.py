@@ -120,9 +120,10 @@ def build(force=False):
 RX_LIB = os.path.join(BUILD, "librx_emul.so")
 
 RX_LAUNCHER = r'''
-extern "C" int emul_inner_codes(const uint8_t *dm, const int *out_src, const int *out_symidx, const short *H, const short *Hinv, int P, int m,
-                                int n_out, int rate, uint32_t *codes, int nbt) {
-  InnerMap im{dm, out_src, out_symidx, H, Hinv, P, m, n_out};
+// shift_bits: bit of row 0 that is bit 0 of the Viterbi input stream (a run that continues a stream starts inside a symbol)
+extern "C" int emul_inner_codes_at(const uint8_t *dm, const int *out_src, const int *out_symidx, const short *H, const short *Hinv, int P, int m,
+                                   int n_out, int rate, uint32_t *codes, int nbt, int shift_bits) {
+  InnerMap im{dm, out_src, out_symidx, H, Hinv, P, m, n_out, shift_bits};
   const int G = kInnerTileCells / P;
   const unsigned grid = (unsigned)((n_out + G - 1) / G);
 #define EMUL_INNER(R, M) emul_launch(rx_inner_codes_kernel<R, M>, grid, 256u, im, codes, nbt)
@@ -137,12 +138,35 @@ extern "C" int emul_inner_codes(const uint8_t *dm, const int *out_src, const int
   return 0;
 }
 
+extern "C" int emul_inner_codes(const uint8_t *dm, const int *out_src, const int *out_symidx, const short *H, const short *Hinv, int P, int m,
+                                int n_out, int rate, uint32_t *codes, int nbt) {
+  return emul_inner_codes_at(dm, out_src, out_symidx, H, Hinv, P, m, n_out, rate, codes, nbt, 0);
+}
+
+// one call of the descrambler stage: plan (the block's NSYNC state machine over the pending packets) + descramble.
+// pk_io: d_index in packets, carried from call to call; end: end of stream (the tail is flushed)
+extern "C" int emul_descramble_stream(const uint8_t *rs, long long npk, const uint32_t *prbs, uint8_t *ts, long long ts_capacity, int grid,
+                                      int end, int *pk_io, long long *first_packet, long long *ngroups, long long *items_used) {
+  DescrState st;
+  memset(&st, 0, sizeof st);
+  st.pk = *pk_io;
+  st.first_packet = -1;
+  std::vector<int> plan((size_t)(npk / 16 + 2));
+  emul_launch(rx_descr_plan_kernel, 1u, 1024u, rs, npk, &st, plan.data(), (long long)plan.size(), end);
+  emul_launch(rx_descramble_kernel, (unsigned)grid, 256u, rs, (const DescrState *)&st, (const int *)plan.data(), prbs, ts, ts_capacity);
+  *pk_io = st.pk;
+  *first_packet = st.first_packet;
+  *ngroups = 2LL * st.n_pairs + st.n_tail;
+  *items_used = st.items_used;
+  return 0;
+}
+
 extern "C" int emul_descramble(const uint8_t *rs, long long npk, const uint32_t *prbs, uint8_t *ts, long long ts_capacity, int grid,
                                int *p0, long long *ngroups) {
-  DescrInfo info{-1, 0};
-  emul_launch(rx_descramble_kernel, (unsigned)grid, 256u, rs, npk, prbs, ts, ts_capacity, &info);
-  *p0 = info.p0;
-  *ngroups = info.ngroups;
+  int pk = 0;
+  long long first = -1, used = 0;
+  emul_descramble_stream(rs, npk, prbs, ts, ts_capacity, grid, 1, &pk, &first, ngroups, &used);
+  *p0 = (int)first;
   return 0;
 }
 '''
@@ -154,7 +178,7 @@ def rx_device_text():
     b = src.index("\nstruct dvbt_b200_rx {")
     text = src[a:b]
     text = text[: text.rindex("}  // namespace")]
-    for needle in ("rx_inner_codes_kernel(InnerMap im", "rx_descramble_kernel(", "struct DescrInfo"):
+    for needle in ("rx_inner_codes_kernel(InnerMap im", "rx_descramble_kernel(", "rx_descr_plan_kernel(", "struct DescrState"):
         assert needle in text, "rx_chain.cu changed shape: %r not in the extracted device part" % needle
     assert "cudaMalloc" not in text and "cudaStream" not in text
     return text.replace("extern __shared__", "extern")
@@ -167,7 +191,7 @@ def build_rx(force=False):
         return RX_LIB
     os.makedirs(BUILD, exist_ok=True)
     tu = ('// GENERATED by tests/emul/build_vit_emul.py from gr_dvbt_b200/csrc/rx_chain.cu -- test infrastructure\n'
-          '#include <string.h>\n#include "../cuda_host_emul.h"\n'
+          '#include <string.h>\n#include <vector>\n#include "../cuda_host_emul.h"\n'
           'namespace {\nalignas(16) uint8_t s_bit[1 << 17];   // the dynamic shared memory of the running block\n'
           + rx_device_text() + RX_LAUNCHER + "}  // namespace\n")
     # the launchers are extern "C": they must sit outside the unnamed namespace
@@ -188,8 +212,8 @@ extern "C" int emul_rs(const uint8_t *in, uint8_t *out, int *status, long long n
   if (npackets <= 0) return 0;
   if (dvbt::rs_upload_tables()) return -1;
   const unsigned grid = (unsigned)((npackets + kTilePk - 1) / kTilePk);
-  if (gather_stream_bytes >= 0) emul_launch(rs_decode_kernel<true>, grid, (unsigned)kTilePk, in, out, status, npackets, as_built, gather_stream_bytes);
-  else emul_launch(rs_decode_kernel<false>, grid, (unsigned)kTilePk, in, out, status, npackets, as_built, 0LL);
+  if (gather_stream_bytes >= 0) emul_launch(rs_decode_kernel<true>, grid, (unsigned)kTilePk, in, out, status, npackets, as_built, gather_stream_bytes, 0LL);
+  else emul_launch(rs_decode_kernel<false>, grid, (unsigned)kTilePk, in, out, status, npackets, as_built, 0LL, 0LL);
   return 0;
 }
 '''
@@ -327,8 +351,9 @@ extern "C" int emul_demod(const float *Xf, int nsym, int constellation, int tm, 
   emul_launch(demod_stage1_kernel, (unsigned)(((long long)nparse * 32 + 127) / 128), 128u, md, X, nparse, fo.data(), rot.data(), mod.data());
   emul_launch(demod_equalise_kernel, (unsigned)nparse, 256u, md, dt, 1, X, (const int *)fo.data(), (const float2 *)rot.data(), (const int *)mod.data(),
               tps.data(), (float2 *)Y_out, dm_out);
-  emul_launch(demod_vote_kernel, (unsigned)((nparse + 127) / 128), 128u, md.ntps, nparse, (const float2 *)tps.data(), &st, vote.data());
-  emul_launch(demod_scan_kernel, 1u, (unsigned)(32 * kScanWarps), md.ntps, nparse, fi_start, sync_start_at0, (const int *)mod.data(), (const int *)vote.data(),
+  emul_launch(demod_vote_kernel, (unsigned)((nparse + 127) / 128), 128u, md.ntps, nparse, (const float2 *)tps.data(), &st, vote.data(),
+              sync_start_at0, (const int *)nullptr, 0);
+  emul_launch(demod_scan_kernel, 1u, (unsigned)(32 * kScanWarps), md.ntps, nparse, fi_start, 0, (const int *)mod.data(), (const int *)vote.data(),
               (const float2 *)tps.data(), &st, osym.data(), osrc.data());
   *n_out = st.n_out; *first_out = st.first_out; *sf_tag_at = st.sf_tag_at;
   for (int i = 0; i < st.n_out; i++) { symidx_out[i] = osym[i]; src_out[i] = osrc[i]; }

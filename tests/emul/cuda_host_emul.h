@@ -97,6 +97,11 @@ static inline unsigned long long atomicMin(unsigned long long *p, unsigned long 
   while (v < old && !__atomic_compare_exchange_n(p, &old, v, false, __ATOMIC_RELAXED, __ATOMIC_RELAXED)) {}
   return old;
 }
+static inline int atomicMin(int *p, int v) {
+  int old = __atomic_load_n(p, __ATOMIC_RELAXED);
+  while (v < old && !__atomic_compare_exchange_n(p, &old, v, false, __ATOMIC_RELAXED, __ATOMIC_RELAXED)) {}
+  return old;
+}
 static int emul_block_or = 0;
 static inline int __syncthreads_or(int pred) {
   if (pred) __atomic_fetch_or(&emul_block_or, 1, __ATOMIC_RELAXED);

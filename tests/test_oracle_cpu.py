@@ -193,3 +193,37 @@ def test_demap_port_matches_the_reference_build_on_hierarchical_constellations(c
     ref = np.zeros(n, np.uint8)
     R.RefBlock("dvbt_demap", 1512, con, hier, R.T2k, 1.0).work(2, 2, np.ascontiguousarray(c), ref)
     assert np.array_equal(O.demap(c, con, alpha, 1.0), ref)
+
+
+@pytest.mark.skipif(not R.available(), reason="oracle/_ref not built")
+def test_descrambler_call_by_call_matches_reference_with_broken_nsync():
+    """energy_descramble keeps one piece of state (d_index) and re-checks NSYNC once per call (energy_descramble_impl.cc:
+    121-141): the restatement at the scheduler's smallest call size against the reference block driven the same way, on a
+    packet stream whose NSYNC bytes are partly destroyed and whose 8-packet phase jumps in the middle (what a mid-stream
+    re-synchronisation of the outer deinterleaver looks like from here)"""
+    rng = np.random.default_rng(5)
+    src = CH["rs"].reshape(-1, 188)[:160].copy()
+    assert src[0, 0] == 0xB8 or (src[:, 0] == 0xB8).any()
+    a = int(np.flatnonzero(src[:, 0] == 0xB8)[0])
+    stream = np.concatenate([rng.integers(0, 0xB0, (5, 188), dtype=np.uint8), src[a: a + 64], src[a + 67: a + 67 + 77]])   # lead junk, then a phase jump of 3
+    nsync = np.flatnonzero(stream[:, 0] == 0xB8)
+    for kill in ([], [nsync[1]], [nsync[2], nsync[3]], list(nsync[4:7])):
+        pk = stream.copy()
+        pk[kill, 0] = 0x00
+        n = len(pk) // 8 * 8
+        items = n // 8
+        out = np.zeros(n * 188 + 16, np.uint8)
+        b = R.RefBlock("energy_descramble", 8)
+        oo = 0
+        while items - b.nread >= 4:
+            r, cons = b.work(4 * 1504, items - b.nread, pk.ctypes.data + b.nread * 1504, out.ctypes.data + oo)
+            oo += max(r, 0)
+            if cons == 0:
+                break
+        got, used, pkidx, first = O.descramble_calls(pk[:n])
+        assert used == b.nread and len(got) == oo and np.array_equal(got, out[:oo])
+        # in two pieces, carrying d_index: the same bytes
+        cut = 40
+        g1, u1, p1, f1 = O.descramble_calls(pk[:cut])
+        g2, u2, p2, f2 = O.descramble_calls(pk[8 * u1: n], pk=p1)
+        assert np.array_equal(np.concatenate([g1, g2]), got)

@@ -102,3 +102,43 @@ def test_descramble_kernel_matches_oracle(lib, lead):
         assert rc == 0 and p0.value == first
         n = min(ng.value * 1504, len(want))
         assert n >= 1504 * 10 and np.array_equal(ts[:n], want[:n])
+
+
+@pytest.mark.parametrize("pieces", [1, 3])
+def test_descrambler_state_machine_matches_oracle_with_broken_nsync(lib, pieces):
+    """rx_descr_plan_kernel replays energy_descramble's per-call NSYNC check (energy_descramble_impl.cc:121-141): destroyed
+    NSYNC bytes, a jump of the 8-packet phase, the index carried across pieces - against the oracle restatement
+    (dvbt_oracle_descramble_calls, itself pinned to the reference block in tests/test_oracle_cpu.py)"""
+    rng = np.random.default_rng(9)
+    src = CH["rs"].reshape(-1, 188)
+    a = int(np.flatnonzero(src[:, 0] == 0xB8)[0])
+    stream = np.concatenate([rng.integers(0, 0xB0, (5, 188), dtype=np.uint8), src[a: a + 64], src[a + 67: a + 67 + 93]])
+    nsync = np.flatnonzero(stream[:, 0] == 0xB8)
+    prbs = prbs_table()
+    for kill in ([], [nsync[1]], [nsync[2], nsync[3]], list(nsync[4:7]), [nsync[-2]]):
+        pk = stream.copy()
+        pk[kill, 0] = 0
+        cuts = [0, len(pk)] if pieces == 1 else [0, 37, 90, len(pk)]
+        want_all, got_all = [], []
+        pend_o = np.zeros((0, 188), np.uint8)
+        pend_k = np.zeros((0, 188), np.uint8)
+        pk_o, pk_k = 0, 0
+        for ci in range(len(cuts) - 1):
+            end = ci == len(cuts) - 2
+            new = pk[cuts[ci]: cuts[ci + 1]]
+            pend_o = np.concatenate([pend_o, new])
+            want, used, pk_o, first = O.descramble_calls(pend_o, pk=pk_o, flush=end)
+            want_all.append(want)
+            pend_o = pend_o[8 * used:]
+            pend_k = np.ascontiguousarray(np.concatenate([pend_k, new]))
+            ts = np.zeros(pend_k.size + 3008, np.uint8)
+            pkc, fp, ng, iu = C.c_int(pk_k), C.c_longlong(-1), C.c_longlong(0), C.c_longlong(0)
+            rc = lib.emul_descramble_stream(C.c_void_p(pend_k.ctypes.data), C.c_longlong(pend_k.shape[0]), C.c_void_p(prbs.ctypes.data),
+                                            C.c_void_p(ts.ctypes.data), C.c_longlong(ts.size), 2, int(end), C.byref(pkc), C.byref(fp), C.byref(ng), C.byref(iu))
+            assert rc == 0
+            pk_k = pkc.value
+            got_all.append(ts[: ng.value * 1504].copy())
+            assert iu.value == used and pk_k == pk_o and fp.value == first
+            pend_k = pend_k[8 * iu.value:]
+        assert np.array_equal(np.concatenate(got_all), np.concatenate(want_all))
+        assert len(np.concatenate(want_all)) >= 1504 * 8
