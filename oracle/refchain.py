@@ -29,7 +29,7 @@ QPSK, QAM16, QAM64 = 0, 1, 2
 NH = 0
 C1_2, C2_3, C3_4, C5_6, C7_8 = 0, 1, 2, 3, 4
 T2k, T8k = 0, 1
-G1_32 = 0
+G1_32, G1_16, G1_8, G1_4 = 0, 1, 2, 3
 
 RATE_KN = {C1_2: (1, 2), C2_3: (2, 3), C3_4: (3, 4), C5_6: (5, 6), C7_8: (7, 8)}
 BITS_PER_CELL = {QPSK: 2, QAM16: 4, QAM64: 6}
@@ -155,8 +155,10 @@ class RefBlock:
 # Stage helpers (whole arrays in, whole arrays out), SURVEY Appendix B recipe
 # ----------------------------------------------------------------------------------------
 
-def mode_dims(tm):
-    return (2048, 1512, 1705, 64) if tm == T2k else (8192, 6048, 6817, 256)
+def mode_dims(tm, gi=G1_32):
+    """(N, P, K, cp): cp = N/32, N/16, N/8, N/4 for the guard intervals G1_32 .. G1_4 (lib/dvbt_config.cc:194-208)"""
+    N, P, K = (2048, 1512, 1705) if tm == T2k else (8192, 6048, 6817)
+    return N, P, K, N // (32 >> gi)
 
 
 def tx_outer(ts_bytes):
@@ -176,7 +178,7 @@ def tx_outer(ts_bytes):
     return ed[: ng * 1504], rs, ci
 
 
-def tx_inner(ci, con, cr, tm, nsym=None):
+def tx_inner(ci, con, cr, tm, nsym=None, gi=G1_32):
     """Forney-interleaved bytes -> inner coder -> bit/symbol interleave -> map -> pilots.
     Returns dict with every intermediate; X is (nsym, N) complex64 frequency-domain symbols."""
     N, P, _, _ = mode_dims(tm)
@@ -195,12 +197,12 @@ def tx_inner(ci, con, cr, tm, nsym=None):
     ma = np.zeros(nsym * P, np.complex64)
     RefBlock("dvbt_map", P, con, NH, tm, 1.0).work(nsym, nsym, si, ma)
     X = np.zeros((nsym + 1) * N + 64, np.complex64)
-    RefBlock("reference_signals", 8, P, N, con, NH, cr, cr, G1_32, tm, 0, 0).work(nsym, nsym, ma, X[32:])
+    RefBlock("reference_signals", 8, P, N, con, NH, cr, cr, gi, tm, 0, 0).work(nsym, nsym, ma, X[32:])
     X = X[32 : 32 + nsym * N].reshape(nsym, N).copy()
     return dict(ic=ic, bi=bi, si=si, ma=ma, X=X, nsym=nsym, per_item=per_item)
 
 
-def rx_demod(Xf, con, cr, tm, sync_offsets=(0,)):
+def rx_demod(Xf, con, cr, tm, sync_offsets=(0,), gi=G1_32):
     """demod_reference_signals one item per call, two items visible, sync_start tags at the item
     offsets `sync_offsets` (what ofdm_sym_acquisition sends on every acquisition attempt; a tag on the
     item being parsed re-arms the wait for a superframe start, demod_reference_signals_impl.cc:96-150).
@@ -210,7 +212,7 @@ def rx_demod(Xf, con, cr, tm, sync_offsets=(0,)):
     buf = np.zeros((nsym + 1) * N + 64, np.complex64)
     buf[32 : 32 + nsym * N] = Xf.reshape(-1)
     Y = np.zeros(nsym * P, np.complex64)
-    b = RefBlock("demod_reference_signals", 8, N, P, con, NH, cr, cr, G1_32, tm, 0, 0)
+    b = RefBlock("demod_reference_signals", 8, N, P, con, NH, cr, cr, gi, tm, 0, 0)
     for off in sorted(set(int(o) for o in sync_offsets)):
         b.add_tag(off, "sync_start", 1)
     nout = 0
@@ -319,11 +321,11 @@ def rx_outer(vo, vtags, fixed_rs=False, min_calls=False):
     return cd, rd, out[:oo].copy()
 
 
-def rx_acquisition(x, tm, max_symbols=None):
+def rx_acquisition(x, tm, max_symbols=None, gi=G1_32):
     """ofdm_sym_acquisition one symbol per call with >= 2N+cp+16 samples visible
     (ofdm_sym_acquisition_impl.cc:488-568).  x: complex64 samples at the OFDM rate.
     Returns (symbols (nout, N) complex64, consumed samples, tags)."""
-    N, P, K, cp = mode_dims(tm)
+    N, P, K, cp = mode_dims(tm, gi)
     x = np.ascontiguousarray(x, np.complex64)
     pad = np.zeros(64, np.complex64)
     buf = np.concatenate([pad, x, pad])  # the reference reads in[-2] on initial acquisition (SURVEY 0.9)

@@ -12,7 +12,7 @@ def random_ts(npackets, seed):
     return ts.reshape(-1)
 
 
-def tx_frequency_domain(con, cr, tm, nsym_min, seed):
+def tx_frequency_domain(con, cr, tm, nsym_min, seed, gi=0):
     """Reference TX chain (verbatim reference blocks through oracle/_ref) up to the pilot insertion.
     Returns dict(ts, ci, X (nsym, N) complex64, plus the inner-chain intermediates)."""
     N, P, _, _ = R.mode_dims(tm)
@@ -22,7 +22,7 @@ def tx_frequency_domain(con, cr, tm, nsym_min, seed):
     npk = ((nsym_min + 8) * per_item // 204 // 8 + 3) * 8
     ts = random_ts(npk, seed)
     ed, rs, ci = R.tx_outer(ts)
-    tx = R.tx_inner(ci, con, cr, tm, nsym=(nsym_min + 3) // 4 * 4)
+    tx = R.tx_inner(ci, con, cr, tm, nsym=(nsym_min + 3) // 4 * 4, gi=gi)
     tx["ts"] = ts
     tx["ci"] = ci
     return tx
@@ -39,11 +39,11 @@ def channel(X, scale=0.01, noise=0.0, bin_shift=0, seed=0):
     return np.ascontiguousarray(Y)
 
 
-def ofdm_modulate(X, tm, gain=None, offset=0, cfo_bins=0.0, noise=0.0, seed=0):
+def ofdm_modulate(X, tm, gain=None, offset=0, cfo_bins=0.0, noise=0.0, seed=0, gi=0):
     """What the TX flowgraph does after reference_signals (apps/dvbt_tx_demo*.grc): fft_vxx(reverse,
     shift=True) = unnormalised inverse DFT of the half-swapped vector, cyclic prefix N/32,
     multiply_const.  Plus a test channel: `offset` leading samples, carrier offset in bins, AWGN."""
-    N, P, K, cp = R.mode_dims(tm)
+    N, P, K, cp = R.mode_dims(tm, gi)
     if gain is None:
         gain = 0.0022097087 if tm == R.T2k else 0.00055242272
     t = np.fft.ifft(np.fft.ifftshift(X.astype(np.complex128), axes=1), axis=1) * N
