@@ -55,11 +55,13 @@ extern "C" int emul_viterbi(const uint8_t *in, long long n_in, int rate, int m, 
   const int gfw = variant == 2 ? 32 : 16;
   const unsigned grid = (unsigned)((nchunks + bd - 1) / bd);
   std::vector<uint32_t> G((size_t)nchunks * gfw), F((size_t)nchunks * gfw), gr(gring ? (size_t)grid * ntb * 16 * bd : 1);
-  std::vector<uint8_t> bad((size_t)nchunks);
+  const int nch16 = (nchunks + 15) / 16 * 16;
+  std::vector<uint8_t> bad_store((size_t)nch16 * 5 + 16);
+  uint8_t *bad_base = (uint8_t *)(((uintptr_t)bad_store.data() + 15) & ~(uintptr_t)15);
   unsigned counters[4] = {0, 0, 0, 0};
   VitGeom g;
   g.codes = codes.data(); g.codes_stride = nbt; g.out = out; g.out_stride = 0;
-  g.G = G.data(); g.F = F.data(); g.prevF = nullptr; g.bad = bad.data(); g.counters = counters;
+  g.G = G.data(); g.F = F.data(); g.prevF = nullptr; g.bad = bad_base; g.counters = counters;
   g.nstreams = 1; g.nchunks = nchunks; g.L = L; g.W = W; g.ntb = ntb; g.nbt = (int)nbt; g.O0 = 0; g.O1 = O1; g.reset_at_0 = 1;
   g.neg1 = 0xffffffffu; g.two = 2u; g.one = 1u; g.ring_depth = depth; g.gring = gring ? gr.data() : nullptr; g.gf_words = gfw;
   if ((size_t)(kLutWords + (ntb + 16 * depth) * bd) > sizeof(smem) / 4 || (size_t)(kLutWords + ntb * kRowWords * 32) > sizeof(smem) / 4) return -1;
@@ -68,9 +70,21 @@ extern "C" int emul_viterbi(const uint8_t *in, long long n_in, int rate, int m, 
   else emul_acs<0>(gring, grid, (unsigned)bd, g);
   if (gfw == 32) emul_launch(vit_verify_kernel<32>, (unsigned)((nchunks + 63) / 64), 64u, g);
   else emul_launch(vit_verify_kernel<16>, (unsigned)((nchunks + 63) / 64), 64u, g);
-  if (variant == 2) emul_launch(vit_repair_kernel<2>, 1u, 32u, g);
-  else if (variant == 1) emul_launch(vit_repair_kernel<1>, 1u, 32u, g);
-  else emul_launch(vit_repair_kernel<0>, 1u, 32u, g);
+  // the repair as run_decode() launches it: `rounds` parallel rounds (DVBT_EMUL_REPAIR_ROUNDS, default 2), then the sequential kernel
+  {
+    const char *e = getenv("DVBT_EMUL_REPAIR_ROUNDS");
+    const int rounds = e ? atoi(e) : 2;
+    uint8_t *f0 = bad_base, *b1 = f0 + nch16, *c1 = f0 + 2 * nch16, *b2 = f0 + 3 * nch16, *c2 = f0 + 4 * nch16;
+    int left = -1;
+    const uint8_t *bad_last = f0, *chg_last = nullptr;
+    const unsigned rgrid = (unsigned)((nchunks + 31) / 32);
+#define EMUL_ROUND(V) \
+    if (rounds >= 1) { emul_launch(vit_repair_round_kernel<V>, rgrid, 32u, g, (const uint8_t *)f0, (const uint8_t *)nullptr, b1, c1, 2); bad_last = b1; chg_last = c1; left = 2; } \
+    if (rounds >= 2) { emul_launch(vit_repair_round_kernel<V>, rgrid, 32u, g, (const uint8_t *)b1, (const uint8_t *)c1, b2, c2, 3); bad_last = b2; chg_last = c2; left = 3; } \
+    emul_launch(vit_repair_kernel<V>, 1u, 32u, g, bad_last, chg_last, left);
+    if (variant == 2) { EMUL_ROUND(2) } else if (variant == 1) { EMUL_ROUND(1) } else { EMUL_ROUND(0) }
+#undef EMUL_ROUND
+  }
   for (int i = 0; i < 4; i++) counters_out[i] = counters[i];
   return 0;
 }
@@ -85,7 +99,7 @@ def device_text():
     # the banner of the host part trails the device part: cut after the namespace that holds the kernels
     text = text[: text.rindex("}  // namespace") + len("}  // namespace")] + "\n"
     text = text.replace("extern __shared__", "extern")
-    for needle in ("vit_acs_kernel(VitGeom g)", "vit_repair_kernel(VitGeom g)", "vit_verify_kernel(VitGeom g)", "vit_decode_range("):
+    for needle in ("vit_acs_kernel(VitGeom g)", "vit_repair_kernel(VitGeom g,", "vit_repair_round_kernel(VitGeom g,", "vit_verify_kernel(VitGeom g)", "vit_decode_range("):
         assert needle in text, "viterbi.cu changed shape: %r not in the extracted device part" % needle
     assert "cudaMalloc" not in text and "cudaStream" not in text
     return text

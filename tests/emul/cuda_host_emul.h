@@ -30,6 +30,7 @@ static thread_local emul_dim3 threadIdx, blockIdx;
 static emul_dim3 blockDim, gridDim;
 
 struct uint4 { uint32_t x, y, z, w; };   // not over-aligned: the host compiler then never assumes 16-byte alignment
+static inline uint4 make_uint4(uint32_t x, uint32_t y, uint32_t z, uint32_t w) { uint4 r; r.x = x; r.y = y; r.z = z; r.w = w; return r; }
 
 using std::max;
 using std::min;

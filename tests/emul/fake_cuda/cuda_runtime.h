@@ -21,7 +21,6 @@ static inline double2 make_double2(double x, double y) { return double2{x, y}; }
 static inline int2 make_int2(int x, int y) { return int2{x, y}; }
 static inline uint2 make_uint2(unsigned x, unsigned y) { return uint2{x, y}; }
 static inline int4 make_int4(int x, int y, int z, int w) { return int4{x, y, z, w}; }
-static inline uint4 make_uint4(unsigned x, unsigned y, unsigned z, unsigned w) { return uint4{x, y, z, w}; }
 
 // single / double operations with one rounding each (the TU is built with -ffp-contract=off)
 static inline float __fadd_rn(float a, float b) { return a + b; }

@@ -79,3 +79,21 @@ def test_split_survivor_ring_is_exact(emul, variant, rate, m, ber, depth):
     ref = O.Viterbi(m, rate).work(rx)
     out, st = emul(rx, rate, m, variant, L=80, W=40, bd=16, depth=depth)
     assert np.array_equal(out, ref)
+
+
+@pytest.mark.parametrize("rounds", [0, 1, 2])
+def test_parallel_repair_rounds_equal_sequential_repair(emul, rounds, monkeypatch):
+    """vit_repair_round_kernel re-decodes all bad chunks whose predecessor is settled at once; whatever the number of
+    rounds, the sequential kernel finishes the job: same bytes as the oracle with 0, 1 or 2 parallel rounds - with every
+    boundary bad (warm-up of one byte time: runs of consecutive bad chunks, worst case for the rounds) and with sparse
+    bad chunks (noisy input, short warm-up)"""
+    monkeypatch.setenv("DVBT_EMUL_REPAIR_ROUNDS", str(rounds))
+    rate, m = 4, 6
+    k, n = O.RATE_KN[rate]
+    data = np.random.default_rng(3).integers(0, 256, 40 * 96 * k, dtype=np.uint8)
+    for ber, W in ((0.0, 1), (0.01, 1), (0.012, 12), (0.02, 20)):
+        rx = O.flip_bits(O.conv_encode(data, m, rate), m, ber, 5)
+        want = O.Viterbi(m, rate).work(rx)
+        out, st = emul(rx, rate, m, "h16", L=96, W=W, bd=32)
+        assert np.array_equal(out, want), (rounds, ber, W)
+        assert st["flagged"] > 0 and st["repaired"] > 0, (rounds, ber, W, st)
