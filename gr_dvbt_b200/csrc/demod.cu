@@ -15,16 +15,17 @@
 // decision or an output keeps the reference's operand order and rounding (explicit
 // __f*_rn / __d*_rn, no FMA contraction; complex division as libgcc's __divsc3 does it for
 // float operands: straight formula in double), but the work is split:
-//   demod_stage1_kernel : one warp per symbol  - CFO sums (16 lanes), one-shot sums (2 lanes),
-//                                                rotor, scattered-pilot phase (4 lanes)
-//   demod_equalise_kernel: one block per symbol - pilot gains -> shared memory, interpolation,
-//                                                TPS carriers, payload cells (+ demap)
+//   demod_symbol_kernel : one block per symbol  - the symbol staged once by a bulk async copy (TMA engine); CFO
+//                                                products by all threads, the reference's sequential sums by warp 0
+//                                                (integer offset, one-shot estimate, rotor, scattered-pilot phase);
+//                                                pilot gains and slopes; TPS carriers, payload cells (+ demap)
 //   demod_vote_kernel   : one thread per symbol - TPS majority vote against the previous symbol
-//   demod_scan_kernel   : one thread            - the genuinely sequential part (symbol/frame
+//   demod_scan_kernel   : one block             - the genuinely sequential part (symbol/frame
 //                                                index, TPS FIFO, BCH, superframe gating)
-// HBM traffic per symbol: 2 x 8N B read (this + next symbol for the one-shot estimate; the
-// second read hits L2) and 8P (cells) + P (demapped) written.
+// HBM traffic per symbol: 8 (K + 17) B read once (+ 128 B around each continual pilot of the next symbol, L2 hits) and
+// P (demapped) written, + 8P when the caller wants the equalised cells.
 #include "demod.cuh"
+#include "bulk_copy.cuh"
 
 #include <math.h>
 #include <string.h>
@@ -126,6 +127,17 @@ int ModeTables::init(int tm, int gi) {
     if (n > d.pil_stride) { set_error("mode tables: %d pilots for phase %d", n, r); return DVBT_B200_EINVAL; }
     d.npil[r] = n;
   }
+  // The fused symbol kernel keeps pilot gains and interval slopes by pilot ORDINAL (their number, not the K carriers, sets
+  // the shared-memory footprint): payload entry = k | (k - k0) << 13 | ordinal(k0) << 17 with k0 the channel-estimation
+  // carrier at or below k; the same for the TPS carriers; and for every pilot the ordinal of the next one up.
+  std::vector<int> pay3(4 * P), tps3(4 * d.ntps);
+  std::vector<short> ordk(4 * K, 0);
+  for (int r = 0; r < 4; r++) {
+    for (int i = 0; i < d.npil[r]; i++) ordk[r * K + pil[(size_t)r * d.pil_stride + i]] = (short)i;
+    auto pack = [&](int k) { int k0 = prevp[r * K + k]; return k | ((k - k0) << 13) | ((int)ordk[r * K + k0] << 17); };
+    for (int i = 0; i < P; i++) pay3[r * P + i] = pack(payload[r * P + i]);
+    for (int i = 0; i < d.ntps; i++) tps3[r * d.ntps + i] = pack(tpl[i]);
+  }
   // symbol interleaver H(q) (symbol_inner_interleaver_impl.cc:35-96)
   std::vector<short> H(P), Hinv(P);
   {
@@ -158,7 +170,8 @@ int ModeTables::init(int tm, int gi) {
   auto place = [&](size_t bytes) { size_t o = off; off += (bytes + 15) & ~(size_t)15; return o; };
   size_t o_cp = place(cpl.size() * 2), o_tps = place(tpl.size() * 2), o_known = place(known.size() * 4), o_pval = place(pval.size() * 4),
          o_kind = place(kind.size()), o_prev = place(prevp.size() * 2), o_next = place(nextp.size() * 2), o_pay = place(payload.size() * 2),
-         o_H = place(H.size() * 2), o_Hi = place(Hinv.size() * 2), o_pil = place(pil.size() * 2), o_pay32 = place(pay32.size() * 4);
+         o_H = place(H.size() * 2), o_Hi = place(Hinv.size() * 2), o_pil = place(pil.size() * 2), o_pay32 = place(pay32.size() * 4),
+         o_pay3 = place(pay3.size() * 4), o_tps3 = place(tps3.size() * 4);
   std::vector<unsigned char> host(off);
   memcpy(&host[o_cp], cpl.data(), cpl.size() * 2);
   memcpy(&host[o_tps], tpl.data(), tpl.size() * 2);
@@ -172,6 +185,8 @@ int ModeTables::init(int tm, int gi) {
   memcpy(&host[o_Hi], Hinv.data(), Hinv.size() * 2);
   memcpy(&host[o_pil], pil.data(), pil.size() * 2);
   memcpy(&host[o_pay32], pay32.data(), pay32.size() * 4);
+  memcpy(&host[o_pay3], pay3.data(), pay3.size() * 4);
+  memcpy(&host[o_tps3], tps3.data(), tps3.size() * 4);
   int rc = blob.reserve(off);
   if (rc) return rc;
   DVBT_CUDA_TRY(cudaMemcpy(blob.p, host.data(), off, cudaMemcpyHostToDevice));
@@ -188,6 +203,8 @@ int ModeTables::init(int tm, int gi) {
   d.Hinv = (const short *)(base + o_Hi);
   d.pilots = (const short *)(base + o_pil);
   d.pay32 = (const int *)(base + o_pay32);
+  d.pay3 = (const int *)(base + o_pay3);
+  d.tps3 = (const int *)(base + o_tps3);
   return 0;
 }
 
@@ -211,149 +228,165 @@ __device__ __forceinline__ float2 cdiv(float2 n, float2 d) {
 }
 
 // ---------------------------------------------------------------------------------------
-// stage 1: one warp per symbol
+// one block per symbol: everything parse_input does to a symbol except the sequential bookkeeping
 // ---------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) demod_stage1_kernel(ModeDev md, const float2 *__restrict__ X, int nparse,
-                                                           int *__restrict__ fo_out, float2 *__restrict__ rot_out,
-                                                           int *__restrict__ mod_out) {
-  int s = (int)((blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5);
-  int lane = threadIdx.x & 31;
-  if (s >= nparse) return;
-  const float2 *x0 = X + (long long)s * md.N;
-  const float2 *x1 = x0 + md.N;
-  // ---- process_cpilot_data (:714-744): lanes 0..15 hold candidate i = zl - 8 + lane
-  float sum = 0.f;
-  if (lane < 16) {
-    int i = md.zl - 8 + lane;
-    float2 prev = x0[i + md.cpilot[0]];
-    for (int j = 0; j < md.ncp - 1; j++) {
-      float2 cur = x0[i + md.cpilot[j + 1]];
-      float phase = cnorm(csub(cur, prev));
-      sum = __fadd_rn(sum, __fmul_rn(md.known[j], phase));
-      prev = cur;
+// The symbol's active carriers (K + 16 around them for the 16 integer-CFO candidates) are staged in shared memory ONCE by
+// a bulk asynchronous copy (cp.async.bulk / TMA engine, bulk_copy.cuh) - 8 (K + 17) bytes per symbol instead of the three
+// passes over global memory the separate stage-1 and equalise kernels made - while the threads fetch the only other
+// input, the next symbol's carriers around the continual pilots (16 x ncp values, one-shot estimate).  Then:
+//   all threads   products of process_cpilot_data (:714-744), 16 candidates x (ncp - 1) pilot pairs
+//   warp 0        the sequential sums the reference's loops define (same operand order: bit-identical floats) - 16 lanes =
+//                 the 16 candidates; first-strict-maximum scan -> integer offset; compute_oneshot_csft (:746-790): terms by all
+//                 lanes, the two half sums by lanes 0 / 1; rotor (:792-819); scattered-pilot phase (:547-582): 40 terms, 4 sums
+//   all threads   pilot gains tx / rx (:484-489; complex division as libgcc's __divsc3), interval slopes with the reference's
+//                 constant /11 (:617-642) - kept by pilot ordinal, not by carrier
+//   all threads   TPS carriers (:929-945) and payload cells (:1104-1113), four consecutive cells per thread: one 16-byte
+//                 table load, gains interpolated where they are used, fused demap, ONE 4-byte store of the four demapped
+//                 cells (and two 16-byte stores of the equalised cells when the caller wants them)
+constexpr int kSymThreads = 384;
+
+__global__ void __launch_bounds__(kSymThreads) demod_symbol_kernel(ModeDev md, const __grid_constant__ DemapTable dt, int do_demap, int use_bulk,
+                                                                   const float2 *__restrict__ X, int *__restrict__ fo_out,
+                                                                   float2 *__restrict__ rot_out, int *__restrict__ mod_out,
+                                                                   float2 *__restrict__ tpsval, float2 *__restrict__ Y,
+                                                                   uint8_t *__restrict__ dm) {
+  extern __shared__ __align__(16) unsigned char s_sym[];
+  __shared__ uint64_t s_bar;
+  __shared__ int s_fo, s_mod;
+  __shared__ float2 s_rot;
+  const int s = blockIdx.x, t = threadIdx.x, lane = t & 31;
+  const int K = md.K, ncp = md.ncp, nxs = K + 17;
+  float2 *xs = reinterpret_cast<float2 *>(s_sym);                  // xs[i] = X[s][zl - 8 + i]
+  float2 *x1seg = xs + ((nxs + 1) & ~1);                           // [ncp][16]: next symbol at zl - 8 + cpilot[j] + 0..15
+  float *prod = reinterpret_cast<float *>(x1seg + ncp * 16);       // [ncp - 1][16]
+  float2 *t1 = reinterpret_cast<float2 *>(prod + 16 * ncp);        // [ncp] one-shot terms
+  float2 *sp = t1 + ncp;                                           // [40] scattered-pilot terms
+  float2 *gain = sp + 40;                                          // [npil] by pilot ordinal
+  float2 *slope = gain + md.pil_stride;
+  const float2 *x0g = X + (long long)s * md.N + md.zl - 8;
+  const float2 *x1g = x0g + md.N;
+  if (t == 0) mbar_init(&s_bar, 1);
+  __syncthreads();
+  if (use_bulk && t == 0) bulk_g2s(xs, x0g, (unsigned)nxs * 8u, &s_bar);
+  for (int i = t; i < ncp * 16; i += kSymThreads) x1seg[i] = x1g[md.cpilot[i >> 4] + (i & 15)];
+  if (use_bulk) {
+    mbar_wait(&s_bar, 0);
+  } else {   // the caller's buffer is not 16-byte aligned: plain loads
+    for (int i = t; i < nxs; i += kSymThreads) xs[i] = x0g[i];
+  }
+  __syncthreads();
+  // ---- process_cpilot_data (:714-744): candidate l <-> offset l - 8
+  for (int i = t; i < 16 * (ncp - 1); i += kSymThreads) {
+    const int j = i >> 4, l = i & 15;
+    const float2 prev = xs[l + md.cpilot[j]], cur = xs[l + md.cpilot[j + 1]];
+    prod[i] = __fmul_rn(md.known[j], cnorm(csub(cur, prev)));
+  }
+  __syncthreads();
+  if (t < 32) {
+    float sum = 0.f;
+    if (lane < 16)
+      for (int j = 0; j < ncp - 1; j++) sum = __fadd_rn(sum, prod[16 * j + lane]);
+    float best = 0.f;
+    int start = 0;
+    for (int l = 0; l < 16; l++) {  // sequential first-strict-maximum scan
+      float v = __shfl_sync(0xffffffffu, sum, l);
+      if (v > best) { best = v; start = md.zl - 8 + l; }
+    }
+    // all-zero input leaves start = 0 in the reference (offset -zl, out-of-bounds reads there); a zero offset is used instead
+    const int fo = (best > 0.f) ? start - md.zl : 0;
+    const float2 *x = xs + 8 + fo;                                 // x[k] = carrier k of this symbol, integer offset applied
+    // ---- compute_oneshot_csft (:746-790): terms by all lanes, left half by lane 0, right half by lane 1
+    for (int j = lane; j < ncp; j += 32) t1[j] = cmul_conj(x[md.cpilot[j]], x1seg[16 * j + 8 + fo]);
+    __syncwarp();
+    float angle = 0.f;
+    if (lane < 2) {
+      const int half = (ncp - 1) / 2;
+      const int j0 = lane == 0 ? 0 : half + 1, j1 = lane == 0 ? half : ncp;
+      float2 acc = make_float2(0.f, 0.f);
+      for (int j = j0; j < j1; j++) acc = cadd(acc, t1[j]);
+      angle = atan2f(acc.y, acc.x);
+    }
+    const float left = __shfl_sync(0xffffffffu, angle, 0), right = __shfl_sync(0xffffffffu, angle, 1);
+    const float corr = __fmul_rn(__fadd_rn(right, left), md.carrier_coeff);
+    // ---- frequency_correction (:792-819): one rotor for the whole symbol
+    const float correction = __fadd_rn((float)fo, corr);
+    const double ang = __ddiv_rn(__dmul_rn(__dmul_rn(-2.0 * M_PI, (double)correction), (double)(md.N + md.cp)), (double)md.N);
+    float sn, cs;
+    sincosf((float)ang, &sn, &cs);
+    const float2 rot = make_float2(cs, sn);
+    // ---- process_spilot_data, phase detection (:547-582): candidate phase p, pilot j -> term 10 p + j
+    for (int i = lane; i < 40; i += 32) {
+      const int k = 3 * (i / 10) + 12 * (i % 10);
+      sp[i] = cmul_conj(make_float2(md.pval[k], 0.f), cmul(rot, x[k]));
+    }
+    __syncwarp();
+    float ssum = 0.f;
+    if (lane < 4) {
+      float2 c = make_float2(0.f, 0.f);
+      for (int j = 0; j < 10; j++) c = cadd(c, sp[10 * lane + j]);
+      ssum = cnorm(c);
+    }
+    float smax = 0.f;
+    int mod = -1;  // -1: no candidate exceeded 0, the reference keeps the previous value
+    for (int l = 0; l < 4; l++) {
+      float v = __shfl_sync(0xffffffffu, ssum, l);
+      if (v > smax) { smax = v; mod = l; }
+    }
+    if (lane == 0) {
+      s_fo = fo; s_mod = mod; s_rot = rot;
+      fo_out[s] = fo;
+      rot_out[s] = rot;
+      mod_out[s] = mod;
     }
   }
-  float best = 0.f;
-  int start = 0;
-  for (int l = 0; l < 16; l++) {  // sequential first-strict-maximum scan
-    float v = __shfl_sync(0xffffffffu, sum, l);
-    if (v > best) { best = v; start = md.zl - 8 + l; }
+  __syncthreads();
+  const int fo = s_fo;
+  const float2 rot = s_rot;
+  int r = s_mod;
+  if (r < 0) r = 0;  // degenerate all-zero symbol; the scan resolves the index bookkeeping
+  const float2 *x = xs + 8 + fo;
+  // ---- pilot gains: gain = tx / rx (:484-489 set_channel_gain), then the slope of every pilot interval (:617-642)
+  const short *pil = md.pilots + r * md.pil_stride;
+  const int npil = md.npil[r];
+  for (int i = t; i < npil; i += kSymThreads) {
+    const int k = pil[i];
+    gain[i] = cdiv(make_float2(md.pval[k], 0.f), cmul(rot, x[k]));
   }
-  // all-zero input leaves start = 0 in the reference (offset -zl, out-of-bounds reads there);
-  // a zero offset is used instead
-  int fo = (best > 0.f) ? start - md.zl : 0;
-  // ---- compute_oneshot_csft (:746-790): lane 0 = left half, lane 1 = right half
-  float angle = 0.f;
-  if (lane < 2) {
-    int half = (md.ncp - 1) / 2;
-    int j0 = lane == 0 ? 0 : half + 1, j1 = lane == 0 ? half : md.ncp;
-    float2 acc = make_float2(0.f, 0.f);
-    for (int j = j0; j < j1; j++) {
-      int idx = fo + md.zl + md.cpilot[j];
-      acc = cadd(acc, cmul_conj(x0[idx], x1[idx]));
+  __syncthreads();
+  for (int i = t; i < npil; i += kSymThreads) {
+    const int nx = i + 1 < npil ? i + 1 : i;                       // the last pilot (carrier Kmax) closes its own interval
+    slope[i] = cdiv(csub(gain[nx], gain[i]), make_float2(11.0f, 0.0f));
+  }
+  __syncthreads();
+  // gain of a data carrier: g[k0] + (k - k0) * slope[k0], k0 the channel-estimation carrier below (same operations in the
+  // same order as the reference's loop over the interval, so the same floats)
+  auto cell = [&](int e) {
+    const int k = e & 0x1fff, dk = (e >> 13) & 15, o = e >> 17;
+    const float2 g = cadd(gain[o], cmul(slope[o], make_float2((float)dk, 0.0f)));
+    return cmul(cmul(rot, x[k]), g);
+  };
+  if (t < md.ntps) tpsval[(long long)s * md.ntps + t] = cell(md.tps3[r * md.ntps + t]);   // :929-945
+  const int4 *pay = reinterpret_cast<const int4 *>(md.pay3 + r * md.P);
+  for (int q = t; q < md.P / 4; q += kSymThreads) {                // :1104-1113
+    const int4 e = pay[q];
+    const float2 c0 = cell(e.x), c1 = cell(e.y), c2 = cell(e.z), c3 = cell(e.w);
+    const long long o = (long long)s * md.P + 4 * q;
+    if (Y) {
+      float4 *yo = reinterpret_cast<float4 *>(Y + o);
+      yo[0] = make_float4(c0.x, c0.y, c1.x, c1.y);
+      yo[1] = make_float4(c2.x, c2.y, c3.x, c3.y);
     }
-    angle = atan2f(acc.y, acc.x);
-  }
-  float left = __shfl_sync(0xffffffffu, angle, 0), right = __shfl_sync(0xffffffffu, angle, 1);
-  float corr = __fmul_rn(__fadd_rn(right, left), md.carrier_coeff);
-  // ---- frequency_correction (:792-819): one rotor for the whole symbol
-  float correction = __fadd_rn((float)fo, corr);
-  double ang = __ddiv_rn(__dmul_rn(__dmul_rn(-2.0 * M_PI, (double)correction), (double)(md.N + md.cp)), (double)md.N);
-  float sn, cs;
-  sincosf((float)ang, &sn, &cs);
-  float2 rot = make_float2(cs, sn);
-  // ---- process_spilot_data, phase detection (:547-582): lanes 0..3 = candidate phase
-  float ssum = 0.f;
-  if (lane < 4) {
-    float2 c = make_float2(0.f, 0.f);
-    for (int j = 0; j < 10; j++) {
-      int k = 3 * lane + 12 * j;
-      float2 dv = cmul(rot, x0[md.zl + k + fo]);
-      c = cadd(c, cmul_conj(make_float2(md.pval[k], 0.f), dv));
+    if (do_demap) {
+      const uint32_t d = (uint32_t)demap_cell_any(dt, c0) | ((uint32_t)demap_cell_any(dt, c1) << 8) | ((uint32_t)demap_cell_any(dt, c2) << 16) |
+                         ((uint32_t)demap_cell_any(dt, c3) << 24);
+      *reinterpret_cast<uint32_t *>(dm + o) = d;
     }
-    ssum = cnorm(c);
-  }
-  float smax = 0.f;
-  int mod = -1;  // -1: no candidate exceeded 0, the reference keeps the previous value
-  for (int l = 0; l < 4; l++) {
-    float v = __shfl_sync(0xffffffffu, ssum, l);
-    if (v > smax) { smax = v; mod = l; }
-  }
-  if (lane == 0) {
-    fo_out[s] = fo;
-    rot_out[s] = rot;
-    mod_out[s] = mod;
   }
 }
 
-// ---------------------------------------------------------------------------------------
-// stage 2: one block per symbol — gains, interpolation, TPS carriers, payload (+ demap)
-// ---------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) demod_equalise_kernel(ModeDev md, const __grid_constant__ DemapTable dt, int do_demap,
-                                                             const float2 *__restrict__ X, const int *__restrict__ fo_in,
-                                                             const float2 *__restrict__ rot_in, const int *__restrict__ mod_in,
-                                                             float2 *__restrict__ tpsval, float2 *__restrict__ Y,
-                                                             uint8_t *__restrict__ dm) {
-  extern __shared__ float2 s_gain[];  // [K] gains, then [K] interval slopes
-  const int s = blockIdx.x;
-  const int fo = fo_in[s];
-  const float2 rot = rot_in[s];
-  int r = mod_in[s];
-  if (r < 0) r = 0;  // degenerate all-zero symbol; the scan resolves the index bookkeeping
-  const float2 *x = X + (long long)s * md.N + md.zl + fo;
-  const unsigned char *kind = md.kind + r * md.K;
-  // pilot gains: gain = tx / rx (:484-489 set_channel_gain)
-  const short *pil = md.pilots + r * md.pil_stride;
-  const int npil = md.npil[r];
-  for (int i = threadIdx.x; i < npil; i += blockDim.x) {
-    int k = pil[i];
-    s_gain[k] = cdiv(make_float2(md.pval[k], 0.f), cmul(rot, x[k]));
-  }
-  __syncthreads();
-  // linear interpolation with the reference's fixed /11 slope (:617-642): the slope of an interval
-  // is computed once, by the thread that owns the pilot at its left end
-  const short *prevp = md.prevp + r * md.K, *nextp = md.nextp + r * md.K;
-  float2 *s_slope = s_gain + md.K;
-  for (int i = threadIdx.x; i < npil; i += blockDim.x) {
-    int k = pil[i];
-    s_slope[k] = cdiv(csub(s_gain[nextp[k]], s_gain[k]), make_float2(11.0f, 0.0f));
-  }
-  __syncthreads();
-  // The gain of a data carrier is interpolated where it is used: g[k0] + (k - k0) * slope[k0] with k0 the channel-estimation
-  // carrier below k (:617-642: same operations in the same order as the reference's loop over the interval, so the same
-  // floats; materialising all K gains first cost a pass over the carriers with two table loads each and a barrier)
-  auto gain_at = [&](int k0, int dk) {
-    float2 step = cmul(s_slope[k0], make_float2((float)dk, 0.0f));
-    return cadd(s_gain[k0], step);
-  };
-  if (threadIdx.x < md.ntps) {  // :929-945
-    int k = md.tps[threadIdx.x];
-    int k0 = prevp[k];
-    tpsval[(long long)s * md.ntps + threadIdx.x] = cmul(cmul(rot, x[k]), gain_at(k0, k - k0));
-  }
-  const int *pay = md.pay32 + r * md.P;
-  for (int ib = threadIdx.x; ib < md.P; ib += 3 * blockDim.x) {  // :1104-1113
-    int k[3], dk[3];
-    float2 xv[3];
-#pragma unroll
-    for (int u = 0; u < 3; u++) {
-      int i = ib + u * blockDim.x;
-      int e = i < md.P ? pay[i] : (1 << 16);
-      k[u] = e & 0xffff;
-      dk[u] = e >> 16;
-    }
-#pragma unroll
-    for (int u = 0; u < 3; u++) xv[u] = x[k[u]];
-#pragma unroll
-    for (int u = 0; u < 3; u++) {
-      int i = ib + u * blockDim.x;
-      if (i < md.P) {
-        float2 y = cmul(cmul(rot, xv[u]), gain_at(k[u] - dk[u], dk[u]));
-        if (Y) Y[(long long)s * md.P + i] = y;
-        if (do_demap) dm[(long long)s * md.P + i] = demap_cell_any(dt, y);
-      }
-    }
-  }
+size_t demod_symbol_smem(const ModeDev &md) {
+  const size_t nxs = (size_t)md.K + 17;
+  return ((nxs + 1) & ~(size_t)1) * 8 + (size_t)md.ncp * 16 * 8 + (size_t)md.ncp * 16 * 4 + (size_t)md.ncp * 8 + 40 * 8 + (size_t)md.pil_stride * 16 + 64;
 }
 
 // TPS DBPSK majority vote against the previous symbol (:929-948).  The low half of vote[s] is the vote (|v| <= 68);
@@ -631,20 +664,17 @@ int demod_run(const ModeDev &md, const DemapTable *demap, const float2 *X, int n
               int fi_start, int sync_start_at0, float2 *Y, uint8_t *dm, cudaStream_t st, const int *sync_at, int nsync, int src_base) {
   if (nparse <= 0) return 0;
   {
-    int threads = 128;
-    long long total = (long long)nparse * 32;
-    demod_stage1_kernel<<<(unsigned)((total + threads - 1) / threads), threads, 0, st>>>(md, X, nparse, b.fo, b.rot, b.modidx);
-    DVBT_CUDA_TRY(cudaGetLastError());
-  }
-  {
-    size_t smem = (size_t)md.K * sizeof(float2) * 2;
+    const size_t smem = demod_symbol_smem(md);
     // per launch, like every other kernel of the library: the attribute is per device and handles live on any device
-    DVBT_CUDA_TRY(cudaFuncSetAttribute(demod_equalise_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
+    DVBT_CUDA_TRY(cudaFuncSetAttribute(demod_symbol_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     DemapTable dummy;
     dummy.size = 0;
+    // bulk copies and the vector stores want 16-byte aligned buffers (every buffer of this library is; a caller's may not be)
+    const int aligned = (((uintptr_t)X & 15) == 0) ? 1 : 0;
+    if ((Y && ((uintptr_t)Y & 15)) || (dm && ((uintptr_t)dm & 3))) { set_error("demod: output buffers must be 16-byte (cells) / 4-byte (demapped) aligned"); return DVBT_B200_EINVAL; }
     if (b.ev_eq0) DVBT_CUDA_TRY(cudaEventRecord(b.ev_eq0, st));
-    demod_equalise_kernel<<<nparse, 256, smem, st>>>(md, demap ? *demap : dummy, (demap && dm) ? 1 : 0, X, b.fo, b.rot, b.modidx,
-                                                    b.tpsval, Y, dm);
+    demod_symbol_kernel<<<nparse, kSymThreads, smem, st>>>(md, demap ? *demap : dummy, (demap && dm) ? 1 : 0, aligned, X, b.fo, b.rot, b.modidx,
+                                                          b.tpsval, Y, dm);
     DVBT_CUDA_TRY(cudaGetLastError());
     if (b.ev_eq1) DVBT_CUDA_TRY(cudaEventRecord(b.ev_eq1, st));
   }
@@ -652,7 +682,7 @@ int demod_run(const ModeDev &md, const DemapTable *demap, const float2 *X, int n
   DVBT_CUDA_TRY(cudaGetLastError());
   demod_scan_kernel<<<1, 32 * kScanWarps, 0, st>>>(md.ntps, nparse, fi_start, src_base, b.modidx, b.vote, b.tpsval, d_state, b.out_symidx, b.out_src);
   DVBT_CUDA_TRY(cudaGetLastError());
-  count_launch(4);
+  count_launch(3);
   return 0;
 }
 

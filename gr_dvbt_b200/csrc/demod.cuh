@@ -157,6 +157,8 @@ struct ModeDev {
   const short *nextp;      // [4][K] nearest channel-estimation carrier  > k
   const short *payload;    // [4][P] payload carriers in increasing order
   const int *pay32;        // [4][P] the same with the distance to the channel-estimation carrier below: k | (k - prevp[k]) << 16
+  const int *pay3;         // [4][P] payload carrier k | (k - k0) << 13 | ordinal of k0 among the phase's pilots << 17
+  const int *tps3;         // [4][ntps] the same for the TPS carriers
   const short *H;          // [P] symbol interleaver permutation H(q) (symbol_inner_interleaver_impl.cc:35-96)
   const short *Hinv;       // [P]
   const short *pilots;     // [4][pil_stride] channel-estimation carriers of scattered phase r, increasing

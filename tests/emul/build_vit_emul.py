@@ -269,7 +269,6 @@ DEMAP_SHIM = r'''
 #include <math.h>
 #include "../../../include/dvbt_b200.h"
 struct float2 { float x, y; };
-struct float4 { float x, y, z, w; };
 struct uchar4 { unsigned char x, y, z, w; };
 static inline float2 make_float2(float x, float y) { return float2{x, y}; }
 // round-to-nearest single operations: plain operators (the TU is built with -ffp-contract=off, SSE arithmetic)
@@ -362,8 +361,7 @@ extern "C" int emul_demod(const float *Xf, int nsym, int constellation, int tm, 
   std::vector<float2> rot(nparse), tps((size_t)nparse * md.ntps);
   DemodState st;
   memset(&st, 0, sizeof st);
-  emul_launch(demod_stage1_kernel, (unsigned)(((long long)nparse * 32 + 127) / 128), 128u, md, X, nparse, fo.data(), rot.data(), mod.data());
-  emul_launch(demod_equalise_kernel, (unsigned)nparse, 256u, md, dt, 1, X, (const int *)fo.data(), (const float2 *)rot.data(), (const int *)mod.data(),
+  emul_launch(demod_symbol_kernel, (unsigned)nparse, (unsigned)kSymThreads, md, dt, 1, (int)((((uintptr_t)X) & 15) == 0), X, fo.data(), rot.data(), mod.data(),
               tps.data(), (float2 *)Y_out, dm_out);
   emul_launch(demod_vote_kernel, (unsigned)((nparse + 127) / 128), 128u, md.ntps, nparse, (const float2 *)tps.data(), &st, vote.data(),
               sync_start_at0, (const int *)nullptr, 0);
@@ -374,6 +372,18 @@ extern "C" int emul_demod(const float *Xf, int nsym, int constellation, int tm, 
   tabs.release();
   return 0;
 }
+'''
+
+
+# bulk_copy.cuh for the host: the bulk asynchronous copy is a memcpy that has landed when the call returns, the mbarrier
+# is a no-op (the block barrier that follows in every user orders the threads)
+BULK_COPY_HOST = r'''
+#include <string.h>
+namespace dvbt {
+static inline void mbar_init(uint64_t *bar, unsigned) { *bar = 0; }
+static inline void bulk_g2s(void *smem_dst, const void *gmem_src, unsigned bytes, uint64_t *) { memcpy(smem_dst, gmem_src, bytes); }
+static inline void mbar_wait(uint64_t *, unsigned) {}
+}  // namespace dvbt
 '''
 
 
@@ -389,11 +399,11 @@ def build_demod(force=False):
     dm = dm[dm.index("namespace dvbt {"): dm.index("__device__ __forceinline__ uint8_t demap_cell(")] + "}  // namespace dvbt\n"
     src = open(os.path.join(CSRC, "demod.cu")).read()
     body = src[src.index("namespace dvbt {"): src.index("int demod_run(")] + "}  // namespace dvbt\n"
-    for needle in ("demod_stage1_kernel(", "demod_equalise_kernel(", "demod_vote_kernel(", "demod_scan_kernel(", "ModeTables::init("):
+    for needle in ("demod_symbol_kernel(", "demod_vote_kernel(", "demod_scan_kernel(", "ModeTables::init("):
         assert needle in body, "demod.cu changed shape: %r" % needle
     tu = ('// GENERATED by tests/emul/build_vit_emul.py from gr_dvbt_b200/csrc/demod.cu, demod.cuh, demap.cu -- test infrastructure\n'
-          '#include "../cuda_host_emul.h"\n' + DEMAP_SHIM + DEMOD_SHIM + hdr + dm
-          + 'namespace dvbt { alignas(16) float2 s_gain[1 << 15]; }   // the dynamic shared memory of the running block\n'
+          '#include "../cuda_host_emul.h"\n' + BULK_COPY_HOST + DEMAP_SHIM + DEMOD_SHIM + hdr + dm
+          + 'namespace dvbt { alignas(16) unsigned char s_sym[1 << 18]; }   // the dynamic shared memory of the running block\n'
           + body.replace("extern __shared__", "extern") + DEMOD_LAUNCHER)
     path = os.path.join(BUILD, "demod_emul.cpp")
     open(path, "w").write(tu)
@@ -468,6 +478,9 @@ def build_whole(libname, files, force=False, extra_flags=()):
         if not h.endswith(".cuh"):
             continue
         t = open(os.path.join(CSRC, h)).read()
+        if h == "bulk_copy.cuh":   # inline PTX only: the host version (a synchronous copy is one of its legal executions)
+            open(os.path.join(wdir, h), "w").write("#pragma once\n#include <stdint.h>\n" + BULK_COPY_HOST)
+            continue
         if h == "viterbi_acs_gen.cuh":
             t, n1 = re.subn(r'asm\("prmt\.b32 [^;]*;"[^;]*;', "r = emul_prmt(a, b, sel);", t)
             t, n2 = re.subn(r'asm\("mad\.lo\.u32 [^;]*;"[^;]*;', "r = a * b + c;", t)

@@ -7,20 +7,16 @@
 #include <math.h>
 
 struct float2 { float x, y; };
-struct float4 { float x, y, z, w; };
 struct double2 { double x, y; };
 struct int2 { int x, y; };
 struct uint2 { unsigned x, y; };
-struct int4 { int x, y, z, w; };
 struct dim3 { unsigned x = 1, y = 1, z = 1; dim3(unsigned a = 1, unsigned b = 1, unsigned c = 1) : x(a), y(b), z(c) {} };
 struct uchar4 { unsigned char x, y, z, w; };
 struct char4 { signed char x, y, z, w; };
 static inline float2 make_float2(float x, float y) { return float2{x, y}; }
-static inline float4 make_float4(float x, float y, float z, float w) { return float4{x, y, z, w}; }
 static inline double2 make_double2(double x, double y) { return double2{x, y}; }
 static inline int2 make_int2(int x, int y) { return int2{x, y}; }
 static inline uint2 make_uint2(unsigned x, unsigned y) { return uint2{x, y}; }
-static inline int4 make_int4(int x, int y, int z, int w) { return int4{x, y, z, w}; }
 
 // single / double operations with one rounding each (the TU is built with -ffp-contract=off)
 static inline float __fadd_rn(float a, float b) { return a + b; }
