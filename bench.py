@@ -826,6 +826,11 @@ def main():
         if sampler:
             r["clocks"] = sampler.stop()
         r["launches"] = (lib.dvbt_b200_kernel_launches() - l1) // steps
+        # the same stage clocks with the captures in flight: CUDA-event spans on each handle's stream, which now include
+        # the time a kernel shares the GPU with the other captures' kernels (e.g. the ACS kernel's survivor-ring
+        # write-through beside the HBM-bound resampler / FFT of another capture)
+        infl = [h.info() for h in w.rx2[: w.NCONC]]
+        r["stage_in_flight"] = {k: float(np.mean([i[k] for i in infl])) for k in infl[0] if k.startswith("ms_")}
         barrier()
         same = bool(all(b == w.ts_bytes for b in w.pair_bytes) and all(w.torch.equal(w.d_ts2[0][: w.ts_bytes], t[: w.ts_bytes]) for t in w.d_ts2[1:]))
         r["ok"] = bool(r["ok"] and same)
@@ -881,7 +886,7 @@ def main():
             "data": "synthetic (seeded random TS -> reference TX blocks -> IFFT/CP -> 35/32 resampler -> 10 Msps capture, no added noise; robustness.* adds AWGN)",
             "chain_info": {k: v for k, v in info.items() if not k.startswith("ms_")},
             "viterbi_mbit_per_s": vbits * w.NCONC * WORLD / (head["ms_pair"] / 1e3) / 1e6,
-            "realtime_factor": value / WORLD / 10.0, "stage_ms": stage,
+            "realtime_factor": value / WORLD / 10.0, "stage_ms": stage, "stage_ms_in_flight": head.get("stage_in_flight"),
             "one_capture_at_a_time": {"ms_per_capture": head["ms_single"], "value": units / (head["ms_single"] / 1e3),
                                       "note": "one capture at a time on one handle (one stream): the stage_ms / roofline kernel times are measured in this leg "
                                               "with CUDA events; `value` is the same chain with %d captures in flight" % w.NCONC},
@@ -1053,6 +1058,17 @@ def viterbi_sweep(g, torch, timed, barrier):
 
 
 def drop_in_leg(g, w):
+    """the leg below at the shims' work-item size (64 symbols per call) and at 512 (what a flowgraph with larger buffers gets)"""
+    res = drop_in_leg_at(g, w, 64)
+    try:
+        big = drop_in_leg_at(g, w, 512)
+        res["items_per_call_512"] = {k: big[k] for k in ("blocks", "pipelined_msamples_per_s", "serial_msamples_per_s", "realtime_factor_pipelined")}
+    except Exception as e:
+        res["items_per_call_512"] = {"error": repr(e)[:200]}
+    return res
+
+
+def drop_in_leg_at(g, w, IPC):
     """What a gr-dvbt flowgraph gets with the five hot blocks swapped for the shims: the block-level `*_work` entry points
     (include/dvbt_b200.h) called the way the GNU Radio scheduler calls them - pageable host buffers, one call per work item
     batch (sizes: the shims' set_min_noutput_items / output multiples), H2D + kernels + D2H + stream sync inside every call.
@@ -1061,7 +1077,7 @@ def drop_in_leg(g, w):
     import ctypes as C
     from gr_dvbt_b200 import capi
     N, P, cp = w.N, w.P, w.N // 32
-    nsym = 2176
+    nsym = max(2176, 8 * IPC)
     total = N + cp
     # baseband for acquisition: the front end (a stock GNU Radio block in the flowgraph) run once on the GPU
     ncap = (nsym + 8) * total * 35 // 32 + 4000
@@ -1079,41 +1095,41 @@ def drop_in_leg(g, w):
     # ofdm_sym_acquisition (+ FFT folded in, as the shim does with apply_fft): 64 symbols per call (shim: set_min_noutput_items(64))
     acq = g.ofdm_sym_acquisition(1, N, w.N * 0 + (1705 if N == 2048 else 6817), cp, 30.0)
     pos, syms, calls, t = 0, [], 0, 0.0
-    while len(syms) < nsym // 64 and pos + 66 * total < len(bb):
-        chunk = bb[pos: pos + 2 * N + cp + 32 + 63 * total]
+    while len(syms) < nsym // IPC and pos + (IPC + 2) * total < len(bb):
+        chunk = bb[pos: pos + 2 * N + cp + 32 + (IPC - 1) * total]
         t0 = time.perf_counter()
-        o, cons, _tags = acq.general_work(chunk, out_capacity=64, apply_fft=True)
+        o, cons, _tags = acq.general_work(chunk, out_capacity=IPC, apply_fft=True)
         t += time.perf_counter() - t0
         pos += cons; calls += 1
         syms.append(o)
         if cons == 0:
             break
     X = np.concatenate(syms)
-    record("ofdm_sym_acquisition+fft", t, calls, 64)
+    record("ofdm_sym_acquisition+fft", t, calls, IPC)
     # demod_reference_signals: 64 symbols per call (65 visible)
     dem = g.demod_reference_signals(8, N, P, w.CON, g.NH, w.CR, w.CR, g.G1_32, w.TM, 0, 0)
     t, calls, ys, first = 0.0, 0, [], True
-    for i in range(0, len(X) - 65, 64):
+    for i in range(0, len(X) - IPC - 1, IPC):
         t0 = time.perf_counter()
-        y, cons, tags = dem.general_work(X[i: i + 65], tags=[(0, "sync_start", 1)] if first else [])
+        y, cons, tags = dem.general_work(X[i: i + IPC + 1], tags=[(0, "sync_start", 1)] if first else [])
         t += time.perf_counter() - t0
         first = False; calls += 1
         ys.append(y)
-    record("demod_reference_signals", t, calls, 64)
+    record("demod_reference_signals", t, calls, IPC)
     Y = np.concatenate(ys) if ys else np.zeros((0, P), np.complex64)
-    if len(Y) < 64:
+    if len(Y) < IPC:
         Y = np.tile((np.random.default_rng(3).normal(size=(64, P)) + 1j * np.random.default_rng(4).normal(size=(64, P))).astype(np.complex64), (nsym // 64, 1))
     # dvbt_demap: 64 items per call
     dm = g.dvbt_demap(P, w.CON, g.NH, w.TM, 1.0)
     reps = max(1, nsym // max(len(Y), 1))
     t, calls = 0.0, 0
     for _ in range(reps):
-        for i in range(0, len(Y) - 63, 64):
+        for i in range(0, len(Y) - IPC + 1, IPC):
             t0 = time.perf_counter()
-            dm.general_work(64, Y[i: i + 64])
+            dm.general_work(IPC, Y[i: i + IPC])
             t += time.perf_counter() - t0
             calls += 1
-    record("dvbt_demap", t * (nsym / (calls * 64.0)), calls, 64)
+    record("dvbt_demap", t * (nsym / (max(calls, 1) * float(IPC))), calls, IPC)
     # viterbi_decoder: 64 x 768-blocks per call, input = the bit-deinterleaved bytes of the fused chain's last run
     w.rx.run_file_dev(w.d_in.data_ptr(), w.nfile, w.GAIN, w.d_ts.data_ptr(), w.ts_cap)
     vin = w.rx.stage("bitdeint")
@@ -1121,12 +1137,12 @@ def drop_in_leg(g, w):
     nsymb, nout = 768 * w.n // w.m, 96 * w.k
     need = nsym * P
     t, calls, pos = 0.0, 0, 0
-    while pos + 64 * nsymb <= min(need, len(vin)):
+    while pos + IPC * nsymb <= min(need, len(vin)):
         t0 = time.perf_counter()
-        vit.general_work(64 * nout, vin[pos: pos + 64 * nsymb], tags=[(0, "superframe_start", 1)] if pos == 0 else [])
+        vit.general_work(IPC * nout, vin[pos: pos + IPC * nsymb], tags=[(0, "superframe_start", 1)] if pos == 0 else [])
         t += time.perf_counter() - t0
-        pos += 64 * nsymb; calls += 1
-    record("viterbi_decoder", t * (need / max(pos, 1)), calls, "64 x 768-blocks")
+        pos += IPC * nsymb; calls += 1
+    record("viterbi_decoder", t * (need / max(pos, 1)), calls, "%d x 768-blocks" % IPC)
     # reed_solomon_dec: 64 items of 8 packets per call on the deinterleaved Viterbi output
     vo = w.rx.stage("viterbi")
     npk = min(len(vo) // 204, nsym * P * w.m * w.k // (8 * w.n) // 204) // 8 * 8
@@ -1135,12 +1151,12 @@ def drop_in_leg(g, w):
     pk = np.where(src >= 0, vo[np.clip(src, 0, None)], 0).astype(np.uint8)
     rs = g.reed_solomon_dec(2, 8, 0x11D, 255, 239, 8, 51, 8)
     t, calls = 0.0, 0
-    for i in range(0, npk // 8 - 63, 64):
+    for i in range(0, npk // 8 - IPC + 1, IPC):
         t0 = time.perf_counter()
-        rs.general_work(64, pk[i * 1632: (i + 64) * 1632])
+        rs.general_work(IPC, pk[i * 1632: (i + IPC) * 1632])
         t += time.perf_counter() - t0
         calls += 1
-    record("reed_solomon_dec", t * (npk / 8.0 / max(calls * 64, 1)), calls, 64)
+    record("reed_solomon_dec", t * (npk / 8.0 / max(calls * IPC, 1)), calls, IPC)
     slow = min(res["blocks"].values(), key=lambda b: b["msamples_per_s"])
     res["pipelined_msamples_per_s"] = slow["msamples_per_s"]
     res["serial_msamples_per_s"] = samples / 1e6 / sum(b["seconds"] for b in res["blocks"].values())

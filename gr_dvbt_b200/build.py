@@ -32,7 +32,8 @@ def build_native(force=False, verbose=False):
         return LIB
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     tmp = LIB + ".building"   # the finished library replaces the old one atomically (a GPU-box snapshot never sees half a file)
-    cmd = [nvcc] + NVCC_FLAGS + ["-o", tmp] + sources() + ["-lcufft"]
+    extra = ["-DDVBT_B200_LEGACY_ACS"] if os.environ.get("DVBT_B200_BUILD_LEGACY_ACS") else []   # byte-SWAR + two-lane ACS kernels (A/B baselines)
+    cmd = [nvcc] + NVCC_FLAGS + extra + ["-o", tmp] + sources() + ["-lcufft"]
     if verbose:
         cmd.insert(1, "-Xptxas")
         cmd.insert(2, "-v")

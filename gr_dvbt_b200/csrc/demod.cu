@@ -15,10 +15,11 @@
 // decision or an output keeps the reference's operand order and rounding (explicit
 // __f*_rn / __d*_rn, no FMA contraction; complex division as libgcc's __divsc3 does it for
 // float operands: straight formula in double), but the work is split:
-//   demod_symbol_kernel : one block per symbol  - the symbol staged once by a bulk async copy (TMA engine); CFO
-//                                                products by all threads, the reference's sequential sums by warp 0
-//                                                (integer offset, one-shot estimate, rotor, scattered-pilot phase);
-//                                                pilot gains and slopes; TPS carriers, payload cells (+ demap)
+//   demod_stage1_kernel : one warp per symbol   - CFO sums (16 lanes), one-shot sums (2 lanes), rotor,
+//                                                scattered-pilot phase (4 lanes)
+//   demod_symbol_kernel : one block per symbol  - the symbol staged once by a bulk async copy (TMA engine); pilot
+//                                                gains and slopes; TPS carriers, payload cells (+ demap), four cells
+//                                                per thread.  <true>: stage 1 fused in as well (opt-in, slower)
 //   demod_vote_kernel   : one thread per symbol - TPS majority vote against the previous symbol
 //   demod_scan_kernel   : one block             - the genuinely sequential part (symbol/frame
 //                                                index, TPS FIFO, BCH, superframe gating)
@@ -28,6 +29,7 @@
 #include "bulk_copy.cuh"
 
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 #include <new>
 #include <vector>
@@ -228,6 +230,83 @@ __device__ __forceinline__ float2 cdiv(float2 n, float2 d) {
 }
 
 // ---------------------------------------------------------------------------------------
+// stage 1: one warp per symbol
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) demod_stage1_kernel(ModeDev md, const float2 *__restrict__ X, int nparse,
+                                                           int *__restrict__ fo_out, float2 *__restrict__ rot_out,
+                                                           int *__restrict__ mod_out) {
+  int s = (int)((blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5);
+  int lane = threadIdx.x & 31;
+  if (s >= nparse) return;
+  const float2 *x0 = X + (long long)s * md.N;
+  const float2 *x1 = x0 + md.N;
+  // ---- process_cpilot_data (:714-744): lanes 0..15 hold candidate i = zl - 8 + lane
+  float sum = 0.f;
+  if (lane < 16) {
+    int i = md.zl - 8 + lane;
+    float2 prev = x0[i + md.cpilot[0]];
+    for (int j = 0; j < md.ncp - 1; j++) {
+      float2 cur = x0[i + md.cpilot[j + 1]];
+      float phase = cnorm(csub(cur, prev));
+      sum = __fadd_rn(sum, __fmul_rn(md.known[j], phase));
+      prev = cur;
+    }
+  }
+  float best = 0.f;
+  int start = 0;
+  for (int l = 0; l < 16; l++) {  // sequential first-strict-maximum scan
+    float v = __shfl_sync(0xffffffffu, sum, l);
+    if (v > best) { best = v; start = md.zl - 8 + l; }
+  }
+  // all-zero input leaves start = 0 in the reference (offset -zl, out-of-bounds reads there);
+  // a zero offset is used instead
+  int fo = (best > 0.f) ? start - md.zl : 0;
+  // ---- compute_oneshot_csft (:746-790): lane 0 = left half, lane 1 = right half
+  float angle = 0.f;
+  if (lane < 2) {
+    int half = (md.ncp - 1) / 2;
+    int j0 = lane == 0 ? 0 : half + 1, j1 = lane == 0 ? half : md.ncp;
+    float2 acc = make_float2(0.f, 0.f);
+    for (int j = j0; j < j1; j++) {
+      int idx = fo + md.zl + md.cpilot[j];
+      acc = cadd(acc, cmul_conj(x0[idx], x1[idx]));
+    }
+    angle = atan2f(acc.y, acc.x);
+  }
+  float left = __shfl_sync(0xffffffffu, angle, 0), right = __shfl_sync(0xffffffffu, angle, 1);
+  float corr = __fmul_rn(__fadd_rn(right, left), md.carrier_coeff);
+  // ---- frequency_correction (:792-819): one rotor for the whole symbol
+  float correction = __fadd_rn((float)fo, corr);
+  double ang = __ddiv_rn(__dmul_rn(__dmul_rn(-2.0 * M_PI, (double)correction), (double)(md.N + md.cp)), (double)md.N);
+  float sn, cs;
+  sincosf((float)ang, &sn, &cs);
+  float2 rot = make_float2(cs, sn);
+  // ---- process_spilot_data, phase detection (:547-582): lanes 0..3 = candidate phase
+  float ssum = 0.f;
+  if (lane < 4) {
+    float2 c = make_float2(0.f, 0.f);
+    for (int j = 0; j < 10; j++) {
+      int k = 3 * lane + 12 * j;
+      float2 dv = cmul(rot, x0[md.zl + k + fo]);
+      c = cadd(c, cmul_conj(make_float2(md.pval[k], 0.f), dv));
+    }
+    ssum = cnorm(c);
+  }
+  float smax = 0.f;
+  int mod = -1;  // -1: no candidate exceeded 0, the reference keeps the previous value
+  for (int l = 0; l < 4; l++) {
+    float v = __shfl_sync(0xffffffffu, ssum, l);
+    if (v > smax) { smax = v; mod = l; }
+  }
+  if (lane == 0) {
+    fo_out[s] = fo;
+    rot_out[s] = rot;
+    mod_out[s] = mod;
+  }
+}
+
+
+// ---------------------------------------------------------------------------------------
 // one block per symbol: everything parse_input does to a symbol except the sequential bookkeeping
 // ---------------------------------------------------------------------------------------
 // The symbol's active carriers (K + 16 around them for the 16 integer-CFO candidates) are staged in shared memory ONCE by
@@ -243,11 +322,12 @@ __device__ __forceinline__ float2 cdiv(float2 n, float2 d) {
 //   all threads   TPS carriers (:929-945) and payload cells (:1104-1113), four consecutive cells per thread: one 16-byte
 //                 table load, gains interpolated where they are used, fused demap, ONE 4-byte store of the four demapped
 //                 cells (and two 16-byte stores of the equalised cells when the caller wants them)
-constexpr int kSymThreads = 384;
-
-__global__ void __launch_bounds__(kSymThreads) demod_symbol_kernel(ModeDev md, const __grid_constant__ DemapTable dt, int do_demap, int use_bulk,
-                                                                   const float2 *__restrict__ X, int *__restrict__ fo_out,
-                                                                   float2 *__restrict__ rot_out, int *__restrict__ mod_out,
+// FRONT = false (default): the integer offset, rotor and scattered-pilot phase come from demod_stage1_kernel (one warp per
+// symbol, good occupancy for its latency-bound sums) and this kernel does the wide part only; FRONT = true: everything in
+// one kernel (DVBT_B200_DEMOD_FUSED=1; measured slower on B200: the other eleven warps of the block wait for warp 0's sums).
+template <bool FRONT, int kSymThreads>
+__global__ void __launch_bounds__(kSymThreads, FRONT ? 1 : 1536 / kSymThreads) demod_symbol_kernel(ModeDev md, const __grid_constant__ DemapTable dt, int do_demap, int use_bulk,
+                                                                   const float2 *__restrict__ X, int *fo_out, float2 *rot_out, int *mod_out,
                                                                    float2 *__restrict__ tpsval, float2 *__restrict__ Y,
                                                                    uint8_t *__restrict__ dm) {
   extern __shared__ __align__(16) unsigned char s_sym[];
@@ -261,20 +341,23 @@ __global__ void __launch_bounds__(kSymThreads) demod_symbol_kernel(ModeDev md, c
   float *prod = reinterpret_cast<float *>(x1seg + ncp * 16);       // [ncp - 1][16]
   float2 *t1 = reinterpret_cast<float2 *>(prod + 16 * ncp);        // [ncp] one-shot terms
   float2 *sp = t1 + ncp;                                           // [40] scattered-pilot terms
-  float2 *gain = sp + 40;                                          // [npil] by pilot ordinal
+  float2 *gain = FRONT ? sp + 40 : xs + ((nxs + 1) & ~1);          // [npil] by pilot ordinal
   float2 *slope = gain + md.pil_stride;
   const float2 *x0g = X + (long long)s * md.N + md.zl - 8;
   const float2 *x1g = x0g + md.N;
   if (t == 0) mbar_init(&s_bar, 1);
   __syncthreads();
   if (use_bulk && t == 0) bulk_g2s(xs, x0g, (unsigned)nxs * 8u, &s_bar);
-  for (int i = t; i < ncp * 16; i += kSymThreads) x1seg[i] = x1g[md.cpilot[i >> 4] + (i & 15)];
+  if (FRONT)
+    for (int i = t; i < ncp * 16; i += kSymThreads) x1seg[i] = x1g[md.cpilot[i >> 4] + (i & 15)];
+  if (!FRONT && t == 0) { s_fo = fo_out[s]; s_rot = rot_out[s]; s_mod = mod_out[s]; }
   if (use_bulk) {
     mbar_wait(&s_bar, 0);
   } else {   // the caller's buffer is not 16-byte aligned: plain loads
     for (int i = t; i < nxs; i += kSymThreads) xs[i] = x0g[i];
   }
   __syncthreads();
+  if (FRONT) {
   // ---- process_cpilot_data (:714-744): candidate l <-> offset l - 8
   for (int i = t; i < 16 * (ncp - 1); i += kSymThreads) {
     const int j = i >> 4, l = i & 15;
@@ -340,6 +423,7 @@ __global__ void __launch_bounds__(kSymThreads) demod_symbol_kernel(ModeDev md, c
     }
   }
   __syncthreads();
+  }   // FRONT
   const int fo = s_fo;
   const float2 rot = s_rot;
   int r = s_mod;
@@ -384,8 +468,9 @@ __global__ void __launch_bounds__(kSymThreads) demod_symbol_kernel(ModeDev md, c
   }
 }
 
-size_t demod_symbol_smem(const ModeDev &md) {
+size_t demod_symbol_smem(const ModeDev &md, bool front) {
   const size_t nxs = (size_t)md.K + 17;
+  if (!front) return ((nxs + 1) & ~(size_t)1) * 8 + (size_t)md.pil_stride * 16 + 64;
   return ((nxs + 1) & ~(size_t)1) * 8 + (size_t)md.ncp * 16 * 8 + (size_t)md.ncp * 16 * 4 + (size_t)md.ncp * 8 + 40 * 8 + (size_t)md.pil_stride * 16 + 64;
 }
 
@@ -664,16 +749,33 @@ int demod_run(const ModeDev &md, const DemapTable *demap, const float2 *X, int n
               int fi_start, int sync_start_at0, float2 *Y, uint8_t *dm, cudaStream_t st, const int *sync_at, int nsync, int src_base) {
   if (nparse <= 0) return 0;
   {
-    const size_t smem = demod_symbol_smem(md);
+    static const bool fused_front = getenv("DVBT_B200_DEMOD_FUSED") && atoi(getenv("DVBT_B200_DEMOD_FUSED")) != 0;
+    if (!fused_front) {
+      const int threads = 128;
+      const long long total = (long long)nparse * 32;
+      demod_stage1_kernel<<<(unsigned)((total + threads - 1) / threads), threads, 0, st>>>(md, X, nparse, b.fo, b.rot, b.modidx);
+      DVBT_CUDA_TRY(cudaGetLastError());
+      count_launch();
+    }
+    const size_t smem = demod_symbol_smem(md, fused_front);
+    // threads per block: the payload loop takes P / 4 = 378 (1512) quads of cells per symbol - 192 threads make it two (eight)
+    // full passes, and eight blocks (1536 threads, <= 42 registers) fit an SM
+    static const int nt_env = getenv("DVBT_B200_DEMOD_THREADS") ? atoi(getenv("DVBT_B200_DEMOD_THREADS")) : 192;
+    const int kSymThreads = fused_front ? 384 : (nt_env == 128 || nt_env == 256 || nt_env == 384) ? nt_env : 192;
+    void (*symk)(ModeDev, const DemapTable, int, int, const float2 *, int *, float2 *, int *, float2 *, float2 *, uint8_t *) =
+        fused_front ? demod_symbol_kernel<true, 384>
+        : kSymThreads == 128 ? demod_symbol_kernel<false, 128>
+        : kSymThreads == 256 ? demod_symbol_kernel<false, 256>
+        : kSymThreads == 384 ? demod_symbol_kernel<false, 384> : demod_symbol_kernel<false, 192>;
     // per launch, like every other kernel of the library: the attribute is per device and handles live on any device
-    DVBT_CUDA_TRY(cudaFuncSetAttribute(demod_symbol_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    DVBT_CUDA_TRY(cudaFuncSetAttribute(symk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     DemapTable dummy;
     dummy.size = 0;
     // bulk copies and the vector stores want 16-byte aligned buffers (every buffer of this library is; a caller's may not be)
     const int aligned = (((uintptr_t)X & 15) == 0) ? 1 : 0;
     if ((Y && ((uintptr_t)Y & 15)) || (dm && ((uintptr_t)dm & 3))) { set_error("demod: output buffers must be 16-byte (cells) / 4-byte (demapped) aligned"); return DVBT_B200_EINVAL; }
     if (b.ev_eq0) DVBT_CUDA_TRY(cudaEventRecord(b.ev_eq0, st));
-    demod_symbol_kernel<<<nparse, kSymThreads, smem, st>>>(md, demap ? *demap : dummy, (demap && dm) ? 1 : 0, aligned, X, b.fo, b.rot, b.modidx,
+    symk<<<nparse, kSymThreads, smem, st>>>(md, demap ? *demap : dummy, (demap && dm) ? 1 : 0, aligned, X, b.fo, b.rot, b.modidx,
                                                           b.tpsval, Y, dm);
     DVBT_CUDA_TRY(cudaGetLastError());
     if (b.ev_eq1) DVBT_CUDA_TRY(cudaEventRecord(b.ev_eq1, st));

@@ -7,10 +7,12 @@
  *   - plain pointers and sizes, no C++ or torch types; never throws across the ABI;
  *   - return 0 on success, a negative DVBT_B200_E* code on failure;
  *     dvbt_b200_last_error() returns a thread-local description of the last failure;
- *   - "host" buffers are borrowed for the duration of the call (the library stages them
- *     through pinned memory); "dev" entry points take CUDA device pointers on the current
- *     device and enqueue on the handle's stream, then synchronise before returning unless
- *     stated otherwise;
+ *   - "host" buffers are borrowed for the duration of the call: they are copied to and from
+ *     device buffers the handle owns with cudaMemcpyAsync on the handle's stream (pageable
+ *     memory is staged by the CUDA driver, pinned memory - cudaHostAlloc / cudaHostRegister by
+ *     the caller - is copied at PCIe speed), and the call returns after the stream has been
+ *     synchronised; "dev" entry points take CUDA device pointers on the current device and
+ *     enqueue on the handle's stream, then synchronise before returning unless stated otherwise;
  *   - a handle is not thread-safe; distinct handles are independent (the reference's
  *     process-global Viterbi state, viterbi_decoder_impl.cc:49-52, is not reproduced);
  *   - there is NO CPU fallback: without a CUDA device every create() fails with

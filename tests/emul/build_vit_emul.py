@@ -361,8 +361,15 @@ extern "C" int emul_demod(const float *Xf, int nsym, int constellation, int tm, 
   std::vector<float2> rot(nparse), tps((size_t)nparse * md.ntps);
   DemodState st;
   memset(&st, 0, sizeof st);
-  emul_launch(demod_symbol_kernel, (unsigned)nparse, (unsigned)kSymThreads, md, dt, 1, (int)((((uintptr_t)X) & 15) == 0), X, fo.data(), rot.data(), mod.data(),
-              tps.data(), (float2 *)Y_out, dm_out);
+  const char *fused = getenv("DVBT_EMUL_DEMOD_FUSED");
+  if (fused && atoi(fused)) {
+    emul_launch(demod_symbol_kernel<true, 384>, (unsigned)nparse, 384u, md, dt, 1, (int)((((uintptr_t)X) & 15) == 0), X, fo.data(), rot.data(), mod.data(),
+                tps.data(), (float2 *)Y_out, dm_out);
+  } else {
+    emul_launch(demod_stage1_kernel, (unsigned)(((long long)nparse * 32 + 127) / 128), 128u, md, X, nparse, fo.data(), rot.data(), mod.data());
+    emul_launch(demod_symbol_kernel<false, 192>, (unsigned)nparse, 192u, md, dt, 1, (int)((((uintptr_t)X) & 15) == 0), X, fo.data(), rot.data(), mod.data(),
+                tps.data(), (float2 *)Y_out, dm_out);
+  }
   emul_launch(demod_vote_kernel, (unsigned)((nparse + 127) / 128), 128u, md.ntps, nparse, (const float2 *)tps.data(), &st, vote.data(),
               sync_start_at0, (const int *)nullptr, 0);
   emul_launch(demod_scan_kernel, 1u, (unsigned)(32 * kScanWarps), md.ntps, nparse, fi_start, 0, (const int *)mod.data(), (const int *)vote.data(),
@@ -399,7 +406,7 @@ def build_demod(force=False):
     dm = dm[dm.index("namespace dvbt {"): dm.index("__device__ __forceinline__ uint8_t demap_cell(")] + "}  // namespace dvbt\n"
     src = open(os.path.join(CSRC, "demod.cu")).read()
     body = src[src.index("namespace dvbt {"): src.index("int demod_run(")] + "}  // namespace dvbt\n"
-    for needle in ("demod_symbol_kernel(", "demod_vote_kernel(", "demod_scan_kernel(", "ModeTables::init("):
+    for needle in ("demod_stage1_kernel(", "demod_symbol_kernel(", "demod_vote_kernel(", "demod_scan_kernel(", "ModeTables::init("):
         assert needle in body, "demod.cu changed shape: %r" % needle
     tu = ('// GENERATED by tests/emul/build_vit_emul.py from gr_dvbt_b200/csrc/demod.cu, demod.cuh, demap.cu -- test infrastructure\n'
           '#include "../cuda_host_emul.h"\n' + BULK_COPY_HOST + DEMAP_SHIM + DEMOD_SHIM + hdr + dm
@@ -517,7 +524,8 @@ def build_acq(force=False):
 def build_all(force=False):
     """tests/emul/_build/libdvbt_b200_emul.so: EVERY source file of the library (kernels and host code) on the stand-in
     runtime - the whole C ABI of include/dvbt_b200.h, running on the CPU.  Loaded by tests only, by explicit path."""
-    return build_whole("libdvbt_b200_emul.so", sorted(f for f in os.listdir(CSRC) if f.endswith(".cu")), force)
+    return build_whole("libdvbt_b200_emul.so", sorted(f for f in os.listdir(CSRC) if f.endswith(".cu")), force,
+                       extra_flags=("-DDVBT_B200_LEGACY_ACS",))   # the round-1 byte-SWAR schedule stays covered here
 
 
 def build_all_asan(force=False):

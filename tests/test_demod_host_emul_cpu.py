@@ -21,8 +21,11 @@ pytestmark = pytest.mark.timeout(900, method="thread")
 CH = np.load(os.path.join(os.path.dirname(__file__), "golden", "chain_2k_qam16_r12.npz"))
 
 
-@pytest.fixture(scope="module")
-def demod():
+@pytest.fixture(scope="module", params=[0, 1], ids=["stage1+symbol", "fused-front"])
+def demod(request):
+    """both launch forms of demod_run: demod_stage1_kernel + demod_symbol_kernel<false> (default) and the opt-in
+    demod_symbol_kernel<true> that does stage 1 inside the block (DVBT_B200_DEMOD_FUSED=1)"""
+    os.environ["DVBT_EMUL_DEMOD_FUSED"] = str(request.param)
     lib = C.CDLL(build_vit_emul.build_demod())
 
     def run(X, con, tm):
@@ -36,6 +39,7 @@ def demod():
         si, src = np.zeros(nsym, np.int32), np.zeros(nsym, np.int32)
         n_out, first, sf = C.c_int(0), C.c_int(0), C.c_int(0)
         fi_start = 2 if (con == 2 and tm == 1) else 3
+        os.environ["DVBT_EMUL_DEMOD_FUSED"] = str(request.param)
         rc = lib.emul_demod(C.c_void_p(Xp.ctypes.data + 32 * 8), nsym, con, tm, fi_start, 1, C.c_void_p(Y.ctypes.data), C.c_void_p(dm.ctypes.data),
                             C.c_void_p(si.ctypes.data), C.c_void_p(src.ctypes.data), C.byref(n_out), C.byref(first), C.byref(sf))
         assert rc == 0

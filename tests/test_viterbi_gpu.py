@@ -10,10 +10,13 @@ pytestmark = pytest.mark.gpu
 CON = {2: 0, 4: 1, 6: 2}
 
 
-@pytest.fixture(autouse=True, params=["2", "1"], ids=["two-lane-acs", "one-lane-acs"])
+@pytest.fixture(autouse=True, params=["h16", "h16b"], ids=["h16-acs", "h16b-acs"])
 def acs_variant(request, monkeypatch):
-    """every test runs with both ACS kernels (the variant is read when a decoder is created)"""
-    monkeypatch.setenv("DVBT_B200_VIT_LANES", request.param)
+    """every test runs with both halfword ACS schedules (the variant is read when a decoder is created): the default and
+    the one with the cheaper event.  The byte-SWAR and two-lane kernels of round 1 are a legacy build
+    option (DVBT_B200_BUILD_LEGACY_ACS=1) and are covered on the host emulation only."""
+    monkeypatch.setenv("DVBT_B200_VIT_ACS", request.param)
+    monkeypatch.delenv("DVBT_B200_VIT_LANES", raising=False)
     return request.param
 
 
