@@ -11,13 +11,14 @@ import numpy as np
 from . import capi
 from .capi import check, lib
 
-__all__ = ["viterbi_decoder", "reed_solomon_dec", "dvbt_demap", "demod_reference_signals", "rx_chain", "ofdm_sym_acquisition", "QPSK", "QAM16", "QAM64", "NH", "C1_2", "C2_3", "C3_4", "C5_6", "C7_8", "T2k", "T8k", "G1_32"]
+__all__ = ["viterbi_decoder", "reed_solomon_dec", "dvbt_demap", "demod_reference_signals", "rx_chain", "tx_chain", "ofdm_sym_acquisition", "QPSK", "QAM16", "QAM64", "NH", "C1_2", "C2_3", "C3_4", "C5_6", "C7_8", "T2k", "T8k",
+           "G1_32", "G1_16", "G1_8", "G1_4"]
 
 QPSK, QAM16, QAM64 = 0, 1, 2
 NH = 0
 C1_2, C2_3, C3_4, C5_6, C7_8 = 0, 1, 2, 3, 4
 T2k, T8k = 0, 1
-G1_32 = 0
+G1_32, G1_16, G1_8, G1_4 = 0, 1, 2, 3
 
 
 def _addr(x):
@@ -290,6 +291,44 @@ class rx_chain(_Handle):
         n = C.c_size_t(0)
         check(lib().dvbt_b200_rx_read_stage(self._h, sid, buf.ctypes.data, cap, C.byref(n)))
         return buf[: n.value].view(dt).copy()
+
+
+class tx_chain(_Handle):
+    """The transmit flowgraph on the device (include/dvbt_b200.h: dvbt_b200_tx_*): TS packets -> frequency-domain symbols /
+    baseband / 10 Msps capture.  A synthetic-input generator for the receive path."""
+    _destroy = "dvbt_b200_tx_destroy"
+    LEVELS = dict(file=0, baseband=1, freq=2)
+    STAGES = dict(energy=0, rs=1, outer=2, inner_coder=3, bit_interleaver=4, symbol_interleaver=5)
+
+    def __init__(self, constellation, hierarchy, code_rate, guard_interval, transmission_mode):
+        self._h = C.c_void_p()
+        par = capi.RxParams(constellation, hierarchy, code_rate, guard_interval, transmission_mode)
+        check(lib().dvbt_b200_tx_create(C.byref(par), C.byref(self._h)))
+        self.N = 2048 if transmission_mode == T2k else 8192
+        self.P = 1512 if transmission_mode == T2k else 6048
+        self.cp = self.N // (32 >> guard_interval)
+
+    def run(self, ts, level="freq", gain=1.0):
+        """ts: TS bytes (188-byte packets).  Returns complex64 (nsym, N) / samples and the symbol count."""
+        ts = np.ascontiguousarray(ts, np.uint8).reshape(-1)
+        npk = len(ts) // 188
+        cap = (npk * 204 // 300 + 8) * (self.N + self.cp) * 35 // 32 + 4096   # >= any level's size (a symbol carries >= 378 bytes)
+        out = np.zeros(cap, np.complex64)
+        n, nsym = C.c_size_t(0), C.c_size_t(0)
+        check(lib().dvbt_b200_tx_run_host(self._h, ts.ctypes.data, npk, self.LEVELS[level], gain, out.ctypes.data, cap, C.byref(n), C.byref(nsym)))
+        res = out[: n.value].copy()
+        return (res.reshape(-1, self.N) if level == "freq" else res), int(nsym.value)
+
+    def run_dev(self, d_ts, npackets, level, gain, d_out, capacity):
+        n, nsym = C.c_size_t(0), C.c_size_t(0)
+        check(lib().dvbt_b200_tx_run_dev(self._h, _addr(d_ts), npackets, self.LEVELS[level], gain, _addr(d_out), capacity, C.byref(n), C.byref(nsym)))
+        return int(n.value), int(nsym.value)
+
+    def stage(self, name, capacity):
+        buf = np.zeros(capacity, np.uint8)
+        n = C.c_size_t(0)
+        check(lib().dvbt_b200_tx_read_stage(self._h, self.STAGES[name], buf.ctypes.data, capacity, C.byref(n)))
+        return buf[: n.value].copy()
 
 
 class ofdm_sym_acquisition(_Handle):

@@ -123,6 +123,11 @@ def declare(L):
         L.dvbt_b200_rx_stream_reset.argtypes = [vp]
         for name in ("dvbt_b200_rx_stream_push_host", "dvbt_b200_rx_stream_push_dev"):
             getattr(L, name).argtypes = [vp, C.c_int, vp, C.c_size_t, C.c_float, C.c_int, vp, C.c_size_t, C.POINTER(C.c_size_t)]
+        L.dvbt_b200_tx_create.argtypes = [C.POINTER(RxParams), C.POINTER(vp)]
+        L.dvbt_b200_tx_destroy.argtypes = [vp]
+        for name in ("dvbt_b200_tx_run_host", "dvbt_b200_tx_run_dev"):
+            getattr(L, name).argtypes = [vp, vp, C.c_size_t, C.c_int, C.c_float, vp, C.c_size_t, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]
+        L.dvbt_b200_tx_read_stage.argtypes = [vp, C.c_int, vp, C.c_size_t, C.POINTER(C.c_size_t)]
         L.dvbt_b200_resampler_taps.argtypes = [vp, C.c_int]
         L.dvbt_b200_resample_host.argtypes = [vp, C.c_size_t, C.c_float, vp, C.c_size_t, C.POINTER(C.c_size_t), C.c_int]
     return L

@@ -1153,7 +1153,7 @@ int acq_run(dvbt_b200_acq *h, const float2 *x, long long n, float2 *d_out, long 
   int sync_tags = 0, lost_total = -1, fb = 0;
   int rc;
   DVBT_CUDA_TRY(cudaMemcpyAsync(hs, h->d_state.p, sizeof(AcqState), cudaMemcpyDeviceToHost, st));
-  DVBT_CUDA_TRY(cudaStreamSynchronize(st));
+  DVBT_CUDA_TRY(dvbt::stream_wait(st));
   // frequency-domain output: derotation + FFT in one kernel for the two DVB-T sizes (cuFFT otherwise)
   const bool fused_fft = do_fft && (p.N == 2048 || p.N == 8192) && !getenv("DVBT_B200_ACQ_CUFFT");
   if (fused_fft && h->tw_n != p.N) {
@@ -1164,7 +1164,7 @@ int acq_run(dvbt_b200_acq *h, const float2 *x, long long n, float2 *d_out, long 
     }
     if ((rc = h->d_tw.reserve((size_t)p.N * sizeof(float2)))) return rc;
     DVBT_CUDA_TRY(cudaMemcpyAsync(h->d_tw.p, tw.data(), (size_t)p.N * sizeof(float2), cudaMemcpyHostToDevice, st));
-    DVBT_CUDA_TRY(cudaStreamSynchronize(st));
+    DVBT_CUDA_TRY(dvbt::stream_wait(st));
     h->tw_n = p.N;
   }
   h->n_fft_ev = 0;
@@ -1182,7 +1182,7 @@ int acq_run(dvbt_b200_acq *h, const float2 *x, long long n, float2 *d_out, long 
       count_launch(3);
       DVBT_CUDA_TRY(cudaGetLastError());
       DVBT_CUDA_TRY(cudaMemcpyAsync(hs, h->d_state.p, sizeof(AcqState), cudaMemcpyDeviceToHost, st));
-      DVBT_CUDA_TRY(cudaStreamSynchronize(st));
+      DVBT_CUDA_TRY(dvbt::stream_wait(st));
       probe_lost1 = hs->probe_lost1;
       sync_tags++;  // send_sync_start() on every attempt (:507), tagged at nitems_written = symbols produced so far
       if (sync_at && (sync_at->empty() || sync_at->back() != produced)) sync_at->push_back(produced);
@@ -1257,7 +1257,7 @@ int acq_run(dvbt_b200_acq *h, const float2 *x, long long n, float2 *d_out, long 
       DVBT_CUDA_TRY(cudaGetLastError());
     }
     DVBT_CUDA_TRY(cudaMemcpyAsync(hs, h->d_state.p, sizeof(AcqState), cudaMemcpyDeviceToHost, st));
-    DVBT_CUDA_TRY(cudaStreamSynchronize(st));
+    DVBT_CUDA_TRY(dvbt::stream_wait(st));
     if (getenv("DVBT_B200_ACQ_TRACE")) {
       AcqWalk wk;
       if (cudaMemcpy(&wk, h->d_eps.p, sizeof wk, cudaMemcpyDeviceToHost) == cudaSuccess)
@@ -1328,7 +1328,7 @@ int acq_run(dvbt_b200_acq *h, const float2 *x, long long n, float2 *d_out, long 
       s2.initial = 0;
       pos += total / 2;
       DVBT_CUDA_TRY(cudaMemcpyAsync(h->d_state.p, &s2, sizeof(AcqState), cudaMemcpyHostToDevice, st));
-      DVBT_CUDA_TRY(cudaStreamSynchronize(st));
+      DVBT_CUDA_TRY(dvbt::stream_wait(st));
       *hs = s2;
       continue;
     }
@@ -1451,7 +1451,7 @@ int dvbt_b200_acq_work(dvbt_b200_acq *h, const void *in, size_t n_in_items, void
   rc = dvbt::acq_run(h, h->d_x.as<float2>(), (long long)n_in_items, h->d_out.as<float2>(), (long long)out_capacity_items, apply_fft, &hs, &sync_at);
   if (rc) return rc;
   if (hs.n_out > 0) DVBT_CUDA_TRY(cudaMemcpyAsync(out, h->d_out.p, (size_t)hs.n_out * N * 8, cudaMemcpyDeviceToHost, h->stream));
-  DVBT_CUDA_TRY(cudaStreamSynchronize(h->stream));
+  DVBT_CUDA_TRY(dvbt::stream_wait(h->stream));
   *consumed = (size_t)hs.consumed;
   *produced = (size_t)hs.n_out;
   // send_sync_start() (:353-360) on every acquisition attempt (:507), at the output position it happened at: the first

@@ -52,3 +52,13 @@ long long resample_out_count(long long nin);
 // restarts there, so output m of this call is output 32 q + m of the stream); 0 = the stream starts at d_x (zero history)
 int resample_launch(const float2 *d_x, long long nin, float2 *d_y, long long nout, float scale, cudaStream_t st, int nhist = 0);
 }  // namespace dvbt
+
+namespace dvbt {
+// transmit side (tx_chain.cu)
+int tx_outer_launch(const uint8_t *d_ts, long long npk, const uint8_t *d_prbs, uint8_t *d_ed, uint8_t *d_rs, uint8_t *d_ci, cudaStream_t st);
+// the 8-packet PRBS of energy_dispersal / energy_descramble (energy_descramble_impl.cc:46-67): 1 + x^14 + x^15, init 0xa9, 8
+// clocks per byte, clocked but unused on the sync bytes
+void energy_prbs_table(uint8_t tab[1504]);
+// polyphase prototype of rational_resampler_ccc(interp, decim) after gcd reduction (GNU Radio 3.7 design_filter, beta 7, fractional_bw 0.4)
+int resampler_taps_for(int interp, int decim, std::vector<float> *taps, int *per_arm);
+}  // namespace dvbt

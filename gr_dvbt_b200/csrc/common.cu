@@ -1,5 +1,6 @@
 // libdvbt_b200.so: error text, device selection, launch counter.
 #include "common.cuh"
+#include "chain_internal.cuh"
 
 #include <atomic>
 
@@ -27,6 +28,24 @@ int ensure_device() {
     return DVBT_B200_ENODEV;
   }
   return 0;
+}
+
+void energy_prbs_table(uint8_t tab[1504]) {
+  unsigned reg = 0xa9;
+  auto clock8 = [&]() {
+    unsigned res = 0;
+    for (int i = 0; i < 8; i++) {
+      unsigned fb = ((reg >> 13) ^ (reg >> 14)) & 1u;
+      reg = ((reg << 1) | fb) & 0x7fff;
+      res = (res << 1) | fb;
+    }
+    return (uint8_t)res;
+  };
+  for (int pk = 0; pk < 8; pk++) {
+    tab[pk * 188] = 0;
+    for (int k = 1; k < 188; k++) tab[pk * 188 + k] = clock8();
+    clock8();
+  }
 }
 
 }  // namespace dvbt

@@ -60,16 +60,20 @@ static std::vector<float> firdes_low_pass_kaiser(double gain, double fs, double 
 
 constexpr int kInterp = 32, kDecim = 35;
 
-int resampler_taps(std::vector<float> *out, int *per_arm) {
-  double rate = (double)kInterp / kDecim;
-  double tw = rate * (0.5 - 0.4);
-  double mid = rate * 0.5 - tw / 2.0;
-  std::vector<float> t = firdes_low_pass_kaiser(kInterp, kInterp, mid, tw, 7.0);
-  while (t.size() % kInterp) t.push_back(0.f);  // install_taps pads to a multiple of the arm count
-  *per_arm = (int)(t.size() / kInterp);
+// python/rational_resampler.py design_filter(interpolation, decimation, fractional_bw = 0.4) of GNU Radio 3.7
+int resampler_taps_for(int interp, int decim, std::vector<float> *out, int *per_arm) {
+  const double rate = (double)interp / decim, halfband = 0.5, fractional_bw = 0.4;
+  double tw, mid;
+  if (rate >= 1.0) { tw = halfband - fractional_bw; mid = halfband - tw / 2.0; }
+  else { tw = rate * (halfband - fractional_bw); mid = rate * halfband - tw / 2.0; }
+  std::vector<float> t = firdes_low_pass_kaiser(interp, interp, mid, tw, 7.0);
+  while (t.size() % interp) t.push_back(0.f);  // install_taps pads to a multiple of the arm count
+  *per_arm = (int)(t.size() / interp);
   *out = t;
   return 0;
 }
+
+int resampler_taps(std::vector<float> *out, int *per_arm) { return resampler_taps_for(kInterp, kDecim, out, per_arm); }
 
 // taps laid out arm-major: tap[phase * per_arm + j] = h[phase + 32 j].  A block produces 512 outputs
 // (2 per thread); the 560 + per_arm input samples they need are staged in shared memory with coalesced

@@ -312,6 +312,50 @@ __global__ void __launch_bounds__(kTilePk) rs_decode_kernel(const uint8_t *__res
   }
 }
 
+
+// ---- transmit side (a synthetic-input generator on the device) ------------------------------------
+// energy_dispersal (energy_dispersal_impl.cc:93-140: PRBS 1 + x^14 + x^15 restarted every 8 packets, first sync byte
+// inverted) + reed_solomon_enc (reed_solomon.cc:216-244: systematic, parity = remainder of data x^16 modulo g(x) - the
+// same division the decoder's clean-packet test makes, with the same table): one thread per packet.
+__global__ void __launch_bounds__(128) tx_outer_kernel(const uint8_t *__restrict__ ts, long long npk, const uint8_t *__restrict__ prbs,
+                                                       uint8_t *__restrict__ ed, uint8_t *__restrict__ rs) {
+  __shared__ uint4 s_lfsr[256];
+  __shared__ uint8_t s_prbs[1504];
+  for (int i = threadIdx.x; i < 256; i += blockDim.x) s_lfsr[i] = reinterpret_cast<const uint4 *>(d_lfsr)[i];
+  for (int i = threadIdx.x; i < 1504; i += blockDim.x) s_prbs[i] = prbs[i];
+  __syncthreads();
+  const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= npk) return;
+  const int j = (int)(p & 7);
+  const uint8_t *in = ts + p * 188;
+  uint8_t *e = ed + p * 188, *o = rs + p * 204;
+  uint32_t r0 = 0, r1 = 0, r2 = 0, r3 = 0;
+  for (int k = 0; k < 188; k++) {
+    const uint8_t d = k == 0 ? (j == 0 ? 0xB8 : 0x47) : (uint8_t)(in[k] ^ s_prbs[j * 188 + k]);
+    e[k] = d;
+    o[k] = d;
+    const uint32_t fb = d ^ (r3 >> 24);
+    r3 = __funnelshift_l(r2, r3, 8);
+    r2 = __funnelshift_l(r1, r2, 8);
+    r1 = __funnelshift_l(r0, r1, 8);
+    r0 <<= 8;
+    const uint4 row = s_lfsr[fb];
+    r0 ^= row.x; r1 ^= row.y; r2 ^= row.z; r3 ^= row.w;
+  }
+  const uint32_t r[4] = {r3, r2, r1, r0};          // parity[0] = coefficient of x^15 ... parity[15] = x^0
+#pragma unroll
+  for (int q = 0; q < 16; q++) o[188 + q] = (uint8_t)(r[q >> 2] >> (24 - 8 * (q & 3)));
+}
+
+// convolutional_interleaver(136, 12, 17) (convolutional_interleaver_impl.cc:66-88): branch j = t % 12 delays by 17 j cells
+// of its own = 204 j stream positions, the FIFOs start zeroed
+__global__ void tx_outer_interleave_kernel(const uint8_t *__restrict__ rs, long long nbytes, uint8_t *__restrict__ ci) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= nbytes) return;
+  const long long src = t - 204LL * (t % 12);
+  ci[t] = src >= 0 ? rs[src] : (uint8_t)0;
+}
+
 }  // namespace
 
 struct dvbt_b200_rsdec {
@@ -378,6 +422,19 @@ int rs_launch(const uint8_t *d_in, uint8_t *d_out, int *d_status, long long npac
     rs_decode_kernel<false><<<grid, kTilePk, smem, st>>>(d_in, d_out, d_status, npackets, as_built, 0, 0);
   }
   count_launch();
+  DVBT_CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+// TS packets -> energy dispersal -> RS(204,188) -> Forney interleaver (all on the device); ed / rs / ci are npk x 188 / 204 / 204 bytes
+int tx_outer_launch(const uint8_t *d_ts, long long npk, const uint8_t *d_prbs, uint8_t *d_ed, uint8_t *d_rs, uint8_t *d_ci, cudaStream_t st) {
+  if (npk <= 0) return 0;
+  int rc = rs_upload_tables();
+  if (rc) return rc;
+  tx_outer_kernel<<<(unsigned)((npk + 127) / 128), 128, 0, st>>>(d_ts, npk, d_prbs, d_ed, d_rs);
+  const long long nb = npk * 204;
+  tx_outer_interleave_kernel<<<(unsigned)((nb + 255) / 256), 256, 0, st>>>(d_rs, nb, d_ci);
+  count_launch(2);
   DVBT_CUDA_TRY(cudaGetLastError());
   return 0;
 }

@@ -215,7 +215,7 @@ struct DescrState {
   int n_pairs;             // pairs of groups emitted by the last plan
   int n_tail;              // 1: one more single group follows the pairs (end of stream only)
   long long items_used;    // 8-packet items consumed by the last plan
-  long long first_packet;  // stream packet number of the first packet ever emitted, -1: none yet (info)
+  long long first_packet1; // 1 + stream packet number of the first packet ever emitted, 0: none yet (info; all-zero = a new stream)
   long long packets_seen;  // packets consumed before the pending ones (stream position of pending packet 0)
 };
 
@@ -228,7 +228,7 @@ __global__ void __launch_bounds__(1024) rx_descr_plan_kernel(const uint8_t *__re
   const int t = threadIdx.x;
   long long i = 0;          // item index of the next call
   int pk = st->pk, np = 0;
-  long long first_packet = st->first_packet;
+  long long first_packet = st->first_packet1 - 1;
   const long long seen = st->packets_seen;
   const long long calls_strict = npk >= 32 ? (npk - 32) / 16 + 1 : 0;   // a call at item i needs items i .. i+3 visible
   long long calls_total = calls_strict;
@@ -287,7 +287,7 @@ __global__ void __launch_bounds__(1024) rx_descr_plan_kernel(const uint8_t *__re
     st->n_pairs = np;
     st->n_tail = tail;
     st->items_used = i;
-    st->first_packet = first_packet;
+    st->first_packet1 = first_packet + 1;
     st->packets_seen = seen + 8 * i;
   }
 }
@@ -345,7 +345,7 @@ struct dvbt_b200_rx {
   cudaStream_t stream = nullptr;
   int fi_start = 3, rs_as_built = 0, sm_count = 148;
   int k = 1, n = 2, m = 4, ntb = 5, vit_in_block = 0, vit_out_block = 0;
-  dvbt::DevBuf d_state, d_fo, d_rot, d_mod, d_tps, d_vote, d_Y, d_rsst, d_ts, d_prbs, h_state, h_info, d_sync, d_plan, d_dstate;
+  dvbt::DevBuf d_state, d_fo, d_rot, d_mod, d_tps, d_vote, d_Y, d_rsst, d_ts, d_prbs, h_state, h_info, d_sync, h_sync, d_plan, d_dstate;
   dvbt_b200_rx_info info;
   cudaEvent_t ev[10];
 
@@ -409,7 +409,7 @@ int reserve_keep(dvbt::DevBuf &b, size_t bytes, size_t keep, cudaStream_t st) {
   int rc = bigger.reserve(bytes + bytes / 4);
   if (rc) return rc;
   DVBT_CUDA_TRY(cudaMemcpyAsync(bigger.p, b.p, keep, cudaMemcpyDeviceToDevice, st));
-  DVBT_CUDA_TRY(cudaStreamSynchronize(st));
+  DVBT_CUDA_TRY(dvbt::stream_wait(st));
   b.release();
   b = bigger;
   return 0;
@@ -641,13 +641,13 @@ int rx_back_end(dvbt_b200_rx *h, int nrows, bool end, uint8_t *ts_host, uint8_t 
   h->descr_pending_shift = true;
   long long nbytes = (long long)ds->n_pairs * 3008 + (long long)ds->n_tail * 1504;
   if (nbytes > (long long)cap) nbytes = (long long)(cap / 3008) * 3008;
-  h->info.first_packet = ds->first_packet;
+  h->info.first_packet = ds->first_packet1 - 1;
   h->info.ts_bytes = nbytes;
   h->ts_total += nbytes;
   h->info.ts_total = h->ts_total;
   if (ts_host && nbytes > 0) {
     DVBT_CUDA_TRY(cudaMemcpyAsync(ts_host, ts_out, (size_t)nbytes, cudaMemcpyDeviceToHost, st));
-    DVBT_CUDA_TRY(cudaStreamSynchronize(st));
+    DVBT_CUDA_TRY(dvbt::stream_wait(st));
   }
   if (ts_bytes) *ts_bytes = (size_t)nbytes;
   float ms;
@@ -698,9 +698,11 @@ int rx_from_symbols(dvbt_b200_rx *h, const float2 *X, size_t nsym, bool x_is_int
     }
     h->info.n_sync_start += (long long)sync_rows.size();
     if (!sync_rows.empty()) {
-      if ((rc = h->d_sync.reserve(sync_rows.size() * 4))) return rc;
-      DVBT_CUDA_TRY(cudaMemcpyAsync(h->d_sync.p, sync_rows.data(), sync_rows.size() * 4, cudaMemcpyHostToDevice, st));
-      DVBT_CUDA_TRY(cudaStreamSynchronize(st));                 // sync_rows is a local (the tags are rare)
+      // through a pinned buffer of the handle: it is not written again before the call's final stream synchronisation
+      h->h_sync.host = true;
+      if ((rc = h->d_sync.reserve(sync_rows.size() * 4)) || (rc = h->h_sync.reserve(sync_rows.size() * 4))) return rc;
+      memcpy(h->h_sync.p, sync_rows.data(), sync_rows.size() * 4);
+      DVBT_CUDA_TRY(cudaMemcpyAsync(h->d_sync.p, h->h_sync.p, sync_rows.size() * 4, cudaMemcpyHostToDevice, st));
     }
     dvbt::DemodBuffers b{h->d_fo.as<int>(), h->d_rot.as<float2>(), h->d_mod.as<int>(), h->d_tps.as<float2>(), h->d_vote.as<int>(),
                          h->d_osym[h->cur].as<int>() + c, h->d_osrc[h->cur].as<int>() + c, h->ev[8], h->ev[9]};
@@ -720,7 +722,7 @@ int rx_from_symbols(dvbt_b200_rx *h, const float2 *X, size_t nsym, bool x_is_int
       }
       h->sym_carry = 1;
     }
-    DVBT_CUDA_TRY(cudaStreamSynchronize(st));
+    DVBT_CUDA_TRY(dvbt::stream_wait(st));
     const dvbt::DemodState *S = h->h_state.as<dvbt::DemodState>();
     if (S->n_sf > dvbt::kMaxSfTags) {
       set_error("rx: %d re-synchronisations in one batch (at most %d): feed the capture in smaller pieces", S->n_sf, dvbt::kMaxSfTags);
@@ -857,13 +859,7 @@ int rx_push(dvbt_b200_rx *h, int level, const void *data, size_t count, float ga
     rx_stream_reset(h);
     rx_info_reset(h);
     DVBT_CUDA_TRY(cudaMemsetAsync(h->d_state.p, 0, sizeof(dvbt::DemodState), st));
-    DescrState ds0;
-    memset(&ds0, 0, sizeof ds0);
-    ds0.first_packet = -1;
-    DescrState *hd = h->h_info.as<DescrState>();
-    *hd = ds0;
-    DVBT_CUDA_TRY(cudaMemcpyAsync(h->d_dstate.p, hd, sizeof(DescrState), cudaMemcpyHostToDevice, st));
-    DVBT_CUDA_TRY(cudaStreamSynchronize(st));   // h_info is reused for the read-back at the end of the call
+    DVBT_CUDA_TRY(cudaMemsetAsync(h->d_dstate.p, 0, sizeof(DescrState), st));   // NSYNC index 0, nothing emitted yet
     if ((rc = h->d_D.reserve(kOuterHist + 4096))) return rc;
     DVBT_CUDA_TRY(cudaMemsetAsync(h->d_D.p, 0, kOuterHist, st));   // the delay lines start zeroed (convolutional_deinterleaver_impl.cc:62-64)
     dvbt::vit_stream_reset(h->vit);
@@ -950,21 +946,7 @@ int dvbt_b200_rx_create(const dvbt_b200_rx_params *p, dvbt_b200_rx **out) {
   // byte, clocked but unused on every sync byte except the first of the group
   {
     uint8_t tab[1504];
-    unsigned reg = 0xa9;
-    auto clock8 = [&]() {
-      unsigned res = 0;
-      for (int i = 0; i < 8; i++) {
-        unsigned fb = ((reg >> 13) ^ (reg >> 14)) & 1u;
-        reg = ((reg << 1) | fb) & 0x7fff;
-        res = (res << 1) | fb;
-      }
-      return (uint8_t)res;
-    };
-    for (int pk = 0; pk < 8; pk++) {
-      tab[pk * 188] = 0;
-      for (int k = 1; k < 188; k++) tab[pk * 188 + k] = clock8();
-      clock8();
-    }
+    dvbt::energy_prbs_table(tab);
     if ((rc = h->d_prbs.reserve(1504))) { dvbt_b200_rx_destroy(h); return rc; }
     if (cudaMemcpy(h->d_prbs.p, tab, 1504, cudaMemcpyHostToDevice) != cudaSuccess) { set_error("rx_create: PRBS table upload failed"); dvbt_b200_rx_destroy(h); return DVBT_B200_ECUDA; }
   }
@@ -982,7 +964,7 @@ void dvbt_b200_rx_destroy(dvbt_b200_rx *h) {
   if (!h) return;
   if (h->stream) cudaStreamSynchronize(h->stream);
   dvbt::DevBuf *bufs[] = {&h->d_state, &h->d_fo, &h->d_rot, &h->d_mod, &h->d_tps, &h->d_vote, &h->d_Y, &h->d_rsst, &h->d_ts, &h->d_prbs, &h->h_state,
-                          &h->h_info, &h->d_sync, &h->d_plan, &h->d_dstate, &h->d_file, &h->d_file2, &h->d_samples, &h->d_samples2, &h->d_sym,
+                          &h->h_info, &h->d_sync, &h->h_sync, &h->d_plan, &h->d_dstate, &h->d_file, &h->d_file2, &h->d_samples, &h->d_samples2, &h->d_sym,
                           &h->d_sym2, &h->d_dm[0], &h->d_dm[1], &h->d_osym[0], &h->d_osym[1], &h->d_osrc[0], &h->d_osrc[1], &h->d_D, &h->d_D2,
                           &h->d_rs, &h->d_rs2, &h->d_vit_tap};
   for (auto *b : bufs) b->release();
@@ -1034,7 +1016,7 @@ int dvbt_b200_rx_run_file_dev(dvbt_b200_rx *h, const void *data, size_t count, f
 int dvbt_b200_rx_stream_reset(dvbt_b200_rx *h) {
   dvbt::DeviceScope dev_scope__(h ? h->device : -1);
   if (!h) { set_error("rx_stream_reset: null handle"); return DVBT_B200_EINVAL; }
-  DVBT_CUDA_TRY(cudaStreamSynchronize(h->stream));
+  DVBT_CUDA_TRY(dvbt::stream_wait(h->stream));
   rx_stream_reset(h);
   rx_info_reset(h);
   return 0;

@@ -338,6 +338,32 @@ int dvbt_b200_rx_last_info(const dvbt_b200_rx *h, dvbt_b200_rx_info *info);
 /* copies an intermediate of the last run to the host (parity tests): DVBT_RX_STAGE_* */
 int dvbt_b200_rx_read_stage(dvbt_b200_rx *h, int stage, void *host_out, size_t capacity_bytes, size_t *nbytes);
 
+/* ------------------------------------------------------------------------------------
+ * Transmit chain on the device: apps/dvbt_tx_demo*.grc as a synthetic-input generator
+ * for the receive path - energy_dispersal -> reed_solomon_enc -> convolutional_interleaver(136,12,17) ->
+ * inner_coder (lib/inner_coder_impl.cc:34-121, :226-262) -> bit_inner_interleaver -> symbol_inner_interleaver ->
+ * dvbt_map (lib/dvbt_map_impl.cc:100-170) -> reference_signals (lib/reference_signals_impl.cc:1126-1186) ->
+ * fft_vxx(reverse, shift=True) -> ofdm_cyclic_prefixer -> multiply_const(gain) -> rational_resampler_ccc(70, 64).
+ * The gr-dvbt stages are bit-exact against the reference's blocks (read_stage taps); IFFT / prefix / resampler
+ * are stock GNU Radio blocks restated from their documented behaviour (parity unpinned, like the RX front end).
+ * npackets TS packets of 188 bytes (sync byte 0x47 first; whole groups of 8 are used) give
+ * nsym = floor(npackets*204 / (P*m*k/(8n)) / 4) * 4 OFDM symbols.  level: DVBT_RX_LEVEL_FREQ = nsym x N
+ * frequency-domain symbols (DC at bin N/2, what demod_reference_signals receives after a perfect channel),
+ * DVBT_RX_LEVEL_BASEBAND = nsym x (N + cp) samples at the OFDM rate, DVBT_RX_LEVEL_FILE = the 10 Msps capture.
+ * *count = complex values written.
+ * ------------------------------------------------------------------------------------ */
+typedef struct dvbt_b200_tx dvbt_b200_tx;
+enum { DVBT_TX_STAGE_ENERGY = 0, DVBT_TX_STAGE_RS = 1, DVBT_TX_STAGE_OUTER = 2, DVBT_TX_STAGE_INNER_CODER = 3,
+       DVBT_TX_STAGE_BIT_INTERLEAVER = 4, DVBT_TX_STAGE_SYMBOL_INTERLEAVER = 5 };
+int dvbt_b200_tx_create(const dvbt_b200_rx_params *p, dvbt_b200_tx **out);
+void dvbt_b200_tx_destroy(dvbt_b200_tx *h);
+int dvbt_b200_tx_run_host(dvbt_b200_tx *h, const uint8_t *ts, size_t npackets, int level, float gain, void *out, size_t capacity,
+                          size_t *count, size_t *nsym);
+int dvbt_b200_tx_run_dev(dvbt_b200_tx *h, const uint8_t *d_ts, size_t npackets, int level, float gain, void *d_out, size_t capacity,
+                         size_t *count, size_t *nsym);
+/* intermediates of the last run, to the host: DVBT_TX_STAGE_* (bytes) */
+int dvbt_b200_tx_read_stage(dvbt_b200_tx *h, int stage, void *host_out, size_t capacity_bytes, size_t *nbytes);
+
 #ifdef __cplusplus
 }
 #endif

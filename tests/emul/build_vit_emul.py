@@ -164,12 +164,12 @@ extern "C" int emul_descramble_stream(const uint8_t *rs, long long npk, const ui
   DescrState st;
   memset(&st, 0, sizeof st);
   st.pk = *pk_io;
-  st.first_packet = -1;
+  st.first_packet1 = 0;
   std::vector<int> plan((size_t)(npk / 16 + 2));
   emul_launch(rx_descr_plan_kernel, 1u, 1024u, rs, npk, &st, plan.data(), (long long)plan.size(), end);
   emul_launch(rx_descramble_kernel, (unsigned)grid, 256u, rs, (const DescrState *)&st, (const int *)plan.data(), prbs, ts, ts_capacity);
   *pk_io = st.pk;
-  *first_packet = st.first_packet;
+  *first_packet = st.first_packet1 - 1;
   *ngroups = 2LL * st.n_pairs + st.n_tail;
   *items_used = st.items_used;
   return 0;

@@ -42,7 +42,7 @@ template <class T> static inline size_t __cvta_generic_to_shared(T *) { return 0
 
 // ---- runtime API
 typedef int cudaError_t;
-enum { cudaSuccess = 0, cudaErrorEmul = 1 };
+enum { cudaSuccess = 0, cudaErrorEmul = 1, cudaErrorNotReady = 600 };
 typedef struct emul_stream *cudaStream_t;
 typedef struct emul_event *cudaEvent_t;
 #define cudaStreamLegacy ((cudaStream_t)0)
@@ -77,6 +77,7 @@ static inline cudaError_t cudaStreamCreateWithFlags(cudaStream_t *s, unsigned) {
 static inline cudaError_t cudaStreamCreate(cudaStream_t *s) { *s = (cudaStream_t)1; return cudaSuccess; }
 static inline cudaError_t cudaStreamDestroy(cudaStream_t) { return cudaSuccess; }
 static inline cudaError_t cudaStreamSynchronize(cudaStream_t) { return cudaSuccess; }
+static inline cudaError_t cudaStreamQuery(cudaStream_t) { return cudaSuccess; }
 static inline cudaError_t cudaDeviceSynchronize() { return cudaSuccess; }
 static inline cudaError_t cudaStreamWaitEvent(cudaStream_t, cudaEvent_t, unsigned = 0) { return cudaSuccess; }
 static inline cudaError_t cudaEventCreate(cudaEvent_t *e) { *e = (cudaEvent_t)1; return cudaSuccess; }
