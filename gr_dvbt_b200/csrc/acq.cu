@@ -1136,6 +1136,7 @@ struct dvbt_b200_acq {
   cudaEvent_t ev_fft[2 * kFftEv] = {nullptr};
   int n_fft_ev = 0;
   bool pending_sync = false;                // a sync_start whose item the next acq_work call produces
+  dvbt::Staging stg;                        // pinned staging of acq_work's pageable buffers
 };
 
 namespace dvbt {
@@ -1430,6 +1431,7 @@ void dvbt_b200_acq_destroy(dvbt_b200_acq *h) {
   if (h->plan) cufftDestroy(h->plan);
   dvbt::DevBuf *bufs[] = {&h->d_x, &h->d_state, &h->h_state, &h->d_lambda, &h->d_gamma, &h->d_avg1, &h->d_avg2, &h->d_peak, &h->d_sym, &h->d_out, &h->d_il, &h->d_ig, &h->d_eps, &h->d_flag, &h->d_maps, &h->d_cof, &h->d_bof, &h->d_peakof, &h->d_eof, &h->d_seg, &h->d_runs, &h->d_tw};
   for (auto *b : bufs) b->release();
+  h->stg.release();
   for (auto &e : h->ev_fft) if (e) cudaEventDestroy(e);
   if (h->stream && h->own_stream) cudaStreamDestroy(h->stream);
   delete h;
@@ -1445,12 +1447,12 @@ int dvbt_b200_acq_work(dvbt_b200_acq *h, const void *in, size_t n_in_items, void
   int rc;
   const int N = h->kp.N;
   if ((rc = h->d_x.reserve(n_in_items * 8)) || (rc = h->d_out.reserve(out_capacity_items * N * 8))) return rc;
-  DVBT_CUDA_TRY(cudaMemcpyAsync(h->d_x.p, in, n_in_items * 8, cudaMemcpyHostToDevice, h->stream));
+  if ((rc = h->stg.h2d(h->d_x.p, in, n_in_items * 8, h->stream))) return rc;
   AcqState hs;
   std::vector<long long> sync_at;
   rc = dvbt::acq_run(h, h->d_x.as<float2>(), (long long)n_in_items, h->d_out.as<float2>(), (long long)out_capacity_items, apply_fft, &hs, &sync_at);
   if (rc) return rc;
-  if (hs.n_out > 0) DVBT_CUDA_TRY(cudaMemcpyAsync(out, h->d_out.p, (size_t)hs.n_out * N * 8, cudaMemcpyDeviceToHost, h->stream));
+  if (hs.n_out > 0 && (rc = h->stg.d2h(out, h->d_out.p, (size_t)hs.n_out * N * 8, h->stream))) return rc;
   DVBT_CUDA_TRY(dvbt::stream_wait(h->stream));
   *consumed = (size_t)hs.consumed;
   *produced = (size_t)hs.n_out;

@@ -3,6 +3,7 @@
 #include "chain_internal.cuh"
 
 #include <atomic>
+#include <string.h>
 
 namespace dvbt {
 
@@ -26,6 +27,79 @@ int ensure_device() {
               e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
     cudaGetLastError();
     return DVBT_B200_ENODEV;
+  }
+  return 0;
+}
+
+int Staging::ensure() {
+  for (int b = 0; b < 2; b++) {
+    if (!pin[b] && cudaMallocHost(&pin[b], kChunk) != cudaSuccess) { pin[b] = nullptr; set_error("staging: cudaMallocHost failed"); return DVBT_B200_ENOMEM; }
+    if (!ev[b]) DVBT_CUDA_TRY(cudaEventCreateWithFlags(&ev[b], cudaEventDisableTiming));
+  }
+  return 0;
+}
+
+void Staging::release() {
+  for (int b = 0; b < 2; b++) {
+    if (pin[b]) cudaFreeHost(pin[b]);
+    if (ev[b]) cudaEventDestroy(ev[b]);
+    pin[b] = nullptr;
+    ev[b] = nullptr;
+  }
+}
+
+static bool host_pointer_is_pinned(const void *p) {
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+  return a.type == cudaMemoryTypeHost;
+}
+
+static cudaError_t event_wait_yield(cudaEvent_t e) { return cudaEventSynchronize(e); }
+
+int Staging::h2d(void *d_dst, const void *h_src, size_t bytes, cudaStream_t st) {
+  if (bytes == 0) return 0;
+  if (bytes < 65536 || host_pointer_is_pinned(h_src)) {
+    DVBT_CUDA_TRY(cudaMemcpyAsync(d_dst, h_src, bytes, cudaMemcpyHostToDevice, st));
+    return 0;
+  }
+  if (int rc = ensure()) return rc;
+  size_t off = 0;
+  for (int i = 0; off < bytes; i++) {
+    const int b = i & 1;
+    const size_t n = bytes - off < kChunk ? bytes - off : kChunk;
+    if (i >= 2) DVBT_CUDA_TRY(event_wait_yield(ev[b]));       // the DMA that last read this pinned buffer is done
+    memcpy(pin[b], (const char *)h_src + off, n);
+    DVBT_CUDA_TRY(cudaMemcpyAsync((char *)d_dst + off, pin[b], n, cudaMemcpyHostToDevice, st));
+    DVBT_CUDA_TRY(cudaEventRecord(ev[b], st));
+    off += n;
+  }
+  // the pinned buffers are reused by the next call: its first two chunks must not overtake this call's DMAs
+  DVBT_CUDA_TRY(event_wait_yield(ev[0]));
+  DVBT_CUDA_TRY(event_wait_yield(ev[1]));
+  return 0;
+}
+
+int Staging::d2h(void *h_dst, const void *d_src, size_t bytes, cudaStream_t st) {
+  if (bytes == 0) return 0;
+  if (bytes < 65536 || host_pointer_is_pinned(h_dst)) {
+    DVBT_CUDA_TRY(cudaMemcpyAsync(h_dst, d_src, bytes, cudaMemcpyDeviceToHost, st));
+    DVBT_CUDA_TRY(stream_wait(st));
+    return 0;
+  }
+  if (int rc = ensure()) return rc;
+  const size_t nchunks = (bytes + kChunk - 1) / kChunk;
+  auto issue = [&](size_t i) -> int {
+    const size_t off = i * kChunk, n = bytes - off < kChunk ? bytes - off : kChunk;
+    DVBT_CUDA_TRY(cudaMemcpyAsync(pin[i & 1], (const char *)d_src + off, n, cudaMemcpyDeviceToHost, st));
+    DVBT_CUDA_TRY(cudaEventRecord(ev[i & 1], st));
+    return 0;
+  };
+  if (int rc = issue(0)) return rc;
+  for (size_t i = 0; i < nchunks; i++) {
+    if (i + 1 < nchunks) { if (int rc = issue(i + 1)) return rc; }     // the other pinned buffer was drained in the previous iteration
+    DVBT_CUDA_TRY(event_wait_yield(ev[i & 1]));
+    const size_t off = i * kChunk, n = bytes - off < kChunk ? bytes - off : kChunk;
+    memcpy((char *)h_dst + off, pin[i & 1], n);
   }
   return 0;
 }

@@ -1,7 +1,6 @@
 // Internal helpers shared by the CUDA translation units of libdvbt_b200.so.
 #pragma once
 #include <cuda_runtime.h>
-#include <sched.h>
 #include <stdarg.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -57,17 +56,11 @@ inline int join_default_stream(cudaStream_t st) {
   return 0;
 }
 
-// Waits for a stream the way cudaStreamSynchronize does, but gives the core away between polls.  The library is driven by
-// one host thread per handle (GNU Radio: one per block); with as many waiting threads as cores - 8 ranks x 4 captures in
-// flight on a 32-core host - a spinning synchronise that the kernel deschedules for a time slice stalls its capture for
-// milliseconds (measured: 14 % at 8 GPUs).  sched_yield returns at once when nothing else wants the core.
-inline cudaError_t stream_wait(cudaStream_t st) {
-  for (;;) {
-    cudaError_t e = cudaStreamQuery(st);
-    if (e != cudaErrorNotReady) return e;
-    sched_yield();
-  }
-}
+// Waits for a stream.  (A polling wait that yields the core between cudaStreamQuery calls was tried for hosts with as many
+// waiting threads as cores - 8 ranks x 4 captures in flight on 32 cores - and measured on one GPU: four threads polling
+// contend with each other's kernel launches inside the driver, 12.7 ms per batch of four captures instead of 7.1.  The
+// driver's own wait it is.)
+inline cudaError_t stream_wait(cudaStream_t st) { return cudaStreamSynchronize(st); }
 
 // A growable device (or pinned-host) buffer; never shrinks.
 struct DevBuf {
@@ -101,6 +94,23 @@ struct DevBuf {
     cap = 0;
   }
   template <class T> T *as() const { return (T *)p; }
+};
+
+// Host <-> device copies of the block-level entry points (`*_work`): the scheduler's buffers are pageable, and a
+// cudaMemcpyAsync from pageable memory is staged by the driver in small pieces (measured 2-4 GB/s on the B200 boxes,
+// the whole cost of a drop-in block call).  A handle therefore stages through two pinned buffers of its own: the host
+// memcpy of one chunk runs while the DMA of the previous one is in flight.  Pinned caller memory (cudaHostAlloc /
+// cudaHostRegister) is recognised and copied directly.
+struct Staging {
+  static constexpr size_t kChunk = 2u << 20;
+  void *pin[2] = {nullptr, nullptr};
+  cudaEvent_t ev[2] = {nullptr, nullptr};
+  int ensure();
+  void release();
+  // enqueue the copy of `bytes` from host memory to device memory on `st` (returns when the host buffer has been read)
+  int h2d(void *d_dst, const void *h_src, size_t bytes, cudaStream_t st);
+  // copy device memory to host memory; returns when the host buffer holds the data (the stream's earlier work is waited for)
+  int d2h(void *h_dst, const void *d_src, size_t bytes, cudaStream_t st);
 };
 
 }  // namespace dvbt

@@ -118,6 +118,7 @@ struct dvbt_b200_demap {
   dvbt::DemapTable table;
   cudaStream_t stream = nullptr;
   dvbt::DevBuf d_in, d_out;
+  dvbt::Staging stg;
 };
 
 extern "C" {
@@ -152,6 +153,7 @@ void dvbt_b200_demap_destroy(dvbt_b200_demap *h) {
   if (h->stream) { cudaStreamSynchronize(h->stream); cudaStreamDestroy(h->stream); }
   h->d_in.release();
   h->d_out.release();
+  h->stg.release();
   delete h;
 }
 
@@ -184,11 +186,10 @@ int dvbt_b200_demap_work(dvbt_b200_demap *h, const void *in, size_t n_in_items, 
   int rc;
   if ((rc = h->d_in.reserve(ncells * 8))) return rc;
   if ((rc = h->d_out.reserve(ncells))) return rc;
-  DVBT_CUDA_TRY(cudaMemcpyAsync(h->d_in.p, in, ncells * 8, cudaMemcpyHostToDevice, h->stream));
+  if ((rc = h->stg.h2d(h->d_in.p, in, ncells * 8, h->stream))) return rc;
   rc = dvbt::demap_launch(h->table, h->d_in.as<float2>(), h->d_out.as<uint8_t>(), (long long)ncells, h->stream);
   if (rc) return rc;
-  DVBT_CUDA_TRY(cudaMemcpyAsync(out, h->d_out.p, ncells, cudaMemcpyDeviceToHost, h->stream));
-  DVBT_CUDA_TRY(cudaStreamSynchronize(h->stream));
+  if ((rc = h->stg.d2h(out, h->d_out.p, ncells, h->stream))) return rc;
   *consumed = *produced = noutput_items;  // 1:1 (dvbt_demap_impl.cc:211-215, :236-239)
   return 0;
 }

@@ -801,6 +801,7 @@ struct dvbt_b200_demod {
   dvbt::DevBuf d_X, d_Y, d_Yc, d_state, d_fo, d_rot, d_mod, d_tps, d_vote, d_osym, d_osrc, h_state;
   int fi_start = 3;
   bool pending_sync = false;
+  dvbt::Staging stg;
 };
 
 namespace {
@@ -848,6 +849,7 @@ void dvbt_b200_demod_destroy(dvbt_b200_demod *h) {
   if (h->stream) { cudaStreamSynchronize(h->stream); cudaStreamDestroy(h->stream); }
   dvbt::DevBuf *bufs[] = {&h->d_X, &h->d_Y, &h->d_Yc, &h->d_state, &h->d_fo, &h->d_rot, &h->d_mod, &h->d_tps, &h->d_vote, &h->d_osym, &h->d_osrc, &h->h_state};
   for (auto *b : bufs) b->release();
+  h->stg.release();
   h->tables.release();
   delete h;
 }
@@ -884,7 +886,7 @@ int dvbt_b200_demod_work(dvbt_b200_demod *h, const void *in, size_t n_in_items, 
   if ((rc = h->d_vote.reserve(nparse * 4))) return rc;
   if ((rc = h->d_osym.reserve(nparse * 4))) return rc;
   if ((rc = h->d_osrc.reserve(nparse * 4))) return rc;
-  DVBT_CUDA_TRY(cudaMemcpyAsync(h->d_X.p, in, nsym * md.N * 8, cudaMemcpyHostToDevice, h->stream));
+  if ((rc = h->stg.h2d(h->d_X.p, in, nsym * md.N * 8, h->stream))) return rc;
   dvbt::DemodBuffers b{h->d_fo.as<int>(), h->d_rot.as<float2>(), h->d_mod.as<int>(), h->d_tps.as<float2>(), h->d_vote.as<int>(),
                        h->d_osym.as<int>(), h->d_osrc.as<int>()};
   rc = dvbt::demod_run(md, nullptr, h->d_X.as<float2>(), (int)nparse, b, h->d_state.as<dvbt::DemodState>(), h->fi_start, sync0 ? 1 : 0,
@@ -899,8 +901,8 @@ int dvbt_b200_demod_work(dvbt_b200_demod *h, const void *in, size_t n_in_items, 
     demod_compact_kernel<<<(unsigned)nout, 256, 0, h->stream>>>(md.P, h->d_osrc.as<int>(), h->d_Y.as<float2>(), h->d_Yc.as<float2>());
     dvbt::count_launch();
     DVBT_CUDA_TRY(cudaGetLastError());
-    DVBT_CUDA_TRY(cudaMemcpyAsync(out, h->d_Yc.p, nout * md.P * 8, cudaMemcpyDeviceToHost, h->stream));
     DVBT_CUDA_TRY(cudaMemcpyAsync(symidx.data(), h->d_osym.p, nout * 4, cudaMemcpyDeviceToHost, h->stream));
+    if ((rc = h->stg.d2h(out, h->d_Yc.p, nout * md.P * 8, h->stream))) return rc;
     DVBT_CUDA_TRY(cudaStreamSynchronize(h->stream));
   }
   // tags: superframe_start (0xaa) on the first output after sync, symbol_index on every output (:126-143)

@@ -364,6 +364,7 @@ struct dvbt_b200_rsdec {
   int as_built = 0;
   cudaStream_t stream = nullptr;
   dvbt::DevBuf d_in, d_out;
+  dvbt::Staging stg;
   int sm_count = 148;
 };
 
@@ -472,6 +473,7 @@ void dvbt_b200_rsdec_destroy(dvbt_b200_rsdec *h) {
   if (h->stream) { cudaStreamSynchronize(h->stream); cudaStreamDestroy(h->stream); }
   h->d_in.release();
   h->d_out.release();
+  h->stg.release();
   delete h;
 }
 
@@ -507,11 +509,10 @@ int dvbt_b200_rsdec_work(dvbt_b200_rsdec *h, const uint8_t *in, size_t n_in_item
   int rc;
   if ((rc = h->d_in.reserve(npk * kPktIn))) return rc;
   if ((rc = h->d_out.reserve(npk * kPktOut))) return rc;
-  DVBT_CUDA_TRY(cudaMemcpyAsync(h->d_in.p, in, npk * kPktIn, cudaMemcpyHostToDevice, h->stream));
+  if ((rc = h->stg.h2d(h->d_in.p, in, npk * kPktIn, h->stream))) return rc;
   rc = dvbt::rs_launch(h->d_in.as<uint8_t>(), h->d_out.as<uint8_t>(), nullptr, (long long)npk, h->as_built, h->sm_count, h->stream, -1, 0);
   if (rc) return rc;
-  DVBT_CUDA_TRY(cudaMemcpyAsync(out, h->d_out.p, npk * kPktOut, cudaMemcpyDeviceToHost, h->stream));
-  DVBT_CUDA_TRY(cudaStreamSynchronize(h->stream));
+  if ((rc = h->stg.d2h(out, h->d_out.p, npk * kPktOut, h->stream))) return rc;
   *consumed = noutput_items;
   *produced = noutput_items;
   return 0;
