@@ -751,10 +751,19 @@ def main():
         # the only collective on this path: the configuration
         cfg = broadcast_config([a.mbit, a.steps, a.warmup, a.tiles], "cuda")
         a.mbit, a.steps, a.warmup, a.tiles = float(cfg[0]), int(cfg[1]), int(cfg[2]), int(cfg[3])
+    # the SASS facts of the roofline record come from cuobjdump in a CHILD PROCESS: parsing 9 MB of SASS in a thread of this
+    # process holds the interpreter lock for seconds and adds 5 ms switch intervals to every timed step beside it
     facts_box = {}
     facts_thread = None
     if RANK == 0:
-        facts_thread = threading.Thread(target=lambda: facts_box.update(sass_facts()), daemon=True)
+        def _facts():
+            try:
+                r = subprocess.run([sys.executable, "-c", "import json, bench; print(json.dumps(bench.sass_facts()))"], cwd=ROOT,
+                                   capture_output=True, text=True, timeout=300)
+                facts_box.update(json.loads(r.stdout.strip().splitlines()[-1]))
+            except Exception as e:
+                facts_box.update({"error": repr(e)[:200]})
+        facts_thread = threading.Thread(target=_facts, daemon=True)
         facts_thread.start()
 
     lib = g.capi.lib()
@@ -1134,6 +1143,7 @@ def drop_in_leg_at(g, w, IPC):
 
     # ofdm_sym_acquisition (+ FFT folded in, as the shim does with apply_fft): 64 symbols per call (shim: set_min_noutput_items(64))
     acq = g.ofdm_sym_acquisition(1, N, w.N * 0 + (1705 if N == 2048 else 6817), cp, 30.0)
+    g.ofdm_sym_acquisition(1, N, 1705 if N == 2048 else 6817, cp, 30.0).general_work(bb[: 2 * N + cp + 32 + (IPC - 1) * total], out_capacity=IPC, apply_fft=True)   # untimed: first-use costs of the process (module load, pinned staging)
     pos, syms, calls, t = 0, [], 0, 0.0
     while len(syms) < nsym // IPC and pos + (IPC + 2) * total < len(bb):
         chunk = bb[pos: pos + 2 * N + cp + 32 + (IPC - 1) * total]
@@ -1148,6 +1158,7 @@ def drop_in_leg_at(g, w, IPC):
     record("ofdm_sym_acquisition+fft", t, calls, IPC)
     # demod_reference_signals: 64 symbols per call (65 visible)
     dem = g.demod_reference_signals(8, N, P, w.CON, g.NH, w.CR, w.CR, g.G1_32, w.TM, 0, 0)
+    g.demod_reference_signals(8, N, P, w.CON, g.NH, w.CR, w.CR, g.G1_32, w.TM, 0, 0).general_work(X[: IPC + 1], tags=[(0, "sync_start", 1)])   # untimed warm-up
     t, calls, ys, first = 0.0, 0, [], True
     for i in range(0, len(X) - IPC - 1, IPC):
         t0 = time.perf_counter()
@@ -1162,6 +1173,7 @@ def drop_in_leg_at(g, w, IPC):
     # dvbt_demap: 64 items per call
     dm = g.dvbt_demap(P, w.CON, g.NH, w.TM, 1.0)
     reps = max(1, nsym // max(len(Y), 1))
+    dm.general_work(IPC, Y[:IPC])   # untimed warm-up
     t, calls = 0.0, 0
     for _ in range(reps):
         for i in range(0, len(Y) - IPC + 1, IPC):
@@ -1176,6 +1188,7 @@ def drop_in_leg_at(g, w, IPC):
     vit = g.viterbi_decoder(w.CON, g.NH, w.CR)
     nsymb, nout = 768 * w.n // w.m, 96 * w.k
     need = nsym * P
+    g.viterbi_decoder(w.CON, g.NH, w.CR).general_work(IPC * nout, vin[: IPC * nsymb], tags=[(0, "superframe_start", 1)])   # untimed warm-up
     t, calls, pos = 0.0, 0, 0
     while pos + IPC * nsymb <= min(need, len(vin)):
         t0 = time.perf_counter()
@@ -1190,6 +1203,7 @@ def drop_in_leg_at(g, w, IPC):
     src = tt - 204 * (11 - tt % 12)
     pk = np.where(src >= 0, vo[np.clip(src, 0, None)], 0).astype(np.uint8)
     rs = g.reed_solomon_dec(2, 8, 0x11D, 255, 239, 8, 51, 8)
+    rs.general_work(IPC, pk[: IPC * 1632])   # untimed warm-up
     t, calls = 0.0, 0
     for i in range(0, npk // 8 - IPC + 1, IPC):
         t0 = time.perf_counter()

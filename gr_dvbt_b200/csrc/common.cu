@@ -3,6 +3,7 @@
 #include "chain_internal.cuh"
 
 #include <atomic>
+#include <stdlib.h>
 #include <string.h>
 
 namespace dvbt {
@@ -29,6 +30,21 @@ int ensure_device() {
     return DVBT_B200_ENODEV;
   }
   return 0;
+}
+
+cudaError_t stream_wait(cudaStream_t st) {
+  static const bool blocking = getenv("DVBT_B200_BLOCKING_WAIT") && atoi(getenv("DVBT_B200_BLOCKING_WAIT")) != 0;
+  if (!blocking) return cudaStreamSynchronize(st);
+  thread_local cudaEvent_t ev[64] = {nullptr};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return cudaStreamSynchronize(st);
+  if (!ev[dev]) {
+    cudaError_t e = cudaEventCreateWithFlags(&ev[dev], cudaEventBlockingSync | cudaEventDisableTiming);
+    if (e != cudaSuccess) { ev[dev] = nullptr; return cudaStreamSynchronize(st); }
+  }
+  cudaError_t e = cudaEventRecord(ev[dev], st);
+  if (e != cudaSuccess) return e;
+  return cudaEventSynchronize(ev[dev]);
 }
 
 int Staging::ensure() {

@@ -56,11 +56,13 @@ inline int join_default_stream(cudaStream_t st) {
   return 0;
 }
 
-// Waits for a stream.  (A polling wait that yields the core between cudaStreamQuery calls was tried for hosts with as many
-// waiting threads as cores - 8 ranks x 4 captures in flight on 32 cores - and measured on one GPU: four threads polling
-// contend with each other's kernel launches inside the driver, 12.7 ms per batch of four captures instead of 7.1.  The
-// driver's own wait it is.)
-inline cudaError_t stream_wait(cudaStream_t st) { return cudaStreamSynchronize(st); }
+// Waits for a stream.  Default: cudaStreamSynchronize (the driver spins - lowest latency, right for one thread per GPU).
+// DVBT_B200_BLOCKING_WAIT=1: record an event created with cudaEventBlockingSync and sleep on it - for hosts that drive more
+// waiting threads than they have cores to spin on (8 ranks x 4 captures in flight on 32 cores lost 14 % to descheduled
+// spinners); the wake-up latency is hidden when other captures keep the GPU busy.  (A polling wait that yields the core
+// between cudaStreamQuery calls was tried too: four polling threads contend with each other's kernel launches inside the
+// driver, 12.7 ms per batch of four captures instead of 7.1.)
+cudaError_t stream_wait(cudaStream_t st);
 
 // A growable device (or pinned-host) buffer; never shrinks.
 struct DevBuf {

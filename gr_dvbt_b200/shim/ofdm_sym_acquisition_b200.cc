@@ -28,10 +28,10 @@ class ofdm_sym_acquisition_b200 : public ofdm_sym_acquisition {
   }
 
   int general_work(int noutput_items, gr_vector_int &ninput_items, gr_vector_const_void_star &input_items, gr_vector_void_star &output_items) {
-    dvbt_b200_tag tout[4];
+    dvbt_b200_tag tout[64];   // one sync_start per (re)acquisition inside the call
     size_t consumed = 0, produced = 0, ntout = 0;
     b200::check(dvbt_b200_acq_work(d_h, input_items[0], (size_t)ninput_items[0], output_items[0], (size_t)noutput_items, &consumed, &produced, tout,
-                                   4, &ntout, 0),
+                                   64, &ntout, 0),
                 "ofdm_sym_acquisition");
     b200::emit_tags(this, nitems_written(0), tout, ntout);
     consume_each((int)consumed);
