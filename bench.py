@@ -803,17 +803,20 @@ def main():
         """bare pinned cudaMemcpyAsync of one capture on every rank at once: what the box gives the e2e legs"""
         h = torch.empty(nbytes, dtype=torch.uint8).pin_memory()
         d = torch.empty(nbytes, dtype=torch.uint8, device="cuda")
-        for _ in range(2):
+        for _ in range(3):
             d.copy_(h, non_blocking=True)
-        barrier()
-        t0 = time.perf_counter()
-        for _ in range(reps):
-            d.copy_(h, non_blocking=True)
-        torch.cuda.synchronize()
-        ms = max_over_ranks((time.perf_counter() - t0) * 1e3, "cuda")
+        best = None
+        for _round in range(3):                                   # best of three rounds: a roof, not an average
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(reps):
+                d.copy_(h, non_blocking=True)
+            torch.cuda.synchronize()
+            ms = max_over_ranks((time.perf_counter() - t0) * 1e3, "cuda")
+            best = ms if best is None else min(best, ms)
         barrier()
         del h, d
-        return nbytes * reps * WORLD / (ms / 1e3) / 1e9
+        return nbytes * reps * WORLD / (best / 1e3) / 1e9
 
     def rx_legs(w, steps, warm, sampler=None, full=True):
         """resident (one capture at a time, then NCONC in flight) and host-buffer legs of one RX configuration"""
@@ -1119,104 +1122,130 @@ def drop_in_leg(g, w):
 
 def drop_in_leg_at(g, w, IPC):
     """What a gr-dvbt flowgraph gets with the five hot blocks swapped for the shims: the block-level `*_work` entry points
-    (include/dvbt_b200.h) called the way the GNU Radio scheduler calls them - pageable host buffers, one call per work item
-    batch (sizes: the shims' set_min_noutput_items / output multiples), H2D + kernels + D2H + stream sync inside every call.
-    Each block is timed on its own over the same 2176-symbol stretch (GNU Radio runs one thread per block, so the chain
-    runs at the pace of the slowest block); inputs of the later blocks come from the fused chain's stage taps."""
+    (include/dvbt_b200.h) called the way a C++ shim under the GNU Radio scheduler calls them - pageable host buffers that are
+    allocated ONCE and reused (the scheduler's ring buffers), one call per batch of IPC work items, staging + H2D + kernels +
+    D2H + stream sync inside every call; the ctypes call is the only Python on the timed path.  Each block is timed on its own
+    over the same stretch (GNU Radio runs one thread per block, so the chain runs at the pace of the slowest block); inputs of
+    the later blocks come from the earlier blocks' outputs / the fused chain's stage taps."""
     import ctypes as C
     from gr_dvbt_b200 import capi
+    L = capi.lib()
     N, P, cp = w.N, w.P, w.N // 32
     nsym = max(2176, 8 * IPC)
     total = N + cp
+    sz = C.c_size_t
     # baseband for acquisition: the front end (a stock GNU Radio block in the flowgraph) run once on the GPU
     ncap = (nsym + 8) * total * 35 // 32 + 4000
     cap = w.pin_in[:ncap].numpy().copy()                      # pageable
     bb = np.zeros(len(cap), np.complex64)
-    nbb = C.c_size_t(0)
-    capi.check(capi.lib().dvbt_b200_resample_host(cap.ctypes.data, len(cap), w.GAIN, bb.ctypes.data, len(bb), C.byref(nbb), -1))
+    nbb = sz(0)
+    capi.check(L.dvbt_b200_resample_host(cap.ctypes.data, len(cap), w.GAIN, bb.ctypes.data, len(bb), C.byref(nbb), -1))
     bb = bb[: nbb.value].copy()
     res = {"ofdm_symbols": nsym, "samples_10msps_equivalent": nsym * total * 35 / 32.0, "blocks": {}}
     samples = res["samples_10msps_equivalent"]
 
-    def record(name, seconds, calls, items):
-        res["blocks"][name] = {"seconds": seconds, "calls": calls, "items_per_call": items, "msamples_per_s": samples / 1e6 / seconds, "us_per_call": seconds / max(calls, 1) * 1e6}
+    def record(name, seconds, calls, items, done_syms):
+        per_nsym = seconds * nsym / max(done_syms, 1)         # the block's time for nsym symbols of the capture
+        res["blocks"][name] = {"seconds": per_nsym, "calls": calls, "items_per_call": items, "msamples_per_s": samples / 1e6 / max(per_nsym, 1e-12),
+                               "us_per_call": seconds / max(calls, 1) * 1e6}
 
-    # ofdm_sym_acquisition (+ FFT folded in, as the shim does with apply_fft): 64 symbols per call (shim: set_min_noutput_items(64))
-    acq = g.ofdm_sym_acquisition(1, N, w.N * 0 + (1705 if N == 2048 else 6817), cp, 30.0)
-    g.ofdm_sym_acquisition(1, N, 1705 if N == 2048 else 6817, cp, 30.0).general_work(bb[: 2 * N + cp + 32 + (IPC - 1) * total], out_capacity=IPC, apply_fft=True)   # untimed: first-use costs of the process (module load, pinned staging)
-    pos, syms, calls, t = 0, [], 0, 0.0
-    while len(syms) < nsym // IPC and pos + (IPC + 2) * total < len(bb):
-        chunk = bb[pos: pos + 2 * N + cp + 32 + (IPC - 1) * total]
-        t0 = time.perf_counter()
-        o, cons, _tags = acq.general_work(chunk, out_capacity=IPC, apply_fft=True)
-        t += time.perf_counter() - t0
-        pos += cons; calls += 1
-        syms.append(o)
-        if cons == 0:
+    tags = (capi.Tag * 64)()
+    nt, cons, prod = sz(0), sz(0), sz(0)
+    # ---- ofdm_sym_acquisition (+ the FFT that follows it, as the shim can fold it in)
+    acq = g.ofdm_sym_acquisition(1, N, 1705 if N == 2048 else 6817, cp, 30.0)
+    window = 2 * N + cp + 32 + (IPC - 1) * total
+    out_sym = np.zeros((IPC, N), np.complex64)               # reused output buffer
+    X = np.zeros((nsym + IPC, N), np.complex64)
+    pos, done, calls, t = 0, 0, 0, 0.0
+    for it in range(-1, 1 << 30):                             # iteration -1: untimed (first-use costs: pinned staging, module load)
+        if done >= nsym or pos + window > len(bb):
             break
-    X = np.concatenate(syms)
-    record("ofdm_sym_acquisition+fft", t, calls, IPC)
-    # demod_reference_signals: 64 symbols per call (65 visible)
+        t0 = time.perf_counter()
+        capi.check(L.dvbt_b200_acq_work(acq._h, bb.ctypes.data + pos * 8, window, out_sym.ctypes.data, IPC, C.byref(cons), C.byref(prod), tags, 64, C.byref(nt), 1))
+        dt = time.perf_counter() - t0
+        X[done: done + prod.value] = out_sym[: prod.value]
+        pos += cons.value; done += prod.value
+        if it >= 0:
+            t += dt; calls += 1
+        if cons.value == 0:
+            break
+    X = X[:done]
+    record("ofdm_sym_acquisition+fft", t, calls, IPC, max(done - IPC, 1))
+    # ---- demod_reference_signals: IPC symbols per call (one more visible)
     dem = g.demod_reference_signals(8, N, P, w.CON, g.NH, w.CR, w.CR, g.G1_32, w.TM, 0, 0)
-    g.demod_reference_signals(8, N, P, w.CON, g.NH, w.CR, w.CR, g.G1_32, w.TM, 0, 0).general_work(X[: IPC + 1], tags=[(0, "sync_start", 1)])   # untimed warm-up
-    t, calls, ys, first = 0.0, 0, [], True
+    out_y = np.zeros((IPC, P), np.complex64)
+    Y = np.zeros((len(X) + IPC, P), np.complex64)
+    tin = (capi.Tag * 1)(capi.Tag(0, capi.TAG_SYNC_START, 1))
+    tout = (capi.Tag * (IPC + 4))()
+    ny, calls, t, parsed = 0, 0, 0.0, 0
     for i in range(0, len(X) - IPC - 1, IPC):
         t0 = time.perf_counter()
-        y, cons, tags = dem.general_work(X[i: i + IPC + 1], tags=[(0, "sync_start", 1)] if first else [])
-        t += time.perf_counter() - t0
-        first = False; calls += 1
-        ys.append(y)
-    record("demod_reference_signals", t, calls, IPC)
-    Y = np.concatenate(ys) if ys else np.zeros((0, P), np.complex64)
+        capi.check(L.dvbt_b200_demod_work(dem._h, X.ctypes.data + i * N * 8, IPC + 1, out_y.ctypes.data, IPC, C.byref(cons), C.byref(prod), tin, 1 if i == 0 else 0,
+                                          tout, IPC + 4, C.byref(nt)))
+        dt = time.perf_counter() - t0
+        Y[ny: ny + prod.value] = out_y[: prod.value]
+        ny += prod.value
+        if i > 0:
+            t += dt; calls += 1; parsed += IPC
+    Y = Y[:ny]
+    record("demod_reference_signals", t, calls, IPC, parsed)
     if len(Y) < IPC:
-        Y = np.tile((np.random.default_rng(3).normal(size=(64, P)) + 1j * np.random.default_rng(4).normal(size=(64, P))).astype(np.complex64), (nsym // 64, 1))
-    # dvbt_demap: 64 items per call
+        rng = np.random.default_rng(3)
+        Y = (rng.normal(size=(2 * IPC, P)) + 1j * rng.normal(size=(2 * IPC, P))).astype(np.complex64)
+    # ---- dvbt_demap: IPC items per call
     dm = g.dvbt_demap(P, w.CON, g.NH, w.TM, 1.0)
-    reps = max(1, nsym // max(len(Y), 1))
-    dm.general_work(IPC, Y[:IPC])   # untimed warm-up
-    t, calls = 0.0, 0
-    for _ in range(reps):
-        for i in range(0, len(Y) - IPC + 1, IPC):
-            t0 = time.perf_counter()
-            dm.general_work(IPC, Y[i: i + IPC])
-            t += time.perf_counter() - t0
-            calls += 1
-    record("dvbt_demap", t * (nsym / (max(calls, 1) * float(IPC))), calls, IPC)
-    # viterbi_decoder: 64 x 768-blocks per call, input = the bit-deinterleaved bytes of the fused chain's last run
+    out_d = np.zeros(IPC * P, np.uint8)
+    calls, t, items = 0, 0.0, 0
+    for rep in range(-1, max(2, nsym // IPC)):
+        i = (max(rep, 0) * IPC) % max(len(Y) - IPC + 1, 1)
+        t0 = time.perf_counter()
+        capi.check(L.dvbt_b200_demap_work(dm._h, Y.ctypes.data + i * P * 8, IPC, out_d.ctypes.data, IPC, C.byref(cons), C.byref(prod)))
+        dt = time.perf_counter() - t0
+        if rep >= 0:
+            t += dt; calls += 1; items += IPC
+    record("dvbt_demap", t, calls, IPC, items)
+    # ---- viterbi_decoder: IPC x 768-blocks per call, input = the bit-deinterleaved bytes of the fused chain's last run
     w.rx.run_file_dev(w.d_in.data_ptr(), w.nfile, w.GAIN, w.d_ts.data_ptr(), w.ts_cap)
-    vin = w.rx.stage("bitdeint")
+    vin = np.ascontiguousarray(w.rx.stage("bitdeint"))
     vit = g.viterbi_decoder(w.CON, g.NH, w.CR)
     nsymb, nout = 768 * w.n // w.m, 96 * w.k
-    need = nsym * P
-    g.viterbi_decoder(w.CON, g.NH, w.CR).general_work(IPC * nout, vin[: IPC * nsymb], tags=[(0, "superframe_start", 1)])   # untimed warm-up
-    t, calls, pos = 0.0, 0, 0
-    while pos + IPC * nsymb <= min(need, len(vin)):
+    out_v = np.zeros(IPC * nout, np.uint8)
+    tsf = (capi.Tag * 1)(capi.Tag(0, capi.TAG_SUPERFRAME_START, 1))
+    tv = (capi.Tag * 4)()
+    calls, t, pos = 0, 0.0, 0
+    while pos + IPC * nsymb <= min((nsym + IPC) * P, len(vin)):
         t0 = time.perf_counter()
-        vit.general_work(IPC * nout, vin[pos: pos + IPC * nsymb], tags=[(0, "superframe_start", 1)] if pos == 0 else [])
-        t += time.perf_counter() - t0
-        pos += IPC * nsymb; calls += 1
-    record("viterbi_decoder", t * (need / max(pos, 1)), calls, "%d x 768-blocks" % IPC)
-    # reed_solomon_dec: 64 items of 8 packets per call on the deinterleaved Viterbi output
+        capi.check(L.dvbt_b200_viterbi_work(vit._h, vin.ctypes.data + pos, IPC * nsymb, out_v.ctypes.data, IPC * nout, C.byref(cons), C.byref(prod), tsf, 1 if pos == 0 else 0,
+                                            tv, 4, C.byref(nt)))
+        dt = time.perf_counter() - t0
+        if pos > 0:
+            t += dt; calls += 1
+        pos += IPC * nsymb
+    record("viterbi_decoder", t, calls, "%d x 768-blocks" % IPC, max(calls, 1) * IPC * nsymb / float(P))
+    # ---- reed_solomon_dec: IPC items of 8 packets per call on the deinterleaved Viterbi output
     vo = w.rx.stage("viterbi")
-    npk = min(len(vo) // 204, nsym * P * w.m * w.k // (8 * w.n) // 204) // 8 * 8
+    npk = min(len(vo) // 204, (nsym + IPC) * P * w.m * w.k // (8 * w.n) // 204) // 8 * 8
     tt = np.arange(npk * 204)
     src = tt - 204 * (11 - tt % 12)
-    pk = np.where(src >= 0, vo[np.clip(src, 0, None)], 0).astype(np.uint8)
+    pk = np.ascontiguousarray(np.where(src >= 0, vo[np.clip(src, 0, None)], 0).astype(np.uint8))
     rs = g.reed_solomon_dec(2, 8, 0x11D, 255, 239, 8, 51, 8)
-    rs.general_work(IPC, pk[: IPC * 1632])   # untimed warm-up
-    t, calls = 0.0, 0
+    out_r = np.zeros(IPC * 1504, np.uint8)
+    calls, t = 0, 0.0
     for i in range(0, npk // 8 - IPC + 1, IPC):
         t0 = time.perf_counter()
-        rs.general_work(IPC, pk[i * 1632: (i + IPC) * 1632])
-        t += time.perf_counter() - t0
-        calls += 1
-    record("reed_solomon_dec", t * (npk / 8.0 / max(calls * IPC, 1)), calls, IPC)
+        capi.check(L.dvbt_b200_rsdec_work(rs._h, pk.ctypes.data + i * 1632, IPC, out_r.ctypes.data, IPC, C.byref(cons), C.byref(prod)))
+        dt = time.perf_counter() - t0
+        if i > 0:
+            t += dt; calls += 1
+    pk_per_sym = P * w.m * w.k / (8.0 * w.n) / 204.0
+    record("reed_solomon_dec", t, calls, IPC, max(calls, 1) * IPC * 8 / pk_per_sym)
     slow = min(res["blocks"].values(), key=lambda b: b["msamples_per_s"])
     res["pipelined_msamples_per_s"] = slow["msamples_per_s"]
     res["serial_msamples_per_s"] = samples / 1e6 / sum(b["seconds"] for b in res["blocks"].values())
     res["realtime_factor_pipelined"] = slow["msamples_per_s"] / 10.0
-    res["note"] = ("block-level C-ABI calls on pageable host buffers, every call synchronous (H2D, kernels, D2H, stream sync): one thread per block "
-                   "as in GNU Radio => the flowgraph runs at the slowest block's pace (pipelined); serial = one thread calling all five")
+    res["note"] = ("block-level C-ABI calls on reused pageable host buffers, every call synchronous (pinned staging, H2D, kernels, D2H, stream sync): "
+                   "one thread per block as in GNU Radio => the flowgraph runs at the slowest block's pace (pipelined); serial = one thread calling all "
+                   "five.  `seconds` and Msamples/s are per %d OFDM symbols of the capture" % nsym)
     return res
 
 

@@ -164,3 +164,28 @@ def test_acquisition_block_tags_every_reacquisition():
     o2, c2, t2 = acq2.general_work(x[c1:])
     offs = [t[0] for t in t1] + [len(o1) + t[0] for t in t2]
     assert sorted(set(offs)) == want
+
+
+@needs_ref
+def test_two_lock_losses_under_noise_in_pieces():
+    """25 dB AWGN (Viterbi and RS both correcting), two gaps - the second one only a symbol and a half long - and the capture
+    fed in pieces: the reference chain's transport stream, byte for byte"""
+    import gr_dvbt_b200 as g
+    from dvbt_testlib import tx_frequency_domain, ofdm_modulate
+    con, cr, tm = R.QAM16, R.C2_3, R.T2k
+    N, P, K, cp = R.mode_dims(tm)
+    tx = tx_frequency_domain(con, cr, tm, 1300, 23)
+    x = ofdm_modulate(tx["X"], tm, offset=911, cfo_bins=0.17, noise=10 ** (-25 / 20), seed=8)
+    for at, n in ((380, 3.0), (830, 1.5)):
+        z0 = 911 + at * (N + cp) + 333
+        x[z0: z0 + int(n * (N + cp))] = 0
+    ref = reference_stream_rx(x, con, cr, tm, fixed_rs=True)
+    assert len(ref["sf"]) == 3 and len(ref["ts"]) > 300 * 188
+    rx = g.rx_chain(con, g.NH, cr, g.G1_32, tm)
+    whole = rx.run_baseband(x)
+    assert rx.info()["n_superframe_start"] == 3
+    assert len(whole) >= len(ref["ts"]) and np.array_equal(whole[: len(ref["ts"])], ref["ts"])
+    cuts = pieces_of(len(x), [400001, 2112, 77, 650000, 31, 123456])
+    rx2 = g.rx_chain(con, g.NH, cr, g.G1_32, tm)
+    got = [rx2.stream_push("baseband", x[a:b], end=(b == len(x))) for a, b in cuts]
+    assert np.array_equal(np.concatenate(got), whole)
