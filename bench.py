@@ -1021,13 +1021,13 @@ def main():
 
 
 def viterbi_sweep(g, torch, timed, barrier):
-    """config 5 of BASELINE.json: 10^8 received code bits per code rate, error free and with channel bit errors at
-    1e-3 / 1e-2, m = 6 bits per cell (plus m = 2, 4 at rate 1/2); decoded with the block's own I/O format through
+    """config 5 of BASELINE.json: 10^8 received code bits per code rate and constellation (m = 2, 4, 6 bits per cell), error
+    free and with channel bit errors at 1e-3 / 1e-2; decoded with the block's own I/O format through
     dvbt_b200_viterbi_decode_dev.  Parity: the error-free stream decodes to its source; every stream equals the oracle
     on its first 40 blocks and equals itself decoded with another chunking (the chunk boundaries are verified, not assumed)."""
     from oracle import port as O
     res = {"code_bits_per_case": int(1e8), "cases": []}
-    cases = [(r, 6) for r in range(5)] + [(0, 2), (0, 4)]
+    cases = [(r, m) for m in (6, 4, 2) for r in range(5)]          # the full grid of config 5: 5 rates x 3 constellations (x 3 channel BERs below)
     for rate, m in cases:
         k, n = O.RATE_KN[rate]
         nblocks = int(1e8 * k / n / 8 / (96 * k))

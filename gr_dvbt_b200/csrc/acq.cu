@@ -1137,6 +1137,7 @@ struct dvbt_b200_acq {
   int n_fft_ev = 0;
   bool pending_sync = false;                // a sync_start whose item the next acq_work call produces
   dvbt::Staging stg;                        // pinned staging of acq_work's pageable buffers
+  bool state_is_zero = false;               // set by acq_reset(): acq_run need not read the state back
 };
 
 namespace dvbt {
@@ -1153,8 +1154,13 @@ int acq_run(dvbt_b200_acq *h, const float2 *x, long long n, float2 *d_out, long 
   long long produced = 0;
   int sync_tags = 0, lost_total = -1, fb = 0;
   int rc;
-  DVBT_CUDA_TRY(cudaMemcpyAsync(hs, h->d_state.p, sizeof(AcqState), cudaMemcpyDeviceToHost, st));
-  DVBT_CUDA_TRY(dvbt::stream_wait(st));
+  if (h->state_is_zero) {
+    memset(hs, 0, sizeof(AcqState));       // right after acq_reset(): the device state is the memset that is still in the stream - no round trip
+    h->state_is_zero = false;
+  } else {
+    DVBT_CUDA_TRY(cudaMemcpyAsync(hs, h->d_state.p, sizeof(AcqState), cudaMemcpyDeviceToHost, st));
+    DVBT_CUDA_TRY(dvbt::stream_wait(st));
+  }
   // frequency-domain output: derotation + FFT in one kernel for the two DVB-T sizes (cuFFT otherwise)
   const bool fused_fft = do_fft && (p.N == 2048 || p.N == 8192) && !getenv("DVBT_B200_ACQ_CUFFT");
   if (fused_fft && h->tw_n != p.N) {
@@ -1381,6 +1387,8 @@ void acq_use_stream(dvbt_b200_acq *h, cudaStream_t st) {
 
 int acq_reset(dvbt_b200_acq *h) {
   DVBT_CUDA_TRY(cudaMemsetAsync(h->d_state.p, 0, sizeof(AcqState), h->stream));
+  h->state_is_zero = true;
+  h->pending_sync = false;
   return 0;
 }
 

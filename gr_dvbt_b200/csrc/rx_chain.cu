@@ -623,6 +623,13 @@ int rx_back_end(dvbt_b200_rx *h, int nrows, bool end, uint8_t *ts_host, uint8_t 
     ts_out = h->d_ts.as<uint8_t>();
     if (cap > (size_t)max_pairs * 3008 || ts_host == nullptr) cap = (size_t)max_pairs * 3008;
   }
+  const size_t ts_need = (size_t)(h->rs_pend / 16) * 3008 + ((h->rs_pend % 16) >= 8 ? 1504 : 0);
+  if (ts_capacity < ts_need) {
+    // the descrambler's consumption is decided on the device: refuse up front what might not fit rather than drop groups
+    set_error("rx: ts_capacity %zu is below what this call can deliver (%lld pending packets: up to %lld bytes)", ts_capacity, h->rs_pend,
+              (long long)ts_need);
+    return DVBT_B200_ENOSPC;
+  }
   if ((rc = h->d_plan.reserve((size_t)max_pairs * 4))) return rc;
   rx_descr_plan_kernel<<<1, 1024, 0, st>>>(h->d_rs.as<uint8_t>(), h->rs_pend, h->d_dstate.as<DescrState>(), h->d_plan.as<int>(), max_pairs, end ? 1 : 0);
   {
@@ -1027,7 +1034,7 @@ int dvbt_b200_rx_stream_push_host(dvbt_b200_rx *h, int level, const void *data, 
   dvbt::DeviceScope dev_scope__(h ? h->device : -1);
   if (!h || (count && !data) || !ts || level < kLevelFile || level > kLevelFreq) { set_error("rx_stream_push_host: bad argument"); return DVBT_B200_EINVAL; }
   int rc = rx_push(h, level, data, count, gain, true, end_of_stream != 0, ts, nullptr, ts_capacity, ts_bytes);
-  if (end_of_stream) { h->fresh = true; h->level = -1; }
+  if (end_of_stream || rc) { h->fresh = true; h->level = -1; }   // after an error the stream state is undefined: the next push starts a new stream
   return rc;
 }
 
@@ -1037,7 +1044,7 @@ int dvbt_b200_rx_stream_push_dev(dvbt_b200_rx *h, int level, const void *d_data,
   if (!h || (count && !d_data) || !d_ts || level < kLevelFile || level > kLevelFreq) { set_error("rx_stream_push_dev: bad argument"); return DVBT_B200_EINVAL; }
   if (int rc = dvbt::join_default_stream(h->stream)) return rc;
   int rc = rx_push(h, level, d_data, count, gain, false, end_of_stream != 0, nullptr, d_ts, ts_capacity, ts_bytes);
-  if (end_of_stream) { h->fresh = true; h->level = -1; }
+  if (end_of_stream || rc) { h->fresh = true; h->level = -1; }
   return rc;
 }
 

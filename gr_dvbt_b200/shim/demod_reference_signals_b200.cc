@@ -17,7 +17,8 @@ class demod_reference_signals_b200 : public demod_reference_signals {
     dvbt_b200_demod_params p = {itemsize, ninput, noutput, (int)constellation, (int)hierarchy, (int)code_rate_HP, (int)code_rate_LP,
                                 (int)guard_interval, (int)transmission_mode, include_cell_id, cell_id};
     b200::check(dvbt_b200_demod_create(&p, &d_h), "demod_reference_signals");
-    set_min_noutput_items(68);  // a TPS frame per call
+    set_min_noutput_items(8 * 68);               // eight TPS frames per call (bench.py drop_in_blocks: 64 items -> 18 x, 512 -> 74 x real time)
+    set_min_output_buffer(0, 2 * 8 * 68);
   }
   ~demod_reference_signals_b200() { dvbt_b200_demod_destroy(d_h); }
 

@@ -13,7 +13,8 @@ class dvbt_demap_b200 : public dvbt_demap {
       : block("dvbt_demap", io_signature::make(1, 1, sizeof(gr_complex) * nsize), io_signature::make(1, 1, sizeof(unsigned char) * nsize)), d_h(0) {
     dvbt_b200_demap_params p = {nsize, (int)constellation, (int)hierarchy, (int)transmission, gain};
     b200::check(dvbt_b200_demap_create(&p, &d_h), "dvbt_demap");
-    set_min_noutput_items(64);
+    set_min_noutput_items(512);
+    set_min_output_buffer(0, 2 * 512);
   }
   ~dvbt_demap_b200() { dvbt_b200_demap_destroy(d_h); }
 

@@ -17,7 +17,8 @@ class ofdm_sym_acquisition_b200 : public ofdm_sym_acquisition {
     dvbt_b200_acq_params p = {blocks, fft_length, occupied_tones, cp_length, snr};
     b200::check(dvbt_b200_acq_create(&p, &d_h), "ofdm_sym_acquisition");
     set_relative_rate(1.0 / (double)(cp_length + fft_length));  // :388
-    set_min_noutput_items(64);
+    set_min_noutput_items(512);                   // large work items: a call costs ~0.3 ms + 3 us per symbol (bench.py drop_in_blocks)
+    set_min_output_buffer(0, 2 * 512);
   }
   ~ofdm_sym_acquisition_b200() { dvbt_b200_acq_destroy(d_h); }
 

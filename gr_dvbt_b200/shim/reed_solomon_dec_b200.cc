@@ -17,7 +17,8 @@ class reed_solomon_dec_b200 : public reed_solomon_dec {
     b200::check(dvbt_b200_rsdec_create(&par, &d_h), "reed_solomon_dec");
     // bit-for-bit the binary the reference builds with gcc when asked for
     if (getenv("DVBT_B200_RS_AS_BUILT")) dvbt_b200_rsdec_set_compat(d_h, 1);
-    set_min_noutput_items(32);
+    set_min_noutput_items(256);
+    set_min_output_buffer(0, 2 * 256);
   }
   ~reed_solomon_dec_b200() { dvbt_b200_rsdec_destroy(d_h); }
 

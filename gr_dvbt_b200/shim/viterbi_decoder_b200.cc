@@ -19,7 +19,8 @@ class viterbi_decoder_b200 : public viterbi_decoder {
     // the reference passes (k*m)/(8*n) in integer arithmetic, i.e. 0 (viterbi_decoder_impl.cc:138)
     set_relative_rate((double)om / (double)dvbt_b200_viterbi_forecast(d_h, om));
     set_output_multiple(om);                      // :141
-    set_min_noutput_items(64 * om);               // one launch per 64 blocks at least
+    set_min_noutput_items(512 * om);              // one decode per 512 blocks at least (64 blocks are launch-latency bound: 0.54 ms per call)
+    set_min_output_buffer(0, 2 * 512 * om);
   }
   ~viterbi_decoder_b200() { dvbt_b200_viterbi_destroy(d_h); }
 

@@ -313,6 +313,9 @@ int dvbt_b200_rx_run_file_dev(dvbt_b200_rx *h, const void *d_samples, size_t nsa
  * bytes that became available (*ts_bytes) at the start of ts.  end_of_stream != 0: no more input follows (a tail that
  * would need more input is dropped, exactly as at the end of a one-shot run); the next push starts a new stream.
  * The concatenated output of the pieces is the output of the one-shot run on the concatenated input.
+ * ts_capacity must cover what a call can deliver (188/204 of the Viterbi bytes the piece completes, plus up to 48 packets
+ * held back earlier): a buffer that might not fit is refused with DVBT_B200_ENOSPC.  After an error the stream state is
+ * undefined and the next push starts a new stream.
  * Re-synchronisation inside a stream: a missed peak restarts acquisition (ofdm_sym_acquisition_impl.cc:545-558), every
  * attempt sends sync_start (:507), demod re-arms on it and waits for the next superframe start
  * (demod_reference_signals_impl.cc:112-116), whose tag resets the Viterbi decoder and re-aligns the outer

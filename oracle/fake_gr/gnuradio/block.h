@@ -89,6 +89,7 @@ class block {
   void set_tag_propagation_policy(int) {}
   void set_min_noutput_items(int) {}
   void set_min_output_buffer(long) {}
+  void set_min_output_buffer(int, long) {}
 
   void consume_each(int n) { h_consumed = n; }
   uint64_t nitems_read(unsigned) { return h_nread; }
