@@ -78,6 +78,20 @@ class viterbi_decoder:
         otags = [(int(tout[i].offset), capi.TAG_NAMES[tout[i].key], int(tout[i].value)) for i in range(ntout.value)]
         return out[: prod.value].copy(), int(cons.value), otags
 
+    def set_soft(self, on=True):
+        """soft-decision mode (beyond the reference, include/dvbt_b200.h): decode_soft() instead of decode() / general_work()"""
+        check(lib().dvbt_b200_viterbi_set_soft(self._h, 1 if on else 0))
+
+    def decode_soft(self, values):
+        """one stream from a reset; values: one int8 per transmitted code bit, > 0 = "1", clamped to +-6"""
+        v = np.ascontiguousarray(values, np.int8).reshape(-1)
+        nbt = len(v) * self.k // (8 * self.n)
+        out = np.zeros(max(nbt - self.ntraceback, 0), np.uint8)
+        n_out = C.c_size_t(0)
+        check(lib().dvbt_b200_viterbi_decode_soft_host(self._h, v.ctypes.data, len(v), out.ctypes.data, C.byref(n_out)))
+        assert n_out.value == len(out)
+        return out
+
     def decode(self, inp, nstreams=1):
         """Batch decode of nstreams equal-length streams (rows of inp), each from a reset (host arrays)."""
         inp = np.ascontiguousarray(inp, np.uint8).reshape(nstreams, -1)

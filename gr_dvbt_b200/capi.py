@@ -90,6 +90,9 @@ def declare(L):
                                              C.POINTER(Tag), C.c_size_t, C.POINTER(Tag), C.c_size_t, C.POINTER(C.c_size_t)]
         for name in ("dvbt_b200_viterbi_decode_host", "dvbt_b200_viterbi_decode_dev"):
             getattr(L, name).argtypes = [vp, vp, C.c_size_t, C.c_size_t, C.c_int, vp, C.c_size_t, C.POINTER(C.c_size_t)]
+        L.dvbt_b200_viterbi_set_soft.argtypes = [vp, C.c_int]
+        for name in ("dvbt_b200_viterbi_decode_soft_host", "dvbt_b200_viterbi_decode_soft_dev"):
+            getattr(L, name).argtypes = [vp, vp, C.c_size_t, vp, C.POINTER(C.c_size_t)]
         L.dvbt_b200_viterbi_last_stats.argtypes = [vp, C.POINTER(C.c_longlong), C.POINTER(C.c_longlong), C.POINTER(C.c_float)]
         L.dvbt_b200_rsdec_create.argtypes = [C.POINTER(RsdecParams), C.POINTER(vp)]
         L.dvbt_b200_rsdec_destroy.argtypes = [vp]

@@ -9,6 +9,7 @@ struct dvbt_b200_viterbi;
 
 namespace dvbt {
 cudaStream_t vit_stream(dvbt_b200_viterbi *h);
+bool vit_is_soft(const dvbt_b200_viterbi *h);
 int vit_params(const dvbt_b200_viterbi *h, int *k, int *n, int *m, int *ntb, int *nsymbols, int *nout);
 uint32_t *vit_reserve_codes(dvbt_b200_viterbi *h, size_t nbt);
 int vit_decode_prepared(dvbt_b200_viterbi *h, int nbt, uint8_t *d_out);

@@ -125,6 +125,22 @@ int dvbt_b200_viterbi_decode_host(dvbt_b200_viterbi *h, const uint8_t *in, size_
 int dvbt_b200_viterbi_decode_dev(dvbt_b200_viterbi *h, const uint8_t *d_in, size_t in_stride,
                                  size_t n_in, int nstreams, uint8_t *d_out, size_t out_stride,
                                  size_t *n_out);
+/* Soft-decision mode - BEYOND the reference: gr-dvbt decodes hard decisions only (its soft metric table,
+ * lib/d_metrics.c:57-74, is a stub and TODO.txt:25 lists soft decoding as future work), so there is no
+ * reference output to match; the mode is off by default and nothing else changes when it is off.  The decoder
+ * is the same trellis, traceback cadence and tie rules (viterbi_decoder_impl.cc:261-292, d_viterbi.c:461-576,
+ * 680-735) with the branch metric generalised: a code bit arrives as a signed value v in [-6, 6] (clamped),
+ * v > 0 meaning "1", and a branch that expects bit c earns max(v, 0) if c = 1, max(-v, 0) if c = 0.  With
+ * v = +1 / -1 for hard bits 1 / 0 this IS the reference's metric (number of agreeing bits), which is how the
+ * tests pin it: soft decode of +-1 values == hard decode, bit for bit; other values against oracle/port's
+ * scalar restatement of the same rule.
+ *   set_soft(h, 1): switch the handle (resets the stream state); work()/decode_*() then refuse.
+ *   decode_soft_*:  one stream from a reset; `in` holds one int8 per TRANSMITTED code bit in the order of the
+ *                   reference's input stream (X1 Y1 X2 ..., punctured positions absent); n_in*k must be a
+ *                   multiple of 8n.  Writes n_in*k/(8n) - ntraceback decoded bytes. */
+int dvbt_b200_viterbi_set_soft(dvbt_b200_viterbi *h, int on);
+int dvbt_b200_viterbi_decode_soft_host(dvbt_b200_viterbi *h, const int8_t *in, size_t n_in, uint8_t *out, size_t *n_out);
+int dvbt_b200_viterbi_decode_soft_dev(dvbt_b200_viterbi *h, const int8_t *d_in, size_t n_in, uint8_t *d_out, size_t *n_out);
 /* statistics of the last decode: chunks launched, chunks whose warm-up state differed from
  * the sequential state and were re-decoded, and device time of the ACS kernel in ms */
 int dvbt_b200_viterbi_last_stats(const dvbt_b200_viterbi *h, long long *chunks,

@@ -34,6 +34,8 @@ def lib():
         L.dvbt_oracle_viterbi_out_bytes_per_block.argtypes = [C.c_void_p]
         L.dvbt_oracle_viterbi_ntraceback.argtypes = [C.c_void_p]
         L.dvbt_oracle_viterbi_metrics.argtypes = [C.c_void_p, C.c_void_p]
+        L.dvbt_oracle_viterbi_soft.restype = C.c_long
+        L.dvbt_oracle_viterbi_soft.argtypes = [C.c_void_p, C.c_long, C.c_int, C.c_void_p]
         L.dvbt_oracle_conv_encode.restype = C.c_long
         L.dvbt_oracle_conv_encode.argtypes = [C.c_void_p, C.c_long, C.c_int, C.c_int, C.c_void_p]
         L.dvbt_oracle_rs_decode.argtypes = [C.c_void_p, C.c_long, C.c_void_p, C.c_int, C.c_void_p]
@@ -94,6 +96,18 @@ class Viterbi:
         m = np.zeros(64, np.uint8)
         self.L.dvbt_oracle_viterbi_metrics(self.h, m.ctypes.data)
         return m
+
+
+def viterbi_soft(values, rate):
+    """Soft-decision generalisation of the restated decoder (not in the reference; viterbi_port.c): one stream from a
+    reset, one int8 per transmitted code bit (> 0 = "1", clamped to +-6).  +-1 values decode like the hard decoder."""
+    v = np.ascontiguousarray(values, np.int8).reshape(-1)
+    k, n = RATE_KN[rate]
+    assert (len(v) * k) % (8 * n) == 0
+    out = np.zeros(len(v) * k // (8 * n), np.uint8)
+    r = lib().dvbt_oracle_viterbi_soft(v.ctypes.data, len(v), rate, out.ctypes.data)
+    assert r >= 0
+    return out[:r]
 
 
 def conv_encode(data, m, rate):

@@ -38,6 +38,9 @@ int dvbt_oracle_viterbi_ntraceback(const dvbt_oracle_viterbi *);
 /* the 64 path metrics as the reference holds them right now (after the last
  * get_output's min subtraction), for boundary-state tests */
 void dvbt_oracle_viterbi_metrics(const dvbt_oracle_viterbi *, uint8_t metrics[64]);
+/* soft-decision generalisation of the same decoder (not in the reference; see viterbi_port.c): one stream from a reset,
+ * one int8 per transmitted code bit, returns the number of decoded bytes written (n_in*k/(8n) - ntraceback) */
+long dvbt_oracle_viterbi_soft(const int8_t *in, long n_in, int rate, uint8_t *out);
 /* K=7 encoder + DVB-T puncturing + packing of m bits per byte, MSB first:
  * d_viterbi.c:106-124 (d_encode) with the puncture order of
  * viterbi_decoder_impl.cc:61-65.  nbytes*8 must be a multiple of k, and

@@ -214,3 +214,59 @@ long dvbt_oracle_conv_encode(const uint8_t *data, long nbytes, int m, int rate, 
   }
   return nout;
 }
+
+/* ---- soft-decision generalisation (NOT in the reference: lib/d_metrics.c:57-74 is a stub, TODO.txt:25) ----------------
+ * The same decoder - trellis and ACS tie rule of d_viterbi.c:477-524, output cadence of viterbi_decoder_impl.cc:261-292,
+ * argmax / ring traceback / renormalisation of d_viterbi.c:680-735 - with the agreement count of a branch replaced by
+ *     w(c0, v0) + w(c1, v1),   w(1, v) = max(v, 0),  w(0, v) = max(-v, 0),
+ * v the signed soft value of a received code bit (clamped to +-6; 0 for a punctured position).  v = +-1 gives exactly
+ * metsv / metsvm of :487-501, so dvbt_oracle_viterbi_soft on +-1 values equals dvbt_oracle_viterbi_work on the hard bits
+ * (checked in tests/test_soft_decision_cpu.py): that is the pin of this function; beyond it, it is the definition of the
+ * mode ("parity unpinned": the reference has no soft path to compare with). */
+static void acs_step_soft(const dvbt_oracle_viterbi *v, int v0, int v1, const uint8_t *M, const uint8_t *P, uint8_t *Mn, uint8_t *Pn) {
+  for (int i = 0; i < 32; i++) {
+    int c0 = v->branch[0][i], c1 = v->branch[1][i];
+    int w_same = (c0 ? (v0 > 0 ? v0 : 0) : (v0 < 0 ? -v0 : 0)) + (c1 ? (v1 > 0 ? v1 : 0) : (v1 < 0 ? -v1 : 0));
+    int w_inv = (c0 ? (v0 < 0 ? -v0 : 0) : (v0 > 0 ? v0 : 0)) + (c1 ? (v1 < 0 ? -v1 : 0) : (v1 > 0 ? v1 : 0));
+    uint8_t metsv = (uint8_t)w_same, metsvm = (uint8_t)w_inv;
+    uint8_t m0 = (uint8_t)(M[i] + metsv), m1 = (uint8_t)(M[i + 32] + metsvm);
+    uint8_t m2 = (uint8_t)(M[i] + metsvm), m3 = (uint8_t)(M[i + 32] + metsv);
+    int d0 = (int8_t)(uint8_t)(m0 - m1) > 0, d1 = (int8_t)(uint8_t)(m2 - m3) > 0;
+    uint8_t shift0 = (uint8_t)(P[i] << 1), shift1 = (uint8_t)((P[i + 32] << 1) + 1);
+    Mn[2 * i] = d0 ? m0 : m1;
+    Mn[2 * i + 1] = d1 ? m2 : m3;
+    Pn[2 * i] = d0 ? shift0 : shift1;
+    Pn[2 * i + 1] = d1 ? shift0 : shift1;
+  }
+}
+
+/* One stream from a reset: `in` = one int8 per transmitted code bit (order X1 Y1 X2 ..., punctured positions absent);
+ * n_in * k must be a multiple of 8 n.  Writes n_in*k/(8n) - ntraceback bytes; returns that count. */
+long dvbt_oracle_viterbi_soft(const int8_t *in, long n_in, int rate, uint8_t *out) {
+  if (rate < 0 || rate > 4) return -1;
+  dvbt_oracle_viterbi *v = dvbt_oracle_viterbi_create(2, rate, 768);
+  if (!v) return -1;
+  const int k = v->k, n = v->n, period = 2 * k;
+  if (((long long)n_in * k) % (8LL * n) != 0) { dvbt_oracle_viterbi_destroy(v); return -1; }
+  const long nsteps = (long)((long long)n_in * k / n);
+  long idx = 0, nout = 0, nbt = 0;
+  int ph = 0;
+  for (long t = 0; t < nsteps; t += 2) {
+    int sv[4];
+    for (int q = 0; q < 4; q++) {
+      int val = 0;
+      if (v->punct[ph]) { val = in[idx++]; if (val > 6) val = 6; if (val < -6) val = -6; }
+      sv[q] = val;
+      ph = (ph + 1) % period;
+    }
+    acs_step_soft(v, sv[0], sv[1], v->metric0, v->path0, v->metric1, v->path1);
+    acs_step_soft(v, sv[2], sv[3], v->metric1, v->path1, v->metric0, v->path0);
+    if ((t % 8) == 4) { /* after the 6th step of a byte time: in_count % 16 == 8 of viterbi_decoder_impl.cc:270 */
+      unsigned char c = get_output(v);
+      if (nbt >= v->ntb) out[nout++] = c;
+      nbt++;
+    }
+  }
+  dvbt_oracle_viterbi_destroy(v);
+  return nout;
+}
