@@ -422,10 +422,12 @@ class RxWorkload:
                                                                       self.pin_ts.data_ptr(), self.ts_cap, C.byref(n)))
         return int(n.value)
 
-    def noisy_leg(self, snr_db, steps, seed):
+    def noisy_leg(self, snr_db, steps, seed, soft=False):
         """same capture + complex AWGN at `snr_db` (signal power over the non-silent part, noise over the full 10 MHz band):
-        device-resident throughput with the Viterbi traceback and RS correction doing real work"""
+        device-resident throughput with the Viterbi traceback and RS correction doing real work.  soft: the chain's
+        soft-decision mode (beyond the reference: dvbt_b200_rx_set_soft_decision) on the same noisy capture"""
         torch = self.torch
+        self.rx.set_soft_decision(bool(soft))
         x = self.d_in
         p_sig = float((x[1000:].abs() ** 2).mean())
         gen = torch.Generator(device="cuda").manual_seed(seed)
@@ -442,13 +444,15 @@ class RxWorkload:
         torch.cuda.synchronize()
         ms = (time.perf_counter() - t0) * 1e3 / steps
         inf = self.rx.info()
+        if soft:
+            self.rx.set_soft_decision(False)
         ts = self.d_ts[:n].cpu().numpy().reshape(-1, 188)
         # a tiled capture maps 1:1 onto the source TS in its first tile only (from the mode's first packet on); a capture of
         # distinct superframes over its whole length
         src = self.ts_src[: len(self.ts_src) // 188 * 188].reshape(-1, 188)
         m = min(len(ts), len(src) - self.first_packet) if self.distinct else min(len(ts), 3900)
         good = int((ts[:m] == src[self.first_packet:self.first_packet + m]).all(axis=1).sum()) if m > 0 else 0
-        return {"snr_db": snr_db, "ms_per_capture": ms, "value": self.nfile / 1e6 / (ms / 1e3), "ms_viterbi_acs": inf["ms_viterbi_acs"],
+        return {"snr_db": snr_db, "decisions": "soft" if soft else "hard", "ms_per_capture": ms, "value": self.nfile / 1e6 / (ms / 1e3), "ms_viterbi_acs": inf["ms_viterbi_acs"],
                 "viterbi_repaired_chunks": inf["viterbi_repaired"], "acq_sequential_symbols": inf["acq_sequential_symbols"],
                 "acq_lost_at": inf["acq_lost_at"], "resyncs": max(0, inf["n_superframe_start"] - 1), "ts_packets": int(len(ts)),
                 "packets_checked": int(m), "packets_equal_to_source": good}
@@ -947,6 +951,10 @@ def main():
                 rob["awgn_tiled_capture"] = [w.noisy_leg(snr, max(3, a.steps // 4), 4242) for snr in (27.0, 25.0, 20.0)]
             except Exception as e:
                 rob["awgn_tiled_capture"] = {"error": repr(e)[:300]}
+            try:   # the soft-decision mode (beyond the reference) beside the hard chain on the same noisy captures
+                rob["soft_decision"] = [w.noisy_leg(snr, max(3, a.steps // 4), 4242, soft) for snr, soft in ((25.0, True), (22.0, False), (22.0, True), (20.0, True))]
+            except Exception as e:
+                rob["soft_decision"] = {"error": repr(e)[:300]}
         if WORLD == 1 and not os.environ.get("BENCH_NO_SWEEP") and (os.cpu_count() or 1) >= 8:
             nc = w.NCONC
             line["in_flight_sweep"] = w.in_flight_sweep([("%d_again" % nc, nc, {}), ("6", 6, {}), ("8", 8, {})], max(3, a.steps // 4))

@@ -220,7 +220,8 @@ class rx_chain(_Handle):
     does from the FFT output to the TS file."""
     _destroy = "dvbt_b200_rx_destroy"
     STAGES = dict(cells=(0, np.complex64), demap=(1, np.uint8), bitdeint=(2, np.uint8), viterbi=(3, np.uint8), rs=(4, np.uint8),
-                  rs_status=(5, np.int32), symbol_index=(6, np.int32))
+                  rs_status=(5, np.int32), symbol_index=(6, np.int32),
+                  soft_cells=(7, np.uint32), soft_values=(8, np.int8))
 
     def __init__(self, constellation, hierarchy, code_rate, guard_interval, transmission_mode):
         self._h = C.c_void_p()
@@ -231,6 +232,10 @@ class rx_chain(_Handle):
 
     def set_rs_compat(self, as_built):
         check(lib().dvbt_b200_rx_set_rs_compat(self._h, int(as_built)))
+
+    def set_soft_decision(self, on=True, scale=0.0):
+        """soft-decision mode of the chain (beyond the reference; include/dvbt_b200.h: dvbt_b200_rx_set_soft_decision)"""
+        check(lib().dvbt_b200_rx_set_soft_decision(self._h, 1 if on else 0, float(scale)))
 
     def run_freq(self, X):
         """X: (nsym, N) complex64 host array -> TS bytes (numpy)."""

@@ -71,6 +71,18 @@ int make_demap_table(int constellation, int hierarchy, float gain, DemapTable *t
       t->bx |= (unsigned long long)ix << (8 * kx);
       t->by |= (unsigned long long)iy << (8 * ky);
     }
+    // soft-decision view: the levels in ascending order and, per bit, the levels where it is 1
+    for (int k = 0; k < 8; k++) { t->soft_lv[0][k] = t->soft_lv[1][k] = 0.f; t->soft_ones[k] = 0; }
+    t->soft_scale = 4.0f;
+    for (int k = 0; k < L; k++) {
+      const int ix = (int)((t->bx >> (8 * k)) & 0xff), iy = (int)((t->by >> (8 * k)) & 0xff);
+      t->soft_lv[0][k] = t->pts[ix].x;
+      t->soft_lv[1][k] = t->pts[iy].y;
+      for (int e = 0; e < m; e++) {
+        const int idx = (e & 1) ? iy : ix;
+        if ((idx >> (m - 1 - e)) & 1) t->soft_ones[e] |= (unsigned char)(1u << k);
+      }
+    }
     // every point must be the product of its two axis levels (separable constellation)
     for (int i = 0; i < size && t->near_ok; i++) {
       int xm = 0, ym = 0;

@@ -325,11 +325,13 @@ __global__ void __launch_bounds__(128) demod_stage1_kernel(ModeDev md, const flo
 // FRONT = false (default): the integer offset, rotor and scattered-pilot phase come from demod_stage1_kernel (one warp per
 // symbol, good occupancy for its latency-bound sums) and this kernel does the wide part only; FRONT = true: everything in
 // one kernel (DVBT_B200_DEMOD_FUSED=1; measured slower on B200: the other eleven warps of the block wait for warp 0's sums).
-template <bool FRONT, int kSymThreads>
-__global__ void __launch_bounds__(kSymThreads, FRONT ? 1 : 1536 / kSymThreads) demod_symbol_kernel(ModeDev md, const __grid_constant__ DemapTable dt, int do_demap, int use_bulk,
+// SOFT (only with FRONT = false): the demap writes one word of soft decisions per cell to `soft` instead of the hard byte to
+// `dm` (demap_cell_soft); the channel-state weight of a cell is |H|^2 = 1 / |gain|^2 over its mean at the symbol's pilots.
+template <bool FRONT, int kSymThreads, bool SOFT = false>
+__global__ void __launch_bounds__(kSymThreads, FRONT ? 1 : SOFT ? 1 : 1536 / kSymThreads) demod_symbol_kernel(ModeDev md, const __grid_constant__ DemapTable dt, int do_demap, int use_bulk,
                                                                    const float2 *__restrict__ X, int *fo_out, float2 *rot_out, int *mod_out,
                                                                    float2 *__restrict__ tpsval, float2 *__restrict__ Y,
-                                                                   uint8_t *__restrict__ dm) {
+                                                                   uint8_t *__restrict__ dm, uint32_t *__restrict__ soft) {
   extern __shared__ __align__(16) unsigned char s_sym[];
   __shared__ uint64_t s_bar;
   __shared__ int s_fo, s_mod;
@@ -442,6 +444,25 @@ __global__ void __launch_bounds__(kSymThreads, FRONT ? 1 : 1536 / kSymThreads) d
     slope[i] = cdiv(csub(gain[nx], gain[i]), make_float2(11.0f, 0.0f));
   }
   __syncthreads();
+  float soft_f = 0.f;   // soft_scale / (4 g^2 mean |H|^2)
+  if constexpr (SOFT) {
+    __shared__ float s_part[kSymThreads / 32];
+    __shared__ float s_f;
+    float acc = 0.f;
+    for (int i = t; i < npil; i += kSymThreads) acc += 1.0f / (gain[i].x * gain[i].x + gain[i].y * gain[i].y);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) s_part[t >> 5] = acc;
+    __syncthreads();
+    if (t == 0) {
+      float sum = 0.f;
+      for (int i = 0; i < kSymThreads / 32; i++) sum += s_part[i];
+      const float mean = sum / (float)npil;
+      s_f = (mean > 0.f && mean < 3.0e38f) ? dt.soft_scale / (4.0f * dt.g * dt.g * mean) : 0.f;   // a dead symbol: everything erased
+    }
+    __syncthreads();
+    soft_f = s_f;
+  }
   // gain of a data carrier: g[k0] + (k - k0) * slope[k0], k0 the channel-estimation carrier below (same operations in the
   // same order as the reference's loop over the interval, so the same floats)
   auto cell = [&](int e) {
@@ -460,7 +481,15 @@ __global__ void __launch_bounds__(kSymThreads, FRONT ? 1 : 1536 / kSymThreads) d
       yo[0] = make_float4(c0.x, c0.y, c1.x, c1.y);
       yo[1] = make_float4(c2.x, c2.y, c3.x, c3.y);
     }
-    if (do_demap) {
+    if constexpr (SOFT) {
+      auto weight = [&](int e) {
+        const int dk = (e >> 13) & 15, o = e >> 17;
+        const float2 g = cadd(gain[o], cmul(slope[o], make_float2((float)dk, 0.0f)));
+        return soft_f / (g.x * g.x + g.y * g.y);
+      };
+      *reinterpret_cast<uint4 *>(soft + o) = make_uint4(demap_cell_soft_any(dt, c0, weight(e.x)), demap_cell_soft_any(dt, c1, weight(e.y)),
+                                                        demap_cell_soft_any(dt, c2, weight(e.z)), demap_cell_soft_any(dt, c3, weight(e.w)));
+    } else if (do_demap) {
       const uint32_t d = (uint32_t)demap_cell_any(dt, c0) | ((uint32_t)demap_cell_any(dt, c1) << 8) | ((uint32_t)demap_cell_any(dt, c2) << 16) |
                          ((uint32_t)demap_cell_any(dt, c3) << 24);
       *reinterpret_cast<uint32_t *>(dm + o) = d;
@@ -746,10 +775,13 @@ __global__ void __launch_bounds__(32 * kScanWarps) demod_scan_kernel(int ntps, i
 }
 
 int demod_run(const ModeDev &md, const DemapTable *demap, const float2 *X, int nparse, DemodBuffers b, DemodState *d_state,
-              int fi_start, int sync_start_at0, float2 *Y, uint8_t *dm, cudaStream_t st, const int *sync_at, int nsync, int src_base) {
+              int fi_start, int sync_start_at0, float2 *Y, uint8_t *dm, cudaStream_t st, const int *sync_at, int nsync, int src_base,
+              uint32_t *soft) {
   if (nparse <= 0) return 0;
+  if (soft && (!demap || ((uintptr_t)soft & 15))) { set_error("demod: soft decisions need a demap table and a 16-byte aligned buffer"); return DVBT_B200_EINVAL; }
   {
-    static const bool fused_front = getenv("DVBT_B200_DEMOD_FUSED") && atoi(getenv("DVBT_B200_DEMOD_FUSED")) != 0;
+    static const bool fused_env = getenv("DVBT_B200_DEMOD_FUSED") && atoi(getenv("DVBT_B200_DEMOD_FUSED")) != 0;
+    const bool fused_front = fused_env && !soft;
     if (!fused_front) {
       const int threads = 128;
       const long long total = (long long)nparse * 32;
@@ -761,8 +793,9 @@ int demod_run(const ModeDev &md, const DemapTable *demap, const float2 *X, int n
     // threads per block: the payload loop takes P / 4 = 378 (1512) quads of cells per symbol - 192 threads make it two (eight)
     // full passes, and eight blocks (1536 threads, <= 42 registers) fit an SM
     static const int nt_env = getenv("DVBT_B200_DEMOD_THREADS") ? atoi(getenv("DVBT_B200_DEMOD_THREADS")) : 192;
-    const int kSymThreads = fused_front ? 384 : (nt_env == 128 || nt_env == 256 || nt_env == 384) ? nt_env : 192;
-    void (*symk)(ModeDev, const DemapTable, int, int, const float2 *, int *, float2 *, int *, float2 *, float2 *, uint8_t *) =
+    const int kSymThreads = fused_front ? 384 : soft ? 192 : (nt_env == 128 || nt_env == 256 || nt_env == 384) ? nt_env : 192;
+    void (*symk)(ModeDev, const DemapTable, int, int, const float2 *, int *, float2 *, int *, float2 *, float2 *, uint8_t *, uint32_t *) =
+        soft ? demod_symbol_kernel<false, 192, true> :
         fused_front ? demod_symbol_kernel<true, 384>
         : kSymThreads == 128 ? demod_symbol_kernel<false, 128>
         : kSymThreads == 256 ? demod_symbol_kernel<false, 256>
@@ -776,7 +809,7 @@ int demod_run(const ModeDev &md, const DemapTable *demap, const float2 *X, int n
     if ((Y && ((uintptr_t)Y & 15)) || (dm && ((uintptr_t)dm & 3))) { set_error("demod: output buffers must be 16-byte (cells) / 4-byte (demapped) aligned"); return DVBT_B200_EINVAL; }
     if (b.ev_eq0) DVBT_CUDA_TRY(cudaEventRecord(b.ev_eq0, st));
     symk<<<nparse, kSymThreads, smem, st>>>(md, demap ? *demap : dummy, (demap && dm) ? 1 : 0, aligned, X, b.fo, b.rot, b.modidx,
-                                                          b.tpsval, Y, dm);
+                                                          b.tpsval, Y, dm, soft);
     DVBT_CUDA_TRY(cudaGetLastError());
     if (b.ev_eq1) DVBT_CUDA_TRY(cudaEventRecord(b.ev_eq1, st));
   }

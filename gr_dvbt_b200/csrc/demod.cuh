@@ -14,6 +14,11 @@ struct DemapTable {
   float g, inv_step;
   int alpha, near_ok;
   unsigned long long bx, by;
+  // soft-decision view (demap_cell_soft; beyond the reference): the levels of the I / Q axis in ascending order, and for
+  // bit e of a cell (e = 0 the first = most significant bit; even e ride on I, odd e on Q) the set of levels where it is 1
+  float soft_lv[2][8];
+  unsigned char soft_ones[8];
+  float soft_scale;   // soft value of a cell sitting exactly on its constellation point next to a decision boundary (default 4)
 };
 int make_demap_table(int constellation, int hierarchy, float gain, DemapTable *t);
 
@@ -131,6 +136,47 @@ __device__ __forceinline__ uint8_t demap_cell_near(const DemapTable &t, float2 v
   return demap_cell_exact<M>(t, v);
 }
 
+// Soft decisions (beyond the reference, whose demapper is hard only): per bit the max-log metric
+//     (min over the levels where the bit is 0 of (x - level)^2  -  min over the levels where it is 1 of the same) * w,
+// x the I or Q coordinate the bit rides on, rounded to the nearest integer and clamped to +-6; > 0 = "1".  w carries the
+// scale (soft_scale / (4 g^2): a cell on its constellation point next to a boundary gets +-soft_scale) and the cell's
+// channel-state weight |H|^2 / mean |H|^2.  Result: value + 8 of bit e in nibble e (Inf / NaN cells give 0 = erased).
+// The sign of a non-zero value is the hard decision of demap_cell_exact (nearest level along each axis).
+template <int M>
+__device__ __forceinline__ uint32_t demap_cell_soft(const DemapTable &t, float2 v, float w) {
+  constexpr int H = M / 2, L = 1 << H;
+  const float inf = __int_as_float(0x7f800000);
+  uint32_t word = 0;
+#pragma unroll
+  for (int a = 0; a < 2; a++) {
+    const float x = a ? v.y : v.x;
+    float d[L];
+#pragma unroll
+    for (int k = 0; k < L; k++) { const float df = x - t.soft_lv[a][k]; d[k] = df * df; }
+#pragma unroll
+    for (int j = 0; j < H; j++) {
+      const int e = 2 * j + a;
+      const unsigned ones = t.soft_ones[e];
+      float d0 = inf, d1 = inf;
+#pragma unroll
+      for (int k = 0; k < L; k++) {
+        const bool one = (ones >> k) & 1u;
+        d0 = one ? d0 : fminf(d0, d[k]);
+        d1 = one ? fminf(d1, d[k]) : d1;
+      }
+      int q = __float2int_rn((d0 - d1) * w);   // NaN -> 0
+      q = max(-6, min(6, q));
+      word |= (uint32_t)(q + 8) << (4 * e);
+    }
+  }
+  return word;
+}
+__device__ __forceinline__ uint32_t demap_cell_soft_any(const DemapTable &t, float2 v, float w) {
+  if (t.size == 64) return demap_cell_soft<6>(t, v, w);
+  if (t.size == 16) return demap_cell_soft<4>(t, v, w);
+  return demap_cell_soft<2>(t, v, w);
+}
+
 __device__ __forceinline__ uint8_t demap_cell_any(const DemapTable &t, float2 v) {
   if (t.near_ok) {
     if (t.size == 64) return demap_cell_near<6>(t, v);
@@ -203,11 +249,12 @@ struct DemodBuffers {
 // (phase detection) for symbols [0, nparse) of X (nparse+1 symbols must be readable), then the
 // channel estimate + equalisation (+ optional demap) of every parsed symbol, the TPS votes and the
 // sequential scan.  Y (optional) receives P equalised cells per *parsed* symbol (not compacted);
-// dm (optional) the demapped bytes per parsed symbol.
+// dm (optional) the demapped bytes per parsed symbol; soft (optional, instead of dm): one word of soft decisions per cell
+// (demap_cell_soft), P per parsed symbol.
 // sync_at / nsync: batch indices of the symbols that carry a sync_start tag (device array, may be null);
 // sync_start_at0 = 1 is the same as listing symbol 0.  src_base is added to the values written to out_src.
 int demod_run(const ModeDev &md, const DemapTable *demap, const float2 *X, int nparse, DemodBuffers b,
               DemodState *d_state, int fi_start, int sync_start_at0, float2 *Y, uint8_t *dm, cudaStream_t st,
-              const int *sync_at = nullptr, int nsync = 0, int src_base = 0);
+              const int *sync_at = nullptr, int nsync = 0, int src_base = 0, uint32_t *soft = nullptr);
 
 }  // namespace dvbt

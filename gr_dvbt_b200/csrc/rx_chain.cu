@@ -189,6 +189,116 @@ __global__ void __launch_bounds__(256) rx_inner_codes_kernel(InnerMap im, uint32
   for (int i = threadIdx.x; i < nj; i += blockDim.x) codes[jlo + i] = s_codes[i];
 }
 
+// ---- soft decisions (beyond the reference): the same index map on 4-bit values --------------------------------------
+// dm holds one word per cell (demap_cell_soft: value + 8 of bit e in nibble e); the step codes are two words per byte time
+// (8 bits per step: X value + 8 | Y value + 8 << 4, punctured positions = 8, see viterbi.cu).
+__device__ __forceinline__ uint32_t inner_soft(const InnerMap &im, long long tbit) {
+  long long b = tbit / im.m;
+  int kbit = (int)(tbit - b * im.m);
+  int sym = (int)(b / im.P);
+  int i = (int)(b - (long long)sym * im.P);
+  int blk = i / 126, ii = i - blk * 126;
+  int half = im.m >> 1;
+  int e = kbit / half + 2 * (kbit % half);
+  int off = e == 0 ? 0 : e == 1 ? 63 : e == 2 ? 105 : e == 3 ? 42 : e == 4 ? 21 : 84;
+  int w = ii - off;
+  if (w < 0) w += 126;
+  int x = blk * 126 + w;
+  int q = (im.out_symidx[sym] & 1) ? im.Hinv[x] : im.H[x];
+  uint32_t cell = reinterpret_cast<const uint32_t *>(im.dm)[(long long)im.out_src[sym] * im.P + q];
+  return (cell >> (4 * e)) & 15u;
+}
+
+template <int RATE, int PH0>
+__device__ __forceinline__ uint2 inner_soft_code(const uint8_t *v) {
+  constexpr int K = rate_k(RATE);
+  constexpr unsigned PX = rate_px(RATE), PY = rate_py(RATE);
+  uint32_t w[2] = {0u, 0u};
+  int pos = 0, ph = PH0;
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    uint32_t vx = 8u, vy = 8u;
+    if ((PX >> ph) & 1u) vx = v[pos++];
+    if ((PY >> ph) & 1u) vy = v[pos++];
+    w[i >> 2] |= (vx | (vy << 4)) << (8 * (i & 3));
+    ph = (ph + 1 == K) ? 0 : ph + 1;
+  }
+  return make_uint2(w[0], w[1]);
+}
+
+// Same tiling and phases as rx_inner_codes_kernel, without the bit packing: the value bytes are read where they lie.
+template <int RATE, int M>
+__global__ void __launch_bounds__(256) rx_inner_soft_kernel(InnerMap im, uint2 *__restrict__ codes, int nbt) {
+  extern __shared__ __align__(16) uint8_t s_val[];  // [tile cells * M + kInnerTail] values + 8, then the step codes of the tile
+  constexpr int HALF = M / 2;
+  const int G = kInnerTileCells / im.P;
+  const int sym0 = blockIdx.x * G;
+  const int nsym = min(G, im.n_out - sym0);
+  const int ncell = nsym * im.P, nbits = ncell * M;
+  const long long lo = (long long)sym0 * im.P * M, hi = lo + nbits;
+  uint2 *s_codes = reinterpret_cast<uint2 *>(s_val + ((kInnerTileCells * M + kInnerTail + 15) & ~15));
+  const uint32_t *dm32 = reinterpret_cast<const uint32_t *>(im.dm);
+  for (int ls = 0; ls < nsym; ls++) {
+    const int sym = sym0 + ls;
+    const short *perm = (im.out_symidx[sym] & 1) ? im.Hinv : im.H;
+    const uint32_t *row = dm32 + (long long)im.out_src[sym] * im.P;
+    uint8_t *base = s_val + ls * im.P * M;
+    for (int x = threadIdx.x; x < im.P; x += blockDim.x) {
+      uint32_t cell = row[perm[x]];
+      int blk126 = (x / 126) * 126, w = x - blk126;
+      uint8_t *dst = base + blk126 * M;
+#pragma unroll
+      for (int e = 0; e < M; e++) {
+        constexpr int kOff[6] = {0, 63, 105, 42, 21, 84};
+        int ii = w + kOff[e];
+        if (ii >= 126) ii -= 126;
+        const int kbit = (e & 1) * HALF + (e >> 1);
+        dst[ii * M + kbit] = (uint8_t)((cell >> (4 * e)) & 15u);
+      }
+    }
+  }
+  const long long total_bits = (long long)im.n_out * im.P * M;
+  for (int b = threadIdx.x; b < kInnerTail; b += blockDim.x) s_val[nbits + b] = (hi + b < total_bits) ? (uint8_t)inner_soft(im, hi + b) : 8;
+  __syncthreads();
+  constexpr int K = rate_k(RATE), N = K + 1;
+  const long long shift = im.shift_bits;
+  long long jlo = lo > shift ? ((lo - shift) * K / N) / 8 - 2 : 0, jhi = hi > shift ? ((hi - shift) * K / N) / 8 - 2 : 0;
+  if (jlo < 0) jlo = 0;
+  if (jhi < 0) jhi = 0;
+  while (inner_bits_before<RATE>(8 * jlo) + shift < lo) jlo++;
+  while (inner_bits_before<RATE>(8 * jhi) + shift < hi) jhi++;
+  if (jhi > nbt) jhi = nbt;
+  const int nj = jhi > jlo ? (int)(jhi - jlo) : 0;
+  for (int c = 0; c < K; c++) {
+    const long long t0 = 8 * (jlo + c);
+    const int ph = (int)(t0 % K);
+    const int local0 = (int)(inner_bits_before<RATE>(t0) + shift - lo);
+    const int cnt = (nj - c + K - 1) / K;
+#define INNER_CLASS(PH)                                                              \
+    for (int i = threadIdx.x; i < cnt; i += blockDim.x)                              \
+      s_codes[c + K * i] = inner_soft_code<RATE, (PH) % K>(s_val + local0 + 8 * N * i);
+    switch (ph) {
+      case 0: INNER_CLASS(0) break;
+      case 1: INNER_CLASS(1) break;
+      case 2: INNER_CLASS(2) break;
+      case 3: INNER_CLASS(3) break;
+      case 4: INNER_CLASS(4) break;
+      case 5: INNER_CLASS(5) break;
+      default: INNER_CLASS(6) break;
+    }
+#undef INNER_CLASS
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < nj; i += blockDim.x) codes[jlo + i] = s_codes[i];
+}
+
+// test tap: the soft values in the order of the Viterbi block's input stream, one signed byte per code bit
+__global__ void rx_inner_soft_values_kernel(InnerMap im, int8_t *__restrict__ out, long long nbits) {
+  long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= nbits) return;
+  out[b] = (int8_t)((int)inner_soft(im, b) - 8);
+}
+
 // test tap: the bit_inner_deinterleaver output bytes (what the reference feeds its Viterbi block)
 __global__ void rx_inner_bytes_kernel(InnerMap im, uint8_t *__restrict__ out, long long nbytes) {
   long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -344,6 +454,8 @@ struct dvbt_b200_rx {
   dvbt_b200_acq *acq = nullptr;
   cudaStream_t stream = nullptr;
   int fi_start = 3, rs_as_built = 0, sm_count = 148;
+  bool soft = false;                 // soft-decision mode (dvbt_b200_rx_set_soft_decision): d_dm holds one word per cell
+  int esz() const { return soft ? 4 : 1; }
   int k = 1, n = 2, m = 4, ntb = 5, vit_in_block = 0, vit_out_block = 0;
   dvbt::DevBuf d_state, d_fo, d_rot, d_mod, d_tps, d_vote, d_Y, d_rsst, d_ts, d_prbs, h_state, h_info, d_sync, h_sync, d_plan, d_dstate;
   dvbt_b200_rx_info info;
@@ -449,6 +561,27 @@ int launch_inner(dvbt_b200_rx *h, const InnerMap &im, int rows, uint32_t *codes,
   unsigned grid = (unsigned)((rows + G - 1) / G);
   size_t smem = (size_t)((kInnerTileCells * h->m + kInnerTail + 15) & ~15) + (size_t)(kInnerTileCells * h->m + kInnerTail) / 8 + 16;
   cudaStream_t st = h->stream;
+  if (h->soft) {
+    // value bytes + the tile's step codes (at most one byte time per 8 N / K >= 64 / 7 stream bits), 8 bytes each
+    smem = (size_t)((kInnerTileCells * h->m + kInnerTail + 15) & ~15) + ((size_t)(kInnerTileCells * h->m) * 7 / 64 + 8) * 8;
+    uint2 *codes2 = reinterpret_cast<uint2 *>(codes);
+#define RX_SOFT_LAUNCH(R, M) do { \
+      DVBT_CUDA_TRY(cudaFuncSetAttribute(rx_inner_soft_kernel<R, M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+      rx_inner_soft_kernel<R, M><<<grid, 256, smem, st>>>(im, codes2, nbt); } while (0)
+#define RX_SOFT_RATE(R) do { if (h->m == 2) RX_SOFT_LAUNCH(R, 2); else if (h->m == 4) RX_SOFT_LAUNCH(R, 4); else RX_SOFT_LAUNCH(R, 6); } while (0)
+    switch (h->par.code_rate) {
+      case 0: RX_SOFT_RATE(0); break;
+      case 1: RX_SOFT_RATE(1); break;
+      case 2: RX_SOFT_RATE(2); break;
+      case 3: RX_SOFT_RATE(3); break;
+      default: RX_SOFT_RATE(4); break;
+    }
+#undef RX_SOFT_RATE
+#undef RX_SOFT_LAUNCH
+    dvbt::count_launch();
+    DVBT_CUDA_TRY(cudaGetLastError());
+    return 0;
+  }
 #define RX_INNER_LAUNCH(R, M) rx_inner_codes_kernel<R, M><<<grid, 256, smem, st>>>(im, codes, nbt)
 #define RX_INNER_RATE(R) (h->m == 2 ? RX_INNER_LAUNCH(R, 2) : h->m == 4 ? RX_INNER_LAUNCH(R, 4) : RX_INNER_LAUNCH(R, 6))
   switch (h->par.code_rate) {
@@ -540,8 +673,8 @@ int rx_back_end(dvbt_b200_rx *h, int nrows, bool end, uint8_t *ts_host, uint8_t 
     const int keep = end ? 0 : nrows - drop;
     if (keep > 0) {
       const int o = h->cur ^ 1;
-      if ((rc = h->d_dm[o].reserve((size_t)keep * P)) || (rc = h->d_osym[o].reserve((size_t)keep * 4)) || (rc = h->d_osrc[o].reserve((size_t)keep * 4))) return rc;
-      rx_carry_kernel<<<keep, 256, 0, st>>>(md.P, drop, keep, dm, osrc, osym, h->d_dm[o].as<uint8_t>(), h->d_osrc[o].as<int>(), h->d_osym[o].as<int>());
+      if ((rc = h->d_dm[o].reserve((size_t)keep * P * h->esz())) || (rc = h->d_osym[o].reserve((size_t)keep * 4)) || (rc = h->d_osrc[o].reserve((size_t)keep * 4))) return rc;
+      rx_carry_kernel<<<keep, 256, 0, st>>>(md.P * h->esz(), drop, keep, dm, osrc, osym, h->d_dm[o].as<uint8_t>(), h->d_osrc[o].as<int>(), h->d_osym[o].as<int>());
       dvbt::count_launch();
       DVBT_CUDA_TRY(cudaGetLastError());
       h->cur = o;
@@ -686,7 +819,7 @@ int rx_from_symbols(dvbt_b200_rx *h, const float2 *X, size_t nsym, bool x_is_int
     if ((rc = h->d_fo.reserve(nparse * 4)) || (rc = h->d_rot.reserve(nparse * 8)) || (rc = h->d_mod.reserve(nparse * 4)) ||
         (rc = h->d_tps.reserve(nparse * md.ntps * 8)) || (rc = h->d_vote.reserve(nparse * 4)))
       return rc;
-    if ((rc = reserve_keep(h->d_dm[h->cur], (size_t)(c + nparse) * md.P, (size_t)c * md.P, st)) ||
+    if ((rc = reserve_keep(h->d_dm[h->cur], (size_t)(c + nparse) * md.P * h->esz(), (size_t)c * md.P * h->esz(), st)) ||
         (rc = reserve_keep(h->d_osym[h->cur], (size_t)(c + nparse) * 4, (size_t)c * 4, st)) ||
         (rc = reserve_keep(h->d_osrc[h->cur], (size_t)(c + nparse) * 4, (size_t)c * 4, st)))
       return rc;
@@ -714,8 +847,9 @@ int rx_from_symbols(dvbt_b200_rx *h, const float2 *X, size_t nsym, bool x_is_int
     dvbt::DemodBuffers b{h->d_fo.as<int>(), h->d_rot.as<float2>(), h->d_mod.as<int>(), h->d_tps.as<float2>(), h->d_vote.as<int>(),
                          h->d_osym[h->cur].as<int>() + c, h->d_osrc[h->cur].as<int>() + c, h->ev[8], h->ev[9]};
     rc = dvbt::demod_run(md, &h->demap, X, (int)nparse, b, h->d_state.as<dvbt::DemodState>(), h->fi_start, 0,
-                         keep_cells ? h->d_Y.as<float2>() : nullptr, h->d_dm[h->cur].as<uint8_t>() + (size_t)c * md.P, st,
-                         sync_rows.empty() ? nullptr : h->d_sync.as<int>(), (int)sync_rows.size(), c);
+                         keep_cells ? h->d_Y.as<float2>() : nullptr, h->soft ? nullptr : h->d_dm[h->cur].as<uint8_t>() + (size_t)c * md.P, st,
+                         sync_rows.empty() ? nullptr : h->d_sync.as<int>(), (int)sync_rows.size(), c,
+                         h->soft ? h->d_dm[h->cur].as<uint32_t>() + (size_t)c * md.P : nullptr);
     if (rc) return rc;
     DVBT_CUDA_TRY(cudaEventRecord(h->ev[1], st));
     DVBT_CUDA_TRY(cudaMemcpyAsync(h->h_state.p, h->d_state.p, sizeof(dvbt::DemodState), cudaMemcpyDeviceToHost, st));
@@ -988,6 +1122,21 @@ int dvbt_b200_rx_set_rs_compat(dvbt_b200_rx *h, int as_built) {
   return 0;
 }
 
+// Soft-decision mode of the fused chain (beyond the reference; include/dvbt_b200.h): the demapper hands 4-bit values to the
+// inner deinterleavers and the Viterbi decoder instead of hard bits.  Switching resets the stream state.
+int dvbt_b200_rx_set_soft_decision(dvbt_b200_rx *h, int on, float scale) {
+  dvbt::DeviceScope dev_scope__(h ? h->device : -1);
+  if (!h) { set_error("rx_set_soft_decision: null handle"); return DVBT_B200_EINVAL; }
+  if (on && !(scale >= 0.f && scale <= 64.f)) { set_error("rx_set_soft_decision: scale must be in [0, 64] (0 = default 4)"); return DVBT_B200_EINVAL; }
+  if (int rc = dvbt_b200_viterbi_set_soft(h->vit, on ? 1 : 0)) return rc;
+  DVBT_CUDA_TRY(dvbt::stream_wait(h->stream));
+  h->soft = on != 0;
+  h->demap.soft_scale = (on && scale > 0.f) ? scale : 4.0f;
+  rx_stream_reset(h);
+  h->fresh = true;
+  return 0;
+}
+
 // ---- one-shot entry points: a whole capture = reset, one piece, end of stream ----
 #define RX_ONE_SHOT(NAME, LEVEL, GAIN, HOST)                                                                              \
   dvbt::DeviceScope dev_scope__(h ? h->device : -1);                                                                      \
@@ -1069,10 +1218,30 @@ int dvbt_b200_rx_read_stage(dvbt_b200_rx *h, int stage, void *host_out, size_t c
     case DVBT_RX_STAGE_CELLS:  // equalised cells of the output symbols (contiguous when no resync happened)
       if (nout > 0 && h->d_Y.p) { src = h->d_Y.as<float2>() + first * md.P; n = (size_t)nout * md.P * 8; }
       break;
+    case DVBT_RX_STAGE_SOFT_CELLS:   // soft mode: one word per cell of the output symbols (value + 8 of bit e in nibble e)
+      if (!h->soft) { set_error("rx_read_stage: the handle is not in soft-decision mode"); return DVBT_B200_EINVAL; }
+      if (nout > 0) { src = h->d_dm[h->tap_set].as<uint32_t>() + (h->tap_carry + first) * md.P; n = (size_t)nout * md.P * 4; }
+      break;
+    case DVBT_RX_STAGE_SOFT_VALUES: {   // soft mode: one int8 per code bit in the order of the Viterbi block's input stream
+      if (!h->soft) { set_error("rx_read_stage: the handle is not in soft-decision mode"); return DVBT_B200_EINVAL; }
+      if (nout <= 0) break;
+      n = (size_t)nout * md.P * h->m;
+      int rc = tmp.reserve(n);
+      if (rc) return rc;
+      InnerMap im{h->d_dm[h->tap_set].as<uint8_t>(), h->d_osrc[h->tap_set].as<int>() + h->tap_carry, h->d_osym[h->tap_set].as<int>() + h->tap_carry,
+                  md.H, md.Hinv, md.P, h->m, (int)nout, 0};
+      rx_inner_soft_values_kernel<<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>(im, tmp.as<int8_t>(), (long long)n);
+      dvbt::count_launch();
+      DVBT_CUDA_TRY(cudaGetLastError());
+      src = tmp.p;
+      break;
+    }
     case DVBT_RX_STAGE_DEMAP:
+      if (h->soft) { set_error("rx_read_stage: soft-decision mode keeps no hard demapper output (read DVBT_RX_STAGE_SOFT_CELLS)"); return DVBT_B200_EINVAL; }
       if (nout > 0) { src = h->d_dm[h->tap_set].as<uint8_t>() + (h->tap_carry + first) * md.P; n = (size_t)nout * md.P; }
       break;
     case DVBT_RX_STAGE_BITDEINT: {
+      if (h->soft) { set_error("rx_read_stage: soft-decision mode keeps no hard bits (read DVBT_RX_STAGE_SOFT_VALUES)"); return DVBT_B200_EINVAL; }
       if (nout <= 0) break;
       n = (size_t)nout * md.P;
       int rc = tmp.reserve(n);

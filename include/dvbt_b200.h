@@ -299,11 +299,22 @@ typedef struct dvbt_b200_rx_info { /* counts since the stream was reset (= of th
   long long ts_total;            /* TS bytes written since the stream was reset (ts_bytes: by the last call) */
 } dvbt_b200_rx_info;
 enum { DVBT_RX_STAGE_CELLS = 0, DVBT_RX_STAGE_DEMAP = 1, DVBT_RX_STAGE_BITDEINT = 2, DVBT_RX_STAGE_VITERBI = 3,
-       DVBT_RX_STAGE_RS = 4, DVBT_RX_STAGE_RS_STATUS = 5, DVBT_RX_STAGE_SYMBOL_INDEX = 6 };
+       DVBT_RX_STAGE_RS = 4, DVBT_RX_STAGE_RS_STATUS = 5, DVBT_RX_STAGE_SYMBOL_INDEX = 6,
+       DVBT_RX_STAGE_SOFT_CELLS = 7,  /* soft mode: uint32 per cell of the output symbols, value + 8 of bit e (0 = first) in nibble e */
+       DVBT_RX_STAGE_SOFT_VALUES = 8  /* soft mode: int8 per code bit, in the order of the Viterbi block's input stream */ };
 
 int dvbt_b200_rx_create(const dvbt_b200_rx_params *p, dvbt_b200_rx **out);
 void dvbt_b200_rx_destroy(dvbt_b200_rx *h);
 int dvbt_b200_rx_set_rs_compat(dvbt_b200_rx *h, int as_built); /* see dvbt_b200_rsdec_set_compat */
+/* Soft-decision mode of the chain - BEYOND the reference (hard decisions only; lib/d_metrics.c:57-74 is a stub,
+ * TODO.txt:25), off by default; with it off nothing changes.  on = 1: the demapper emits, per bit of a cell, the max-log
+ * metric (nearest level with the bit 0 vs. nearest with the bit 1, along the axis the bit rides on) scaled so that a cell
+ * on its constellation point next to a decision boundary gets +-scale (0 = default 4), weighted by the cell's channel
+ * state |H|^2 / mean |H|^2 (from the pilot-based channel estimate the equaliser already holds), rounded and clamped to
+ * +-6; the inner deinterleavers move these values instead of bits and the Viterbi decoder runs in soft mode
+ * (dvbt_b200_viterbi_set_soft).  Everything after the Viterbi decoder is unchanged.  The sign of a non-zero value is the
+ * hard decision, so a noise-free capture gives the same TS in both modes.  Switching resets the stream state. */
+int dvbt_b200_rx_set_soft_decision(dvbt_b200_rx *h, int on, float scale);
 /* nsym post-FFT symbols (N gr_complex each, DC at bin N/2).  _host: X and ts are host buffers;
  * _dev: device pointers.  *ts_bytes receives the TS bytes written (multiple of 1504). */
 int dvbt_b200_rx_run_freq_host(dvbt_b200_rx *h, const void *X, size_t nsym, uint8_t *ts, size_t ts_capacity, size_t *ts_bytes);

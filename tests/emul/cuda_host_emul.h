@@ -31,6 +31,8 @@ static emul_dim3 blockDim, gridDim;
 
 struct uint4 { uint32_t x, y, z, w; };   // not over-aligned: the host compiler then never assumes 16-byte alignment
 static inline uint4 make_uint4(uint32_t x, uint32_t y, uint32_t z, uint32_t w) { uint4 r; r.x = x; r.y = y; r.z = z; r.w = w; return r; }
+struct uint2 { uint32_t x, y; };
+static inline uint2 make_uint2(uint32_t x, uint32_t y) { return uint2{x, y}; }
 struct float4 { float x, y, z, w; };
 struct int4 { int x, y, z, w; };
 static inline float4 make_float4(float x, float y, float z, float w) { return float4{x, y, z, w}; }

@@ -9,14 +9,12 @@
 struct float2 { float x, y; };
 struct double2 { double x, y; };
 struct int2 { int x, y; };
-struct uint2 { unsigned x, y; };
 struct dim3 { unsigned x = 1, y = 1, z = 1; dim3(unsigned a = 1, unsigned b = 1, unsigned c = 1) : x(a), y(b), z(c) {} };
 struct uchar4 { unsigned char x, y, z, w; };
 struct char4 { signed char x, y, z, w; };
 static inline float2 make_float2(float x, float y) { return float2{x, y}; }
 static inline double2 make_double2(double x, double y) { return double2{x, y}; }
 static inline int2 make_int2(int x, int y) { return int2{x, y}; }
-static inline uint2 make_uint2(unsigned x, unsigned y) { return uint2{x, y}; }
 
 // single / double operations with one rounding each (the TU is built with -ffp-contract=off)
 static inline float __fadd_rn(float a, float b) { return a + b; }
