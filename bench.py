@@ -82,7 +82,10 @@ def seed_of_rank(rank, base=1):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+    """nvidia-smi clocks / throttle reasons sampled during the timed region.  The process is started BEFORE the leg's warm-up
+    and left to reach its steady state (its start-up enumerates every GPU of the box through the driver: with 8 ranks doing
+    that inside a 140 ms timed region the launches of all ranks stalled - 2.00 instead of 1.81 ms per capture at N = 8,
+    profiles/r02_n8_in_flight_and_wait_mode.txt); mark() brackets the timed region and only its samples are reported."""
 
     Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
@@ -95,21 +98,28 @@ class ClockSampler:
         if os.environ.get("BENCH_SAMPLER", "1") == "0":   # diagnostic switch: no nvidia-smi process during the timed region
             return
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
+            t_end = time.perf_counter() + 5.0
+            while not self.rows and time.perf_counter() < t_end:      # first sample = the process is past its start-up
+                time.sleep(0.02)
         except Exception:
             self.proc = None
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append(line.strip())
+            self.rows.append((time.perf_counter(), line.strip()))
+
+    def mark(self):
+        """call at the start and at the end of the timed region"""
+        self.marks = getattr(self, "marks", []) + [time.perf_counter()]
 
     def stop(self):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+        time.sleep(0.06)
         self.proc.terminate()
         try:
             self.proc.wait(timeout=2)
@@ -117,7 +127,13 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, reasons = [], None, set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        marks = getattr(self, "marks", [])
+        rows = self.rows
+        if len(marks) >= 2:
+            inside = [r for r in rows if marks[0] <= r[0] <= marks[-1] + 0.06]
+            # a region shorter than the sampling interval: the samples closest to it
+            rows = inside if inside else sorted(rows, key=lambda r: abs(r[0] - 0.5 * (marks[0] + marks[-1])))[:2]
+        for _t, r in rows:
             f = [x.strip() for x in r.split(",")]
             if len(f) < 7:
                 continue
@@ -377,15 +393,19 @@ class RxWorkload:
             t.join()
         return (time.perf_counter() - t0) * 1e3
 
-    def in_flight_sweep(self, legs, steps):
+    def in_flight_sweep(self, legs, steps, reduce=None):
         """informational: the resident leg with other numbers of captures in flight (same kernels, more handles) and with
-        launch-geometry knobs of the library that are read at every launch; legs = [(label, captures in flight, env)]"""
+        launch-geometry knobs of the library that are read at every launch; legs = [(label, captures in flight, env)].
+        env key "_blocking_wait": dvbt_b200_set_blocking_wait for the leg.  reduce: max over ranks (every rank runs the legs)"""
         res = {}
         keep = self.NCONC
+        lib = self.g.capi.lib()
         try:
             for label, ns, env in legs:
                 for k in ("DVBT_B200_VIT_SM_DIV",):
                     os.environ.pop(k, None)
+                env = dict(env)
+                lib.dvbt_b200_set_blocking_wait(int(env.pop("_blocking_wait", 0)))
                 os.environ.update(env)
                 g = self.g
                 while len(self.rx2) < ns:
@@ -396,13 +416,18 @@ class RxWorkload:
                 self.torch.cuda.synchronize()
                 self.NCONC = ns
                 self.resident_pair(2)
+                if reduce:
+                    reduce(0.0)                      # ranks start the leg together
                 ms = self.resident_pair(steps)
+                if reduce:
+                    ms = reduce(ms)
                 same = all(b == self.ts_bytes for b in self.pair_bytes) and all(self.torch.equal(self.d_ts2[0][: self.ts_bytes], t[: self.ts_bytes]) for t in self.d_ts2[1:ns])
                 res[label] = {"captures_in_flight": ns, "env": env, "ms_per_capture": ms / steps / ns, "value": self.nfile / 1e6 * ns / (ms / steps / 1e3), "outputs_identical": bool(same)}
         except Exception as e:   # informational leg: never fatal
             res["error"] = repr(e)[:200]
         finally:
             self.NCONC = keep
+            lib.dvbt_b200_set_blocking_wait(1 if os.environ.get("DVBT_B200_BLOCKING_WAIT", "0") not in ("", "0") else 0)
             os.environ.pop("DVBT_B200_VIT_SM_DIV", None)
         return res
 
@@ -833,13 +858,16 @@ def main():
         r["stage"] = {k: float(np.mean([s[k] for s in w.stage_ms[warm:]])) for k in w.stage_ms[-1]}
         r["info"] = dict(w.info)
         r["ms_single"] = ms1 / steps
+        if sampler:
+            sampler.start()                      # before the warm-up: see ClockSampler
         w.resident_pair(warm)
         barrier()
         l1 = lib.dvbt_b200_kernel_launches()
         if sampler:
-            sampler.start()
+            sampler.mark()
         r["ms_pair"] = max_over_ranks(w.resident_pair(steps), "cuda") / steps
         if sampler:
+            sampler.mark()
             r["clocks"] = sampler.stop()
         r["launches"] = (lib.dvbt_b200_kernel_launches() - l1) // steps
         # the same stage clocks with the captures in flight: CUDA-event spans on each handle's stream, which now include
@@ -887,6 +915,14 @@ def main():
         if RANK == 0:
             sys.stderr.write("[bench quick] one capture %.3f ms, %d concurrent %.3f ms per capture, acs %.3f ms, e2e %.3f ms, parity %s %s\n"
                              % (head["ms_single"], w.NCONC, head["ms_pair"] / w.NCONC, head["kms"], head["ms_e2e"], head["ok"], head["check"]))
+        if os.environ.get("BENCH_QUICK_SWEEP"):   # host-side tuning of the resident leg at any N: captures in flight x wait mode
+            legs = []
+            for spec in os.environ["BENCH_QUICK_SWEEP"].split(","):      # e.g. "4s,3s,2s,6s,4b,6b,8b": count + s(pin) / b(lock)
+                legs.append((spec, int(spec[:-1]), {"_blocking_wait": 1 if spec.endswith("b") else 0}))
+            sw = w.in_flight_sweep(legs, a.steps, reduce=lambda ms: max_over_ranks(ms, "cuda"))
+            if RANK == 0:
+                for k, v in sw.items():
+                    sys.stderr.write("[bench quick sweep N=%d] %s: %s\n" % (WORLD, k, json.dumps(v) if isinstance(v, dict) else v))
         if WORLD > 1:
             dist.destroy_process_group()
         return 0

@@ -110,6 +110,7 @@ def declare(L):
                                            C.POINTER(Tag), C.c_size_t, C.POINTER(Tag), C.c_size_t, C.POINTER(C.c_size_t)]
         L.dvbt_b200_rx_create.argtypes = [C.POINTER(RxParams), C.POINTER(vp)]
         L.dvbt_b200_rx_destroy.argtypes = [vp]
+        L.dvbt_b200_set_blocking_wait.argtypes = [C.c_int]
         L.dvbt_b200_rx_set_rs_compat.argtypes = [vp, C.c_int]
         L.dvbt_b200_rx_set_soft_decision.argtypes = [vp, C.c_int, C.c_float]
         L.dvbt_b200_rx_run_freq_host.argtypes = [vp, vp, C.c_size_t, vp, C.c_size_t, C.POINTER(C.c_size_t)]

@@ -32,8 +32,15 @@ int ensure_device() {
   return 0;
 }
 
+static std::atomic<int> g_blocking_wait{-1};   // -1: not decided yet (DVBT_B200_BLOCKING_WAIT), 0 spin, 1 block
+void set_blocking_wait(int on) { g_blocking_wait.store(on ? 1 : 0); }
+
 cudaError_t stream_wait(cudaStream_t st) {
-  static const bool blocking = getenv("DVBT_B200_BLOCKING_WAIT") && atoi(getenv("DVBT_B200_BLOCKING_WAIT")) != 0;
+  int blocking = g_blocking_wait.load(std::memory_order_relaxed);
+  if (blocking < 0) {
+    blocking = (getenv("DVBT_B200_BLOCKING_WAIT") && atoi(getenv("DVBT_B200_BLOCKING_WAIT")) != 0) ? 1 : 0;
+    g_blocking_wait.store(blocking);
+  }
   if (!blocking) return cudaStreamSynchronize(st);
   thread_local cudaEvent_t ev[64] = {nullptr};
   int dev = 0;
@@ -161,5 +168,6 @@ int dvbt_b200_set_device(int device) {
 }
 
 unsigned long long dvbt_b200_kernel_launches(void) { return dvbt::g_launches.load(); }
+int dvbt_b200_set_blocking_wait(int on) { dvbt::set_blocking_wait(on); return 0; }
 
 }  // extern "C"

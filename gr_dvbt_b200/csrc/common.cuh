@@ -63,6 +63,7 @@ inline int join_default_stream(cudaStream_t st) {
 // between cudaStreamQuery calls was tried too: four polling threads contend with each other's kernel launches inside the
 // driver, 12.7 ms per batch of four captures instead of 7.1.)
 cudaError_t stream_wait(cudaStream_t st);
+void set_blocking_wait(int on);
 
 // A growable device (or pinned-host) buffer; never shrinks.
 struct DevBuf {

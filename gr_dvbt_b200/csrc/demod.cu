@@ -232,9 +232,12 @@ __device__ __forceinline__ float2 cdiv(float2 n, float2 d) {
 // ---------------------------------------------------------------------------------------
 // stage 1: one warp per symbol
 // ---------------------------------------------------------------------------------------
+// tpsval (optional): the symbol's TPS carriers, equalised exactly as demod_symbol_kernel does it (gain of the pilot below,
+// slope of its interval, :617-642, :929-945) - 17 / 68 carriers per symbol, so that the TPS vote and the sequential scan can
+// start before the payload is equalised.
 __global__ void __launch_bounds__(128) demod_stage1_kernel(ModeDev md, const float2 *__restrict__ X, int nparse,
                                                            int *__restrict__ fo_out, float2 *__restrict__ rot_out,
-                                                           int *__restrict__ mod_out) {
+                                                           int *__restrict__ mod_out, float2 *__restrict__ tpsval) {
   int s = (int)((blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5);
   int lane = threadIdx.x & 31;
   if (s >= nparse) return;
@@ -302,6 +305,25 @@ __global__ void __launch_bounds__(128) demod_stage1_kernel(ModeDev md, const flo
     fo_out[s] = fo;
     rot_out[s] = rot;
     mod_out[s] = mod;
+  }
+  if (tpsval) {
+    const int r = mod < 0 ? 0 : mod;
+    const float2 *x = x0 + md.zl + fo;                             // x[k] = carrier k, integer offset applied
+    const short *pil = md.pilots + r * md.pil_stride;
+    const int npil = md.npil[r];
+    auto pilot_gain = [&](int i) {                                 // :484-489 set_channel_gain
+      const int k = pil[i];
+      return cdiv(make_float2(md.pval[k], 0.f), cmul(rot, x[k]));
+    };
+    for (int t = lane; t < md.ntps; t += 32) {
+      const int e = md.tps3[r * md.ntps + t];
+      const int k = e & 0x1fff, dk = (e >> 13) & 15, o = e >> 17;
+      const int nx = o + 1 < npil ? o + 1 : o;
+      const float2 g0 = pilot_gain(o);
+      const float2 slope = cdiv(csub(pilot_gain(nx), g0), make_float2(11.0f, 0.0f));
+      const float2 g = cadd(g0, cmul(slope, make_float2((float)dk, 0.0f)));
+      tpsval[(long long)s * md.ntps + t] = cmul(cmul(rot, x[k]), g);
+    }
   }
 }
 
@@ -470,7 +492,7 @@ __global__ void __launch_bounds__(kSymThreads, FRONT ? 1 : SOFT ? 1 : 1536 / kSy
     const float2 g = cadd(gain[o], cmul(slope[o], make_float2((float)dk, 0.0f)));
     return cmul(cmul(rot, x[k]), g);
   };
-  if (t < md.ntps) tpsval[(long long)s * md.ntps + t] = cell(md.tps3[r * md.ntps + t]);   // :929-945
+  if (tpsval && t < md.ntps) tpsval[(long long)s * md.ntps + t] = cell(md.tps3[r * md.ntps + t]);   // :929-945 (null: stage 1 did it)
   const int4 *pay = reinterpret_cast<const int4 *>(md.pay3 + r * md.P);
   for (int q = t; q < md.P / 4; q += kSymThreads) {                // :1104-1113
     const int4 e = pay[q];
@@ -782,12 +804,33 @@ int demod_run(const ModeDev &md, const DemapTable *demap, const float2 *X, int n
   {
     static const bool fused_env = getenv("DVBT_B200_DEMOD_FUSED") && atoi(getenv("DVBT_B200_DEMOD_FUSED")) != 0;
     const bool fused_front = fused_env && !soft;
+    static const bool side_env = !(getenv("DVBT_B200_DEMOD_SIDE_SCAN") && atoi(getenv("DVBT_B200_DEMOD_SIDE_SCAN")) == 0);   // =0: scan behind the equalise kernel (A/B)
+    const bool tps_early = !fused_front && side_env && b.side && b.ev_fork && b.ev_join;
     if (!fused_front) {
       const int threads = 128;
       const long long total = (long long)nparse * 32;
-      demod_stage1_kernel<<<(unsigned)((total + threads - 1) / threads), threads, 0, st>>>(md, X, nparse, b.fo, b.rot, b.modidx);
+      demod_stage1_kernel<<<(unsigned)((total + threads - 1) / threads), threads, 0, st>>>(md, X, nparse, b.fo, b.rot, b.modidx,
+                                                                                            tps_early ? b.tpsval : nullptr);
       DVBT_CUDA_TRY(cudaGetLastError());
       count_launch();
+    }
+    if (tps_early) {
+      // fork: the TPS vote and the scan on the side stream, beside the equalise + demap kernel below.  The scan is ONE block
+      // that must be resident before the wide kernel takes every register of every SM (streams do not preempt): the main
+      // stream therefore waits for the (short) vote, so that scan and equalise become ready together, and the side stream
+      // has the higher priority - its block is placed first, the wide kernel fills the rest of the GPU.
+      DVBT_CUDA_TRY(cudaEventRecord(b.ev_fork, st));
+      DVBT_CUDA_TRY(cudaStreamWaitEvent(b.side, b.ev_fork, 0));
+      demod_vote_kernel<<<(nparse + 127) / 128, 128, 0, b.side>>>(md.ntps, nparse, b.tpsval, d_state, b.vote, sync_start_at0, sync_at, sync_at ? nsync : 0);
+      DVBT_CUDA_TRY(cudaGetLastError());
+      if (b.ev_mid) {
+        DVBT_CUDA_TRY(cudaEventRecord(b.ev_mid, b.side));
+        DVBT_CUDA_TRY(cudaStreamWaitEvent(st, b.ev_mid, 0));
+      }
+      demod_scan_kernel<<<1, 32 * kScanWarps, 0, b.side>>>(md.ntps, nparse, fi_start, src_base, b.modidx, b.vote, b.tpsval, d_state, b.out_symidx, b.out_src);
+      DVBT_CUDA_TRY(cudaGetLastError());
+      DVBT_CUDA_TRY(cudaEventRecord(b.ev_join, b.side));
+      count_launch(2);
     }
     const size_t smem = demod_symbol_smem(md, fused_front);
     // threads per block: the payload loop takes P / 4 = 378 (1512) quads of cells per symbol - 192 threads make it two (eight)
@@ -809,9 +852,14 @@ int demod_run(const ModeDev &md, const DemapTable *demap, const float2 *X, int n
     if ((Y && ((uintptr_t)Y & 15)) || (dm && ((uintptr_t)dm & 3))) { set_error("demod: output buffers must be 16-byte (cells) / 4-byte (demapped) aligned"); return DVBT_B200_EINVAL; }
     if (b.ev_eq0) DVBT_CUDA_TRY(cudaEventRecord(b.ev_eq0, st));
     symk<<<nparse, kSymThreads, smem, st>>>(md, demap ? *demap : dummy, (demap && dm) ? 1 : 0, aligned, X, b.fo, b.rot, b.modidx,
-                                                          b.tpsval, Y, dm, soft);
+                                                          tps_early ? nullptr : b.tpsval, Y, dm, soft);
     DVBT_CUDA_TRY(cudaGetLastError());
     if (b.ev_eq1) DVBT_CUDA_TRY(cudaEventRecord(b.ev_eq1, st));
+    if (tps_early) {
+      DVBT_CUDA_TRY(cudaStreamWaitEvent(st, b.ev_join, 0));       // join: the scan's results are ordered before everything behind
+      count_launch(1);
+      return 0;
+    }
   }
   demod_vote_kernel<<<(nparse + 127) / 128, 128, 0, st>>>(md.ntps, nparse, b.tpsval, d_state, b.vote, sync_start_at0, sync_at, sync_at ? nsync : 0);
   DVBT_CUDA_TRY(cudaGetLastError());

@@ -243,6 +243,10 @@ struct DemodBuffers {
   int *out_symidx;  // [n_out] symbol_index tag value of each output symbol
   int *out_src;     // [n_out] batch index of each output symbol
   cudaEvent_t ev_eq0 = nullptr, ev_eq1 = nullptr;   // optional: recorded around demod_equalise_kernel (bench timing)
+  // optional: a second stream + two events.  The TPS vote and the sequential scan (one block, ~0.1 ms per 20 000 symbols)
+  // then run beside the wide equalise + demap kernel instead of behind it (the TPS carriers are equalised by stage 1)
+  cudaStream_t side = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_mid = nullptr;   // ev_mid: recorded behind the vote (see demod_run)
 };
 
 // Runs process_cpilot_data / compute_oneshot_csft / frequency_correction / process_spilot_data

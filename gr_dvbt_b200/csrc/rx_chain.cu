@@ -460,6 +460,8 @@ struct dvbt_b200_rx {
   dvbt::DevBuf d_state, d_fo, d_rot, d_mod, d_tps, d_vote, d_Y, d_rsst, d_ts, d_prbs, h_state, h_info, d_sync, h_sync, d_plan, d_dstate;
   dvbt_b200_rx_info info;
   cudaEvent_t ev[10];
+  cudaStream_t side = nullptr;       // the demod scan runs here, beside the equalise kernel (demod.cuh: DemodBuffers::side)
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_mid = nullptr;
 
   // ---- stream state: what the blocks of the flowgraph carry from one scheduler call to the next --------------------
   // The one-shot entry points are "reset, one piece, end of stream"; dvbt_b200_rx_stream_* feed a capture in pieces.
@@ -845,7 +847,7 @@ int rx_from_symbols(dvbt_b200_rx *h, const float2 *X, size_t nsym, bool x_is_int
       DVBT_CUDA_TRY(cudaMemcpyAsync(h->d_sync.p, h->h_sync.p, sync_rows.size() * 4, cudaMemcpyHostToDevice, st));
     }
     dvbt::DemodBuffers b{h->d_fo.as<int>(), h->d_rot.as<float2>(), h->d_mod.as<int>(), h->d_tps.as<float2>(), h->d_vote.as<int>(),
-                         h->d_osym[h->cur].as<int>() + c, h->d_osrc[h->cur].as<int>() + c, h->ev[8], h->ev[9]};
+                         h->d_osym[h->cur].as<int>() + c, h->d_osrc[h->cur].as<int>() + c, h->ev[8], h->ev[9], h->side, h->ev_fork, h->ev_join, h->ev_mid};
     rc = dvbt::demod_run(md, &h->demap, X, (int)nparse, b, h->d_state.as<dvbt::DemodState>(), h->fi_start, 0,
                          keep_cells ? h->d_Y.as<float2>() : nullptr, h->soft ? nullptr : h->d_dm[h->cur].as<uint8_t>() + (size_t)c * md.P, st,
                          sync_rows.empty() ? nullptr : h->d_sync.as<int>(), (int)sync_rows.size(), c,
@@ -1083,6 +1085,15 @@ int dvbt_b200_rx_create(const dvbt_b200_rx_params *p, dvbt_b200_rx **out) {
     return rc;
   }
   for (auto &e : h->ev) cudaEventCreate(&e);
+  int prio_least = 0, prio_greatest = 0;
+  cudaDeviceGetStreamPriorityRange(&prio_least, &prio_greatest);
+  if (cudaStreamCreateWithPriority(&h->side, cudaStreamNonBlocking, prio_greatest) != cudaSuccess ||
+      cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming) != cudaSuccess || cudaEventCreateWithFlags(&h->ev_mid, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming) != cudaSuccess) {
+    set_error("rx_create: side stream: %s", cudaGetErrorString(cudaGetLastError()));
+    dvbt_b200_rx_destroy(h);
+    return DVBT_B200_ECUDA;
+  }
   // energy_descramble PRBS (energy_descramble_impl.cc:46-67): 1 + x^14 + x^15, init 0xa9, 8 clocks per
   // byte, clocked but unused on every sync byte except the first of the group
   {
@@ -1104,6 +1115,10 @@ void dvbt_b200_rx_destroy(dvbt_b200_rx *h) {
   dvbt::DeviceScope dev_scope__(h ? h->device : -1);
   if (!h) return;
   if (h->stream) cudaStreamSynchronize(h->stream);
+  if (h->side) { cudaStreamSynchronize(h->side); cudaStreamDestroy(h->side); }
+  if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+  if (h->ev_join) cudaEventDestroy(h->ev_join);
+  if (h->ev_mid) cudaEventDestroy(h->ev_mid);
   dvbt::DevBuf *bufs[] = {&h->d_state, &h->d_fo, &h->d_rot, &h->d_mod, &h->d_tps, &h->d_vote, &h->d_Y, &h->d_rsst, &h->d_ts, &h->d_prbs, &h->h_state,
                           &h->h_info, &h->d_sync, &h->h_sync, &h->d_plan, &h->d_dstate, &h->d_file, &h->d_file2, &h->d_samples, &h->d_samples2, &h->d_sym,
                           &h->d_sym2, &h->d_dm[0], &h->d_dm[1], &h->d_osym[0], &h->d_osym[1], &h->d_osrc[0], &h->d_osrc[1], &h->d_D, &h->d_D2,

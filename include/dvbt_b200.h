@@ -60,6 +60,10 @@ int dvbt_b200_device_count(void);
 int dvbt_b200_set_device(int device);
 /* how many kernels of this library have been launched by this process (bench evidence) */
 unsigned long long dvbt_b200_kernel_launches(void);
+/* How the library waits for its CUDA streams inside a call: 0 (default) = cudaStreamSynchronize, the driver spins - lowest
+ * latency, right while every calling thread has a host core to itself; 1 = a blocking event, the thread sleeps - for
+ * processes that drive more handles than they have cores.  Process-wide; DVBT_B200_BLOCKING_WAIT=1 sets the initial value. */
+int dvbt_b200_set_blocking_wait(int on);
 
 /* ------------------------------------------------------------------------------------
  * viterbi_decoder  — replaces gr::dvbt::viterbi_decoder

@@ -366,9 +366,10 @@ extern "C" int emul_demod(const float *Xf, int nsym, int constellation, int tm, 
     emul_launch(demod_symbol_kernel<true, 384>, (unsigned)nparse, 384u, md, dt, 1, (int)((((uintptr_t)X) & 15) == 0), X, fo.data(), rot.data(), mod.data(),
                 tps.data(), (float2 *)Y_out, dm_out, (uint32_t *)nullptr);
   } else {
-    emul_launch(demod_stage1_kernel, (unsigned)(((long long)nparse * 32 + 127) / 128), 128u, md, X, nparse, fo.data(), rot.data(), mod.data());
+    // as demod_run() launches them with a side stream: stage 1 equalises the TPS carriers, the symbol kernel the payload only
+    emul_launch(demod_stage1_kernel, (unsigned)(((long long)nparse * 32 + 127) / 128), 128u, md, X, nparse, fo.data(), rot.data(), mod.data(), tps.data());
     emul_launch(demod_symbol_kernel<false, 192>, (unsigned)nparse, 192u, md, dt, 1, (int)((((uintptr_t)X) & 15) == 0), X, fo.data(), rot.data(), mod.data(),
-                tps.data(), (float2 *)Y_out, dm_out, (uint32_t *)nullptr);
+                (float2 *)nullptr, (float2 *)Y_out, dm_out, (uint32_t *)nullptr);
   }
   emul_launch(demod_vote_kernel, (unsigned)((nparse + 127) / 128), 128u, md.ntps, nparse, (const float2 *)tps.data(), &st, vote.data(),
               sync_start_at0, (const int *)nullptr, 0);

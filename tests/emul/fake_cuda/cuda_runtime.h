@@ -72,6 +72,8 @@ static inline cudaError_t cudaMemset(void *d, int v, size_t n) { if (n) memset(d
 static inline cudaError_t cudaMemsetAsync(void *d, int v, size_t n, cudaStream_t = nullptr) { if (n) memset(d, v, n); return cudaSuccess; }
 #define cudaMemcpyToSymbol(sym, src, n) (memcpy((void *)&(sym), (src), (n)), cudaSuccess)
 static inline cudaError_t cudaStreamCreateWithFlags(cudaStream_t *s, unsigned) { *s = (cudaStream_t)1; return cudaSuccess; }
+static inline cudaError_t cudaStreamCreateWithPriority(cudaStream_t *s, unsigned, int) { *s = (cudaStream_t)1; return cudaSuccess; }
+static inline cudaError_t cudaDeviceGetStreamPriorityRange(int *least, int *greatest) { *least = 0; *greatest = -5; return cudaSuccess; }
 static inline cudaError_t cudaStreamCreate(cudaStream_t *s) { *s = (cudaStream_t)1; return cudaSuccess; }
 static inline cudaError_t cudaStreamDestroy(cudaStream_t) { return cudaSuccess; }
 static inline cudaError_t cudaStreamSynchronize(cudaStream_t) { return cudaSuccess; }
