@@ -480,7 +480,8 @@ class RxWorkload:
         return {"snr_db": snr_db, "decisions": "soft" if soft else "hard", "ms_per_capture": ms, "value": self.nfile / 1e6 / (ms / 1e3), "ms_viterbi_acs": inf["ms_viterbi_acs"],
                 "viterbi_repaired_chunks": inf["viterbi_repaired"], "acq_sequential_symbols": inf["acq_sequential_symbols"],
                 "acq_lost_at": inf["acq_lost_at"], "resyncs": max(0, inf["n_superframe_start"] - 1), "ts_packets": int(len(ts)),
-                "packets_checked": int(m), "packets_equal_to_source": good}
+                "packets_checked": int(m), "packets_equal_to_source": good,
+                "stage_ms": {k[3:]: round(float(v), 4) for k, v in inf.items() if k.startswith("ms_")}}
 
     def check(self):
         """the WHOLE transport stream of the last resident run against the transmitted one: the capture is one block of 4

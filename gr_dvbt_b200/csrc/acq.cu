@@ -54,11 +54,24 @@ __device__ __forceinline__ float2 cmulf(float2 a, float2 b) {
 __device__ __forceinline__ float2 cmul_conjf(float2 a, float2 b) { return cmulf(a, make_float2(b.x, -b.y)); }
 __device__ __forceinline__ float cnormf(float2 a) { return __fadd_rn(__fmul_rn(a.x, a.x), __fmul_rn(a.y, a.y)); }
 
-// lambda/gamma for the candidate symbol end at absolute sample index p (ofdm_sym_acquisition_impl.cc:162-250)
+// lambda/gamma for the candidate symbol end at absolute sample index p (ofdm_sym_acquisition_impl.cc:162-250).
+// lo: lowest readable index of x (0, or -history).  The reference's window reaches up to 8 samples in front of its input
+// pointer when the peak sits at the very start of the search range (earlier items of the scheduler's circular
+// buffer; zeros on a fresh buffer), the candidate table here up to kD: what lies in front of `lo` reads as zero - the
+// start of a stream - and callers that continue a stream keep kAcqHistory consumed samples in front of x.
 __device__ __forceinline__ void ml_point(const float2 *__restrict__ x, long long p, int N, int cp, float rho2, float *lambda,
-                                         float2 *gamma) {
+                                         float2 *gamma, long long lo = 0) {
   float2 g = make_float2(0.f, 0.f);
   float phi = 0.f;
+  if (p - (cp - 1) - N < lo) {   // rare: only candidates within kD samples of the start of the buffer
+    for (int j = 0; j < cp; j++) {
+      const long long ia = p - j, ib = p - j - N;
+      float2 a = ia >= lo ? x[ia] : make_float2(0.f, 0.f), b = ib >= lo ? x[ib] : make_float2(0.f, 0.f);
+      float2 c = cmul_conjf(a, b);
+      g = make_float2(__fadd_rn(g.x, c.x), __fadd_rn(g.y, c.y));
+      phi = __fadd_rn(phi, __fadd_rn(cnormf(a), cnormf(b)));
+    }
+  } else
   for (int j = 0; j < cp; j++) {
     float2 a = x[p - j], b = x[p - j - N];
     float2 c = cmul_conjf(a, b);                       // d_corr[i-j-N] = in[i-j] * conj(in[i-j-N])
@@ -258,7 +271,7 @@ __global__ void __launch_bounds__(256) acq_init_peak_kernel(AcqParams p, const f
 // kernels decide what is output, whatever this kernel says.
 constexpr int kProbe = 4;
 __global__ void __launch_bounds__(kProbe * kCand) acq_probe_kernel(AcqParams p, const float2 *__restrict__ x, long long base, long long nsamples,
-                                                                   AcqState *st) {
+                                                                   AcqState *st, long long lo) {
   __shared__ float s_l[kProbe * kCand];
   const int t = threadIdx.x, n = t / kCand, c = t % kCand;
   if (!st->initial) { if (t == 0) st->probe_lost1 = 0; return; }
@@ -266,7 +279,7 @@ __global__ void __launch_bounds__(kProbe * kCand) acq_probe_kernel(AcqParams p, 
   long long q = base + (long long)n * total + c0 - kD + c;
   float lam = -INFINITY;
   float2 g;
-  if (q < nsamples && q - p.cp - p.N + 1 >= 0) ml_point(x, q, p.N, p.cp, p.rho2, &lam, &g);
+  if (q < nsamples) ml_point(x, q, p.N, p.cp, p.rho2, &lam, &g, lo);
   s_l[t] = lam;
   __syncthreads();
   if (t != 0) return;
@@ -285,11 +298,11 @@ __global__ void __launch_bounds__(kProbe * kCand) acq_probe_kernel(AcqParams p, 
 
 // ---- tracking table: symbol n, candidate c <-> symbol end at base + n*(N+cp) + c0 - kD + c
 __global__ void acq_lambda_kernel(AcqParams p, const float2 *__restrict__ x, long long base, int c0, int nsym,
-                                  float *__restrict__ lambda, float2 *__restrict__ gamma) {
+                                  float *__restrict__ lambda, float2 *__restrict__ gamma, long long lo) {
   long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= (long long)nsym * kCand) return;
   int n = (int)(t / kCand), c = (int)(t % kCand);
-  ml_point(x, base + (long long)n * (p.N + p.cp) + c0 - kD + c, p.N, p.cp, p.rho2, &lambda[t], &gamma[t]);
+  ml_point(x, base + (long long)n * (p.N + p.cp) + c0 - kD + c, p.N, p.cp, p.rho2, &lambda[t], &gamma[t], lo);
 }
 
 // ---- tracking as a finite-state machine, evaluated in parallel -----------------------------------
@@ -1130,6 +1143,8 @@ struct dvbt_b200_acq {
   bool own_stream = true;
   cufftHandle plan = 0;
   int plan_batch = 0;
+  dvbt::DevBuf d_hist;                      // acq_work: the last kAcqHistory samples consumed by the previous calls
+  bool hist_valid = false;
   dvbt::DevBuf d_x, d_state, h_state, d_lambda, d_gamma, d_avg1, d_avg2, d_peak, d_sym, d_out, d_il, d_ig, d_eps, d_flag, d_maps, d_cof, d_bof, d_peakof, d_eof, d_seg, d_runs, d_tw;
   int tw_n = 0;
   static constexpr int kFftEv = 8;          // CUDA events around the derotation+FFT kernel of the first batches of a run
@@ -1144,8 +1159,10 @@ namespace dvbt {
 
 // Runs acquisition + derotation (+ optional FFT) over device samples x[0..n).  Output symbols go to
 // d_out (N complex each).  Returns counts through the host copy of the state.
+// nhist: consumed samples of the stream that are still readable in front of x (x[-nhist .. -1]); what lies further back reads
+// as zero (ml_point).
 int acq_run(dvbt_b200_acq *h, const float2 *x, long long n, float2 *d_out, long long out_capacity_syms, int do_fft,
-            AcqState *host_state_out, std::vector<long long> *sync_at = nullptr) {
+            AcqState *host_state_out, std::vector<long long> *sync_at = nullptr, int nhist = 0) {
   const AcqParams &p = h->kp;
   const int total = p.N + p.cp;
   cudaStream_t st = h->stream;
@@ -1185,7 +1202,7 @@ int acq_run(dvbt_b200_acq *h, const float2 *x, long long n, float2 *d_out, long 
       acq_init_lambda_kernel<<<(p.N + 127) / 128, 128, 0, st>>>(p, x, pos, h->d_il.as<float>(), h->d_ig.as<float2>());
       DVBT_CUDA_TRY(cudaFuncSetAttribute(acq_init_peak_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, p.N * 8));
       acq_init_peak_kernel<<<1, 256, (size_t)p.N * 8, st>>>(p, h->d_il.as<float>(), h->d_ig.as<float2>(), h->d_state.as<AcqState>());
-      acq_probe_kernel<<<1, kProbe * kCand, 0, st>>>(p, x, pos, n, h->d_state.as<AcqState>());
+      acq_probe_kernel<<<1, kProbe * kCand, 0, st>>>(p, x, pos, n, h->d_state.as<AcqState>(), -(long long)nhist);
       count_launch(3);
       DVBT_CUDA_TRY(cudaGetLastError());
       DVBT_CUDA_TRY(cudaMemcpyAsync(hs, h->d_state.p, sizeof(AcqState), cudaMemcpyDeviceToHost, st));
@@ -1218,7 +1235,7 @@ int acq_run(dvbt_b200_acq *h, const float2 *x, long long n, float2 *d_out, long 
     {
       long long threads = nsym * kCand;
       acq_lambda_kernel<<<(unsigned)((threads + 127) / 128), 128, 0, st>>>(p, x, pos, c0, (int)nsym, h->d_lambda.as<float>(),
-                                                                          h->d_gamma.as<float2>());
+                                                                          h->d_gamma.as<float2>(), -(long long)nhist);
       int per_thread = kChunk;
       while ((nsym + per_thread - 1) / per_thread > 1024) per_thread *= 2;
       int nthreads = (int)((nsym + per_thread - 1) / per_thread);
@@ -1389,13 +1406,14 @@ int acq_reset(dvbt_b200_acq *h) {
   DVBT_CUDA_TRY(cudaMemsetAsync(h->d_state.p, 0, sizeof(AcqState), h->stream));
   h->state_is_zero = true;
   h->pending_sync = false;
+  h->hist_valid = false;
   return 0;
 }
 
 int acq_run_simple(dvbt_b200_acq *h, const float2 *x, long long n, float2 *d_out, long long out_capacity_syms, int do_fft,
-                   AcqResult *res, std::vector<long long> *sync_at) {
+                   AcqResult *res, std::vector<long long> *sync_at, int nhist) {
   AcqState hs;
-  int rc = acq_run(h, x, n, d_out, out_capacity_syms, do_fft, &hs, sync_at);
+  int rc = acq_run(h, x, n, d_out, out_capacity_syms, do_fft, &hs, sync_at, nhist);
   if (rc) return rc;
   if (res) { res->n_run = hs.n_run; res->n_single = hs.n_single; res->n_seq = hs.n_seq; res->consumed = hs.consumed; res->n_out = hs.n_out; res->lost_at = hs.lost_at; res->fallback = hs.fallback; res->cp_start = hs.cp_start; }
   return 0;
@@ -1437,7 +1455,7 @@ void dvbt_b200_acq_destroy(dvbt_b200_acq *h) {
   if (!h) return;
   if (h->stream) cudaStreamSynchronize(h->stream);
   if (h->plan) cufftDestroy(h->plan);
-  dvbt::DevBuf *bufs[] = {&h->d_x, &h->d_state, &h->h_state, &h->d_lambda, &h->d_gamma, &h->d_avg1, &h->d_avg2, &h->d_peak, &h->d_sym, &h->d_out, &h->d_il, &h->d_ig, &h->d_eps, &h->d_flag, &h->d_maps, &h->d_cof, &h->d_bof, &h->d_peakof, &h->d_eof, &h->d_seg, &h->d_runs, &h->d_tw};
+  dvbt::DevBuf *bufs[] = {&h->d_hist, &h->d_x, &h->d_state, &h->h_state, &h->d_lambda, &h->d_gamma, &h->d_avg1, &h->d_avg2, &h->d_peak, &h->d_sym, &h->d_out, &h->d_il, &h->d_ig, &h->d_eps, &h->d_flag, &h->d_maps, &h->d_cof, &h->d_bof, &h->d_peakof, &h->d_eof, &h->d_seg, &h->d_runs, &h->d_tw};
   for (auto *b : bufs) b->release();
   h->stg.release();
   for (auto &e : h->ev_fft) if (e) cudaEventDestroy(e);
@@ -1454,12 +1472,19 @@ int dvbt_b200_acq_work(dvbt_b200_acq *h, const void *in, size_t n_in_items, void
   if (!in || !out || out_capacity_items == 0) return 0;
   int rc;
   const int N = h->kp.N;
-  if ((rc = h->d_x.reserve(n_in_items * 8)) || (rc = h->d_out.reserve(out_capacity_items * N * 8))) return rc;
-  if ((rc = h->stg.h2d(h->d_x.p, in, n_in_items * 8, h->stream))) return rc;
+  // [kAcqHistory samples consumed by the previous calls (zeros after a reset) | this call's input]: the reference's window
+  // reaches a few samples in front of its input pointer, into the scheduler's circular buffer (ml_point)
+  constexpr int H = dvbt::kAcqHistory;
+  if ((rc = h->d_x.reserve((H + n_in_items) * 8)) || (rc = h->d_hist.reserve((size_t)H * 8)) || (rc = h->d_out.reserve(out_capacity_items * N * 8))) return rc;
+  if (!h->hist_valid) { DVBT_CUDA_TRY(cudaMemsetAsync(h->d_hist.p, 0, (size_t)H * 8, h->stream)); h->hist_valid = true; }
+  DVBT_CUDA_TRY(cudaMemcpyAsync(h->d_x.p, h->d_hist.p, (size_t)H * 8, cudaMemcpyDeviceToDevice, h->stream));
+  if ((rc = h->stg.h2d(h->d_x.as<float2>() + H, in, n_in_items * 8, h->stream))) return rc;
   AcqState hs;
   std::vector<long long> sync_at;
-  rc = dvbt::acq_run(h, h->d_x.as<float2>(), (long long)n_in_items, h->d_out.as<float2>(), (long long)out_capacity_items, apply_fft, &hs, &sync_at);
+  rc = dvbt::acq_run(h, h->d_x.as<float2>() + H, (long long)n_in_items, h->d_out.as<float2>(), (long long)out_capacity_items, apply_fft, &hs, &sync_at, H);
   if (rc) return rc;
+  // the H samples in front of the new read position (d_x still holds the old history in front of the input)
+  DVBT_CUDA_TRY(cudaMemcpyAsync(h->d_hist.p, h->d_x.as<float2>() + hs.consumed, (size_t)H * 8, cudaMemcpyDeviceToDevice, h->stream));
   if (hs.n_out > 0 && (rc = h->stg.d2h(out, h->d_out.p, (size_t)hs.n_out * N * 8, h->stream))) return rc;
   DVBT_CUDA_TRY(dvbt::stream_wait(h->stream));
   *consumed = (size_t)hs.consumed;

@@ -42,8 +42,10 @@ int acq_reset(dvbt_b200_acq *h);
 // sync_at (optional) receives, in increasing order, the output-symbol offsets (relative to this call) at which an
 // acquisition attempt sent sync_start (ofdm_sym_acquisition_impl.cc:507); an offset equal to n_out refers to the
 // symbol the NEXT call will produce first
+// nhist: consumed samples of the stream still readable in front of x (the acquisition window reaches up to 16 samples back)
+constexpr int kAcqHistory = 64;
 int acq_run_simple(dvbt_b200_acq *h, const float2 *x, long long n, float2 *d_out, long long out_capacity_syms, int do_fft,
-                   AcqResult *res, std::vector<long long> *sync_at = nullptr);
+                   AcqResult *res, std::vector<long long> *sync_at = nullptr, int nhist = 0);
 }  // namespace dvbt
 
 namespace dvbt {

@@ -472,7 +472,7 @@ struct dvbt_b200_rx {
   long long res_pend = 0;            // capture samples behind the history
   int res_hist = 0;                  // valid history samples in front of them
   // ofdm_sym_acquisition: baseband samples not yet consumed (the block's input buffer)
-  dvbt::DevBuf d_samples, d_samples2;
+  dvbt::DevBuf d_samples, d_samples2;   // [kAcqHistory consumed samples (zeros at the start of a stream) | pending samples]
   long long bb_pend = 0;
   long long acq_total = 0;           // symbols acquisition has produced since the reset
   std::vector<long long> sync_abs;   // sync_start tags (absolute symbol numbers) whose symbol demod has not parsed yet
@@ -505,6 +505,7 @@ struct dvbt_b200_rx {
 namespace {
 
 constexpr int kResHist = 64;          // >= 35 input samples of FIR history, kept 16-byte friendly
+constexpr int kBbHist = dvbt::kAcqHistory;   // consumed baseband samples kept in front of the pending ones (acq.cu: ml_point)
 constexpr int kOuterHist = 204 * 11;  // deepest delay line of the outer deinterleaver, in stream bytes
 enum { kLevelFile = 0, kLevelBaseband = 1, kLevelFreq = 2 };
 
@@ -908,7 +909,7 @@ int rx_from_baseband(dvbt_b200_rx *h, const float2 *x, size_t n, bool x_is_inter
   DVBT_CUDA_TRY(cudaEventRecord(h->ev[7], st));
   dvbt::AcqResult ar;
   std::vector<long long> sync_at;
-  rc = dvbt::acq_run_simple(h->acq, x, (long long)n, h->d_sym.as<float2>() + (size_t)carry * md.N, cap_syms, 1, &ar, &sync_at);
+  rc = dvbt::acq_run_simple(h->acq, x, (long long)n, h->d_sym.as<float2>() + (size_t)carry * md.N, cap_syms, 1, &ar, &sync_at, x_is_internal ? kBbHist : 0);
   if (rc) return rc;
   cudaEvent_t ev_acq_end = h->ev[0];   // recorded next by rx_from_symbols: end of the acquisition stage
   for (long long o : sync_at) {
@@ -927,10 +928,14 @@ int rx_from_baseband(dvbt_b200_rx *h, const float2 *x, size_t n, bool x_is_inter
     const long long left = (long long)n - ar.consumed;
     if (left < 0) { set_error("rx: acquisition consumed more than it was given"); return DVBT_B200_ECUDA; }
     if (x_is_internal) {
-      if ((rc = shift_front(h->d_samples, h->d_samples2, (size_t)ar.consumed * 8, (size_t)left * 8, 0, 0, st))) return rc;
+      // x = d_samples + kBbHist: the kBbHist samples in front of the new read position travel along
+      if ((rc = shift_front(h->d_samples, h->d_samples2, (size_t)ar.consumed * 8, (size_t)(kBbHist + left) * 8, 0, 0, st))) return rc;
     } else {
-      if ((rc = h->d_samples.reserve((size_t)left * 8 + 16))) return rc;
-      if (left) DVBT_CUDA_TRY(cudaMemcpyAsync(h->d_samples.p, x + ar.consumed, (size_t)left * 8, cudaMemcpyDeviceToDevice, st));
+      // the caller's buffer (first piece of a stream read in place): history = its last consumed samples, zeros in front
+      const long long have = ar.consumed < kBbHist ? ar.consumed : kBbHist;
+      if ((rc = h->d_samples.reserve((size_t)(kBbHist + left) * 8 + 16))) return rc;
+      if (have < kBbHist) DVBT_CUDA_TRY(cudaMemsetAsync(h->d_samples.p, 0, (size_t)(kBbHist - have) * 8, st));
+      if (have + left) DVBT_CUDA_TRY(cudaMemcpyAsync(h->d_samples.as<float2>() + (kBbHist - have), x + ar.consumed - have, (size_t)(have + left) * 8, cudaMemcpyDeviceToDevice, st));
     }
     h->bb_pend = left;
   }
@@ -957,12 +962,12 @@ int rx_from_file(dvbt_b200_rx *h, const float2 *x_direct, size_t n_direct, float
   // next piece starts on input sample 35 q, where the polyphase pattern restarts
   long long nout = dvbt::resample_out_count(nin);
   if (!end) nout = nout / 32 * 32;
-  if ((rc = reserve_keep(h->d_samples, (size_t)(h->bb_pend + nout) * 8 + 16, (size_t)h->bb_pend * 8, st))) return rc;
+  if ((rc = reserve_keep(h->d_samples, (size_t)(kBbHist + h->bb_pend + nout) * 8 + 16, (size_t)(kBbHist + h->bb_pend) * 8, st))) return rc;
   cudaEvent_t e0, e1;
   DVBT_CUDA_TRY(cudaEventCreate(&e0));
   DVBT_CUDA_TRY(cudaEventCreate(&e1));
   cudaEventRecord(e0, st);
-  rc = dvbt::resample_launch(x, nin, h->d_samples.as<float2>() + h->bb_pend, nout, gain, st, nhist);
+  rc = dvbt::resample_launch(x, nin, h->d_samples.as<float2>() + kBbHist + h->bb_pend, nout, gain, st, nhist);
   cudaEventRecord(e1, st);
   if (!rc && !end) {
     // keep the FIR history + the inputs of the outputs not produced yet
@@ -979,7 +984,7 @@ int rx_from_file(dvbt_b200_rx *h, const float2 *x_direct, size_t n_direct, float
   }
   if (!rc) {
     const size_t nbb = (size_t)(h->bb_pend + nout);
-    rc = rx_from_baseband(h, h->d_samples.as<float2>(), nbb, true, end, ts_host, ts_dev, ts_capacity, ts_bytes, 0);
+    rc = rx_from_baseband(h, h->d_samples.as<float2>() + kBbHist, nbb, true, end, ts_host, ts_dev, ts_capacity, ts_bytes, 0);
   }
   float ms = 0;
   if (elapsed_ms(&ms, e0, e1)) h->info.ms_resample = ms;
@@ -1023,11 +1028,19 @@ int rx_push(dvbt_b200_rx *h, int level, const void *data, size_t count, float ga
   }
   if (level == kLevelBaseband) {
     if (in_place) return rx_from_baseband(h, (const float2 *)data, count, false, end, ts_host, ts_dev, ts_capacity, ts_bytes, 0);
-    if ((rc = reserve_keep(h->d_samples, (size_t)(h->bb_pend + count) * 8 + 16, (size_t)h->bb_pend * 8, st))) return rc;
-    if (count) DVBT_CUDA_TRY(cudaMemcpyAsync(h->d_samples.as<float2>() + h->bb_pend, data, count * 8, host ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, st));
-    return rx_from_baseband(h, h->d_samples.as<float2>(), (size_t)h->bb_pend + count, true, end, ts_host, ts_dev, ts_capacity, ts_bytes, host ? 1 : 0);
+    if (first) {
+      if ((rc = h->d_samples.reserve((size_t)(kBbHist + count) * 8 + 16))) return rc;
+      DVBT_CUDA_TRY(cudaMemsetAsync(h->d_samples.p, 0, (size_t)kBbHist * 8, st));   // nothing in front of the stream's first sample
+    }
+    if ((rc = reserve_keep(h->d_samples, (size_t)(kBbHist + h->bb_pend + count) * 8 + 16, (size_t)(kBbHist + h->bb_pend) * 8, st))) return rc;
+    if (count) DVBT_CUDA_TRY(cudaMemcpyAsync(h->d_samples.as<float2>() + kBbHist + h->bb_pend, data, count * 8, host ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, st));
+    return rx_from_baseband(h, h->d_samples.as<float2>() + kBbHist, (size_t)h->bb_pend + count, true, end, ts_host, ts_dev, ts_capacity, ts_bytes, host ? 1 : 0);
   }
   // capture file
+  if (first) {   // the resampler's output buffer starts with kBbHist zeros: nothing in front of the stream's first baseband sample
+    if ((rc = h->d_samples.reserve((size_t)kBbHist * 8 + 16))) return rc;
+    DVBT_CUDA_TRY(cudaMemsetAsync(h->d_samples.p, 0, (size_t)kBbHist * 8, st));
+  }
   if (in_place) return rx_from_file(h, (const float2 *)data, count, gain, end, ts_host, ts_dev, ts_capacity, ts_bytes);
   if (first) {
     if ((rc = h->d_file.reserve((size_t)(kResHist + count) * 8 + 16))) return rc;
