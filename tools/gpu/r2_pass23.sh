@@ -1,0 +1,7 @@
+#!/bin/bash
+# round 2, GPU pass 23 (1 GPU): demod stage 1 with its loads batched - parity, quick bench x2
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests -m gpu -q -x 2>&1 | tail -2 | tee gpurun_out/r2_p23_pytest.log
+for i in 1 2; do
+  BENCH_VERBOSE=1 BENCH_QUICK=1 timeout 600 python bench.py --steps 20 --warmup 3 2>&1 | grep -E "bench quick|stages:" | cut -c1-200 | tee -a gpurun_out/r2_p23_quick.log
+done
