@@ -1115,6 +1115,65 @@ def viterbi_sweep(g, torch, timed, barrier):
             del d_in
         del dec, d_out
         torch.cuda.empty_cache()
+    # ---- the same microbench on SOFT decisions (BASELINE.json configs[4] says "10^8 soft bits"; the reference decodes hard bits
+    # only - lib/d_metrics.c is a stub - so this is the library's soft mode, include/dvbt_b200.h): 10^8 soft values per rate, one
+    # int8 per transmitted code bit (+-4 = a clean bit, Gaussian noise added on the device, clamped to +-6).  Parity: the clean
+    # stream decodes to its source; every stream equals oracle/port's scalar soft decoder on its first 40 blocks and itself
+    # decoded with another chunking.
+    res["soft_cases"] = []
+    try:
+        for rate in range(5):
+            k, n = O.RATE_KN[rate]
+            nblocks = int(1e8 * k / n / 8 / (96 * k))
+            nbytes_out = nblocks * 96 * k
+            nvals = nblocks * 768 * n
+            data = np.random.default_rng(1).integers(0, 256, nbytes_out, dtype=np.uint8)
+            enc = O.conv_encode(data, 2, rate)                                          # two code bits per byte, MSB first
+            d_enc = torch.from_numpy(enc).cuda()
+            bits = torch.stack([(d_enc >> 1) & 1, d_enc & 1], dim=1).reshape(-1).to(torch.float32)
+            del d_enc
+            dec = g.viterbi_decoder(0, g.NH, rate)
+            dec.set_soft(True)
+            d_out = torch.zeros(nbytes_out, dtype=torch.uint8, device="cuda")
+            for sigma in (0.0, 0.35):                                                   # noise relative to the bit amplitude 1
+                gen = torch.Generator(device="cuda").manual_seed(99 + rate)
+                v = (2.0 * bits - 1.0)
+                if sigma > 0:
+                    v = v + sigma * torch.randn(v.shape, device="cuda", generator=gen)
+                d_in = torch.clamp(torch.round(v * 4.0), -6, 6).to(torch.int8).contiguous()
+                hard_err = float(((v > 0).to(torch.float32) != bits).float().mean())
+                del v
+                ms, kms, rep = [], [], 0
+                for i in range(2 + 5):
+                    torch.cuda.synchronize()
+                    t0 = time.perf_counter()
+                    nout = dec.decode_soft_dev(d_in.data_ptr(), nvals, d_out.data_ptr())
+                    dt = (time.perf_counter() - t0) * 1e3
+                    st = dec.last_stats()
+                    if i >= 2:
+                        ms.append(dt); kms.append(st["acs_kernel_ms"]); rep = st["repaired"]
+                got = d_out[:nout].cpu().numpy()
+                want = O.viterbi_soft(d_in[: 40 * 768 * n].cpu().numpy(), rate)
+                ok = bool(len(want) > 0 and np.array_equal(got[: len(want)], want))
+                if sigma == 0.0:
+                    ok = ok and bool(np.array_equal(got, data[:nout]))
+                dec2 = g.viterbi_decoder(0, g.NH, rate)
+                dec2.set_soft(True)
+                dec2.set_tuning(chunk_bytes=1000 + 24 * 7, warmup_bytes=48, threads_per_block=128)
+                d_out2 = torch.zeros(nbytes_out, dtype=torch.uint8, device="cuda")
+                dec2.decode_soft_dev(d_in.data_ptr(), nvals, d_out2.data_ptr())
+                ok = ok and bool(torch.equal(d_out[:nout], d_out2[:nout]))
+                bits_out = nout * 8
+                res["soft_cases"].append({"rate": "%d/%d" % (k, n), "noise_sigma": sigma, "hard_decision_ber_of_the_input": hard_err,
+                                          "info_mbit": bits_out / 1e6, "mbit_per_s": bits_out / 1e6 / (float(np.mean(ms)) / 1e3) * WORLD,
+                                          "mbit_per_s_acs_kernel": bits_out / 1e6 / (float(np.mean(kms)) / 1e3), "ms_per_decode": float(np.mean(ms)),
+                                          "acs_kernel_ms": float(np.mean(kms)), "repaired_chunks": int(rep),
+                                          "decoded_byte_errors_vs_source": int((got != data[:nout]).sum()), "parity": ok})
+                del d_in, d_out2, dec2
+            del dec, d_out, bits
+            torch.cuda.empty_cache()
+    except Exception as e:   # an extra leg must not cost the run its line
+        res["soft_cases"] = {"error": repr(e)[:300]}
     barrier()
     return res if RANK == 0 else None
 

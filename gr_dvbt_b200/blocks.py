@@ -110,6 +110,12 @@ class viterbi_decoder:
                                                  C.byref(n_out)))
         return int(n_out.value)
 
+    def decode_soft_dev(self, d_in, n_in, d_out):
+        """device buffers: n_in int8 soft values (one per transmitted code bit) -> decoded bytes; returns their count"""
+        n_out = C.c_size_t(0)
+        check(lib().dvbt_b200_viterbi_decode_soft_dev(self._h, _addr(d_in), n_in, _addr(d_out), C.byref(n_out)))
+        return int(n_out.value)
+
     def last_stats(self):
         a, b, ms = C.c_longlong(0), C.c_longlong(0), C.c_float(0)
         check(lib().dvbt_b200_viterbi_last_stats(self._h, C.byref(a), C.byref(b), C.byref(ms)))
