@@ -98,7 +98,7 @@ class ClockSampler:
         if os.environ.get("BENCH_SAMPLER", "1") == "0":   # diagnostic switch: no nvidia-smi process during the timed region
             return
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "50"],
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "200"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -119,7 +119,7 @@ class ClockSampler:
     def stop(self):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.06)
+        time.sleep(0.21)
         self.proc.terminate()
         try:
             self.proc.wait(timeout=2)
@@ -130,7 +130,7 @@ class ClockSampler:
         marks = getattr(self, "marks", [])
         rows = self.rows
         if len(marks) >= 2:
-            inside = [r for r in rows if marks[0] <= r[0] <= marks[-1] + 0.06]
+            inside = [r for r in rows if marks[0] <= r[0] <= marks[-1] + 0.21]      # a sample reports the interval before it
             # a region shorter than the sampling interval: the samples closest to it
             rows = inside if inside else sorted(rows, key=lambda r: abs(r[0] - 0.5 * (marks[0] + marks[-1])))[:2]
         for _t, r in rows:

@@ -209,56 +209,107 @@ __device__ __forceinline__ uint32_t inner_soft(const InnerMap &im, long long tbi
   return (cell >> (4 * e)) & 15u;
 }
 
+// ---- phase B of the soft kernel: two code words of a byte time from its window of <= 16 value bytes ----------------------
+// Selector (PRMT) / keep mask / fill constant of the four steps of one half of a byte time: the half starts in puncturing
+// phase PH, its values are the next bytes of the window; a punctured position becomes the value 0 (byte 8).
+template <int RATE, int PH, int XY>   // XY: 0 = the X bits of the four steps, 1 = the Y bits
+struct InnerSoftHalf {
+  static constexpr unsigned compute(int what) {
+    constexpr int K = rate_k(RATE);
+    constexpr unsigned PX = rate_px(RATE), PY = rate_py(RATE);
+    unsigned sel = 0, keep = 0, fill = 0;
+    int pos = 0, ph = PH;
+    for (int i = 0; i < 4; i++) {
+      const bool hx = (PX >> ph) & 1u, hy = (PY >> ph) & 1u;
+      const int px = pos, py = pos + (hx ? 1 : 0);
+      const bool have = XY ? hy : hx;
+      const int at = XY ? py : px;
+      if (have) { sel |= (unsigned)at << (4 * i); keep |= 0xffu << (8 * i); }
+      else fill |= 0x08u << (8 * i);
+      pos += (hx ? 1 : 0) + (hy ? 1 : 0);
+      ph = (ph + 1 == K) ? 0 : ph + 1;
+    }
+    return what == 0 ? sel : what == 1 ? keep : fill;
+  }
+  static constexpr unsigned sel = compute(0), keep = compute(1), fill = compute(2);
+};
+
+// bits consumed by 4 trellis steps that start in puncturing phase PH0
 template <int RATE, int PH0>
-__device__ __forceinline__ uint2 inner_soft_code(const uint8_t *v) {
+__host__ __device__ constexpr int inner_half_values() {
   constexpr int K = rate_k(RATE);
   constexpr unsigned PX = rate_px(RATE), PY = rate_py(RATE);
-  uint32_t w[2] = {0u, 0u};
-  int pos = 0, ph = PH0;
-#pragma unroll
-  for (int i = 0; i < 8; i++) {
-    uint32_t vx = 8u, vy = 8u;
-    if ((PX >> ph) & 1u) vx = v[pos++];
-    if ((PY >> ph) & 1u) vy = v[pos++];
-    w[i >> 2] |= (vx | (vy << 4)) << (8 * (i & 3));
+  int n = 0, ph = PH0;
+  for (int i = 0; i < 4; i++) {
+    n += (int)((PX >> ph) & 1u) + (int)((PY >> ph) & 1u);
     ph = (ph + 1 == K) ? 0 : ph + 1;
   }
-  return make_uint2(w[0], w[1]);
+  return n;
+}
+
+// A[0..3] = the 16 window bytes (byte k of the window = byte k & 3 of A[k >> 2]); 4 steps -> one code word
+template <int RATE, int PH, int OFF>
+__device__ __forceinline__ uint32_t inner_soft_half(const uint32_t (&A)[4]) {
+  constexpr int q = OFF >> 2, r = OFF & 3;
+  // window bytes [OFF, OFF + 8) as two registers (OFF <= 8, so q + 2 <= 4; the register behind A[3] is never selected)
+  const uint32_t a0 = A[q], a1 = q + 1 < 4 ? A[q + 1] : 0u, a2 = q + 2 < 4 ? A[q + 2] : 0u;
+  const uint32_t b0 = r ? __byte_perm(a0, a1, 0x3210u + 0x1111u * r) : a0;
+  const uint32_t b1 = r ? __byte_perm(a1, a2, 0x3210u + 0x1111u * r) : a1;
+  using HX = InnerSoftHalf<RATE, PH, 0>;
+  using HY = InnerSoftHalf<RATE, PH, 1>;
+  const uint32_t xw = (__byte_perm(b0, b1, HX::sel) & HX::keep) | HX::fill;
+  const uint32_t yw = (__byte_perm(b0, b1, HY::sel) & HY::keep) | HY::fill;
+  return xw | (yw << 4);
+}
+
+template <int RATE, int PH0>
+__device__ __forceinline__ uint2 inner_soft_code(const uint32_t (&A)[4]) {
+  constexpr int K = rate_k(RATE);
+  constexpr int H1 = inner_half_values<RATE, PH0>();
+  return make_uint2(inner_soft_half<RATE, PH0, 0>(A), inner_soft_half<RATE, (PH0 + 4) % K, H1>(A));
 }
 
 // Same tiling and phases as rx_inner_codes_kernel, without the bit packing: the value bytes are read where they lie.
+// Shared-memory layout of the value bytes: one pad word behind every 16 (byte i lives at i + 4 (i >> 6)).  The byte times of
+// one puncturing class are 8 N = 16 .. 64 bytes apart, so without the pad a warp's window loads hit two to eight banks
+// (measured: the whole kernel was those bank conflicts, 0.55 ms against 0.16 ms for the hard-decision kernel); a window is
+// fetched as five aligned words and aligned with funnel shifts, the steps' values are picked with PRMT.
+__device__ __forceinline__ int inner_soft_phys(int i) { return i + ((i >> 6) << 2); }
+
 template <int RATE, int M>
 __global__ void __launch_bounds__(256) rx_inner_soft_kernel(InnerMap im, uint2 *__restrict__ codes, int nbt) {
-  extern __shared__ __align__(16) uint8_t s_val[];  // [tile cells * M + kInnerTail] values + 8, then the step codes of the tile
+  extern __shared__ __align__(16) uint8_t s_val[];  // [tile cells * M + kInnerTail] values + 8 (padded), then the step codes of the tile
   constexpr int HALF = M / 2;
   const int G = kInnerTileCells / im.P;
   const int sym0 = blockIdx.x * G;
   const int nsym = min(G, im.n_out - sym0);
   const int ncell = nsym * im.P, nbits = ncell * M;
   const long long lo = (long long)sym0 * im.P * M, hi = lo + nbits;
-  uint2 *s_codes = reinterpret_cast<uint2 *>(s_val + ((kInnerTileCells * M + kInnerTail + 15) & ~15));
+  constexpr int kValBytes = (kInnerTileCells * M + kInnerTail + 63) / 64 * 68 + 64;   // padded size, + the words a window may read past the tail
+  uint2 *s_codes = reinterpret_cast<uint2 *>(s_val + ((kValBytes + 15) & ~15));
   const uint32_t *dm32 = reinterpret_cast<const uint32_t *>(im.dm);
   for (int ls = 0; ls < nsym; ls++) {
     const int sym = sym0 + ls;
     const short *perm = (im.out_symidx[sym] & 1) ? im.Hinv : im.H;
     const uint32_t *row = dm32 + (long long)im.out_src[sym] * im.P;
-    uint8_t *base = s_val + ls * im.P * M;
+    const int base = ls * im.P * M;
     for (int x = threadIdx.x; x < im.P; x += blockDim.x) {
       uint32_t cell = row[perm[x]];
       int blk126 = (x / 126) * 126, w = x - blk126;
-      uint8_t *dst = base + blk126 * M;
+      const int dst = base + blk126 * M;
 #pragma unroll
       for (int e = 0; e < M; e++) {
         constexpr int kOff[6] = {0, 63, 105, 42, 21, 84};
         int ii = w + kOff[e];
         if (ii >= 126) ii -= 126;
         const int kbit = (e & 1) * HALF + (e >> 1);
-        dst[ii * M + kbit] = (uint8_t)((cell >> (4 * e)) & 15u);
+        s_val[inner_soft_phys(dst + ii * M + kbit)] = (uint8_t)((cell >> (4 * e)) & 15u);
       }
     }
   }
   const long long total_bits = (long long)im.n_out * im.P * M;
-  for (int b = threadIdx.x; b < kInnerTail; b += blockDim.x) s_val[nbits + b] = (hi + b < total_bits) ? (uint8_t)inner_soft(im, hi + b) : 8;
+  for (int b = threadIdx.x; b < kInnerTail + 32; b += blockDim.x)
+    s_val[inner_soft_phys(nbits + b)] = (b < kInnerTail && hi + b < total_bits) ? (uint8_t)inner_soft(im, hi + b) : 8;
   __syncthreads();
   constexpr int K = rate_k(RATE), N = K + 1;
   const long long shift = im.shift_bits;
@@ -269,14 +320,20 @@ __global__ void __launch_bounds__(256) rx_inner_soft_kernel(InnerMap im, uint2 *
   while (inner_bits_before<RATE>(8 * jhi) + shift < hi) jhi++;
   if (jhi > nbt) jhi = nbt;
   const int nj = jhi > jlo ? (int)(jhi - jlo) : 0;
+  const uint32_t *s_w = reinterpret_cast<const uint32_t *>(s_val);
   for (int c = 0; c < K; c++) {
     const long long t0 = 8 * (jlo + c);
     const int ph = (int)(t0 % K);
     const int local0 = (int)(inner_bits_before<RATE>(t0) + shift - lo);
     const int cnt = (nj - c + K - 1) / K;
 #define INNER_CLASS(PH)                                                              \
-    for (int i = threadIdx.x; i < cnt; i += blockDim.x)                              \
-      s_codes[c + K * i] = inner_soft_code<RATE, (PH) % K>(s_val + local0 + 8 * N * i);
+    for (int i = threadIdx.x; i < cnt; i += blockDim.x) {                            \
+      const int local = local0 + 8 * N * i, w0 = local >> 2, sh = 8 * (local & 3);   \
+      uint32_t W[5], A[4];                                                           \
+      _Pragma("unroll") for (int k = 0; k < 5; k++) W[k] = s_w[(w0 + k) + ((w0 + k) >> 4)]; \
+      _Pragma("unroll") for (int k = 0; k < 4; k++) A[k] = __funnelshift_r(W[k], W[k + 1], sh); \
+      s_codes[c + K * i] = inner_soft_code<RATE, (PH) % K>(A);                       \
+    }
     switch (ph) {
       case 0: INNER_CLASS(0) break;
       case 1: INNER_CLASS(1) break;
@@ -566,7 +623,7 @@ int launch_inner(dvbt_b200_rx *h, const InnerMap &im, int rows, uint32_t *codes,
   cudaStream_t st = h->stream;
   if (h->soft) {
     // value bytes + the tile's step codes (at most one byte time per 8 N / K >= 64 / 7 stream bits), 8 bytes each
-    smem = (size_t)((kInnerTileCells * h->m + kInnerTail + 15) & ~15) + ((size_t)(kInnerTileCells * h->m) * 7 / 64 + 8) * 8;
+    smem = (size_t)((((kInnerTileCells * h->m + kInnerTail + 63) / 64 * 68 + 64) + 15) & ~15) + ((size_t)(kInnerTileCells * h->m) * 7 / 64 + 8) * 8;
     uint2 *codes2 = reinterpret_cast<uint2 *>(codes);
 #define RX_SOFT_LAUNCH(R, M) do { \
       DVBT_CUDA_TRY(cudaFuncSetAttribute(rx_inner_soft_kernel<R, M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
