@@ -389,7 +389,15 @@ struct DescrState {
 // At the end of a stream (`end`) the locked state keeps going while whole pairs are left (the scheduler would not call the
 // block without 4 items visible, :102-106, so the reference stops earlier: its file is a prefix of this), and one last
 // complete group is delivered on its own.
-__global__ void __launch_bounds__(1024) rx_descr_plan_kernel(const uint8_t *__restrict__ rs, long long npk, DescrState *st,
+// sb[p] = first byte of pending packet p (rx_descr_syncbytes_kernel): the plan only ever looks at those, and while the
+// block is out of lock one thread replays the reference's search call by call - on a compact array its loads are cache hits
+// instead of one 188-byte stride each (a capture that lost lock nine times spent 6.6 ms here before, profiles/README.md).
+__global__ void rx_descr_syncbytes_kernel(const uint8_t *__restrict__ rs, long long npk, uint8_t *__restrict__ sb) {
+  long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p < npk) sb[p] = rs[p * 188];
+}
+
+__global__ void __launch_bounds__(1024) rx_descr_plan_kernel(const uint8_t *__restrict__ sb, long long npk, DescrState *st,
                                                              int *__restrict__ plan, long long plan_capacity, int end) {
   __shared__ int s_fail;
   const int t = threadIdx.x;
@@ -412,7 +420,7 @@ __global__ void __launch_bounds__(1024) rx_descr_plan_kernel(const uint8_t *__re
     if (pk < 16) {
       for (int r = 0; r < 4; r++) {
         long long cc = c + t + 1024LL * r;
-        if (cc < calls_total && rs[(16 * cc + pk) * 188] != 0xB8) atomicMin(&s_fail, t + 1024 * r);
+        if (cc < calls_total && sb[16 * cc + pk] != 0xB8) atomicMin(&s_fail, t + 1024 * r);
       }
     }
     __syncthreads();
@@ -430,21 +438,26 @@ __global__ void __launch_bounds__(1024) rx_descr_plan_kernel(const uint8_t *__re
     __syncthreads();
     if (c >= calls_total || np >= plan_capacity) break;
     if (pk < 16 && good == 4096) continue;   // a full round without a failed test: next round
-    if (pk < 16 && good > 0 && rs[(16 * c + pk) * 188] == 0xB8) continue;   // the round ended at a limit, not at a failed test
+    if (pk < 16 && good > 0 && sb[16 * c + pk] == 0xB8) continue;   // the round ended at a limit, not at a failed test
     if (c >= calls_strict) break;            // a failed test beyond the strict range: the search would run past the data
-    // ---- one call of the reference loop (:121-134), every thread the same scalar code
-    while (pk < 16 && rs[(16 * c + pk) * 188] != 0xB8) pk++;
-    if (pk >= 16) {
-      pk = 0;               // d_index = 0, consume 2, no output
-    } else {
-      if (t == 0) plan[np] = (int)(16 * c + pk);
-      if (first_packet < 0) first_packet = seen + 16 * c + pk;
-      np++;
+    // ---- calls of the reference loop (:121-134), every thread the same scalar code: call after call while the block is out
+    // of lock (no barrier in here), back to the parallel test above as soon as a call has found its inverted sync byte
+    while (c < calls_strict && np < plan_capacity) {
+      while (pk < 16 && sb[16 * c + pk] != 0xB8) pk++;
+      bool found = pk < 16;
+      if (!found) {
+        pk = 0;             // d_index = 0, consume 2, no output
+      } else {
+        if (t == 0) plan[np] = (int)(16 * c + pk);
+        if (first_packet < 0) first_packet = seen + 16 * c + pk;
+        np++;
+      }
+      c++;
+      if (found) break;
     }
-    c++;
   }
   i = 2 * c;
-  if (end && pk < 16 && np < plan_capacity && 16 * c + pk + 8 <= npk && rs[(16 * c + pk) * 188] == 0xB8) {
+  if (end && pk < 16 && np < plan_capacity && 16 * c + pk + 8 <= npk && sb[16 * c + pk] == 0xB8) {
     if (t == 0) plan[np] = (int)(16 * c + pk);    // the last complete group, on its own
     if (first_packet < 0) first_packet = seen + 16 * c + pk;
     tail = 1;
@@ -514,7 +527,7 @@ struct dvbt_b200_rx {
   bool soft = false;                 // soft-decision mode (dvbt_b200_rx_set_soft_decision): d_dm holds one word per cell
   int esz() const { return soft ? 4 : 1; }
   int k = 1, n = 2, m = 4, ntb = 5, vit_in_block = 0, vit_out_block = 0;
-  dvbt::DevBuf d_state, d_fo, d_rot, d_mod, d_tps, d_vote, d_Y, d_rsst, d_ts, d_prbs, h_state, h_info, d_sync, h_sync, d_plan, d_dstate;
+  dvbt::DevBuf d_state, d_fo, d_rot, d_mod, d_tps, d_vote, d_Y, d_rsst, d_ts, d_prbs, h_state, h_info, d_sync, h_sync, d_plan, d_dstate, d_syncb;
   dvbt_b200_rx_info info;
   cudaEvent_t ev[10];
   cudaStream_t side = nullptr;       // the demod scan runs here, beside the equalise kernel (demod.cuh: DemodBuffers::side)
@@ -824,7 +837,10 @@ int rx_back_end(dvbt_b200_rx *h, int nrows, bool end, uint8_t *ts_host, uint8_t 
     return DVBT_B200_ENOSPC;
   }
   if ((rc = h->d_plan.reserve((size_t)max_pairs * 4))) return rc;
-  rx_descr_plan_kernel<<<1, 1024, 0, st>>>(h->d_rs.as<uint8_t>(), h->rs_pend, h->d_dstate.as<DescrState>(), h->d_plan.as<int>(), max_pairs, end ? 1 : 0);
+  if ((rc = h->d_syncb.reserve((size_t)h->rs_pend + 16))) return rc;
+  if (h->rs_pend > 0) rx_descr_syncbytes_kernel<<<(unsigned)((h->rs_pend + 255) / 256), 256, 0, st>>>(h->d_rs.as<uint8_t>(), h->rs_pend, h->d_syncb.as<uint8_t>());
+  rx_descr_plan_kernel<<<1, 1024, 0, st>>>(h->d_syncb.as<uint8_t>(), h->rs_pend, h->d_dstate.as<DescrState>(), h->d_plan.as<int>(), max_pairs, end ? 1 : 0);
+  dvbt::count_launch(h->rs_pend > 0 ? 1 : 0);
   {
     long long blocks = max_pairs * 752 / 256 / 4 + 1;   // ~4 words per thread
     unsigned grid = (unsigned)(blocks < 8LL * h->sm_count ? blocks : 8LL * h->sm_count);
@@ -1192,7 +1208,7 @@ void dvbt_b200_rx_destroy(dvbt_b200_rx *h) {
   dvbt::DevBuf *bufs[] = {&h->d_state, &h->d_fo, &h->d_rot, &h->d_mod, &h->d_tps, &h->d_vote, &h->d_Y, &h->d_rsst, &h->d_ts, &h->d_prbs, &h->h_state,
                           &h->h_info, &h->d_sync, &h->h_sync, &h->d_plan, &h->d_dstate, &h->d_file, &h->d_file2, &h->d_samples, &h->d_samples2, &h->d_sym,
                           &h->d_sym2, &h->d_dm[0], &h->d_dm[1], &h->d_osym[0], &h->d_osym[1], &h->d_osrc[0], &h->d_osrc[1], &h->d_D, &h->d_D2,
-                          &h->d_rs, &h->d_rs2, &h->d_vit_tap};
+                          &h->d_rs, &h->d_rs2, &h->d_vit_tap, &h->d_syncb};
   for (auto *b : bufs) b->release();
   for (auto &e : h->ev) if (e) cudaEventDestroy(e);
   h->tables.release();

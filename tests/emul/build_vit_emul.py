@@ -166,7 +166,9 @@ extern "C" int emul_descramble_stream(const uint8_t *rs, long long npk, const ui
   st.pk = *pk_io;
   st.first_packet1 = 0;
   std::vector<int> plan((size_t)(npk / 16 + 2));
-  emul_launch(rx_descr_plan_kernel, 1u, 1024u, rs, npk, &st, plan.data(), (long long)plan.size(), end);
+  std::vector<uint8_t> sb((size_t)npk + 16);
+  if (npk > 0) emul_launch(rx_descr_syncbytes_kernel, (unsigned)((npk + 255) / 256), 256u, rs, npk, sb.data());
+  emul_launch(rx_descr_plan_kernel, 1u, 1024u, (const uint8_t *)sb.data(), npk, &st, plan.data(), (long long)plan.size(), end);
   emul_launch(rx_descramble_kernel, (unsigned)grid, 256u, rs, (const DescrState *)&st, (const int *)plan.data(), prbs, ts, ts_capacity);
   *pk_io = st.pk;
   *first_packet = st.first_packet1 - 1;
