@@ -888,7 +888,10 @@ def main():
         r["ms_single"] = ms1 / steps
         if sampler:
             sampler.start()                      # before the warm-up: see ClockSampler
-        w.resident_pair(warm)
+        # warm-up of the in-flight leg: the driver's W steps, and at least 12 - it is the first phase of the run in which every
+        # rank drives four host threads at once, and at N = 8 the first ~10 steps after the single-threaded capture synthesis ran
+        # 4 % slower than the same leg repeated later (host cores ramping up; profiles/r02_n8_in_flight_and_wait_mode.txt)
+        w.resident_pair(max(warm, 12))
         barrier()
         l1 = lib.dvbt_b200_kernel_launches()
         if sampler:
