@@ -107,3 +107,47 @@ def test_other_acs_schedules_through_the_whole_library(emulated_library, monkeyp
 def test_config3_8k_qam16_rate12(emulated_library):
     import test_zz_apps_test_ts_gpu as T
     T.test_cuda_chain_config3_8k_qam16_rate12_stage_by_stage()
+
+
+# ---- round 2: the stream interface, re-synchronisation, the transmit chain and the soft-decision mode ------------------------
+@needs_ref
+def test_stream_in_pieces_from_post_fft_symbols(emulated_library):
+    """a capture in uneven pieces (some of one symbol) == the one-shot run: every block's call-to-call state is carried"""
+    import test_stream_resync_gpu as T
+    T.test_pieces_give_the_one_shot_transport_stream(*T.STREAM_CASES[2])
+
+
+def test_stream_edge_cases(emulated_library):
+    import test_stream_edge_cases_gpu as T
+    from dvbt_testlib import tx_frequency_domain, ofdm_modulate
+    con, cr, tm = R.QAM16, R.C1_2, R.T2k
+    tx = tx_frequency_domain(con, cr, tm, 420, 17)
+    cap = (con, cr, tm, tx, ofdm_modulate(tx["X"], tm, offset=333, cfo_bins=0.0, seed=2))
+    T.test_empty_and_one_sample_pieces_change_nothing(cap)
+    T.test_level_change_in_mid_stream_is_refused(cap)
+
+
+@needs_ref
+def test_transmit_chain_against_the_reference_tx_blocks(emulated_library):
+    import test_tx_chain_gpu as T
+    T.test_tx_stages_match_reference_blocks(*T.MODES[0])
+
+
+def test_soft_decision_viterbi(emulated_library):
+    """+-1 values == the hard decoder; arbitrary values == oracle/port's scalar restatement; the repair path on soft codes"""
+    import test_soft_decision_gpu as T
+    T.test_plus_minus_one_is_the_hard_decoder(4)
+    T.test_soft_values_match_the_scalar_restatement(4, 0.38)
+    T.test_soft_values_match_the_scalar_restatement(0, 0.7)
+    T.test_soft_repair_path_is_exact()
+    T.test_extreme_values_do_not_overflow_the_metrics()
+
+
+def test_soft_decision_chain(emulated_library):
+    """noise-free: the hard chain's TS; signs == the reference demapper; values == the documented rule; the chain's Viterbi
+    output == the scalar soft decoder on the tapped values; pieces == one shot (rates 1/2, 3/4, 5/6, 7/8 between them)"""
+    import test_soft_chain_gpu as T
+    T.test_noise_free_soft_chain_gives_the_hard_chain_ts(R.QAM64, R.C7_8, R.T2k)
+    T.test_soft_values_follow_the_documented_rule_and_the_decoder_is_exact(R.QAM16, R.C1_2)
+    T.test_soft_values_follow_the_documented_rule_and_the_decoder_is_exact(R.QAM64, R.C3_4)
+    T.test_soft_stream_in_pieces_equals_one_shot()
