@@ -16,13 +16,16 @@
 // __f*_rn / __d*_rn, no FMA contraction; complex division as libgcc's __divsc3 does it for
 // float operands: straight formula in double), but the work is split:
 //   demod_stage1_kernel : one warp per symbol   - CFO sums (16 lanes), one-shot sums (2 lanes), rotor,
-//                                                scattered-pilot phase (4 lanes)
+//                                                scattered-pilot phase (4 lanes); in the fused chain also the symbol's
+//                                                17 / 68 TPS carriers, equalised exactly as the symbol kernel would
 //   demod_symbol_kernel : one block per symbol  - the symbol staged once by a bulk async copy (TMA engine); pilot
-//                                                gains and slopes; TPS carriers, payload cells (+ demap), four cells
-//                                                per thread.  <true>: stage 1 fused in as well (opt-in, slower)
+//                                                gains and slopes; (TPS carriers,) payload cells (+ demap), four cells
+//                                                per thread.  <true>: stage 1 fused in as well (opt-in, slower);
+//                                                <.., SOFT>: soft decisions instead of the hard demap (demod.cuh)
 //   demod_vote_kernel   : one thread per symbol - TPS majority vote against the previous symbol
 //   demod_scan_kernel   : one block             - the genuinely sequential part (symbol/frame
-//                                                index, TPS FIFO, BCH, superframe gating)
+//                                                index, TPS FIFO, BCH, superframe gating, sync_start re-arming)
+// In the fused chain vote + scan run on a high-priority side stream BESIDE the symbol kernel (demod_run).
 // HBM traffic per symbol: 8 (K + 17) B read once (+ 128 B around each continual pilot of the next symbol, L2 hits) and
 // P (demapped) written, + 8P when the caller wants the equalised cells.
 #include "demod.cuh"

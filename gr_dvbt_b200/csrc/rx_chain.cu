@@ -1,20 +1,28 @@
-// Device-resident receive chain: post-FFT OFDM symbols -> transport stream, one H2D and one
-// D2H per batch.  Stages and the reference blocks they stand for:
+// Device-resident receive chain: 10 Msps capture / baseband / post-FFT OFDM symbols -> transport stream, one H2D and one
+// D2H per call, as a STREAM: every block's call-to-call state is carried (dvbt_b200_rx_stream_push_*),
+// the one-shot entry points are "reset, one piece, end of stream".  Stages and the reference blocks they stand for:
 //
-//   demod_run (demod.cu)        demod_reference_signals + dvbt_demap (fused epilogue)
+//   resample_launch (resample.cu)  rational_resampler_ccc(64, 70) + multiply_const (stock GNU Radio, parity unpinned)
+//   acq_run (acq.cu)               ofdm_sym_acquisition + fft_vxx(shift = True); a lost peak restarts acquisition and
+//                                  sends sync_start, as the reference does
+//   demod_run (demod.cu)        demod_reference_signals + dvbt_demap (fused epilogue; soft decisions as a separate mode)
 //   rx_inner_codes_kernel       symbol_inner_interleaver (deinterleave,
 //                               symbol_inner_interleaver_impl.cc:161-219), bit_inner_deinterleaver
 //                               (bit_inner_deinterleaver_impl.cc:120-184), vector_to_stream and the
 //                               Viterbi block's unpack/depuncture (viterbi_decoder_impl.cc:241-256),
 //                               all as ONE index map from demapped cells to Viterbi step codes
-//   vit_* kernels (viterbi.cu)  viterbi_decoder
-//   rs_decode_kernel<GATHER>    convolutional_deinterleaver (index map while loading) +
-//                               reed_solomon_dec
-//   rx_descramble_kernel        energy_descramble (energy_descramble_impl.cc:108-174): NSYNC search
-//                               over 2 groups, PRBS 1 + x^14 + x^15 restarted every 8 packets
+//                               (rx_inner_soft_kernel: the same map on 4-bit soft values)
+//   vit_* kernels (viterbi.cu)  viterbi_decoder, one chunk-parallel run per stretch between superframe_start tags
+//   rs_decode_kernel<GATHER>    convolutional_deinterleaver (index map while loading, 2244 bytes of stream history =
+//                               the delay lines that are never cleared) + reed_solomon_dec
+//   rx_descr_syncbytes_kernel / rx_descr_plan_kernel / rx_descramble_kernel
+//                               energy_descramble (energy_descramble_impl.cc:108-174): the block's per-call NSYNC
+//                               state machine replayed over all pending packets, then PRBS 1 + x^14 + x^15 over the
+//                               planned pairs of groups
 //
-// Tags become batch metadata: symbol_index per output symbol, superframe_start = first output
-// symbol (the Viterbi reset and the outer deinterleaver alignment).
+// Tags are metadata of the stream: sync_start (acquisition -> demod re-arm), symbol_index per output symbol,
+// superframe_start (demod -> Viterbi reset -> outer deinterleaver re-alignment), at the positions and with the
+// consequences they have in the reference chain driven with the scheduler's smallest calls.
 #include "chain_internal.cuh"
 
 #include <string.h>

@@ -1,4 +1,5 @@
-// K1 — chunk-parallel K=7 punctured hard-decision Viterbi decoder for sm_100a.
+// K1 — chunk-parallel K=7 punctured Viterbi decoder for sm_100a (hard decisions as the reference; soft decisions as a
+// separate mode beyond it).
 //
 // Replaces gr::dvbt::viterbi_decoder (lib/viterbi_decoder_impl.cc:191-324) and its SSE2
 // kernels (lib/d_viterbi.c:461-576 d_viterbi_butterfly2_sse2, :680-735
@@ -8,21 +9,24 @@
 //    m bits, MSB first) into one 32-bit "step code" word per byte time (8 trellis steps,
 //    4 bits per step: sym0, valid0, sym1, valid1), following the depuncture loop of
 //    viterbi_decoder_impl.cc:241-256 and the puncture tables :61-65.
-//  * vit_acs_kernel: ONE THREAD PER CHUNK of the stream.  The 64 path metrics and the 64
-//    eight-bit path registers of the reference live in 32 registers (4 states per register,
-//    unsigned-byte SWAR; schedule generated by gen_viterbi_acs.py).  Every 8 steps (after
-//    the 6th step of a byte time, the reference's cadence :263-272) the path bytes go to a
-//    per-thread ring of ntraceback rows in shared memory ([slot][word][thread], conflict
-//    free), the best state is found with the reference's tie rule (first strict maximum,
-//    d_viterbi.c:699-711) and the ring is traced back ntraceback-1 hops (:714-721).  The
-//    trace stops early when it meets the previous byte's trace (identical result, fewer
-//    hops).  Metrics are renormalised by a lower bound of the minimum (decisions depend on
-//    differences only; spread <= 12, so bytes stay < 128).
+//  * vit_acs_kernel: ONE THREAD PER CHUNK of the stream, all 64 states in registers.  Default schedule (H16 = 1,
+//    viterbi_acs_h16_gen.cuh, generated and simulated by gen_viterbi_acs_h16.py): a state is one halfword
+//    metric << 8 | path byte, two states per register, and one VIADDMNMX.U16x2 per two states and step selects the
+//    survivor's metric and path at once (the reference's tie rule falls out of the packing).  H16 = 2 (h16b): the same
+//    steps with a cheaper event; the byte-SWAR and two-lane schedules of round 1 are a legacy build option
+//    (DVBT_B200_LEGACY_ACS).  Every 8 steps (after the 6th step of a byte time, the reference's cadence :263-272) the path
+//    bytes go to a per-thread survivor ring - the newest D rows in shared memory ([slot][word][thread], conflict free),
+//    for ntraceback > 13 all rows also written through to a global ring - the best state is found with the reference's
+//    tie rule (first strict maximum, d_viterbi.c:699-711) and the ring is traced back ntraceback-1 hops (:714-721).  The
+//    trace stops early when it meets the previous byte's trace (identical result, fewer hops).  Metrics are
+//    renormalised by a lower bound of the minimum (decisions depend on differences only; spread <= 12).
 //  * Chunks start `warm` byte times early from the all-zero state.  Exactness does not rest
 //    on that heuristic: every chunk records its metrics at its first byte time (G) and at
 //    the next chunk's first byte time (F); vit_verify_kernel compares G[c] with F[c-1]
-//    (min-normalised); vit_repair_kernel re-decodes, sequentially from the true state, any
-//    chunk whose warm-up had not converged (and cascades while states differ).
+//    (min-normalised); two parallel rounds of vit_repair_round_kernel re-decode, from the true state, every flagged chunk
+//    whose predecessor is settled, and vit_repair_kernel walks what is left sequentially (cascading while states differ).
+//  * SOFT = true (dvbt_b200_viterbi_set_soft; the reference has no soft path, include/dvbt_b200.h): the same schedule with
+//    8 bits per step in the step codes (two values in [-6, 6]) and a 4 x 256-entry addend table; spread bound 72.
 #include "common.cuh"
 // FMAADD (a template parameter of the functions that expand the generated macros) selects which additions
 // of the schedule are forced onto the FMA pipe as IMAD with a run-time multiplier (vit_one / vit_neg1 /
