@@ -51,3 +51,49 @@ def test_committed_bench_line_keeps_the_contract(path):
     vs = d["viterbi_sweep"]
     assert len(vs["cases"]) == 45 and all(x["parity"] for x in vs["cases"])
     assert len(vs["soft_cases"]) == 10 and all(x["parity"] for x in vs["soft_cases"])
+
+
+def test_viterbi_workload_line_is_assembled(monkeypatch, capsys):
+    """`bench.py --workload viterbi`: the line's assembly code runs end to end on stand-ins (no GPU here) and keeps the contract"""
+    import io
+    import sys
+    sys.path.insert(0, ROOT)
+    import numpy as np
+    import bench
+
+    class FakeWorkload:
+        nbytes_in, nbytes_out, alg_bytes, info_bits = 1000, 896, 1872, (896 - 24) * 8
+        h2d, d2h = 1000, 872
+
+        def __init__(self, mbit): self.kernel_ms = []
+        def setup_gpu(self, seed): pass
+        def step_resident(self, i): self.kernel_ms.append(0.5); return 872
+        def step_e2e(self, i): return 872
+        def check(self): return True
+        def units_per_step(self): return self.info_bits / 1e6
+        def describe(self): return {"workload": "viterbi_decoder stage of configs[1] (stand-in)"}
+        def cpu_sample(self, hint): return 1.0, 0.1, "port"
+
+    class FakeLib:
+        n = 0
+        def dvbt_b200_kernel_launches(self): FakeLib.n += 7; return FakeLib.n
+
+    def timed(stepfn, steps, warm, w):
+        for i in range(warm + steps):
+            stepfn(i)
+        w.last_i = warm + steps - 1
+        return 2.0 * steps
+
+    monkeypatch.setattr(bench, "ViterbiWorkload", FakeWorkload)
+    monkeypatch.setattr(bench, "all_ranks_ok", lambda flag, device: bool(flag))
+    args = type("A", (), dict(mbit=1.0, steps=4, warmup=3))()
+    out = io.StringIO()
+    rc = bench.main_viterbi(args, out, "metric", "Mbit/s (Viterbi decoded bits)", None, FakeLib(), timed, lambda: None, 6556.2, "measured", None, {})
+    assert rc == 0
+    d = json.loads(out.getvalue())
+    for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline", "dtype", "data",
+              "config", "e2e", "gpu_launches", "clocks", "roofline", "cpu_baseline", "parity_check"):
+        assert k in d, k
+    assert d["ms_per_step"] == 2.0 and abs(d["value"] - FakeWorkload.info_bits / 1e6 / 2e-3) < 1e-9
+    assert d["roofline"]["bound"] == "alu" and abs(d["roofline"]["frac"] - d["roofline"]["achieved"] / d["roofline"]["peak"]) < 1e-12
+    assert d["e2e"]["h2d_bytes_per_step"] == 1000 and d["cpu_baseline"]["kind"] == "port"
