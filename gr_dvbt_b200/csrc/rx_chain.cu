@@ -413,6 +413,9 @@ __global__ void __launch_bounds__(1024) rx_descr_plan_kernel(const uint8_t *__re
   int pk = st->pk, np = 0;
   long long first_packet = st->first_packet1 - 1;
   const long long seen = st->packets_seen;
+  __syncthreads();          // every thread has read the state before thread 0 may rewrite it (a short input leaves the loop below
+                            // without meeting a barrier; the values would be the same ones, but a race is a race - found by the
+                            // ThreadSanitizer build of tests/emul)
   const long long calls_strict = npk >= 32 ? (npk - 32) / 16 + 1 : 0;   // a call at item i needs items i .. i+3 visible
   long long calls_total = calls_strict;
   long long c = 0;          // calls made so far (i == 2 c)
